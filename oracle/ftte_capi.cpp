@@ -1,0 +1,68 @@
+// TEST INFRASTRUCTURE ONLY (see ftte_common.h).  extern "C" entry points of the CPU oracle, loaded with ctypes
+// by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.  Never by the product.
+#include "ftte_common.h"
+
+using namespace ftte;
+
+extern "C" {
+
+void* ftte_grid_create(int nx, int64_t nleaf, const int8_t* level, const double* HI, const double* HeI,
+                       const double* HeII, const double* rho, const double* abun2, double boxSize, int* status) {
+  Grid* g = new Grid();
+  LeafInput in{level, HI, HeI, HeII, rho, abun2, nleaf};
+  int st = buildGrid(*g, nx, boxSize, in);
+  if (status) *status = st;
+  if (st) { delete g; return nullptr; }
+  return g;
+}
+
+void ftte_grid_destroy(void* h) { delete (Grid*)h; }
+
+int64_t ftte_grid_nnodes(void* h) { return (int64_t)((Grid*)h)->node.size(); }
+
+// update the absorber densities in place (outer transport<->chemistry iteration, equiSources.f90:3671-3673)
+int ftte_grid_set_species(void* h, const double* HI, const double* HeI, const double* HeII) {
+  Grid& g = *(Grid*)h;
+  for (size_t l = 0; l < g.leafNode.size(); l++) {
+    Zone& z = g.node[g.leafNode[l]];
+    if (HI) z.HI = HI[l];
+    if (HeI) z.HeI = HeI[l];
+    if (HeII) z.HeII = HeII[l];
+  }
+  return OK;
+}
+
+// Diffuse solve over directions [rayBegin, rayEnd) (pass 0,-1 for all).  beta = [group][beta24, beta26, beta25].
+// J1..J3: caller-allocated [nleaf], overwritten.  Optional trace of direction traceRay (-1 = none):
+//   nbLeaf [3][nleaf] (xy, yz, xz upstream leaf; -1 boundary; -2 inactive), pattern [nx][12], izone, angles[2].
+int ftte_diffuse(void* h, int nAngularLevel, const double* uvb, const double* beta, int64_t rayBegin,
+                 int64_t rayEnd, double* J1, double* J2, double* J3, int64_t* nseg, int64_t traceRay,
+                 int32_t* nbLeaf, double* patternOut, int32_t* izoneOut, double* anglesOut) {
+  Grid& g = *(Grid*)h;
+  DiffuseTrace tr{nbLeaf, patternOut, izoneOut, anglesOut};
+  int st = diffuseSolve(g, nAngularLevel, uvb, beta, rayBegin, rayEnd, traceRay, traceRay >= 0 ? &tr : nullptr, nseg);
+  for (size_t l = 0; l < g.leafNode.size(); l++) {
+    const Zone& z = g.node[g.leafNode[l]];
+    if (J1) J1[l] = z.Jmean[0];
+    if (J2) J2[l] = z.Jmean[1];
+    if (J3) J3[l] = z.Jmean[2];
+  }
+  return st;
+}
+
+int ftte_direction(int nAngularLevel, int64_t iray, int32_t* izone, double* phi, double* theta) {
+  int iz = 0;
+  int st = directionSetup(nAngularLevel, iray, iz, *phi, *theta);
+  *izone = iz;
+  return st;
+}
+
+int ftte_pix2ang_nest(int nside, int64_t ipix, double* phi, double* theta) { return pix2ang_nest(nside, ipix, *phi, *theta); }
+
+void ftte_rotate_indices(int i, int j, int k, int nx, int ny, int nz, int izone, int32_t* out) {
+  int a, b, c;
+  rotateIndices(i, j, k, nx, ny, nz, izone, a, b, c);
+  out[0] = a; out[1] = b; out[2] = c;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes loader for the CPU oracle (oracle/libftte_oracle.so).
+
+The oracle is a line-by-line C++ restatement of the reference hot path (see oracle/ftte_common.h for the
+"parity unpinned" note).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module; the product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_d = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_i8 = np.ctypeslib.ndpointer(dtype=np.int8, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libftte_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.ftte_grid_create.restype = C.c_void_p
+        L.ftte_grid_create.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_int)]
+        L.ftte_grid_destroy.argtypes = [C.c_void_p]
+        L.ftte_grid_set_species.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ftte_diffuse.restype = C.c_int
+        L.ftte_diffuse.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int64,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ftte_direction.restype = C.c_int
+        L.ftte_direction.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double)]
+        L.ftte_pix2ang_nest.restype = C.c_int
+        L.ftte_pix2ang_nest.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ftte_rotate_indices.argtypes = [C.c_int] * 7 + [C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+class OracleGrid:
+    """Octree rebuilt from the flattened leaf arrays (leaf pre-order, equiSources.f90:4044-4079)."""
+
+    def __init__(self, nx, level, HI, HeI=None, HeII=None, rho=None, abun2=None, box_size=1.0):
+        self.L = lib()
+        self.nx = int(nx)
+        self.level = np.ascontiguousarray(level, dtype=np.int8)
+        self.nleaf = int(self.level.size)
+        arrs = [_f64(HI), _f64(HeI), _f64(HeII), _f64(rho), _f64(abun2)]
+        st = C.c_int(0)
+        self.h = self.L.ftte_grid_create(self.nx, self.nleaf, _p(self.level), *[_p(a) for a in arrs],
+                                         float(box_size), C.byref(st))
+        if not self.h:
+            raise RuntimeError(f"ftte_grid_create failed: status {st.value}")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ftte_grid_destroy(self.h)
+            self.h = None
+
+    def set_species(self, HI=None, HeI=None, HeII=None):
+        a = [_f64(HI), _f64(HeI), _f64(HeII)]
+        self.L.ftte_grid_set_species(self.h, *[_p(x) for x in a])
+
+    def diffuse(self, uvb, beta, n_angular_level=3, ray_begin=0, ray_end=-1, trace_ray=-1):
+        """Returns dict(J=[3,nleaf], nseg, status[, nb, pattern, izone, angles])."""
+        uvb = _f64(uvb)
+        beta = _f64(np.asarray(beta).reshape(9))
+        J = np.zeros((3, self.nleaf))
+        nseg = C.c_int64(0)
+        nb = pat = iz = ang = None
+        if trace_ray >= 0:
+            nb = np.full((3, self.nleaf), -9, dtype=np.int32)
+            pat = np.zeros((self.nx, 12))
+            iz = np.zeros(1, dtype=np.int32)
+            ang = np.zeros(2)
+        st = self.L.ftte_diffuse(self.h, int(n_angular_level), _p(uvb), _p(beta), int(ray_begin), int(ray_end),
+                                 _p(J[0]), _p(J[1]), _p(J[2]), C.byref(nseg), int(trace_ray),
+                                 _p(nb), _p(pat), _p(iz), _p(ang))
+        out = dict(J=J, nseg=nseg.value, status=st)
+        if trace_ray >= 0:
+            out.update(nb=nb, pattern=pat, izone=int(iz[0]), angles=ang)
+        return out
+
+
+def direction(n_angular_level, iray):
+    iz, phi, th = C.c_int32(0), C.c_double(0), C.c_double(0)
+    st = lib().ftte_direction(int(n_angular_level), int(iray), C.byref(iz), C.byref(phi), C.byref(th))
+    return st, iz.value, phi.value, th.value
+
+
+def pix2ang_nest(nside, ipix):
+    phi, th = C.c_double(0), C.c_double(0)
+    st = lib().ftte_pix2ang_nest(int(nside), int(ipix), C.byref(phi), C.byref(th))
+    return st, phi.value, th.value
+
+
+def rotate_indices(i, j, k, nx, ny, nz, izone):
+    out = np.zeros(3, dtype=np.int32)
+    lib().ftte_rotate_indices(i, j, k, nx, ny, nz, izone, _p(out))
+    return tuple(int(v) for v in out)
