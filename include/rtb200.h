@@ -1,0 +1,117 @@
+/* rtb200.h -- C-ABI of the B200-native transport kernels for razoumov/radiativeTransfer (FTTE).
+ *
+ * The reference has NO plugin / FFI interface for its hot path: the diffuse sweep is inline in
+ * `program pointTransfer` (equiSources.f90:1372-1808) and the point-source caster is a set of internal
+ * procedures (equiSources.f90:3120-3385), both reading and writing `zoneType` fields through Fortran
+ * pointers.  This header therefore DEFINES the drop-in boundary: each entry point names the reference block it
+ * replaces.  All arrays are plain host pointers unless the name ends in `_device`; per-leaf arrays are in the
+ * reference's own flattened leaf order (`writeCell` pre-order, equiSources.f90:4044-4079 driven by the
+ * i/j/k loops at :4830-4836: base cells i outer, j, k inner; children i, j, k), the order of the
+ * `cellArrayNNNN.h4` datasets.  Every function returns 0 on success or an RTB200_ERR_* code where the
+ * reference would `write(*,*) ...; stop`; the Fortran shim (radiativetransfer_b200/fortran/rtb200_shim.f90)
+ * turns a non-zero status into the same `stop`.  There is no CPU fallback: without a CUDA device
+ * rtb200_create fails with RTB200_ERR_CUDA.
+ */
+#ifndef RTB200_H
+#define RTB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB200_VERSION 100
+
+enum rtb200_status {
+  RTB200_OK = 0,
+  RTB200_ERR_PHI = 1,             /* equiSources.f90:1413 'error in phi' */
+  RTB200_ERR_THETA = 2,           /* equiSources.f90:1426 'error in theta' */
+  RTB200_ERR_THETA_OR_PHI = 3,    /* equiSources.f90:1449 */
+  RTB200_ERR_PATTERN_RANGE = 4,   /* transportRoutinesModule.f90:33,60,183; equiSources.f90:1523 */
+  RTB200_ERR_TOP_SELECTOR = 5,    /* 'error in xyTop/xzTop/yzTop': equiSources.f90:1605,1672,1741; transportRoutinesModule.f90:609 */
+  RTB200_ERR_RAY_INACTIVE = 6,    /* 'Error: xzRay should be active': equiSources.f90:1679 ... */
+  RTB200_ERR_INTENSITY_GUARD = 7, /* transportRoutinesModule.f90:680-688 */
+  RTB200_ERR_ANGLE_LARGE = 8,     /* equiSources.f90:2224 */
+  RTB200_ERR_LEVELS = 9,          /* readCellArray.f90:181 'error in levels' */
+  RTB200_ERR_CHECKPOINT = 10,     /* equiSources.f90:2962 checkPoint */
+  RTB200_ERR_IDEPTH = 11,         /* equiSources.f90:4196 'error in idepth123' */
+  RTB200_ERR_ARG = 12,            /* bad argument (null pointer, size mismatch, grid not set ...) */
+  RTB200_ERR_CUDA = 13,           /* CUDA runtime failure or no device: no CPU fallback exists */
+  RTB200_ERR_NOMEM = 14
+};
+
+/* arithmetic mode of the per-segment update (transportRoutinesModule.f90:651-698, 1036-1054) */
+enum rtb200_math {
+  RTB200_MATH_FAST = 0,     /* J_seg = Iin*(1-exp(-tau))/tau: the same quantity without the exp->log round trip */
+  RTB200_MATH_FAITHFUL = 1  /* J_seg = (Iin-Iout)/log(Iin/Iout), operation for operation as the reference */
+};
+
+typedef struct rtb200_ctx rtb200_ctx;
+
+int rtb200_version(void);
+const char* rtb200_status_string(int status);
+
+/* One context per process and GPU.  `device` is the CUDA ordinal (LOCAL_RANK under torchrun). */
+int rtb200_create(int device, rtb200_ctx** ctx);
+int rtb200_destroy(rtb200_ctx* ctx);
+int rtb200_set_math(rtb200_ctx* ctx, int math_mode);
+/* launch tuning knobs ("tile_y", "slots", "graph", "l2_mb"); results do not depend on them */
+int rtb200_set_tuning(rtb200_ctx* ctx, const char* key, double value);
+/* status raised by a device-side guard during an asynchronous (*_device) call since the last query; clears it */
+int rtb200_device_error(rtb200_ctx* ctx);
+
+/* Replaces the pointer-linked octree (definitionsModule.f90:163-182; built at equiSources.f90:1870-1974) with
+ * structure-of-arrays device buffers plus a linear octree rebuilt from `level` alone, exactly as
+ * readCellArray.f90:154-187 does.  nx = ny = nz (equiSources.f90:427-436 requires a cubic level-1 grid).
+ * rho and abun2 may be NULL when only the diffuse path is used.  Arrays are copied. */
+int rtb200_grid_set(rtb200_ctx* ctx, int nx, int64_t nleaf, const int8_t* level, const double* HI,
+                    const double* HeI, const double* HeII, const double* rho, const double* abun2,
+                    double physicalBoxSize);
+
+/* New absorber densities after a chemistry step (solveRateEquations writes back HI, HeI, HeII only:
+ * equiSources.f90:3671-3673).  NULL keeps the current array. */
+int rtb200_grid_update_species(rtb200_ctx* ctx, const double* HI, const double* HeI, const double* HeII);
+
+/* Diffuse (UV background) sweep: replaces equiSources.f90:1372-1808 (computeOpacities :4956, the loop over
+ * 12*4**(nAngularLevel-1) HEALPix directions, pattern set-up, neighbour threading, transport).
+ *   uvb[3]      boundary intensities uvb1..3 (definitionsModule.f90:53)
+ *   beta[9]     group cross-sections, [group g=1..3][beta24, beta26, beta25] (uvbBetaTable.f90:262-296)
+ *   rays/nrays  HEALPix NESTED pixel numbers to sweep (direction sharding across GPUs); NULL/0 = all
+ *   Jmean1..3   caller-allocated [nleaf], OVERWRITTEN with the sum over the swept directions (Jmean is zeroed
+ *               by computeOpacities in the reference); a multi-GPU caller sums the per-rank results
+ *   nseg        optional: number of ray-cell segment updates performed (the benchmark's unit)               */
+int rtb200_diffuse(rtb200_ctx* ctx, int nAngularLevel, const double* uvb, const double* beta,
+                   const int32_t* rays, int32_t nrays, double* Jmean1, double* Jmean2, double* Jmean3,
+                   int64_t* nseg);
+
+/* Same sweep with the result left on the GPU: J_device is a device pointer to [3][nleaf] doubles (Jmean1, then
+ * Jmean2, then Jmean3), `stream` a cudaStream_t (NULL = default stream).  Asynchronous with respect to the host
+ * except for plan building on first use.  Used for the NCCL all-reduce and the resident-data benchmark. */
+int rtb200_diffuse_device(rtb200_ctx* ctx, int nAngularLevel, const double* uvb, const double* beta,
+                          const int32_t* rays, int32_t nrays, double* J_device, void* stream, int64_t* nseg);
+
+/* Diffuse contribution to the photo-rates (equiSources.f90:3546-3553), fused after the (all-reduced) J:
+ *   krate24 += 4*pi*(J1*ksi24[0] + J2*ksi24[1] + J3*ksi24[2]);  krate25 += 4*pi*J3*ksi25;
+ *   krate26 += 4*pi*(J2*ksi26[0] + J3*ksi26[1]).   All pointers are device pointers, k* accumulate. */
+int rtb200_diffuse_rates_device(rtb200_ctx* ctx, const double* J_device, const double* ksi24, const double* ksi25,
+                                const double* ksi26, double* k24_device, double* k25_device, double* k26_device,
+                                void* stream);
+
+/* --- debugging / parity exports (bit-exact traversal checks) ------------------------------------------- */
+/* zone number (1..24) and local angles of one direction: equiSources.f90:1391-1454 */
+int rtb200_direction(int nAngularLevel, int64_t iray, int32_t* izone, double* phi, double* theta);
+/* base-layer pattern table of one direction, [nx][12] = xy(x0,y0,len) xz(x0,z0,len) yz(y0,z0,len) xyTop xzTop yzTop */
+int rtb200_patterns(int nAngularLevel, int64_t iray, int nx, double* out);
+/* upstream leaf of every leaf for one direction, [3][nleaf] = xy, yz, xz; -1 boundary, -2 ray inactive
+ * (transportRoutinesModule.f90:264-418) */
+int rtb200_neighbours(rtb200_ctx* ctx, int nAngularLevel, int64_t iray, int32_t* nb);
+
+/* timing of the last rtb200_diffuse* call: milliseconds of device time between CUDA events on the launch stream,
+ * number of kernel launches issued, and algorithmic bytes (72 B per leaf per direction). */
+int rtb200_last_stats(rtb200_ctx* ctx, double* device_ms, int64_t* launches, double* algorithmic_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB200_H */

@@ -1,0 +1,389 @@
+// C-ABI of librtb200.so (declared in include/rtb200.h).  No torch types, no CPU fallback.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "rtb200_internal.h"
+
+namespace rtb {
+
+static thread_local char g_cudaErr[512] = "";
+
+void set_cuda_error(const char* what, cudaError_t e, const char* file, int line) {
+  snprintf(g_cudaErr, sizeof(g_cudaErr), "%s:%d: %s -> %s", file, line, what, cudaGetErrorString(e));
+  if (getenv("RTB200_VERBOSE")) fprintf(stderr, "[rtb200] %s\n", g_cudaErr);
+}
+const char* last_cuda_error() { return g_cudaErr; }
+
+int ensure_buffer(void** p, size_t* have, size_t need) {
+  if (*p && *have >= need) return RTB200_OK;
+  if (*p) { cudaFree(*p); *p = nullptr; *have = 0; }
+  cudaError_t e = cudaMalloc(p, need);
+  if (e != cudaSuccess) {
+    set_cuda_error("cudaMalloc", e, __FILE__, __LINE__);
+    *p = nullptr;
+    return e == cudaErrorMemoryAllocation ? RTB200_ERR_NOMEM : RTB200_ERR_CUDA;
+  }
+  *have = need;
+  return RTB200_OK;
+}
+
+static void free_grid(Context& c) {
+  cudaFree(c.dLevel); cudaFree(c.dHI); cudaFree(c.dHeI); cudaFree(c.dHeII); cudaFree(c.dRho); cudaFree(c.dAbun2);
+  cudaFree(c.dKappa); cudaFree(c.tree.child); cudaFree(c.tree.leafX); cudaFree(c.tree.leafY); cudaFree(c.tree.leafZ);
+  cudaFree(c.dJ);
+  c.dLevel = nullptr; c.dHI = c.dHeI = c.dHeII = c.dRho = c.dAbun2 = c.dKappa = c.dJ = nullptr;
+  c.tree = DevTree();
+  c.uniPlanKey.clear();
+  c.amrPlanKey.clear();
+  if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
+}
+
+// Linear octree from the leaf `level` array alone (readCellArray.f90:154-187): nodes 0..n^3-1 are the base cells in
+// leaf order (x slowest); every refined node owns 8 consecutive children, x slowest / z fastest
+// (the i, j, k loop order of writeCell, equiSources.f90:4053-4059).
+static int build_tree(Context& c, const int8_t* level) {
+  const int n = c.nx;
+  const int64_t nbase = (int64_t)n * n * n;
+  c.hChild.assign((size_t)nbase, 0);
+  c.hLeafX.resize((size_t)c.nleaf); c.hLeafY.resize((size_t)c.nleaf); c.hLeafZ.resize((size_t)c.nleaf);
+  c.maxLevel = 0;
+  for (int a = 0; a < 3; a++) c.refinedLayer[a].clear();
+  struct Frame { int32_t node; int32_t x, y, z; int8_t lvl; int8_t next; };
+  std::vector<Frame> stack;
+  int64_t leaf = 0;
+  auto mark_refined = [&](int lvl, int x, int y, int z) {
+    for (int a = 0; a < 3; a++) {
+      if ((int)c.refinedLayer[a].size() <= lvl) c.refinedLayer[a].resize(lvl + 1);
+      auto& v = c.refinedLayer[a][lvl];
+      if (v.empty()) v.assign((size_t)n << lvl, 0);
+      v[a == 0 ? x : (a == 1 ? y : z)] = 1;
+    }
+  };
+  for (int64_t b = 0; b < nbase; b++) {
+    int bx = (int)(b / ((int64_t)n * n)), by = (int)((b / n) % n), bz = (int)(b % n);
+    stack.clear();
+    stack.push_back({(int32_t)b, bx, by, bz, 0, 0});
+    while (!stack.empty()) {
+      Frame& f = stack.back();
+      if (f.next == 0) {
+        if (leaf >= c.nleaf) return RTB200_ERR_LEVELS;
+        int lv = level[leaf];
+        if (lv == f.lvl) {
+          c.hChild[f.node] = -(int32_t)(leaf + 1);
+          c.hLeafX[leaf] = f.x; c.hLeafY[leaf] = f.y; c.hLeafZ[leaf] = f.z;
+          if (lv > c.maxLevel) c.maxLevel = lv;
+          leaf++;
+          stack.pop_back();
+          continue;
+        }
+        if (lv < f.lvl) return RTB200_ERR_LEVELS;
+        if (c.hChild.size() + 8 > (size_t)INT32_MAX) return RTB200_ERR_ARG;
+        int32_t first = (int32_t)c.hChild.size();
+        c.hChild[f.node] = first;
+        c.hChild.resize(c.hChild.size() + 8, 0);
+        mark_refined(f.lvl, f.x, f.y, f.z);
+      }
+      Frame& g = stack.back();  // hChild.resize does not move the stack
+      if (g.next == 8) { stack.pop_back(); continue; }
+      int q = g.next++;
+      Frame ch{c.hChild[g.node] + q, 2 * g.x + (q >> 2), 2 * g.y + ((q >> 1) & 1), 2 * g.z + (q & 1), (int8_t)(g.lvl + 1), 0};
+      stack.push_back(ch);
+    }
+  }
+  if (leaf != c.nleaf) return RTB200_ERR_LEVELS;
+  c.tree.nnodes = (int64_t)c.hChild.size();
+  return RTB200_OK;
+}
+
+static int upload(void** dst, const void* src, size_t bytes, cudaStream_t s) {
+  cudaError_t e = cudaMalloc(dst, bytes ? bytes : 8);
+  if (e != cudaSuccess) { set_cuda_error("cudaMalloc", e, __FILE__, __LINE__); return e == cudaErrorMemoryAllocation ? RTB200_ERR_NOMEM : RTB200_ERR_CUDA; }
+  if (src) RTB_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, s));
+  else RTB_CUDA(cudaMemsetAsync(*dst, 0, bytes ? bytes : 8, s));
+  return RTB200_OK;
+}
+
+static int resolve_directions(int nAngularLevel, const int32_t* rays, int32_t nrays, std::vector<Direction>& dirs) {
+  if (nAngularLevel < 1 || nAngularLevel > 8) return RTB200_ERR_ARG;
+  const int64_t total = 12LL << (2 * (nAngularLevel - 1));
+  dirs.clear();
+  if (!rays || nrays <= 0) {
+    if (rays == nullptr && nrays == 0) {
+      for (int64_t r = 0; r < total; r++) dirs.push_back(classify_direction(nAngularLevel, r));
+    } else if (nrays < 0) {
+      return RTB200_ERR_ARG;
+    }  // rays != NULL && nrays == 0: empty shard
+  } else {
+    for (int32_t q = 0; q < nrays; q++) {
+      if (rays[q] < 0 || rays[q] >= total) return RTB200_ERR_ARG;
+      dirs.push_back(classify_direction(nAngularLevel, rays[q]));
+    }
+  }
+  for (const auto& d : dirs)
+    if (d.status) return d.status;
+  return RTB200_OK;
+}
+
+static int run_diffuse(Context& c, int nAngularLevel, const double* uvb, const double* beta, const int32_t* rays,
+                       int32_t nrays, double* dJ, cudaStream_t s, int64_t* nseg) {
+  if (!uvb || !beta || !dJ) return RTB200_ERR_ARG;
+  if (c.nleaf == 0) return RTB200_ERR_ARG;
+  std::vector<Direction> dirs;
+  if (int st = resolve_directions(nAngularLevel, rays, nrays, dirs)) return st;
+  RTB_CUDA(cudaSetDevice(c.device));
+  RTB_CUDA(cudaEventRecord(c.evStart, s));
+  if (int st = launch_compute_opacities(c, beta, s)) return st;
+  int64_t ns = 0;
+  int st = c.uniform ? diffuse_uniform(c, nAngularLevel, uvb, dirs, dJ, s, &ns)
+                     : diffuse_amr(c, nAngularLevel, uvb, dirs, dJ, s, &ns);
+  if (st) return st;
+  RTB_CUDA(cudaEventRecord(c.evStop, s));
+  if (nseg) *nseg = ns;
+  c.lastAlgBytes = 72.0 * (double)c.nleaf * (double)dirs.size();
+  c.statsPending = true;
+  return RTB200_OK;
+}
+
+}  // namespace rtb
+
+using namespace rtb;
+
+struct rtb200_ctx {
+  Context c;
+};
+
+extern "C" {
+
+int rtb200_version(void) { return RTB200_VERSION; }
+
+const char* rtb200_status_string(int status) {
+  switch (status) {
+    case RTB200_OK: return "ok";
+    case RTB200_ERR_PHI: return "error in phi (direction on a quadrant boundary)";
+    case RTB200_ERR_THETA: return "error in theta";
+    case RTB200_ERR_THETA_OR_PHI: return "error in theta or phi (tie between exit faces)";
+    case RTB200_ERR_PATTERN_RANGE: return "Error: ray entry coordinate > 1";
+    case RTB200_ERR_TOP_SELECTOR: return "error in xyTop/xzTop/yzTop";
+    case RTB200_ERR_RAY_INACTIVE: return "Error: xzRay/yzRay should be active";
+    case RTB200_ERR_INTENSITY_GUARD: return "intensity guard: |Iout1+Iout2+Iout3| >= 1e-20 in a refined cell";
+    case RTB200_ERR_ANGLE_LARGE: return "angle too large";
+    case RTB200_ERR_LEVELS: return "error in levels";
+    case RTB200_ERR_CHECKPOINT: return "error in coordinates";
+    case RTB200_ERR_IDEPTH: return "error in idepth123";
+    case RTB200_ERR_ARG: return "bad argument";
+    case RTB200_ERR_CUDA: return last_cuda_error()[0] ? last_cuda_error() : "CUDA error or no CUDA device (no CPU fallback)";
+    case RTB200_ERR_NOMEM: return "out of device memory";
+    default: return "unknown status";
+  }
+}
+
+int rtb200_create(int device, rtb200_ctx** out) {
+  if (!out) return RTB200_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_cuda_error("cudaGetDeviceCount", e == cudaSuccess ? cudaErrorNoDevice : e, __FILE__, __LINE__);
+    return RTB200_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) return RTB200_ERR_ARG;
+  RTB_CUDA(cudaSetDevice(device));
+  rtb200_ctx* h = new (std::nothrow) rtb200_ctx();
+  if (!h) return RTB200_ERR_NOMEM;
+  Context& c = h->c;
+  c.device = device;
+  cudaDeviceProp prop;
+  RTB_CUDA(cudaGetDeviceProperties(&prop, device));
+  c.smCount = prop.multiProcessorCount;
+  c.l2Bytes = (size_t)prop.l2CacheSize;
+  if (c.l2Bytes) c.tune.l2BudgetMB = 0.75 * (double)c.l2Bytes / 1048576.0;
+  RTB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  RTB_CUDA(cudaEventCreate(&c.evStart));
+  RTB_CUDA(cudaEventCreate(&c.evStop));
+  RTB_CUDA(cudaMalloc((void**)&c.dErr, 64));
+  RTB_CUDA(cudaMemset(c.dErr, 0, 64));
+  if (const char* v = getenv("RTB200_TILE_Y")) c.tune.tileY = atoi(v);
+  if (const char* v = getenv("RTB200_SLOTS")) c.tune.slots = atoi(v);
+  if (const char* v = getenv("RTB200_GRAPH")) c.tune.useGraph = atoi(v);
+  if (const char* v = getenv("RTB200_L2_MB")) c.tune.l2BudgetMB = atof(v);
+  *out = h;
+  return RTB200_OK;
+}
+
+int rtb200_destroy(rtb200_ctx* h) {
+  if (!h) return RTB200_OK;
+  Context& c = h->c;
+  cudaSetDevice(c.device);
+  cudaDeviceSynchronize();
+  free_grid(c);
+  cudaFree(c.dAcc); cudaFree(c.dPlanes); cudaFree(c.dTasks); cudaFree(c.dPats); cudaFree(c.dAmrScratch); cudaFree(c.dErr);
+  if (c.hPinned) cudaFreeHost(c.hPinned);
+  if (c.evStart) cudaEventDestroy(c.evStart);
+  if (c.evStop) cudaEventDestroy(c.evStop);
+  if (c.stream) cudaStreamDestroy(c.stream);
+  delete h;
+  return RTB200_OK;
+}
+
+int rtb200_set_math(rtb200_ctx* h, int mode) {
+  if (!h || (mode != RTB200_MATH_FAST && mode != RTB200_MATH_FAITHFUL)) return RTB200_ERR_ARG;
+  if (h->c.mathMode != mode && h->c.graphExec) { cudaGraphExecDestroy(h->c.graphExec); h->c.graphExec = nullptr; }
+  h->c.mathMode = mode;
+  return RTB200_OK;
+}
+
+int rtb200_set_tuning(rtb200_ctx* h, const char* key, double value) {
+  if (!h || !key) return RTB200_ERR_ARG;
+  Context& c = h->c;
+  std::string k(key);
+  if (k == "tile_y") c.tune.tileY = (int)value;
+  else if (k == "slots") c.tune.slots = (int)value;
+  else if (k == "graph") c.tune.useGraph = (int)value;
+  else if (k == "l2_mb") c.tune.l2BudgetMB = value;
+  else return RTB200_ERR_ARG;
+  c.uniPlanKey.clear();
+  if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
+  return RTB200_OK;
+}
+
+int rtb200_grid_set(rtb200_ctx* h, int nx, int64_t nleaf, const int8_t* level, const double* HI, const double* HeI,
+                    const double* HeII, const double* rho, const double* abun2, double physicalBoxSize) {
+  if (!h || nx < 1 || nx > 4096 || !level || !HI || nleaf < (int64_t)nx * nx * nx || nleaf > (int64_t)INT32_MAX)
+    return RTB200_ERR_ARG;
+  Context& c = h->c;
+  RTB_CUDA(cudaSetDevice(c.device));
+  RTB_CUDA(cudaDeviceSynchronize());
+  free_grid(c);
+  c.nx = nx; c.nleaf = nleaf; c.boxSize = physicalBoxSize;
+  c.hLevel.assign(level, level + nleaf);
+  c.uniform = true;
+  for (int64_t i = 0; i < nleaf; i++)
+    if (level[i] != 0) { c.uniform = false; break; }
+  if (c.uniform && nleaf != (int64_t)nx * nx * nx) { c.nleaf = 0; return RTB200_ERR_LEVELS; }
+  if (int st = build_tree(c, level)) { c.nleaf = 0; return st; }
+  cudaStream_t s = c.stream;
+  const size_t nb = (size_t)nleaf * sizeof(double);
+  int st = upload((void**)&c.dLevel, level, (size_t)nleaf, s);
+  if (!st) st = upload((void**)&c.dHI, HI, nb, s);
+  if (!st) st = upload((void**)&c.dHeI, HeI, nb, s);
+  if (!st) st = upload((void**)&c.dHeII, HeII, nb, s);
+  if (!st) st = upload((void**)&c.dRho, rho, nb, s);
+  if (!st) st = upload((void**)&c.dAbun2, abun2, nb, s);
+  if (!st) st = upload((void**)&c.dKappa, nullptr, 3 * nb, s);
+  if (!st) st = upload((void**)&c.dJ, nullptr, 3 * nb, s);
+  if (!st && !c.uniform) {
+    st = upload((void**)&c.tree.child, c.hChild.data(), c.hChild.size() * sizeof(int32_t), s);
+    if (!st) st = upload((void**)&c.tree.leafX, c.hLeafX.data(), (size_t)nleaf * sizeof(int32_t), s);
+    if (!st) st = upload((void**)&c.tree.leafY, c.hLeafY.data(), (size_t)nleaf * sizeof(int32_t), s);
+    if (!st) st = upload((void**)&c.tree.leafZ, c.hLeafZ.data(), (size_t)nleaf * sizeof(int32_t), s);
+  }
+  if (st) { free_grid(c); c.nleaf = 0; return st; }
+  RTB_CUDA(cudaStreamSynchronize(s));
+  return RTB200_OK;
+}
+
+int rtb200_grid_update_species(rtb200_ctx* h, const double* HI, const double* HeI, const double* HeII) {
+  if (!h || h->c.nleaf == 0) return RTB200_ERR_ARG;
+  Context& c = h->c;
+  RTB_CUDA(cudaSetDevice(c.device));
+  const size_t nb = (size_t)c.nleaf * sizeof(double);
+  if (HI) RTB_CUDA(cudaMemcpyAsync(c.dHI, HI, nb, cudaMemcpyHostToDevice, c.stream));
+  if (HeI) RTB_CUDA(cudaMemcpyAsync(c.dHeI, HeI, nb, cudaMemcpyHostToDevice, c.stream));
+  if (HeII) RTB_CUDA(cudaMemcpyAsync(c.dHeII, HeII, nb, cudaMemcpyHostToDevice, c.stream));
+  RTB_CUDA(cudaStreamSynchronize(c.stream));
+  return RTB200_OK;
+}
+
+int rtb200_diffuse_device(rtb200_ctx* h, int nAngularLevel, const double* uvb, const double* beta, const int32_t* rays,
+                          int32_t nrays, double* J_device, void* stream, int64_t* nseg) {
+  if (!h) return RTB200_ERR_ARG;
+  return run_diffuse(h->c, nAngularLevel, uvb, beta, rays, nrays, J_device, (cudaStream_t)stream, nseg);
+}
+
+int rtb200_diffuse(rtb200_ctx* h, int nAngularLevel, const double* uvb, const double* beta, const int32_t* rays,
+                   int32_t nrays, double* J1, double* J2, double* J3, int64_t* nseg) {
+  if (!h || !J1 || !J2 || !J3) return RTB200_ERR_ARG;
+  Context& c = h->c;
+  int st = run_diffuse(c, nAngularLevel, uvb, beta, rays, nrays, c.dJ, c.stream, nseg);
+  if (st) return st;
+  const size_t nb = (size_t)c.nleaf * sizeof(double);
+  RTB_CUDA(cudaMemcpyAsync(J1, c.dJ, nb, cudaMemcpyDeviceToHost, c.stream));
+  RTB_CUDA(cudaMemcpyAsync(J2, c.dJ + c.nleaf, nb, cudaMemcpyDeviceToHost, c.stream));
+  RTB_CUDA(cudaMemcpyAsync(J3, c.dJ + 2 * c.nleaf, nb, cudaMemcpyDeviceToHost, c.stream));
+  RTB_CUDA(cudaStreamSynchronize(c.stream));
+  int32_t err = 0;
+  RTB_CUDA(cudaMemcpy(&err, c.dErr, sizeof(err), cudaMemcpyDeviceToHost));
+  if (err) { cudaMemset(c.dErr, 0, 64); return err; }
+  return RTB200_OK;
+}
+
+int rtb200_diffuse_rates_device(rtb200_ctx* h, const double* J, const double* ksi24, const double* ksi25,
+                                const double* ksi26, double* k24, double* k25, double* k26, void* stream) {
+  if (!h || !J || !ksi24 || !ksi25 || !ksi26 || !k24 || !k25 || !k26 || h->c.nleaf == 0) return RTB200_ERR_ARG;
+  RTB_CUDA(cudaSetDevice(h->c.device));
+  return launch_diffuse_rates(h->c, J, ksi24, ksi25, ksi26, k24, k25, k26, (cudaStream_t)stream);
+}
+
+int rtb200_device_error(rtb200_ctx* h) {  // status raised by device-side guards of asynchronous calls
+  if (!h) return RTB200_ERR_ARG;
+  int32_t err = 0;
+  RTB_CUDA(cudaSetDevice(h->c.device));
+  RTB_CUDA(cudaMemcpy(&err, h->c.dErr, sizeof(err), cudaMemcpyDeviceToHost));
+  if (err) cudaMemset(h->c.dErr, 0, 64);
+  return err;
+}
+
+int rtb200_direction(int nAngularLevel, int64_t iray, int32_t* izone, double* phi, double* theta) {
+  if (!izone || !phi || !theta || nAngularLevel < 1) return RTB200_ERR_ARG;
+  Direction d = classify_direction(nAngularLevel, iray);
+  *izone = d.izone; *phi = d.phi; *theta = d.theta;
+  return d.status;
+}
+
+int rtb200_patterns(int nAngularLevel, int64_t iray, int nx, double* out) {
+  if (!out || nx < 1) return RTB200_ERR_ARG;
+  Direction d = classify_direction(nAngularLevel, iray);
+  if (d.status) return d.status;
+  std::vector<RayPattern> pat;
+  layer_patterns_level0(d.phi, d.theta, nx, pat);
+  for (int i = 0; i < nx; i++) {
+    const RayPattern& p = pat[i];
+    if (p.status) return p.status;
+    double* o = out + 12 * i;
+    o[0] = p.xy_x0; o[1] = p.xy_y0; o[2] = p.xy_len;
+    o[3] = p.xzActive ? p.xz_x0 : 0.; o[4] = p.xzActive ? p.xz_z0 : 0.; o[5] = p.xzActive ? p.xz_len : 0.;
+    o[6] = p.yzActive ? p.yz_y0 : 0.; o[7] = p.yzActive ? p.yz_z0 : 0.; o[8] = p.yzActive ? p.yz_len : 0.;
+    o[9] = p.xyTop; o[10] = p.xzTop; o[11] = p.yzTop;
+  }
+  return RTB200_OK;
+}
+
+int rtb200_neighbours(rtb200_ctx* h, int nAngularLevel, int64_t iray, int32_t* nb) {
+  if (!h || !nb || h->c.nleaf == 0) return RTB200_ERR_ARG;
+  Direction d = classify_direction(nAngularLevel, iray);
+  if (d.status) return d.status;
+  RTB_CUDA(cudaSetDevice(h->c.device));
+  return amr_neighbours(h->c, d, nb);
+}
+
+int rtb200_last_stats(rtb200_ctx* h, double* ms, int64_t* launches, double* algBytes) {
+  if (!h) return RTB200_ERR_ARG;
+  Context& c = h->c;
+  if (c.statsPending) {
+    RTB_CUDA(cudaSetDevice(c.device));
+    RTB_CUDA(cudaEventSynchronize(c.evStop));
+    float f = 0;
+    RTB_CUDA(cudaEventElapsedTime(&f, c.evStart, c.evStop));
+    c.lastMs = f;
+    c.statsPending = false;
+  }
+  if (ms) *ms = c.lastMs;
+  if (launches) *launches = c.lastLaunches;
+  if (algBytes) *algBytes = c.lastAlgBytes;
+  return RTB200_OK;
+}
+
+}  // extern "C"

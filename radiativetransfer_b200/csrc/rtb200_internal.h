@@ -1,0 +1,147 @@
+// Internal declarations shared by the C-ABI (api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/rtb200.h"
+#include "geometry.h"
+
+namespace rtb {
+
+#define RTB_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      rtb::set_cuda_error(#call, e_, __FILE__, __LINE__);                           \
+      return RTB200_ERR_CUDA;                                                       \
+    }                                                                               \
+  } while (0)
+
+void set_cuda_error(const char* what, cudaError_t e, const char* file, int line);
+const char* last_cuda_error();
+
+// ------------------------------------------------------------------------------------------------
+// Device tables of the uniform-grid sweep
+// ------------------------------------------------------------------------------------------------
+// One layer of one direction, in CHAIN order: a characteristic entering the layer through the bottom face
+// crosses 1..3 cells (segments 0,1,2) before it leaves through the top.
+//   kind 0: xy                      kind 1: xy -> yz            kind 2: xy -> yz -> xz
+//   kind 3: xy -> xz                kind 4: xy -> xz -> yz
+// The second segment of kinds 1,2 (a yz ray) is fed by the cell at k-1, of kinds 3,4 (an xz ray) by the cell at
+// j-1; the third segment by the other one.
+struct LayerSeg {
+  double d[3];     // path length [cm]: cellSize * len
+  double invd[3];  // 1 / d
+  double wn;       // weight / nseg   (fast mode)
+  double w;        // weight          (faithful mode divides by nseg first, transportRoutinesModule.f90:953)
+  int32_t kind;
+  int32_t nseg;
+  int32_t pad[2];
+};
+static_assert(sizeof(LayerSeg) == 80, "LayerSeg layout");
+
+constexpr int kMaxDirPerTask = 16;
+
+// One task = the directions of one zone (same index rotation), swept together layer by layer so that kappa is
+// read once and J is accumulated in registers across the directions.
+struct UniTask {
+  int64_t origin, si, sj, sk;  // leaf index = origin + i*si + j*sj + k*sk (0-based rotated indices)
+  double* acc;                 // slot accumulator [3][N] this task adds into
+  int32_t ndir;
+  int32_t laneIsK;             // 1: threadIdx.x runs along rotated k, 0: along rotated j
+  int32_t firstInSlot;         // 1: overwrite the accumulator instead of adding
+  int32_t pad;
+  int32_t dir[kMaxDirPerTask]; // local direction index (row of the LayerSeg table and of the planes)
+};
+
+struct Tuning {
+  int tileY = 16;        // block = 32 x tileY threads
+  int slots = 0;         // zones swept concurrently (0 = choose from the L2 budget)
+  int useGraph = 1;
+  double l2BudgetMB = 96.0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// AMR tables
+// ------------------------------------------------------------------------------------------------
+struct DevTree {
+  int32_t* child = nullptr;      // [nnodes] >=0: first of 8 children (x slowest, z fastest); <0: -(leaf+1)
+  int32_t* leafX = nullptr;      // [nleaf] integer coordinates at the leaf's own level
+  int32_t* leafY = nullptr;
+  int32_t* leafZ = nullptr;
+  int64_t nnodes = 0;
+};
+
+struct Context {
+  int device = 0;
+  int mathMode = RTB200_MATH_FAST;
+  Tuning tune;
+  cudaStream_t stream = nullptr;  // internal stream for host-buffer calls
+  cudaEvent_t evStart = nullptr, evStop = nullptr;
+  int smCount = 148;
+  size_t l2Bytes = 0;
+
+  // grid
+  int nx = 0;
+  int64_t nleaf = 0;
+  int maxLevel = 0;
+  double boxSize = 0;
+  bool uniform = true;
+  std::vector<int8_t> hLevel;
+  int8_t* dLevel = nullptr;
+  double *dHI = nullptr, *dHeI = nullptr, *dHeII = nullptr, *dRho = nullptr, *dAbun2 = nullptr;
+  double* dKappa = nullptr;  // [3][nleaf]
+  DevTree tree;
+  std::vector<int32_t> hChild;               // host copy of the linear octree
+  std::vector<int32_t> hLeafX, hLeafY, hLeafZ;
+  // per physical axis and level: which layers contain a refined cell (pattern sub-tree exists there)
+  std::vector<std::vector<uint8_t>> refinedLayer[3];
+
+  // scratch owned by the diffuse paths (sized lazily, reused across calls)
+  double* dJ = nullptr;        // [3][nleaf] result buffer for the host-pointer API
+  double* dAcc = nullptr;      // slot accumulators
+  size_t accBytes = 0;
+  double* dPlanes = nullptr;   // ping-pong top-exit planes
+  size_t planeBytes = 0;
+  void* dTasks = nullptr;
+  size_t taskBytes = 0;
+  void* dPats = nullptr;
+  size_t patBytes = 0;
+  void* dAmrScratch = nullptr;
+  size_t amrScratchBytes = 0;
+  int32_t* dErr = nullptr;     // device error flag
+  double* hPinned = nullptr;   // pinned staging for host-pointer results
+  size_t pinnedBytes = 0;
+
+  // graph cache for the uniform sweep
+  cudaGraphExec_t graphExec = nullptr;
+  std::string graphKey;
+  // cached plan of the uniform sweep (pattern tables, zone tasks): valid while uniPlanKey matches
+  std::string uniPlanKey;
+  int uniNtask = 0, uniSlots = 0;
+  int64_t uniNseg = 0;
+  std::string amrPlanKey;
+  bool statsPending = false;
+
+  // stats of the last call
+  double lastMs = 0;
+  int64_t lastLaunches = 0;
+  double lastAlgBytes = 0;
+};
+
+int ensure_buffer(void** p, size_t* have, size_t need);
+
+// kernels / launchers --------------------------------------------------------------------------------
+int launch_compute_opacities(Context& c, const double* beta, cudaStream_t s);
+int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std::vector<Direction>& dirs,
+                    double* dJout, cudaStream_t s, int64_t* nseg);
+int diffuse_amr(Context& c, int nAngularLevel, const double* uvb, const std::vector<Direction>& dirs,
+                double* dJout, cudaStream_t s, int64_t* nseg);
+int amr_neighbours(Context& c, const Direction& d, int32_t* nbHost);
+int launch_diffuse_rates(Context& c, const double* J, const double* ksi24, const double* ksi25, const double* ksi26,
+                         double* k24, double* k25, double* k26, cudaStream_t s);
+
+}  // namespace rtb

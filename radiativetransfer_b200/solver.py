@@ -1,0 +1,124 @@
+"""Host-side mirror of the reference's hot-path call sites, on top of the C-ABI (include/rtb200.h).
+
+The reference has no operator API: `program pointTransfer` runs, once per outer iteration,
+    setZeroRates -> [point sources] -> computeOpacities + 192-direction diffuse sweep -> solveRateEquations
+(equiSources.f90:1246-1831).  `Transport` keeps that shape: a grid in the reference's flattened leaf order goes in,
+`diffuse()` returns Jmean1..3 per leaf exactly where the Fortran loop would have left them in `zoneType`.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+MATH_FAST, MATH_FAITHFUL = 0, 1
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def direction(n_angular_level, iray):
+    """(izone, phi, theta) of one HEALPix direction -- equiSources.f90:1391-1454."""
+    iz, phi, th = C.c_int32(0), C.c_double(0), C.c_double(0)
+    st = _lib.lib().rtb200_direction(int(n_angular_level), int(iray), C.byref(iz), C.byref(phi), C.byref(th))
+    _lib.check(st, "rtb200_direction")
+    return iz.value, phi.value, th.value
+
+
+def patterns(n_angular_level, iray, nx):
+    out = np.zeros((nx, 12))
+    _lib.check(_lib.lib().rtb200_patterns(int(n_angular_level), int(iray), int(nx), _ptr(out)), "rtb200_patterns")
+    return out
+
+
+class Transport:
+    """One GPU's transport engine (one per process; `device` = LOCAL_RANK)."""
+
+    def __init__(self, device=0, math=MATH_FAST):
+        self.L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(self.L.rtb200_create(int(device), C.byref(h)), "rtb200_create")
+        self.h = h
+        self.nleaf = 0
+        self.nx = 0
+        self.set_math(math)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rtb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_math(self, mode):
+        _lib.check(self.L.rtb200_set_math(self.h, int(mode)), "rtb200_set_math")
+
+    def set_tuning(self, **kw):
+        for k, v in kw.items():
+            _lib.check(self.L.rtb200_set_tuning(self.h, k.encode(), float(v)), f"rtb200_set_tuning({k})")
+
+    def set_grid(self, nx, level, HI, HeI=None, HeII=None, rho=None, abun2=None, box_size=1.0):
+        level = np.ascontiguousarray(level, dtype=np.int8)
+        arrs = [_f64(HI), _f64(HeI), _f64(HeII), _f64(rho), _f64(abun2)]
+        for a in arrs:
+            if a is not None and a.size != level.size:
+                raise ValueError("per-leaf arrays must all have nleaf entries")
+        st = self.L.rtb200_grid_set(self.h, int(nx), int(level.size), _ptr(level), *[_ptr(a) for a in arrs],
+                                    float(box_size))
+        _lib.check(st, "rtb200_grid_set")
+        self.nleaf, self.nx = int(level.size), int(nx)
+
+    def update_species(self, HI=None, HeI=None, HeII=None):
+        a = [_f64(HI), _f64(HeI), _f64(HeII)]
+        _lib.check(self.L.rtb200_grid_update_species(self.h, *[_ptr(x) for x in a]), "rtb200_grid_update_species")
+
+    def diffuse(self, uvb, beta, n_angular_level=3, rays=None, out=None):
+        """Host-buffer call (H2D of nothing but tables, D2H of J): returns (J[3, nleaf], nseg)."""
+        uvb, beta = _f64(uvb), _f64(np.asarray(beta).reshape(9))
+        J = out if out is not None else np.empty((3, self.nleaf))
+        r = None if rays is None else np.ascontiguousarray(rays, dtype=np.int32)
+        nseg = C.c_int64(0)
+        st = self.L.rtb200_diffuse(self.h, int(n_angular_level), _ptr(uvb), _ptr(beta), _ptr(r),
+                                   0 if r is None else int(r.size), _ptr(J[0]), _ptr(J[1]), _ptr(J[2]), C.byref(nseg))
+        _lib.check(st, "rtb200_diffuse")
+        return J, nseg.value
+
+    def diffuse_device(self, uvb, beta, J_ptr, n_angular_level=3, rays=None, stream=0):
+        """Resident call: J_ptr is a device pointer to [3][nleaf] doubles (e.g. torch tensor .data_ptr())."""
+        uvb, beta = _f64(uvb), _f64(np.asarray(beta).reshape(9))
+        r = None if rays is None else np.ascontiguousarray(rays, dtype=np.int32)
+        nseg = C.c_int64(0)
+        st = self.L.rtb200_diffuse_device(self.h, int(n_angular_level), _ptr(uvb), _ptr(beta), _ptr(r),
+                                          0 if r is None else int(r.size), C.c_void_p(int(J_ptr)),
+                                          C.c_void_p(int(stream)), C.byref(nseg))
+        _lib.check(st, "rtb200_diffuse_device")
+        return nseg.value
+
+    def diffuse_rates_device(self, J_ptr, ksi24, ksi25, ksi26, k24_ptr, k25_ptr, k26_ptr, stream=0):
+        a, b, c = _f64(ksi24), _f64(np.atleast_1d(ksi25)), _f64(ksi26)
+        st = self.L.rtb200_diffuse_rates_device(self.h, C.c_void_p(int(J_ptr)), _ptr(a), _ptr(b), _ptr(c),
+                                                C.c_void_p(int(k24_ptr)), C.c_void_p(int(k25_ptr)),
+                                                C.c_void_p(int(k26_ptr)), C.c_void_p(int(stream)))
+        _lib.check(st, "rtb200_diffuse_rates_device")
+
+    def device_error(self):
+        return self.L.rtb200_device_error(self.h)
+
+    def neighbours(self, n_angular_level, iray):
+        nb = np.full((3, self.nleaf), -9, dtype=np.int32)
+        _lib.check(self.L.rtb200_neighbours(self.h, int(n_angular_level), int(iray), _ptr(nb)), "rtb200_neighbours")
+        return nb
+
+    def last_stats(self):
+        ms, n, b = C.c_double(0), C.c_int64(0), C.c_double(0)
+        _lib.check(self.L.rtb200_last_stats(self.h, C.byref(ms), C.byref(n), C.byref(b)), "rtb200_last_stats")
+        return dict(device_ms=ms.value, launches=n.value, algorithmic_bytes=b.value)

@@ -1,0 +1,219 @@
+"""Synthetic inputs of the shapes named in BASELINE.json (none of the reference's data files ship with it).
+
+Grids are produced directly in the reference's flattened leaf order (`writeCell` pre-order,
+equiSources.f90:4044-4079): base cells x outer / y / z inner, the 8 children of a refined cell x, y, z.
+The UV-background amplitudes and group cross-sections follow the reference formulas
+(equiSources.f90:198-255, :4985-5043; uvbBetaTable.f90) evaluated with numpy -- they are workload parameters
+fed identically to the GPU path and to the CPU oracle, not part of the parity claim.
+"""
+import numpy as np
+
+# definitionsModule.f90:8-41 (single-precision literals widened)
+_f = np.float32
+PI = float(_f(3.141592654))
+HP = float(_f(6.6260693e-27))
+PC = float(_f(3.08568025e18))
+KPC = 1.0e3 * PC
+MP = float(_f(1.6726231e-24))
+MN = float(_f(1.67492728e-24))
+MHE = 2.0 * (MP + MN)
+PSI = float(_f(0.76))
+NU1, NU2, NU3 = float(_f(13.598)), float(_f(24.587)), float(_f(54.418))
+EV_TO_ERG = 1.60217646e-12
+EV_TO_HZ = EV_TO_ERG / HP
+
+
+def _sigmas(nu):
+    """HI, HeII, HeI photo-ionisation cross-sections (uvbBetaTable.f90:31-62)."""
+    s24 = np.zeros_like(nu)
+    s25 = np.zeros_like(nu)
+    s26 = np.zeros_like(nu)
+    m = nu > NU1
+    d = np.sqrt(nu[m] / NU1 - 1)
+    s24[m] = float(_f(6.3e-18)) * (NU1 / nu[m]) ** 4 * np.exp(4.0 - 4.0 * np.arctan(d) / d) / (1 - np.exp(-2.0 * PI / d))
+    m = nu > NU3
+    d = np.sqrt(nu[m] / NU3 - 1)
+    s25[m] = float(_f(1.58e-18)) * (NU3 / nu[m]) ** 4 * np.exp(4.0 - 4.0 * np.arctan(d) / d) / (1 - np.exp(-2.0 * PI / d))
+    m = nu > NU2
+    s26[m] = float(_f(7.42e-18)) * (float(_f(1.66)) * (nu[m] / NU2) ** (-2.05) - float(_f(0.66)) * (nu[m] / NU2) ** (-3.05))
+    return s24, s25, s26
+
+
+def _power_index(u1, a1, u2, a2, nug, nugplus, bound):
+    """equiSources.f90:4985-5043: slope of the single power law matching the two-component band integral."""
+    tot = u1 + u2
+    r = nug / nugplus
+
+    def band(u, a):
+        return u / (a - 1.0) * (1.0 - r ** (a - 1.0)) if bound else u / (a - 1.0)
+
+    target = band(u1, a1) + band(u2, a2)
+    t1, t2 = 1.1 * a1 - 0.1 * a2, 1.1 * a2 - 0.1 * a1
+    f1, f2 = band(tot, t1) - target, band(tot, t2) - target
+    told, t = t1, t2
+    while abs(t - told) >= 1e-8:
+        told = t
+        t = (t1 * abs(f2) + t2 * abs(f1)) / (abs(f1) + abs(f2))
+        f = band(tot, t) - target
+        if (f > 0 > f1) or (f < 0 < f1):
+            t2, f2 = t, f
+        else:
+            t1, f1 = t, f
+    return tot, t
+
+
+def uvb_background(redshift=3.0, uvb_coefficient=1.0, nfreq=400, freqdel=0.02):
+    """uvb[3], beta[3][3] = [group][beta24, beta26, beta25], ksi24[3], ksi25[1], ksi26[2], alpha[3]."""
+    z = redshift
+    stellar99 = 1.0 / (1.0 + (7.0 / (1.0 + z)) ** 4) * np.exp(-((z / 4.0) ** 3))
+    pascal02 = 0.0188 * np.exp(-((z - 0.5) ** 2) / (1.0 + 0.0625 * (z + 2.09) ** 2.075)) * (1.0 + z) ** 3.35
+    step = 0.5 * (np.tanh((z - 4.2) * 1.5) + 1.0)
+    stellar02 = (1.0 - step) * stellar99 + step * pascal02
+    quasar02 = 10.0 / (1.0 + (7.0 / (1.0 + z)) ** 4) * np.exp(-((z / 2.5) ** 3))
+    gaussian = np.exp(-(((z - 4.5) / 2.0) ** 2)) * 0.3
+    newQ = gaussian * stellar02 + (1.0 - gaussian) * quasar02
+    newS = (1.0 - gaussian) * stellar02 + gaussian * quasar02
+    step = 0.5 * (np.tanh((z - 14.0) * 0.5) + 1.0)
+    newS = (1.0 - step) * newS
+    aQ, aS = 1.8, 5.0
+    s1 = newS * 1e-21 * uvb_coefficient
+    s2 = s1 * (NU2 / NU1) ** (-aS)
+    s3 = s2 * (NU3 / NU2) ** (-aS)
+    q1 = newQ * 1e-21 * uvb_coefficient
+    q2 = q1 * (NU2 / NU1) ** (-aQ)
+    q3 = q2 * (NU3 / NU2) ** (-aQ)
+    u1, al1 = _power_index(s1, aS, q1, aQ, NU1, NU2, True)
+    u2, al2 = _power_index(s2, aS, q2, aQ, NU2, NU3, True)
+    u3, al3 = _power_index(s3, aS, q3, aQ, NU3, NU3, False)
+    alpha = [al1, al2, al3]
+    nu = 10.0 ** (np.arange(nfreq) * freqdel)
+    s24, s25, s26 = _sigmas(nu)
+    dnu = np.diff(nu, prepend=nu[0])
+    bands = [(NU1, NU2), (NU2, NU3), (NU3, np.inf)]
+    thr = [NU1, NU2, NU3]
+    beta = np.zeros((3, 3))
+    ksi = np.zeros((3, 3))  # [group][24, 26, 25]
+    for g, (lo, hi) in enumerate(bands):
+        m = (nu >= lo) & (nu <= hi)
+        m[0] = False
+        dt = (nu[m] / thr[g]) ** (-alpha[g]) * dnu[m]
+        doe = dt * EV_TO_HZ / (nu[m] * EV_TO_ERG)
+        for c, sg in enumerate((s24, s26, s25)):
+            beta[g, c] = np.sum(dt * sg[m])
+            ksi[g, c] = np.sum(doe * sg[m])
+    shape = [(1.0 - (NU2 / NU1) ** (1.0 - al1)) / (al1 - 1.0), (1.0 - (NU3 / NU2) ** (1.0 - al2)) / (al2 - 1.0),
+             1.0 / (al3 - 1.0)]
+    for g in range(3):
+        beta[g] /= shape[g] * thr[g]
+    return dict(uvb=np.array([u1, u2, u3]), beta=beta, alpha=np.array(alpha),
+                ksi24=ksi[:, 0].copy(), ksi25=np.array([ksi[2, 2]]), ksi26=np.array([ksi[1, 1], ksi[2, 1]]))
+
+
+# ------------------------------------------------------------------------------------------------------
+# grids
+# ------------------------------------------------------------------------------------------------------
+def nested_leaves(n, refine, max_level):
+    """Leaves of an octree over an n^3 base grid in reference leaf order.
+
+    refine(level, x, y, z, size) -> bool mask, with x, y, z the cell CENTRES in box units [0,1) and `size` the cell
+    edge; a cell for which it is true (and level < max_level) is replaced by its 8 children.
+    Returns level[int8], and the leaf centres cx, cy, cz.
+    """
+    ix, iy, iz = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    cur = (ix.ravel().astype(np.int64), iy.ravel().astype(np.int64), iz.ravel().astype(np.int64))
+    done = []
+    for lvl in range(max_level + 1):
+        x, y, z = cur
+        size = 1.0 / (n << lvl)
+        if lvl < max_level and x.size:
+            m = np.asarray(refine(lvl, (x + 0.5) * size, (y + 0.5) * size, (z + 0.5) * size, size), dtype=bool)
+        else:
+            m = np.zeros(x.size, dtype=bool)
+        done.append((lvl, x[~m], y[~m], z[~m]))
+        px, py, pz = x[m], y[m], z[m]
+        off = np.arange(8)
+        cur = ((2 * px[:, None] + (off >> 2)).ravel(), (2 * py[:, None] + ((off >> 1) & 1)).ravel(),
+               (2 * pz[:, None] + (off & 1)).ravel())
+    keys, lv, cx, cy, cz = [], [], [], [], []
+    for lvl, x, y, z in done:
+        if x.size == 0:
+            continue
+        bx, by, bz = x >> lvl, y >> lvl, z >> lvl
+        key = (bx * n + by) * n + bz
+        for d in range(lvl - 1, -1, -1):
+            key = (key << 3) | ((((x >> d) & 1) << 2) | (((y >> d) & 1) << 1) | ((z >> d) & 1))
+        key = key << (3 * (max_level - lvl))
+        size = 1.0 / (n << lvl)
+        keys.append(key); lv.append(np.full(x.size, lvl, dtype=np.int8))
+        cx.append((x + 0.5) * size); cy.append((y + 0.5) * size); cz.append((z + 0.5) * size)
+    keys = np.concatenate(keys)
+    order = np.argsort(keys, kind="stable")
+    cat = lambda a: np.concatenate(a)[order]
+    return cat(lv), cat(cx), cat(cy), cat(cz)
+
+
+def species_from_density(nH, xneu):
+    """HI, HeI, HeII, rho as the reference initialises a leaf (equiSources.f90:1935-1944)."""
+    rho = nH * MP / PSI
+    HI = nH * xneu
+    HeI = (1.0 - PSI) * rho / MHE
+    return HI, HeI, np.zeros_like(HI), rho
+
+
+def uniform_grid(n, seed=1, box_kpc=100.0, tau_lo=1e-3, tau_hi=20.0, beta24=2.0e-18, helium=True):
+    """Config-2/4 style uniform grid: lognormal density (sigma_ln = 1) times a neutral fraction, rescaled so that the
+    group-1 optical depth of one cell spans [tau_lo, tau_hi] (per-segment tau then lies in ~[1e-5, 30])."""
+    rng = np.random.default_rng(seed)
+    N = n ** 3
+    box = box_kpc * KPC
+    cell = box / n
+    ln_tau = rng.uniform(np.log(tau_lo), np.log(tau_hi), N)
+    HI = np.exp(ln_tau) / (beta24 * cell)
+    nH = HI / 10.0 ** rng.uniform(-4.0, 0.0, N)  # implied total hydrogen density, neutral fraction 1e-4..1
+    rho = nH * MP / PSI
+    if helium:
+        nHe = (1.0 - PSI) * rho / MHE
+        f1 = rng.uniform(0.0, 1.0, N)
+        HeI = nHe * f1 * (HI / nH)
+        HeII = nHe * (1.0 - f1) * rng.uniform(0.0, 1.0, N) * (HI / nH)
+    else:
+        HeI = np.zeros(N)
+        HeII = np.zeros(N)
+    return dict(nx=n, level=np.zeros(N, dtype=np.int8), HI=HI, HeI=HeI, HeII=HeII, rho=rho,
+                abun2=np.full(N, 0.02), box_size=box)
+
+
+def nested_grid(n, max_level, refine, seed=1, box_kpc=100.0, tau_lo=1e-3, tau_hi=20.0, beta24=2.0e-18):
+    """AMR grid (configs 3 and 5 style): same per-cell optical-depth distribution, measured per base-cell size
+    divided by 2^level so that refined cells are not optically thinner on average."""
+    level, cx, cy, cz = nested_leaves(n, refine, max_level)
+    rng = np.random.default_rng(seed)
+    N = level.size
+    box = box_kpc * KPC
+    cell = box / n / (1 << level.astype(np.int64))
+    HI = np.exp(rng.uniform(np.log(tau_lo), np.log(tau_hi), N)) / (beta24 * cell)
+    nH = HI / 10.0 ** rng.uniform(-4.0, 0.0, N)
+    rho = nH * MP / PSI
+    nHe = (1.0 - PSI) * rho / MHE
+    f1 = rng.uniform(0.0, 1.0, N)
+    HeI = nHe * f1 * (HI / nH)
+    HeII = nHe * (1.0 - f1) * rng.uniform(0.0, 1.0, N) * (HI / nH)
+    abun2 = 10.0 ** rng.uniform(np.log10(4e-4), np.log10(5e-2), N)
+    return dict(nx=n, level=level, HI=HI, HeI=HeI, HeII=HeII, rho=rho, abun2=abun2, box_size=box,
+                centres=(cx, cy, cz))
+
+
+def central_box_refine(lo, hi, levels=1):
+    """refine predicate: cells whose centre lies in [lo, hi)^3 (box units) down to `levels` levels"""
+    def f(level, x, y, z, size):
+        return (level < levels) & (x >= lo) & (x < hi) & (y >= lo) & (y < hi) & (z >= lo) & (z < hi)
+    return f
+
+
+def disc_refine(max_level, r0=0.28, h0=0.06):
+    """refine predicate for a synthetic exponential disc (config 5): deeper levels closer to the mid-plane/centre"""
+    def f(level, x, y, z, size):
+        R = np.sqrt((x - 0.5) ** 2 + (y - 0.5) ** 2)
+        s = 0.5 ** level
+        return (level < max_level) & (R < r0 * s + size) & (np.abs(z - 0.5) < h0 * s + size)
+    return f
