@@ -56,7 +56,7 @@ const char* rtb200_status_string(int status);
 int rtb200_create(int device, rtb200_ctx** ctx);
 int rtb200_destroy(rtb200_ctx* ctx);
 int rtb200_set_math(rtb200_ctx* ctx, int math_mode);
-/* launch tuning knobs ("tile_y", "slots", "graph", "l2_mb"); results do not depend on them */
+/* launch tuning knobs ("slots", "graph", "dense"); results do not depend on them */
 int rtb200_set_tuning(rtb200_ctx* ctx, const char* key, double value);
 /* status raised by a device-side guard during an asynchronous (*_device) call since the last query; clears it */
 int rtb200_device_error(rtb200_ctx* ctx);
@@ -107,9 +107,11 @@ int rtb200_patterns(int nAngularLevel, int64_t iray, int nx, double* out);
  * (transportRoutinesModule.f90:264-418) */
 int rtb200_neighbours(rtb200_ctx* ctx, int nAngularLevel, int64_t iray, int32_t* nb);
 
-/* timing of the last rtb200_diffuse* call: milliseconds of device time between CUDA events on the launch stream,
- * number of kernel launches issued, and algorithmic bytes (72 B per leaf per direction). */
-int rtb200_last_stats(rtb200_ctx* ctx, double* device_ms, int64_t* launches, double* algorithmic_bytes);
+/* timing of the last rtb200_diffuse* call, from CUDA events on the launch stream: device milliseconds of the whole
+ * call (opacities + sweep + merge) and of the sweep kernels alone, kernel launches issued (all / sweep kernel), and
+ * the algorithmic bytes of the call (72 B per leaf per direction). */
+int rtb200_last_stats(rtb200_ctx* ctx, double* device_ms, double* sweep_ms, int64_t* launches,
+                      int64_t* sweep_launches, double* algorithmic_bytes);
 
 #ifdef __cplusplus
 }

@@ -144,6 +144,7 @@ static int run_diffuse(Context& c, int nAngularLevel, const double* uvb, const d
   if (nseg) *nseg = ns;
   c.lastAlgBytes = 72.0 * (double)c.nleaf * (double)dirs.size();
   c.statsPending = true;
+  c.sweepTimed = c.uniform && !dirs.empty();
   return RTB200_OK;
 }
 
@@ -203,9 +204,12 @@ int rtb200_create(int device, rtb200_ctx** out) {
   RTB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   RTB_CUDA(cudaEventCreate(&c.evStart));
   RTB_CUDA(cudaEventCreate(&c.evStop));
+  RTB_CUDA(cudaEventCreate(&c.evSweep0));
+  RTB_CUDA(cudaEventCreate(&c.evSweep1));
+  RTB_CUDA(cudaEventCreateWithFlags(&c.evFork, cudaEventDisableTiming));
   RTB_CUDA(cudaMalloc((void**)&c.dErr, 64));
   RTB_CUDA(cudaMemset(c.dErr, 0, 64));
-  if (const char* v = getenv("RTB200_TILE_Y")) c.tune.tileY = atoi(v);
+  if (const char* v = getenv("RTB200_DENSE")) c.tune.minBlocks = atoi(v);
   if (const char* v = getenv("RTB200_SLOTS")) c.tune.slots = atoi(v);
   if (const char* v = getenv("RTB200_GRAPH")) c.tune.useGraph = atoi(v);
   if (const char* v = getenv("RTB200_L2_MB")) c.tune.l2BudgetMB = atof(v);
@@ -219,10 +223,15 @@ int rtb200_destroy(rtb200_ctx* h) {
   cudaSetDevice(c.device);
   cudaDeviceSynchronize();
   free_grid(c);
-  cudaFree(c.dAcc); cudaFree(c.dPlanes); cudaFree(c.dTasks); cudaFree(c.dPats); cudaFree(c.dAmrScratch); cudaFree(c.dErr);
+  cudaFree(c.dAcc); cudaFree(c.dPlanes); cudaFree(c.dAmrScratch); cudaFree(c.dErr);
   if (c.hPinned) cudaFreeHost(c.hPinned);
   if (c.evStart) cudaEventDestroy(c.evStart);
   if (c.evStop) cudaEventDestroy(c.evStop);
+  if (c.evSweep0) cudaEventDestroy(c.evSweep0);
+  if (c.evSweep1) cudaEventDestroy(c.evSweep1);
+  if (c.evFork) cudaEventDestroy(c.evFork);
+  for (auto e : c.chainEvents) cudaEventDestroy(e);
+  for (auto st : c.chainStreams) cudaStreamDestroy(st);
   if (c.stream) cudaStreamDestroy(c.stream);
   delete h;
   return RTB200_OK;
@@ -239,7 +248,7 @@ int rtb200_set_tuning(rtb200_ctx* h, const char* key, double value) {
   if (!h || !key) return RTB200_ERR_ARG;
   Context& c = h->c;
   std::string k(key);
-  if (k == "tile_y") c.tune.tileY = (int)value;
+  if (k == "dense") c.tune.minBlocks = (int)value;
   else if (k == "slots") c.tune.slots = (int)value;
   else if (k == "graph") c.tune.useGraph = (int)value;
   else if (k == "l2_mb") c.tune.l2BudgetMB = value;
@@ -369,7 +378,8 @@ int rtb200_neighbours(rtb200_ctx* h, int nAngularLevel, int64_t iray, int32_t* n
   return amr_neighbours(h->c, d, nb);
 }
 
-int rtb200_last_stats(rtb200_ctx* h, double* ms, int64_t* launches, double* algBytes) {
+int rtb200_last_stats(rtb200_ctx* h, double* ms, double* sweepMs, int64_t* launches, int64_t* sweepLaunches,
+                      double* algBytes) {
   if (!h) return RTB200_ERR_ARG;
   Context& c = h->c;
   if (c.statsPending) {
@@ -378,9 +388,16 @@ int rtb200_last_stats(rtb200_ctx* h, double* ms, int64_t* launches, double* algB
     float f = 0;
     RTB_CUDA(cudaEventElapsedTime(&f, c.evStart, c.evStop));
     c.lastMs = f;
+    c.lastSweepMs = 0;
+    if (c.sweepTimed) {
+      RTB_CUDA(cudaEventElapsedTime(&f, c.evSweep0, c.evSweep1));
+      c.lastSweepMs = f;
+    }
     c.statsPending = false;
   }
   if (ms) *ms = c.lastMs;
+  if (sweepMs) *sweepMs = c.lastSweepMs;
+  if (sweepLaunches) *sweepLaunches = c.lastSweepLaunches;
   if (launches) *launches = c.lastLaunches;
   if (algBytes) *algBytes = c.lastAlgBytes;
   return RTB200_OK;

@@ -46,118 +46,154 @@ int launch_compute_opacities(Context& c, const double* beta, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// one layer step of up to gridDim.z zones
+// one layer step of one zone
+//
+// thread = one cell of the layer; it loops over the zone's directions, keeping kappa (own cell and the three
+// upstream neighbours of the layer) and the J sum in registers.  A segment fed by a same-layer neighbour needs that
+// neighbour's outgoing intensity, which is a pure function of the previous layer's top-exit plane and of kappa:
+// the thread RECOMPUTES it (one or two extra exponentials, bit-identical to what the neighbour's own thread
+// computes) instead of waiting for it.  Threads are independent: no shared memory, no halo, no barrier.
+// The per-step tables travel as a __grid_constant__ kernel parameter, i.e. they are read from the constant bank.
 // ---------------------------------------------------------------------------------------------------------
-template <int TY, bool FAITHFUL>
-__global__ void __launch_bounds__(32 * TY)
-sweep_layer_kernel(const UniTask* __restrict__ tasks, int taskBase, int step, int n, const LayerSeg* __restrict__ pats,
-                   const double* __restrict__ kappa, int64_t N, double u0, double u1, double u2,
-                   const double* __restrict__ planeIn, double* __restrict__ planeOut) {
-  __shared__ double sm[2][3][TY][33];
-  const UniTask& T = tasks[taskBase + blockIdx.z];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int a = blockIdx.x * 31 - 1 + tx;        // coordinate along the lane axis (0-based), halo at tx == 0
-  const int b = blockIdx.y * (TY - 1) - 1 + ty;  // coordinate along the other axis, halo at ty == 0
-  const bool inDom = a >= 0 && a < n && b >= 0 && b < n;
-  const bool writer = inDom && tx >= 1 && ty >= 1;
-  const int laneIsK = T.laneIsK;
-  const int j = laneIsK ? b : a, k = laneIsK ? a : b;
-  const int64_t nn = (int64_t)n * n;
-  const int64_t pidx = (int64_t)b * n + a;
-  double kap[3] = {0., 0., 0.}, invk[3] = {0., 0., 0.};
-  bool kpos[3] = {false, false, false};
-  int64_t leaf = 0;
-  if (inDom) {
-    leaf = T.origin + step * T.si + j * T.sj + k * T.sk;
-#pragma unroll
-    for (int g = 0; g < 3; g++) {
-      kap[g] = kappa[g * N + leaf];
-      kpos[g] = kap[g] > 0.;
-      if (!FAITHFUL) invk[g] = 1.0 / kap[g];
-    }
+struct StepParams {
+  LayerSeg P[kMaxDirPerTask];
+  const double* planeIn;   // this task's planes of the previous layer  [ndir][3][n+1][n+1] (padded, see below)
+  double* planeOut;
+  double* acc;             // slot accumulator [3][N]
+  int32_t origin;          // leaf index of rotated (step, 0, 0)
+  int32_t sj, sk;
+  int32_t ndir, laneIsK, firstInSlot, n;
+};
+
+// Planes carry one extra row and column on the upstream side (index -1) that permanently hold the boundary
+// intensity, and the plane read by the first layer is filled with it: together with kappa = 0 for out-of-domain
+// neighbours (exp(-0) = 1 exactly) this makes "no neighbour -> uvb" (transportRoutinesModule.f90:594-597) fall out
+// of the same arithmetic as an interior cell, with no per-direction edge test.
+__global__ void fill_planes_kernel(double* __restrict__ planes, int64_t perGroup, int64_t total, double u0, double u1,
+                                   double u2) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int g = (int)((i / perGroup) % 3);
+    planes[i] = g == 0 ? u0 : (g == 1 ? u1 : u2);
   }
-  // upstream neighbours in shared memory: "from k-1" and "from j-1"
-  const int txm = tx > 0 ? tx - 1 : 0, tym = ty > 0 ? ty - 1 : 0;
-  const int kx = laneIsK ? txm : tx, ky = laneIsK ? ty : tym;  // cell (j, k-1)
-  const int jx = laneIsK ? tx : txm, jy = laneIsK ? tym : ty;  // cell (j-1, k)
-  const bool kEdge = (k == 0), jEdge = (j == 0);
-  const double uvb[3] = {u0, u1, u2};
-  double acc[3] = {0., 0., 0.};
-  int ring = 0;
-  for (int q = 0; q < T.ndir; q++) {
-    const int d = T.dir[q];
-    const LayerSeg P = pats[(int64_t)d * n + step];
-    const double* pin = planeIn + (int64_t)d * 3 * nn;
-    double I[3], Js[3], J2[3] = {0., 0., 0.}, J3[3] = {0., 0., 0.};
-    if (inDom) {
+}
+
+template <bool FAITHFUL>
+__device__ __forceinline__ double attenuate(double Iin, double kappa, double dpath) {
+  if (FAITHFUL) return __dmul_rn(Iin, exp(-__dmul_rn(kappa, dpath)));
+  return Iin * exp_neg_only(kappa * dpath);
+}
+
+// One direction of one cell, straight-line for a given segment count and chain order.
+//   NSEG: 1..3 segments;  SECK: second segment fed from the k-1 cell (kinds 1,2) or from the j-1 cell (kinds 3,4).
+//   k2 / k3: kappa of the cell feeding the second / third segment, kd: kappa of the diagonal cell.
+template <bool FAITHFUL, int NSEG, bool SECK>
+__device__ __forceinline__ void direction_body(const LayerSeg& P, const double (&cur)[3], const double (&up2)[3],
+                                               const double (&upD)[3], const double (&kap)[3], const double (&invk)[3],
+                                               const double (&k2)[3], const double (&k3)[3], const double (&kd)[3],
+                                               double (&I)[3], double (&acc)[3]) {
 #pragma unroll
-      for (int g = 0; g < 3; g++) {
-        double Iin = (step == 0) ? uvb[g] : pin[g * nn + pidx];
-        SegResult r = segment_update<FAITHFUL>(Iin, kap[g], P.d[0], invk[g] * P.invd[0], kpos[g]);
-        I[g] = r.Iout;
-        Js[g] = r.J;
+  for (int g = 0; g < 3; g++) {
+    SegResult r1 = segment_update<FAITHFUL>(cur[g], kap[g], P.d[0], invk[g] * P.invd[0]);
+    double Jsum = r1.J;
+    I[g] = r1.Iout;
+    if (NSEG >= 2) {
+      const double in2 = attenuate<FAITHFUL>(up2[g], k2[g], P.d[0]);     // what the upstream cell's xy segment emits
+      SegResult r2 = segment_update<FAITHFUL>(in2, kap[g], P.d[1], invk[g] * P.invd[1]);
+      I[g] = r2.Iout;
+      double J3 = 0.;
+      if (NSEG == 3) {
+        const double x = attenuate<FAITHFUL>(upD[g], kd[g], P.d[0]);     // diagonal cell's xy segment ...
+        const double in3 = attenuate<FAITHFUL>(x, k3[g], P.d[1]);        // ... through the third-upstream cell
+        SegResult r3 = segment_update<FAITHFUL>(in3, kap[g], P.d[2], invk[g] * P.invd[2]);
+        I[g] = r3.Iout;
+        J3 = r3.J;
       }
-    } else {
-      I[0] = I[1] = I[2] = 0.; Js[0] = Js[1] = Js[2] = 0.;
-    }
-    if (P.kind != 0) {  // uniform across the block
-      const bool secondFromK = P.kind <= 2;
-#pragma unroll
-      for (int g = 0; g < 3; g++) sm[ring][g][ty][tx] = I[g];
-      __syncthreads();
-      if (inDom) {
-        const bool edge = secondFromK ? kEdge : jEdge;
-        const int sx = secondFromK ? kx : jx, sy = secondFromK ? ky : jy;
-#pragma unroll
-        for (int g = 0; g < 3; g++) {
-          double Iin = edge ? uvb[g] : sm[ring][g][sy][sx];
-          SegResult r = segment_update<FAITHFUL>(Iin, kap[g], P.d[1], invk[g] * P.invd[1], kpos[g]);
-          I[g] = r.Iout;
-          J2[g] = r.J;
-        }
-      }
-      ring ^= 1;
-      if (P.kind == 2 || P.kind == 4) {
-#pragma unroll
-        for (int g = 0; g < 3; g++) sm[ring][g][ty][tx] = I[g];
-        __syncthreads();
-        if (inDom) {
-          const bool edge = secondFromK ? jEdge : kEdge;
-          const int sx = secondFromK ? jx : kx, sy = secondFromK ? jy : ky;
-#pragma unroll
-          for (int g = 0; g < 3; g++) {
-            double Iin = edge ? uvb[g] : sm[ring][g][sy][sx];
-            SegResult r = segment_update<FAITHFUL>(Iin, kap[g], P.d[2], invk[g] * P.invd[2], kpos[g]);
-            I[g] = r.Iout;
-            J3[g] = r.J;
-          }
-        }
-        ring ^= 1;
-      }
-    }
-    if (writer) {
-      double* pout = planeOut + (int64_t)d * 3 * nn;
-#pragma unroll
-      for (int g = 0; g < 3; g++) {
-        pout[g * nn + pidx] = I[g];
+      if (FAITHFUL) {
         // the reference sums the segments in the order xy, xz, yz (transportRoutinesModule.f90:698,818,941)
-        const bool yzSecond = P.kind <= 2;  // kinds 1,2: second segment is the yz ray, third the xz ray
-        double Jxz = yzSecond ? J3[g] : J2[g];
-        double Jyz = yzSecond ? J2[g] : J3[g];
-        double sum = Js[g];
-        if (P.kind >= 2) sum = __dadd_rn(sum, Jxz);                  // xz ray active: kinds 2, 3, 4
-        if (P.kind != 0 && P.kind != 3) sum = __dadd_rn(sum, Jyz);   // yz ray active: kinds 1, 2, 4
-        if (FAITHFUL) acc[g] = __dadd_rn(acc[g], __dmul_rn(__ddiv_rn(sum, (double)P.nseg), P.w));
-        else acc[g] = fma(sum, P.wn, acc[g]);
+        const double Jxz = SECK ? J3 : r2.J, Jyz = SECK ? r2.J : J3;
+        if (NSEG == 3 || !SECK) Jsum = __dadd_rn(Jsum, Jxz);
+        if (NSEG == 3 || SECK) Jsum = __dadd_rn(Jsum, Jyz);
+      } else {
+        Jsum = (Jsum + r2.J) + J3;
       }
     }
+    if (FAITHFUL) acc[g] = __dadd_rn(acc[g], __dmul_rn(__ddiv_rn(Jsum, (double)NSEG), P.w));
+    else acc[g] = fma(Jsum, P.wn, acc[g]);
   }
-  if (writer) {
+}
+
+template <bool FAITHFUL, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+sweep_cell_kernel(const __grid_constant__ StepParams sp, const double* __restrict__ kappa, int N) {
+  const int n = sp.n;
+  const int a = blockIdx.x * 32 + threadIdx.x, b = blockIdx.y * 8 + threadIdx.y;
+  if (a >= n || b >= n) return;
+  const int laneIsK = sp.laneIsK;
+  const int j = laneIsK ? b : a, k = laneIsK ? a : b;
+  const int leaf = sp.origin + j * sp.sj + k * sp.sk;
+  const int np1 = n + 1;
+  const int npl = np1 * np1;                                   // doubles per padded plane
+  const int oK = laneIsK ? -1 : -np1, oJ = laneIsK ? -np1 : -1;  // plane offsets of the (j,k-1) and (j-1,k) cells
+  const bool edgeK = (k == 0), edgeJ = (j == 0);
+  double kap[3], invk[3], kK[3], kJ[3], kD[3];
+#pragma unroll
+  for (int g = 0; g < 3; g++) {
+    const double* kg = kappa + (int64_t)g * N + leaf;
+    kap[g] = kg[0];
+    kK[g] = edgeK ? 0. : kg[-sp.sk];
+    kJ[g] = edgeJ ? 0. : kg[-sp.sj];
+    kD[g] = (edgeK || edgeJ) ? 0. : kg[-sp.sk - sp.sj];
+    if (!FAITHFUL) {
+      kap[g] = kap[g] > 0. ? kap[g] : 1e-200;  // kappa = 0 limit through the same formulas (segment_math.cuh)
+      invk[g] = 1.0 / kap[g];
+    } else {
+      invk[g] = 0.;
+    }
+  }
+  double acc[3] = {0., 0., 0.};
+  const int pidx = (b + 1) * np1 + (a + 1);
+  const double* pin = sp.planeIn + pidx;
+  double* pout = sp.planeOut + pidx;
+  const int ndir = sp.ndir;
+  double cur[3];
+#pragma unroll
+  for (int g = 0; g < 3; g++) cur[g] = pin[g * npl];
+  for (int q = 0; q < ndir; q++, pin += 3 * npl, pout += 3 * npl) {
+    const LayerSeg& P = sp.P[q];
+    const int kind = P.kind;
+    // kinds 1,2: second segment fed from k-1, third (kind 2) from j-1; kinds 3,4 the other way round
+    const int o2 = (kind <= 2) ? oK : oJ;
+    // issue every load of this direction, and the next direction's own plane values, before the arithmetic
+    double up2[3] = {0., 0., 0.}, upD[3] = {0., 0., 0.}, nxt[3] = {0., 0., 0.}, I[3];
+    if (kind != 0) {
+#pragma unroll
+      for (int g = 0; g < 3; g++) up2[g] = pin[g * npl + o2];
+      if (kind == 2 || kind == 4) {
+#pragma unroll
+        for (int g = 0; g < 3; g++) upD[g] = pin[g * npl + oK + oJ];
+      }
+    }
+    if (q + 1 < ndir) {
+#pragma unroll
+      for (int g = 0; g < 3; g++) nxt[g] = pin[(3 + g) * npl];
+    }
+    switch (kind) {  // uniform across the grid
+      case 0: direction_body<FAITHFUL, 1, true>(P, cur, up2, upD, kap, invk, kK, kJ, kD, I, acc); break;
+      case 1: direction_body<FAITHFUL, 2, true>(P, cur, up2, upD, kap, invk, kK, kJ, kD, I, acc); break;
+      case 2: direction_body<FAITHFUL, 3, true>(P, cur, up2, upD, kap, invk, kK, kJ, kD, I, acc); break;
+      case 3: direction_body<FAITHFUL, 2, false>(P, cur, up2, upD, kap, invk, kJ, kK, kD, I, acc); break;
+      default: direction_body<FAITHFUL, 3, false>(P, cur, up2, upD, kap, invk, kJ, kK, kD, I, acc); break;
+    }
 #pragma unroll
     for (int g = 0; g < 3; g++) {
-      double* p = T.acc + g * N + leaf;
-      *p = T.firstInSlot ? acc[g] : __dadd_rn(*p, acc[g]);
+      pout[g * npl] = I[g];
+      cur[g] = nxt[g];
     }
+  }
+#pragma unroll
+  for (int g = 0; g < 3; g++) {
+    double* p = sp.acc + (int64_t)g * N + leaf;
+    *p = sp.firstInSlot ? acc[g] : __dadd_rn(*p, acc[g]);
   }
 }
 
@@ -219,157 +255,188 @@ static LayerSeg make_layer_seg(const RayPattern& p, double cellSize, double weig
   return L;
 }
 
-template <int TY>
-static void launch_layer(bool faithful, dim3 grid, cudaStream_t s, const UniTask* tasks, int taskBase, int step, int n,
-                         const LayerSeg* pats, const double* kappa, int64_t N, const double* uvb, const double* pin,
-                         double* pout) {
-  dim3 block(32, TY);
-  if (faithful)
-    sweep_layer_kernel<TY, true><<<grid, block, 0, s>>>(tasks, taskBase, step, n, pats, kappa, N, uvb[0], uvb[1],
-                                                        uvb[2], pin, pout);
-  else
-    sweep_layer_kernel<TY, false><<<grid, block, 0, s>>>(tasks, taskBase, step, n, pats, kappa, N, uvb[0], uvb[1],
-                                                         uvb[2], pin, pout);
+static void launch_cells(int dense, bool faithful, dim3 grid, cudaStream_t s, const StepParams& sp, const double* kappa,
+                         int N) {
+  dim3 block(32, 8);
+  // `dense`: 0 = compiler's choice of registers (2 blocks per SM), 1 = cap for 3 blocks, 2 = cap for 4 blocks
+  if (faithful) sweep_cell_kernel<true, 2><<<grid, block, 0, s>>>(sp, kappa, N);
+  else if (dense == 1) sweep_cell_kernel<false, 3><<<grid, block, 0, s>>>(sp, kappa, N);
+  else if (dense >= 2) sweep_cell_kernel<false, 4><<<grid, block, 0, s>>>(sp, kappa, N);
+  else sweep_cell_kernel<false, 2><<<grid, block, 0, s>>>(sp, kappa, N);
 }
 
 int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std::vector<Direction>& dirs,
                     double* dJout, cudaStream_t s, int64_t* nsegOut) {
   const int n = c.nx;
-  const int64_t N = c.nleaf, nn = (int64_t)n * n;
+  const int64_t N = c.nleaf, nn = (int64_t)n * n, npl = (int64_t)(n + 1) * (n + 1);
   const int ndir = (int)dirs.size();
   const int64_t nraysTotal = 12LL << (2 * (nAngularLevel - 1));
   const double weight = (double)(1.f / (float)nraysTotal);  // equiSources.f90:1386 (single-precision division)
   const double cellSize = c.boxSize / (double)n;             // equiSources.f90:1570
 
-  // ---- plan: pattern tables, zone tasks, slot assignment.  Depends only on the grid size and the direction
-  //      list, so it is cached across the outer transport<->chemistry iterations. ----
+  // ---- plan: pattern tables and zone tasks.  Depends only on the grid size and the direction list, so it is
+  //      cached across the outer transport<->chemistry iterations. ----
   std::string planKey;
   {
     char buf[128];
-    snprintf(buf, sizeof(buf), "%d:%a:%d:%d:%d:", n, c.boxSize, nAngularLevel, c.tune.slots, (int)c.tune.l2BudgetMB);
+    snprintf(buf, sizeof(buf), "%d:%a:%d:%d:", n, c.boxSize, nAngularLevel, c.tune.slots);
     planKey = buf;
     for (const auto& d : dirs) { snprintf(buf, sizeof(buf), "%lld,", (long long)d.iray); planKey += buf; }
   }
   if (planKey != c.uniPlanKey) {
-    std::vector<LayerSeg> hp((size_t)ndir * n);
+    c.uniTasks.clear();
     std::vector<RayPattern> pat;
     int64_t nseg = 0;
-    for (int d = 0; d < ndir; d++) {
-      if (dirs[d].status) return dirs[d].status;
-      layer_patterns_level0(dirs[d].phi, dirs[d].theta, n, pat);
-      for (int i = 0; i < n; i++) {
-        if (pat[i].status) return pat[i].status;
-        hp[(size_t)d * n + i] = make_layer_seg(pat[i], cellSize, weight);
-        nseg += (int64_t)hp[(size_t)d * n + i].nseg * nn;
-      }
-    }
-    // tasks: directions grouped by zone, split into chunks of kMaxDirPerTask
-    std::vector<UniTask> tasks;
+    int planeCursor = 0;
     for (int z = 1; z <= 24; z++) {
       std::vector<int> mine;
       for (int d = 0; d < ndir; d++)
         if (dirs[d].izone == z) mine.push_back(d);
-      for (size_t o = 0; o < mine.size(); o += kMaxDirPerTask) {
-        UniTask T;
-        std::memset(&T, 0, sizeof(T));
+      if (mine.empty()) continue;
+      const int pieces = ((int)mine.size() + kMaxDirPerTask - 1) / kMaxDirPerTask;
+      size_t o = 0;
+      for (int pc = 0; pc < pieces; pc++) {
+        const size_t cnt = (mine.size() - o + (pieces - pc) - 1) / (pieces - pc);  // balanced split
+        UniTaskHost T;
         ZoneStrides zs = zone_strides(z, n);
         T.origin = zs.origin; T.si = zs.stride[0]; T.sj = zs.stride[1]; T.sk = zs.stride[2];
-        T.ndir = (int)std::min<size_t>(kMaxDirPerTask, mine.size() - o);
-        for (int q = 0; q < T.ndir; q++) T.dir[q] = mine[o + q];
+        T.ndir = (int)cnt;
+        T.planeFirst = planeCursor;
+        planeCursor += T.ndir;
         int64_t aj = T.sj < 0 ? -T.sj : T.sj, ak = T.sk < 0 ? -T.sk : T.sk;
         T.laneIsK = ak <= aj;
-        tasks.push_back(T);
+        T.seg.assign((size_t)n * kMaxDirPerTask, LayerSeg());
+        for (int q = 0; q < T.ndir; q++) {
+          const Direction& dd = dirs[mine[o + q]];
+          if (dd.status) return dd.status;
+          layer_patterns_level0(dd.phi, dd.theta, n, pat);
+          for (int i = 0; i < n; i++) {
+            if (pat[i].status) return pat[i].status;
+            LayerSeg L = make_layer_seg(pat[i], cellSize, weight);
+            T.seg[(size_t)i * kMaxDirPerTask + q] = L;
+            nseg += (int64_t)L.nseg * nn;
+          }
+        }
+        o += cnt;
+        c.uniTasks.push_back(std::move(T));
       }
     }
-    const int ntask = (int)tasks.size();
-    // heaviest first so that the tasks sharing a launch have similar cost
-    std::stable_sort(tasks.begin(), tasks.end(), [](const UniTask& x, const UniTask& y) { return x.ndir > y.ndir; });
-    // zones in flight: the planes of the in-flight zones (ping + pong) should fit the L2 budget
+    const int ntask = (int)c.uniTasks.size();
+    // slots = zones in flight, each an independent stream / graph branch with a private J accumulator;
+    // longest-processing-time-first assignment of the tasks to the slots
     int slots = c.tune.slots;
-    if (slots <= 0) {
-      double perTask = 2.0 * 8 * 3 * nn * 8.0;  // ~8 directions per zone at nAngularLevel 3
-      slots = (int)(c.tune.l2BudgetMB * 1048576.0 / perTask);
-      slots = std::max(2, std::min(slots, 24));
-    }
+    if (slots <= 0) slots = 24;
     slots = std::max(1, std::min(slots, ntask));
+    std::vector<int> order(ntask), load(slots, 0), seen(slots, 0);
+    for (int t = 0; t < ntask; t++) order[t] = t;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return c.uniTasks[x].ndir > c.uniTasks[y].ndir; });
+    for (int t : order) {
+      int best = 0;
+      for (int k = 1; k < slots; k++)
+        if (load[k] < load[best]) best = k;
+      c.uniTasks[t].slot = best;
+      load[best] += c.uniTasks[t].ndir;
+    }
+    for (int t = 0; t < ntask; t++) {  // first task of a slot (in issue order) overwrites the accumulator
+      c.uniTasks[t].firstInSlot = !seen[c.uniTasks[t].slot];
+      seen[c.uniTasks[t].slot] = 1;
+    }
     if (int st = ensure_buffer((void**)&c.dAcc, &c.accBytes, (size_t)slots * 3 * N * sizeof(double))) return st;
-    if (int st = ensure_buffer((void**)&c.dPlanes, &c.planeBytes, (size_t)2 * std::max(ndir, 1) * 3 * nn * sizeof(double))) return st;
-    if (int st = ensure_buffer(&c.dTasks, &c.taskBytes, (size_t)std::max(ntask, 1) * sizeof(UniTask))) return st;
-    if (int st = ensure_buffer(&c.dPats, &c.patBytes, std::max<size_t>(hp.size(), 1) * sizeof(LayerSeg))) return st;
-    std::vector<int> seen(slots, 0);
-    for (int t = 0; t < ntask; t++) {
-      int slot = t % slots;
-      tasks[t].acc = c.dAcc + (size_t)slot * 3 * N;
-      tasks[t].firstInSlot = !seen[slot];
-      seen[slot] = 1;
-    }
-    if (ntask) {
-      RTB_CUDA(cudaMemcpyAsync(c.dTasks, tasks.data(), (size_t)ntask * sizeof(UniTask), cudaMemcpyHostToDevice, s));
-      RTB_CUDA(cudaMemcpyAsync(c.dPats, hp.data(), hp.size() * sizeof(LayerSeg), cudaMemcpyHostToDevice, s));
-      RTB_CUDA(cudaStreamSynchronize(s));  // pageable sources go out of scope below
-    }
+    if (int st = ensure_buffer((void**)&c.dPlanes, &c.planeBytes, (size_t)2 * std::max(ndir, 1) * 3 * npl * sizeof(double))) return st;
     c.uniPlanKey = planKey;
-    c.uniNtask = ntask;
     c.uniSlots = slots;
     c.uniNseg = nseg;
     if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
   }
-  const int ntask = c.uniNtask, slots = c.uniSlots;
+  const int ntask = (int)c.uniTasks.size(), slots = c.uniSlots;
   if (nsegOut) *nsegOut = c.uniNseg;
   if (ntask == 0) {
     RTB_CUDA(cudaMemsetAsync(dJout, 0, 3 * N * sizeof(double), s));
+    c.lastSweepLaunches = 0;
+    c.lastLaunches = 1;
     return RTB200_OK;
   }
 
-  const int TY = c.tune.tileY == 8 ? 8 : 16;
-  dim3 grid((n + 30) / 31, (n + TY - 2) / (TY - 1), 1);
+  dim3 grid((n + 31) / 32, (n + 7) / 8, 1);
   double* planeA = c.dPlanes;
-  double* planeB = c.dPlanes + (size_t)ndir * 3 * nn;
+  double* planeB = c.dPlanes + (size_t)ndir * 3 * npl;
   const bool faithful = c.mathMode == RTB200_MATH_FAITHFUL;
-  int64_t launches = 0;
+  while ((int)c.chainStreams.size() < slots) {
+    cudaStream_t cs;
+    RTB_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    cudaEvent_t ce;
+    RTB_CUDA(cudaEventCreateWithFlags(&ce, cudaEventDisableTiming));
+    c.chainStreams.push_back(cs);
+    c.chainEvents.push_back(ce);
+  }
+  const int64_t launches = (int64_t)ntask * n + 1;
 
+  // Every task (zone) is a chain of n layer steps; the tasks of one slot run back to back because they share the
+  // slot's J accumulator.  Each slot is an independent stream (a parallel branch of the captured graph), so the
+  // hardware block scheduler balances the zones and there is no device-wide barrier between layers.
   auto issue = [&](cudaStream_t st) -> int {
-    for (int base = 0; base < ntask; base += slots) {
-      grid.z = std::min(slots, ntask - base);
-      for (int step = 0; step < n; step++) {
-        const double* pin = (step & 1) ? planeA : planeB;
-        double* pout = (step & 1) ? planeB : planeA;
-        switch (TY) {
-          case 8: launch_layer<8>(faithful, grid, st, (const UniTask*)c.dTasks, base, step, n, (const LayerSeg*)c.dPats, c.dKappa, N, uvb, pin, pout); break;
-          default: launch_layer<16>(faithful, grid, st, (const UniTask*)c.dTasks, base, step, n, (const LayerSeg*)c.dPats, c.dKappa, N, uvb, pin, pout); break;
+    {  // both plane buffers start as "boundary intensity everywhere": first-layer input and the permanent pads
+      const int64_t total = (int64_t)2 * ndir * 3 * npl;
+      int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)c.smCount * 16);
+      fill_planes_kernel<<<blocks, 256, 0, st>>>(c.dPlanes, npl, total, uvb[0], uvb[1], uvb[2]);
+    }
+    RTB_CUDA(cudaEventRecord(c.evFork, st));
+    for (int k = 0; k < slots; k++) {
+      cudaStream_t cs = slots > 1 ? c.chainStreams[k] : st;
+      if (slots > 1) RTB_CUDA(cudaStreamWaitEvent(cs, c.evFork, 0));
+      for (int t = 0; t < ntask; t++) {
+        const UniTaskHost& T = c.uniTasks[t];
+        if (T.slot != k) continue;
+        StepParams sp;
+        sp.acc = c.dAcc + (size_t)k * 3 * N;
+        sp.sj = (int32_t)T.sj; sp.sk = (int32_t)T.sk;
+        sp.ndir = T.ndir; sp.laneIsK = T.laneIsK; sp.firstInSlot = T.firstInSlot; sp.n = n;
+        for (int step = 0; step < n; step++) {
+          std::memcpy(sp.P, &T.seg[(size_t)step * kMaxDirPerTask], sizeof(sp.P));
+          sp.planeIn = ((step & 1) ? planeA : planeB) + (size_t)T.planeFirst * 3 * npl;
+          sp.planeOut = ((step & 1) ? planeB : planeA) + (size_t)T.planeFirst * 3 * npl;
+          sp.origin = (int32_t)(T.origin + step * T.si);
+          launch_cells(c.tune.minBlocks, faithful, grid, cs, sp, c.dKappa, (int)N);
         }
-        launches++;
+      }
+      if (slots > 1) {
+        RTB_CUDA(cudaEventRecord(c.chainEvents[k], cs));
+        RTB_CUDA(cudaStreamWaitEvent(st, c.chainEvents[k], 0));
       }
     }
-    int blocks = std::min<int64_t>((3 * N + 255) / 256, (int64_t)c.smCount * 16);
-    merge_slots_kernel<<<blocks, 256, 0, st>>>(c.dAcc, slots, 3 * N, dJout);
-    launches++;
     return RTB200_OK;
   };
-
+  RTB_CUDA(cudaEventRecord(c.evSweep0, s));
   if (c.tune.useGraph) {
-    // The launch sequence depends only on (n, ntask, slots, TY, mode, buffers): capture once, replay afterwards.
+    // The launch sequence depends only on the plan, the mode and the buffers: capture once, replay afterwards.
     char key[256];
-    snprintf(key, sizeof(key), "u:%d:%d:%d:%d:%d:%p:%p:%p:%p:%p:%g:%g:%g", n, ntask, slots, TY, (int)faithful,
-             (void*)c.dAcc, (void*)c.dPlanes, c.dTasks, c.dPats, (void*)dJout, uvb[0], uvb[1], uvb[2]);
+    snprintf(key, sizeof(key), "u:%d:%d:%d:%d:%p:%p:%p:%a:%a:%a", n, ntask, slots, (int)faithful * 8 + c.tune.minBlocks,
+             (void*)c.dAcc, (void*)c.dPlanes, (void*)c.dKappa, uvb[0], uvb[1], uvb[2]);
     if (!c.graphExec || c.graphKey != key) {
       if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
       cudaGraph_t graph;
-      RTB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-      issue(s);
-      RTB_CUDA(cudaStreamEndCapture(s, &graph));
+      // capture on the internal stream (the caller's stream may be the legacy default stream, which cannot capture)
+      RTB_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+      int ist = issue(c.stream);
+      cudaError_t ce = cudaStreamEndCapture(c.stream, &graph);
+      if (ist) return ist;
+      RTB_CUDA(ce);
       RTB_CUDA(cudaGraphInstantiate(&c.graphExec, graph, 0));
       cudaGraphDestroy(graph);
       c.graphKey = key;
-    } else {
-      launches = (int64_t)((ntask + slots - 1) / slots) * n + 1;
     }
     RTB_CUDA(cudaGraphLaunch(c.graphExec, s));
   } else {
-    issue(s);
+    if (int ist = issue(s)) return ist;
+  }
+  RTB_CUDA(cudaEventRecord(c.evSweep1, s));
+  {
+    int blocks = std::min<int64_t>((3 * N + 255) / 256, (int64_t)c.smCount * 16);
+    merge_slots_kernel<<<blocks, 256, 0, s>>>(c.dAcc, slots, 3 * N, dJout);
   }
   RTB_CUDA(cudaGetLastError());
-  c.lastLaunches = launches + 1;  // + compute_opacities
+  c.lastSweepLaunches = launches;
+  c.lastLaunches = launches + 2;  // + compute_opacities + merge
   return RTB200_OK;
 }
 

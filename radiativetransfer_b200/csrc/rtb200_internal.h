@@ -43,24 +43,24 @@ struct LayerSeg {
 };
 static_assert(sizeof(LayerSeg) == 80, "LayerSeg layout");
 
-constexpr int kMaxDirPerTask = 16;
+constexpr int kMaxDirPerTask = 8;
 
-// One task = the directions of one zone (same index rotation), swept together layer by layer so that kappa is
-// read once and J is accumulated in registers across the directions.
-struct UniTask {
-  int64_t origin, si, sj, sk;  // leaf index = origin + i*si + j*sj + k*sk (0-based rotated indices)
-  double* acc;                 // slot accumulator [3][N] this task adds into
-  int32_t ndir;
-  int32_t laneIsK;             // 1: threadIdx.x runs along rotated k, 0: along rotated j
-  int32_t firstInSlot;         // 1: overwrite the accumulator instead of adding
-  int32_t pad;
-  int32_t dir[kMaxDirPerTask]; // local direction index (row of the LayerSeg table and of the planes)
+// One task = up to kMaxDirPerTask directions of one zone (same index rotation), swept together layer by layer so
+// that kappa is read once and J is accumulated in registers across the directions.
+struct UniTaskHost {
+  int64_t origin = 0, si = 0, sj = 0, sk = 0;  // leaf index = origin + i*si + j*sj + k*sk (0-based rotated indices)
+  int ndir = 0;
+  int laneIsK = 1;       // 1: threadIdx.x runs along rotated k, 0: along rotated j
+  int slot = 0;          // J accumulator / stream this task uses
+  int firstInSlot = 0;   // 1: overwrite the accumulator instead of adding
+  int planeFirst = 0;    // index of the task's first direction in the plane buffers
+  std::vector<LayerSeg> seg;  // [n layers][kMaxDirPerTask]
 };
 
 struct Tuning {
-  int tileY = 16;        // block = 32 x tileY threads
-  int slots = 0;         // zones swept concurrently (0 = choose from the L2 budget)
+  int slots = 0;         // zones swept concurrently (independent streams), each with its own J accumulator (0 = 24)
   int useGraph = 1;
+  int minBlocks = 0;     // 1: cap the sweep kernel's registers for 3 blocks per SM instead of 2
   double l2BudgetMB = 96.0;
 };
 
@@ -80,7 +80,9 @@ struct Context {
   int mathMode = RTB200_MATH_FAST;
   Tuning tune;
   cudaStream_t stream = nullptr;  // internal stream for host-buffer calls
-  cudaEvent_t evStart = nullptr, evStop = nullptr;
+  cudaEvent_t evStart = nullptr, evStop = nullptr, evSweep0 = nullptr, evSweep1 = nullptr, evFork = nullptr;
+  std::vector<cudaStream_t> chainStreams;
+  std::vector<cudaEvent_t> chainEvents;
   int smCount = 148;
   size_t l2Bytes = 0;
 
@@ -106,10 +108,6 @@ struct Context {
   size_t accBytes = 0;
   double* dPlanes = nullptr;   // ping-pong top-exit planes
   size_t planeBytes = 0;
-  void* dTasks = nullptr;
-  size_t taskBytes = 0;
-  void* dPats = nullptr;
-  size_t patBytes = 0;
   void* dAmrScratch = nullptr;
   size_t amrScratchBytes = 0;
   int32_t* dErr = nullptr;     // device error flag
@@ -121,13 +119,15 @@ struct Context {
   std::string graphKey;
   // cached plan of the uniform sweep (pattern tables, zone tasks): valid while uniPlanKey matches
   std::string uniPlanKey;
-  int uniNtask = 0, uniSlots = 0;
+  int uniSlots = 0;
+  std::vector<UniTaskHost> uniTasks;
   int64_t uniNseg = 0;
   std::string amrPlanKey;
-  bool statsPending = false;
+  bool statsPending = false, sweepTimed = false;
 
   // stats of the last call
-  double lastMs = 0;
+  double lastMs = 0, lastSweepMs = 0;
+  int64_t lastSweepLaunches = 0;
   int64_t lastLaunches = 0;
   double lastAlgBytes = 0;
 };

@@ -119,6 +119,8 @@ class Transport:
         return nb
 
     def last_stats(self):
-        ms, n, b = C.c_double(0), C.c_int64(0), C.c_double(0)
-        _lib.check(self.L.rtb200_last_stats(self.h, C.byref(ms), C.byref(n), C.byref(b)), "rtb200_last_stats")
-        return dict(device_ms=ms.value, launches=n.value, algorithmic_bytes=b.value)
+        ms, sms, n, sn, b = C.c_double(0), C.c_double(0), C.c_int64(0), C.c_int64(0), C.c_double(0)
+        _lib.check(self.L.rtb200_last_stats(self.h, C.byref(ms), C.byref(sms), C.byref(n), C.byref(sn), C.byref(b)),
+                   "rtb200_last_stats")
+        return dict(device_ms=ms.value, sweep_ms=sms.value, launches=n.value, sweep_launches=sn.value,
+                    algorithmic_bytes=b.value)
