@@ -39,7 +39,8 @@ struct LayerSeg {
   double w;        // weight          (faithful mode divides by nseg first, transportRoutinesModule.f90:953)
   int32_t kind;
   int32_t nseg;
-  int32_t pad[2];
+  int32_t thin;    // an active segment is shorter than 1e-2 cell: evaluate this layer with the reference's operation sequence
+  int32_t pad;
 };
 static_assert(sizeof(LayerSeg) == 80, "LayerSeg layout");
 
@@ -60,7 +61,8 @@ struct UniTaskHost {
 struct Tuning {
   int slots = 0;         // zones swept concurrently (independent streams), each with its own J accumulator (0 = 24)
   int useGraph = 1;
-  int minBlocks = 0;     // 1: cap the sweep kernel's registers for 3 blocks per SM instead of 2
+  int minBlocks = 2;     // 0: compiler's register choice (2 blocks per SM); 1: cap for 3 blocks; 2: cap for 4 blocks
+  int expVariant = 0;    // exp(-tau) of the fast path: 0 = polynomial, 1 = 16-entry shared-memory table
   double l2BudgetMB = 96.0;
 };
 
@@ -121,7 +123,7 @@ struct Context {
   std::string uniPlanKey;
   int uniSlots = 0;
   std::vector<UniTaskHost> uniTasks;
-  int64_t uniNseg = 0;
+  int64_t uniNseg = 0, uniLaunches = 0;
   std::string amrPlanKey;
   bool statsPending = false, sweepTimed = false;
 

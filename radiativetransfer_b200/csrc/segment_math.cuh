@@ -13,68 +13,92 @@
 
 namespace rtb {
 
-// Coefficients live in constant memory so that every DFMA takes its coefficient straight from the constant bank
-// (no register moves for 64-bit immediates; the kernel is issue-slot bound otherwise).
+// exp(-tau) = 2^(-k/16) * exp(-r),  k = round(tau * 16/ln2),  r = tau - k*ln2/16,  |r| <= ln2/32:
+// a 16-entry table of 2^(-j/16) (one row of shared memory: any set of lanes reads it without bank conflicts), an
+// exponent-field subtraction for 2^-(k>>4) and a degree-7 polynomial.  13-15 FP64 instructions instead of ~20 for a
+// table-free evaluation; the sweep is bound by the FP64 pipe, so this is where its time goes.
+// Constants sit in constant memory so that the DFMAs read them from the constant bank / uniform registers.
 static __constant__ double kExpC[16] = {
-    2.08767569878680989792e-09,  // 1/12!
-    2.50521083854417187751e-08,  // 1/11!
-    2.75573192239858906526e-07,  // 1/10!
-    2.75573192239858906526e-06,  // 1/9!
-    2.48015873015873015873e-05,  // 1/8!
-    1.98412698412698412698e-04,  // 1/7!
-    1.38888888888888888889e-03,  // 1/6!
-    8.33333333333333333333e-03,  // 1/5!
-    4.16666666666666666667e-02,  // 1/4!
-    1.66666666666666666667e-01,  // 1/3!
-    0.5,
-    -1.4426950408889634074,      // [11] -log2(e)
-    6755399441055744.0,          // [12] 1.5 * 2^52: adding it rounds to nearest integer
-    -6.93147180369123816490e-01, // [13] -ln2 hi
-    -1.90821492927058770002e-10, // [14] -ln2 lo
-    1400.0};                     // [15] clamp: 2^(n/2) must stay a normal number
+    -1.98412698412698412698e-04,  // [0] -1/7!
+    1.38888888888888888889e-03,   // [1]  1/6!
+    -8.33333333333333333333e-03,  // [2] -1/5!
+    4.16666666666666666667e-02,   // [3]  1/4!
+    -1.66666666666666666667e-01,  // [4] -1/3!
+    0.5,                          // [5]
+    -1.0,                         // [6]
+    23.083120654223414,           // [7]  16/ln2
+    6755399441055744.0,           // [8]  1.5 * 2^52: adding it rounds to nearest integer
+    -0.0433216979727149,          // [9]  -ln2/16, high part (27 trailing zero bits: k*hi is exact)
+    -8.12281680868118e-10,        // [10] -ln2/16, low part
+    707.0,                        // [11] clamp: keeps 2^-(k>>4) * 2^(-j/16) a normal number
+    0., 0., 0., 0.};
+static __constant__ double kExpTable[16] = {
+    1.00000000000000000000e+00, 9.57603280698573700036e-01, 9.17004043204671215328e-01, 8.78126080186649726755e-01,
+    8.40896415253714502036e-01, 8.05245165974627141736e-01, 7.71105412703970372057e-01, 7.38413072969749673113e-01,
+    7.07106781186547572737e-01, 6.77127773468446325644e-01, 6.48419777325504820276e-01, 6.20928906036742001007e-01,
+    5.94603557501360513449e-01, 5.69394317378345782288e-01, 5.45253866332628844837e-01, 5.22136891213706877402e-01};
 
-// e = exp(-tau), ome = 1 - exp(-tau) for tau >= 0.  Relative error of e ~2e-16; ome is free of cancellation.
 // Straight-line code on purpose: a rare-case branch here would end the basic block and keep the compiler from
 // interleaving the (independent) exponentials of the three frequency groups and of the 1..3 segments, which is where
-// the instruction-level parallelism of the sweep comes from.
-//   2^n is applied as two factors so that results down to the subnormal range and an underflow to 0 (tau > 745)
-//   come out of the same multiplications; 1 - sc*(1 + em1) = fma(-sc, em1, 1 - sc) is exactly -em1 for n == 0.
-__device__ __forceinline__ void exp_neg(double tau, double& e, double& ome) {
-  tau = fmin(tau, kExpC[15]);                                     // beyond this exp(-tau) is 0 in fp64 anyway
-  double t = fma(tau, kExpC[11], kExpC[12]);
-  int n = __double2loint(t);
-  double fn = t - kExpC[12];
-  double r = fma(fn, kExpC[13], -tau);
-  r = fma(fn, kExpC[14], r);
-  // exp(r) - 1 - r = r^2 * q(r), |r| <= ln2/2; Taylor through r^12
+// the instruction-level parallelism of the sweep comes from.  tau is clamped at 707: exp(-tau) below 2^-1020 is
+// returned as ~2^-1020 (it only ever multiplies an intensity, and such products are far below anything physical).
+// Returns Ts = 2^(-k/16) and p = exp(-r) - 1, so that  exp(-tau) = Ts + Ts*p  and  1 - exp(-tau) = (1 - Ts) - Ts*p
+// (1 - Ts is exact, and for k == 0 the latter is exactly -p: no cancellation for small tau).
+__device__ __forceinline__ void exp_neg_parts(double tau, const double* __restrict__ T, double& Ts, double& p) {
+  tau = fmin(tau, kExpC[11]);
+  double t = fma(tau, kExpC[7], kExpC[8]);
+  int k = __double2loint(t);
+  double fn = t - kExpC[8];
+  double r = fma(fn, kExpC[9], tau);
+  r = fma(fn, kExpC[10], r);
   double q = kExpC[0];
 #pragma unroll
-  for (int i = 1; i <= 10; i++) q = fma(q, r, kExpC[i]);
-  double em1 = fma(r * r, q, r);                                  // exp(r) - 1
-  int h = n >> 1;
-  double sc1 = __hiloint2double(0x3ff00000 + (h << 20), 0);       // 2^h
-  double sc2 = __hiloint2double(0x3ff00000 + ((n - h) << 20), 0); // 2^(n-h)
-  double sc = sc1 * sc2;                                          // 2^n (0 or subnormal below 2^-1022)
-  ome = fma(-sc, em1, 1.0 - sc);
-  e = ((1.0 + em1) * sc1) * sc2;
+  for (int i = 1; i <= 6; i++) q = fma(q, r, kExpC[i]);
+  p = q * r;
+  double Tj = T[k & 15];
+  Ts = __hiloint2double(__double2hiint(Tj) - ((k >> 4) << 20), __double2loint(Tj));
 }
 
-// exp(-tau) only (upstream segments that are recomputed need no J)
-__device__ __forceinline__ double exp_neg_only(double tau) {
-  tau = fmin(tau, kExpC[15]);
-  double t = fma(tau, kExpC[11], kExpC[12]);
+// Table-free variant (T == nullptr at compile time is not needed: chosen by the EXPV template parameter):
+// exp(-tau) = 2^n * exp(r), n = round(-tau/ln2), |r| <= ln2/2, Taylor through r^12.  ~20 FP64 instructions.
+static __constant__ double kExpP[16] = {
+    2.08767569878680989792e-09, 2.50521083854417187751e-08, 2.75573192239858906526e-07, 2.75573192239858906526e-06,
+    2.48015873015873015873e-05, 1.98412698412698412698e-04, 1.38888888888888888889e-03, 8.33333333333333333333e-03,
+    4.16666666666666666667e-02, 1.66666666666666666667e-01, 0.5,
+    -1.4426950408889634074,       // [11] -log2(e)
+    6755399441055744.0,           // [12]
+    -6.93147180369123816490e-01,  // [13] -ln2 hi
+    -1.90821492927058770002e-10,  // [14] -ln2 lo
+    707.0};
+__device__ __forceinline__ void exp_neg_parts_poly(double tau, double& Ts, double& p) {
+  tau = fmin(tau, kExpP[15]);
+  double t = fma(tau, kExpP[11], kExpP[12]);
   int n = __double2loint(t);
-  double fn = t - kExpC[12];
-  double r = fma(fn, kExpC[13], -tau);
-  r = fma(fn, kExpC[14], r);
-  double q = kExpC[0];
+  double fn = t - kExpP[12];
+  double r = fma(fn, kExpP[13], -tau);
+  r = fma(fn, kExpP[14], r);
+  double q = kExpP[0];
 #pragma unroll
-  for (int i = 1; i <= 10; i++) q = fma(q, r, kExpC[i]);
-  double s = 1.0 + fma(r * r, q, r);
-  int h = n >> 1;
-  double sc1 = __hiloint2double(0x3ff00000 + (h << 20), 0);
-  double sc2 = __hiloint2double(0x3ff00000 + ((n - h) << 20), 0);
-  return (s * sc1) * sc2;
+  for (int i = 1; i <= 10; i++) q = fma(q, r, kExpP[i]);
+  p = fma(r * r, q, r);                                       // exp(r) - 1
+  Ts = __hiloint2double(0x3ff00000 + (n << 20), 0);           // 2^n
+}
+
+template <int EXPV>
+__device__ __forceinline__ void exp_neg(double tau, const double* __restrict__ T, double& e, double& ome) {
+  double Ts, p;
+  if (EXPV == 1) exp_neg_parts(tau, T, Ts, p);
+  else exp_neg_parts_poly(tau, Ts, p);
+  e = fma(Ts, p, Ts);
+  ome = fma(-Ts, p, 1.0 - Ts);
+}
+
+template <int EXPV>
+__device__ __forceinline__ double exp_neg_only(double tau, const double* __restrict__ T) {
+  double Ts, p;
+  if (EXPV == 1) exp_neg_parts(tau, T, Ts, p);
+  else exp_neg_parts_poly(tau, Ts, p);
+  return fma(Ts, p, Ts);
 }
 
 struct SegResult {
@@ -83,8 +107,9 @@ struct SegResult {
 
 // FAST mode expects kappa > 0 (callers replace an exact zero by a tiny positive number, for which every formula
 // below returns the kappa = 0 limits Iout = Iin, J = Iin) and invtau = 1 / (kappa * dpath).
-template <bool FAITHFUL>
-__device__ __forceinline__ SegResult segment_update(double Iin, double kappa, double dpath, double invtau) {
+template <bool FAITHFUL, int EXPV>
+__device__ __forceinline__ SegResult segment_update(double Iin, double kappa, double dpath, double invtau,
+                                                    const double* __restrict__ T) {
   SegResult r;
   if (FAITHFUL) {
     double tau = __dmul_rn(kappa, dpath);
@@ -94,7 +119,7 @@ __device__ __forceinline__ SegResult segment_update(double Iin, double kappa, do
     else r.J = __dmul_rn(0.5, __dadd_rn(Iin, r.Iout));
   } else {
     double tau = kappa * dpath, e, ome;
-    exp_neg(tau, e, ome);
+    exp_neg<EXPV>(tau, T, e, ome);
     r.Iout = Iin * e;
     // Iout == 0 (underflow): the reference gets (Iin - 0)/log(Iin/0) = 0.  (Where Iout is a non-zero SUBNORMAL,
     // i.e. per-segment tau of ~650-745, the reference's log sees only the few bits Iout has left; FAST mode returns

