@@ -250,6 +250,7 @@ int rtb200_set_tuning(rtb200_ctx* h, const char* key, double value) {
   std::string k(key);
   if (k == "dense") c.tune.minBlocks = (int)value;
   else if (k == "expv") c.tune.expVariant = (int)value;
+  else if (k == "lockstep") c.tune.lockstep = (int)value;
   else if (k == "slots") c.tune.slots = (int)value;
   else if (k == "graph") c.tune.useGraph = (int)value;
   else if (k == "l2_mb") c.tune.l2BudgetMB = value;

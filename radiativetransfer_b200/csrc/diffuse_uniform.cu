@@ -138,9 +138,17 @@ __device__ __forceinline__ void direction_body(const LayerSeg& P, const double (
 
 // block = 8 warps; a warp covers 31 cells of one row plus, in lane 0, the recomputed last cell of the strip to its
 // left (for strip 0 that is the pad column, which behaves as "no neighbour").
+constexpr int kMaxBatch = 40;  // tasks per launch: 40 x 728 B of parameters (the limit is 32764 B since CUDA 12.1)
+struct BatchParams {
+  StepParams t[kMaxBatch];
+};
+
+// gridDim.z tasks (zones) per launch, all at the same layer index: one launch per layer keeps the device full
+// (thousands of blocks) instead of many small concurrent kernels.
 template <bool FAITHFUL, int EXPV, int MINB>
 __global__ void __launch_bounds__(256, MINB)
-sweep_cell_kernel(const __grid_constant__ StepParams sp, const double* __restrict__ kappa, int N) {
+sweep_cell_kernel(const __grid_constant__ BatchParams bp, const double* __restrict__ kappa, int N) {
+  const StepParams& sp = bp.t[blockIdx.z];
   __shared__ double sT[16];
   if (threadIdx.y == 0 && threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
   __syncthreads();
@@ -280,15 +288,15 @@ static LayerSeg make_layer_seg(const RayPattern& p, double cellSize, double weig
   return L;
 }
 
-static void launch_cells(int dense, int expv, bool faithful, dim3 grid, cudaStream_t s, const StepParams& sp,
+static void launch_cells(int dense, int expv, bool faithful, dim3 grid, cudaStream_t s, const BatchParams& bp,
                          const double* kappa, int N) {
   dim3 block(32, 8);
   // `dense`: 0 = compiler's choice of registers (2 blocks per SM), 1 = cap for 3 blocks, 2 = cap for 4 blocks
-  if (faithful) { sweep_cell_kernel<true, 0, 2><<<grid, block, 0, s>>>(sp, kappa, N); return; }
+  if (faithful) { sweep_cell_kernel<true, 0, 2><<<grid, block, 0, s>>>(bp, kappa, N); return; }
 #define RTB_LAUNCH(E)                                                                       \
-  if (dense == 1) sweep_cell_kernel<false, E, 3><<<grid, block, 0, s>>>(sp, kappa, N);      \
-  else if (dense >= 2) sweep_cell_kernel<false, E, 4><<<grid, block, 0, s>>>(sp, kappa, N); \
-  else sweep_cell_kernel<false, E, 2><<<grid, block, 0, s>>>(sp, kappa, N)
+  if (dense == 1) sweep_cell_kernel<false, E, 3><<<grid, block, 0, s>>>(bp, kappa, N);      \
+  else if (dense >= 2) sweep_cell_kernel<false, E, 4><<<grid, block, 0, s>>>(bp, kappa, N); \
+  else sweep_cell_kernel<false, E, 2><<<grid, block, 0, s>>>(bp, kappa, N)
   if (expv == 1) { RTB_LAUNCH(1); } else { RTB_LAUNCH(0); }
 #undef RTB_LAUNCH
 }
@@ -307,7 +315,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
   std::string planKey;
   {
     char buf[128];
-    snprintf(buf, sizeof(buf), "%d:%a:%d:%d:", n, c.boxSize, nAngularLevel, c.tune.slots);
+    snprintf(buf, sizeof(buf), "%d:%a:%d:%d:%d:", n, c.boxSize, nAngularLevel, c.tune.slots, c.tune.lockstep);
     planKey = buf;
     for (const auto& d : dirs) { snprintf(buf, sizeof(buf), "%lld,", (long long)d.iray); planKey += buf; }
   }
@@ -353,17 +361,22 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
     // slots = zones in flight, each an independent stream / graph branch with a private J accumulator;
     // longest-processing-time-first assignment of the tasks to the slots
     int slots = c.tune.slots;
-    if (slots <= 0) slots = 24;
+    if (slots <= 0) slots = c.tune.lockstep ? kMaxBatch : 24;
     slots = std::max(1, std::min(slots, ntask));
     std::vector<int> order(ntask), load(slots, 0), seen(slots, 0);
     for (int t = 0; t < ntask; t++) order[t] = t;
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return c.uniTasks[x].ndir > c.uniTasks[y].ndir; });
-    for (int t : order) {
-      int best = 0;
-      for (int k = 1; k < slots; k++)
-        if (load[k] < load[best]) best = k;
-      c.uniTasks[t].slot = best;
-      load[best] += c.uniTasks[t].ndir;
+    if (c.tune.lockstep) {
+      slots = std::min(slots, kMaxBatch);
+      for (int t = 0; t < ntask; t++) c.uniTasks[t].slot = t % slots;   // batch b = tasks [b*slots, (b+1)*slots)
+    } else {
+      for (int t : order) {
+        int best = 0;
+        for (int k = 1; k < slots; k++)
+          if (load[k] < load[best]) best = k;
+        c.uniTasks[t].slot = best;
+        load[best] += c.uniTasks[t].ndir;
+      }
     }
     for (int t = 0; t < ntask; t++) {  // first task of a slot (in issue order) overwrites the accumulator
       c.uniTasks[t].firstInSlot = !seen[c.uniTasks[t].slot];
@@ -398,6 +411,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
     c.chainEvents.push_back(ce);
   }
   int64_t nLaunched = 1;
+  const bool lockstep = c.tune.lockstep != 0;
 
   // Every task (zone) is a chain of n layer steps; the tasks of one slot run back to back because they share the
   // slot's J accumulator.  Each slot is an independent stream (a parallel branch of the captured graph), so the
@@ -408,6 +422,57 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
       int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)c.smCount * 16);
       fill_planes_kernel<<<blocks, 256, 0, st>>>(c.dPlanes, npl, total, uvb[0], uvb[1], uvb[2]);
     }
+    // fill one task's parameters for one layer; returns the number of directions taken by this pass
+    auto fill = [&](StepParams& sp, const UniTaskHost& T, int step, int pass, int first) -> int {
+      sp.acc = c.dAcc + (size_t)T.slot * 3 * N;
+      sp.sj = (int32_t)T.sj; sp.sk = (int32_t)T.sk;
+      sp.laneIsK = T.laneIsK; sp.n = n;
+      sp.planeIn = ((step & 1) ? planeA : planeB) + (size_t)T.planeFirst * 3 * npl;
+      sp.planeOut = ((step & 1) ? planeB : planeA) + (size_t)T.planeFirst * 3 * npl;
+      sp.origin = (int32_t)(T.origin + step * T.si);
+      int cnt = 0;
+      for (int q = 0; q < T.ndir; q++) {
+        const LayerSeg& L = T.seg[(size_t)step * kMaxDirPerTask + q];
+        const bool thin = !faithful && L.thin;
+        if (thin != (pass == 1)) continue;
+        sp.P[cnt] = L;
+        sp.pl[cnt] = q;
+        cnt++;
+      }
+      sp.ndir = cnt;
+      sp.firstInSlot = first;
+      return cnt;
+    };
+    // A layer whose pattern has a very short segment (a corner clip, len < 1e-2 cell) is evaluated with the
+    // reference's own operation sequence even in FAST mode: there tau is tiny and the rounding noise of the
+    // reference's (Iin-Iout)/log(Iin/Iout), ~1.1e-16/tau, would otherwise show up as a parity difference.
+    // ~1.7% of the (direction, layer) pairs; they go to a second launch (pass 1) of the FAITHFUL kernel.
+    static thread_local BatchParams bp;
+    if (lockstep) {
+      // all tasks of a batch advance one layer per launch; each task of a batch has its own accumulator slot
+      for (int base = 0; base < ntask; base += slots) {
+        const int nb = std::min(slots, ntask - base);
+        std::vector<int> firstFlag(nb);
+        for (int z = 0; z < nb; z++) firstFlag[z] = c.uniTasks[base + z].firstInSlot;
+        for (int step = 0; step < n; step++) {
+          std::vector<int> fastDone(nb, 0);
+          for (int pass = 0; pass < 2; pass++) {
+            int cntZ = 0;
+            for (int z = 0; z < nb; z++) {
+              const UniTaskHost& T = c.uniTasks[base + z];
+              const int first = fastDone[z] ? 0 : firstFlag[z];
+              if (fill(bp.t[cntZ], T, step, pass, first) > 0) { cntZ++; fastDone[z] = 1; }
+            }
+            if (cntZ == 0) continue;
+            dim3 gz = grid;
+            gz.z = cntZ;
+            launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful || pass == 1, gz, st, bp, c.dKappa, (int)N);
+            nLaunched++;
+          }
+        }
+      }
+      return RTB200_OK;
+    }
     RTB_CUDA(cudaEventRecord(c.evFork, st));
     for (int k = 0; k < slots; k++) {
       cudaStream_t cs = slots > 1 ? c.chainStreams[k] : st;
@@ -415,35 +480,12 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
       for (int t = 0; t < ntask; t++) {
         const UniTaskHost& T = c.uniTasks[t];
         if (T.slot != k) continue;
-        StepParams sp;
-        sp.acc = c.dAcc + (size_t)k * 3 * N;
-        sp.sj = (int32_t)T.sj; sp.sk = (int32_t)T.sk;
-        sp.laneIsK = T.laneIsK; sp.n = n;
         for (int step = 0; step < n; step++) {
-          sp.planeIn = ((step & 1) ? planeA : planeB) + (size_t)T.planeFirst * 3 * npl;
-          sp.planeOut = ((step & 1) ? planeB : planeA) + (size_t)T.planeFirst * 3 * npl;
-          sp.origin = (int32_t)(T.origin + step * T.si);
-          // A layer whose pattern has a very short segment (a corner clip, len < 1e-2 cell) is evaluated with the
-          // reference's own operation sequence even in FAST mode: there tau is tiny and the rounding noise of the
-          // reference's (Iin-Iout)/log(Iin/Iout), ~1.1e-16/tau, would otherwise show up as a parity difference.
-          // ~1.7% of the (direction, layer) pairs; they go to a second launch of the FAITHFUL kernel.
           int first = T.firstInSlot;
           for (int pass = 0; pass < 2; pass++) {
-            const bool passFaithful = faithful || pass == 1;
-            int cnt = 0;
-            for (int q = 0; q < T.ndir; q++) {
-              const LayerSeg& L = T.seg[(size_t)step * kMaxDirPerTask + q];
-              const bool thin = !faithful && L.thin;
-              if (thin != (pass == 1)) continue;
-              sp.P[cnt] = L;
-              sp.pl[cnt] = q;
-              cnt++;
-            }
-            if (cnt == 0) continue;
-            sp.ndir = cnt;
-            sp.firstInSlot = first;
+            if (fill(bp.t[0], T, step, pass, first) == 0) continue;
             first = 0;
-            launch_cells(c.tune.minBlocks, c.tune.expVariant, passFaithful, grid, cs, sp, c.dKappa, (int)N);
+            launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful || pass == 1, grid, cs, bp, c.dKappa, (int)N);
             nLaunched++;
           }
         }
@@ -460,7 +502,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
     // The launch sequence depends only on the plan, the mode and the buffers: capture once, replay afterwards.
     char key[256];
     snprintf(key, sizeof(key), "u:%d:%d:%d:%d:%p:%p:%p:%a:%a:%a", n, ntask, slots,
-             (int)faithful * 64 + c.tune.minBlocks * 4 + c.tune.expVariant,
+             (int)faithful * 64 + c.tune.minBlocks * 4 + c.tune.expVariant + 1000 * c.tune.lockstep,
              (void*)c.dAcc, (void*)c.dPlanes, (void*)c.dKappa, uvb[0], uvb[1], uvb[2]);
     if (!c.graphExec || c.graphKey != key) {
       if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }

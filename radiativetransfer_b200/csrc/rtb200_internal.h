@@ -61,8 +61,9 @@ struct UniTaskHost {
 struct Tuning {
   int slots = 0;         // zones swept concurrently (independent streams), each with its own J accumulator (0 = 24)
   int useGraph = 1;
+  int lockstep = 1;      // 1: one launch per layer for all zones of a batch; 0: every slot an independent stream
   int minBlocks = 2;     // 0: compiler's register choice (2 blocks per SM); 1: cap for 3 blocks; 2: cap for 4 blocks
-  int expVariant = 0;    // exp(-tau) of the fast path: 0 = polynomial, 1 = 16-entry shared-memory table
+  int expVariant = 1;    // exp(-tau) of the fast path: 0 = polynomial, 1 = 16-entry shared-memory table
   double l2BudgetMB = 96.0;
 };
 
