@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named by BASELINE.json: the per-direction diffuse-radiation sweep.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torch.distributed.run)
+    python bench.py --impl reference ...                      (CPU arm: the reference algorithm on the host cores)
+
+One *step* = one full diffuse solve (all 12*4**(nAngularLevel-1) = 192 directions) over one synthetic grid:
+computeOpacities + sweep + merge [+ NCCL all-reduce of Jmean1..3 when N > 1].  Default workload: the configuration the
+metric's target is quoted on -- a 256^3 uniform grid, 192 directions (BASELINE.json configs[3], one sweep of it).
+Directions are sharded across ranks (every GPU holds the whole grid), so per-GPU work shrinks with N: "strong".
+
+Prints ONE JSON line (rank 0).  `value` = ray-cell segment updates per second with inputs resident in HBM;
+`e2e` = the same metric through the host-buffer API (H2D of HI/HeI/HeII from pinned memory, D2H of Jmean1..3) inside the
+timed region; `roofline` = algorithmic bytes (72 B per leaf per direction) of the sweep kernel launches
+over their CUDA-event time, against the measured HBM copy bandwidth; `cpu_baseline` = the CPU oracle (a port of the
+reference: the Fortran itself cannot be built here) on a bounded sample of the same workload, one core.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ray-cell segment updates/sec (diffuse sweep)"
+UNIT = "segment-updates/s"
+
+# DRAM traffic of the dominant kernel under `ncu --set full` (profiles/r01_ncu_full_sweep_cell_256.txt):
+# dram__bytes_read.sum + dram__bytes_write.sum per launch over gpu__time_duration, 256^3 workload, 1 GPU
+NCU_TRAFFIC_GBS = {"diffuse-256^3-uniform-192dir": (551.46e6 + 373.16e6) / 268.96e-6 / 1e9}
+
+WORKLOADS = {
+    # name: (n, description)
+    "diffuse-256^3-uniform-192dir": 256,
+    "diffuse-128^3-uniform-192dir": 128,
+    "diffuse-64^3-uniform-192dir": 64,
+}
+
+
+def make_inputs(n, seed=1):
+    from radiativetransfer_b200 import workloads as W
+    return W.uniform_grid(n, seed=seed), W.uvb_background(3.0)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def sample_clocks(stop, out, dev):
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(dev)],
+                               capture_output=True, text=True, timeout=5)
+            f = [x.strip() for x in r.stdout.strip().split(",")]
+            if len(f) >= 6:
+                out.append(f)
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def clocks_summary(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+    sm = sorted(float(s[0]) for s in samples if s[0].replace(".", "").isdigit())
+    mx = [float(s[1]) for s in samples if s[1].replace(".", "").isdigit()]
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [nm for i, nm in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in samples)]
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+            "samples": len(samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_oracle_sample(n, grid, bg, seconds, threads):
+    """times the CPU oracle on a bounded number of directions of the same grid; returns (updates/s, description)"""
+    from oracle import ftte_oracle as fo
+    og = fo.OracleGrid(n, grid["level"], grid["HI"], grid["HeI"], grid["HeII"], box_size=grid["box_size"])
+    # spread the sampled directions over the zones (ray numbers 0, 37, 74, ... mod 192)
+    order = (np.arange(192) * 37) % 192
+    t0 = time.perf_counter()
+    o = og.diffuse_mt(bg["uvb"], bg["beta"], order[:threads], nthreads=threads)
+    dt1 = time.perf_counter() - t0
+    assert o["status"] == 0
+    per_batch = dt1
+    nb = int(max(1, min(192 // threads - 1, seconds / per_batch - 1)))
+    rays = order[threads:threads + nb * threads]
+    if rays.size:
+        t0 = time.perf_counter()
+        o2 = og.diffuse_mt(bg["uvb"], bg["beta"], rays, nthreads=threads)
+        dt = time.perf_counter() - t0
+        assert o2["status"] == 0
+        nseg, ndirs = o2["nseg"], rays.size
+    else:
+        nseg, dt, ndirs = o["nseg"], dt1, threads
+    del og
+    return nseg / dt, f"{ndirs} of 192 directions of the same {n}^3 grid, {dt:.1f} s, {threads} thread(s)"
+
+
+def run_reference(args):
+    """CPU arm: the reference algorithm (C++ oracle port; the Fortran cannot be compiled in this image) on the host
+    cores, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = WORKLOADS[args.workload]
+    grid, bg = make_inputs(n)
+    import psutil
+    cores = os.cpu_count() or 1
+    avail = psutil.virtual_memory().available
+    per_copy = 200.0 * n ** 3 * 1.15          # bytes per private octree copy
+    threads = int(max(1, min(cores, 32, (0.5 * avail) // per_copy)))
+    if args.cpu_threads:
+        threads = args.cpu_threads
+    vals = []
+    desc = ""
+    for it in range(args.warmup + args.steps):
+        budget = max(2.0, min(20.0, 150.0 / (args.warmup + args.steps)))
+        v, desc = cpu_oracle_sample(n, grid, bg, budget, threads)
+        if it >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    nseg_full = None
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "grid": f"{n}^3 uniform", "directions": 192,
+                   "note": "each step = a bounded sample of directions of the workload, scaled per segment update"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="rtb200", choices=["rtb200", "reference"])
+    ap.add_argument("--workload", default="diffuse-256^3-uniform-192dir", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import radiativetransfer_b200 as rt
+    from radiativetransfer_b200 import sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the rtb200 path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+
+    n = WORKLOADS[args.workload]
+    grid, bg = make_inputs(n)
+    N = n ** 3
+    eng = rt.Transport(device=local)
+    eng.set_grid(n, grid["level"], grid["HI"], grid["HeI"], grid["HeII"], grid["rho"], grid["abun2"], grid["box_size"])
+    shards = sharding.shard_directions(world, n_angular_level=3, nx=n)
+    rays = shards[rank] if world > 1 else None
+    J = torch.zeros(3, N, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        nseg = eng.diffuse_device(bg["uvb"], bg["beta"], J.data_ptr(), rays=rays, stream=stream)
+        if world > 1:
+            dist.all_reduce(J)            # per-leaf Jmean1..3 summed over the ranks' direction shards (NCCL, NVLink)
+        return nseg
+
+    # ---- resident-data timing: W warm-ups, then exactly K steps between barrier + synchronize ----
+    for _ in range(W):
+        nseg_rank = step_resident()
+    barrier()
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=sample_clocks, args=(stop, samples, local), daemon=True)
+    if rank == 0:
+        th.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sweep_ms, sweep_launches, launches = 0.0, 0, 0
+    e0.record()
+    for _ in range(args.steps):
+        nseg_rank = step_resident()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    # the library's own CUDA events (same stream) bracket the sweep-kernel launches of the LAST step
+    st = eng.last_stats()
+    sweep_ms, sweep_launches, launches = st["sweep_ms"], st["sweep_launches"], st["launches"]
+    alg_bytes_rank = st["algorithmic_bytes"]
+    barrier()
+    t = torch.tensor([ms, float(nseg_rank), sweep_ms, alg_bytes_rank], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, nseg_total = float(tmax[0]), float(tsum[1])
+    else:
+        nseg_total = float(nseg_rank)
+    ms_per_step = ms / args.steps
+    value = nseg_total / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the host-buffer API: H2D of the species arrays + D2H of J inside the timed region ----
+    hHI = torch.from_numpy(grid["HI"]).pin_memory()
+    hHeI = torch.from_numpy(grid["HeI"]).pin_memory()
+    hHeII = torch.from_numpy(grid["HeII"]).pin_memory()
+    hJ = torch.empty(3, N, dtype=torch.float64).pin_memory()
+    Jd = torch.zeros(3, N, dtype=torch.float64, device=dev)
+
+    def step_e2e():
+        eng.update_species(hHI.numpy(), hHeI.numpy(), hHeII.numpy())          # H2D from pinned host memory
+        if world > 1:
+            eng.diffuse_device(bg["uvb"], bg["beta"], Jd.data_ptr(), rays=rays, stream=stream)
+            dist.all_reduce(Jd)
+            hJ.copy_(Jd, non_blocking=False)                                   # D2H of the reduced result
+        else:
+            eng.diffuse(bg["uvb"], bg["beta"], out=hJ.numpy())                 # host-pointer C-ABI call, D2H inside
+        return float(hJ[0, 0])
+
+    e2e_steps = max(1, min(args.steps, 3))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if world > 1:
+        tt = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt[0])
+    e2e_value = nseg_total / (e2e_ms * 1e-3)
+    stop.set()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        # dominant kernel: sweep_cell_kernel; algorithmic bytes of this rank's launches over their event time
+        achieved = alg_bytes_rank / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "grid": f"{n}^3 uniform, lognormal tau", "directions": 192,
+                       "n_angular_level": 3, "frequency_groups": 3, "leaves": N,
+                       "segment_updates_per_step": nseg_total, "math": "fast",
+                       "parallelism": f"directions sharded over {world} GPU(s), full grid per GPU, all-reduce of J",
+                       "l2_policy": "inputs larger than L2 (kappa + J + planes >> 126 MB)" if n >= 200 else
+                                    "working set comparable to L2; not flushed between steps"},
+            "clocks": clocks_summary(samples),
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 3 * N * 8,
+                    "d2h_bytes_per_step": 3 * N * 8},
+            "gpu_launches": int(launches) * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None,
+                         "traffic": NCU_TRAFFIC_GBS.get(args.workload) if world == 1 else None, "peak_source": peak_src,
+                         "kernel": "rtb::sweep_cell_kernel", "launches_per_step": int(sweep_launches),
+                         "algorithmic_bytes_per_step_this_rank": alg_bytes_rank, "kernel_ms_per_step": sweep_ms,
+                         "note": "72 B per leaf per direction; zones are swept with their directions fused, so DRAM "
+                                 "traffic differs from the algorithmic bytes (see profiles/)"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                v, desc = cpu_oracle_sample(n, grid, bg, args.cpu_seconds, 1)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}
+            except Exception as e:  # the checker is optional for the measurement itself
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

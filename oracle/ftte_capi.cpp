@@ -50,6 +50,12 @@ int ftte_diffuse(void* h, int nAngularLevel, const double* uvb, const double* be
   return st;
 }
 
+// multi-threaded variant over an explicit list of HEALPix pixels; J = [3][nleaf] contiguous
+int ftte_diffuse_mt(void* h, int nAngularLevel, const double* uvb, const double* beta, const int32_t* rays, int nrays,
+                    int nthreads, double* J, int64_t* nseg) {
+  return diffuseSolveThreaded(*(Grid*)h, nAngularLevel, uvb, beta, rays, nrays, nthreads, J, nseg);
+}
+
 int ftte_direction(int nAngularLevel, int64_t iray, int32_t* izone, double* phi, double* theta) {
   int iz = 0;
   int st = directionSetup(nAngularLevel, iray, iz, *phi, *theta);

@@ -64,7 +64,6 @@ enum Status {
 struct Zone {
   double Iout[3][3];      // rt%{xy,yz,xz}Ray%Iout{1,2,3}; first index: 0=xy 1=yz 2=xz  (ray id - 1)
   double rho, HI, HeI, HeII, abun2;
-  double krate24, krate25, krate26, crate24, crate25, crate26;
   double kappa[3];
   double Jmean[3];
   int32_t parent;         // node index, -1 = baseGrid
@@ -82,6 +81,7 @@ struct Grid {
   double physicalBoxSize = 0;
   std::vector<Zone> node;           // base cells first: index ((i-1)*ny + (j-1))*nz + (k-1)
   std::vector<int32_t> leafNode;    // leaf number -> node index
+  std::vector<double> rate;         // [6][nleaf] krate24, krate25, krate26, crate24, crate25, crate26 (point sources)
   int maxLevel = 0;
   int base(int i, int j, int k) const { return ((i - 1) * ny + (j - 1)) * nz + (k - 1); }
   // child (i,j,k) in 1..2 of a refined node
@@ -105,6 +105,10 @@ struct DiffuseTrace {      // optional per-direction exports for the bit-exact t
 int buildGrid(Grid& g, int nx, double boxSize, const LeafInput& in);
 int diffuseSolve(Grid& g, int nAngularLevel, const double* uvb, const double* beta, int64_t rayBegin, int64_t rayEnd,
                  int64_t traceRay, DiffuseTrace* tr, int64_t* nsegOut);
+// several host threads, each sweeping its own share of `rays` on a private copy of the octree (the reference itself
+// is serial; this is the "all host threads" variant used by bench.py --impl reference)
+int diffuseSolveThreaded(Grid& g, int nAngularLevel, const double* uvb, const double* beta, const int32_t* rays,
+                         int nrays, int nthreads, double* J /* [3][nleaf] */, int64_t* nsegOut);
 int directionSetup(int nAngularLevel, int64_t iray, int& izone, double& phi, double& theta);
 int pix2ang_nest(int nside, int64_t ipix, double& phi, double& theta);
 void rotateIndices(int i, int j, int k, int nx, int ny, int nz, int izone, int& ic, int& jc, int& kc);

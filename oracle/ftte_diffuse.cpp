@@ -7,6 +7,8 @@
 // Single thread, libm exp/log/trig (what gfortran calls), no FMA contraction (build with -ffp-contract=off).
 #include "ftte_common.h"
 
+#include <thread>
+
 namespace ftte {
 
 // ------------------------------------------------------------------------------------------------------
@@ -669,6 +671,49 @@ int diffuseSolve(Grid& g, int nAngularLevel, const double* uvb, const double* be
     if (st) { if (nsegOut) *nsegOut = s.nseg; return st; }
   }
   if (nsegOut) *nsegOut = s.nseg;
+  return OK;
+}
+
+int diffuseSolveThreaded(Grid& g, int nAngularLevel, const double* uvb, const double* beta, const int32_t* rays,
+                         int nrays, int nthreads, double* J, int64_t* nsegOut) {
+  computeOpacities(g, beta);
+  const int64_t nraysTotal = 12 * ((int64_t)1 << (2 * (nAngularLevel - 1)));
+  const double weight = (double)(1.f / (float)nraysTotal);
+  const size_t nleaf = g.leafNode.size();
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > nrays) nthreads = nrays > 0 ? nrays : 1;
+  std::vector<int> status(nthreads, OK);
+  std::vector<int64_t> nseg(nthreads, 0);
+  std::vector<std::vector<double>> part(nthreads);
+  auto work = [&](int t, Grid* mine) {
+    Sweep s;
+    s.g = mine;
+    s.uvb[0] = uvb[0]; s.uvb[1] = uvb[1]; s.uvb[2] = uvb[2];
+    s.nseg = 0;
+    for (int q = t; q < nrays; q += nthreads) {
+      int st = sweepDirection(s, nAngularLevel, rays[q], weight, nullptr);
+      if (st) { status[t] = st; break; }
+    }
+    nseg[t] = s.nseg;
+    part[t].resize(3 * nleaf);
+    for (size_t l = 0; l < nleaf; l++) {
+      const Zone& z = mine->node[mine->leafNode[l]];
+      for (int gI = 0; gI < 3; gI++) part[t][gI * nleaf + l] = z.Jmean[gI];
+    }
+  };
+  std::vector<Grid> copies(nthreads > 1 ? nthreads - 1 : 0, g);  // thread 0 works on g itself
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; t++) th.emplace_back(work, t, &copies[t - 1]);
+  work(0, &g);
+  for (auto& x : th) x.join();
+  int64_t tot = 0;
+  for (size_t i = 0; i < 3 * nleaf; i++) {
+    double sum = 0.;
+    for (int t = 0; t < nthreads; t++) sum += part[t][i];
+    J[i] = sum;
+  }
+  for (int t = 0; t < nthreads; t++) { tot += nseg[t]; if (status[t]) return status[t]; }
+  if (nsegOut) *nsegOut = tot;
   return OK;
 }
 

@@ -38,6 +38,9 @@ def lib():
         L.ftte_diffuse.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int64,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ftte_diffuse_mt.restype = C.c_int
+        L.ftte_diffuse_mt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_void_p, C.POINTER(C.c_int64)]
         L.ftte_direction.restype = C.c_int
         L.ftte_direction.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_double),
                                      C.POINTER(C.c_double)]
@@ -99,6 +102,21 @@ class OracleGrid:
         if trace_ray >= 0:
             out.update(nb=nb, pattern=pat, izone=int(iz[0]), angles=ang)
         return out
+
+
+def _diffuse_mt(self, uvb, beta, rays, n_angular_level=3, nthreads=1):
+    """all-host-threads variant over an explicit ray list (each thread sweeps a private copy of the octree)"""
+    uvb = _f64(uvb)
+    beta = _f64(np.asarray(beta).reshape(9))
+    rays = np.ascontiguousarray(rays, dtype=np.int32)
+    J = np.zeros((3, self.nleaf))
+    nseg = C.c_int64(0)
+    st = self.L.ftte_diffuse_mt(self.h, int(n_angular_level), _p(uvb), _p(beta), _p(rays), int(rays.size),
+                                int(nthreads), _p(J), C.byref(nseg))
+    return dict(J=J, nseg=nseg.value, status=st)
+
+
+OracleGrid.diffuse_mt = _diffuse_mt
 
 
 def direction(n_angular_level, iray):
