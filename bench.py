@@ -92,6 +92,8 @@ def cpu_oracle_sample(n, grid, bg, seconds, threads):
     og = fo.OracleGrid(n, grid["level"], grid["HI"], grid["HeI"], grid["HeII"], box_size=grid["box_size"])
     # spread the sampled directions over the zones (ray numbers 0, 37, 74, ... mod 192)
     order = (np.arange(192) * 37) % 192
+    if threads > 1:  # creates the worker threads' private octree copies (set-up, untimed)
+        og.diffuse_mt(bg["uvb"], bg["beta"], order[:0], nthreads=threads)
     t0 = time.perf_counter()
     o = og.diffuse_mt(bg["uvb"], bg["beta"], order[:threads], nthreads=threads)
     dt1 = time.perf_counter() - t0

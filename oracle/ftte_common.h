@@ -82,6 +82,7 @@ struct Grid {
   std::vector<Zone> node;           // base cells first: index ((i-1)*ny + (j-1))*nz + (k-1)
   std::vector<int32_t> leafNode;    // leaf number -> node index
   std::vector<double> rate;         // [6][nleaf] krate24, krate25, krate26, crate24, crate25, crate26 (point sources)
+  std::vector<Grid> threadCopy;     // private octree copies of the worker threads (diffuseSolveThreaded), made once
   int maxLevel = 0;
   int base(int i, int j, int k) const { return ((i - 1) * ny + (j - 1)) * nz + (k - 1); }
   // child (i,j,k) in 1..2 of a refined node

@@ -681,6 +681,7 @@ int diffuseSolveThreaded(Grid& g, int nAngularLevel, const double* uvb, const do
   const double weight = (double)(1.f / (float)nraysTotal);
   const size_t nleaf = g.leafNode.size();
   if (nthreads < 1) nthreads = 1;
+  const int wantCopies = nthreads - 1;
   if (nthreads > nrays) nthreads = nrays > 0 ? nrays : 1;
   std::vector<int> status(nthreads, OK);
   std::vector<int64_t> nseg(nthreads, 0);
@@ -701,9 +702,23 @@ int diffuseSolveThreaded(Grid& g, int nAngularLevel, const double* uvb, const do
       for (int gI = 0; gI < 3; gI++) part[t][gI * nleaf + l] = z.Jmean[gI];
     }
   };
-  std::vector<Grid> copies(nthreads > 1 ? nthreads - 1 : 0, g);  // thread 0 works on g itself
+  // thread 0 works on g itself; the other threads on private copies that persist across calls (set-up cost, like
+  // the reference's one-time octree build, is not part of the sweep)
+  while ((int)g.threadCopy.size() < wantCopies) {
+    Grid c;
+    c.nx = g.nx; c.ny = g.ny; c.nz = g.nz; c.physicalBoxSize = g.physicalBoxSize; c.maxLevel = g.maxLevel;
+    c.node = g.node; c.leafNode = g.leafNode;
+    g.threadCopy.push_back(std::move(c));
+  }
+  for (int t = 1; t < nthreads; t++) {  // refresh what may have changed since the copy: species -> kappa, J = 0
+    Grid& c = g.threadCopy[t - 1];
+    for (size_t i = 0; i < g.node.size(); i++) {
+      c.node[i].HI = g.node[i].HI; c.node[i].HeI = g.node[i].HeI; c.node[i].HeII = g.node[i].HeII;
+    }
+    computeOpacities(c, beta);
+  }
   std::vector<std::thread> th;
-  for (int t = 1; t < nthreads; t++) th.emplace_back(work, t, &copies[t - 1]);
+  for (int t = 1; t < nthreads; t++) th.emplace_back(work, t, &g.threadCopy[t - 1]);
   work(0, &g);
   for (auto& x : th) x.join();
   int64_t tot = 0;
