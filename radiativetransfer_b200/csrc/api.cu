@@ -31,6 +31,7 @@ int ensure_buffer(void** p, size_t* have, size_t need) {
 }
 
 static void free_grid(Context& c) {
+  amr_release(c);
   cudaFree(c.dLevel); cudaFree(c.dHI); cudaFree(c.dHeI); cudaFree(c.dHeII); cudaFree(c.dRho); cudaFree(c.dAbun2);
   cudaFree(c.dKappa); cudaFree(c.tree.child); cudaFree(c.tree.leafX); cudaFree(c.tree.leafY); cudaFree(c.tree.leafZ);
   cudaFree(c.dJ);
@@ -137,14 +138,15 @@ static int run_diffuse(Context& c, int nAngularLevel, const double* uvb, const d
   RTB_CUDA(cudaEventRecord(c.evStart, s));
   if (int st = launch_compute_opacities(c, beta, s)) return st;
   int64_t ns = 0;
-  int st = c.uniform ? diffuse_uniform(c, nAngularLevel, uvb, dirs, dJ, s, &ns)
-                     : diffuse_amr(c, nAngularLevel, uvb, dirs, dJ, s, &ns);
+  const bool uniformPath = c.uniform && !c.tune.forceAmr;
+  int st = uniformPath ? diffuse_uniform(c, nAngularLevel, uvb, dirs, dJ, s, &ns)
+                       : diffuse_amr(c, nAngularLevel, uvb, dirs, dJ, s, &ns);
   if (st) return st;
   RTB_CUDA(cudaEventRecord(c.evStop, s));
   if (nseg) *nseg = ns;
   c.lastAlgBytes = 72.0 * (double)c.nleaf * (double)dirs.size();
   c.statsPending = true;
-  c.sweepTimed = c.uniform && !dirs.empty();
+  c.sweepTimed = uniformPath && !dirs.empty();
   return RTB200_OK;
 }
 
@@ -251,6 +253,8 @@ int rtb200_set_tuning(rtb200_ctx* h, const char* key, double value) {
   if (k == "dense") c.tune.minBlocks = (int)value;
   else if (k == "expv") c.tune.expVariant = (int)value;
   else if (k == "lockstep") c.tune.lockstep = (int)value;
+  else if (k == "amr_batch") c.tune.amrBatch = (int)value;
+  else if (k == "force_amr") c.tune.forceAmr = (int)value;
   else if (k == "slots") c.tune.slots = (int)value;
   else if (k == "graph") c.tune.useGraph = (int)value;
   else if (k == "l2_mb") c.tune.l2BudgetMB = value;
@@ -285,7 +289,7 @@ int rtb200_grid_set(rtb200_ctx* h, int nx, int64_t nleaf, const int8_t* level, c
   if (!st) st = upload((void**)&c.dAbun2, abun2, nb, s);
   if (!st) st = upload((void**)&c.dKappa, nullptr, 3 * nb, s);
   if (!st) st = upload((void**)&c.dJ, nullptr, 3 * nb, s);
-  if (!st && !c.uniform) {
+  if (!st) {
     st = upload((void**)&c.tree.child, c.hChild.data(), c.hChild.size() * sizeof(int32_t), s);
     if (!st) st = upload((void**)&c.tree.leafX, c.hLeafX.data(), (size_t)nleaf * sizeof(int32_t), s);
     if (!st) st = upload((void**)&c.tree.leafY, c.hLeafY.data(), (size_t)nleaf * sizeof(int32_t), s);

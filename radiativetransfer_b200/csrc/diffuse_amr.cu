@@ -1,6 +1,645 @@
-// placeholder: AMR diffuse sweep (implemented next)
+// Diffuse sweep on refined (AMR) grids: replaces, per direction, the reference's three passes over the octree --
+// pattern assignment (setRaysRefined, transportRoutinesModule.f90:121-218), neighbour threading
+// (localizeCellFindNeighbours / findNeighbours / get??Neighbour, :264-558) and transport (:560-963 plus the inline
+// base-cell copy equiSources.f90:1580-1788).
+//
+//  * Patterns depend only on (direction, level, fine layer index along the sweep axis): full tables per level are
+//    built on the host (geometry.cpp) -- level L has n*2^L entries, entry 2i / 2i+1 derived from entry i of level
+//    L-1 exactly as setRaysRefined derives the lower / upper sub-layer.
+//  * Neighbour threading is integer arithmetic on the leaf's rotated coordinates (walk up while the cell sits on the
+//    low face of its parent, step to the sibling / base neighbour, descend the linear octree with the `.le.0.5`
+//    tests on the exactly halved/doubled entry point).  One thread per (leaf, direction).
+//  * Transport order: the reference visits leaves in rotated i/j/k order so that upstream leaves are finished.  Here
+//    leaves are grouped in waves by the sum of their centre coordinates in rotated space, which increases strictly
+//    along every dependency edge when neighbouring leaves differ by at most one level; one launch per wave for all
+//    directions of the batch.  Grids that violate the 2:1 balance are still handled exactly: a leaf whose upstream
+//    leaf has not been published yet is put on a deferred list that is retried after every wave.
+//  * J is accumulated with fp64 atomics (several directions update a leaf concurrently); everything else is the
+//    reference's arithmetic (segment_math.cuh), incl. the coarse-neighbour averaging fallback
+//    (transportRoutinesModule.f90:612-634) and the intensity guard (:680-688).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
 #include "rtb200_internal.h"
+#include "segment_math.cuh"
+
 namespace rtb {
-int diffuse_amr(Context&, int, const double*, const std::vector<Direction>&, double*, cudaStream_t, int64_t*) { return RTB200_ERR_ARG; }
-int amr_neighbours(Context&, const Direction&, int32_t*) { return RTB200_ERR_ARG; }
+
+struct DevPattern {      // subset of RayPattern the device needs (64 B)
+  double len[3];         // xy, yz, xz   (ray id 0, 1, 2)
+  double e0[3], e1[3];   // entry point of each ray on its face: xy (x0,y0), yz (y0,z0), xz (x0,z0)
+  int8_t top[3];         // xyTop, yzTop, xzTop: which ray (1 xy, 2 yz, 3 xz) leaves through the top / x=1 / y=1 face
+  int8_t active[3];      // xy (always), yz, xz
+  int8_t pad[2];
+};
+
+struct AmrDir {          // one direction of the batch
+  int8_t src[3], refl[3];  // zone map: physical component c takes rotated index src[c], reflected if refl[c]
+  int8_t inv[3];           // rotated axis r is physical component inv[r]
+  int8_t combo;            // reflection combination 0..7 -> wave order
+  int32_t patBase;         // offset of this direction's pattern tables
+  double w;                // weight
+};
+
+struct AmrParams {
+  const int32_t* child;
+  const int32_t *lx, *ly, *lz;
+  const int8_t* level;
+  const double* kappa;     // [3][N]
+  const DevPattern* pats;
+  const int32_t* levelOff; // [maxLevel+2] offsets of the per-level tables inside one direction's block
+  const AmrDir* dirs;
+  int32_t* nb;             // [ndir][3][N] upstream leaf per ray (xy, yz, xz): -1 boundary, -2 inactive
+  uint8_t* code;           // [ndir][3][N] what to read from the upstream leaf
+  double* Iout;            // [ndir][N][9]
+  uint8_t* done;           // [ndir][N]
+  double* J;               // [3][N] (atomics)
+  int32_t* err;
+  int64_t N;
+  int n, maxLevel;
+  double u0, u1, u2, cellSize0;
+};
+
+// codes: 0,1,2 = take that ray of the neighbour; 3 = 0.5*(xz+xy); 4 = 0.5*(yz+xy); 5 = xy (fallback, no side ray)
+__device__ __forceinline__ void rotated_coords(const AmrDir& D, int nL, int px, int py, int pz, int (&r)[3]) {
+  const int p[3] = {px, py, pz};
+#pragma unroll
+  for (int c = 0; c < 3; c++) r[D.src[c]] = D.refl[c] ? nL - 1 - p[c] : p[c];
 }
+
+__device__ __forceinline__ void physical_coords(const AmrDir& D, int nL, const int (&r)[3], int (&p)[3]) {
+#pragma unroll
+  for (int c = 0; c < 3; c++) p[c] = D.refl[c] ? nL - 1 - r[D.src[c]] : r[D.src[c]];
+}
+
+// node of the cell with physical coordinates p at level l
+__device__ __forceinline__ int node_at(const int32_t* __restrict__ child, int n, int l, const int (&p)[3]) {
+  int node = ((p[0] >> l) * n + (p[1] >> l)) * n + (p[2] >> l);
+  for (int t = l - 1; t >= 0; t--) node = child[node] + (((p[0] >> t) & 1) << 2) + (((p[1] >> t) & 1) << 1) + ((p[2] >> t) & 1);
+  return node;
+}
+
+__global__ void amr_neighbour_kernel(AmrParams P, int ndir) {
+  const int64_t leaf = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int d = blockIdx.y;
+  if (leaf >= P.N || d >= ndir) return;
+  const AmrDir D = P.dirs[d];
+  const int L = P.level[leaf];
+  const int nL = P.n << L;
+  int r[3];
+  rotated_coords(D, nL, P.lx[leaf], P.ly[leaf], P.lz[leaf], r);
+  const DevPattern& pat = P.pats[D.patBase + P.levelOff[L] + r[0]];
+  // ray id: 0 xy (upstream across the low-i face), 1 yz (low-k face), 2 xz (low-j face)
+  for (int ray = 0; ray < 3; ray++) {
+    int32_t result = -2;
+    uint8_t code = 0;
+    if (pat.active[ray]) {
+      // face point (a, b): xy -> (x, y), yz -> (y, z), xz -> (x, z); x follows rotated k, y follows j, z follows i
+      double a = pat.e0[ray], b = pat.e1[ray];
+      const int lead = ray == 0 ? 0 : (ray == 1 ? 2 : 1);            // rotated axis the ray came across
+      const int axA = ray == 0 ? 2 : (ray == 1 ? 1 : 2);             // rotated axis of coordinate a
+      const int axB = ray == 0 ? 1 : 0;                              // rotated axis of coordinate b
+      result = -1;
+      for (int l = L; l >= 0; l--) {
+        const int sh = L - l;
+        int anc[3] = {r[0] >> sh, r[1] >> sh, r[2] >> sh};
+        const int idx = l == 0 ? anc[lead] : (anc[lead] & 1);       // 0-based index on the lead axis
+        if (idx > 0) {
+          anc[lead] -= 1;
+          int p[3];
+          physical_coords(D, P.n << l, anc, p);
+          int node = node_at(P.child, P.n, l, p);
+          int lvl = l;
+          while (P.child[node] >= 0) {                               // get??Neighbour: descend with .le.0.5
+            const int ia = a <= 0.5 ? 0 : 1, ib = b <= 0.5 ? 0 : 1;
+            int cr[3];
+            cr[lead] = 1;                                            // the child touching our face (index 2)
+            cr[axA] = ia;
+            cr[axB] = ib;
+            int cp[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) cp[c] = D.refl[c] ? 1 - cr[D.src[c]] : cr[D.src[c]];
+            node = P.child[node] + (cp[0] << 2) + (cp[1] << 1) + cp[2];
+            a = ia ? 2. * a - 1. : 2. * a;
+            b = ib ? 2. * b - 1. : 2. * b;
+            lvl++;
+          }
+          result = -P.child[node] - 1;
+          // selector: the neighbour's xyTop / yzTop / xzTop (transportRoutinesModule.f90:598-634)
+          const int nbL = P.level[result];
+          int nr[3];
+          rotated_coords(D, P.n << nbL, P.lx[result], P.ly[result], P.lz[result], nr);
+          const DevPattern& np = P.pats[D.patBase + P.levelOff[nbL] + nr[0]];
+          const int sel = np.top[ray];
+          if (sel >= 1) {
+            code = (uint8_t)(sel - 1);
+            if (ray != 0 && !np.active[sel - 1]) atomicMax(P.err, RTB200_ERR_RAY_INACTIVE);
+          } else {
+            // selector 0 is only legal when reading a coarser neighbour from a refined leaf
+            if (L == 0 || L <= nbL) atomicMax(P.err, RTB200_ERR_TOP_SELECTOR);
+            code = np.active[2] ? 3 : (np.active[1] ? 4 : 5);
+          }
+          (void)lvl;
+          break;
+        }
+        // on the low face of the parent: rescale the face point to the parent's units
+        const int ca = l == 0 ? (anc[axA] == 0 ? 0 : 1) : (anc[axA] & 1);
+        const int cb = l == 0 ? (anc[axB] == 0 ? 0 : 1) : (anc[axB] & 1);
+        a = ca ? a / 2. + 0.5 : a / 2.;
+        b = cb ? b / 2. + 0.5 : b / 2.;
+      }
+    }
+    P.nb[((int64_t)d * 3 + ray) * P.N + leaf] = result;
+    P.code[((int64_t)d * 3 + ray) * P.N + leaf] = code;
+  }
+}
+
+// one (leaf, direction): returns false if an upstream leaf is not published yet
+template <bool FAITHFUL>
+__device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, int64_t leaf) {
+  const AmrDir& D = P.dirs[d];
+  int32_t nbl[3];
+  uint8_t cd[3];
+#pragma unroll
+  for (int ray = 0; ray < 3; ray++) {
+    nbl[ray] = P.nb[((int64_t)d * 3 + ray) * P.N + leaf];
+    cd[ray] = P.code[((int64_t)d * 3 + ray) * P.N + leaf];
+  }
+  const volatile uint8_t* done = P.done + (int64_t)d * P.N;
+#pragma unroll
+  for (int ray = 0; ray < 3; ray++)
+    if (nbl[ray] >= 0 && !done[nbl[ray]]) return false;
+  __threadfence();
+  const int L = P.level[leaf];
+  int r[3];
+  rotated_coords(D, P.n << L, P.lx[leaf], P.ly[leaf], P.lz[leaf], r);
+  const DevPattern& pat = P.pats[D.patBase + P.levelOff[L] + r[0]];
+  const double cellSize = P.cellSize0 / (double)(1 << L);  // halved per level (transportRoutinesModule.f90:583)
+  const double uvb[3] = {P.u0, P.u1, P.u2};
+  double kap[3], invk[3];
+#pragma unroll
+  for (int g = 0; g < 3; g++) {
+    kap[g] = P.kappa[g * P.N + leaf];
+    if (!FAITHFUL) {
+      kap[g] = kap[g] > 0. ? kap[g] : 1e-200;
+      invk[g] = 1.0 / kap[g];
+    } else {
+      invk[g] = 0.;
+    }
+  }
+  double out[3][3];
+  double Jm[3] = {0., 0., 0.};
+  int imean = 0;
+  const double* IoutD = P.Iout + (int64_t)d * P.N * 9;
+  // the reference processes xy, then xz, then yz
+  const int order[3] = {0, 2, 1};
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    const int ray = order[q];
+    if (nbl[ray] == -2) {
+      out[ray][0] = out[ray][1] = out[ray][2] = 0.;
+      continue;
+    }
+    double Iin[3];
+    if (nbl[ray] < 0) {
+      Iin[0] = uvb[0]; Iin[1] = uvb[1]; Iin[2] = uvb[2];
+    } else {
+      const double* nI = IoutD + (int64_t)nbl[ray] * 9;  // written by another block, possibly in this launch: read via L2
+      const int c = cd[ray];
+#pragma unroll
+      for (int g = 0; g < 3; g++) {
+        if (c <= 2) Iin[g] = __ldcg(nI + c * 3 + g);
+        else if (c == 3) Iin[g] = __dmul_rn(0.5, __dadd_rn(__ldcg(nI + 2 * 3 + g), __ldcg(nI + g)));
+        else if (c == 4) Iin[g] = __dmul_rn(0.5, __dadd_rn(__ldcg(nI + 1 * 3 + g), __ldcg(nI + g)));
+        else Iin[g] = __ldcg(nI + g);
+      }
+    }
+    const double dpath = __dmul_rn(cellSize, pat.len[ray]);
+    const double invd = FAITHFUL ? 0. : 1.0 / dpath;
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      SegResult sr = segment_update<FAITHFUL, 0>(Iin[g], kap[g], dpath, invk[g] * invd, nullptr);
+      out[ray][g] = sr.Iout;
+      Jm[g] = __dadd_rn(Jm[g], sr.J);
+    }
+    imean++;
+    if (L > 0) {  // refined path only: guard on the xy ray's sum (transportRoutinesModule.f90:680,803,926)
+      const double tmp = __dadd_rn(__dadd_rn(out[0][0], out[0][1]), out[0][2]);
+      if (!(tmp < 1.e-20 && tmp > -1.e-20)) atomicMax(P.err, RTB200_ERR_INTENSITY_GUARD);
+    }
+  }
+  double* mine = P.Iout + ((int64_t)d * P.N + leaf) * 9;
+#pragma unroll
+  for (int ray = 0; ray < 3; ray++)
+#pragma unroll
+    for (int g = 0; g < 3; g++) mine[ray * 3 + g] = out[ray][g];
+#pragma unroll
+  for (int g = 0; g < 3; g++)
+    atomicAdd(P.J + g * P.N + leaf, __dmul_rn(__ddiv_rn(Jm[g], (double)imean), D.w));
+  __threadfence();
+  ((volatile uint8_t*)P.done)[(int64_t)d * P.N + leaf] = 1;
+  return true;
+}
+
+struct WaveParams {
+  const int32_t* sorted[8];   // leaves ordered by wave key, per reflection combination
+  int32_t begin[8], count[8]; // this wave's range in each order
+  int64_t* deferred;          // list of (d << 32 | leaf) that could not run
+  int32_t* deferredCount;
+  int64_t deferredCap;
+};
+
+template <bool FAITHFUL>
+__global__ void amr_wave_kernel(AmrParams P, WaveParams Wp, int ndir) {
+  const int d = blockIdx.y;
+  if (d >= ndir) return;
+  const int combo = P.dirs[d].combo;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Wp.count[combo]) return;
+  const int64_t leaf = Wp.sorted[combo][Wp.begin[combo] + i];
+  if (!amr_transport_leaf<FAITHFUL>(P, d, leaf)) {
+    int slot = atomicAdd(Wp.deferredCount, 1);
+    if (slot < Wp.deferredCap) Wp.deferred[slot] = ((int64_t)d << 32) | leaf;
+    else atomicMax(P.err, RTB200_ERR_NOMEM);
+  }
+}
+
+template <bool FAITHFUL>
+__global__ void amr_retry_kernel(AmrParams P, const int64_t* in, const int32_t* inCount, int64_t* out, int32_t* outCount,
+                                 int64_t cap) {
+  const int n = min((int64_t)*inCount, cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int64_t item = in[i];
+    const int d = (int)(item >> 32);
+    const int64_t leaf = item & 0xffffffffLL;
+    if (!amr_transport_leaf<FAITHFUL>(P, d, leaf)) {
+      int slot = atomicAdd(outCount, 1);
+      if (slot < cap) out[slot] = item;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------------------
+static DevPattern to_dev(const RayPattern& p) {
+  DevPattern q;
+  std::memset(&q, 0, sizeof(q));
+  q.len[0] = p.xy_len; q.len[1] = p.yz_len; q.len[2] = p.xz_len;
+  q.e0[0] = p.xy_x0; q.e1[0] = p.xy_y0;
+  q.e0[1] = p.yz_y0; q.e1[1] = p.yz_z0;
+  q.e0[2] = p.xz_x0; q.e1[2] = p.xz_z0;
+  q.top[0] = p.xyTop; q.top[1] = p.yzTop; q.top[2] = p.xzTop;
+  q.active[0] = 1; q.active[1] = p.yzActive; q.active[2] = p.xzActive;
+  return q;
+}
+
+struct AmrPlan {
+  std::vector<int32_t> sorted[8];
+  std::vector<int32_t> waveStart[8];  // [nkeys + 1]
+  int nkeys = 0;
+  int32_t* dSorted[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+// wave key = sum over the rotated axes of the leaf centre in half-finest-cell units (see header comment)
+static void build_waves(Context& c, AmrPlan& plan) {
+  const int Lmax = c.maxLevel;
+  const int64_t N = c.nleaf;
+  const int span = (c.nx << Lmax) * 2;  // centre coordinate range per axis
+  plan.nkeys = 3 * span + 1;
+  std::vector<int32_t> key((size_t)N);
+  for (int combo = 0; combo < 8; combo++) {
+    std::vector<int32_t>& start = plan.waveStart[combo];
+    start.assign(plan.nkeys + 1, 0);
+    for (int64_t l = 0; l < N; l++) {
+      const int L = c.hLevel[l];
+      const int sc = 1 << (Lmax - L);
+      const int nL = c.nx << L;
+      const int p[3] = {c.hLeafX[l], c.hLeafY[l], c.hLeafZ[l]};
+      int k = 0;
+      for (int a = 0; a < 3; a++) {
+        const int r = (combo >> a) & 1 ? nL - 1 - p[a] : p[a];
+        k += (2 * r + 1) * sc;
+      }
+      key[l] = k;
+      start[k + 1]++;
+    }
+    for (int k = 0; k < plan.nkeys; k++) start[k + 1] += start[k];
+    std::vector<int32_t> cursor(start.begin(), start.end() - 1);
+    plan.sorted[combo].resize((size_t)N);
+    for (int64_t l = 0; l < N; l++) plan.sorted[combo][cursor[key[l]]++] = (int32_t)l;
+  }
+}
+
+struct AmrState {
+  AmrPlan plan;
+  std::string key;
+};
+static std::vector<std::pair<Context*, AmrState*>> g_states;
+static AmrState* state_of(Context& c) {
+  for (auto& p : g_states)
+    if (p.first == &c) return p.second;
+  g_states.push_back({&c, new AmrState()});
+  return g_states.back().second;
+}
+void amr_release(Context& c) {
+  for (size_t i = 0; i < g_states.size(); i++)
+    if (g_states[i].first == &c) {
+      for (int k = 0; k < 8; k++) cudaFree(g_states[i].second->plan.dSorted[k]);
+      delete g_states[i].second;
+      g_states.erase(g_states.begin() + i);
+      return;
+    }
+}
+
+static int ensure_plan(Context& c, AmrState& S) {
+  char buf[64];
+  snprintf(buf, sizeof(buf), "%p:%lld:%d", (void*)c.tree.child, (long long)c.nleaf, c.maxLevel);
+  if (S.key == buf) return RTB200_OK;
+  for (int k = 0; k < 8; k++) { cudaFree(S.plan.dSorted[k]); S.plan.dSorted[k] = nullptr; }
+  build_waves(c, S.plan);
+  for (int k = 0; k < 8; k++) {
+    RTB_CUDA(cudaMalloc((void**)&S.plan.dSorted[k], (size_t)c.nleaf * sizeof(int32_t)));
+    RTB_CUDA(cudaMemcpy(S.plan.dSorted[k], S.plan.sorted[k].data(), (size_t)c.nleaf * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  S.key = buf;
+  return RTB200_OK;
+}
+
+struct DirTables {
+  std::vector<DevPattern> pats;
+  std::vector<AmrDir> dirs;
+  std::vector<int32_t> levelOff;
+  int perDir = 0;
+};
+
+static int build_dir_tables(Context& c, int nAngularLevel, const std::vector<Direction>& dirs, DirTables& T) {
+  const int Lmax = c.maxLevel, n = c.nx;
+  const int64_t nraysTotal = 12LL << (2 * (nAngularLevel - 1));
+  const double weight = (double)(1.f / (float)nraysTotal);
+  T.levelOff.assign(Lmax + 2, 0);
+  for (int L = 0; L <= Lmax; L++) T.levelOff[L + 1] = T.levelOff[L] + (n << L);
+  T.perDir = T.levelOff[Lmax + 1];
+  T.pats.resize((size_t)T.perDir * dirs.size());
+  T.dirs.resize(dirs.size());
+  std::vector<RayPattern> cur, next;
+  for (size_t d = 0; d < dirs.size(); d++) {
+    const Direction& dd = dirs[d];
+    if (dd.status) return dd.status;
+    ZoneMap m = zone_map(dd.izone);
+    AmrDir& A = T.dirs[d];
+    int combo = 0;
+    for (int cc = 0; cc < 3; cc++) {
+      A.src[cc] = m.src[cc]; A.refl[cc] = m.refl[cc];
+      A.inv[m.src[cc]] = (int8_t)cc;
+      if (m.refl[cc]) combo |= 1 << cc;
+    }
+    A.combo = (int8_t)combo;
+    A.patBase = (int32_t)(d * T.perDir);
+    A.w = weight;
+    // which physical axis is the sweep axis, and is it reflected: decides which sub-layers exist in the reference
+    const int sweepAxis = A.inv[0];
+    layer_patterns_level0(dd.phi, dd.theta, n, cur);
+    for (int L = 0; L <= Lmax; L++) {
+      const int nL = n << L;
+      for (int i = 0; i < nL; i++) {
+        const RayPattern& p = cur[i];
+        if (p.status) {
+          // the reference only builds the patterns of layers that hold cells: level 0 always, deeper levels where a
+          // cell of the layer above is refined
+          bool needed = (L == 0);
+          if (L > 0) {
+            const int pi = i >> 1;
+            const int phys = A.refl[sweepAxis] ? (n << (L - 1)) - 1 - pi : pi;
+            const auto& v = c.refinedLayer[sweepAxis];
+            needed = (int)v.size() > L - 1 && !v[L - 1].empty() && v[L - 1][phys];
+          }
+          if (needed) return p.status;
+        }
+        T.pats[(size_t)A.patBase + T.levelOff[L] + i] = to_dev(p);
+      }
+      if (L < Lmax) {
+        layer_patterns_refine(dd.phi, dd.theta, cur, next);
+        cur.swap(next);
+      }
+    }
+  }
+  return RTB200_OK;
+}
+
+// device buffers of one batch of directions
+struct AmrBuffers {
+  DevPattern* pats = nullptr;
+  AmrDir* dirs = nullptr;
+  int32_t* levelOff = nullptr;
+  int32_t* nb = nullptr;
+  uint8_t* code = nullptr;
+  double* Iout = nullptr;
+  uint8_t* done = nullptr;
+  int64_t* defA = nullptr;
+  int64_t* defB = nullptr;
+  int32_t* defCount = nullptr;  // [2]
+  void release() {
+    cudaFree(pats); cudaFree(dirs); cudaFree(levelOff); cudaFree(nb); cudaFree(code); cudaFree(Iout); cudaFree(done);
+    cudaFree(defA); cudaFree(defB); cudaFree(defCount);
+    *this = AmrBuffers();
+  }
+};
+
+static int alloc_batch(AmrBuffers& B, const DirTables& T, int64_t N, int ndirBatch, int64_t defCap) {
+  RTB_CUDA(cudaMalloc((void**)&B.pats, (size_t)T.perDir * ndirBatch * sizeof(DevPattern)));
+  RTB_CUDA(cudaMalloc((void**)&B.dirs, (size_t)ndirBatch * sizeof(AmrDir)));
+  RTB_CUDA(cudaMalloc((void**)&B.levelOff, T.levelOff.size() * sizeof(int32_t)));
+  RTB_CUDA(cudaMalloc((void**)&B.nb, (size_t)ndirBatch * 3 * N * sizeof(int32_t)));
+  RTB_CUDA(cudaMalloc((void**)&B.code, (size_t)ndirBatch * 3 * N));
+  RTB_CUDA(cudaMalloc((void**)&B.Iout, (size_t)ndirBatch * N * 9 * sizeof(double)));
+  RTB_CUDA(cudaMalloc((void**)&B.done, (size_t)ndirBatch * N));
+  RTB_CUDA(cudaMalloc((void**)&B.defA, (size_t)defCap * sizeof(int64_t)));
+  RTB_CUDA(cudaMalloc((void**)&B.defB, (size_t)defCap * sizeof(int64_t)));
+  RTB_CUDA(cudaMalloc((void**)&B.defCount, 2 * sizeof(int32_t)));
+  return RTB200_OK;
+}
+
+static int choose_batch(Context& c, int ndir) {
+  size_t freeB = 0, totalB = 0;
+  cudaMemGetInfo(&freeB, &totalB);
+  const double perDir = (double)c.nleaf * (9 * 8 + 1 + 3 * 4 + 3 + 16) + 1e6;
+  int nb = (int)std::max(1.0, std::min((double)ndir, 0.5 * (double)freeB / perDir));
+  if (c.tune.amrBatch > 0) nb = std::min(nb, c.tune.amrBatch);
+  return nb;
+}
+
+static int run_batch(Context& c, AmrState& S, const DirTables& T, int d0, int nd, const double* uvb, double* dJ,
+                     cudaStream_t s, bool faithful, AmrBuffers& B, int64_t defCap, int64_t* launches) {
+  const int64_t N = c.nleaf;
+  RTB_CUDA(cudaMemcpyAsync(B.pats, T.pats.data() + (size_t)d0 * T.perDir, (size_t)T.perDir * nd * sizeof(DevPattern),
+                           cudaMemcpyHostToDevice, s));
+  std::vector<AmrDir> dl(T.dirs.begin() + d0, T.dirs.begin() + d0 + nd);
+  for (int i = 0; i < nd; i++) dl[i].patBase = i * T.perDir;
+  RTB_CUDA(cudaMemcpyAsync(B.dirs, dl.data(), (size_t)nd * sizeof(AmrDir), cudaMemcpyHostToDevice, s));
+  RTB_CUDA(cudaMemcpyAsync(B.levelOff, T.levelOff.data(), T.levelOff.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  RTB_CUDA(cudaMemsetAsync(B.done, 0, (size_t)nd * N, s));
+  RTB_CUDA(cudaMemsetAsync(B.defCount, 0, 2 * sizeof(int32_t), s));
+  RTB_CUDA(cudaStreamSynchronize(s));  // dl is a local
+  AmrParams P;
+  P.child = c.tree.child; P.lx = c.tree.leafX; P.ly = c.tree.leafY; P.lz = c.tree.leafZ; P.level = c.dLevel;
+  P.kappa = c.dKappa; P.pats = B.pats; P.levelOff = B.levelOff; P.dirs = B.dirs; P.nb = B.nb; P.code = B.code;
+  P.Iout = B.Iout; P.done = B.done; P.J = dJ; P.err = c.dErr; P.N = N; P.n = c.nx; P.maxLevel = c.maxLevel;
+  P.u0 = uvb[0]; P.u1 = uvb[1]; P.u2 = uvb[2];
+  P.cellSize0 = c.boxSize / (double)c.nx;  // equiSources.f90:1570
+  {
+    dim3 grid((unsigned)((N + 127) / 128), nd);
+    amr_neighbour_kernel<<<grid, 128, 0, s>>>(P, nd);
+    (*launches)++;
+  }
+  WaveParams Wp;
+  for (int k = 0; k < 8; k++) Wp.sorted[k] = S.plan.dSorted[k];
+  Wp.deferredCap = defCap;
+  int cur = 0;  // deferred list written by the wave kernels / read by the retry kernel
+  int64_t* lists[2] = {B.defA, B.defB};
+  bool used[8] = {false, false, false, false, false, false, false, false};
+  for (int i = 0; i < nd; i++) used[dl[i].combo] = true;
+  for (int w = 0; w < S.plan.nkeys; w++) {
+    int maxCount = 0;
+    for (int k = 0; k < 8; k++) {
+      Wp.begin[k] = S.plan.waveStart[k][w];
+      Wp.count[k] = S.plan.waveStart[k][w + 1] - S.plan.waveStart[k][w];
+      if (used[k]) maxCount = std::max(maxCount, Wp.count[k]);
+    }
+    if (maxCount == 0) continue;
+    Wp.deferred = lists[cur];
+    Wp.deferredCount = B.defCount + cur;
+    dim3 grid((maxCount + 127) / 128, nd);
+    if (faithful) amr_wave_kernel<true><<<grid, 128, 0, s>>>(P, Wp, nd);
+    else amr_wave_kernel<false><<<grid, 128, 0, s>>>(P, Wp, nd);
+    (*launches)++;
+    if ((w & 15) == 15) {
+      // retry what has been deferred so far (nothing on 2:1-balanced grids)
+      RTB_CUDA(cudaMemsetAsync(B.defCount + (cur ^ 1), 0, sizeof(int32_t), s));
+      if (faithful) amr_retry_kernel<true><<<64, 128, 0, s>>>(P, lists[cur], B.defCount + cur, lists[cur ^ 1], B.defCount + (cur ^ 1), defCap);
+      else amr_retry_kernel<false><<<64, 128, 0, s>>>(P, lists[cur], B.defCount + cur, lists[cur ^ 1], B.defCount + (cur ^ 1), defCap);
+      (*launches)++;
+      cur ^= 1;
+    }
+  }
+  // drain the deferred list
+  for (int iter = 0; iter < 100000; iter++) {
+    int32_t cnt = 0;
+    RTB_CUDA(cudaMemcpyAsync(&cnt, B.defCount + cur, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    RTB_CUDA(cudaStreamSynchronize(s));
+    if (cnt == 0) break;
+    if (cnt > defCap) return RTB200_ERR_NOMEM;
+    RTB_CUDA(cudaMemsetAsync(B.defCount + (cur ^ 1), 0, sizeof(int32_t), s));
+    if (faithful) amr_retry_kernel<true><<<256, 128, 0, s>>>(P, lists[cur], B.defCount + cur, lists[cur ^ 1], B.defCount + (cur ^ 1), defCap);
+    else amr_retry_kernel<false><<<256, 128, 0, s>>>(P, lists[cur], B.defCount + cur, lists[cur ^ 1], B.defCount + (cur ^ 1), defCap);
+    (*launches)++;
+    cur ^= 1;
+    if (iter == 99999) return RTB200_ERR_ARG;
+  }
+  RTB_CUDA(cudaGetLastError());
+  return RTB200_OK;
+}
+
+int diffuse_amr(Context& c, int nAngularLevel, const double* uvb, const std::vector<Direction>& dirs, double* dJout,
+                cudaStream_t s, int64_t* nsegOut) {
+  const int64_t N = c.nleaf;
+  AmrState& S = *state_of(c);
+  if (int st = ensure_plan(c, S)) return st;
+  RTB_CUDA(cudaMemsetAsync(dJout, 0, 3 * N * sizeof(double), s));
+  c.lastSweepLaunches = 0;
+  c.lastLaunches = 2;
+  if (nsegOut) *nsegOut = 0;
+  if (dirs.empty()) return RTB200_OK;
+  DirTables T;
+  if (int st = build_dir_tables(c, nAngularLevel, dirs, T)) return st;
+  const int ndir = (int)dirs.size();
+  const int batch = choose_batch(c, ndir);
+  const int64_t defCap = std::max<int64_t>(1 << 16, std::min<int64_t>((int64_t)batch * N, (int64_t)1 << 26));
+  AmrBuffers B;
+  int st = alloc_batch(B, T, N, batch, defCap);
+  int64_t launches = 0;
+  const bool faithful = c.mathMode == RTB200_MATH_FAITHFUL;
+  for (int d0 = 0; d0 < ndir && !st; d0 += batch)
+    st = run_batch(c, S, T, d0, std::min(batch, ndir - d0), uvb, dJout, s, faithful, B, defCap, &launches);
+  if (!st && nsegOut) {
+    // segment count: leaves per (level, layer) times the layer's segments -- from the host tables
+    std::vector<std::vector<int64_t>> hist[3];  // per physical sweep axis: [level][layer] leaf counts
+    for (int a = 0; a < 3; a++) {
+      hist[a].resize(c.maxLevel + 1);
+      for (int L = 0; L <= c.maxLevel; L++) hist[a][L].assign((size_t)c.nx << L, 0);
+    }
+    for (int64_t l = 0; l < N; l++) {
+      const int L = c.hLevel[l];
+      hist[0][L][c.hLeafX[l]]++; hist[1][L][c.hLeafY[l]]++; hist[2][L][c.hLeafZ[l]]++;
+    }
+    int64_t nseg = 0;
+    for (int d = 0; d < ndir; d++) {
+      const AmrDir& A = T.dirs[d];
+      const int ax = A.inv[0];
+      for (int L = 0; L <= c.maxLevel; L++) {
+        const int nL = c.nx << L;
+        for (int i = 0; i < nL; i++) {
+          const int phys = A.refl[ax] ? nL - 1 - i : i;
+          const int64_t cnt = hist[ax][L][phys];
+          if (!cnt) continue;
+          const DevPattern& p = T.pats[(size_t)A.patBase + T.levelOff[L] + i];
+          nseg += cnt * (1 + p.active[1] + p.active[2]);
+        }
+      }
+    }
+    *nsegOut = nseg;
+  }
+  cudaStreamSynchronize(s);
+  B.release();
+  c.lastSweepLaunches = launches;
+  c.lastLaunches = launches + 2;
+  return st;
+}
+
+// debugging export: upstream leaf per ray for one direction (xy, yz, xz)
+int amr_neighbours(Context& c, const Direction& d, int32_t* nbHost) {
+  const int64_t N = c.nleaf;
+  if (c.uniform && !c.tune.forceAmr) {
+    // implicit on a uniform grid: the (i-1), (k-1), (j-1) cell of the rotated lattice when the ray is active
+    std::vector<RayPattern> pat;
+    layer_patterns_level0(d.phi, d.theta, c.nx, pat);
+    ZoneStrides zs = zone_strides(d.izone, c.nx);
+    const int n = c.nx;
+    for (int i = 0; i < n; i++) {
+      if (pat[i].status) return pat[i].status;
+      for (int j = 0; j < n; j++)
+        for (int k = 0; k < n; k++) {
+          const int64_t leaf = zs.origin + i * zs.stride[0] + j * zs.stride[1] + k * zs.stride[2];
+          nbHost[leaf] = i > 0 ? (int32_t)(leaf - zs.stride[0]) : -1;
+          nbHost[N + leaf] = !pat[i].yzActive ? -2 : (k > 0 ? (int32_t)(leaf - zs.stride[2]) : -1);
+          nbHost[2 * N + leaf] = !pat[i].xzActive ? -2 : (j > 0 ? (int32_t)(leaf - zs.stride[1]) : -1);
+        }
+    }
+    return RTB200_OK;
+  }
+  std::vector<Direction> one{d};
+  DirTables T;
+  if (int st = build_dir_tables(c, 3, one, T)) return st;
+  AmrBuffers B;
+  if (int st = alloc_batch(B, T, N, 1, 16)) { B.release(); return st; }
+  cudaStream_t s = c.stream;
+  RTB_CUDA(cudaMemcpyAsync(B.pats, T.pats.data(), T.pats.size() * sizeof(DevPattern), cudaMemcpyHostToDevice, s));
+  RTB_CUDA(cudaMemcpyAsync(B.dirs, T.dirs.data(), sizeof(AmrDir), cudaMemcpyHostToDevice, s));
+  RTB_CUDA(cudaMemcpyAsync(B.levelOff, T.levelOff.data(), T.levelOff.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  AmrParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.child = c.tree.child; P.lx = c.tree.leafX; P.ly = c.tree.leafY; P.lz = c.tree.leafZ; P.level = c.dLevel;
+  P.pats = B.pats; P.levelOff = B.levelOff; P.dirs = B.dirs; P.nb = B.nb; P.code = B.code; P.err = c.dErr;
+  P.N = N; P.n = c.nx; P.maxLevel = c.maxLevel;
+  dim3 grid((unsigned)((N + 127) / 128), 1);
+  amr_neighbour_kernel<<<grid, 128, 0, s>>>(P, 1);
+  RTB_CUDA(cudaMemcpyAsync(nbHost, B.nb, (size_t)3 * N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  RTB_CUDA(cudaStreamSynchronize(s));
+  B.release();
+  // selector / activity errors found while threading are reported by the sweep, not by this view
+  cudaMemset(c.dErr, 0, 64);
+  return RTB200_OK;
+}
+
+}  // namespace rtb

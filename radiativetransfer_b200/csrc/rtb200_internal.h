@@ -61,6 +61,8 @@ struct UniTaskHost {
 struct Tuning {
   int slots = 0;         // zones swept concurrently (independent streams), each with its own J accumulator (0 = 24)
   int useGraph = 1;
+  int forceAmr = 0;      // route uniform grids through the general (AMR) path as well (cross-check)
+  int amrBatch = 0;      // directions per AMR batch (0 = as many as fit in half of the free memory)
   int lockstep = 1;      // 1: one launch per layer for all zones of a batch; 0: every slot an independent stream
   int minBlocks = 2;     // 0: compiler's register choice (2 blocks per SM); 1: cap for 3 blocks; 2: cap for 4 blocks
   int expVariant = 1;    // exp(-tau) of the fast path: 0 = polynomial, 1 = 16-entry shared-memory table
@@ -144,6 +146,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
 int diffuse_amr(Context& c, int nAngularLevel, const double* uvb, const std::vector<Direction>& dirs,
                 double* dJout, cudaStream_t s, int64_t* nseg);
 int amr_neighbours(Context& c, const Direction& d, int32_t* nbHost);
+void amr_release(Context& c);
 int launch_diffuse_rates(Context& c, const double* J, const double* ksi24, const double* ksi25, const double* ksi26,
                          double* k24, double* k25, double* k26, cudaStream_t s);
 

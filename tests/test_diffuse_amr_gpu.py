@@ -1,0 +1,120 @@
+"""GPU parity tests of the diffuse sweep on refined (AMR) grids: per-direction neighbour threading compared
+bit-exactly with the oracle, Jmean within 1e-9, both arithmetic modes, 2:1-balanced and unbalanced octrees."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from radiativetransfer_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def rt(build_product):
+    import radiativetransfer_b200 as rt
+    return rt
+
+
+@pytest.fixture()
+def engine(rt):
+    t = rt.Transport(device=0)
+    yield t
+    t.close()
+
+
+def _set(t, g):
+    t.set_grid(g["nx"], g["level"], g["HI"], g["HeI"], g["HeII"], g["rho"], g["abun2"], g["box_size"])
+
+
+def _grids():
+    yield "one-level-box", W.nested_grid(8, 1, W.central_box_refine(0.25, 0.75), seed=3)
+    yield "two-level-box", W.nested_grid(6, 2, W.central_box_refine(0.3, 0.7, levels=2), seed=4)
+    yield "disc-3-levels", W.nested_grid(6, 3, W.disc_refine(3, r0=0.45, h0=0.2), seed=5)
+
+    def corner(level, x, y, z, size):  # refined region touching the domain boundary, 3 levels deep, unbalanced
+        return (level < 3) & (x < 0.26) & (y < 0.26) & (z > 0.74)
+    yield "unbalanced-corner", W.nested_grid(4, 3, corner, seed=6)
+
+    def single(level, x, y, z, size):  # a single base cell refined to level 3 next to level-0 cells
+        return (level < 3) & (np.abs(x - 0.3) < 0.1) & (np.abs(y - 0.5) < 0.1) & (np.abs(z - 0.7) < 0.1)
+    yield "single-deep-cell", W.nested_grid(5, 3, single, seed=7)
+
+
+GRIDS = dict(_grids())
+
+
+@pytest.mark.parametrize("name", sorted(GRIDS))
+def test_neighbour_threading_bit_exact(rt, engine, oracle, uvbg, name):
+    g = GRIDS[name]
+    _set(engine, g)
+    og = oracle.OracleGrid(g["nx"], g["level"], g["HI"], g["HeI"], g["HeII"], box_size=g["box_size"])
+    uvb = uvbg["uvb"] * 1e-3
+    for ray in (0, 5, 23, 47, 77, 100, 133, 166, 191):
+        o = og.diffuse(uvb, uvbg["beta"], ray_begin=ray, ray_end=ray + 1, trace_ray=ray)
+        assert o["status"] == 0
+        nb = engine.neighbours(3, ray)
+        assert np.array_equal(nb, o["nb"]), (name, ray)
+
+
+@pytest.mark.parametrize("name", sorted(GRIDS))
+@pytest.mark.parametrize("mode", ["faithful", "fast"])
+def test_amr_parity_vs_oracle(rt, engine, oracle, uvbg, name, mode):
+    g = GRIDS[name]
+    engine.set_math(rt.MATH_FAITHFUL if mode == "faithful" else rt.MATH_FAST)
+    _set(engine, g)
+    uvb = uvbg["uvb"] * 1e-3   # keeps |Iout1+Iout2+Iout3| < 1e-20 (transportRoutinesModule.f90:680-688)
+    J, nseg = engine.diffuse(uvb, uvbg["beta"])
+    og = oracle.OracleGrid(g["nx"], g["level"], g["HI"], g["HeI"], g["HeII"], box_size=g["box_size"])
+    o = og.diffuse(uvb, uvbg["beta"])
+    assert o["status"] == 0
+    assert nseg == o["nseg"]
+    assert rel_err(J, o["J"]) < TOL, (name, rel_err(J, o["J"]))
+
+
+def test_amr_zero_opacity_known_answer(rt, engine, uvbg):
+    g = dict(GRIDS["disc-3-levels"])
+    z = np.zeros(g["level"].size)
+    g.update(HI=z, HeI=z, HeII=z)
+    _set(engine, g)
+    uvb = uvbg["uvb"] * 1e-3
+    J, _ = engine.diffuse(uvb, uvbg["beta"])
+    w = float(np.float32(1) / np.float32(192))
+    for gi in range(3):
+        assert np.allclose(J[gi], uvb[gi] * 192 * w, rtol=1e-13, atol=0)
+
+
+def test_intensity_guard_reported(rt, engine, uvbg):
+    # the reference stops when |Iout1+Iout2+Iout3| >= 1e-20 in a refined leaf
+    g = GRIDS["one-level-box"]
+    _set(engine, g)
+    with pytest.raises(rt.RTB200Error) as e:
+        engine.diffuse(uvbg["uvb"] * 1e3, uvbg["beta"])
+    assert e.value.status == 7
+
+
+def test_general_path_equals_uniform_path(rt, engine, oracle, uvbg):
+    g = W.uniform_grid(12, seed=9)
+    _set(engine, g)
+    engine.set_math(rt.MATH_FAITHFUL)
+    Ju, nu = engine.diffuse(uvbg["uvb"], uvbg["beta"])
+    engine.set_tuning(force_amr=1)
+    Ja, na = engine.diffuse(uvbg["uvb"], uvbg["beta"])
+    assert nu == na
+    assert rel_err(Ja, Ju) < 1e-13      # same arithmetic, different summation order (atomics)
+    nb = engine.neighbours(3, 42)
+    engine.set_tuning(force_amr=0)
+    assert np.array_equal(nb, engine.neighbours(3, 42))
+
+
+def test_amr_direction_batches_and_shards(rt, engine, uvbg):
+    g = GRIDS["two-level-box"]
+    _set(engine, g)
+    uvb = uvbg["uvb"] * 1e-3
+    full, nfull = engine.diffuse(uvb, uvbg["beta"])
+    engine.set_tuning(amr_batch=7)
+    part, npart = engine.diffuse(uvb, uvbg["beta"])
+    assert npart == nfull and np.allclose(part, full, rtol=1e-13, atol=0)
+    a, na = engine.diffuse(uvb, uvbg["beta"], rays=np.arange(0, 90, dtype=np.int32))
+    b, nb_ = engine.diffuse(uvb, uvbg["beta"], rays=np.arange(90, 192, dtype=np.int32))
+    assert na + nb_ == nfull and np.allclose(a + b, full, rtol=1e-13, atol=0)
