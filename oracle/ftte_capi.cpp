@@ -56,6 +56,24 @@ int ftte_diffuse_mt(void* h, int nAngularLevel, const double* uvb, const double*
   return diffuseSolveThreaded(*(Grid*)h, nAngularLevel, uvb, beta, rays, nrays, nthreads, J, nseg);
 }
 
+// Point sources.  rates = [6][nleaf] (krate24, krate25, krate26, crate24, crate25, crate26), accumulated in place.
+int ftte_point(void* h, int nWave, const double* wavelength, const double* lum, const double* metallicity,
+               double coefSpectrum, const double* aDust, int dustApproximation, int maxPixelLevel, int nsrc,
+               const int32_t* srcLeaf, const int32_t* srcWeight, double* rates, double* ndotRemaining,
+               double* ndotBoundary, double* ndotDust, double* ndotSpectrum, int64_t* nseg, int64_t* trace,
+               int64_t traceCap, int64_t* traceLen) {
+  PointSpectra S{nWave, wavelength, lum, metallicity, coefSpectrum, aDust};
+  return pointSolve(*(Grid*)h, S, dustApproximation, maxPixelLevel, nsrc, srcLeaf, srcWeight, rates, ndotRemaining,
+                    ndotBoundary, ndotDust, ndotSpectrum, nseg, trace, traceCap, traceLen);
+}
+
+int ftte_point_tables(int nWave, const double* wavelength, const double* lum, const double* metallicity,
+                      double coefSpectrum, const double* aDust, int iMetal, double coefMetal, double* out,
+                      double* totalIntegral, double* outputSigma) {
+  PointSpectra S{nWave, wavelength, lum, metallicity, coefSpectrum, aDust};
+  return pointTables(S, iMetal, coefMetal, out, totalIntegral, outputSigma);
+}
+
 int ftte_direction(int nAngularLevel, int64_t iray, int32_t* izone, double* phi, double* theta) {
   int iz = 0;
   int st = directionSetup(nAngularLevel, iray, iz, *phi, *theta);

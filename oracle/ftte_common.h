@@ -103,6 +103,22 @@ struct DiffuseTrace {      // optional per-direction exports for the bit-exact t
   double* anglesOut;       // phi, theta (local)
 };
 
+// stellar population synthesis inputs of the point-source path (equiSources.f90:840-892, dustModule.f90:15-24):
+// none of these data files ship with the reference, so they are arguments
+struct PointSpectra {
+  int nWave;                  // nWavelengths (1221 in the reference)
+  const double* wavelength;   // [nWave] cm, increasing
+  const double* lum;          // [5 metallicities][2 time slices: iSpectrum, iSpectrum+1][nWave] log10(erg/s/A)
+  const double* metallicity;  // [5] log10 Z
+  double coefSpectrum;        // time interpolation weight (equiSources.f90:1241-1242)
+  const double* aDust;        // [7][5] SMC extinction-fit parameters a_smc(i, 1..5)
+};
+int pointSolve(Grid& g, const PointSpectra& S, int dustApproximation, int maxPixelLevel, int nsrc, const int32_t* srcLeaf,
+               const int32_t* srcWeight, double* rates, double* ndotRemaining, double* ndotBoundary, double* ndotDust,
+               double* ndotSpectrum, int64_t* nsegOut, int64_t* trace, int64_t traceCap, int64_t* traceLen);
+int pointTables(const PointSpectra& S, int iMetal, double coefMetal, double* out, double* totalIntegral,
+                double* outputSigma);
+
 int buildGrid(Grid& g, int nx, double boxSize, const LeafInput& in);
 int diffuseSolve(Grid& g, int nAngularLevel, const double* uvb, const double* beta, int64_t rayBegin, int64_t rayEnd,
                  int64_t traceRay, DiffuseTrace* tr, int64_t* nsegOut);

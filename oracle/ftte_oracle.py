@@ -41,6 +41,14 @@ def lib():
         L.ftte_diffuse_mt.restype = C.c_int
         L.ftte_diffuse_mt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_void_p, C.POINTER(C.c_int64)]
+        L.ftte_point.restype = C.c_int
+        L.ftte_point.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
+                                 C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_int64,
+                                 C.POINTER(C.c_int64)]
+        L.ftte_point_tables.restype = C.c_int
+        L.ftte_point_tables.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
+                                        C.c_double, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]
         L.ftte_direction.restype = C.c_int
         L.ftte_direction.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_double),
                                      C.POINTER(C.c_double)]
@@ -117,6 +125,40 @@ def _diffuse_mt(self, uvb, beta, rays, n_angular_level=3, nthreads=1):
 
 
 OracleGrid.diffuse_mt = _diffuse_mt
+
+
+def _point(self, spectra, src_leaf, src_weight, dust_approximation=0, max_pixel_level=6, rates=None, trace_cap=0):
+    """Point-source pass (equiSources.f90:1256-1370).  spectra = dict(wavelength, lum[5,2,nw], metallicity[5],
+    coef_spectrum, a_dust[7,5]).  Returns dict(rates[6,nleaf], ndot_remaining[nsrc,7], ndot_boundary, ndot_dust,
+    ndot_spectrum[nsrc,300], nseg, status[, trace])."""
+    wl = _f64(spectra["wavelength"]); lum = _f64(spectra["lum"]); met = _f64(spectra["metallicity"])
+    ad = _f64(spectra["a_dust"])
+    leaf = np.ascontiguousarray(src_leaf, dtype=np.int32); wt = np.ascontiguousarray(src_weight, dtype=np.int32)
+    ns = int(leaf.size)
+    R = np.zeros((6, self.nleaf)) if rates is None else np.ascontiguousarray(rates, dtype=np.float64).copy()
+    rem = np.zeros((ns, 7)); bnd = np.zeros((ns, 7)); dust = np.zeros(ns); spec = np.zeros((ns, 300))
+    nseg = C.c_int64(0); tl = C.c_int64(0)
+    tr = np.zeros(max(trace_cap, 1), dtype=np.int64)
+    st = self.L.ftte_point(self.h, int(wl.size), _p(wl), _p(lum), _p(met), float(spectra["coef_spectrum"]), _p(ad),
+                           int(dust_approximation), int(max_pixel_level), ns, _p(leaf), _p(wt), _p(R), _p(rem), _p(bnd),
+                           _p(dust), _p(spec), C.byref(nseg), _p(tr) if trace_cap else None, int(trace_cap), C.byref(tl))
+    out = dict(rates=R, ndot_remaining=rem, ndot_boundary=bnd, ndot_dust=dust, ndot_spectrum=spec, nseg=nseg.value,
+               status=st)
+    if trace_cap:
+        out["trace"] = tr[:tl.value].copy()
+    return out
+
+
+OracleGrid.point = _point
+
+
+def point_tables(spectra, i_metal, coef_metal):
+    wl = _f64(spectra["wavelength"]); lum = _f64(spectra["lum"]); met = _f64(spectra["metallicity"])
+    ad = _f64(spectra["a_dust"])
+    out = np.zeros((6, 11 ** 4)); tot = C.c_double(0); sig = np.zeros((5, 300))
+    st = lib().ftte_point_tables(int(wl.size), _p(wl), _p(lum), _p(met), float(spectra["coef_spectrum"]), _p(ad),
+                                 int(i_metal), float(coef_metal), _p(out), C.byref(tot), _p(sig))
+    return dict(tables=out, total_integral=tot.value, output_sigma=sig, status=st)
 
 
 def direction(n_angular_level, iray):

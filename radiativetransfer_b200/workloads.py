@@ -35,7 +35,7 @@ def _sigmas(nu):
     d = np.sqrt(nu[m] / NU3 - 1)
     s25[m] = float(_f(1.58e-18)) * (NU3 / nu[m]) ** 4 * np.exp(4.0 - 4.0 * np.arctan(d) / d) / (1 - np.exp(-2.0 * PI / d))
     m = nu > NU2
-    s26[m] = float(_f(7.42e-18)) * (float(_f(1.66)) * (nu[m] / NU2) ** (-2.05) - float(_f(0.66)) * (nu[m] / NU2) ** (-3.05))
+    s26[m] = float(_f(7.42e-18)) * (float(_f(1.66)) * (nu[m] / NU2) ** float(_f(-2.05)) - float(_f(0.66)) * (nu[m] / NU2) ** float(_f(-3.05)))
     return s24, s25, s26
 
 
@@ -217,3 +217,27 @@ def disc_refine(max_level, r0=0.28, h0=0.06):
         s = 0.5 ** level
         return (level < max_level) & (R < r0 * s + size) & (np.abs(z - 0.5) < h0 * s + size)
     return f
+
+
+# ------------------------------------------------------------------------------------------------------
+# point sources
+# ------------------------------------------------------------------------------------------------------
+def synthetic_spectra(n_wave=1221, seed=0):
+    """Stand-in for the starburst99 tables the reference reads (equiSources.f90:840-892; not shipped with it):
+    blackbody-like spectra, hotter and brighter at lower metallicity, two time slices, on a log wavelength grid
+    91 A .. 1.6e6 A; plus SMC-type extinction-fit parameters in the layout of smc_dust_parameters.dat
+    (dustModule.f90:15-24: a(i,1)=lambda_i [micron], a(i,2)=a_i, a(i,3)=b_i, a(i,4)=p_i, a(i,5)=q_i)."""
+    wl_A = np.logspace(np.log10(91.0), np.log10(1.6e6), n_wave)
+    hc_over_k = 1.4387769e8  # Angstrom K
+    lum = np.zeros((5, 2, n_wave))
+    for m in range(5):
+        for t in range(2):
+            T = 4.5e4 * (1.0 - 0.05 * m) * (1.0 - 0.08 * t)
+            x = hc_over_k / (wl_A * T)
+            planck = 1.0 / (wl_A ** 5 * np.expm1(np.minimum(x, 600.0)))
+            lum[m, t] = np.log10(planck / planck.max()) + 40.0 - 0.1 * m - 0.2 * t
+    a_dust = np.array([[0.042, 185.0, 90.0, 2.0, 2.0], [0.08, 27.0, 5.5, 4.0, 4.0], [0.22, 0.005, -1.95, 2.0, 2.0],
+                       [9.7, 0.010, -1.95, 2.0, 2.0], [18.0, 0.012, -1.8, 2.0, 2.0], [25.0, 0.030, 0.0, 2.0, 2.0],
+                       [0.067, 10.0, 1.9, 4.0, 15.0]])
+    return dict(wavelength=wl_A * 1.0e-8, lum=lum, metallicity=np.log10(np.array([0.0004, 0.004, 0.008, 0.020, 0.050])),
+                coef_spectrum=0.37, a_dust=a_dust)
