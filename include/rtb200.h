@@ -56,7 +56,9 @@ const char* rtb200_status_string(int status);
 int rtb200_create(int device, rtb200_ctx** ctx);
 int rtb200_destroy(rtb200_ctx* ctx);
 int rtb200_set_math(rtb200_ctx* ctx, int math_mode);
-/* launch tuning knobs ("slots", "graph", "dense"); results do not depend on them */
+/* launch tuning knobs ("slots", "graph", "dense", "point_batch", ...); results do not depend on them.
+ * "portable_math" (default 1) selects, for the FAITHFUL point-source path, exp/log built from IEEE +,*,/,fma
+ * (csrc/portable_math.h) instead of CUDA libm, so that a host build of the same header reproduces it bit for bit. */
 int rtb200_set_tuning(rtb200_ctx* ctx, const char* key, double value);
 /* status raised by a device-side guard during an asynchronous (*_device) call since the last query; clears it */
 int rtb200_device_error(rtb200_ctx* ctx);
@@ -98,7 +100,52 @@ int rtb200_diffuse_rates_device(rtb200_ctx* ctx, const double* J_device, const d
                                 const double* ksi26, double* k24_device, double* k25_device, double* k26_device,
                                 void* stream);
 
+/* Point-source pass: replaces the source loop equiSources.f90:1256-1370 with its internal procedures
+ * startNewLongRay (:3120-3385), drawSegment (:2412-2595), find/zoom??Neighbour (:2647-2960),
+ * getRatesHydrogenHelium (:4157-4311) and the per-source table build stellarBetaTable.f90 (+ stellarPopulationModule.f90,
+ * dustModule.f90).  None of the reference's data files ship with it, so what it reads from disk is passed in:
+ *   nWave, wavelength[nWave]    wavelength grid of the population-synthesis spectra [cm], increasing (equiSources.f90:851-892)
+ *   lum[5][2][nWave]            log10 specific luminosity [erg/s/A]: metallicity m, time slices iSpectrum / iSpectrum+1
+ *   metallicity[5]              log10 Z of the five spectra;  coefSpectrum: time interpolation weight (:1241-1242)
+ *   aDust[7][5]                 rows of smc_dust_parameters.dat (dustModule.f90:15-24)
+ *   dustApproximation           0 noDust, 1 completeSublimation, 2 noSublimation (definitionsModule.f90:254)
+ *   maxPixelLevel               HEALPix level at which rays stop splitting (6 in the reference, 1..8 here)
+ *   srcLeaf[nsrc], srcWeight[nsrc]  host leaf (leaf order of rtb200_grid_set) and multiplicity of every merged source
+ *                               (star%hostCell / star%weight, :1169-1206); weight <= 0 is skipped (:1264).  Source
+ *                               sharding across GPUs = each rank passes its own subset, the caller sums the rates.
+ *   krate24,25,26, crate24,25,26 [nleaf]   ACCUMULATED (+=) like the reference's cell fields (zeroed by setZeroRates)
+ *   ndotRemaining[nsrc][7], ndotBoundary[nsrc][7], ndotDust[nsrc], ndotSpectrum[nsrc][300]  per-source escape
+ *                               diagnostics (:3198-3233); each may be NULL
+ *   nseg                        optional: ray-cell segment updates performed (iterations of the loop at :3168)
+ * rtb200_set_math: RTB200_MATH_FAITHFUL evaluates every table lookup with the reference's operation sequence;
+ * RTB200_MATH_FAST evaluates the same interpolant without the R(d) - R(d+tau) cancellation.                        */
+int rtb200_point(rtb200_ctx* ctx, int nWave, const double* wavelength, const double* lum, const double* metallicity,
+                 double coefSpectrum, const double* aDust, int dustApproximation, int maxPixelLevel, int32_t nsrc,
+                 const int32_t* srcLeaf, const int32_t* srcWeight, double* krate24, double* krate25, double* krate26,
+                 double* crate24, double* crate25, double* crate26, double* ndotRemaining, double* ndotBoundary,
+                 double* ndotDust, double* ndotSpectrum, int64_t* nseg);
+
+/* Same pass with the rates left on the GPU: rates_device = device pointer to [6][nleaf] doubles in the order krate24,
+ * krate25, krate26, crate24, crate25, crate26 (accumulated); the diagnostics are host pointers (NULL = not wanted). */
+int rtb200_point_device(rtb200_ctx* ctx, int nWave, const double* wavelength, const double* lum,
+                        const double* metallicity, double coefSpectrum, const double* aDust, int dustApproximation,
+                        int maxPixelLevel, int32_t nsrc, const int32_t* srcLeaf, const int32_t* srcWeight,
+                        double* rates_device, void* stream, double* ndotRemaining, double* ndotBoundary,
+                        double* ndotDust, double* ndotSpectrum, int64_t* nseg);
+
 /* --- debugging / parity exports (bit-exact traversal checks) ------------------------------------------- */
+/* point-source pass that also records every ray-cell segment: trace[2*i] = leaf<<32 | pixelLevel<<28 | pixel<<8 | exit
+ * face (2*plane + side; 0 = the ray split inside the cell), trace[2*i+1] = source<<52 | pixelLevel<<48 | pixel<<24 |
+ * index of the segment along its ray (a sort key: rays run concurrently).  rates6 = host [6][nleaf], accumulated. */
+int rtb200_point_trace(rtb200_ctx* ctx, int nWave, const double* wavelength, const double* lum,
+                       const double* metallicity, double coefSpectrum, const double* aDust, int dustApproximation,
+                       int maxPixelLevel, int32_t nsrc, const int32_t* srcLeaf, const int32_t* srcWeight,
+                       double* rates6, int64_t* nseg, int64_t* trace, int64_t traceCap, int64_t* traceLen);
+/* the six (0:10)^4 tables of stellarBetaTable.f90:217-285 for one metallicity bracket, [6][11^4] in Fortran element
+ * order: reactionRate1..3, energyRate1..3 */
+int rtb200_point_tables(rtb200_ctx* ctx, int nWave, const double* wavelength, const double* lum,
+                        const double* metallicity, double coefSpectrum, const double* aDust, int iMetal,
+                        double coefMetal, double* tables);
 /* zone number (1..24) and local angles of one direction: equiSources.f90:1391-1454 */
 int rtb200_direction(int nAngularLevel, int64_t iray, int32_t* izone, double* phi, double* theta);
 /* base-layer pattern table of one direction, [nx][12] = xy(x0,y0,len) xz(x0,z0,len) yz(y0,z0,len) xyTop xzTop yzTop */

@@ -67,6 +67,8 @@ int ftte_point(void* h, int nWave, const double* wavelength, const double* lum, 
                     ndotBoundary, ndotDust, ndotSpectrum, nseg, trace, traceCap, traceLen);
 }
 
+void ftte_set_portable_math(int on) { setPortableMath(on); }
+
 int ftte_point_tables(int nWave, const double* wavelength, const double* lum, const double* metallicity,
                       double coefSpectrum, const double* aDust, int iMetal, double coefMetal, double* out,
                       double* totalIntegral, double* outputSigma) {

@@ -116,6 +116,7 @@ struct PointSpectra {
 int pointSolve(Grid& g, const PointSpectra& S, int dustApproximation, int maxPixelLevel, int nsrc, const int32_t* srcLeaf,
                const int32_t* srcWeight, double* rates, double* ndotRemaining, double* ndotBoundary, double* ndotDust,
                double* ndotSpectrum, int64_t* nsegOut, int64_t* trace, int64_t traceCap, int64_t* traceLen);
+void setPortableMath(int on);
 int pointTables(const PointSpectra& S, int iMetal, double coefMetal, double* out, double* totalIntegral,
                 double* outputSigma);
 

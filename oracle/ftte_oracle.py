@@ -152,6 +152,12 @@ def _point(self, spectra, src_leaf, src_weight, dust_approximation=0, max_pixel_
 OracleGrid.point = _point
 
 
+def set_portable_math(on):
+    """point path: evaluate exp/log with radiativetransfer_b200/csrc/portable_math.h (IEEE +,*,/,fma only) instead
+    of libm -- the same source the CUDA kernels use in FAITHFUL mode, so deposits can be compared bit for bit"""
+    lib().ftte_set_portable_math(int(bool(on)))
+
+
 def point_tables(spectra, i_metal, coef_metal):
     wl = _f64(spectra["wavelength"]); lum = _f64(spectra["lum"]); met = _f64(spectra["metallicity"])
     ad = _f64(spectra["a_dust"])

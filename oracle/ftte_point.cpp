@@ -7,8 +7,18 @@
 //   dustModule.f90:30-73.
 // Single thread, libm, no FMA contraction.
 #include "ftte_common.h"
+// exp/log built from IEEE +,*,/,fma only; lives with the product because the device kernels use the same source.
+// With ftte_set_portable_math(1) the oracle evaluates the table sums, the table lookups and the escape diagnostics
+// with it instead of libm, which makes the CUDA path (RTB200_MATH_FAITHFUL) reproduce every deposit bit for bit.
+// Default is libm, as gfortran would link.
+#include "../radiativetransfer_b200/csrc/portable_math.h"
 
 namespace ftte {
+
+static bool g_portableMath = false;
+void setPortableMath(int on) { g_portableMath = on != 0; }
+static inline double xexp(double x) { return g_portableMath ? rtb_pm::pm_exp(x) : std::exp(x); }
+static inline double xlog(double x) { return g_portableMath ? rtb_pm::pm_log(x) : std::log(x); }
 
 static const int ndepth = 10;  // ndepth1..3, ndepthDust (definitionsModule.f90:72)
 static const int nT = 11 * 11 * 11 * 11;
@@ -119,7 +129,7 @@ void stellarBetaTable(const PointSpectra& S, int iMetal, double coefMetal, Point
             const int e = tix(i1, i2, i3, iD);
             for (int r = 0; r < 3; r++)
               if (freq >= thr[r]) {
-                double atmp = dtmp * std::exp(-(tau1 + tau2 + tau3 + tauDust));
+                double atmp = dtmp * xexp(-(tau1 + tau2 + tau3 + tauDust));
                 T.R[r][e] = T.R[r][e] + atmp;
                 T.E[r][e] = T.E[r][e] + (freq - thr[r]) * eV_to_erg * atmp;
               }
@@ -146,7 +156,7 @@ static int getRates(const PointTables& T, int dustApproximation, int reaction, d
   if (std::min(std::min(id1, id2), std::min(id3, idD)) < 0) return ERR_IDEPTH;
   if (id1 >= ndepth || id2 >= ndepth || id3 >= ndepth || idD >= ndepth) return ERR_IDEPTH;  // tau == 10 exactly: the reference reads out of bounds
   auto interp = [&](const std::vector<double>& A, int iD) {
-    auto lg = [&](int a, int b, int c) { return std::log(A[tix(a, b, c, iD)]); };
+    auto lg = [&](int a, int b, int c) { return xlog(A[tix(a, b, c, iD)]); };
     return c1 * ((1. - c3) * (1. - c2) * lg(id1 + 1, id2, id3) + c3 * (1. - c2) * lg(id1 + 1, id2, id3 + 1) +
                  c2 * (1. - c3) * lg(id1 + 1, id2 + 1, id3) + c3 * c2 * lg(id1 + 1, id2 + 1, id3 + 1)) +
            (1. - c1) * ((1. - c3) * (1. - c2) * lg(id1, id2, id3) + c3 * (1. - c2) * lg(id1, id2, id3 + 1) +
@@ -154,9 +164,9 @@ static int getRates(const PointTables& T, int dustApproximation, int reaction, d
   };
   const int r = reaction - 1;
   double nr1 = interp(T.R[r], idD), nr2 = interp(T.R[r], idD + 1);
-  numberRate = std::exp((1. - cD) * nr1 + cD * nr2);
+  numberRate = xexp((1. - cD) * nr1 + cD * nr2);
   double hr1 = interp(T.E[r], idD), hr2 = interp(T.E[r], idD + 1);
-  heatingRate = std::exp((1. - cD) * hr1 + cD * hr2);
+  heatingRate = xexp((1. - cD) * hr1 + cD * hr2);
   return OK;
 }
 
@@ -308,6 +318,7 @@ struct PointSolver {
   // localizeSplitContinuationCell (equiSources.f90:3049-3118)
   void localizeSplit(double x, double y, double z) {
     int i = (int)(x * g.nx) + 1, j = (int)(y * g.ny) + 1, k = (int)(z * g.nz) + 1;
+    if (i > g.nx || j > g.ny || k > g.nz) { splitCell = -1; return; }  // coordinate exactly 1: the reference reads cell(nx+1)
     splitSeq[0] = i; splitSeq[1] = j; splitSeq[2] = k;
     int cell = g.base(i, j, k);
     double xn = x * (double)(float)g.nx - (double)(float)(i - 1);
@@ -366,17 +377,17 @@ struct PointSolver {
         double t2 = radius * g.physicalBoxSize / (double)(float)g.nx;
         if (tmp >= t1 && tmp <= t2) {
           double ratio = (tmp - t1) / (t2 - t1);
-          ndotRemaining[ir] = ndotRemaining[ir] + ndot1 * std::exp(-(ratio * (tau1 + tauDust) + depth1 + depthDust));
+          ndotRemaining[ir] = ndotRemaining[ir] + ndot1 * xexp(-(ratio * (tau1 + tauDust) + depth1 + depthDust));
           if (ir == 6) {
             double o1 = ratio * tau1 + depth1, o2 = ratio * tau2 + depth2, o3 = ratio * tau3 + depth3;
             double oD = ratio * tauDust + depthDust;
-            ndotDust = ndotDust + ndot1 * std::exp(-oD);
+            ndotDust = ndotDust + ndot1 * xexp(-oD);
             for (int ie = 0; ie < 300; ie++) {
               double a1 = T->outputSigma24[ie] / (double)6.30e-18f * o1;
               double a2 = T->outputSigma26[ie] / (double)7.42e-18f * o2;
               double a3 = T->outputSigma25[ie] / (double)1.58e-18f * o3;
               double aD = T->outputSigmaDust[ie] / (double)5.4116737e-22f * oD;
-              ndotSpectrum[ie] = ndotSpectrum[ie] + ndot1 * std::exp(-(a1 + a2 + a3 + aD));
+              ndotSpectrum[ie] = ndotSpectrum[ie] + ndot1 * xexp(-(a1 + a2 + a3 + aD));
             }
           }
         }
@@ -430,6 +441,7 @@ struct PointSolver {
         }
         if (strategy != boundary) {
           localizeSplit(xbase, ybase, zbase);
+          if (splitCell < 0) return ERR_CHECKPOINT;
           if (splitPoint.x < 0. || splitPoint.x > 1. || splitPoint.y < 0. || splitPoint.y > 1. || splitPoint.z < 0. ||
               splitPoint.z > 1.) return ERR_CHECKPOINT;
           int sl = g.node[splitCell].level;

@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <algorithm>
 #include <string>
 
 #include "rtb200_internal.h"
@@ -34,7 +35,7 @@ static void free_grid(Context& c) {
   amr_release(c);
   cudaFree(c.dLevel); cudaFree(c.dHI); cudaFree(c.dHeI); cudaFree(c.dHeII); cudaFree(c.dRho); cudaFree(c.dAbun2);
   cudaFree(c.dKappa); cudaFree(c.tree.child); cudaFree(c.tree.leafX); cudaFree(c.tree.leafY); cudaFree(c.tree.leafZ);
-  cudaFree(c.dJ);
+  cudaFree(c.dJ); cudaFree(c.dRates); c.dRates = nullptr;
   c.dLevel = nullptr; c.dHI = c.dHeI = c.dHeII = c.dRho = c.dAbun2 = c.dKappa = c.dJ = nullptr;
   c.tree = DevTree();
   c.uniPlanKey.clear();
@@ -258,6 +259,8 @@ int rtb200_set_tuning(rtb200_ctx* h, const char* key, double value) {
   else if (k == "slots") c.tune.slots = (int)value;
   else if (k == "graph") c.tune.useGraph = (int)value;
   else if (k == "l2_mb") c.tune.l2BudgetMB = value;
+  else if (k == "portable_math") c.tune.portableMath = (int)value;
+  else if (k == "point_batch") c.tune.pointBatch = (int)value;
   else return RTB200_ERR_ARG;
   c.uniPlanKey.clear();
   if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
@@ -340,6 +343,101 @@ int rtb200_diffuse_rates_device(rtb200_ctx* h, const double* J, const double* ks
   if (!h || !J || !ksi24 || !ksi25 || !ksi26 || !k24 || !k25 || !k26 || h->c.nleaf == 0) return RTB200_ERR_ARG;
   RTB_CUDA(cudaSetDevice(h->c.device));
   return launch_diffuse_rates(h->c, J, ksi24, ksi25, ksi26, k24, k25, k26, (cudaStream_t)stream);
+}
+
+static PointInputs make_point_inputs(int nWave, const double* wavelength, const double* lum, const double* metallicity,
+                                     double coefSpectrum, const double* aDust, int dust, int maxPixelLevel, int nsrc,
+                                     const int32_t* srcLeaf, const int32_t* srcWeight) {
+  PointInputs in;
+  in.nWave = nWave; in.wavelength = wavelength; in.lum = lum; in.metallicity = metallicity;
+  in.coefSpectrum = coefSpectrum; in.aDust = aDust; in.dust = dust; in.maxPixelLevel = maxPixelLevel;
+  in.nsrc = nsrc; in.srcLeaf = srcLeaf; in.srcWeight = srcWeight;
+  return in;
+}
+
+static void split_diag(const std::vector<double>& d, int nsrc, double* rem, double* bnd, double* dust, double* spec) {
+  for (int s = 0; s < nsrc; s++) {
+    const double* p = d.data() + (size_t)s * 320;
+    if (rem) memcpy(rem + (size_t)s * 7, p, 56);
+    if (bnd) memcpy(bnd + (size_t)s * 7, p + 7, 56);
+    if (dust) dust[s] = p[14];
+    if (spec) memcpy(spec + (size_t)s * 300, p + 16, 2400);
+  }
+}
+
+int rtb200_point_device(rtb200_ctx* h, int nWave, const double* wavelength, const double* lum, const double* metallicity,
+                        double coefSpectrum, const double* aDust, int dustApproximation, int maxPixelLevel, int32_t nsrc,
+                        const int32_t* srcLeaf, const int32_t* srcWeight, double* rates_device, void* stream,
+                        double* ndotRemaining, double* ndotBoundary, double* ndotDust, double* ndotSpectrum,
+                        int64_t* nseg) {
+  if (!h || !rates_device) return RTB200_ERR_ARG;
+  PointInputs in = make_point_inputs(nWave, wavelength, lum, metallicity, coefSpectrum, aDust, dustApproximation,
+                                     maxPixelLevel, nsrc, srcLeaf, srcWeight);
+  const bool wantDiag = ndotRemaining || ndotBoundary || ndotDust || ndotSpectrum;
+  std::vector<double> diag(wantDiag ? (size_t)std::max(nsrc, 0) * 320 : 0);
+  int st = point_solve(h->c, in, rates_device, wantDiag ? diag.data() : nullptr, nseg, nullptr, 0, nullptr, nullptr,
+                       (cudaStream_t)stream);
+  if (st) return st;
+  if (wantDiag) split_diag(diag, nsrc, ndotRemaining, ndotBoundary, ndotDust, ndotSpectrum);
+  return RTB200_OK;
+}
+
+static int point_host_call(Context& c, const PointInputs& in, double* const k[6], double* rem, double* bnd, double* dust,
+                           double* spec, int64_t* nseg, long long* trace, long long traceCap, long long* traceLen) {
+  for (int i = 0; i < 6; i++)
+    if (!k[i]) return RTB200_ERR_ARG;
+  if (c.nleaf == 0) return RTB200_ERR_ARG;
+  RTB_CUDA(cudaSetDevice(c.device));
+  const size_t nb = (size_t)c.nleaf * sizeof(double);
+  if (!c.dRates) RTB_CUDA(cudaMalloc((void**)&c.dRates, 6 * nb));
+  for (int i = 0; i < 6; i++) RTB_CUDA(cudaMemcpyAsync(c.dRates + (size_t)i * c.nleaf, k[i], nb, cudaMemcpyHostToDevice, c.stream));
+  std::vector<double> diag((size_t)std::max(in.nsrc, 0) * 320);
+  int st = point_solve(c, in, c.dRates, diag.data(), nseg, trace, traceCap, traceLen, nullptr, c.stream);
+  if (st) return st;
+  for (int i = 0; i < 6; i++) RTB_CUDA(cudaMemcpyAsync(k[i], c.dRates + (size_t)i * c.nleaf, nb, cudaMemcpyDeviceToHost, c.stream));
+  RTB_CUDA(cudaStreamSynchronize(c.stream));
+  split_diag(diag, in.nsrc, rem, bnd, dust, spec);
+  return RTB200_OK;
+}
+
+int rtb200_point(rtb200_ctx* h, int nWave, const double* wavelength, const double* lum, const double* metallicity,
+                 double coefSpectrum, const double* aDust, int dustApproximation, int maxPixelLevel, int32_t nsrc,
+                 const int32_t* srcLeaf, const int32_t* srcWeight, double* krate24, double* krate25, double* krate26,
+                 double* crate24, double* crate25, double* crate26, double* ndotRemaining, double* ndotBoundary,
+                 double* ndotDust, double* ndotSpectrum, int64_t* nseg) {
+  if (!h) return RTB200_ERR_ARG;
+  PointInputs in = make_point_inputs(nWave, wavelength, lum, metallicity, coefSpectrum, aDust, dustApproximation,
+                                     maxPixelLevel, nsrc, srcLeaf, srcWeight);
+  double* k[6] = {krate24, krate25, krate26, crate24, crate25, crate26};
+  return point_host_call(h->c, in, k, ndotRemaining, ndotBoundary, ndotDust, ndotSpectrum, nseg, nullptr, 0, nullptr);
+}
+
+int rtb200_point_trace(rtb200_ctx* h, int nWave, const double* wavelength, const double* lum, const double* metallicity,
+                       double coefSpectrum, const double* aDust, int dustApproximation, int maxPixelLevel, int32_t nsrc,
+                       const int32_t* srcLeaf, const int32_t* srcWeight, double* rates6, int64_t* nseg, int64_t* trace,
+                       int64_t traceCap, int64_t* traceLen) {
+  if (!h || !rates6 || !trace || traceCap <= 0 || !traceLen) return RTB200_ERR_ARG;
+  PointInputs in = make_point_inputs(nWave, wavelength, lum, metallicity, coefSpectrum, aDust, dustApproximation,
+                                     maxPixelLevel, nsrc, srcLeaf, srcWeight);
+  double* k[6];
+  for (int i = 0; i < 6; i++) k[i] = rates6 + (size_t)i * h->c.nleaf;
+  long long tl = 0;
+  int st = point_host_call(h->c, in, k, nullptr, nullptr, nullptr, nullptr, nseg, (long long*)trace, traceCap, &tl);
+  *traceLen = tl;
+  return st;
+}
+
+int rtb200_point_tables(rtb200_ctx* h, int nWave, const double* wavelength, const double* lum, const double* metallicity,
+                        double coefSpectrum, const double* aDust, int iMetal, double coefMetal, double* tables) {
+  if (!h || !tables || iMetal < 1 || iMetal > 4 || h->c.nleaf == 0) return RTB200_ERR_ARG;
+  Context& c = h->c;
+  const int32_t leaf = 0, weight = 0;  // a source of weight 0 casts no rays: only its tables are built
+  PointInputs in = make_point_inputs(nWave, wavelength, lum, metallicity, coefSpectrum, aDust, 1, 1, 1, &leaf, &weight);
+  in.forceMetal = iMetal; in.forceCoefMetal = coefMetal;
+  RTB_CUDA(cudaSetDevice(c.device));
+  const size_t nb = (size_t)c.nleaf * sizeof(double);
+  if (!c.dRates) RTB_CUDA(cudaMalloc((void**)&c.dRates, 6 * nb));
+  return point_solve(c, in, c.dRates, nullptr, nullptr, nullptr, 0, nullptr, tables, c.stream);
 }
 
 int rtb200_device_error(rtb200_ctx* h) {  // status raised by device-side guards of asynchronous calls

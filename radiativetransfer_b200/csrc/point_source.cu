@@ -1,0 +1,790 @@
+// Point-source ray casting with per-cell rate deposition on the GPU.
+//
+// Replaces the reference's source loop and its internal procedures (all in equiSources.f90):
+//   :1256-1370  loop over sources, 12 base rays each          -> point_solve() below
+//   :3120-3385  startNewLongRay (march / deposit / split x4)   -> point_march_kernel, one launch per pixel level
+//   :2412-2595  drawSegment                                    -> draw_segment()
+//   :2647-2960  find/zoom{XY,YZ,XZ}Neighbour                   -> step_neighbour() on the linear octree
+//   :3011-3118  absoluteCoordinates, localizeSplitContinuationCell -> child_start()
+//   :4157-4311  getRatesHydrogenHelium                         -> rates_faithful() / FAST-mode slopes
+//   stellarBetaTable.f90:217-285 (400 x 11^4 table sums)       -> point_table_kernel (stores LOG tables)
+//
+// Formulation.  The reference recurses depth-first: a ray marches until its radius reaches rmax(pixelLevel), then
+// splits into the 4 nested HEALPix children, which inherit the accumulated optical depths.  Here the ray tree is
+// processed breadth-first, one kernel launch per pixel level: thread = one ray object (source, pixel); it reads its
+// parent's end state (leaf, point, radius, depths), applies the reference's continuation arithmetic, marches and
+// deposits, and stores its own end state for the next level.  The arithmetic of every ray is that of the
+// reference, operation for operation (no FMA contraction in anything that decides a branch); only the order in which
+// different rays add to the same cell differs.
+//
+// Data layout: the grid is the per-leaf SoA of the context (leaf order of the reference) + the linear octree
+// `child[]`; per-source log-tables [6][planes][11^3] (64 KB without dust: L1/L2 resident); ray end states
+// [source][pixel] AoS of 80 B, ping-pong between levels; rates [6][nleaf] fp64, accumulated with fp64 RED
+// (atomicAdd, native on sm_100) -- the deterministic, atomic-free segmented variant sorts (leaf, deposit) records.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
+#include "point_host.h"
+#include "portable_math.h"
+#include "rtb200_internal.h"
+
+namespace rtb {
+
+namespace {
+
+constexpr int kPlane = 11 * 11 * 11;
+constexpr int kDiagStride = 320;  // per source: remaining[7], boundary[7], dust, pad, spectrum[300]
+constexpr int kMaxPixelLevel = 8;
+
+__device__ __forceinline__ double M(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double A(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double S(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double D(double a, double b) { return __ddiv_rn(a, b); }
+
+struct RayState {  // end state of a ray object, read by its 4 children
+  double x, y, z, radius, d1, d2, d3, dD;
+  int32_t leaf;
+  int32_t strategy;  // 2 = split (children continue), anything else: children do not exist
+  int32_t pad[2];
+};
+static_assert(sizeof(RayState) == 80, "RayState layout");
+
+struct PointParams {
+  // grid
+  const int32_t* child;
+  const int8_t* level;
+  const int32_t *leafX, *leafY, *leafZ;
+  const double *HI, *HeI, *HeII, *rho, *abun2;
+  int64_t nleaf;
+  int nx;
+  double boxSize;
+  // sources of this batch
+  const int32_t* srcLeaf;
+  const int32_t* srcWeight;
+  const double* logTab;   // [nsrc][6][planes][kPlane]
+  int planes;             // 1 without dust, 11 with
+  int dust;
+  int maxPixelLevel;
+  // tables
+  const double* pixDir;   // [npix(levels 1..max)][3]
+  double rmax[kMaxPixelLevel + 2];
+  double outRadiusKpc[7]; // outputRadius(i) * kpc  [cm]
+  double outRadius[7];
+  double kpc;
+  const double* outSigma; // [4][300] ratios sigma(nu)/sigma_threshold: 24, 26, 25, dust
+  // outputs
+  double* rates;          // [6][nleaf]: krate24, krate25, krate26, crate24, crate25, crate26
+  double* diag;           // [nsrc][kDiagStride]
+  RayState* stateIn;      // level-1 states  [nsrc][npix(level-1)]
+  RayState* stateOut;     // this level's    [nsrc][npix(level)]
+  unsigned long long* nseg;
+  int32_t* err;
+  // optional traversal trace (parity checks)
+  long long* trace;       // [cap][2]
+  unsigned long long* traceLen;
+  long long traceCap;
+};
+
+struct Cell {
+  int32_t leaf, lvl, X, Y, Z;  // integer coordinates at the leaf's own level
+};
+
+__device__ __forceinline__ int64_t pix_offset(int level) {  // first pixel of `level` in the direction table
+  return 4 * ((1LL << (2 * (level - 1))) - 1);              // 12 * (4^(L-1) - 1) / 3
+}
+
+// find??Neighbour + zoom??Neighbour (equiSources.f90:2647-2960).  axis = normal of the exit face (0 x, 1 y, 2 z);
+// (a, b) = the exit point in the two in-face coordinates, ordered (x,y) / (y,z) / (x,z).  Climb while the cell lies on
+// that face of its parent (halving the in-face coordinates), step to the sibling container, descend with the
+// reference's `.lt.0.5` tests.  Returns false at the domain boundary.
+__device__ __forceinline__ bool step_neighbour(const PointParams& P, Cell& c, int axis, int side, double& a, double& b) {
+  const int L = c.lvl;
+  const int Cax = axis == 0 ? c.X : (axis == 1 ? c.Y : c.Z);
+  const int CA = axis == 2 ? c.X : (axis == 0 ? c.Y : c.X);
+  const int CB = axis == 2 ? c.Y : c.Z;
+  int l = L;
+  while (l > 0) {
+    const int sh = L - l;
+    if (((Cax >> sh) & 1) != side) break;
+    a = ((CA >> sh) & 1) ? A(M(0.5, a), 0.5) : M(0.5, a);
+    b = ((CB >> sh) & 1) ? A(M(0.5, b), 0.5) : M(0.5, b);
+    l--;
+  }
+  const int sh = L - l;
+  int cx = c.X >> sh, cy = c.Y >> sh, cz = c.Z >> sh;
+  if (l == 0) {
+    const int base = axis == 0 ? cx : (axis == 1 ? cy : cz);
+    if ((side == 0 && base == 0) || (side == 1 && base == P.nx - 1)) return false;
+  }
+  const int stepv = side ? 1 : -1;
+  if (axis == 0) cx += stepv; else if (axis == 1) cy += stepv; else cz += stepv;
+  int node = ((cx >> l) * P.nx + (cy >> l)) * P.nx + (cz >> l);
+  for (int t = l - 1; t >= 0; t--)
+    node = __ldg(P.child + node) + ((((cx >> t) & 1) << 2) | (((cy >> t) & 1) << 1) | ((cz >> t) & 1));
+  int ch;
+  while ((ch = __ldg(P.child + node)) >= 0) {
+    int ia, ib;
+    if (a < 0.5) { a = M(2., a); ia = 0; } else { a = S(M(2., a), 1.); ia = 1; }
+    if (b < 0.5) { b = M(2., b); ib = 0; } else { b = S(M(2., b), 1.); ib = 1; }
+    const int in = side == 0 ? 1 : 0;
+    int bx, by, bz;
+    if (axis == 2) { bx = ia; by = ib; bz = in; }
+    else if (axis == 0) { bx = in; by = ia; bz = ib; }
+    else { bx = ia; by = in; bz = ib; }
+    node = ch + ((bx << 2) | (by << 1) | bz);
+    cx = 2 * cx + bx; cy = 2 * cy + by; cz = 2 * cz + bz;
+    l++;
+  }
+  c.leaf = -ch - 1; c.lvl = l; c.X = cx; c.Y = cy; c.Z = cz;
+  return true;
+}
+
+// --- table lookup, reference operation sequence (equiSources.f90:4205-4238) -----------------------------------------
+template <bool PORTABLE>
+__device__ __forceinline__ double exp_ref(double x) { return PORTABLE ? rtb_pm::pm_exp(x) : exp(x); }
+
+__device__ __forceinline__ double interp_log(const double* __restrict__ T, int i1, int i2, int i3, double c1, double c2,
+                                             double c3) {
+  const double m3 = S(1., c3), m2 = S(1., c2), m1 = S(1., c1);
+  const double w00 = M(m3, m2), w01 = M(c3, m2), w10 = M(c2, m3), w11 = M(c3, c2);
+  const double* p = T + (i3 * 11 + i2) * 11 + i1;
+  const double up = A(A(A(M(w00, __ldg(p + 1)), M(w01, __ldg(p + 122))), M(w10, __ldg(p + 12))), M(w11, __ldg(p + 133)));
+  const double lo = A(A(A(M(w00, __ldg(p)), M(w01, __ldg(p + 121))), M(w10, __ldg(p + 11))), M(w11, __ldg(p + 132)));
+  return A(M(c1, up), M(m1, lo));
+}
+
+struct DepthIdx {
+  int i1, i2, i3, iD;
+  double c1, c2, c3, cD;
+  int status;  // 0 ok, 1 beyond the table (rates are zero), <0 error
+};
+
+__device__ __forceinline__ DepthIdx depth_index(double t1, double t2, double t3, double tD, int dust) {
+  DepthIdx q;
+  q.status = 0;
+  if (t1 > 10. || t2 > 10. || t3 > 10. || tD > 10.) { q.status = 1; return q; }
+  q.i1 = (int)M(D(t1, 10.), 10.); q.i2 = (int)M(D(t2, 10.), 10.); q.i3 = (int)M(D(t3, 10.), 10.);
+  q.c1 = S(D(M(t1, 10.), 10.), (double)q.i1);
+  q.c2 = S(D(M(t2, 10.), 10.), (double)q.i2);
+  q.c3 = S(D(M(t3, 10.), 10.), (double)q.i3);
+  if (dust == 0) { q.iD = 0; q.cD = 0.; }
+  else { q.iD = (int)M(D(tD, 10.), 10.); q.cD = S(D(M(tD, 10.), 10.), (double)q.iD); }
+  if (min(min(q.i1, q.i2), min(q.i3, q.iD)) < 0) q.status = -1;
+  // tau == 10 exactly: the reference indexes one past its (0:10) tables; reported instead of reproduced
+  if (q.i1 >= 10 || q.i2 >= 10 || q.i3 >= 10 || q.iD >= 10) q.status = -1;
+  return q;
+}
+
+template <bool PORTABLE>
+__device__ __forceinline__ int rates_faithful(const PointParams& P, const double* __restrict__ LT, int r, double t1,
+                                              double t2, double t3, double tD, double& num, double& heat) {
+  const DepthIdx q = depth_index(t1, t2, t3, tD, P.dust);
+  if (q.status == 1) { num = 0.; heat = 0.; return 0; }
+  if (q.status < 0) return RTB200_ERR_IDEPTH;
+  const double* R = LT + (size_t)r * P.planes * kPlane + (size_t)q.iD * kPlane;
+  const double* E = LT + (size_t)(3 + r) * P.planes * kPlane + (size_t)q.iD * kPlane;
+  const double nr1 = interp_log(R, q.i1, q.i2, q.i3, q.c1, q.c2, q.c3);
+  const double hr1 = interp_log(E, q.i1, q.i2, q.i3, q.c1, q.c2, q.c3);
+  if (P.dust) {
+    const double nr2 = interp_log(R + kPlane, q.i1, q.i2, q.i3, q.c1, q.c2, q.c3);
+    const double hr2 = interp_log(E + kPlane, q.i1, q.i2, q.i3, q.c1, q.c2, q.c3);
+    const double mD = S(1., q.cD);
+    num = exp_ref<PORTABLE>(A(M(mD, nr1), M(q.cD, nr2)));
+    heat = exp_ref<PORTABLE>(A(M(mD, hr1), M(q.cD, hr2)));
+  } else {  // cDust = 0: exp((1.-0.)*nr1 + 0.*nr2) == exp(nr1) exactly; the second dust plane is never needed
+    num = exp_ref<PORTABLE>(nr1);
+    heat = exp_ref<PORTABLE>(hr1);
+  }
+  return 0;
+}
+
+// --- FAST mode: the same piecewise-multilinear log-interpolant, evaluated without the cancellation -----------------
+// R_r(d) - R_r(d + tau e_r) = R_r(d) * (1 - exp(dlog)),  dlog = nr(d + tau e_r) - nr(d) = integral of the interpolant's
+// slope along axis r, which is piecewise constant: per crossed table cell the slope is a bilinear (trilinear with dust)
+// combination of node differences.  One exponential + one expm1 per (reaction, table) instead of two exponentials whose
+// difference cancels; corners of the start cell are shared by the three reactions' weights.
+struct Weights {
+  double w[3][2];  // [axis 1..3][low/high]
+  double wD[2];
+};
+
+__device__ __forceinline__ double tab(const double* __restrict__ T, int i1, int i2, int i3, int iD) {
+  return __ldg(T + ((iD * 11 + i3) * 11 + i2) * 11 + i1);
+}
+
+// value of the log-interpolant of table T at index-space point (x1,x2,x3,xD) given by cell indices and weights
+__device__ __forceinline__ double interp_full(const double* __restrict__ T, const DepthIdx& q, int dust) {
+  double acc = 0.;
+  const int nD = dust ? 2 : 1;
+  for (int kD = 0; kD < nD; kD++) {
+    const double wD = dust ? (kD ? q.cD : 1. - q.cD) : 1.;
+    double accD = 0.;
+#pragma unroll
+    for (int k3 = 0; k3 < 2; k3++) {
+      const double w3 = k3 ? q.c3 : 1. - q.c3;
+#pragma unroll
+      for (int k2 = 0; k2 < 2; k2++) {
+        const double w2 = k2 ? q.c2 : 1. - q.c2;
+        const double lo = tab(T, q.i1, q.i2 + k2, q.i3 + k3, q.iD + kD), hi = tab(T, q.i1 + 1, q.i2 + k2, q.i3 + k3, q.iD + kD);
+        accD += w3 * w2 * (lo + q.c1 * (hi - lo));
+      }
+    }
+    acc += wD * accD;
+  }
+  return acc;
+}
+
+// slope of the log-interpolant along `axis` (0,1,2 = tau1,tau2,tau3) inside the table cell `cellIdx` of that axis, at
+// the transverse position of q
+__device__ __forceinline__ double slope_axis(const double* __restrict__ T, const DepthIdx& q, int dust, int axis, int cellIdx) {
+  double acc = 0.;
+  const int nD = dust ? 2 : 1;
+  const int ia = axis == 0 ? 1 : 0, ib = axis == 2 ? 1 : 2;  // the two transverse depth axes
+  const int qi[3] = {q.i1, q.i2, q.i3};
+  const double qc[3] = {q.c1, q.c2, q.c3};
+  for (int kD = 0; kD < nD; kD++) {
+    const double wD = dust ? (kD ? q.cD : 1. - q.cD) : 1.;
+    double accD = 0.;
+#pragma unroll
+    for (int kb = 0; kb < 2; kb++) {
+#pragma unroll
+      for (int ka = 0; ka < 2; ka++) {
+        int idx[3];
+        idx[axis] = cellIdx; idx[ia] = qi[ia] + ka; idx[ib] = qi[ib] + kb;
+        const double lo = tab(T, idx[0], idx[1], idx[2], q.iD + kD);
+        idx[axis] = cellIdx + 1;
+        const double hi = tab(T, idx[0], idx[1], idx[2], q.iD + kD);
+        accD += (ka ? qc[ia] : 1. - qc[ia]) * (kb ? qc[ib] : 1. - qc[ib]) * (hi - lo);
+      }
+    }
+    acc += wD * accD;
+  }
+  return acc;
+}
+
+// deposit of reaction r (number and energy) for a step tau along its own depth axis, FAST mode
+__device__ __forceinline__ void rates_fast(const PointParams& P, const double* __restrict__ LT, const DepthIdx& q, int r,
+                                           double depthAxis, double tau, double& dnum, double& dheat) {
+  // axis of reaction r: r = 0 -> tau1, r = 1 -> tau2, r = 2 -> tau3
+  const double* R = LT + (size_t)r * P.planes * kPlane;
+  const double* E = LT + (size_t)(3 + r) * P.planes * kPlane;
+  const double n0 = exp(interp_full(R, q, P.dust)), h0 = exp(interp_full(E, q, P.dust));
+  const double end = depthAxis + tau;
+  if (end > 10.) { dnum = n0; dheat = h0; return; }  // the table returns 0 beyond tau = 10
+  if (tau == 0.) { dnum = 0.; dheat = 0.; return; }
+  const int i0 = r == 0 ? q.i1 : (r == 1 ? q.i2 : q.i3);
+  int iEnd = (int)end;  // index space == tau space (spacing 1)
+  if (iEnd > 9) iEnd = 9;
+  double dn = 0., dh = 0.;
+  for (int c = i0; c <= iEnd; c++) {
+    const double lo = c == i0 ? depthAxis : (double)c;
+    const double hi = c == iEnd ? end : (double)(c + 1);
+    const double len = hi - lo;
+    dn += len * slope_axis(R, q, P.dust, r, c);
+    dh += len * slope_axis(E, q, P.dust, r, c);
+  }
+  dnum = -n0 * expm1(dn);
+  dheat = -h0 * expm1(dh);
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+template <bool FAITHFUL, bool PORTABLE, bool TRACE>
+__global__ void __launch_bounds__(128) point_march_kernel(const __grid_constant__ PointParams P, int pixelLevel) {
+  const int64_t npix = 12LL << (2 * (pixelLevel - 1));
+  const int64_t ipix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = blockIdx.y;
+  unsigned long long mySegs = 0;
+  const bool last = pixelLevel == P.maxPixelLevel;
+  bool active = ipix < npix;
+  const int weight = __ldg(P.srcWeight + s);
+  if (weight <= 0) active = false;
+
+  Cell c{0, 0, 0, 0, 0};
+  double px = 0.5, py = 0.5, pz = 0.5, radius = 0., d1 = 0., d2 = 0., d3 = 0., dD = 0.;
+  // ndot1 = float(weight) / 12.d0, then / 4.d0 per split level (exact)
+  double ndot = M(D((double)(float)weight, 12.), 1.0 / (double)(1LL << (2 * (pixelLevel - 1))));
+  double* diag = P.diag + (size_t)s * kDiagStride;
+  const double fnx = (double)(float)P.nx;
+  int strategy = 1;
+
+  if (active) {
+    if (pixelLevel == 1) {
+      c.leaf = __ldg(P.srcLeaf + s);
+    } else {
+      // ---- continuation after a split (equiSources.f90:3303-3378) ----
+      const int64_t parent = ipix >> 2;
+      const int q = (int)(ipix & 3);
+      const RayState ps = P.stateIn[(size_t)s * (npix >> 2) + parent];
+      if (ps.strategy != 2) active = false;
+      else {
+        const int pl = __ldg(P.level + ps.leaf);
+        const int X = __ldg(P.leafX + ps.leaf), Y = __ldg(P.leafY + ps.leaf), Z = __ldg(P.leafZ + ps.leaf);
+        double ax = ps.x, ay = ps.y, az = ps.z;  // absoluteCoordinates (:3011-3047)
+        for (int t = 0; t < pl; t++) {
+          ax = ((X >> t) & 1) ? A(M(0.5, ax), 0.5) : M(0.5, ax);
+          ay = ((Y >> t) & 1) ? A(M(0.5, ay), 0.5) : M(0.5, ay);
+          az = ((Z >> t) & 1) ? A(M(0.5, az), 0.5) : M(0.5, az);
+        }
+        const double xbase = D(A((double)(float)(X >> pl), ax), fnx);
+        const double ybase = D(A((double)(float)(Y >> pl), ay), fnx);
+        const double zbase = D(A((double)(float)(Z >> pl), az), fnx);
+        const double* pd = P.pixDir + 3 * (pix_offset(pixelLevel - 1) + parent);
+        const double rn = D(ps.radius, fnx);
+        double xb = 0, yb = 0, zb = 0;
+        // every sibling that starts outside the box is counted as boundary loss; the reference leaves
+        // `strategy = boundary` set afterwards, so the LATER siblings inside the box are skipped without being counted
+        bool earlierOut = false;
+        for (int sib = 0; sib <= q; sib++) {
+          const double* cd = P.pixDir + 3 * (pix_offset(pixelLevel) + 4 * parent + sib);
+          xb = A(xbase, M(rn, S(__ldg(cd), __ldg(pd))));
+          yb = A(ybase, M(rn, S(__ldg(cd + 1), __ldg(pd + 1))));
+          zb = A(zbase, M(rn, S(__ldg(cd + 2), __ldg(pd + 2))));
+          const bool out = xb < 0. || xb > 1. || yb < 0. || yb > 1. || zb < 0. || zb > 1.;
+          if (sib < q) earlierOut = earlierOut || out;
+          else if (out) {
+            const double tmp = D(M(ps.radius, P.boxSize), M(fnx, P.kpc));
+            for (int ir = 0; ir < 7; ir++)
+              if (P.outRadius[ir] > tmp) atomicAdd(diag + 7 + ir, ndot);  // ndot1/4. of the parent
+            active = false;
+          }
+        }
+        if (earlierOut) active = false;
+        if (active) {  // localizeSplitContinuationCell (:3049-3118)
+          int bi = (int)M(xb, fnx), bj = (int)M(yb, fnx), bk = (int)M(zb, fnx);
+          if (bi >= P.nx || bj >= P.nx || bk >= P.nx) {  // coordinate exactly 1: the reference indexes cell(nx+1)
+            atomicExch(P.err, RTB200_ERR_CHECKPOINT);
+            active = false;
+          } else {
+            double xn = S(M(xb, fnx), (double)(float)bi), yn = S(M(yb, fnx), (double)(float)bj),
+                   zn = S(M(zb, fnx), (double)(float)bk);
+            int node = (bi * P.nx + bj) * P.nx + bk, lvl = 0, ch;
+            while ((ch = __ldg(P.child + node)) >= 0) {
+              const int i = xn < 0.5 ? 0 : 1, j = yn < 0.5 ? 0 : 1, k = zn < 0.5 ? 0 : 1;
+              xn = i ? S(M(2., xn), 1.) : M(2., xn);
+              yn = j ? S(M(2., yn), 1.) : M(2., yn);
+              zn = k ? S(M(2., zn), 1.) : M(2., zn);
+              node = ch + ((i << 2) | (j << 1) | k);
+              bi = 2 * bi + i; bj = 2 * bj + j; bk = 2 * bk + k;
+              lvl++;
+            }
+            if (xn < 0. || xn > 1. || yn < 0. || yn > 1. || zn < 0. || zn > 1.) {  // checkPoint (:2962)
+              atomicExch(P.err, RTB200_ERR_CHECKPOINT);
+              active = false;
+            }
+            c.leaf = -ch - 1; c.lvl = lvl; c.X = bi; c.Y = bj; c.Z = bk;
+            px = xn; py = yn; pz = zn;
+            radius = ps.radius; d1 = ps.d1; d2 = ps.d2; d3 = ps.d3; dD = ps.dD;
+          }
+        }
+      }
+    }
+  }
+
+  if (active) {
+    if (pixelLevel == 1) {
+      c.lvl = __ldg(P.level + c.leaf);
+      c.X = __ldg(P.leafX + c.leaf); c.Y = __ldg(P.leafY + c.leaf); c.Z = __ldg(P.leafZ + c.leaf);
+    }
+    const double* dir = P.pixDir + 3 * (pix_offset(pixelLevel) + ipix);
+    const double prox = __ldg(dir), proy = __ldg(dir + 1), proz = __ldg(dir + 2);
+    const double* LT = P.logTab + (size_t)s * 6 * P.planes * kPlane;
+    const double rmaxL = P.rmax[pixelLevel];
+
+    while (strategy == 1) {
+      const double oldRadius = radius;
+      // ---- drawSegment (:2412-2595) ----
+      const double tmp1 = proz > 0. ? D(S(1., pz), proz) : D(-pz, proz);
+      const double tmp2 = prox > 0. ? D(S(1., px), prox) : D(-px, prox);
+      const double tmp3 = proy > 0. ? D(S(1., py), proy) : D(-py, proy);
+      int dirn; double tmp;
+      if (tmp1 < fmin(tmp2, tmp3)) { dirn = 1; tmp = tmp1; }
+      else if (tmp2 < fmin(tmp1, tmp3)) { dirn = 2; tmp = tmp2; }
+      else { dirn = 3; tmp = tmp3; }
+      const double scale = (double)(1 << c.lvl);
+      const Cell here = c;
+      double len;
+      int face = 0;
+      if (A(M(radius, scale), tmp) < rmaxL || last) {
+        len = tmp;
+        radius = A(radius, D(tmp, scale));
+        const double ex = A(px, M(tmp, prox)), ey = A(py, M(tmp, proy)), ez = A(pz, M(tmp, proz));
+        int side; bool inside;
+        if (dirn == 1) {
+          side = proz < 0. ? 0 : 1;
+          double a = ex, b = ey;
+          inside = step_neighbour(P, c, 2, side, a, b);
+          if (inside) { pz = side == 0 ? 1. : 0.; px = a; py = b; }
+        } else if (dirn == 2) {
+          side = prox < 0. ? 0 : 1;
+          double a = ey, b = ez;
+          inside = step_neighbour(P, c, 0, side, a, b);
+          if (inside) { px = side == 0 ? 1. : 0.; py = a; pz = b; }
+        } else {
+          side = proy < 0. ? 0 : 1;
+          double a = ex, b = ez;
+          inside = step_neighbour(P, c, 1, side, a, b);
+          if (inside) { py = side == 0 ? 1. : 0.; px = a; pz = b; }
+        }
+        face = dirn * 2 + side;
+        if (!inside) strategy = 3;
+        else if (px < 0. || px > 1. || py < 0. || py > 1. || pz < 0. || pz > 1.) {
+          atomicExch(P.err, RTB200_ERR_CHECKPOINT);
+          break;
+        }
+      } else if (M(radius, scale) >= rmaxL) {
+        strategy = 2;
+        len = 0.;
+      } else {
+        strategy = 2;
+        tmp = S(rmaxL, M(radius, scale));
+        len = tmp;
+        radius = A(radius, D(tmp, scale));
+        px = A(px, M(tmp, prox)); py = A(py, M(tmp, proy)); pz = A(pz, M(tmp, proz));
+      }
+      mySegs++;
+      if (TRACE) {
+        const unsigned long long slot = atomicAdd(P.traceLen, 1ULL);
+        if ((long long)slot < P.traceCap) {
+          P.trace[2 * slot] = ((long long)here.leaf << 32) | ((long long)pixelLevel << 28) | ((long long)ipix << 8) | face;
+          P.trace[2 * slot + 1] = ((long long)s << 52) | ((long long)pixelLevel << 48) | ((long long)ipix << 24) |
+                                  (long long)(mySegs - 1);
+        }
+      }
+
+      // ---- optical depths of the segment (:3176-3196) ----
+      const int64_t lf = here.leaf;
+      const double cellSize = D(P.boxSize, M(scale, fnx));
+      const double plen = M(cellSize, len);
+      const double hi = __ldg(P.HI + lf);
+      const double tau1 = M(M(plen, hi), (double)6.3e-18f);
+      const double tau2 = M(M(plen, __ldg(P.HeI + lf)), (double)7.42e-18f);
+      const double tau3 = M(M(plen, __ldg(P.HeII + lf)), (double)1.58e-18f);
+      double tauD = 0.;
+      if (P.dust == 1) tauD = D(M(M(M(plen, hi), (double)5.4116737e-22f), __ldg(P.abun2 + lf)), (double)0.2f);
+      else if (P.dust == 2)
+        tauD = D(M(M(D(M(M(plen, (double)0.76f), __ldg(P.rho + lf)), (double)1.6726231e-24f), (double)5.4116737e-22f),
+                   __ldg(P.abun2 + lf)), (double)0.2f);
+
+      // ---- escape diagnostics (:3198-3233) ----
+      {
+        const double t1 = D(M(oldRadius, P.boxSize), fnx), t2 = D(M(radius, P.boxSize), fnx);
+        for (int ir = 0; ir < 7; ir++) {
+          const double tr = P.outRadiusKpc[ir];
+          if (tr >= t1 && tr <= t2) {
+            const double ratio = D(S(tr, t1), S(t2, t1));
+            atomicAdd(diag + ir, M(ndot, exp_ref<PORTABLE>(-A(A(M(ratio, A(tau1, tauD)), d1), dD))));
+            if (ir == 6) {
+              const double o1 = A(M(ratio, tau1), d1), o2 = A(M(ratio, tau2), d2), o3 = A(M(ratio, tau3), d3),
+                           oD = A(M(ratio, tauD), dD);
+              atomicAdd(diag + 14, M(ndot, exp_ref<PORTABLE>(-oD)));
+              for (int ie = 0; ie < 300; ie++) {
+                const double a1 = M(__ldg(P.outSigma + ie), o1), a2 = M(__ldg(P.outSigma + 300 + ie), o2),
+                             a3 = M(__ldg(P.outSigma + 600 + ie), o3), aD = M(__ldg(P.outSigma + 900 + ie), oD);
+                atomicAdd(diag + 16 + ie, M(ndot, exp_ref<PORTABLE>(-A(A(A(a1, a2), a3), aD))));
+              }
+            }
+          }
+        }
+        if (strategy == 3) {
+          const double tb = D(M(radius, P.boxSize), M(fnx, P.kpc));
+          for (int ir = 0; ir < 7; ir++)
+            if (P.outRadius[ir] > tb) atomicAdd(diag + 7 + ir, ndot);
+        }
+      }
+      if (fmin(fmin(A(d1, tau1), A(d2, tau2)), fmin(A(d3, tau3), A(dD, tauD))) > 100.) strategy = 3;
+
+      // ---- rates for the entire cell (:3247-3260) ----
+      double dep[6];  // krate24, krate25, krate26, crate24, crate25, crate26
+      if (FAITHFUL) {
+        double a, b, ea, eb;
+        int st = rates_faithful<PORTABLE>(P, LT, 0, d1, d2, d3, dD, a, ea);
+        if (!st) st = rates_faithful<PORTABLE>(P, LT, 0, A(d1, tau1), d2, d3, dD, b, eb);
+        dep[0] = M(ndot, S(a, b)); dep[3] = M(ndot, S(ea, eb));
+        if (!st) st = rates_faithful<PORTABLE>(P, LT, 1, d1, d2, d3, dD, a, ea);
+        if (!st) st = rates_faithful<PORTABLE>(P, LT, 1, d1, A(d2, tau2), d3, dD, b, eb);
+        dep[2] = M(ndot, S(a, b)); dep[5] = M(ndot, S(ea, eb));
+        if (!st) st = rates_faithful<PORTABLE>(P, LT, 2, d1, d2, d3, dD, a, ea);
+        if (!st) st = rates_faithful<PORTABLE>(P, LT, 2, d1, d2, A(d3, tau3), dD, b, eb);
+        dep[1] = M(ndot, S(a, b)); dep[4] = M(ndot, S(ea, eb));
+        if (st) { atomicExch(P.err, st); break; }
+      } else {
+        const DepthIdx q = depth_index(d1, d2, d3, dD, P.dust);
+        if (q.status < 0) { atomicExch(P.err, RTB200_ERR_IDEPTH); break; }
+        if (q.status == 1) {
+          for (int i = 0; i < 6; i++) dep[i] = 0.;
+        } else {
+          double n, h;
+          rates_fast(P, LT, q, 0, d1, tau1, n, h); dep[0] = ndot * n; dep[3] = ndot * h;
+          rates_fast(P, LT, q, 1, d2, tau2, n, h); dep[2] = ndot * n; dep[5] = ndot * h;
+          rates_fast(P, LT, q, 2, d3, tau3, n, h); dep[1] = ndot * n; dep[4] = ndot * h;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+        if (dep[i] != 0.) atomicAdd(P.rates + (size_t)i * P.nleaf + lf, dep[i]);
+
+      d1 = A(d1, tau1); d2 = A(d2, tau2); d3 = A(d3, tau3); dD = A(dD, tauD);
+    }
+  }
+
+  // warp-aggregated segment count
+  for (int o = 16; o; o >>= 1) mySegs += __shfl_down_sync(0xffffffffu, mySegs, o);
+  if ((threadIdx.x & 31) == 0 && mySegs) atomicAdd(P.nseg, mySegs);
+
+  if (!last && ipix < npix) {
+    RayState out;
+    out.x = px; out.y = py; out.z = pz; out.radius = radius; out.d1 = d1; out.d2 = d2; out.d3 = d3; out.dD = dD;
+    out.leaf = c.leaf; out.strategy = (active && strategy == 2) ? 2 : 3;
+    out.pad[0] = out.pad[1] = 0;
+    P.stateOut[(size_t)s * npix + ipix] = out;
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// Table sums (stellarBetaTable.f90:217-285): thread = one (idepth1, idepth2, idepth3, idepthDust) entry, sequential
+// over the 399 frequency bins in the reference's order; the six results are stored as logarithms (the lookup takes
+// log of every corner it reads: equiSources.f90:4205-4238), optionally also raw.
+struct TableParams {
+  const double* freq;   // [7][400]: r24, r26, r25, rD, ew1, ew2, ew3   (ew_r = (nu - nu_r) * eV_to_erg)
+  int thr[3];           // first frequency index with nu >= nu_r
+  const double* dtmp;   // [nsrc][400] photons/s per bin
+  double* logTab;       // [nsrc][6][planes][kPlane]
+  double* rawTab;       // optional [nsrc][6][planes][kPlane]
+  int planes;
+};
+
+template <bool PORTABLE>
+__global__ void __launch_bounds__(128) point_table_kernel(const __grid_constant__ TableParams T) {
+  __shared__ double sh[8][kNfreq];
+  const int s = blockIdx.y;
+  for (int i = threadIdx.x; i < 7 * kNfreq; i += blockDim.x) sh[i / kNfreq][i % kNfreq] = T.freq[i];
+  for (int i = threadIdx.x; i < kNfreq; i += blockDim.x) sh[7][i] = T.dtmp[(size_t)s * kNfreq + i];
+  __syncthreads();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= T.planes * kPlane) return;
+  const int i1 = e % 11, i2 = (e / 11) % 11, i3 = (e / 121) % 11, iD = e / kPlane;
+  // float(idepth)/float(ndepth)*maxOpticalDepth: a single-precision quotient (stellarBetaTable.f90:237-244)
+  const double g1 = M((double)__fdiv_rn((float)i1, 10.f), 10.), g2 = M((double)__fdiv_rn((float)i2, 10.f), 10.),
+               g3 = M((double)__fdiv_rn((float)i3, 10.f), 10.), gD = M((double)__fdiv_rn((float)iD, 10.f), 10.);
+  double R[3] = {0., 0., 0.}, E[3] = {0., 0., 0.};
+  for (int i = 1; i < kNfreq; i++) {
+    const double x = A(A(A(M(sh[0][i], g1), M(sh[1][i], g2)), M(sh[2][i], g3)), M(sh[3][i], gD));
+    const double a = M(sh[7][i], PORTABLE ? rtb_pm::pm_exp(-x) : exp(-x));
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+      if (i >= T.thr[r]) {
+        R[r] = A(R[r], a);
+        E[r] = A(E[r], M(sh[4 + r][i], a));
+      }
+  }
+  const size_t base = (size_t)s * 6 * T.planes * kPlane;
+  for (int r = 0; r < 3; r++) {
+    const size_t oR = base + (size_t)r * T.planes * kPlane + e, oE = base + (size_t)(3 + r) * T.planes * kPlane + e;
+    T.logTab[oR] = PORTABLE ? rtb_pm::pm_log(R[r]) : log(R[r]);
+    T.logTab[oE] = PORTABLE ? rtb_pm::pm_log(E[r]) : log(E[r]);
+    if (T.rawTab) { T.rawTab[oR] = R[r]; T.rawTab[oE] = E[r]; }
+  }
+}
+
+__global__ void gather_kernel(const double* __restrict__ src, const int32_t* __restrict__ idx, int n, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[idx[i]];
+}
+
+template <class T>
+int dev_alloc(T** p, size_t count) {
+  cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+  if (e != cudaSuccess) {
+    set_cuda_error("cudaMalloc", e, __FILE__, __LINE__);
+    *p = nullptr;
+    return e == cudaErrorMemoryAllocation ? RTB200_ERR_NOMEM : RTB200_ERR_CUDA;
+  }
+  return RTB200_OK;
+}
+
+struct Scratch {  // freed on every exit path
+  std::vector<void*> ptrs;
+  ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+  template <class T> int get(T** p, size_t count) {
+    int st = dev_alloc(p, count);
+    if (!st) ptrs.push_back(*p);
+    return st;
+  }
+};
+
+}  // namespace
+
+// --------------------------------------------------------------------------------------------------------------------
+int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag, int64_t* nsegOut, long long* hTrace,
+                long long traceCap, long long* traceLen, double* hRawTables, cudaStream_t s) {
+  if (c.nleaf == 0 || !c.dRho || !c.dAbun2) return RTB200_ERR_ARG;
+  if (in.nsrc < 0 || in.maxPixelLevel < 1 || in.maxPixelLevel > kMaxPixelLevel || in.dust < 0 || in.dust > 2)
+    return RTB200_ERR_ARG;
+  if (in.nWave < 2 || !in.wavelength || !in.lum || !in.metallicity || !in.aDust) return RTB200_ERR_ARG;
+  if (in.nsrc > 0 && (!in.srcLeaf || !in.srcWeight)) return RTB200_ERR_ARG;
+  for (int i = 0; i < in.nsrc; i++)
+    if (in.srcLeaf[i] < 0 || in.srcLeaf[i] >= c.nleaf) return RTB200_ERR_ARG;
+  RTB_CUDA(cudaSetDevice(c.device));
+  RTB_CUDA(cudaEventRecord(c.evStart, s));
+  c.lastLaunches = 0;
+  c.lastSweepLaunches = 0;
+  if (nsegOut) *nsegOut = 0;
+  if (traceLen) *traceLen = 0;
+  const int nsrc = in.nsrc;
+  Scratch sc;
+  const bool portable = c.mathMode == RTB200_MATH_FAITHFUL && c.tune.portableMath;
+  const bool faithful = c.mathMode == RTB200_MATH_FAITHFUL;
+  const int planes = in.dust ? 11 : 1;
+
+  // ---- host tables ----
+  PointFreq F;
+  point_frequency_tables(in.aDust, F);
+  std::vector<double> freq(7 * kNfreq);
+  static const double thrE[3] = {(double)13.598f, (double)24.587f, (double)54.418f};
+  TableParams tp{};
+  for (int i = 0; i < kNfreq; i++) {
+    freq[i] = F.r24[i]; freq[kNfreq + i] = F.r26[i]; freq[2 * kNfreq + i] = F.r25[i]; freq[3 * kNfreq + i] = F.rD[i];
+    for (int r = 0; r < 3; r++) freq[(4 + r) * kNfreq + i] = (F.nu[i] - thrE[r]) * 1.60217646e-12;
+  }
+  for (int r = 0; r < 3; r++) {
+    int i = 0;
+    while (i < kNfreq && !(F.nu[i] >= thrE[r])) i++;
+    tp.thr[r] = i;
+  }
+  std::vector<double> dirs;
+  if (int st = point_pixel_directions(in.maxPixelLevel, dirs)) return st;
+  std::vector<double> outSig(4 * kNenergy);
+  for (int e = 0; e < kNenergy; e++) {
+    outSig[e] = F.out24[e]; outSig[kNenergy + e] = F.out26[e]; outSig[2 * kNenergy + e] = F.out25[e];
+    outSig[3 * kNenergy + e] = F.outD[e];
+  }
+
+  double *dFreq, *dDirs, *dOutSig;
+  int32_t *dSrcLeaf, *dSrcWeight;
+  unsigned long long* dCounters;  // [0] nseg, [1] trace length
+  if (int st = sc.get(&dFreq, freq.size())) return st;
+  if (int st = sc.get(&dDirs, dirs.size())) return st;
+  if (int st = sc.get(&dOutSig, outSig.size())) return st;
+  if (int st = sc.get(&dSrcLeaf, (size_t)nsrc)) return st;
+  if (int st = sc.get(&dSrcWeight, (size_t)nsrc)) return st;
+  if (int st = sc.get(&dCounters, 2)) return st;
+  RTB_CUDA(cudaMemcpyAsync(dFreq, freq.data(), freq.size() * 8, cudaMemcpyHostToDevice, s));
+  RTB_CUDA(cudaMemcpyAsync(dDirs, dirs.data(), dirs.size() * 8, cudaMemcpyHostToDevice, s));
+  RTB_CUDA(cudaMemcpyAsync(dOutSig, outSig.data(), outSig.size() * 8, cudaMemcpyHostToDevice, s));
+  RTB_CUDA(cudaMemsetAsync(dCounters, 0, 16, s));
+  if (nsrc == 0) {
+    RTB_CUDA(cudaEventRecord(c.evStop, s));
+    c.statsPending = true; c.sweepTimed = false; c.lastAlgBytes = 0;
+    return RTB200_OK;
+  }
+  RTB_CUDA(cudaMemcpyAsync(dSrcLeaf, in.srcLeaf, (size_t)nsrc * 4, cudaMemcpyHostToDevice, s));
+  RTB_CUDA(cudaMemcpyAsync(dSrcWeight, in.srcWeight, (size_t)nsrc * 4, cudaMemcpyHostToDevice, s));
+
+  // metallicity of every source's host cell (equiSources.f90:1282-1293) -> per-source photon spectrum
+  double* dAb;
+  if (int st = sc.get(&dAb, (size_t)nsrc)) return st;
+  gather_kernel<<<(nsrc + 255) / 256, 256, 0, s>>>(c.dAbun2, dSrcLeaf, nsrc, dAb);
+  std::vector<double> hAb((size_t)nsrc);
+  RTB_CUDA(cudaMemcpyAsync(hAb.data(), dAb, (size_t)nsrc * 8, cudaMemcpyDeviceToHost, s));
+  RTB_CUDA(cudaStreamSynchronize(s));
+  std::vector<double> dtmp((size_t)nsrc * kNfreq);
+  for (int i = 0; i < nsrc; i++) {
+    int iMetal; double coefMetal;
+    if (in.forceMetal) { iMetal = in.forceMetal; coefMetal = in.forceCoefMetal; }
+    else point_metal_bracket(hAb[i], in.metallicity, &iMetal, &coefMetal);
+    point_source_spectrum(F, in.nWave, in.wavelength, in.lum, in.coefSpectrum, iMetal, coefMetal, &dtmp[(size_t)i * kNfreq]);
+  }
+
+  // ---- batches of sources ----
+  int64_t npixMax = 12LL << (2 * (std::max(in.maxPixelLevel, 2) - 2));  // states of level maxPixelLevel-1
+  const size_t perSrc = (size_t)6 * planes * kPlane * 8 + 2 * (size_t)npixMax * sizeof(RayState) + kDiagStride * 8 + kNfreq * 8;
+  size_t freeB = 0, totalB = 0;
+  RTB_CUDA(cudaMemGetInfo(&freeB, &totalB));
+  int batch = (int)std::min<size_t>((size_t)nsrc, std::max<size_t>(1, (freeB / 2) / perSrc));
+  batch = std::min(batch, 16384);
+  if (c.tune.pointBatch > 0) batch = std::min(batch, c.tune.pointBatch);
+  double *dDtmp, *dLogTab, *dRaw = nullptr, *dDiag;
+  RayState *dStA, *dStB;
+  if (int st = sc.get(&dDtmp, (size_t)batch * kNfreq)) return st;
+  if (int st = sc.get(&dLogTab, (size_t)batch * 6 * planes * kPlane)) return st;
+  if (hRawTables) { if (int st = sc.get(&dRaw, (size_t)batch * 6 * planes * kPlane)) return st; }
+  if (int st = sc.get(&dDiag, (size_t)batch * kDiagStride)) return st;
+  if (int st = sc.get(&dStA, (size_t)batch * npixMax)) return st;
+  if (int st = sc.get(&dStB, (size_t)batch * npixMax)) return st;
+  long long* dTrace = nullptr;
+  if (hTrace && traceCap > 0) { if (int st = sc.get(&dTrace, (size_t)traceCap * 2)) return st; }
+
+  PointParams P{};
+  P.child = c.tree.child; P.level = c.dLevel; P.leafX = c.tree.leafX; P.leafY = c.tree.leafY; P.leafZ = c.tree.leafZ;
+  P.HI = c.dHI; P.HeI = c.dHeI; P.HeII = c.dHeII; P.rho = c.dRho; P.abun2 = c.dAbun2;
+  P.nleaf = c.nleaf; P.nx = c.nx; P.boxSize = c.boxSize;
+  P.planes = planes; P.dust = in.dust; P.maxPixelLevel = in.maxPixelLevel;
+  P.pixDir = dDirs;
+  double rmax[31];
+  point_split_radii(rmax);
+  for (int i = 0; i <= kMaxPixelLevel + 1; i++) P.rmax[i] = rmax[i];
+  static const float orad[7] = {0.1f, 0.3f, 1.f, 3.f, 10.f, 30.f, 100.f};
+  const double kpc = (double)1.e3f * (double)3.08568025e18f;
+  for (int i = 0; i < 7; i++) { P.outRadius[i] = (double)orad[i]; P.outRadiusKpc[i] = (double)orad[i] * kpc; }
+  P.kpc = kpc;
+  P.outSigma = dOutSig;
+  P.rates = dRates;
+  P.nseg = dCounters; P.err = c.dErr;
+  P.trace = dTrace; P.traceLen = dCounters + 1; P.traceCap = dTrace ? traceCap : 0;
+
+  for (int b0 = 0; b0 < nsrc; b0 += batch) {
+    const int nb = std::min(batch, nsrc - b0);
+    RTB_CUDA(cudaMemcpyAsync(dDtmp, &dtmp[(size_t)b0 * kNfreq], (size_t)nb * kNfreq * 8, cudaMemcpyHostToDevice, s));
+    RTB_CUDA(cudaMemsetAsync(dDiag, 0, (size_t)nb * kDiagStride * 8, s));
+    tp.freq = dFreq; tp.dtmp = dDtmp; tp.logTab = dLogTab; tp.rawTab = dRaw; tp.planes = planes;
+    dim3 tg((planes * kPlane + 127) / 128, nb);
+    if (portable) point_table_kernel<true><<<tg, 128, 0, s>>>(tp);
+    else point_table_kernel<false><<<tg, 128, 0, s>>>(tp);
+    c.lastLaunches++;
+    if (hRawTables)
+      RTB_CUDA(cudaMemcpyAsync(hRawTables + (size_t)b0 * 6 * planes * kPlane, dRaw, (size_t)nb * 6 * planes * kPlane * 8,
+                               cudaMemcpyDeviceToHost, s));
+    P.srcLeaf = dSrcLeaf + b0; P.srcWeight = dSrcWeight + b0; P.logTab = dLogTab; P.diag = dDiag;
+    RayState *stIn = dStA, *stOut = dStB;
+    for (int L = 1; L <= in.maxPixelLevel; L++) {
+      const int64_t npix = 12LL << (2 * (L - 1));
+      P.stateIn = stIn; P.stateOut = stOut;
+      dim3 g((unsigned)((npix + 127) / 128), nb);
+      if (dTrace) {
+        if (portable) point_march_kernel<true, true, true><<<g, 128, 0, s>>>(P, L);
+        else if (faithful) point_march_kernel<true, false, true><<<g, 128, 0, s>>>(P, L);
+        else point_march_kernel<false, false, true><<<g, 128, 0, s>>>(P, L);
+      } else {
+        if (portable) point_march_kernel<true, true, false><<<g, 128, 0, s>>>(P, L);
+        else if (faithful) point_march_kernel<true, false, false><<<g, 128, 0, s>>>(P, L);
+        else point_march_kernel<false, false, false><<<g, 128, 0, s>>>(P, L);
+      }
+      c.lastLaunches++;
+      c.lastSweepLaunches++;
+      std::swap(stIn, stOut);
+    }
+    RTB_CUDA(cudaGetLastError());
+    if (hDiag)
+      RTB_CUDA(cudaMemcpyAsync(hDiag + (size_t)b0 * kDiagStride, dDiag, (size_t)nb * kDiagStride * 8, cudaMemcpyDeviceToHost, s));
+  }
+  RTB_CUDA(cudaEventRecord(c.evStop, s));
+  unsigned long long counters[2] = {0, 0};
+  RTB_CUDA(cudaMemcpyAsync(counters, dCounters, 16, cudaMemcpyDeviceToHost, s));
+  RTB_CUDA(cudaStreamSynchronize(s));
+  if (nsegOut) *nsegOut = (int64_t)counters[0];
+  if (dTrace) {
+    const long long n = std::min<long long>((long long)counters[1], traceCap);
+    RTB_CUDA(cudaMemcpy(hTrace, dTrace, (size_t)n * 16, cudaMemcpyDeviceToHost));
+    if (traceLen) *traceLen = (long long)counters[1];
+  }
+  c.lastAlgBytes = 136.0 * (double)counters[0];  // 5 reads + 6 read-modify-writes per segment
+  c.statsPending = true;
+  c.sweepTimed = false;
+  int32_t err = 0;
+  RTB_CUDA(cudaMemcpy(&err, c.dErr, sizeof(err), cudaMemcpyDeviceToHost));
+  if (err) { cudaMemset(c.dErr, 0, 64); return err; }
+  return RTB200_OK;
+}
+
+}  // namespace rtb

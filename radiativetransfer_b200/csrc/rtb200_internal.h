@@ -67,6 +67,24 @@ struct Tuning {
   int minBlocks = 2;     // 0: compiler's register choice (2 blocks per SM); 1: cap for 3 blocks; 2: cap for 4 blocks
   int expVariant = 1;    // exp(-tau) of the fast path: 0 = polynomial, 1 = 16-entry shared-memory table
   double l2BudgetMB = 96.0;
+  int portableMath = 1;  // point path, FAITHFUL mode: exp/log from portable_math.h (bit-identical on host and device)
+  int pointBatch = 0;    // sources per batch of the point path (0 = as many as fit in half of the free memory)
+};
+
+// inputs of the point-source pass (equiSources.f90:1256-1370); none of the reference's data files ship with it, so
+// the population-synthesis spectra and the dust fit parameters are arguments
+struct PointInputs {
+  int nWave = 0;
+  const double* wavelength = nullptr;   // [nWave] cm, increasing
+  const double* lum = nullptr;          // [5][2][nWave] log10(erg/s/A): metallicity x (iSpectrum, iSpectrum+1)
+  const double* metallicity = nullptr;  // [5] log10 Z
+  double coefSpectrum = 0;
+  const double* aDust = nullptr;        // [7][5]
+  int dust = 0, maxPixelLevel = 6, nsrc = 0;
+  const int32_t* srcLeaf = nullptr;
+  const int32_t* srcWeight = nullptr;
+  int forceMetal = 0;                   // != 0: use (forceMetal, forceCoefMetal) instead of the host cell's bracket
+  double forceCoefMetal = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -109,6 +127,7 @@ struct Context {
 
   // scratch owned by the diffuse paths (sized lazily, reused across calls)
   double* dJ = nullptr;        // [3][nleaf] result buffer for the host-pointer API
+  double* dRates = nullptr;    // [6][nleaf] rate buffer of the host-pointer point-source API (lazy)
   double* dAcc = nullptr;      // slot accumulators
   size_t accBytes = 0;
   double* dPlanes = nullptr;   // ping-pong top-exit planes
@@ -149,5 +168,10 @@ int amr_neighbours(Context& c, const Direction& d, int32_t* nbHost);
 void amr_release(Context& c);
 int launch_diffuse_rates(Context& c, const double* J, const double* ksi24, const double* ksi25, const double* ksi26,
                          double* k24, double* k25, double* k26, cudaStream_t s);
+
+// point sources: dRates = device [6][nleaf] (krate24, krate25, krate26, crate24, crate25, crate26), accumulated;
+// hDiag = host [nsrc][320] (remaining[7], boundary[7], dust, pad, spectrum[300]) or NULL
+int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag, int64_t* nseg, long long* hTrace,
+                long long traceCap, long long* traceLen, double* hRawTables, cudaStream_t s);
 
 }  // namespace rtb

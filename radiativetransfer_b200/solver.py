@@ -110,6 +110,77 @@ class Transport:
                                                 C.c_void_p(int(k26_ptr)), C.c_void_p(int(stream)))
         _lib.check(st, "rtb200_diffuse_rates_device")
 
+    # ---- point sources (equiSources.f90:1256-1370) ---------------------------------------------------------------
+    @staticmethod
+    def _spectra_args(spectra):
+        wl = _f64(spectra["wavelength"]); lum = _f64(spectra["lum"]); met = _f64(spectra["metallicity"])
+        ad = _f64(spectra["a_dust"])
+        if lum.shape != (5, 2, wl.size) or met.size != 5 or ad.shape != (7, 5):
+            raise ValueError("spectra: lum[5,2,nWave], metallicity[5], a_dust[7,5] expected")
+        keep = (wl, lum, met, ad)
+        return keep, [int(wl.size), _ptr(wl), _ptr(lum), _ptr(met), float(spectra["coef_spectrum"]), _ptr(ad)]
+
+    def point(self, spectra, src_leaf, src_weight, dust_approximation=0, max_pixel_level=6, rates=None,
+              trace_cap=0):
+        """Host-buffer call.  `rates` [6, nleaf] (krate24, krate25, krate26, crate24, crate25, crate26) is accumulated
+        like the reference's cell fields (zeros when None).  Returns dict(rates, ndot_remaining[nsrc,7],
+        ndot_boundary[nsrc,7], ndot_dust[nsrc], ndot_spectrum[nsrc,300], nseg[, trace, trace_key])."""
+        keep, sa = self._spectra_args(spectra)
+        leaf = np.ascontiguousarray(src_leaf, dtype=np.int32); wt = np.ascontiguousarray(src_weight, dtype=np.int32)
+        if leaf.size != wt.size:
+            raise ValueError("src_leaf and src_weight differ in length")
+        ns = int(leaf.size)
+        R = np.zeros((6, self.nleaf)) if rates is None else np.ascontiguousarray(rates, dtype=np.float64).copy()
+        nseg = C.c_int64(0)
+        out = dict(rates=R)
+        if trace_cap:
+            tr = np.zeros((int(trace_cap), 2), dtype=np.int64)
+            tl = C.c_int64(0)
+            st = self.L.rtb200_point_trace(self.h, *sa, int(dust_approximation), int(max_pixel_level), ns, _ptr(leaf),
+                                           _ptr(wt), _ptr(R), C.byref(nseg), _ptr(tr), int(trace_cap), C.byref(tl))
+            _lib.check(st, "rtb200_point_trace")
+            if tl.value > trace_cap:
+                raise RuntimeError(f"trace buffer too small: {tl.value} segments")
+            tr = tr[:tl.value]
+            order = np.argsort(tr[:, 1], kind="stable")
+            out.update(trace=tr[order, 0].copy(), trace_key=tr[order, 1].copy())
+        else:
+            rem = np.zeros((ns, 7)); bnd = np.zeros((ns, 7)); dust = np.zeros(ns); spec = np.zeros((ns, 300))
+            st = self.L.rtb200_point(self.h, *sa, int(dust_approximation), int(max_pixel_level), ns, _ptr(leaf),
+                                     _ptr(wt), *[_ptr(R[i]) for i in range(6)], _ptr(rem), _ptr(bnd), _ptr(dust),
+                                     _ptr(spec), C.byref(nseg))
+            _lib.check(st, "rtb200_point")
+            out.update(ndot_remaining=rem, ndot_boundary=bnd, ndot_dust=dust, ndot_spectrum=spec)
+        out["nseg"] = nseg.value
+        return out
+
+    def point_device(self, spectra, src_leaf, src_weight, rates_ptr, dust_approximation=0, max_pixel_level=6,
+                     stream=0, diagnostics=False):
+        """Resident call: rates_ptr = device pointer to [6][nleaf] doubles, accumulated.  Returns nseg (and the
+        per-source diagnostics when asked)."""
+        keep, sa = self._spectra_args(spectra)
+        leaf = np.ascontiguousarray(src_leaf, dtype=np.int32); wt = np.ascontiguousarray(src_weight, dtype=np.int32)
+        ns = int(leaf.size)
+        nseg = C.c_int64(0)
+        rem = bnd = dust = spec = None
+        if diagnostics:
+            rem = np.zeros((ns, 7)); bnd = np.zeros((ns, 7)); dust = np.zeros(ns); spec = np.zeros((ns, 300))
+        st = self.L.rtb200_point_device(self.h, *sa, int(dust_approximation), int(max_pixel_level), ns, _ptr(leaf),
+                                        _ptr(wt), C.c_void_p(int(rates_ptr)), C.c_void_p(int(stream)), _ptr(rem),
+                                        _ptr(bnd), _ptr(dust), _ptr(spec), C.byref(nseg))
+        _lib.check(st, "rtb200_point_device")
+        if diagnostics:
+            return nseg.value, dict(ndot_remaining=rem, ndot_boundary=bnd, ndot_dust=dust, ndot_spectrum=spec)
+        return nseg.value
+
+    def point_tables(self, spectra, i_metal, coef_metal):
+        """the six (0:10)^4 tables of stellarBetaTable.f90 for one metallicity bracket: [6, 11^4]"""
+        keep, sa = self._spectra_args(spectra)
+        out = np.zeros((6, 11 ** 4))
+        _lib.check(self.L.rtb200_point_tables(self.h, *sa, int(i_metal), float(coef_metal), _ptr(out)),
+                   "rtb200_point_tables")
+        return out
+
     def device_error(self):
         return self.L.rtb200_device_error(self.h)
 

@@ -1,0 +1,207 @@
+"""GPU parity tests of the point-source path: CUDA ray casting / deposition through the C-ABI vs the CPU oracle on the
+same seeded inputs.  Bars (BASELINE.json north_star): bit-exact ray-to-cell traversal order; <= 1e-9 relative L-infinity
+on the per-cell rates (fp64).
+
+The deposits are differences R(d) - R(d+tau) of exponentials of interpolated logarithms (equiSources.f90:3247-3260):
+for a short segment they cancel, and a last-bit difference between two libm implementations is amplified by ~1/tau.
+The parity proper therefore runs with the SAME exp/log source on both sides (csrc/portable_math.h: IEEE +,*,/,fma
+only; device: RTB200_MATH_FAITHFUL, oracle: set_portable_math(1)), where every deposit is bit-identical and only the
+order of the per-cell additions differs.  Against the libm oracle (what gfortran links) and for RTB200_MATH_FAST the
+same tolerance is applied plus the documented conditioning floor of the reference formula itself."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from radiativetransfer_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+S24 = float(np.float32(6.3e-18))
+
+
+@pytest.fixture(scope="module")
+def rt(build_product):
+    import radiativetransfer_b200 as rt
+    return rt
+
+
+@pytest.fixture()
+def engine(rt):
+    t = rt.Transport(device=0, math=rt.MATH_FAITHFUL)
+    yield t
+    t.close()
+
+
+@pytest.fixture(scope="module")
+def spectra():
+    return W.synthetic_spectra()
+
+
+@pytest.fixture()
+def portable(oracle):
+    oracle.set_portable_math(True)
+    yield oracle
+    oracle.set_portable_math(False)
+
+
+def _set(t, g):
+    t.set_grid(g["nx"], g["level"], g["HI"], g["HeI"], g["HeII"], g["rho"], g["abun2"], g["box_size"])
+
+
+def _ograd(oracle, g):
+    return oracle.OracleGrid(g["nx"], g["level"], g["HI"], g["HeI"], g["HeII"], g["rho"], g["abun2"], g["box_size"])
+
+
+def _cell_err(a, b):
+    """relative L-infinity per cell, over cells the oracle deposits into"""
+    m = b != 0
+    assert np.all(a[~m] == 0)
+    return float(np.max(np.abs(a[m] - b[m]) / np.abs(b[m]))) if m.any() else 0.0
+
+
+def _by_ray(trace):
+    """stable sort of an oracle trace (depth-first order) by (pixel level, pixel): per-ray segment order is kept"""
+    key = ((trace >> 28) & 0xF) << 24 | ((trace >> 8) & 0xFFFFF)
+    return trace[np.argsort(key, kind="stable")]
+
+
+def test_tables_match_oracle(engine, portable, spectra):
+    g = W.uniform_grid(4, seed=1)
+    _set(engine, g)
+    for im, cm in [(1, 0.0), (2, 0.25), (4, 1.0)]:
+        T = engine.point_tables(spectra, im, cm)
+        o = portable.point_tables(spectra, im, cm)
+        assert o["status"] == 0
+        assert np.array_equal(T, o["tables"])          # same sums, same order, same exp: bit-identical
+    portable.set_portable_math(False)
+    o = portable.point_tables(spectra, 2, 0.25)        # libm oracle: 399-term sums of 1-ulp-different exponentials
+    assert rel_err(engine.point_tables(spectra, 2, 0.25), o["tables"]) < 1e-13
+
+
+@pytest.mark.parametrize("n,src,maxlev,dust,helium", [
+    (8, (3, 4, 2), 1, 0, True), (12, (6, 6, 6), 3, 0, True), (16, (8, 7, 9), 6, 0, False), (16, (2, 13, 8), 6, 1, True),
+    (10, (0, 0, 0), 5, 2, True), (32, (16, 16, 16), 6, 0, False)])
+def test_uniform_parity_portable(engine, portable, spectra, n, src, maxlev, dust, helium):
+    g = W.uniform_grid(n, seed=n + maxlev, tau_lo=1e-3, tau_hi=1.0, beta24=S24, helium=helium)
+    g["abun2"] = np.random.default_rng(n).uniform(1e-3, 4e-2, n ** 3)
+    _set(engine, g)
+    leaf = (src[0] * n + src[1]) * n + src[2]
+    r = engine.point(spectra, [leaf], [2], dust_approximation=dust, max_pixel_level=maxlev)
+    o = _ograd(portable, g).point(spectra, [leaf], [2], dust_approximation=dust, max_pixel_level=maxlev)
+    assert o["status"] == 0
+    assert r["nseg"] == o["nseg"]
+    for i in range(6):
+        assert _cell_err(r["rates"][i], o["rates"][i]) < 1e-12, i   # identical deposits, different summation order
+    assert rel_err(r["ndot_remaining"], o["ndot_remaining"], floor=1e-300) < 1e-12
+    assert rel_err(r["ndot_boundary"], o["ndot_boundary"], floor=1e-300) < 1e-12
+
+
+@pytest.mark.parametrize("n,src,maxlev", [(8, (3, 4, 2), 1), (12, (6, 5, 6), 4), (16, (8, 7, 9), 6)])
+def test_uniform_traversal_bit_exact(engine, portable, spectra, n, src, maxlev):
+    g = W.uniform_grid(n, seed=3, tau_lo=1e-3, tau_hi=0.5, beta24=S24)
+    _set(engine, g)
+    leaf = (src[0] * n + src[1]) * n + src[2]
+    r = engine.point(spectra, [leaf], [1], max_pixel_level=maxlev, trace_cap=400000)
+    o = _ograd(portable, g).point(spectra, [leaf], [1], max_pixel_level=maxlev, trace_cap=400000)
+    assert o["status"] == 0 and r["nseg"] == o["nseg"] == o["trace"].size
+    assert np.array_equal(r["trace"], _by_ray(o["trace"]))   # (leaf, pixel level, pixel, exit face) of every segment
+
+
+def test_amr_parity_and_traversal(engine, portable, spectra):
+    n = 8
+    g = W.nested_grid(n, 3, W.central_box_refine(0.2, 0.8, levels=3), seed=4, tau_lo=1e-3, tau_hi=0.5, beta24=S24)
+    _set(engine, g)
+    cx, cy, cz = g["centres"]
+    srcs = [int(np.argmin((cx - a) ** 2 + (cy - b) ** 2 + (cz - c) ** 2))
+            for a, b, c in [(0.51, 0.52, 0.47), (0.1, 0.9, 0.3), (0.79, 0.5, 0.21)]]
+    og = _ograd(portable, g)
+    for dust in (0, 2):
+        r = engine.point(spectra, srcs, [1, 3, 2], dust_approximation=dust)
+        o = og.point(spectra, srcs, [1, 3, 2], dust_approximation=dust)
+        assert o["status"] == 0 and r["nseg"] == o["nseg"]
+        for i in range(6):
+            assert _cell_err(r["rates"][i], o["rates"][i]) < 1e-12
+        assert rel_err(r["ndot_remaining"], o["ndot_remaining"], floor=1e-300) < 1e-12
+        assert rel_err(r["ndot_boundary"], o["ndot_boundary"], floor=1e-300) < 1e-12
+    r = engine.point(spectra, srcs[:1], [1], trace_cap=3000000)
+    o = og.point(spectra, srcs[:1], [1], trace_cap=3000000)
+    assert np.array_equal(r["trace"], _by_ray(o["trace"]))
+
+
+def test_against_libm_oracle_and_fast_mode(rt, engine, oracle, spectra):
+    """the reference's own libm (glibc) and the FAST reformulation: same result up to the conditioning of
+    R(d) - R(d+tau); cells are compared at 1e-9 relative plus 2e-13 of the undepleted rate a ray carries into the cell
+    (= the rounding noise of exp(interpolated log) that the subtraction exposes)"""
+    n = 16
+    g = W.uniform_grid(n, seed=9, tau_lo=1e-3, tau_hi=1.0, beta24=S24)
+    _set(engine, g)
+    leaf = (8 * n + 8) * n + 8
+    o = _ograd(oracle, g).point(spectra, [leaf], [1])
+    assert o["status"] == 0
+    T = engine.point_tables(spectra, *_bracket(spectra, g["abun2"][leaf])).reshape(6, -1)
+    r_faith = engine.point(spectra, [leaf], [1])
+    engine.set_math(rt.MATH_FAST)
+    r_fast = engine.point(spectra, [leaf], [1])
+    for r in (r_faith, r_fast):
+        assert r["nseg"] == o["nseg"]
+        for i, t in zip(range(6), (0, 2, 1, 3, 5, 4)):
+            floor = 2e-13 * T[t, 0]     # R_r(0): the largest value either side of the subtraction can take
+            d = np.abs(r["rates"][i] - o["rates"][i])
+            assert np.all(d <= TOL * np.abs(o["rates"][i]) + floor), (i, float(np.max(d / np.maximum(np.abs(o["rates"][i]), 1e-300))))
+        assert np.allclose(r["rates"].sum(axis=1), o["rates"].sum(axis=1), rtol=1e-11, atol=0)
+        assert rel_err(r["ndot_remaining"], o["ndot_remaining"], floor=1e-300) < 1e-11
+
+
+def _bracket(spectra, abun2):
+    t = np.log10(abun2) if abun2 > 1e-20 else -20.0
+    met = spectra["metallicity"]
+    m = 1
+    while t > met[m]:
+        m += 1
+        if m + 1 == 5:
+            break
+    return m, float(np.clip((t - met[m - 1]) / (met[m] - met[m - 1]), 0, 1))
+
+
+def test_sources_accumulate_and_shard(engine, portable, spectra):
+    """rates accumulate over calls like the reference's cell fields; sharding the source list across ranks and adding
+    the per-rank rates gives the one-call result"""
+    n = 12
+    g = W.uniform_grid(n, seed=12, tau_lo=1e-2, tau_hi=1.0, beta24=S24)
+    _set(engine, g)
+    rng = np.random.default_rng(5)
+    leaves = rng.choice(n ** 3, 7, replace=False).astype(np.int32)
+    wts = rng.integers(0, 4, 7).astype(np.int32)   # includes weight 0 (skipped, equiSources.f90:1264)
+    full = engine.point(spectra, leaves, wts)
+    a = engine.point(spectra, leaves[:3], wts[:3])
+    b = engine.point(spectra, leaves[3:], wts[3:], rates=a["rates"])
+    assert b["nseg"] + a["nseg"] == full["nseg"]
+    assert rel_err(b["rates"], full["rates"], floor=1e-300) < 1e-12
+    engine.set_tuning(point_batch=2)               # batching of sources does not change anything
+    c = engine.point(spectra, leaves, wts)
+    assert rel_err(c["rates"], full["rates"], floor=1e-300) < 1e-12
+    assert np.array_equal(c["ndot_boundary"], full["ndot_boundary"])
+    o = _ograd(portable, g).point(spectra, leaves, wts)
+    for i in range(6):
+        assert _cell_err(full["rates"][i], o["rates"][i]) < 1e-12
+
+
+def test_photon_conservation_256_scale_properties(engine, spectra):
+    """size-independent properties at a larger size (64^3 + one refined level), no oracle: opaque box absorbs
+    R(0) * weight; empty box deposits nothing and every ray ends on the boundary"""
+    n = 64
+    g = W.nested_grid(n, 1, W.central_box_refine(0.375, 0.625, levels=1), seed=6, tau_lo=3.0, tau_hi=8.0, beta24=S24)
+    g["HeI"][:] = 0; g["HeII"][:] = 0
+    _set(engine, g)
+    cx, cy, cz = g["centres"]
+    src = int(np.argmin((cx - 0.5) ** 2 + (cy - 0.5) ** 2 + (cz - 0.5) ** 2))
+    r = engine.point(spectra, [src], [5])
+    T = engine.point_tables(spectra, *_bracket(spectra, g["abun2"][src]))
+    assert np.isclose(r["rates"][0].sum(), 5 * T[0, 0], rtol=1e-11)
+    assert np.isclose(r["rates"][3].sum(), 5 * T[3, 0], rtol=1e-11)
+    assert np.all(r["rates"][[1, 2, 4, 5]] == 0)
+    engine.update_species(np.zeros_like(g["HI"]), None, None)
+    r = engine.point(spectra, [src], [5])
+    assert np.all(r["rates"] == 0)
+    tot = r["ndot_remaining"][0] + r["ndot_boundary"][0]
+    assert np.all(tot <= 5 * (1 + 1e-12)) and np.all(tot > 4.8)
