@@ -226,7 +226,7 @@ int rtb200_destroy(rtb200_ctx* h) {
   cudaSetDevice(c.device);
   cudaDeviceSynchronize();
   free_grid(c);
-  cudaFree(c.dAcc); cudaFree(c.dPlanes); cudaFree(c.dAmrScratch); cudaFree(c.dErr);
+  cudaFree(c.dAcc); cudaFree(c.dPlanes); cudaFree(c.dAmrScratch); cudaFree(c.dErr); cudaFree(c.dMarchSeg); cudaFree(c.dMarchProg);
   if (c.hPinned) cudaFreeHost(c.hPinned);
   if (c.evStart) cudaEventDestroy(c.evStart);
   if (c.evStop) cudaEventDestroy(c.evStop);
@@ -259,6 +259,9 @@ int rtb200_set_tuning(rtb200_ctx* h, const char* key, double value) {
   else if (k == "slots") c.tune.slots = (int)value;
   else if (k == "graph") c.tune.useGraph = (int)value;
   else if (k == "l2_mb") c.tune.l2BudgetMB = value;
+  else if (k == "march") c.tune.march = (int)value;
+  else if (k == "dirs_per_task") c.tune.dirsPerTask = (int)value;
+  else if (k == "march_debug") c.tune.marchDebug = (int)value;
   else if (k == "portable_math") c.tune.portableMath = (int)value;
   else if (k == "point_batch") c.tune.pointBatch = (int)value;
   else return RTB200_ERR_ARG;

@@ -57,7 +57,6 @@ int launch_compute_opacities(Context& c, const double* beta, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------------
 struct StepParams {
   LayerSeg P[kMaxDirPerTask];
-  int32_t pl[kMaxDirPerTask];  // plane index (within the task) of the q-th direction handled by this launch
   const double* planeIn;   // this task's planes of the previous layer  [ndir][3][n+1][n+1] (padded, see below)
   double* planeOut;
   double* acc;             // slot accumulator [3][N]
@@ -78,63 +77,150 @@ __global__ void fill_planes_kernel(double* __restrict__ planes, int64_t perGroup
   }
 }
 
-template <bool FAITHFUL, int EXPV>
-__device__ __forceinline__ double attenuate(double Iin, double kappa, double dpath, const double* __restrict__ T) {
-  if (FAITHFUL) return __dmul_rn(Iin, exp(-__dmul_rn(kappa, dpath)));
-  return Iin * exp_neg_only<EXPV>(kappa * dpath, T);
-}
-
 // One direction of one cell, straight-line for a given segment count and chain order.
 //   NSEG: 1..3 segments.  SECL: the second segment is fed by the neighbour along the LANE axis (cell a-1, same row)
 //   and the third by the neighbour along the ROW axis (cell b-1, same lane); !SECL: the other way round.
 // Lane-axis hand-over = warp shuffle of the neighbour lane's own result; row-axis hand-over = recompute of what the
 // (b-1) cell emits from the previous layer's plane value `upR` and its kappa `kR` (bit-identical to that cell's own
 // arithmetic).  Every lane of the warp must call this (shuffles), including the halo lane and out-of-domain lanes.
-template <bool FAITHFUL, int EXPV, int NSEG, bool SECL>
-__device__ __forceinline__ void direction_body(const LayerSeg& P, const double (&cur)[3], const double (&upR)[3],
-                                               const double (&kap)[3], const double (&invk)[3], const double (&kR)[3],
-                                               double (&I)[3], double (&acc)[3], const double* __restrict__ T) {
+//
+// FAST arithmetic (segment_math.cuh: segment_fast): A[g] collects Iin (1 - e^-tau) cs over all segments and
+// directions of the layer; the caller multiplies by 2^-200 / kappa once per layer.
+template <int EXPV, int NSEG, bool SECL>
+__device__ __forceinline__ void direction_fast(const LayerSeg& P, const double (&cur)[3], const double (&upR)[3],
+                                               const double (&kap)[3], const double (&kR)[3], double (&I)[3],
+                                               double (&A)[3], const double* __restrict__ T) {
   const unsigned full = 0xffffffffu;
 #pragma unroll
   for (int g = 0; g < 3; g++) {
-    SegResult r1 = segment_update<FAITHFUL, EXPV>(cur[g], kap[g], P.d[0], invk[g] * P.invd[0], T);
-    double Jsum = r1.J;
-    I[g] = r1.Iout;
+    const double I1 = segment_fast<EXPV>(cur[g], kap[g] * P.d[0], P.cs[0], T, A[g]);
+    I[g] = I1;
     if (NSEG >= 2) {
       double rup = 0.;  // xy-segment output of the (b-1) cell
-      if (!SECL || NSEG == 3) rup = attenuate<FAITHFUL, EXPV>(upR[g], kR[g], P.d[0], T);
-      const double in2 = SECL ? __shfl_up_sync(full, r1.Iout, 1) : rup;
-      SegResult r2 = segment_update<FAITHFUL, EXPV>(in2, kap[g], P.d[1], invk[g] * P.invd[1], T);
-      I[g] = r2.Iout;
-      double J3 = 0.;
+      if (!SECL || NSEG == 3) rup = attenuate_fast<EXPV>(upR[g], kR[g] * P.d[0], T);
+      const double in2 = SECL ? __shfl_up_sync(full, I1, 1) : rup;
+      const double I2 = segment_fast<EXPV>(in2, kap[g] * P.d[1], P.cs[1], T, A[g]);
+      I[g] = I2;
       if (NSEG == 3) {
         double in3;
         if (SECL) {
           // third segment from the (b-1) cell's SECOND segment, which was fed by the (b-1, a-1) cell's xy segment
           const double x = __shfl_up_sync(full, rup, 1);
-          in3 = attenuate<FAITHFUL, EXPV>(x, kR[g], P.d[1], T);
+          in3 = attenuate_fast<EXPV>(x, kR[g] * P.d[1], T);
         } else {
-          in3 = __shfl_up_sync(full, r2.Iout, 1);  // the (a-1) cell's second segment
+          in3 = __shfl_up_sync(full, I2, 1);  // the (a-1) cell's second segment
         }
-        SegResult r3 = segment_update<FAITHFUL, EXPV>(in3, kap[g], P.d[2], invk[g] * P.invd[2], T);
+        I[g] = segment_fast<EXPV>(in3, kap[g] * P.d[2], P.cs[2], T, A[g]);
+      }
+    }
+  }
+}
+
+// The reference's own operation sequence (RTB200_MATH_FAITHFUL, and the thin layers of FAST mode): adds
+// (sum of the segments' J) / nseg * weight to acc (transportRoutinesModule.f90:953-955).
+template <int NSEG, bool SECL>
+__device__ __forceinline__ void direction_faithful(const LayerSeg& P, const double (&cur)[3], const double (&upR)[3],
+                                                   const double (&kap)[3], const double (&kR)[3], double (&I)[3],
+                                                   double (&acc)[3]) {
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int g = 0; g < 3; g++) {
+    SegResult r1 = segment_update<true, 0>(cur[g], kap[g], P.d[0], 0., nullptr);
+    double Jsum = r1.J;
+    I[g] = r1.Iout;
+    if (NSEG >= 2) {
+      double rup = 0.;
+      if (!SECL || NSEG == 3) rup = __dmul_rn(upR[g], exp(-__dmul_rn(kR[g], P.d[0])));
+      const double in2 = SECL ? __shfl_up_sync(full, r1.Iout, 1) : rup;
+      SegResult r2 = segment_update<true, 0>(in2, kap[g], P.d[1], 0., nullptr);
+      I[g] = r2.Iout;
+      double J3 = 0.;
+      if (NSEG == 3) {
+        double in3;
+        if (SECL) {
+          const double x = __shfl_up_sync(full, rup, 1);
+          in3 = __dmul_rn(x, exp(-__dmul_rn(kR[g], P.d[1])));
+        } else {
+          in3 = __shfl_up_sync(full, r2.Iout, 1);
+        }
+        SegResult r3 = segment_update<true, 0>(in3, kap[g], P.d[2], 0., nullptr);
         I[g] = r3.Iout;
         J3 = r3.J;
       }
-      Jsum = FAITHFUL ? 0. : (Jsum + r2.J) + J3;
-      if (FAITHFUL) {
-        // the reference sums the segments in the order xy, xz, yz (transportRoutinesModule.f90:698,818,941);
-        // P.kind <= 2 <=> the second segment is the yz ray
-        const bool yzSecond = P.kind <= 2;
-        const double Jxz = yzSecond ? J3 : r2.J, Jyz = yzSecond ? r2.J : J3;
-        Jsum = r1.J;
-        if (NSEG == 3 || !yzSecond) Jsum = __dadd_rn(Jsum, Jxz);
-        if (NSEG == 3 || yzSecond) Jsum = __dadd_rn(Jsum, Jyz);
-      }
+      // the reference sums the segments in the order xy, xz, yz (transportRoutinesModule.f90:698,818,941);
+      // P.kind <= 2 <=> the second segment is the yz ray
+      const bool yzSecond = P.kind <= 2;
+      const double Jxz = yzSecond ? J3 : r2.J, Jyz = yzSecond ? r2.J : J3;
+      Jsum = r1.J;
+      if (NSEG == 3 || !yzSecond) Jsum = __dadd_rn(Jsum, Jxz);
+      if (NSEG == 3 || yzSecond) Jsum = __dadd_rn(Jsum, Jyz);
     }
-    if (FAITHFUL) acc[g] = __dadd_rn(acc[g], __dmul_rn(__ddiv_rn(Jsum, (double)NSEG), P.w));
-    else acc[g] = fma(Jsum, P.wn, acc[g]);
+    acc[g] = __dadd_rn(acc[g], __dmul_rn(__ddiv_rn(Jsum, (double)NSEG), P.w));
   }
 }
+
+// dispatch on the layer's chain kind (warp-uniform)
+template <int EXPV>
+__device__ __forceinline__ void direction_dispatch_fast(const LayerSeg& P, bool secL, const double (&cur)[3],
+                                                        const double (&upR)[3], const double (&kap)[3],
+                                                        const double (&kR)[3], double (&I)[3], double (&A)[3],
+                                                        const double* __restrict__ T) {
+  const int kind = P.kind;
+  if (kind == 0) direction_fast<EXPV, 1, true>(P, cur, upR, kap, kR, I, A, T);
+  else if (kind == 1 || kind == 3) {
+    if (secL) direction_fast<EXPV, 2, true>(P, cur, upR, kap, kR, I, A, T);
+    else direction_fast<EXPV, 2, false>(P, cur, upR, kap, kR, I, A, T);
+  } else {
+    if (secL) direction_fast<EXPV, 3, true>(P, cur, upR, kap, kR, I, A, T);
+    else direction_fast<EXPV, 3, false>(P, cur, upR, kap, kR, I, A, T);
+  }
+}
+
+// Out of line and by value: the rare faithful branch must not force the fast path's per-direction arrays into
+// local memory (a by-reference call would).
+struct Tri {
+  double v[3];
+};
+struct FaithOut {
+  Tri I, acc;
+};
+#ifndef RTB_FAITHFUL_INLINE
+#define RTB_FAITHFUL_CALL __noinline__
+#else
+#define RTB_FAITHFUL_CALL __forceinline__
+#endif
+__device__ RTB_FAITHFUL_CALL FaithOut direction_call_faithful(double d0, double d1, double d2, double w, int kind,
+                                                              bool secL, Tri cur_, Tri upR_, Tri kap_, Tri kR_, Tri acc_) {
+  LayerSeg P;
+  P.d[0] = d0; P.d[1] = d1; P.d[2] = d2; P.w = w; P.kind = kind;
+  double cur[3] = {cur_.v[0], cur_.v[1], cur_.v[2]}, upR[3] = {upR_.v[0], upR_.v[1], upR_.v[2]};
+  double kap[3] = {kap_.v[0], kap_.v[1], kap_.v[2]}, kR[3] = {kR_.v[0], kR_.v[1], kR_.v[2]};
+  double acc[3] = {acc_.v[0], acc_.v[1], acc_.v[2]}, I[3] = {0., 0., 0.};
+  if (kind == 0) direction_faithful<1, true>(P, cur, upR, kap, kR, I, acc);
+  else if (kind == 1 || kind == 3) {
+    if (secL) direction_faithful<2, true>(P, cur, upR, kap, kR, I, acc);
+    else direction_faithful<2, false>(P, cur, upR, kap, kR, I, acc);
+  } else {
+    if (secL) direction_faithful<3, true>(P, cur, upR, kap, kR, I, acc);
+    else direction_faithful<3, false>(P, cur, upR, kap, kR, I, acc);
+  }
+  FaithOut o;
+#pragma unroll
+  for (int g = 0; g < 3; g++) { o.I.v[g] = I[g]; o.acc.v[g] = acc[g]; }
+  return o;
+}
+__device__ __forceinline__ void direction_dispatch_faithful(const LayerSeg& P, bool secL, const double (&cur)[3],
+                                                            const double (&upR)[3], const double (&kap)[3],
+                                                            const double (&kR)[3], double (&I)[3], double (&acc)[3]) {
+  const FaithOut o = direction_call_faithful(P.d[0], P.d[1], P.d[2], P.w, P.kind, secL, Tri{{cur[0], cur[1], cur[2]}},
+                                             Tri{{upR[0], upR[1], upR[2]}}, Tri{{kap[0], kap[1], kap[2]}},
+                                             Tri{{kR[0], kR[1], kR[2]}}, Tri{{acc[0], acc[1], acc[2]}});
+#pragma unroll
+  for (int g = 0; g < 3; g++) { I[g] = o.I.v[g]; acc[g] = o.acc.v[g]; }
+}
+
+constexpr double kKappaFloor = 1e-100;  // FAST mode: kappa = 0 is evaluated as this (every formula takes its limit)
+constexpr double kTwoM200 = 6.223015277861141707e-61;  // 2^-200
 
 // block = 8 warps; a warp covers 31 cells of one row plus, in lane 0, the recomputed last cell of the strip to its
 // left (for strip 0 that is the pad column, which behaves as "no neighbour").
@@ -145,6 +231,10 @@ struct BatchParams {
 
 // gridDim.z tasks (zones) per launch, all at the same layer index: one launch per layer keeps the device full
 // (thousands of blocks) instead of many small concurrent kernels.
+// A layer whose pattern has a very short segment (a corner clip, len < 1e-2 cell; 1.7% of the (direction, layer)
+// pairs) is evaluated with the reference's own operation sequence even in FAST mode: there tau is tiny and the
+// rounding noise of the reference's (Iin-Iout)/log(Iin/Iout), ~1.1e-16/tau, would otherwise show up as a parity
+// difference.  That branch is warp-uniform (P.thin is a per-layer table entry) and kept out of line.
 template <bool FAITHFUL, int EXPV, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 sweep_cell_kernel(const __grid_constant__ BatchParams bp, const double* __restrict__ kappa, int N) {
@@ -163,32 +253,25 @@ sweep_cell_kernel(const __grid_constant__ BatchParams bp, const double* __restri
   const int leaf = sp.origin + a * sA + b * sB;
   const int np1 = n + 1;
   const int npl = np1 * np1;                                   // doubles per padded plane
-  double kap[3], invk[3], kR[3];
+  double kap[3], kapF[3], kR[3];
 #pragma unroll
   for (int g = 0; g < 3; g++) {
     const double* kg = kappa + (int64_t)g * N + leaf;
-    kap[g] = cell ? kg[0] : 0.;
+    kapF[g] = cell ? kg[0] : 0.;
     kR[g] = (cell && b > 0) ? kg[-sB] : 0.;                    // kappa = 0 outside: exp(-0) = 1 exactly
-    if (!FAITHFUL) {
-      kap[g] = kap[g] > 0. ? kap[g] : 1e-200;  // kappa = 0 limit through the same formulas (segment_math.cuh)
-      invk[g] = 1.0 / kap[g];
-    } else {
-      invk[g] = 0.;
-    }
+    kap[g] = kapF[g] > 0. ? kapF[g] : kKappaFloor;
   }
-  double acc[3] = {0., 0., 0.};
+  double A[3] = {0., 0., 0.}, acc[3] = {0., 0., 0.};
   const int pidx = (b + 1) * np1 + (inRow ? a + 1 : 0);
   const int ndir = sp.ndir;
+  const int dstride = 3 * npl;                                 // one direction's planes (3 groups)
+  const double* pin = sp.planeIn + pidx;
+  double* pout = sp.planeOut + pidx;
   double cur[3];
-  {
-    const double* p0 = sp.planeIn + (int64_t)sp.pl[0] * (3 * npl) + pidx;
 #pragma unroll
-    for (int g = 0; g < 3; g++) cur[g] = p0[g * npl];
-  }
-  for (int q = 0; q < ndir; q++) {
+  for (int g = 0; g < 3; g++) cur[g] = pin[g * npl];
+  for (int q = 0; q < ndir; q++, pin += dstride, pout += dstride) {
     const LayerSeg& P = sp.P[q];
-    const double* pin = sp.planeIn + (int64_t)sp.pl[q] * (3 * npl) + pidx;
-    double* pout = sp.planeOut + (int64_t)sp.pl[q] * (3 * npl) + pidx;
     const int kind = P.kind;
     // issue every load of this direction, and the next direction's own plane values, before the arithmetic
     double upR[3] = {0., 0., 0.}, nxt[3] = {0., 0., 0.}, I[3];
@@ -199,18 +282,11 @@ sweep_cell_kernel(const __grid_constant__ BatchParams bp, const double* __restri
       for (int g = 0; g < 3; g++) upR[g] = pin[g * npl - np1];
     }
     if (q + 1 < ndir) {
-      const double* pn = sp.planeIn + (int64_t)sp.pl[q + 1] * (3 * npl) + pidx;
 #pragma unroll
-      for (int g = 0; g < 3; g++) nxt[g] = pn[g * npl];
+      for (int g = 0; g < 3; g++) nxt[g] = pin[dstride + g * npl];
     }
-    if (kind == 0) direction_body<FAITHFUL, EXPV, 1, true>(P, cur, upR, kap, invk, kR, I, acc, sT);
-    else if (kind == 1 || kind == 3) {
-      if (secL) direction_body<FAITHFUL, EXPV, 2, true>(P, cur, upR, kap, invk, kR, I, acc, sT);
-      else direction_body<FAITHFUL, EXPV, 2, false>(P, cur, upR, kap, invk, kR, I, acc, sT);
-    } else {
-      if (secL) direction_body<FAITHFUL, EXPV, 3, true>(P, cur, upR, kap, invk, kR, I, acc, sT);
-      else direction_body<FAITHFUL, EXPV, 3, false>(P, cur, upR, kap, invk, kR, I, acc, sT);
-    }
+    if (FAITHFUL || P.thin) direction_dispatch_faithful(P, secL, cur, upR, kapF, kR, I, acc);
+    else direction_dispatch_fast<EXPV>(P, secL, cur, upR, kap, kR, I, A, sT);
     if (writer) {
 #pragma unroll
       for (int g = 0; g < 3; g++) pout[g * npl] = I[g];
@@ -221,8 +297,190 @@ sweep_cell_kernel(const __grid_constant__ BatchParams bp, const double* __restri
   if (writer) {
 #pragma unroll
     for (int g = 0; g < 3; g++) {
+      if (!FAITHFUL) acc[g] = fma(A[g], kTwoM200 / kap[g], acc[g]);
       double* p = sp.acc + (int64_t)g * N + leaf;
       *p = sp.firstInSlot ? acc[g] : __dadd_rn(*p, acc[g]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Persistent layer-marching kernel
+//
+// The per-layer launches above stream every direction's top-exit plane through HBM twice per layer (read + write):
+// that plane traffic IS the sweep's HBM traffic (ncu: 925 MB per layer launch at 256^3).  Here a block keeps its
+// tile of the planes in shared memory and marches through all n layers itself: block = 8 rows x (31 cells + 1
+// recomputed halo cell), the same tile and the same per-cell arithmetic (direction_body) as sweep_cell_kernel.
+// What a tile needs from its upstream neighbours -- the previous layer's top-exit intensities of the cell column
+// left of it and of the cell row above it -- travels through an L2-resident ring of edge values in global memory,
+// guarded by one progress counter per block (release/acquire).  A block may run at most kRing-1 layers ahead of its
+// downstream neighbours (it checks their counters before it overwrites a ring slot), so all blocks of a task have to
+// be co-resident: the host sizes the batch from the occupancy query and launches cooperatively.
+// HBM traffic left: kappa (read once per zone task) and the J accumulator.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kRing = 4;
+constexpr int kMaxMarchTasks = 16;
+
+struct MarchTask {
+  const LayerSeg* seg;  // [n][kMaxDirPerTask]
+  double* acc;          // slot accumulator [3][N]
+  double* ring;         // [kRing][ndir][3][(n+1)^2], filled with the boundary intensity (pads stay that way)
+  int32_t* prog;        // [gridDim.y][gridDim.x] layers completed
+  int32_t origin, si, sj, sk;
+  int32_t ndir, laneIsK, firstInSlot, pad;
+};
+struct MarchBatch {
+  MarchTask t[kMaxMarchTasks];
+};
+
+__device__ __forceinline__ int ld_acquire(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int32_t* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <bool FAITHFUL_ALL, int EXPV, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+sweep_march_kernel(const __grid_constant__ MarchBatch mb, const double* __restrict__ kappa, int N, int n, double u0,
+                   double u1, double u2, int32_t* __restrict__ err, int dbg) {
+  const MarchTask& T = mb.t[blockIdx.z];
+  extern __shared__ double smem[];
+  double* sT = smem;                // 16-entry exp table
+  double* sX = smem + 16;           // plane tile [2][ndir][3][8][32]
+  if (threadIdx.y == 0 && threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
+  const int ndir = T.ndir;
+  const int lane = threadIdx.x, row = threadIdx.y;
+  const int a = blockIdx.x * 31 - 1 + lane, b = blockIdx.y * 8 + row;
+  const bool rowActive = b < n;
+  const bool inRow = a < n;
+  const bool cell = rowActive && inRow && a >= 0;
+  const bool writer = cell && lane >= 1;
+  const bool halo = lane == 0;
+  const int laneIsK = T.laneIsK;
+  const int sA = laneIsK ? T.sk : T.sj, sB = laneIsK ? T.sj : T.sk;
+  const int np1 = n + 1, npl = np1 * np1;
+  const int pidx = (b + 1) * np1 + (inRow ? a + 1 : 0);
+  const int tileStride = 3 * 8 * 32;                    // doubles per direction in one tile buffer
+  const int bufStride = ndir * tileStride;
+  const int tpos = row * 32 + lane;
+  const double uvb[3] = {u0, u1, u2};
+  // edge duty: the last cell column / row of the tile is read by the block to the right / below
+  const bool pubCol = writer && lane == 31 && blockIdx.x + 1 < gridDim.x;
+  const bool pubRow = writer && row == 7 && blockIdx.y + 1 < gridDim.y;
+  // layer 0 reads "boundary intensity everywhere" (transportRoutinesModule.f90:594-597)
+  for (int q = 0; q < ndir; q++)
+#pragma unroll
+    for (int g = 0; g < 3; g++) sX[bufStride + q * tileStride + g * 256 + tpos] = uvb[g];   // buffer 1 = "layer -1"
+  int32_t* myProg = T.prog + blockIdx.y * gridDim.x + blockIdx.x;
+  // neighbour counters polled by lanes 0..5 of warp 0: 0..2 upstream, 3..5 downstream
+  const int32_t* pollPtr = nullptr;
+  if (row == 0 && lane < 6) {
+    const int dx = (lane == 0 || lane == 2) ? -1 : ((lane == 3 || lane == 5) ? 1 : 0);
+    const int dy = (lane == 1 || lane == 2) ? -1 : ((lane == 4 || lane == 5) ? 1 : 0);
+    const int bx = (int)blockIdx.x + dx, by = (int)blockIdx.y + dy;
+    if (bx >= 0 && bx < (int)gridDim.x && by >= 0 && by < (int)gridDim.y) pollPtr = T.prog + by * gridDim.x + bx;
+  }
+  int leaf = T.origin + a * sA + b * sB;
+  double kapN[3], kRN[3];
+#pragma unroll
+  for (int g = 0; g < 3; g++) {
+    const double* kg = kappa + (int64_t)g * N + leaf;
+    kapN[g] = cell ? __ldg(kg) : 0.;
+    kRN[g] = (cell && b > 0) ? __ldg(kg - sB) : 0.;
+  }
+  for (int i = 0; i < n; i++) {
+    if (pollPtr) {
+      // upstream: layer i-1 published (i layers done).  downstream: before ring slot i%kRing (layer i-kRing) is
+      // overwritten its readers must have completed layer i-kRing+1, i.e. i-kRing+2 layers
+      const int need = lane < 3 ? i : i - kRing + 2;
+      if (need > 0) {
+        unsigned spins = 0;
+        while (ld_acquire(pollPtr) < need) {
+          if (!(dbg & 2)) __nanosleep(64);
+          if (++spins > (1u << 24)) { atomicExch(err, RTB200_ERR_CUDA); break; }
+        }
+      }
+    }
+    __syncthreads();  // neighbours' edges of layer i-1 are visible; the tile buffer of layer i-1 is complete
+    const double* xin = sX + ((i + 1) & 1) * bufStride;   // tile of layer i-1
+    double* xout = sX + (i & 1) * bufStride;              // tile of layer i
+    const double* ringIn = T.ring + (int64_t)((i + kRing - 1) % kRing) * ndir * 3 * npl;
+    double* ringOut = T.ring + (int64_t)(i % kRing) * ndir * 3 * npl;
+    double kap[3], kapF[3], kR[3], old[3];
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      kapF[g] = kapN[g]; kR[g] = kRN[g];
+      kap[g] = kapF[g] > 0. ? kapF[g] : kKappaFloor;
+    }
+    double* accp = T.acc + leaf;
+    if (i + 1 < n) {  // prefetch the next layer's opacities
+#pragma unroll
+      for (int g = 0; g < 3; g++) {
+        const double* kg = kappa + (int64_t)g * N + leaf + T.si;
+        kapN[g] = cell ? __ldg(kg) : 0.;
+        kRN[g] = (cell && b > 0) ? __ldg(kg - sB) : 0.;
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 3; g++) old[g] = (writer && !T.firstInSlot) ? accp[(int64_t)g * N] : 0.;
+    double acc[3] = {0., 0., 0.}, A[3] = {0., 0., 0.};
+    if (rowActive) {
+      for (int q = 0; q < ndir; q++) {
+        const LayerSeg* Pg = T.seg + (size_t)i * kMaxDirPerTask + q;
+        LayerSeg P;
+        P.d[0] = __ldg(&Pg->d[0]); P.d[1] = __ldg(&Pg->d[1]); P.d[2] = __ldg(&Pg->d[2]);
+        P.cs[0] = __ldg(&Pg->cs[0]); P.cs[1] = __ldg(&Pg->cs[1]); P.cs[2] = __ldg(&Pg->cs[2]);
+        P.wn = 0.; P.w = __ldg(&Pg->w);
+        P.kind = __ldg(&Pg->kind); P.nseg = 0; P.thin = __ldg(&Pg->thin);
+        const int kind = P.kind;
+        const bool secL = (kind <= 2) == (laneIsK != 0);
+        const bool needUp = kind == 2 || kind == 4 || (kind != 0 && !secL);
+        double cur[3], upR[3] = {0., 0., 0.}, I[3];
+        // the halo lane owns no cell: its input is the left neighbour tile's edge value
+        if (halo && i > 0) {
+#pragma unroll
+          for (int g = 0; g < 3; g++) cur[g] = __ldcg(ringIn + (int64_t)(q * 3 + g) * npl + pidx);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 3; g++) cur[g] = xin[q * tileStride + g * 256 + tpos];
+        }
+        if (needUp) {
+          if (i == 0) {
+#pragma unroll
+            for (int g = 0; g < 3; g++) upR[g] = uvb[g];
+          } else if (row == 0 || halo) {  // the cell above belongs to another tile (or is the pad row)
+#pragma unroll
+            for (int g = 0; g < 3; g++) upR[g] = __ldcg(ringIn + (int64_t)(q * 3 + g) * npl + pidx - np1);
+          } else {
+#pragma unroll
+            for (int g = 0; g < 3; g++) upR[g] = xin[q * tileStride + g * 256 + tpos - 32];
+          }
+        }
+        if (FAITHFUL_ALL || P.thin) direction_dispatch_faithful(P, secL, cur, upR, kapF, kR, I, acc);
+        else direction_dispatch_fast<EXPV>(P, secL, cur, upR, kap, kR, I, A, sT);
+#pragma unroll
+        for (int g = 0; g < 3; g++) xout[q * tileStride + g * 256 + tpos] = writer ? I[g] : cur[g];
+        if (pubCol || pubRow) {
+#pragma unroll
+          for (int g = 0; g < 3; g++) __stcg(ringOut + (int64_t)(q * 3 + g) * npl + pidx, I[g]);
+        }
+      }
+    }
+    if (writer) {
+#pragma unroll
+      for (int g = 0; g < 3; g++) {
+        if (!FAITHFUL_ALL) acc[g] = fma(A[g], kTwoM200 / kap[g], acc[g]);
+        accp[(int64_t)g * N] = T.firstInSlot ? acc[g] : __dadd_rn(old[g], acc[g]);
+      }
+    }
+    leaf += T.si;
+    __syncthreads();  // every edge value of layer i has been issued
+    if (row == 0 && lane == 0) {
+      __threadfence();
+      st_release(myProg, i + 1);
     }
   }
 }
@@ -259,6 +517,15 @@ int launch_diffuse_rates(Context& c, const double* J, const double* ksi24, const
 // ---------------------------------------------------------------------------------------------------------
 // host side: plan + launch
 // ---------------------------------------------------------------------------------------------------------
+// FAST mode evaluates a layer with the reference's own operation sequence when one of its segments is shorter than
+// this (in cells).  Every segment of a cell enters Jmean with weight 1/(nseg * ndirections) whatever its length
+// (transportRoutinesModule.f90:953-955), and the reference formula's rounding noise is ~1.1e-16 / tau_segment, so a
+// segment disturbs a cell's Jmean by ~1.1e-16 / (576 tau_segment) where all directions contribute alike, and by up to
+// ~1.1e-16 / (3 tau_segment) where a single direction dominates (cells shadowed from most sides).  Measured at 128^3
+// (tau_cell >= 1e-3): threshold 1e-4 leaves a worst cell at 1.03e-9 between FAST and FAITHFUL, 1e-3 at ~1e-10.
+// 0.2% of the (direction, layer) pairs take this branch.
+constexpr double kThinLen = 1e-3;
+
 static LayerSeg make_layer_seg(const RayPattern& p, double cellSize, double weight) {
   LayerSeg L;
   std::memset(&L, 0, sizeof(L));
@@ -278,14 +545,45 @@ static LayerSeg make_layer_seg(const RayPattern& p, double cellSize, double weig
   L.nseg = 1 + (kind != 0) + (kind == 2 || kind == 4);
   for (int s = 0; s < 3; s++) {
     L.d[s] = cellSize * len[s];
-    L.invd[s] = L.d[s] > 0. ? 1.0 / L.d[s] : 0.;
   }
   L.w = weight;
   L.wn = weight / (double)L.nseg;
+  for (int s = 0; s < 3; s++) L.cs[s] = L.d[s] > 0. ? 1.6069380442589903e60 * L.wn / L.d[s] : 0.;  // 2^200 wn / d
   L.thin = 0;
   for (int sg = 0; sg < L.nseg; sg++)
-    if (len[sg] < 1e-2) L.thin = 1;
+    if (len[sg] < kThinLen) L.thin = 1;
   return L;
+}
+
+
+// ---- persistent march path: host side -------------------------------------------------------------------
+template <bool FA, int EXPV, int MINB>
+static int march_launch(Context& c, const MarchBatch& mb, dim3 grid, size_t smemBytes, int N, int n, const double* uvb,
+                        cudaStream_t st) {
+  auto kern = sweep_march_kernel<FA, EXPV, MINB>;
+  RTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(32, 8, 1);
+  cfg.dynamicSmemBytes = smemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;  // all blocks co-resident, or the launch fails instead of hanging
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  RTB_CUDA(cudaLaunchKernelEx(&cfg, kern, mb, (const double*)c.dKappa, N, n, uvb[0], uvb[1], uvb[2], c.dErr, c.tune.marchDebug));
+  return RTB200_OK;
+}
+
+template <bool FA, int EXPV, int MINB>
+static int march_capacity(Context& c, size_t smemBytes, int* blocks) {
+  auto kern = sweep_march_kernel<FA, EXPV, MINB>;
+  RTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+  int perSm = 0;
+  RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 256, smemBytes));
+  *blocks = perSm * c.smCount;
+  return RTB200_OK;
 }
 
 static void launch_cells(int dense, int expv, bool faithful, dim3 grid, cudaStream_t s, const BatchParams& bp,
@@ -299,6 +597,85 @@ static void launch_cells(int dense, int expv, bool faithful, dim3 grid, cudaStre
   else sweep_cell_kernel<false, E, 2><<<grid, block, 0, s>>>(bp, kappa, N)
   if (expv == 1) { RTB_LAUNCH(1); } else { RTB_LAUNCH(0); }
 #undef RTB_LAUNCH
+}
+
+
+// Runs the whole sweep with the persistent kernel.  Returns -1 when the grid of one zone task does not fit
+// co-resident on the device (large n): the caller then uses the per-layer launches.
+static int run_march(Context& c, int n, const double* uvb, double* dJout, cudaStream_t s, bool faithful) {
+  const int64_t N = c.nleaf, npl = (int64_t)(n + 1) * (n + 1);
+  const int ntask = (int)c.uniTasks.size();
+  int maxNd = 1;
+  for (const auto& T : c.uniTasks) maxNd = std::max(maxNd, T.ndir);
+  const size_t smemBytes = (16 + (size_t)2 * maxNd * 768) * sizeof(double);
+  const int expv = c.tune.expVariant;
+  int cap = 0;
+  // register budget: 2 blocks per SM (128 registers) unless the tile buffers allow 4 (64 registers)
+  const bool dense = !faithful && c.tune.minBlocks >= 2 && 4 * (smemBytes + 1024) <= 227 * 1024;
+  int st = faithful ? march_capacity<true, 0, 2>(c, smemBytes, &cap)
+                    : dense ? (expv == 1 ? march_capacity<false, 1, 4>(c, smemBytes, &cap) : march_capacity<false, 0, 4>(c, smemBytes, &cap))
+                            : (expv == 1 ? march_capacity<false, 1, 2>(c, smemBytes, &cap) : march_capacity<false, 0, 2>(c, smemBytes, &cap));
+  if (st) return st;
+  const int gx = (n + 30) / 31, gy = (n + 7) / 8;
+  const int perTask = gx * gy;
+  int B = std::min(std::min(cap / perTask, kMaxMarchTasks), ntask);
+  if (c.tune.slots > 0) B = std::min(B, c.tune.slots);
+  if (B < 1) return -1;
+  if (int e = ensure_buffer((void**)&c.dAcc, &c.accBytes, (size_t)B * 3 * N * sizeof(double))) return e;
+  const size_t ringPerTask = (size_t)kRing * maxNd * 3 * npl;
+  if (int e = ensure_buffer((void**)&c.dPlanes, &c.planeBytes, (size_t)B * ringPerTask * sizeof(double))) return e;
+  if (int e = ensure_buffer((void**)&c.dMarchProg, &c.marchProgBytes, (size_t)B * perTask * sizeof(int32_t))) return e;
+  const size_t segPerTask = (size_t)n * kMaxDirPerTask;
+  if (c.marchSegKey != c.uniPlanKey) {
+    if (int e = ensure_buffer((void**)&c.dMarchSeg, &c.marchSegBytes, (size_t)ntask * segPerTask * sizeof(LayerSeg))) return e;
+    for (int t = 0; t < ntask; t++)
+      RTB_CUDA(cudaMemcpyAsync((LayerSeg*)c.dMarchSeg + (size_t)t * segPerTask, c.uniTasks[t].seg.data(),
+                               segPerTask * sizeof(LayerSeg), cudaMemcpyHostToDevice, s));
+    RTB_CUDA(cudaStreamSynchronize(s));  // the host vectors may be rebuilt by the next plan
+    c.marchSegKey = c.uniPlanKey;
+  }
+  RTB_CUDA(cudaEventRecord(c.evSweep0, s));
+  {
+    const int64_t total = (int64_t)B * ringPerTask;
+    int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)c.smCount * 16);
+    fill_planes_kernel<<<blocks, 256, 0, s>>>(c.dPlanes, npl, total, uvb[0], uvb[1], uvb[2]);
+  }
+  int64_t launches = 1;
+  static thread_local MarchBatch mb;
+  for (int base = 0; base < ntask; base += B) {
+    const int nb = std::min(B, ntask - base);
+    RTB_CUDA(cudaMemsetAsync(c.dMarchProg, 0, (size_t)nb * perTask * sizeof(int32_t), s));
+    for (int z = 0; z < nb; z++) {
+      const UniTaskHost& T = c.uniTasks[base + z];
+      MarchTask& m = mb.t[z];
+      m.seg = (const LayerSeg*)c.dMarchSeg + (size_t)(base + z) * segPerTask;
+      m.acc = c.dAcc + (size_t)z * 3 * N;
+      m.ring = c.dPlanes + (size_t)z * ringPerTask;
+      m.prog = c.dMarchProg + (size_t)z * perTask;
+      m.origin = (int32_t)T.origin; m.si = (int32_t)T.si; m.sj = (int32_t)T.sj; m.sk = (int32_t)T.sk;
+      m.ndir = T.ndir; m.laneIsK = T.laneIsK; m.firstInSlot = base == 0; m.pad = 0;
+    }
+    dim3 grid(gx, gy, nb);
+    if (faithful) st = march_launch<true, 0, 2>(c, mb, grid, smemBytes, (int)N, n, uvb, s);
+    else if (dense) st = expv == 1 ? march_launch<false, 1, 4>(c, mb, grid, smemBytes, (int)N, n, uvb, s)
+                                   : march_launch<false, 0, 4>(c, mb, grid, smemBytes, (int)N, n, uvb, s);
+    else st = expv == 1 ? march_launch<false, 1, 2>(c, mb, grid, smemBytes, (int)N, n, uvb, s)
+                        : march_launch<false, 0, 2>(c, mb, grid, smemBytes, (int)N, n, uvb, s);
+    if (st) return st;
+    launches++;
+  }
+  RTB_CUDA(cudaEventRecord(c.evSweep1, s));
+  {
+    // tasks base+z with z >= ntask % B never ran in the last batch: every slot z < min(B, ntask) has been written
+    const int slotsUsed = std::min(B, ntask);
+    int blocks = std::min<int64_t>((3 * N + 255) / 256, (int64_t)c.smCount * 16);
+    merge_slots_kernel<<<blocks, 256, 0, s>>>(c.dAcc, slotsUsed, 3 * N, dJout);
+  }
+  RTB_CUDA(cudaGetLastError());
+  c.uniLaunches = launches;
+  c.lastSweepLaunches = launches;
+  c.lastLaunches = launches + 2 + (ntask + B - 1) / B;  // + compute_opacities + merge + the counter memsets
+  return RTB200_OK;
 }
 
 int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std::vector<Direction>& dirs,
@@ -315,7 +692,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
   std::string planKey;
   {
     char buf[128];
-    snprintf(buf, sizeof(buf), "%d:%a:%d:%d:%d:", n, c.boxSize, nAngularLevel, c.tune.slots, c.tune.lockstep);
+    snprintf(buf, sizeof(buf), "%d:%a:%d:%d:%d:%d:", n, c.boxSize, nAngularLevel, c.tune.slots, c.tune.lockstep, c.tune.dirsPerTask);
     planKey = buf;
     for (const auto& d : dirs) { snprintf(buf, sizeof(buf), "%lld,", (long long)d.iray); planKey += buf; }
   }
@@ -329,7 +706,8 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
       for (int d = 0; d < ndir; d++)
         if (dirs[d].izone == z) mine.push_back(d);
       if (mine.empty()) continue;
-      const int pieces = ((int)mine.size() + kMaxDirPerTask - 1) / kMaxDirPerTask;
+      const int dpt = std::max(1, std::min(c.tune.dirsPerTask > 0 ? c.tune.dirsPerTask : kMaxDirPerTask, kMaxDirPerTask));
+      const int pieces = ((int)mine.size() + dpt - 1) / dpt;
       size_t o = 0;
       for (int pc = 0; pc < pieces; pc++) {
         const size_t cnt = (mine.size() - o + (pieces - pc) - 1) / (pieces - pc);  // balanced split
@@ -349,6 +727,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
           for (int i = 0; i < n; i++) {
             if (pat[i].status) return pat[i].status;
             LayerSeg L = make_layer_seg(pat[i], cellSize, weight);
+            if (c.tune.marchDebug & 4) L.thin = 0;  // timing experiments only
             T.seg[(size_t)i * kMaxDirPerTask + q] = L;
             nseg += (int64_t)L.nseg * nn;
           }
@@ -398,6 +777,14 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
     return RTB200_OK;
   }
 
+  if (c.tune.march) {
+    const int mst = run_march(c, n, uvb, dJout, s, c.mathMode == RTB200_MATH_FAITHFUL);
+    if (mst >= 0) return mst;
+  }
+  // the march path may have re-sized the shared scratch buffers for its own layout
+  if (int st = ensure_buffer((void**)&c.dAcc, &c.accBytes, (size_t)c.uniSlots * 3 * N * sizeof(double))) return st;
+  if (int st = ensure_buffer((void**)&c.dPlanes, &c.planeBytes, (size_t)2 * std::max(ndir, 1) * 3 * npl * sizeof(double))) return st;
+
   dim3 grid((n + 30) / 31, (n + 7) / 8, 1);
   double* planeA = c.dPlanes;
   double* planeB = c.dPlanes + (size_t)ndir * 3 * npl;
@@ -422,53 +809,33 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
       int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)c.smCount * 16);
       fill_planes_kernel<<<blocks, 256, 0, st>>>(c.dPlanes, npl, total, uvb[0], uvb[1], uvb[2]);
     }
-    // fill one task's parameters for one layer; returns the number of directions taken by this pass
-    auto fill = [&](StepParams& sp, const UniTaskHost& T, int step, int pass, int first) -> int {
+    // fill one task's parameters for one layer
+    auto fill = [&](StepParams& sp, const UniTaskHost& T, int step, int first) -> int {
       sp.acc = c.dAcc + (size_t)T.slot * 3 * N;
       sp.sj = (int32_t)T.sj; sp.sk = (int32_t)T.sk;
       sp.laneIsK = T.laneIsK; sp.n = n;
       sp.planeIn = ((step & 1) ? planeA : planeB) + (size_t)T.planeFirst * 3 * npl;
       sp.planeOut = ((step & 1) ? planeB : planeA) + (size_t)T.planeFirst * 3 * npl;
       sp.origin = (int32_t)(T.origin + step * T.si);
-      int cnt = 0;
-      for (int q = 0; q < T.ndir; q++) {
-        const LayerSeg& L = T.seg[(size_t)step * kMaxDirPerTask + q];
-        const bool thin = !faithful && L.thin;
-        if (thin != (pass == 1)) continue;
-        sp.P[cnt] = L;
-        sp.pl[cnt] = q;
-        cnt++;
-      }
-      sp.ndir = cnt;
+      for (int q = 0; q < T.ndir; q++) sp.P[q] = T.seg[(size_t)step * kMaxDirPerTask + q];
+      sp.ndir = T.ndir;
       sp.firstInSlot = first;
-      return cnt;
+      return T.ndir;
     };
-    // A layer whose pattern has a very short segment (a corner clip, len < 1e-2 cell) is evaluated with the
-    // reference's own operation sequence even in FAST mode: there tau is tiny and the rounding noise of the
-    // reference's (Iin-Iout)/log(Iin/Iout), ~1.1e-16/tau, would otherwise show up as a parity difference.
-    // ~1.7% of the (direction, layer) pairs; they go to a second launch (pass 1) of the FAITHFUL kernel.
     static thread_local BatchParams bp;
     if (lockstep) {
       // all tasks of a batch advance one layer per launch; each task of a batch has its own accumulator slot
       for (int base = 0; base < ntask; base += slots) {
         const int nb = std::min(slots, ntask - base);
-        std::vector<int> firstFlag(nb);
-        for (int z = 0; z < nb; z++) firstFlag[z] = c.uniTasks[base + z].firstInSlot;
         for (int step = 0; step < n; step++) {
-          std::vector<int> fastDone(nb, 0);
-          for (int pass = 0; pass < 2; pass++) {
-            int cntZ = 0;
-            for (int z = 0; z < nb; z++) {
-              const UniTaskHost& T = c.uniTasks[base + z];
-              const int first = fastDone[z] ? 0 : firstFlag[z];
-              if (fill(bp.t[cntZ], T, step, pass, first) > 0) { cntZ++; fastDone[z] = 1; }
-            }
-            if (cntZ == 0) continue;
-            dim3 gz = grid;
-            gz.z = cntZ;
-            launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful || pass == 1, gz, st, bp, c.dKappa, (int)N);
-            nLaunched++;
+          for (int z = 0; z < nb; z++) {
+            const UniTaskHost& T = c.uniTasks[base + z];
+            fill(bp.t[z], T, step, T.firstInSlot);  // every layer touches its own cells once per task
           }
+          dim3 gz = grid;
+          gz.z = nb;
+          launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, gz, st, bp, c.dKappa, (int)N);
+          nLaunched++;
         }
       }
       return RTB200_OK;
@@ -481,13 +848,9 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
         const UniTaskHost& T = c.uniTasks[t];
         if (T.slot != k) continue;
         for (int step = 0; step < n; step++) {
-          int first = T.firstInSlot;
-          for (int pass = 0; pass < 2; pass++) {
-            if (fill(bp.t[0], T, step, pass, first) == 0) continue;
-            first = 0;
-            launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful || pass == 1, grid, cs, bp, c.dKappa, (int)N);
-            nLaunched++;
-          }
+          fill(bp.t[0], T, step, T.firstInSlot);
+          launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, grid, cs, bp, c.dKappa, (int)N);
+          nLaunched++;
         }
       }
       if (slots > 1) {

@@ -34,7 +34,7 @@ const char* last_cuda_error();
 // j-1; the third segment by the other one.
 struct LayerSeg {
   double d[3];     // path length [cm]: cellSize * len
-  double invd[3];  // 1 / d
+  double cs[3];    // fast mode: 2^200 * (weight / nseg) / d   (segment_math.cuh, segment_fast)
   double wn;       // weight / nseg   (fast mode)
   double w;        // weight          (faithful mode divides by nseg first, transportRoutinesModule.f90:953)
   int32_t kind;
@@ -67,6 +67,9 @@ struct Tuning {
   int minBlocks = 2;     // 0: compiler's register choice (2 blocks per SM); 1: cap for 3 blocks; 2: cap for 4 blocks
   int expVariant = 1;    // exp(-tau) of the fast path: 0 = polynomial, 1 = 16-entry shared-memory table
   double l2BudgetMB = 96.0;
+  int march = 0;         // uniform sweep: 1 = persistent layer-marching kernel (experimental, slower: DESIGN.md)
+  int dirsPerTask = 0;   // directions of one zone swept together (0 = kMaxDirPerTask)
+  int marchDebug = 0;    // experiments only: 1 = skip the neighbour polling (wrong results), 2 = spin without nanosleep
   int portableMath = 1;  // point path, FAITHFUL mode: exp/log from portable_math.h (bit-identical on host and device)
   int pointBatch = 0;    // sources per batch of the point path (0 = as many as fit in half of the free memory)
 };
@@ -132,6 +135,11 @@ struct Context {
   size_t accBytes = 0;
   double* dPlanes = nullptr;   // ping-pong top-exit planes
   size_t planeBytes = 0;
+  void* dMarchSeg = nullptr;   // per-task layer tables of the persistent uniform sweep
+  size_t marchSegBytes = 0;
+  std::string marchSegKey;
+  int32_t* dMarchProg = nullptr;
+  size_t marchProgBytes = 0;
   void* dAmrScratch = nullptr;
   size_t amrScratchBytes = 0;
   int32_t* dErr = nullptr;     // device error flag

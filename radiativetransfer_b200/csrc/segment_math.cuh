@@ -45,7 +45,9 @@ static __constant__ double kExpTable[16] = {
 // Returns Ts = 2^(-k/16) and p = exp(-r) - 1, so that  exp(-tau) = Ts + Ts*p  and  1 - exp(-tau) = (1 - Ts) - Ts*p
 // (1 - Ts is exact, and for k == 0 the latter is exactly -p: no cancellation for small tau).
 __device__ __forceinline__ void exp_neg_parts(double tau, const double* __restrict__ T, double& Ts, double& p) {
-  tau = fmin(tau, kExpC[11]);
+  // tau >= 0 (kappa >= 0, path > 0): clamp at 707 with ONE integer min on the high word instead of an FP64 compare
+  // and two selects (0x40861800'00000000 = 707.0; the low word stays, so the clamped value lies in [707, 707.0005))
+  tau = __hiloint2double(min(__double2hiint(tau), 0x40861800), __double2loint(tau));
   double t = fma(tau, kExpC[7], kExpC[8]);
   int k = __double2loint(t);
   double fn = t - kExpC[8];
@@ -71,7 +73,7 @@ static __constant__ double kExpP[16] = {
     -1.90821492927058770002e-10,  // [14] -ln2 lo
     707.0};
 __device__ __forceinline__ void exp_neg_parts_poly(double tau, double& Ts, double& p) {
-  tau = fmin(tau, kExpP[15]);
+  tau = __hiloint2double(min(__double2hiint(tau), 0x40861800), __double2loint(tau));
   double t = fma(tau, kExpP[11], kExpP[12]);
   int n = __double2loint(t);
   double fn = t - kExpP[12];
@@ -99,6 +101,35 @@ __device__ __forceinline__ double exp_neg_only(double tau, const double* __restr
   if (EXPV == 1) exp_neg_parts(tau, T, Ts, p);
   else exp_neg_parts_poly(tau, Ts, p);
   return fma(Ts, p, Ts);
+}
+
+// FAST-mode segment: Iout = Iin e^-tau and the segment's contribution to the cell's mean intensity,
+//   J_seg * weight/nseg = Iin (1 - e^-tau) / (kappa d) * wn = [Iin (1 - e^-tau)] * cs * (2^-200 / kappa),
+// cs = 2^200 wn / d a per-(layer, direction, segment) constant from the host and 2^-200/kappa a per-cell constant that
+// the caller applies ONCE per layer to the sum A over all directions and segments (the power of two keeps every
+// intermediate far from the subnormal range, including the kappa -> 0 limit).  With Ts = 2^(-k/16), p = e^-r - 1:
+//   X = Iin Ts,  Iout = X + X p,  Iin (1 - e^-tau) = (Iin - X) - X p      (Iin - X is exact for k = 0: no cancellation)
+// 5 FP64 instructions after the exponential's 12, instead of 8.
+template <int EXPV>
+__device__ __forceinline__ double segment_fast(double Iin, double tau, double cs, const double* __restrict__ T, double& A) {
+  double Ts, p;
+  if (EXPV == 1) exp_neg_parts(tau, T, Ts, p);
+  else exp_neg_parts_poly(tau, Ts, p);
+  const double X = Iin * Ts;
+  const double Iout = fma(X, p, X);
+  const double Z = fma(-X, p, Iin - X);
+  // Iout == 0 (underflow): the reference gets (Iin - 0)/log(Iin/0) = 0.  Integer test + predicated DFMA.
+  if (((__double2hiint(Iout) << 1) | __double2loint(Iout)) != 0) A = fma(Z, cs, A);
+  return Iout;
+}
+
+template <int EXPV>
+__device__ __forceinline__ double attenuate_fast(double Iin, double tau, const double* __restrict__ T) {
+  double Ts, p;
+  if (EXPV == 1) exp_neg_parts(tau, T, Ts, p);
+  else exp_neg_parts_poly(tau, Ts, p);
+  const double X = Iin * Ts;
+  return fma(X, p, X);
 }
 
 struct SegResult {
