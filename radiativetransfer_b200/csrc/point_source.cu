@@ -72,6 +72,8 @@ struct PointParams {
   double outRadiusKpc[7]; // outputRadius(i) * kpc  [cm]
   double outRadius[7];
   double kpc;
+  double outRadiusCells[7];  // outputRadius(i)*kpc in base-cell units: a conservative pre-filter for the exact test
+  double cellSize[32];       // physicalBoxSize / (float(2**level) * float(nx)), equiSources.f90:3176
   const double* outSigma; // [4][300] ratios sigma(nu)/sigma_threshold: 24, 26, 25, dust
   // outputs
   double* rates;          // [6][nleaf]: krate24, krate25, krate26, crate24, crate25, crate26
@@ -176,6 +178,20 @@ __device__ __forceinline__ DepthIdx depth_index(double t1, double t2, double t3,
   return q;
 }
 
+// FAST mode: index = floor(tau) (table spacing 10/10 = 1) without the reference's tau/10.*10. round trip; the two can
+// differ only where tau is within an ulp of a node, where the interpolant is continuous
+__device__ __forceinline__ DepthIdx depth_index_fast(double t1, double t2, double t3, double tD, int dust) {
+  DepthIdx q;
+  q.status = 0;
+  if (t1 > 10. || t2 > 10. || t3 > 10. || tD > 10.) { q.status = 1; return q; }
+  q.i1 = min((int)t1, 9); q.i2 = min((int)t2, 9); q.i3 = min((int)t3, 9);
+  q.c1 = t1 - (double)q.i1; q.c2 = t2 - (double)q.i2; q.c3 = t3 - (double)q.i3;
+  if (dust == 0) { q.iD = 0; q.cD = 0.; }
+  else { q.iD = min((int)tD, 9); q.cD = tD - (double)q.iD; }
+  if (min(min(q.i1, q.i2), min(q.i3, q.iD)) < 0) q.status = -1;
+  return q;
+}
+
 template <bool PORTABLE>
 __device__ __forceinline__ int rates_faithful(const PointParams& P, const double* __restrict__ LT, int r, double t1,
                                               double t2, double t3, double tD, double& num, double& heat) {
@@ -203,86 +219,64 @@ __device__ __forceinline__ int rates_faithful(const PointParams& P, const double
 // R_r(d) - R_r(d + tau e_r) = R_r(d) * (1 - exp(dlog)),  dlog = nr(d + tau e_r) - nr(d) = integral of the interpolant's
 // slope along axis r, which is piecewise constant: per crossed table cell the slope is a bilinear (trilinear with dust)
 // combination of node differences.  One exponential + one expm1 per (reaction, table) instead of two exponentials whose
-// difference cancels; corners of the start cell are shared by the three reactions' weights.
-struct Weights {
-  double w[3][2];  // [axis 1..3][low/high]
-  double wD[2];
-};
-
-__device__ __forceinline__ double tab(const double* __restrict__ T, int i1, int i2, int i3, int iD) {
-  return __ldg(T + ((iD * 11 + i3) * 11 + i2) * 11 + i1);
-}
-
-// value of the log-interpolant of table T at index-space point (x1,x2,x3,xD) given by cell indices and weights
-__device__ __forceinline__ double interp_full(const double* __restrict__ T, const DepthIdx& q, int dust) {
-  double acc = 0.;
-  const int nD = dust ? 2 : 1;
-  for (int kD = 0; kD < nD; kD++) {
-    const double wD = dust ? (kD ? q.cD : 1. - q.cD) : 1.;
-    double accD = 0.;
-#pragma unroll
-    for (int k3 = 0; k3 < 2; k3++) {
-      const double w3 = k3 ? q.c3 : 1. - q.c3;
-#pragma unroll
-      for (int k2 = 0; k2 < 2; k2++) {
-        const double w2 = k2 ? q.c2 : 1. - q.c2;
-        const double lo = tab(T, q.i1, q.i2 + k2, q.i3 + k3, q.iD + kD), hi = tab(T, q.i1 + 1, q.i2 + k2, q.i3 + k3, q.iD + kD);
-        accD += w3 * w2 * (lo + q.c1 * (hi - lo));
-      }
-    }
-    acc += wD * accD;
+// difference cancels, and 8 table reads instead of 16 (32 with dust): the start value and the slope share their nodes.
+// value of the log-interpolant restricted to the table nodes with index iAx along AXIS (0,1,2 = tau1,tau2,tau3), at
+// the transverse position of q: a bilinear (with dust: trilinear) combination of 4 (8) nodes
+template <int AXIS>
+__device__ __forceinline__ double face_sum(const double* __restrict__ T, int iAx, const DepthIdx& q, int dust) {
+  constexpr int sA = AXIS == 0 ? 1 : (AXIS == 1 ? 11 : 121);
+  constexpr int s1 = AXIS == 0 ? 11 : 1, s2 = AXIS == 2 ? 11 : 121;   // strides of the two transverse depth axes
+  const int j1 = AXIS == 0 ? q.i2 : q.i1, j2 = AXIS == 2 ? q.i2 : q.i3;
+  const double c1 = AXIS == 0 ? q.c2 : q.c1, c2 = AXIS == 2 ? q.c2 : q.c3;
+  const double* p = T + iAx * sA + j1 * s1 + j2 * s2 + q.iD * kPlane;
+  const double a0 = __ldg(p), a1 = __ldg(p + s1), b0 = __ldg(p + s2), b1 = __ldg(p + s1 + s2);
+  const double lo = fma(c1, a1 - a0, a0), hi = fma(c1, b1 - b0, b0);
+  double v = fma(c2, hi - lo, lo);
+  if (dust) {
+    const double* d = p + kPlane;
+    const double e0 = __ldg(d), e1 = __ldg(d + s1), f0 = __ldg(d + s2), f1 = __ldg(d + s1 + s2);
+    const double lo2 = fma(c1, e1 - e0, e0), hi2 = fma(c1, f1 - f0, f0);
+    const double v2 = fma(c2, hi2 - lo2, lo2);
+    v = fma(q.cD, v2 - v, v);
   }
-  return acc;
+  return v;
 }
 
-// slope of the log-interpolant along `axis` (0,1,2 = tau1,tau2,tau3) inside the table cell `cellIdx` of that axis, at
-// the transverse position of q
-__device__ __forceinline__ double slope_axis(const double* __restrict__ T, const DepthIdx& q, int dust, int axis, int cellIdx) {
-  double acc = 0.;
-  const int nD = dust ? 2 : 1;
-  const int ia = axis == 0 ? 1 : 0, ib = axis == 2 ? 1 : 2;  // the two transverse depth axes
-  const int qi[3] = {q.i1, q.i2, q.i3};
-  const double qc[3] = {q.c1, q.c2, q.c3};
-  for (int kD = 0; kD < nD; kD++) {
-    const double wD = dust ? (kD ? q.cD : 1. - q.cD) : 1.;
-    double accD = 0.;
-#pragma unroll
-    for (int kb = 0; kb < 2; kb++) {
-#pragma unroll
-      for (int ka = 0; ka < 2; ka++) {
-        int idx[3];
-        idx[axis] = cellIdx; idx[ia] = qi[ia] + ka; idx[ib] = qi[ib] + kb;
-        const double lo = tab(T, idx[0], idx[1], idx[2], q.iD + kD);
-        idx[axis] = cellIdx + 1;
-        const double hi = tab(T, idx[0], idx[1], idx[2], q.iD + kD);
-        accD += (ka ? qc[ia] : 1. - qc[ia]) * (kb ? qc[ib] : 1. - qc[ib]) * (hi - lo);
-      }
-    }
-    acc += wD * accD;
-  }
-  return acc;
-}
-
-// deposit of reaction r (number and energy) for a step tau along its own depth axis, FAST mode
-__device__ __forceinline__ void rates_fast(const PointParams& P, const double* __restrict__ LT, const DepthIdx& q, int r,
+// deposit of one reaction (number and energy) for a step tau along its own depth axis, FAST mode.  Along that axis the
+// interpolant is piecewise linear with nodes at the integers (table spacing 10/10 = 1), so
+//   log R(end) - log R(start) = sum over the crossed table cells of  (length inside the cell) * (H - L),
+// L/H = face_sum at the cell's lower/upper node; the upper face of one cell is the lower face of the next.
+template <int AXIS>
+__device__ __forceinline__ void rates_fast(const PointParams& P, const double* __restrict__ LT, const DepthIdx& q,
                                            double depthAxis, double tau, double& dnum, double& dheat) {
-  // axis of reaction r: r = 0 -> tau1, r = 1 -> tau2, r = 2 -> tau3
-  const double* R = LT + (size_t)r * P.planes * kPlane;
-  const double* E = LT + (size_t)(3 + r) * P.planes * kPlane;
-  const double n0 = exp(interp_full(R, q, P.dust)), h0 = exp(interp_full(E, q, P.dust));
+  const double* R = LT + (size_t)AXIS * P.planes * kPlane;
+  const double* E = LT + (size_t)(3 + AXIS) * P.planes * kPlane;
+  if (tau == 0.) { dnum = 0.; dheat = 0.; return; }  // R(d) - R(d) (e.g. no helium: tau2 = tau3 = 0)
+  const int i0 = AXIS == 0 ? q.i1 : (AXIS == 1 ? q.i2 : q.i3);
+  const double c0 = AXIS == 0 ? q.c1 : (AXIS == 1 ? q.c2 : q.c3);
+  double Lr = face_sum<AXIS>(R, i0, q, P.dust), Hr = face_sum<AXIS>(R, i0 + 1, q, P.dust);
+  double Le = face_sum<AXIS>(E, i0, q, P.dust), He = face_sum<AXIS>(E, i0 + 1, q, P.dust);
+  const double n0 = exp(fma(c0, Hr - Lr, Lr)), h0 = exp(fma(c0, He - Le, Le));
   const double end = depthAxis + tau;
   if (end > 10.) { dnum = n0; dheat = h0; return; }  // the table returns 0 beyond tau = 10
-  if (tau == 0.) { dnum = 0.; dheat = 0.; return; }
-  const int i0 = r == 0 ? q.i1 : (r == 1 ? q.i2 : q.i3);
-  int iEnd = (int)end;  // index space == tau space (spacing 1)
+  int iEnd = (int)end;
   if (iEnd > 9) iEnd = 9;
-  double dn = 0., dh = 0.;
-  for (int c = i0; c <= iEnd; c++) {
-    const double lo = c == i0 ? depthAxis : (double)c;
-    const double hi = c == iEnd ? end : (double)(c + 1);
-    const double len = hi - lo;
-    dn += len * slope_axis(R, q, P.dust, r, c);
-    dh += len * slope_axis(E, q, P.dust, r, c);
+  double dn, dh;
+  if (iEnd <= i0) {  // the step stays inside the start cell (the common case)
+    dn = tau * (Hr - Lr);
+    dh = tau * (He - Le);
+  } else {
+    const double first = (double)(i0 + 1) - depthAxis;
+    dn = first * (Hr - Lr);
+    dh = first * (He - Le);
+    for (int c = i0 + 1; c <= iEnd; c++) {
+      Lr = Hr; Le = He;
+      Hr = face_sum<AXIS>(R, c + 1, q, P.dust);
+      He = face_sum<AXIS>(E, c + 1, q, P.dust);
+      const double len = c == iEnd ? end - (double)c : 1.0;
+      dn = fma(len, Hr - Lr, dn);
+      dh = fma(len, He - Le, dh);
+    }
   }
   dnum = -n0 * expm1(dn);
   dheat = -h0 * expm1(dh);
@@ -307,6 +301,7 @@ __global__ void __launch_bounds__(128) point_march_kernel(const __grid_constant_
   double* diag = P.diag + (size_t)s * kDiagStride;
   const double fnx = (double)(float)P.nx;
   int strategy = 1;
+  int irLow = 0;
 
   if (active) {
     if (pixelLevel == 1) {
@@ -454,7 +449,7 @@ __global__ void __launch_bounds__(128) point_march_kernel(const __grid_constant_
 
       // ---- optical depths of the segment (:3176-3196) ----
       const int64_t lf = here.leaf;
-      const double cellSize = D(P.boxSize, M(scale, fnx));
+      const double cellSize = P.cellSize[here.lvl];
       const double plen = M(cellSize, len);
       const double hi = __ldg(P.HI + lf);
       const double tau1 = M(M(plen, hi), (double)6.3e-18f);
@@ -468,20 +463,25 @@ __global__ void __launch_bounds__(128) point_march_kernel(const __grid_constant_
 
       // ---- escape diagnostics (:3198-3233) ----
       {
-        const double t1 = D(M(oldRadius, P.boxSize), fnx), t2 = D(M(radius, P.boxSize), fnx);
-        for (int ir = 0; ir < 7; ir++) {
-          const double tr = P.outRadiusKpc[ir];
-          if (tr >= t1 && tr <= t2) {
-            const double ratio = D(S(tr, t1), S(t2, t1));
-            atomicAdd(diag + ir, M(ndot, exp_ref<PORTABLE>(-A(A(M(ratio, A(tau1, tauD)), d1), dD))));
-            if (ir == 6) {
-              const double o1 = A(M(ratio, tau1), d1), o2 = A(M(ratio, tau2), d2), o3 = A(M(ratio, tau3), d3),
-                           oD = A(M(ratio, tauD), dD);
-              atomicAdd(diag + 14, M(ndot, exp_ref<PORTABLE>(-oD)));
-              for (int ie = 0; ie < 300; ie++) {
-                const double a1 = M(__ldg(P.outSigma + ie), o1), a2 = M(__ldg(P.outSigma + 300 + ie), o2),
-                             a3 = M(__ldg(P.outSigma + 600 + ie), o3), aD = M(__ldg(P.outSigma + 900 + ie), oD);
-                atomicAdd(diag + 16 + ie, M(ndot, exp_ref<PORTABLE>(-A(A(A(a1, a2), a3), aD))));
+        // the reference tests all 7 output radii on every segment; radii only grow along a ray, so the exact test is
+        // only evaluated for radii that can lie inside [oldRadius, radius] (1e-9 relative safety margin)
+        while (irLow < 7 && P.outRadiusCells[irLow] * (1. + 1e-9) < oldRadius) irLow++;
+        if (irLow < 7 && P.outRadiusCells[irLow] <= radius * (1. + 1e-9)) {
+          const double t1 = D(M(oldRadius, P.boxSize), fnx), t2 = D(M(radius, P.boxSize), fnx);
+          for (int ir = irLow; ir < 7; ir++) {
+            const double tr = P.outRadiusKpc[ir];
+            if (tr >= t1 && tr <= t2) {
+              const double ratio = D(S(tr, t1), S(t2, t1));
+              atomicAdd(diag + ir, M(ndot, exp_ref<PORTABLE>(-A(A(M(ratio, A(tau1, tauD)), d1), dD))));
+              if (ir == 6) {
+                const double o1 = A(M(ratio, tau1), d1), o2 = A(M(ratio, tau2), d2), o3 = A(M(ratio, tau3), d3),
+                             oD = A(M(ratio, tauD), dD);
+                atomicAdd(diag + 14, M(ndot, exp_ref<PORTABLE>(-oD)));
+                for (int ie = 0; ie < 300; ie++) {
+                  const double a1 = M(__ldg(P.outSigma + ie), o1), a2 = M(__ldg(P.outSigma + 300 + ie), o2),
+                               a3 = M(__ldg(P.outSigma + 600 + ie), o3), aD = M(__ldg(P.outSigma + 900 + ie), oD);
+                  atomicAdd(diag + 16 + ie, M(ndot, exp_ref<PORTABLE>(-A(A(A(a1, a2), a3), aD))));
+                }
               }
             }
           }
@@ -509,15 +509,15 @@ __global__ void __launch_bounds__(128) point_march_kernel(const __grid_constant_
         dep[1] = M(ndot, S(a, b)); dep[4] = M(ndot, S(ea, eb));
         if (st) { atomicExch(P.err, st); break; }
       } else {
-        const DepthIdx q = depth_index(d1, d2, d3, dD, P.dust);
+        const DepthIdx q = depth_index_fast(d1, d2, d3, dD, P.dust);
         if (q.status < 0) { atomicExch(P.err, RTB200_ERR_IDEPTH); break; }
         if (q.status == 1) {
           for (int i = 0; i < 6; i++) dep[i] = 0.;
         } else {
           double n, h;
-          rates_fast(P, LT, q, 0, d1, tau1, n, h); dep[0] = ndot * n; dep[3] = ndot * h;
-          rates_fast(P, LT, q, 1, d2, tau2, n, h); dep[2] = ndot * n; dep[5] = ndot * h;
-          rates_fast(P, LT, q, 2, d3, tau3, n, h); dep[1] = ndot * n; dep[4] = ndot * h;
+          rates_fast<0>(P, LT, q, d1, tau1, n, h); dep[0] = ndot * n; dep[3] = ndot * h;
+          rates_fast<1>(P, LT, q, d2, tau2, n, h); dep[2] = ndot * n; dep[5] = ndot * h;
+          rates_fast<2>(P, LT, q, d3, tau3, n, h); dep[1] = ndot * n; dep[4] = ndot * h;
         }
       }
 #pragma unroll
@@ -728,6 +728,8 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
   const double kpc = (double)1.e3f * (double)3.08568025e18f;
   for (int i = 0; i < 7; i++) { P.outRadius[i] = (double)orad[i]; P.outRadiusKpc[i] = (double)orad[i] * kpc; }
   P.kpc = kpc;
+  for (int i = 0; i < 7; i++) P.outRadiusCells[i] = P.outRadiusKpc[i] * (double)c.nx / c.boxSize;
+  for (int l = 0; l < 32; l++) P.cellSize[l] = l < 31 ? c.boxSize / ((double)(float)(1u << l) * (double)(float)c.nx) : 0.;
   P.outSigma = dOutSig;
   P.rates = dRates;
   P.nseg = dCounters; P.err = c.dErr;

@@ -241,3 +241,27 @@ def synthetic_spectra(n_wave=1221, seed=0):
                        [0.067, 10.0, 1.9, 4.0, 15.0]])
     return dict(wavelength=wl_A * 1.0e-8, lum=lum, metallicity=np.log10(np.array([0.0004, 0.004, 0.008, 0.020, 0.050])),
                 coef_spectrum=0.37, a_dust=a_dust)
+
+
+def point_workload(n, nsrc, seed=3, uniform=False, box_kpc=100.0):
+    """Config-1/3 style point-source workload: n^3 base grid (optionally one refined level over the central (n/4)^3 base
+    cells), tau_cell(nu_1) log-uniform in [1e-3, 1], metallicities log-uniform in [4e-4, 5e-2]; `nsrc` distinct source
+    leaves inside the refined (central) region.  Returns (grid dict, src_leaf[int32])."""
+    s24 = float(np.float32(6.3e-18))
+    if uniform:
+        g = uniform_grid(n, seed=seed, box_kpc=box_kpc, tau_lo=1e-3, tau_hi=1.0, beta24=s24)
+        rng = np.random.default_rng(seed + 100)
+        g["abun2"] = 10.0 ** rng.uniform(np.log10(4e-4), np.log10(5e-2), n ** 3)
+        c = np.arange(n)
+        central = np.where((c >= 3 * n // 8) & (c < 5 * n // 8))[0]
+        ix = rng.choice(central, nsrc); iy = rng.choice(central, nsrc); iz = rng.choice(central, nsrc)
+        leaves = np.unique(((ix * n + iy) * n + iz).astype(np.int64))
+    else:
+        g = nested_grid(n, 1, central_box_refine(0.375, 0.625, levels=1), seed=seed, box_kpc=box_kpc, tau_lo=1e-3,
+                        tau_hi=1.0, beta24=s24)
+        rng = np.random.default_rng(seed + 100)
+        leaves = np.where(g["level"] == 1)[0]
+    pick = rng.choice(leaves, size=min(nsrc, leaves.size), replace=False)
+    if pick.size < nsrc:  # tiny grids: allow repeats
+        pick = np.concatenate([pick, rng.choice(leaves, size=nsrc - pick.size)])
+    return g, np.sort(pick).astype(np.int32)
