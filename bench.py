@@ -30,17 +30,24 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "ray-cell segment updates/sec (diffuse sweep)"
+METRIC_POINT = "ray-cell segment updates/sec (point-source ray casting + rate deposition)"
 UNIT = "segment-updates/s"
 
-# DRAM traffic of the dominant kernel under `ncu --set full` (profiles/r01_ncu_full_sweep_cell_256.txt):
-# dram__bytes_read.sum + dram__bytes_write.sum per launch over gpu__time_duration, 256^3 workload, 1 GPU
-NCU_TRAFFIC_GBS = {"diffuse-256^3-uniform-192dir": (551.46e6 + 373.16e6) / 268.96e-6 / 1e9}
+# DRAM traffic of the dominant kernel, from one `ncu --set full` capture (profiles/): dram__bytes_read.sum +
+# dram__bytes_write.sum of ONE launch, bytes (compare with roofline.algorithmic_bytes_per_launch)
+NCU_TRAFFIC_BYTES = {
+    "diffuse-256^3-uniform-192dir": 559.42e6 + 385.51e6,   # sweep_cell_kernel, one layer of all 32 zone tasks
+    "point-128^3-amr-100src": 5.62e6 + 2.70e6,             # point_march_kernel, pixel level 6 of 100 sources
+}
 
 WORKLOADS = {
-    # name: (n, description)
     "diffuse-256^3-uniform-192dir": 256,
     "diffuse-128^3-uniform-192dir": 128,
     "diffuse-64^3-uniform-192dir": 64,
+    # point sources: n^3 base grid + one refined level over the central (n/4)^3 base cells, sources inside it
+    "point-128^3-amr-100src": (128, 100),
+    "point-256^3-amr-1000src": (256, 1000),
+    "point-32^3-uniform-1src": (32, 1),
 }
 
 
@@ -113,11 +120,59 @@ def cpu_oracle_sample(n, grid, bg, seconds, threads):
     return nseg / dt, f"{ndirs} of 192 directions of the same {n}^3 grid, {dt:.1f} s, {threads} thread(s)"
 
 
+def point_inputs(workload):
+    from radiativetransfer_b200 import workloads as W
+    n, nsrc = WORKLOADS[workload]
+    g, src = W.point_workload(n, nsrc, uniform="uniform" in workload)
+    return n, g, src, np.ones(src.size, dtype=np.int32), W.synthetic_spectra()
+
+
+def cpu_point_sample(g, src, wt, sp, seconds, threads):
+    """times the CPU oracle (libm, as the reference) on a bounded number of the workload's sources, one source per
+    host thread at a time (each thread a private copy of the octree)"""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import ftte_oracle as fo
+    n = g["nx"]
+    grids = [fo.OracleGrid(n, g["level"], g["HI"], g["HeI"], g["HeII"], g["rho"], g["abun2"], g["box_size"])
+             for _ in range(threads)]
+
+    def one(i):
+        return grids[i % threads].point(sp, src[i:i + 1], wt[i:i + 1])["nseg"]
+
+    t0 = time.perf_counter()
+    done, nseg = 0, 0
+    with ThreadPoolExecutor(threads) as ex:    # ctypes releases the GIL inside the oracle call
+        while done < src.size and (done == 0 or time.perf_counter() - t0 < seconds):
+            chunk = list(range(done, min(done + threads, src.size)))
+            nseg += sum(ex.map(one, chunk))
+            done += len(chunk)
+    dt = time.perf_counter() - t0
+    return nseg / dt, f"{done} of {src.size} sources of the same grid, {dt:.1f} s, {threads} thread(s)"
+
+
 def run_reference(args):
     """CPU arm: the reference algorithm (C++ oracle port; the Fortran cannot be compiled in this image) on the host
     cores, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.workload.startswith("point"):
+        n, g, src, wt, sp = point_inputs(args.workload)
+        threads = args.cpu_threads or int(max(1, min(os.cpu_count() or 1, 32)))
+        vals = []
+        for it in range(args.warmup + args.steps):
+            v, desc = cpu_point_sample(g, src, wt, sp, max(2.0, min(20.0, 150.0 / (args.warmup + args.steps))), threads)
+            if it >= args.warmup:
+                vals.append(v)
+        value = float(np.mean(vals))
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC_POINT, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "leaves": int(g["level"].size), "sources": int(src.size),
+                       "note": "each step = a bounded sample of sources of the workload"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
         return
     n = WORKLOADS[args.workload]
     grid, bg = make_inputs(n)
@@ -150,6 +205,125 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def run_point(args):
+    """point-source workloads: sources are sharded across the ranks (every GPU holds the whole grid), the six per-leaf
+    rate fields are summed with one all-reduce"""
+    import torch
+    import torch.distributed as dist
+
+    import radiativetransfer_b200 as rt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the rtb200 path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    n, g, src, wt, sp = point_inputs(args.workload)
+    N = int(g["level"].size)
+    eng = rt.Transport(device=local)
+    eng.set_grid(n, g["level"], g["HI"], g["HeI"], g["HeII"], g["rho"], g["abun2"], g["box_size"])
+    mine = slice(rank, None, world)                       # round-robin over the (sorted) source list
+    R = torch.zeros(6, N, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        R.zero_()                                          # setZeroRates (equiSources.f90:1246)
+        nseg = eng.point_device(sp, src[mine], wt[mine], R.data_ptr(), stream=stream)
+        if world > 1:
+            dist.all_reduce(R)
+        return nseg
+
+    for _ in range(W):
+        nseg_rank = step()
+    barrier()
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=sample_clocks, args=(stop, samples, local), daemon=True)
+    if rank == 0:
+        th.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        nseg_rank = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    st = eng.last_stats()
+    barrier()
+    t = torch.tensor([ms, float(nseg_rank)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, nseg_total = float(tmax[0]), float(tsum[1])
+    else:
+        nseg_total = float(nseg_rank)
+    ms_per_step = ms / args.steps
+    value = nseg_total / (ms_per_step * 1e-3)
+
+    # end to end through the host-buffer C-ABI call: H2D of the six rate arrays, D2H of them and of the diagnostics
+    hR = np.zeros((6, N))
+    e2e_steps = max(1, min(args.steps, 3))
+    eng.point(sp, src[mine], wt[mine], rates=hR)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = eng.point(sp, src[mine], wt[mine], rates=hR)
+        if world > 1:
+            Rt = torch.from_numpy(out["rates"]).to(dev)
+            dist.all_reduce(Rt)
+            out["rates"] = Rt.cpu().numpy()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if world > 1:
+        tt = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt[0])
+    stop.set()
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = st["algorithmic_bytes"] / (st["device_ms"] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC_POINT, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "leaves": N, "sources": int(src.size), "max_pixel_level": 6,
+                       "dust_approximation": 0, "segment_updates_per_step": nseg_total, "math": "fast",
+                       "parallelism": f"sources sharded over {world} GPU(s), full grid per GPU, all-reduce of 6 rate fields",
+                       "l2_policy": "gather workload: grid arrays larger than L2 at 256^3, tables L2-resident"},
+            "clocks": clocks_summary(samples),
+            "e2e": {"value": nseg_total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 6 * N * 8, "d2h_bytes_per_step": 6 * N * 8 + int(src[mine].size) * 315 * 8},
+            "gpu_launches": int(st["launches"]) * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 else None,
+                         "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "peak_source": peak_src, "kernel": "rtb::point_march_kernel",
+                         "kernel_ms_per_step": st["device_ms"],
+                         "note": "136 B per segment (5 reads + 6 read-modify-writes, SURVEY.md 8d); the path is bound "
+                                 "by fp64 issue and gather latency, not by HBM (profiles/)"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                v, desc = cpu_point_sample(g, src, wt, sp, args.cpu_seconds, 1)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,6 +338,9 @@ def main():
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload.startswith("point"):
+        run_point(args)
         return
 
     import torch
@@ -288,7 +465,10 @@ def main():
             "gpu_launches": int(launches) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
-                         "traffic": NCU_TRAFFIC_GBS.get(args.workload) if world == 1 else None, "peak_source": peak_src,
+                         "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 else None,
+                         "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "algorithmic_bytes_per_launch": alg_bytes_rank / max(1, int(sweep_launches) - 1),
+                         "peak_source": peak_src,
                          "kernel": "rtb::sweep_cell_kernel", "launches_per_step": int(sweep_launches),
                          "algorithmic_bytes_per_step_this_rank": alg_bytes_rank, "kernel_ms_per_step": sweep_ms,
                          "note": "72 B per leaf per direction; zones are swept with their directions fused, so DRAM "
