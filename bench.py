@@ -376,10 +376,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    ar0, ar1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
     def step_resident():
         nseg = eng.diffuse_device(bg["uvb"], bg["beta"], J.data_ptr(), rays=rays, stream=stream)
         if world > 1:
+            ar0.record()
             dist.all_reduce(J)            # per-leaf Jmean1..3 summed over the ranks' direction shards (NCCL, NVLink)
+            ar1.record()
         return nseg
 
     # ---- resident-data timing: W warm-ups, then exactly K steps between barrier + synchronize ----
@@ -404,10 +408,15 @@ def main():
     alg_bytes_rank = st["algorithmic_bytes"]
     barrier()
     t = torch.tensor([ms, float(nseg_rank), sweep_ms, alg_bytes_rank], dtype=torch.float64, device=dev)
+    rank_kernel_ms = [sweep_ms]
+    allreduce_ms = ar0.elapsed_time(ar1) if world > 1 else 0.0   # last step; includes waiting for the slowest rank
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms, nseg_total = float(tmax[0]), float(tsum[1])
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_kernel_ms = [float(x[2]) for x in allt]
     else:
         nseg_total = float(nseg_rank)
     ms_per_step = ms / args.steps
@@ -471,6 +480,9 @@ def main():
                          "peak_source": peak_src,
                          "kernel": "rtb::sweep_cell_kernel", "launches_per_step": int(sweep_launches),
                          "algorithmic_bytes_per_step_this_rank": alg_bytes_rank, "kernel_ms_per_step": sweep_ms,
+                         "kernel_ms_per_step_all_ranks": rank_kernel_ms,
+                         "allreduce_ms_rank0_last_step": allreduce_ms,
+                         "allreduce_bytes": 3 * N * 8 if world > 1 else 0,
                          "note": "72 B per leaf per direction; zones are swept with their directions fused, so DRAM "
                                  "traffic differs from the algorithmic bytes (see profiles/)"},
         }

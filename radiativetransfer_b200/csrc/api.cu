@@ -36,6 +36,7 @@ static void free_grid(Context& c) {
   cudaFree(c.dLevel); cudaFree(c.dHI); cudaFree(c.dHeI); cudaFree(c.dHeII); cudaFree(c.dRho); cudaFree(c.dAbun2);
   cudaFree(c.dKappa); cudaFree(c.tree.child); cudaFree(c.tree.leafX); cudaFree(c.tree.leafY); cudaFree(c.tree.leafZ);
   cudaFree(c.dJ); cudaFree(c.dRates); c.dRates = nullptr;
+  cudaFree(c.dKappaT); c.dKappaT = nullptr; c.kappaTBytes = 0;
   c.dLevel = nullptr; c.dHI = c.dHeI = c.dHeII = c.dRho = c.dAbun2 = c.dKappa = c.dJ = nullptr;
   c.tree = DevTree();
   c.uniPlanKey.clear();
@@ -260,6 +261,7 @@ int rtb200_set_tuning(rtb200_ctx* h, const char* key, double value) {
   else if (k == "graph") c.tune.useGraph = (int)value;
   else if (k == "l2_mb") c.tune.l2BudgetMB = value;
   else if (k == "march") c.tune.march = (int)value;
+  else if (k == "transpose_z") c.tune.transposeZ = (int)value;
   else if (k == "dirs_per_task") c.tune.dirsPerTask = (int)value;
   else if (k == "march_debug") c.tune.marchDebug = (int)value;
   else if (k == "portable_math") c.tune.portableMath = (int)value;

@@ -17,6 +17,7 @@
 //  * Zones run in `slots` concurrent lanes (gridDim.z); each slot owns a private J accumulator, so no atomics and a
 //    fixed summation order.  A final kernel sums the slot accumulators into J.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 
@@ -60,6 +61,7 @@ struct StepParams {
   const double* planeIn;   // this task's planes of the previous layer  [ndir][3][n+1][n+1] (padded, see below)
   double* planeOut;
   double* acc;             // slot accumulator [3][N]
+  const double* kappa;     // [3][N] in the layout the task's strides refer to (leaf order or z-major)
   int32_t origin;          // leaf index of rotated (step, 0, 0)
   int32_t sj, sk;
   int32_t ndir, laneIsK, firstInSlot, n;
@@ -239,8 +241,9 @@ struct BatchParams {
 // difference.  That branch is warp-uniform (P.thin is a per-layer table entry) and kept out of line.
 template <bool FAITHFUL, int EXPV, int MINB>
 __global__ void __launch_bounds__(256, MINB)
-sweep_cell_kernel(const __grid_constant__ BatchParams bp, const double* __restrict__ kappa, int N) {
+sweep_cell_kernel(const __grid_constant__ BatchParams bp, int N) {
   const StepParams& sp = bp.t[blockIdx.z];
+  const double* __restrict__ kappa = sp.kappa;
   __shared__ double sT[16];
   if (threadIdx.y == 0 && threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
   __syncthreads();
@@ -489,6 +492,53 @@ sweep_march_kernel(const __grid_constant__ MarchBatch mb, const double* __restri
   }
 }
 
+// z-major layout.  A zone whose sweep axis is the contiguous (z) axis of the leaf order has its lanes run along y:
+// every lane of a kappa load or accumulator store would touch its own 32-byte sector (measured: those 8 zones take 1.7x
+// the time of the others).  Such tasks read a z-major copy of kappa, index (z*n + x)*n + y, and write their accumulator
+// in the same layout, so that lanes are contiguous again; the final merge transposes those slots back through a
+// shared-memory tile.
+__global__ void transpose_kappa_kernel(const double* __restrict__ kap, double* __restrict__ kapT, int n) {
+  __shared__ double tile[32][33];
+  const int x = blockIdx.z % n, g = blockIdx.z / n;
+  const int64_t N = (int64_t)n * n * n;
+  const int z0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {   // read leaf order: z contiguous
+    const int y = y0 + r, z = z0 + threadIdx.x;
+    if (y < n && z < n) tile[r][threadIdx.x] = kap[g * N + ((int64_t)x * n + y) * n + z];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {   // write z-major: y contiguous
+    const int z = z0 + r, y = y0 + threadIdx.x;
+    if (y < n && z < n) kapT[g * N + ((int64_t)z * n + x) * n + y] = tile[threadIdx.x][r];
+  }
+}
+
+// J += sum of the z-major slots [first, first + count), transposed back to leaf order
+__global__ void merge_transposed_kernel(const double* __restrict__ acc, int first, int count, int n,
+                                        double* __restrict__ J) {
+  __shared__ double tile[32][33];
+  const int x = blockIdx.z % n, g = blockIdx.z / n;
+  const int64_t N = (int64_t)n * n * n, total = 3 * N;
+  const int z0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int z = z0 + r, y = y0 + threadIdx.x;
+    if (y < n && z < n) {
+      const int64_t i = g * N + ((int64_t)z * n + x) * n + y;
+      double s = acc[(int64_t)first * total + i];
+      for (int k = 1; k < count; k++) s = __dadd_rn(s, acc[(int64_t)(first + k) * total + i]);
+      tile[r][threadIdx.x] = s;
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int y = y0 + r, z = z0 + threadIdx.x;
+    if (y < n && z < n) {
+      double* p = J + g * N + ((int64_t)x * n + y) * n + z;
+      *p = __dadd_rn(*p, tile[threadIdx.x][r]);
+    }
+  }
+}
+
 // sum of the slot accumulators -> J (fixed order: slot 0, 1, ...)
 __global__ void merge_slots_kernel(const double* __restrict__ acc, int nslots, int64_t total, double* __restrict__ J) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -590,15 +640,14 @@ static int march_capacity(Context& c, size_t smemBytes, int* blocks) {
   return RTB200_OK;
 }
 
-static void launch_cells(int dense, int expv, bool faithful, dim3 grid, cudaStream_t s, const BatchParams& bp,
-                         const double* kappa, int N) {
+static void launch_cells(int dense, int expv, bool faithful, dim3 grid, cudaStream_t s, const BatchParams& bp, int N) {
   dim3 block(32, 8);
   // `dense`: 0 = compiler's choice of registers (2 blocks per SM), 1 = cap for 3 blocks, 2 = cap for 4 blocks
-  if (faithful) { sweep_cell_kernel<true, 0, 2><<<grid, block, 0, s>>>(bp, kappa, N); return; }
+  if (faithful) { sweep_cell_kernel<true, 0, 2><<<grid, block, 0, s>>>(bp, N); return; }
 #define RTB_LAUNCH(E)                                                                       \
-  if (dense == 1) sweep_cell_kernel<false, E, 3><<<grid, block, 0, s>>>(bp, kappa, N);      \
-  else if (dense >= 2) sweep_cell_kernel<false, E, 4><<<grid, block, 0, s>>>(bp, kappa, N); \
-  else sweep_cell_kernel<false, E, 2><<<grid, block, 0, s>>>(bp, kappa, N)
+  if (dense == 1) sweep_cell_kernel<false, E, 3><<<grid, block, 0, s>>>(bp, N);      \
+  else if (dense >= 2) sweep_cell_kernel<false, E, 4><<<grid, block, 0, s>>>(bp, N); \
+  else sweep_cell_kernel<false, E, 2><<<grid, block, 0, s>>>(bp, N)
   if (expv == 1) { RTB_LAUNCH(1); } else { RTB_LAUNCH(0); }
 #undef RTB_LAUNCH
 }
@@ -696,7 +745,8 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
   std::string planKey;
   {
     char buf[128];
-    snprintf(buf, sizeof(buf), "%d:%a:%d:%d:%d:%d:", n, c.boxSize, nAngularLevel, c.tune.slots, c.tune.lockstep, c.tune.dirsPerTask);
+    snprintf(buf, sizeof(buf), "%d:%a:%d:%d:%d:%d:%d:%d:", n, c.boxSize, nAngularLevel, c.tune.slots, c.tune.lockstep, c.tune.dirsPerTask,
+             c.tune.transposeZ, c.tune.march);
     planKey = buf;
     for (const auto& d : dirs) { snprintf(buf, sizeof(buf), "%lld,", (long long)d.iray); planKey += buf; }
   }
@@ -705,12 +755,36 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
     std::vector<RayPattern> pat;
     int64_t nseg = 0;
     int planeCursor = 0;
+    // Directions per task.  Every task contributes (n/31)*(n/8) blocks per layer launch whatever its direction
+    // count, so a shard with few zones (multi-GPU runs) fills the device better when its zones are cut into smaller
+    // pieces: pick the piece size that minimises (waves of resident blocks) x (block time ~ directions + fixed part).
+    int dpt = std::max(1, std::min(c.tune.dirsPerTask > 0 ? c.tune.dirsPerTask : kMaxDirPerTask, kMaxDirPerTask));
+    if (c.tune.dirsPerTask <= 0 && !c.tune.march) {
+      int perZone[25] = {0};
+      for (int d = 0; d < ndir; d++) perZone[dirs[d].izone]++;
+      const int64_t bpt = (int64_t)((n + 30) / 31) * ((n + 7) / 8);
+      const int64_t cap = (int64_t)c.smCount * (c.tune.minBlocks >= 2 ? 4 : (c.tune.minBlocks == 1 ? 3 : 2));
+      double best = 1e300;
+      for (int d = kMaxDirPerTask; d >= 2; d--) {
+        int64_t T = 0;
+        int maxPiece = 0;
+        for (int z = 1; z <= 24; z++)
+          if (perZone[z]) {
+            const int pieces = (perZone[z] + d - 1) / d;
+            T += pieces;
+            maxPiece = std::max(maxPiece, (perZone[z] + pieces - 1) / pieces);
+          }
+        if (T == 0 || T > kMaxBatch) continue;
+        const double waves = std::ceil((double)(T * bpt) / (double)cap);
+        const double cost = waves * (maxPiece + 1.5);
+        if (cost < best * 0.97) { best = cost; dpt = d; }   // prefer larger pieces unless clearly better
+      }
+    }
     for (int z = 1; z <= 24; z++) {
       std::vector<int> mine;
       for (int d = 0; d < ndir; d++)
         if (dirs[d].izone == z) mine.push_back(d);
       if (mine.empty()) continue;
-      const int dpt = std::max(1, std::min(c.tune.dirsPerTask > 0 ? c.tune.dirsPerTask : kMaxDirPerTask, kMaxDirPerTask));
       const int pieces = ((int)mine.size() + dpt - 1) / dpt;
       size_t o = 0;
       for (int pc = 0; pc < pieces; pc++) {
@@ -718,6 +792,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
         UniTaskHost T;
         ZoneStrides zs = zone_strides(z, n);
         T.origin = zs.origin; T.si = zs.stride[0]; T.sj = zs.stride[1]; T.sk = zs.stride[2];
+        T.izone = z;
         T.ndir = (int)cnt;
         T.planeFirst = planeCursor;
         planeCursor += T.ndir;
@@ -760,6 +835,27 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
         c.uniTasks[t].slot = best;
         load[best] += c.uniTasks[t].ndir;
       }
+    }
+    c.uniStdSlots = slots;
+    if (c.tune.transposeZ && c.tune.lockstep && !c.tune.march && ntask <= slots && n >= 32) {
+      // every task owns its slot: tasks sweeping along the contiguous axis switch to the z-major layout (see
+      // transpose_kappa_kernel) and are moved behind the others so that their slots form one range
+      std::stable_partition(c.uniTasks.begin(), c.uniTasks.end(), [](const UniTaskHost& T) { return T.si != 1 && T.si != -1; });
+      int nStd = 0;
+      for (int t = 0; t < ntask; t++) {
+        UniTaskHost& T = c.uniTasks[t];
+        T.slot = t;
+        if (T.si != 1 && T.si != -1) { nStd++; continue; }
+        const int64_t physT[3] = {n, 1, (int64_t)n * n};
+        ZoneStrides zs = zone_strides_layout(T.izone, n, physT);
+        T.origin = zs.origin; T.si = zs.stride[0]; T.sj = zs.stride[1]; T.sk = zs.stride[2];
+        const int64_t aj = T.sj < 0 ? -T.sj : T.sj, ak = T.sk < 0 ? -T.sk : T.sk;
+        T.laneIsK = ak <= aj;
+        T.transposed = 1;
+      }
+      c.uniStdSlots = nStd;
+      if (nStd < ntask)
+        if (int st = ensure_buffer((void**)&c.dKappaT, &c.kappaTBytes, (size_t)3 * N * sizeof(double))) return st;
     }
     for (int t = 0; t < ntask; t++) {  // first task of a slot (in issue order) overwrites the accumulator
       c.uniTasks[t].firstInSlot = !seen[c.uniTasks[t].slot];
@@ -808,6 +904,10 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
   // slot's J accumulator.  Each slot is an independent stream (a parallel branch of the captured graph), so the
   // hardware block scheduler balances the zones and there is no device-wide barrier between layers.
   auto issue = [&](cudaStream_t st) -> int {
+    if (c.uniStdSlots < (int)c.uniTasks.size() && c.uniStdSlots < c.uniSlots) {
+      dim3 tg((n + 31) / 32, (n + 31) / 32, 3 * n);
+      transpose_kappa_kernel<<<tg, dim3(32, 8), 0, st>>>(c.dKappa, c.dKappaT, n);
+    }
     {  // both plane buffers start as "boundary intensity everywhere": first-layer input and the permanent pads
       const int64_t total = (int64_t)2 * ndir * 3 * npl;
       int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)c.smCount * 16);
@@ -816,6 +916,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
     // fill one task's parameters for one layer
     auto fill = [&](StepParams& sp, const UniTaskHost& T, int step, int first) -> int {
       sp.acc = c.dAcc + (size_t)T.slot * 3 * N;
+      sp.kappa = T.transposed ? c.dKappaT : c.dKappa;
       sp.sj = (int32_t)T.sj; sp.sk = (int32_t)T.sk;
       sp.laneIsK = T.laneIsK; sp.n = n;
       sp.planeIn = ((step & 1) ? planeA : planeB) + (size_t)T.planeFirst * 3 * npl;
@@ -838,7 +939,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
           }
           dim3 gz = grid;
           gz.z = nb;
-          launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, gz, st, bp, c.dKappa, (int)N);
+          launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, gz, st, bp, (int)N);
           nLaunched++;
         }
       }
@@ -853,7 +954,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
         if (T.slot != k) continue;
         for (int step = 0; step < n; step++) {
           fill(bp.t[0], T, step, T.firstInSlot);
-          launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, grid, cs, bp, c.dKappa, (int)N);
+          launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, grid, cs, bp, (int)N);
           nLaunched++;
         }
       }
@@ -890,8 +991,14 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
   }
   RTB_CUDA(cudaEventRecord(c.evSweep1, s));
   {
+    const int nStd = std::min(c.uniStdSlots, slots);
     int blocks = std::min<int64_t>((3 * N + 255) / 256, (int64_t)c.smCount * 16);
-    merge_slots_kernel<<<blocks, 256, 0, s>>>(c.dAcc, slots, 3 * N, dJout);
+    if (nStd > 0) merge_slots_kernel<<<blocks, 256, 0, s>>>(c.dAcc, nStd, 3 * N, dJout);
+    else RTB_CUDA(cudaMemsetAsync(dJout, 0, 3 * N * sizeof(double), s));
+    if (nStd < slots) {
+      dim3 tg((n + 31) / 32, (n + 31) / 32, 3 * n);
+      merge_transposed_kernel<<<tg, dim3(32, 8), 0, s>>>(c.dAcc, nStd, slots - nStd, n, dJout);
+    }
   }
   RTB_CUDA(cudaGetLastError());
   if (nLaunched > 1) c.uniLaunches = nLaunched;  // a replayed graph issues what was captured

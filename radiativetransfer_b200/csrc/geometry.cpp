@@ -31,8 +31,12 @@ ZoneMap zone_map(int izone) {
 }
 
 ZoneStrides zone_strides(int izone, int n) {
-  ZoneMap m = zone_map(izone);
   const int64_t phys[3] = {(int64_t)n * n, n, 1};
+  return zone_strides_layout(izone, n, phys);
+}
+
+ZoneStrides zone_strides_layout(int izone, int n, const int64_t phys[3]) {
+  ZoneMap m = zone_map(izone);
   ZoneStrides s;
   s.origin = 0;
   for (int c = 0; c < 3; c++) {

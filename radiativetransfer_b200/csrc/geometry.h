@@ -30,6 +30,8 @@ struct ZoneStrides {
   int64_t stride[3];  // per unit step of rotated i, j, k
 };
 ZoneStrides zone_strides(int izone, int n);
+// same for an array laid out with element strides phys[0..2] along the physical x, y, z axes
+ZoneStrides zone_strides_layout(int izone, int n, const int64_t phys[3]);
 
 struct Direction {
   int64_t iray;

@@ -51,10 +51,12 @@ constexpr int kMaxDirPerTask = 8;
 struct UniTaskHost {
   int64_t origin = 0, si = 0, sj = 0, sk = 0;  // leaf index = origin + i*si + j*sj + k*sk (0-based rotated indices)
   int ndir = 0;
+  int izone = 0;
   int laneIsK = 1;       // 1: threadIdx.x runs along rotated k, 0: along rotated j
   int slot = 0;          // J accumulator / stream this task uses
   int firstInSlot = 0;   // 1: overwrite the accumulator instead of adding
   int planeFirst = 0;    // index of the task's first direction in the plane buffers
+  int transposed = 0;    // 1: this task reads kappa / writes its accumulator in the z-major layout (see diffuse_uniform.cu)
   std::vector<LayerSeg> seg;  // [n layers][kMaxDirPerTask]
 };
 
@@ -68,6 +70,7 @@ struct Tuning {
   int expVariant = 1;    // exp(-tau) of the fast path: 0 = polynomial, 1 = 16-entry shared-memory table
   double l2BudgetMB = 96.0;
   int march = 0;         // uniform sweep: 1 = persistent layer-marching kernel (experimental, slower: DESIGN.md)
+  int transposeZ = 1;    // uniform sweep: zones sweeping along the contiguous axis use a z-major copy of kappa / J
   int dirsPerTask = 0;   // directions of one zone swept together (0 = kMaxDirPerTask)
   int marchDebug = 0;    // experiments only: 1 = skip the neighbour polling (wrong results), 2 = spin without nanosleep
   int portableMath = 1;  // point path, FAITHFUL mode: exp/log from portable_math.h (bit-identical on host and device)
@@ -122,6 +125,9 @@ struct Context {
   int8_t* dLevel = nullptr;
   double *dHI = nullptr, *dHeI = nullptr, *dHeII = nullptr, *dRho = nullptr, *dAbun2 = nullptr;
   double* dKappa = nullptr;  // [3][nleaf]
+  double* dKappaT = nullptr; // [3][nleaf] z-major copy (index (z*n + x)*n + y) for the uniform sweep, lazily allocated
+  size_t kappaTBytes = 0;
+  int uniStdSlots = 0;       // slots [0, uniStdSlots) are in leaf order, the rest z-major
   DevTree tree;
   std::vector<int32_t> hChild;               // host copy of the linear octree
   std::vector<int32_t> hLeafX, hLeafY, hLeafZ;
