@@ -62,3 +62,51 @@ def test_sharded_sum_equals_single_rank(world, oracle, uvbg):
     full = og.diffuse(uvbg["uvb"], uvbg["beta"])
     assert nseg == full["nseg"]
     assert np.allclose(J, full["J"], rtol=1e-13, atol=0)
+
+
+def _point_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    from oracle import ftte_oracle as fo
+    from radiativetransfer_b200 import workloads as W
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g, src = W.point_workload(8, 5, uniform=True)
+    wt = np.arange(1, src.size + 1, dtype=np.int32)
+    sp = W.synthetic_spectra()
+    og = fo.OracleGrid(8, g["level"], g["HI"], g["HeI"], g["HeII"], g["rho"], g["abun2"], g["box_size"])
+    mine = slice(rank, None, world)                     # the round-robin source sharding of bench.py
+    o = og.point(sp, src[mine], wt[mine])
+    assert o["status"] == 0
+    R = torch.from_numpy(o["rates"].copy())
+    nseg = torch.tensor([o["nseg"]], dtype=torch.int64)
+    dist.all_reduce(R)
+    dist.all_reduce(nseg)
+    if rank == 0:
+        q.put((R.numpy(), int(nseg[0])))
+    dist.destroy_process_group()
+
+
+def test_point_sources_sharded_over_ranks(oracle):
+    """sources are independent: per-rank rate fields add up to the single-rank result (all-reduce of 6 fields)"""
+    import torch.multiprocessing as mp
+    from radiativetransfer_b200 import workloads as W
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_point_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    R, nseg = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g, src = W.point_workload(8, 5, uniform=True)
+    wt = np.arange(1, src.size + 1, dtype=np.int32)
+    og = oracle.OracleGrid(8, g["level"], g["HI"], g["HeI"], g["HeII"], g["rho"], g["abun2"], g["box_size"])
+    full = og.point(W.synthetic_spectra(), src, wt)
+    assert nseg == full["nseg"]
+    assert np.allclose(R, full["rates"], rtol=1e-12, atol=0)

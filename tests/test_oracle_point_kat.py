@@ -205,3 +205,44 @@ def test_rates_accumulate_over_sources(oracle, spectra):
     assert ab["nseg"] == a["nseg"] + b["nseg"]
     z = og.point(spectra, [100], [0])
     assert z["nseg"] == 0 and np.all(z["rates"] == 0)
+
+
+def test_golden_fixtures_reproduce(oracle, spectra):
+    """the committed point-source fixtures (tests/golden/make_golden.py) are what the oracle computes today"""
+    import os
+    from conftest import ROOT
+    f = np.load(os.path.join(ROOT, "tests", "golden", "point_uniform_10.npz"))
+    g = W.uniform_grid(10, seed=int(f["seed"]), tau_lo=1e-2, tau_hi=1.0, beta24=float(np.float32(6.3e-18)))
+    g["abun2"] = f["abun2"]
+    o = _grid(oracle, g).point(spectra, f["src"], f["wt"], dust_approximation=int(f["dust"]))
+    assert o["status"] == 0 and o["nseg"] == int(f["nseg"])
+    assert np.allclose(o["rates"], f["rates"], rtol=1e-12, atol=0)
+    assert np.allclose(o["ndot_remaining"], f["ndot_remaining"], rtol=1e-12, atol=0)
+    f = np.load(os.path.join(ROOT, "tests", "golden", "point_amr_6.npz"))
+    g = W.nested_grid(6, 2, W.central_box_refine(0.2, 0.8, levels=2), seed=int(f["seed"]), tau_lo=1e-2, tau_hi=0.5,
+                      beta24=float(np.float32(6.3e-18)))
+    assert np.array_equal(g["level"], f["level"])
+    o = _grid(oracle, g).point(spectra, f["src"], f["wt"], trace_cap=2000000)
+    assert o["status"] == 0 and np.array_equal(o["trace"], f["trace"])   # traversal is integer work: bit-exact
+    assert np.allclose(o["rates"], f["rates"], rtol=1e-12, atol=0)
+
+
+def test_portable_math_switch(oracle, spectra):
+    """exp/log from csrc/portable_math.h (what the CUDA kernels use in FAITHFUL mode) instead of libm: the traversal is
+    unchanged and the rates move only by the conditioning of R(d) - R(d + tau)"""
+    n = 10
+    g = W.uniform_grid(n, seed=31, tau_lo=1e-2, tau_hi=1.0, beta24=float(np.float32(6.3e-18)))
+    og = _grid(oracle, g)
+    a = og.point(spectra, [444], [1], trace_cap=100000)
+    oracle.set_portable_math(True)
+    try:
+        b = og.point(spectra, [444], [1], trace_cap=100000)
+        t = oracle.point_tables(spectra, 2, 0.5)
+    finally:
+        oracle.set_portable_math(False)
+    t0 = oracle.point_tables(spectra, 2, 0.5)
+    assert np.array_equal(a["trace"], b["trace"])
+    assert np.max(np.abs(t["tables"] - t0["tables"]) / t0["tables"]) < 1e-13
+    m = a["rates"][0] != 0
+    assert np.max(np.abs(a["rates"][0][m] - b["rates"][0][m]) / a["rates"][0][m]) < 1e-9
+    assert np.allclose(a["rates"].sum(axis=1), b["rates"].sum(axis=1), rtol=1e-12, atol=0)

@@ -205,3 +205,33 @@ def test_photon_conservation_256_scale_properties(engine, spectra):
     assert np.all(r["rates"] == 0)
     tot = r["ndot_remaining"][0] + r["ndot_boundary"][0]
     assert np.all(tot <= 5 * (1 + 1e-12)) and np.all(tot > 4.8)
+
+
+def test_golden_fixtures(rt, engine, spectra):
+    """committed oracle outputs (tests/golden/, libm oracle): rates within 1e-9 relative plus the conditioning floor,
+    diagnostics within 1e-11, traversal bit-exact"""
+    import os
+    from conftest import ROOT
+    f = np.load(os.path.join(ROOT, "tests", "golden", "point_uniform_10.npz"))
+    g = W.uniform_grid(10, seed=int(f["seed"]), tau_lo=1e-2, tau_hi=1.0, beta24=S24)
+    g["abun2"] = f["abun2"]
+    _set(engine, g)
+    for mode in (rt.MATH_FAITHFUL, rt.MATH_FAST):
+        engine.set_math(mode)
+        r = engine.point(spectra, f["src"], f["wt"], dust_approximation=int(f["dust"]))
+        assert r["nseg"] == int(f["nseg"])
+        scale = np.abs(f["rates"]).max(axis=1, keepdims=True)     # ~ weight * R_r(0)
+        assert np.all(np.abs(r["rates"] - f["rates"]) <= TOL * np.abs(f["rates"]) + 2e-13 * scale)
+        assert rel_err(r["ndot_remaining"], f["ndot_remaining"], floor=1e-300) < 1e-11
+        assert rel_err(r["ndot_dust"], f["ndot_dust"], floor=1e-300) < 1e-11
+        assert np.array_equal(r["ndot_boundary"], f["ndot_boundary"])
+    f = np.load(os.path.join(ROOT, "tests", "golden", "point_amr_6.npz"))
+    g = W.nested_grid(6, 2, W.central_box_refine(0.2, 0.8, levels=2), seed=int(f["seed"]), tau_lo=1e-2, tau_hi=0.5,
+                      beta24=S24)
+    _set(engine, g)
+    engine.set_math(rt.MATH_FAITHFUL)
+    r = engine.point(spectra, f["src"], f["wt"], trace_cap=400000)
+    assert r["nseg"] == int(f["nseg"])
+    # the oracle traces source by source, depth first; the device sorts by (source, pixel level, pixel, segment)
+    tr, n0 = f["trace"], int(f["nseg_source0"])
+    assert np.array_equal(r["trace"], np.concatenate([_by_ray(tr[:n0]), _by_ray(tr[n0:])]))
