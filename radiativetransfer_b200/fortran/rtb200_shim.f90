@@ -15,6 +15,9 @@ module rtb200_shim
   real(c_double), dimension(:), allocatable, target, save :: flatHI, flatHeI, flatHeII, flatRho, flatAbun2, &
        flatJ1, flatJ2, flatJ3
   integer(c_int64_t), save :: icursor
+  ! point sources: six rate fields, leaf number of the first leaf of every base cell
+  real(c_double), dimension(:), allocatable, target, save :: flatK24, flatK25, flatK26, flatC24, flatC25, flatC26
+  integer(c_int64_t), dimension(:,:,:), allocatable, save :: baseFirstLeaf
 
   interface
      integer(c_int) function rtb200_create(device, ctx) bind(C, name='rtb200_create')
@@ -48,6 +51,20 @@ module rtb200_shim
        integer(c_int32_t), value :: nrays
        type(c_ptr), value :: J1, J2, J3, nseg
      end function rtb200_diffuse
+     integer(c_int) function rtb200_point(ctx, nWave, wavelength, lum, metallicity, coefSpectrum, aDust, &
+          dustApproximation, maxPixelLevel, nsrc, srcLeaf, srcWeight, k24, k25, k26, c24, c25, c26, &
+          ndotRemaining, ndotBoundary, ndotDust, ndotSpectrum, nseg) bind(C, name='rtb200_point')
+       import :: c_int, c_int32_t, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: nWave
+       type(c_ptr), value :: wavelength, lum, metallicity
+       real(c_double), value :: coefSpectrum
+       type(c_ptr), value :: aDust
+       integer(c_int), value :: dustApproximation, maxPixelLevel
+       integer(c_int32_t), value :: nsrc
+       type(c_ptr), value :: srcLeaf, srcWeight, k24, k25, k26, c24, c25, c26
+       type(c_ptr), value :: ndotRemaining, ndotBoundary, ndotDust, ndotSpectrum, nseg
+     end function rtb200_point
   end interface
 
 contains
@@ -189,5 +206,154 @@ contains
        enddo
     enddo
   end subroutine rtbDiffuse
+
+  ! ---- point sources ---------------------------------------------------------------------------------------
+
+  recursive subroutine scatterRates(currentCell)
+    type(zoneType) :: currentCell
+    integer :: i, j, k
+    if (currentCell%refined) then
+       do i = 1, 2
+          do j = 1, 2
+             do k = 1, 2
+                call scatterRates(currentCell%cell(i,j,k))
+             enddo
+          enddo
+       enddo
+    else
+       icursor = icursor + 1
+       currentCell%krate24 = flatK24(icursor)
+       currentCell%krate25 = flatK25(icursor)
+       currentCell%krate26 = flatK26(icursor)
+       currentCell%crate24 = flatC24(icursor)
+       currentCell%crate25 = flatC25(icursor)
+       currentCell%crate26 = flatC26(icursor)
+    endif
+  end subroutine scatterRates
+
+  ! leaf number (0-based, writeCell order) of a star's host cell from its call sequence star%position
+  ! (equiSources.f90:753-756): leaves of the preceding base cells + leaves of the preceding siblings on every level
+  function rtbLeafOfStar(currentStar) result(leaf)
+    type(starType), intent(in) :: currentStar
+    integer(c_int64_t) :: leaf, n
+    type(zoneType), pointer :: cell
+    integer :: l, i, j, k, ii, jj, kk
+    i = currentStar%position(1); j = currentStar%position(2); k = currentStar%position(3)
+    leaf = baseFirstLeaf(i,j,k)
+    cell => baseGrid%cell(i,j,k)
+    do l = 1, currentStar%level
+       i = currentStar%position(3*l+1); j = currentStar%position(3*l+2); k = currentStar%position(3*l+3)
+       do ii = 1, 2
+          do jj = 1, 2
+             do kk = 1, 2
+                if ((ii-1)*4+(jj-1)*2+kk-1 .lt. (i-1)*4+(j-1)*2+k-1) then
+                   n = 0
+                   call countLeaves(cell%cell(ii,jj,kk), n)
+                   leaf = leaf + n
+                endif
+             enddo
+          enddo
+       enddo
+       cell => cell%cell(i,j,k)
+    enddo
+  end function rtbLeafOfStar
+
+  ! replaces equiSources.f90:1256-1370 (runStellarTransfer block): all sources with weight > 0 in one call.
+  ! iSpectrum / coefSpectrum are the driver's locals computed at :1236-1242.
+  subroutine rtbPoint(nx, ny, nz, iSpectrum, coefSpectrum, maxPixelLevel, nStarsSpecificAge)
+    integer, intent(in) :: nx, ny, nz, iSpectrum, maxPixelLevel, nStarsSpecificAge
+    real(kind=RealKind), intent(in) :: coefSpectrum
+    integer :: i, j, k, iStar, nsrc, iradius, im
+    integer(c_int64_t) :: n
+    integer(c_int32_t), dimension(:), allocatable, target :: srcLeaf, srcWeight
+    real(c_double), dimension(:,:), allocatable, target :: remaining, boundary, spectrum   ! (7,nsrc), (7,nsrc), (300,nsrc)
+    real(c_double), dimension(:), allocatable, target :: dustEscape
+    real(c_double), dimension(nWavelengths,2,nMetallicity), target :: lumPack   ! = C [5][2][nWave]
+    real(c_double), dimension(5,7), target :: dustPack                         ! = C [7][5]
+    real(c_double), dimension(nWavelengths), target :: wl
+    real(c_double), dimension(nMetallicity), target :: met
+    real(kind=RealKind) :: ndot1, fraction(7)
+
+    if (.not.allocated(baseFirstLeaf)) then
+       allocate(baseFirstLeaf(nx,ny,nz))
+       allocate(flatK24(rtbLeaves), flatK25(rtbLeaves), flatK26(rtbLeaves), flatC24(rtbLeaves), flatC25(rtbLeaves), &
+            flatC26(rtbLeaves))
+       n = 0
+       do i = 1, nx
+          do j = 1, ny
+             do k = 1, nz
+                baseFirstLeaf(i,j,k) = n
+                call countLeaves(baseGrid%cell(i,j,k), n)
+             enddo
+          enddo
+       enddo
+    endif
+    nsrc = 0
+    do iStar = 1, nStars
+       if (star(iStar)%weight.gt.0) nsrc = nsrc + 1
+    enddo
+    allocate(srcLeaf(nsrc), srcWeight(nsrc), remaining(7,nsrc), boundary(7,nsrc), spectrum(300,nsrc), dustEscape(nsrc))
+    nsrc = 0
+    do iStar = 1, nStars
+       if (star(iStar)%weight.gt.0) then
+          nsrc = nsrc + 1
+          srcLeaf(nsrc) = int(rtbLeafOfStar(star(iStar)), c_int32_t)
+          srcWeight(nsrc) = star(iStar)%weight
+       endif
+    enddo
+    do im = 1, nMetallicity
+       lumPack(:,1,im) = specificLuminosity(im,iSpectrum,:)
+       lumPack(:,2,im) = specificLuminosity(im,iSpectrum+1,:)
+    enddo
+    dustPack = transpose(a_smc)
+    wl = wavelength
+    met = metallicity
+    ! absorber densities may have changed since rtbSetGrid (previous chemistry step)
+    icursor = 0
+    do i = 1, nx
+       do j = 1, ny
+          do k = 1, nz
+             call flattenCell(baseGrid%cell(i,j,k), 0)
+          enddo
+       enddo
+    enddo
+    call rtbCheck(rtb200_grid_update_species(rtbContext, c_loc(flatHI), c_loc(flatHeI), c_loc(flatHeII)), &
+         'rtb200_grid_update_species')
+    flatK24 = 0.; flatK25 = 0.; flatK26 = 0.; flatC24 = 0.; flatC25 = 0.; flatC26 = 0.   ! setZeroRates (:1246)
+    call rtbCheck(rtb200_point(rtbContext, int(nWavelengths, c_int), c_loc(wl), c_loc(lumPack), c_loc(met), &
+         real(coefSpectrum, c_double), c_loc(dustPack), int(dustApproximation, c_int), int(maxPixelLevel, c_int), &
+         int(nsrc, c_int32_t), c_loc(srcLeaf), c_loc(srcWeight), c_loc(flatK24), c_loc(flatK25), c_loc(flatK26), &
+         c_loc(flatC24), c_loc(flatC25), c_loc(flatC26), c_loc(remaining), c_loc(boundary), c_loc(dustEscape), &
+         c_loc(spectrum), c_null_ptr), 'rtb200_point')
+    icursor = 0
+    do i = 1, nx
+       do j = 1, ny
+          do k = 1, nz
+             call scatterRates(baseGrid%cell(i,j,k))
+          enddo
+       enddo
+    enddo
+    ! per-source escape fractions and the escaping spectrum (equiSources.f90:1342-1366)
+    cosmicSpectrum = 0.
+    nsrc = 0
+    do iStar = 1, nStars
+       if (star(iStar)%weight.gt.0) then
+          nsrc = nsrc + 1
+          ndot1 = float(star(iStar)%weight)
+          do iradius = 1, 7
+             if (boundary(iradius,nsrc).lt.1.) then
+                fraction(iradius) = remaining(iradius,nsrc)/(ndot1-boundary(iradius,nsrc))
+             else
+                fraction(iradius) = 0.
+             endif
+          enddo
+          cosmicSpectrum = cosmicSpectrum + float(star(iStar)%weight) * spectrum(:,nsrc)/(ndot1-boundary(7,nsrc))
+          write(*,1015) iStar, star(iStar)%level, fraction, star(iStar)%weight
+       endif
+    enddo
+1015 format('src: ', i5, i3, 7f9.5, i8)
+    cosmicSpectrum = cosmicSpectrum / float(nStarsSpecificAge)
+    deallocate(srcLeaf, srcWeight, remaining, boundary, spectrum, dustEscape)
+  end subroutine rtbPoint
 
 end module rtb200_shim
