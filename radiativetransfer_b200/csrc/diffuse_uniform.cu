@@ -58,7 +58,7 @@ int launch_compute_opacities(Context& c, const double* beta, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------------
 struct StepParams {
   LayerSeg P[kMaxDirPerTask];
-  const double* planeIn;   // this task's planes of the previous layer  [ndir][3][n+1][n+1] (padded, see below)
+  const double* planeIn;   // this task's planes of the previous layer  [ndir][n+1][n+1][3 groups] (padded, see below)
   double* planeOut;
   double* acc;             // slot accumulator [3][N]
   const double* kappa;     // [3][N] in the layout the task's strides refer to (leaf order or z-major)
@@ -74,7 +74,7 @@ struct StepParams {
 __global__ void fill_planes_kernel(double* __restrict__ planes, int64_t perGroup, int64_t total, double u0, double u1,
                                    double u2) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int g = (int)((i / perGroup) % 3);
+    int g = (int)(i % 3);  // the three frequency groups of a cell are adjacent: [direction][row][column][group]
     planes[i] = g == 0 ? u0 : (g == 1 ? u1 : u2);
   }
 }
@@ -241,13 +241,14 @@ struct BatchParams {
 // difference.  That branch is warp-uniform (P.thin is a per-layer table entry) and kept out of line.
 template <bool FAITHFUL, int EXPV, int MINB>
 __global__ void __launch_bounds__(256, MINB)
-sweep_cell_kernel(const __grid_constant__ BatchParams bp, int N) {
+sweep_cell_kernel(const __grid_constant__ BatchParams bp, int N, int n, int np1, int npl3) {
+  // n, np1 = n + 1 and npl3 = 3 (n+1)^2 are the same for every task: as top-level parameters they are constant-bank
+  // operands instead of values re-derived from the task table for every direction
   const StepParams& sp = bp.t[blockIdx.z];
   const double* __restrict__ kappa = sp.kappa;
   __shared__ double sT[16];
   if (threadIdx.y == 0 && threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
   __syncthreads();
-  const int n = sp.n;
   const int a = blockIdx.x * 31 - 1 + (int)threadIdx.x, b = blockIdx.y * 8 + threadIdx.y;
   if (b >= n) return;                                          // warp-uniform
   const bool inRow = a < n;                                    // lanes beyond the row only take part in the shuffles
@@ -256,8 +257,6 @@ sweep_cell_kernel(const __grid_constant__ BatchParams bp, int N) {
   const int laneIsK = sp.laneIsK;
   const int sA = laneIsK ? sp.sk : sp.sj, sB = laneIsK ? sp.sj : sp.sk;
   const int leaf = sp.origin + a * sA + b * sB;
-  const int np1 = n + 1;
-  const int npl = np1 * np1;                                   // doubles per padded plane
   double kap[3], kapF[3], kR[3];
 #pragma unroll
   for (int g = 0; g < 3; g++) {
@@ -269,9 +268,10 @@ sweep_cell_kernel(const __grid_constant__ BatchParams bp, int N) {
   double A[3] = {0., 0., 0.}, acc[3] = {0., 0., 0.};
   const int pidx = (b + 1) * np1 + (inRow ? a + 1 : 0);
   const int ndir = sp.ndir;
-  const int dstride = 3 * npl;                                 // one direction's planes (3 groups)
-  const double* pin = sp.planeIn + pidx;
-  double* pout = sp.planeOut + pidx;
+  const int dstride = npl3;                                    // one direction's plane (3 groups per cell)
+  const int up = 3 * np1;                                      // one row up
+  const double* pin = sp.planeIn + 3 * pidx;
+  double* pout = sp.planeOut + 3 * pidx;
   for (int q = 0; q < ndir; q++, pin += dstride, pout += dstride) {
     const LayerSeg& P = sp.P[q];
     const int kind = P.kind;
@@ -279,26 +279,23 @@ sweep_cell_kernel(const __grid_constant__ BatchParams bp, int N) {
     // register (at 64 registers per thread a register prefetch is spilled at once, and the spill store then waits
     // for the load -- 35% of all stall samples in the r01 profile).
     if (q + 1 < ndir) {
-#pragma unroll
-      for (int g = 0; g < 3; g++) {
-        prefetch_l1(pin + dstride + g * npl);
-        prefetch_l1(pin + dstride + g * npl - np1);
-      }
+      prefetch_l1(pin + dstride);
+      prefetch_l1(pin + dstride - up);
     }
     double cur[3], upR[3] = {0., 0., 0.}, I[3];
 #pragma unroll
-    for (int g = 0; g < 3; g++) cur[g] = pin[g * npl];
+    for (int g = 0; g < 3; g++) cur[g] = pin[g];
     // kinds 1,2: second segment fed from k-1, third (kind 2) from j-1; kinds 3,4 the other way round
     const bool secL = (kind <= 2) == (laneIsK != 0);
     if (kind == 2 || kind == 4 || (kind != 0 && !secL)) {
 #pragma unroll
-      for (int g = 0; g < 3; g++) upR[g] = pin[g * npl - np1];
+      for (int g = 0; g < 3; g++) upR[g] = pin[g - up];
     }
     if (FAITHFUL || P.thin) direction_dispatch_faithful(P, secL, cur, upR, kapF, kR, I, acc);
     else direction_dispatch_fast<EXPV>(P, secL, cur, upR, kap, kR, I, A, sT);
     if (writer) {
 #pragma unroll
-      for (int g = 0; g < 3; g++) pout[g * npl] = I[g];
+      for (int g = 0; g < 3; g++) pout[g] = I[g];
     }
   }
   if (writer) {
@@ -449,7 +446,7 @@ sweep_march_kernel(const __grid_constant__ MarchBatch mb, const double* __restri
         // the halo lane owns no cell: its input is the left neighbour tile's edge value
         if (halo && i > 0) {
 #pragma unroll
-          for (int g = 0; g < 3; g++) cur[g] = __ldcg(ringIn + (int64_t)(q * 3 + g) * npl + pidx);
+          for (int g = 0; g < 3; g++) cur[g] = __ldcg(ringIn + ((int64_t)q * npl + pidx) * 3 + g);
         } else {
 #pragma unroll
           for (int g = 0; g < 3; g++) cur[g] = xin[q * tileStride + g * 256 + tpos];
@@ -460,7 +457,7 @@ sweep_march_kernel(const __grid_constant__ MarchBatch mb, const double* __restri
             for (int g = 0; g < 3; g++) upR[g] = uvb[g];
           } else if (row == 0 || halo) {  // the cell above belongs to another tile (or is the pad row)
 #pragma unroll
-            for (int g = 0; g < 3; g++) upR[g] = __ldcg(ringIn + (int64_t)(q * 3 + g) * npl + pidx - np1);
+            for (int g = 0; g < 3; g++) upR[g] = __ldcg(ringIn + ((int64_t)q * npl + pidx - np1) * 3 + g);
           } else {
 #pragma unroll
             for (int g = 0; g < 3; g++) upR[g] = xin[q * tileStride + g * 256 + tpos - 32];
@@ -472,7 +469,7 @@ sweep_march_kernel(const __grid_constant__ MarchBatch mb, const double* __restri
         for (int g = 0; g < 3; g++) xout[q * tileStride + g * 256 + tpos] = writer ? I[g] : cur[g];
         if (pubCol || pubRow) {
 #pragma unroll
-          for (int g = 0; g < 3; g++) __stcg(ringOut + (int64_t)(q * 3 + g) * npl + pidx, I[g]);
+          for (int g = 0; g < 3; g++) __stcg(ringOut + ((int64_t)q * npl + pidx) * 3 + g, I[g]);
         }
       }
     }
@@ -640,14 +637,15 @@ static int march_capacity(Context& c, size_t smemBytes, int* blocks) {
   return RTB200_OK;
 }
 
-static void launch_cells(int dense, int expv, bool faithful, dim3 grid, cudaStream_t s, const BatchParams& bp, int N) {
+static void launch_cells(int dense, int expv, bool faithful, dim3 grid, cudaStream_t s, const BatchParams& bp, int N,
+                         int n) {
   dim3 block(32, 8);
   // `dense`: 0 = compiler's choice of registers (2 blocks per SM), 1 = cap for 3 blocks, 2 = cap for 4 blocks
-  if (faithful) { sweep_cell_kernel<true, 0, 2><<<grid, block, 0, s>>>(bp, N); return; }
+  if (faithful) { sweep_cell_kernel<true, 0, 2><<<grid, block, 0, s>>>(bp, N, n, n + 1, 3 * (n + 1) * (n + 1)); return; }
 #define RTB_LAUNCH(E)                                                                       \
-  if (dense == 1) sweep_cell_kernel<false, E, 3><<<grid, block, 0, s>>>(bp, N);      \
-  else if (dense >= 2) sweep_cell_kernel<false, E, 4><<<grid, block, 0, s>>>(bp, N); \
-  else sweep_cell_kernel<false, E, 2><<<grid, block, 0, s>>>(bp, N)
+  if (dense == 1) sweep_cell_kernel<false, E, 3><<<grid, block, 0, s>>>(bp, N, n, n + 1, 3 * (n + 1) * (n + 1));      \
+  else if (dense >= 2) sweep_cell_kernel<false, E, 4><<<grid, block, 0, s>>>(bp, N, n, n + 1, 3 * (n + 1) * (n + 1)); \
+  else sweep_cell_kernel<false, E, 2><<<grid, block, 0, s>>>(bp, N, n, n + 1, 3 * (n + 1) * (n + 1))
   if (expv == 1) { RTB_LAUNCH(1); } else { RTB_LAUNCH(0); }
 #undef RTB_LAUNCH
 }
@@ -939,7 +937,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
           }
           dim3 gz = grid;
           gz.z = nb;
-          launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, gz, st, bp, (int)N);
+          launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, gz, st, bp, (int)N, n);
           nLaunched++;
         }
       }
@@ -954,7 +952,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
         if (T.slot != k) continue;
         for (int step = 0; step < n; step++) {
           fill(bp.t[0], T, step, T.firstInSlot);
-          launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, grid, cs, bp, (int)N);
+          launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, grid, cs, bp, (int)N, n);
           nLaunched++;
         }
       }
