@@ -25,6 +25,8 @@
 #include <cmath>
 #include <cstdio>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "point_host.h"
 #include "portable_math.h"
 #include "rtb200_internal.h"
@@ -82,6 +84,12 @@ struct PointParams {
   RayState* stateOut;     // this level's    [nsrc][npix(level)]
   unsigned long long* nseg;
   int32_t* err;
+  // segmented (atomic-free) deposition: records instead of RED.ADD, see segmented_reduce_kernel
+  long long* recKey;      // [recCap] leaf << 32 | ray << 12 | segment
+  double* recVal;         // [6][recCap]
+  unsigned long long* recCount;
+  long long recCap;
+  int raysPerSource;      // pixels of levels 1..maxPixelLevel
   // optional traversal trace (parity checks)
   long long* trace;       // [cap][2]
   unsigned long long* traceLen;
@@ -283,7 +291,7 @@ __device__ __forceinline__ void rates_fast(const PointParams& P, const double* _
 }
 
 // --------------------------------------------------------------------------------------------------------------------
-template <bool FAITHFUL, bool PORTABLE, bool TRACE>
+template <bool FAITHFUL, bool PORTABLE, bool TRACE, bool SEGMENTED>
 __global__ void __launch_bounds__(128) point_march_kernel(const __grid_constant__ PointParams P, int pixelLevel) {
   const int64_t npix = 12LL << (2 * (pixelLevel - 1));
   const int64_t ipix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -520,9 +528,26 @@ __global__ void __launch_bounds__(128) point_march_kernel(const __grid_constant_
           rates_fast<2>(P, LT, q, d3, tau3, n, h); dep[1] = ndot * n; dep[4] = ndot * h;
         }
       }
+      if (SEGMENTED) {
+        // one record per segment; slots are handed out per warp (one counter update for the active lanes)
+        const unsigned m = __activemask();
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(P.recCount, (unsigned long long)__popc(m));
+        base = __shfl_sync(m, base, leader);
+        const long long slot = (long long)(base + __popc(m & ((1u << lane) - 1u)));
+        if (slot < P.recCap) {
+          const long long ray = (long long)s * P.raysPerSource + pix_offset(pixelLevel) + ipix;
+          const long long seg = mySegs - 1 < 4095 ? (long long)(mySegs - 1) : 4095;
+          P.recKey[slot] = ((long long)lf << 32) | ((ray & 0xFFFFF) << 12) | seg;
 #pragma unroll
-      for (int i = 0; i < 6; i++)
-        if (dep[i] != 0.) atomicAdd(P.rates + (size_t)i * P.nleaf + lf, dep[i]);
+          for (int i = 0; i < 6; i++) P.recVal[(size_t)i * P.recCap + slot] = dep[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+          if (dep[i] != 0.) atomicAdd(P.rates + (size_t)i * P.nleaf + lf, dep[i]);
+      }
 
       d1 = A(d1, tau1); d2 = A(d2, tau2); d3 = A(d3, tau3); dD = A(dD, tauD);
     }
@@ -584,6 +609,34 @@ __global__ void __launch_bounds__(128) point_table_kernel(const __grid_constant_
     T.logTab[oR] = PORTABLE ? rtb_pm::pm_log(R[r]) : log(R[r]);
     T.logTab[oE] = PORTABLE ? rtb_pm::pm_log(E[r]) : log(E[r]);
     if (T.rawTab) { T.rawTab[oR] = R[r]; T.rawTab[oE] = E[r]; }
+  }
+}
+
+// Segmented, atomic-free deposition.  The march kernel emits one (leaf, 6 deposits) record per segment; the records'
+// 64-bit keys (leaf, ray, segment index) are radix-sorted (cub), which makes the order of the additions to a cell a
+// function of the rays alone, and one thread per run of equal leaves adds the run up and updates the cell once.
+__global__ void iota_kernel(uint32_t* idx, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    idx[i] = (uint32_t)i;
+}
+
+__global__ void segmented_reduce_kernel(const long long* __restrict__ key, const uint32_t* __restrict__ idx,
+                                        const double* __restrict__ val, long long n, long long cap,
+                                        double* __restrict__ rates, int64_t nleaf) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int leaf = (int)(key[i] >> 32);
+    if (i > 0 && (int)(key[i - 1] >> 32) == leaf) continue;  // not the head of its run
+    double sum[6] = {0., 0., 0., 0., 0., 0.};
+    for (long long j = i; j < n && (int)(key[j] >> 32) == leaf; j++) {
+      const uint32_t r = idx[j];
+#pragma unroll
+      for (int f = 0; f < 6; f++) sum[f] = __dadd_rn(sum[f], val[(size_t)f * cap + r]);
+    }
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+      double* p = rates + (size_t)f * nleaf + leaf;
+      *p = __dadd_rn(*p, sum[f]);
+    }
   }
 }
 
@@ -704,6 +757,9 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
   int batch = (int)std::min<size_t>((size_t)nsrc, std::max<size_t>(1, (freeB / 2) / perSrc));
   batch = std::min(batch, 16384);
   if (c.tune.pointBatch > 0) batch = std::min(batch, c.tune.pointBatch);
+  const int raysPerSource = (int)(4 * ((1LL << (2 * in.maxPixelLevel)) - 1));
+  // segmented deposition: 20-bit ray index in the sort key; 16 sources per batch keep the record buffers at a few GB
+  if (c.tune.pointDeposit == 1) batch = std::max(1, std::min(std::min(batch, 16), (1 << 20) / raysPerSource));
   double *dDtmp, *dLogTab, *dRaw = nullptr, *dDiag;
   RayState *dStA, *dStB;
   if (int st = sc.get(&dDtmp, (size_t)batch * kNfreq)) return st;
@@ -714,6 +770,35 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
   if (int st = sc.get(&dStB, (size_t)batch * npixMax)) return st;
   long long* dTrace = nullptr;
   if (hTrace && traceCap > 0) { if (int st = sc.get(&dTrace, (size_t)traceCap * 2)) return st; }
+  // segmented deposition: record buffers sized from the free memory (76 B per record incl. the sort's double buffers)
+  const bool segmented = c.tune.pointDeposit == 1 && !dTrace;
+  long long recCap = 0;
+  long long *dRecKey = nullptr, *dRecKeyOut = nullptr;
+  uint32_t *dRecIdx = nullptr, *dRecIdxOut = nullptr;
+  double* dRecVal = nullptr;
+  void* dSortTmp = nullptr;
+  size_t sortTmpBytes = 0;
+  unsigned long long* dRecCount = nullptr;
+  if (segmented) {
+    RTB_CUDA(cudaMemGetInfo(&freeB, &totalB));
+    // a leaf ray crosses at most ~2 n 2^maxLevel cells; rays of the coarser pixel levels add a few per cent
+    const long long leafRays = 12LL << (2 * (in.maxPixelLevel - 1));
+    const long long estimate = (long long)batch * leafRays * 2 * c.nx * (1LL << c.maxLevel) + (1 << 20);
+    recCap = (long long)std::min<size_t>((size_t)(0.6 * (double)freeB) / 80, (size_t)0xFFFFFFF0u);
+    recCap = std::min(recCap, estimate);
+    if (c.tune.pointRecordCap > 0) recCap = std::min<long long>(recCap, c.tune.pointRecordCap);
+    if (int st = sc.get(&dRecKey, (size_t)recCap)) return st;
+    if (int st = sc.get(&dRecKeyOut, (size_t)recCap)) return st;
+    if (int st = sc.get(&dRecIdx, (size_t)recCap)) return st;
+    if (int st = sc.get(&dRecIdxOut, (size_t)recCap)) return st;
+    if (int st = sc.get(&dRecVal, (size_t)6 * recCap)) return st;
+    if (int st = sc.get(&dRecCount, 1)) return st;
+    RTB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sortTmpBytes, dRecKey, dRecKeyOut, dRecIdx, dRecIdxOut, (long long)recCap,
+                                             0, 64, s));
+    char* tmp = nullptr;
+    if (int st = sc.get(&tmp, sortTmpBytes)) return st;
+    dSortTmp = tmp;
+  }
 
   PointParams P{};
   P.child = c.tree.child; P.level = c.dLevel; P.leafX = c.tree.leafX; P.leafY = c.tree.leafY; P.leafZ = c.tree.leafZ;
@@ -734,6 +819,10 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
   P.rates = dRates;
   P.nseg = dCounters; P.err = c.dErr;
   P.trace = dTrace; P.traceLen = dCounters + 1; P.traceCap = dTrace ? traceCap : 0;
+  P.recKey = segmented ? dRecKey : nullptr; P.recVal = dRecVal; P.recCount = dRecCount; P.recCap = recCap;
+  P.raysPerSource = raysPerSource;
+  int leafBits = 1;
+  while ((1LL << leafBits) < c.nleaf) leafBits++;
 
   for (int b0 = 0; b0 < nsrc; b0 += batch) {
     const int nb = std::min(batch, nsrc - b0);
@@ -748,25 +837,47 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
       RTB_CUDA(cudaMemcpyAsync(hRawTables + (size_t)b0 * 6 * planes * kPlane, dRaw, (size_t)nb * 6 * planes * kPlane * 8,
                                cudaMemcpyDeviceToHost, s));
     P.srcLeaf = dSrcLeaf + b0; P.srcWeight = dSrcWeight + b0; P.logTab = dLogTab; P.diag = dDiag;
+    if (segmented) RTB_CUDA(cudaMemsetAsync(dRecCount, 0, 8, s));
     RayState *stIn = dStA, *stOut = dStB;
     for (int L = 1; L <= in.maxPixelLevel; L++) {
       const int64_t npix = 12LL << (2 * (L - 1));
       P.stateIn = stIn; P.stateOut = stOut;
       dim3 g((unsigned)((npix + 127) / 128), nb);
       if (dTrace) {
-        if (portable) point_march_kernel<true, true, true><<<g, 128, 0, s>>>(P, L);
-        else if (faithful) point_march_kernel<true, false, true><<<g, 128, 0, s>>>(P, L);
-        else point_march_kernel<false, false, true><<<g, 128, 0, s>>>(P, L);
+        if (portable) point_march_kernel<true, true, true, false><<<g, 128, 0, s>>>(P, L);
+        else if (faithful) point_march_kernel<true, false, true, false><<<g, 128, 0, s>>>(P, L);
+        else point_march_kernel<false, false, true, false><<<g, 128, 0, s>>>(P, L);
+      } else if (segmented) {
+        if (portable) point_march_kernel<true, true, false, true><<<g, 128, 0, s>>>(P, L);
+        else if (faithful) point_march_kernel<true, false, false, true><<<g, 128, 0, s>>>(P, L);
+        else point_march_kernel<false, false, false, true><<<g, 128, 0, s>>>(P, L);
       } else {
-        if (portable) point_march_kernel<true, true, false><<<g, 128, 0, s>>>(P, L);
-        else if (faithful) point_march_kernel<true, false, false><<<g, 128, 0, s>>>(P, L);
-        else point_march_kernel<false, false, false><<<g, 128, 0, s>>>(P, L);
+        if (portable) point_march_kernel<true, true, false, false><<<g, 128, 0, s>>>(P, L);
+        else if (faithful) point_march_kernel<true, false, false, false><<<g, 128, 0, s>>>(P, L);
+        else point_march_kernel<false, false, false, false><<<g, 128, 0, s>>>(P, L);
       }
       c.lastLaunches++;
       c.lastSweepLaunches++;
       std::swap(stIn, stOut);
     }
     RTB_CUDA(cudaGetLastError());
+    if (segmented) {
+      unsigned long long nrec = 0;
+      RTB_CUDA(cudaMemcpyAsync(&nrec, dRecCount, 8, cudaMemcpyDeviceToHost, s));
+      RTB_CUDA(cudaStreamSynchronize(s));
+      if ((long long)nrec > recCap) return RTB200_ERR_NOMEM;  // more segments than record slots: lower "point_batch"
+      if (nrec > 0) {
+        const int blocks = (int)std::min<long long>(((long long)nrec + 255) / 256, (long long)c.smCount * 16);
+        iota_kernel<<<blocks, 256, 0, s>>>(dRecIdx, (long long)nrec);
+        size_t tb = sortTmpBytes;
+        RTB_CUDA(cub::DeviceRadixSort::SortPairs(dSortTmp, tb, dRecKey, dRecKeyOut, dRecIdx, dRecIdxOut, (long long)nrec, 0,
+                                                 32 + leafBits, s));
+        segmented_reduce_kernel<<<blocks, 256, 0, s>>>(dRecKeyOut, dRecIdxOut, dRecVal, (long long)nrec, recCap, dRates,
+                                                       c.nleaf);
+        c.lastLaunches += 3;
+        RTB_CUDA(cudaGetLastError());
+      }
+    }
     if (hDiag)
       RTB_CUDA(cudaMemcpyAsync(hDiag + (size_t)b0 * kDiagStride, dDiag, (size_t)nb * kDiagStride * 8, cudaMemcpyDeviceToHost, s));
   }

@@ -74,6 +74,9 @@ struct Tuning {
   int dirsPerTask = 0;   // directions of one zone swept together (0 = kMaxDirPerTask)
   int marchDebug = 0;    // experiments only: 1 = skip the neighbour polling (wrong results), 2 = spin without nanosleep
   int portableMath = 1;  // point path, FAITHFUL mode: exp/log from portable_math.h (bit-identical on host and device)
+  int pointDeposit = 0;  // point path: 0 = fp64 RED.ADD into the rate fields, 1 = atomic-free: (leaf, deposit) records,
+                         // radix sort by (leaf, ray, segment), one thread per cell adds its run (deterministic order)
+  long long pointRecordCap = 0;  // upper limit of the record buffer of mode 1 (0 = 60% of the free memory)
   int pointBatch = 0;    // sources per batch of the point path (0 = as many as fit in half of the free memory)
 };
 

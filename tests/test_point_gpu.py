@@ -239,3 +239,33 @@ def test_golden_fixtures(rt, engine, spectra):
     # the oracle traces source by source, depth first; the device sorts by (source, pixel level, pixel, segment)
     tr, n0 = f["trace"], int(f["nseg_source0"])
     assert np.array_equal(r["trace"], np.concatenate([_by_ray(tr[:n0]), _by_ray(tr[n0:])]))
+
+
+def test_segmented_deposition_is_deterministic_and_atomic_free(rt, engine, portable, spectra):
+    """set_tuning(point_deposit=1): records + radix sort by (leaf, ray, segment) + one thread per cell.  Same deposits
+    as the RED.ADD path (<= 1e-12 per cell: only the order of the additions differs), bit-identical from run to run
+    and independent of the batching of sources."""
+    n = 12
+    g = W.nested_grid(n, 1, W.central_box_refine(0.25, 0.75, levels=1), seed=21, tau_lo=1e-2, tau_hi=1.0, beta24=S24)
+    _set(engine, g)
+    rng = np.random.default_rng(8)
+    leaves = rng.choice(g["level"].size, 5, replace=False).astype(np.int32)
+    wts = np.array([1, 2, 0, 3, 1], dtype=np.int32)
+    atom = engine.point(spectra, leaves, wts, dust_approximation=1)
+    engine.set_tuning(point_deposit=1)
+    seg1 = engine.point(spectra, leaves, wts, dust_approximation=1)
+    seg2 = engine.point(spectra, leaves, wts, dust_approximation=1)
+    assert seg1["nseg"] == atom["nseg"]
+    assert np.array_equal(seg1["rates"], seg2["rates"])
+    for i in range(6):
+        assert _cell_err(seg1["rates"][i], atom["rates"][i]) < 1e-12
+    o = _ograd(portable, g).point(spectra, leaves, wts, dust_approximation=1)
+    for i in range(6):
+        assert _cell_err(seg1["rates"][i], o["rates"][i]) < 1e-12
+    # accumulation into existing rates, and a record buffer that is too small is reported, not truncated
+    seg3 = engine.point(spectra, leaves, wts, dust_approximation=1, rates=seg1["rates"])
+    assert rel_err(seg3["rates"], 2 * seg1["rates"], floor=1e-300) < 1e-12
+    engine.set_tuning(point_record_cap=1000)
+    with pytest.raises(rt.RTB200Error):
+        engine.point(spectra, leaves, wts, dust_approximation=1)
+    engine.set_tuning(point_record_cap=0, point_deposit=0)

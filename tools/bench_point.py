@@ -19,6 +19,7 @@ ap.add_argument("--modes", nargs="+", default=["fast", "faithful"])
 ap.add_argument("--dust", type=int, default=0)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--uniform", action="store_true")
+ap.add_argument("--deposit", type=int, default=0)
 args = ap.parse_args()
 
 t0 = time.time()
@@ -27,6 +28,7 @@ print(f"grid: {g['level'].size} leaves, {args.nsrc} sources, built in {time.time
 sp = W.synthetic_spectra()
 t = rt.Transport(device=0)
 t.set_grid(g["nx"], g["level"], g["HI"], g["HeI"], g["HeII"], g["rho"], g["abun2"], g["box_size"])
+t.set_tuning(point_deposit=args.deposit)
 R = torch.zeros(6, g["level"].size, dtype=torch.float64, device="cuda:0")
 s = torch.cuda.current_stream().cuda_stream
 wt = np.ones(args.nsrc, dtype=np.int32)
@@ -40,7 +42,7 @@ for mode in args.modes:
         torch.cuda.synchronize()
         wall = (time.perf_counter() - w0) * 1e3
         st = t.last_stats()
-        print(f"n={args.n} nsrc={args.nsrc} dust={args.dust} mode={mode}: device_ms={st['device_ms']:.2f} wall_ms={wall:.2f} "
+        print(f"n={args.n} nsrc={args.nsrc} dust={args.dust} deposit={args.deposit} mode={mode}: device_ms={st['device_ms']:.2f} wall_ms={wall:.2f} "
               f"nseg={nseg} seg/s={nseg / st['device_ms'] * 1e3:.3e} alg GB/s={st['algorithmic_bytes'] / st['device_ms'] / 1e6:.1f} "
               f"sum(krate24)={float(R[0].sum()):.6e}", flush=True)
 t.close()
