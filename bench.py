@@ -388,6 +388,7 @@ def main():
         torch.cuda.synchronize()
 
     ar0, ar1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    K = torch.zeros(3, N, dtype=torch.float64, device=dev)     # krate24, krate25, krate26
 
     def step_resident():
         nseg = eng.diffuse_device(bg["uvb"], bg["beta"], J.data_ptr(), rays=rays, stream=stream)
@@ -395,6 +396,9 @@ def main():
             ar0.record()
             dist.all_reduce(J)            # per-leaf Jmean1..3 summed over the ranks' direction shards (NCCL, NVLink)
             ar1.record()
+        # the diffuse contribution to the photo-rates (equiSources.f90:3546-3553) from the summed J
+        eng.diffuse_rates_device(J.data_ptr(), bg["ksi24"], bg["ksi25"], bg["ksi26"], K[0].data_ptr(), K[1].data_ptr(),
+                                 K[2].data_ptr(), stream=stream)
         return nseg
 
     # ---- resident-data timing: W warm-ups, then exactly K steps between barrier + synchronize ----
@@ -476,6 +480,7 @@ def main():
             "config": {"workload": args.workload, "grid": f"{n}^3 uniform, lognormal tau", "directions": 192,
                        "n_angular_level": 3, "frequency_groups": 3, "leaves": N,
                        "segment_updates_per_step": nseg_total, "math": "fast",
+                       "step": "computeOpacities + 192-direction sweep + merge [+ all-reduce of J] + diffuse photo-rates",
                        "parallelism": f"directions sharded over {world} GPU(s), full grid per GPU, all-reduce of J",
                        "l2_policy": "inputs larger than L2 (kappa + J + planes >> 126 MB)" if n >= 200 else
                                     "working set comparable to L2; not flushed between steps"},
