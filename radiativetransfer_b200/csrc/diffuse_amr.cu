@@ -155,8 +155,10 @@ __global__ void amr_neighbour_kernel(AmrParams P, int ndir) {
   }
 }
 
-// one (leaf, direction): returns false if an upstream leaf is not published yet
-template <bool FAITHFUL>
+// one (leaf, direction): returns false if an upstream leaf is not published yet.  CHECK = false: the grid is 2:1
+// balanced, the wave order alone guarantees that every upstream leaf was finished by an earlier launch, so the
+// per-leaf `done` flags (three dependent gathers, two fences and a store per item) are not needed.
+template <bool FAITHFUL, bool CHECK>
 __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, int64_t leaf) {
   const AmrDir& D = P.dirs[d];
   int32_t nbl[3];
@@ -166,11 +168,13 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
     nbl[ray] = P.nb[((int64_t)d * 3 + ray) * P.N + leaf];
     cd[ray] = P.code[((int64_t)d * 3 + ray) * P.N + leaf];
   }
-  const volatile uint8_t* done = P.done + (int64_t)d * P.N;
+  if (CHECK) {
+    const volatile uint8_t* done = P.done + (int64_t)d * P.N;
 #pragma unroll
-  for (int ray = 0; ray < 3; ray++)
-    if (nbl[ray] >= 0 && !done[nbl[ray]]) return false;
-  __threadfence();
+    for (int ray = 0; ray < 3; ray++)
+      if (nbl[ray] >= 0 && !done[nbl[ray]]) return false;
+    __threadfence();
+  }
   const int L = P.level[leaf];
   int r[3];
   rotated_coords(D, P.n << L, P.lx[leaf], P.ly[leaf], P.lz[leaf], r);
@@ -237,8 +241,10 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
 #pragma unroll
   for (int g = 0; g < 3; g++)
     atomicAdd(P.J + g * P.N + leaf, __dmul_rn(__ddiv_rn(Jm[g], (double)imean), D.w));
-  __threadfence();
-  ((volatile uint8_t*)P.done)[(int64_t)d * P.N + leaf] = 1;
+  if (CHECK) {
+    __threadfence();
+    ((volatile uint8_t*)P.done)[(int64_t)d * P.N + leaf] = 1;
+  }
   return true;
 }
 
@@ -250,7 +256,7 @@ struct WaveParams {
   int64_t deferredCap;
 };
 
-template <bool FAITHFUL>
+template <bool FAITHFUL, bool CHECK>
 __global__ void amr_wave_kernel(AmrParams P, WaveParams Wp, int ndir) {
   const int d = blockIdx.y;
   if (d >= ndir) return;
@@ -258,7 +264,7 @@ __global__ void amr_wave_kernel(AmrParams P, WaveParams Wp, int ndir) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Wp.count[combo]) return;
   const int64_t leaf = Wp.sorted[combo][Wp.begin[combo] + i];
-  if (!amr_transport_leaf<FAITHFUL>(P, d, leaf)) {
+  if (!amr_transport_leaf<FAITHFUL, CHECK>(P, d, leaf)) {
     int slot = atomicAdd(Wp.deferredCount, 1);
     if (slot < Wp.deferredCap) Wp.deferred[slot] = ((int64_t)d << 32) | leaf;
     else atomicMax(P.err, RTB200_ERR_NOMEM);
@@ -273,7 +279,7 @@ __global__ void amr_retry_kernel(AmrParams P, const int64_t* in, const int32_t* 
     const int64_t item = in[i];
     const int d = (int)(item >> 32);
     const int64_t leaf = item & 0xffffffffLL;
-    if (!amr_transport_leaf<FAITHFUL>(P, d, leaf)) {
+    if (!amr_transport_leaf<FAITHFUL, true>(P, d, leaf)) {
       int slot = atomicAdd(outCount, 1);
       if (slot < cap) out[slot] = item;
     }
@@ -296,6 +302,7 @@ static DevPattern to_dev(const RayPattern& p) {
 }
 
 struct AmrPlan {
+  bool balanced = false;              // face neighbours differ by at most one level
   std::vector<int32_t> sorted[8];
   std::vector<int32_t> waveStart[8];  // [nkeys + 1]
   int nkeys = 0;
@@ -332,9 +339,66 @@ static void build_waves(Context& c, AmrPlan& plan) {
   }
 }
 
+// level of the leaf that contains the cell with coordinates p at level l (the leaf may be coarser than l)
+static int leaf_level_at(const Context& c, int l, const int (&p)[3]) {
+  const int n = c.nx;
+  int node = ((p[0] >> l) * n + (p[1] >> l)) * n + (p[2] >> l);
+  for (int t = l - 1; t >= 0; t--) {
+    if (c.hChild[node] < 0) return l - 1 - t;
+    node = c.hChild[node] + (((p[0] >> t) & 1) << 2) + (((p[1] >> t) & 1) << 1) + ((p[2] >> t) & 1);
+  }
+  return l;
+}
+
+static bool grid_is_balanced(const Context& c) {
+  for (int64_t leaf = 0; leaf < c.nleaf; leaf++) {
+    const int L = c.hLevel[leaf];
+    if (L < 2) continue;  // a face neighbour cannot be two levels coarser
+    const int nL = c.nx << L;
+    for (int f = 0; f < 6; f++) {
+      int p[3] = {c.hLeafX[leaf], c.hLeafY[leaf], c.hLeafZ[leaf]};
+      p[f >> 1] += (f & 1) ? 1 : -1;
+      if (p[f >> 1] < 0 || p[f >> 1] >= nL) continue;
+      if (leaf_level_at(c, L, p) < L - 1) return false;
+    }
+  }
+  return true;
+}
+
+struct DirTables {
+  std::vector<DevPattern> pats;
+  std::vector<AmrDir> dirs;
+  std::vector<int32_t> levelOff;
+  int perDir = 0;
+};
+
+// device buffers of one batch of directions (kept across calls while the sizes fit)
+struct AmrBuffers {
+  DevPattern* pats = nullptr;
+  AmrDir* dirs = nullptr;
+  int32_t* levelOff = nullptr;
+  int32_t* nb = nullptr;
+  uint8_t* code = nullptr;
+  double* Iout = nullptr;
+  uint8_t* done = nullptr;
+  int64_t* defA = nullptr;
+  int64_t* defB = nullptr;
+  int32_t* defCount = nullptr;  // [2]
+  std::string sizeKey;
+  int batch = 0, batchNdir = 0;   // batch size chosen when the buffers were allocated, and for how many directions
+  void release() {
+    cudaFree(pats); cudaFree(dirs); cudaFree(levelOff); cudaFree(nb); cudaFree(code); cudaFree(Iout); cudaFree(done);
+    cudaFree(defA); cudaFree(defB); cudaFree(defCount);
+    *this = AmrBuffers();
+  }
+};
+
 struct AmrState {
   AmrPlan plan;
   std::string key;
+  DirTables tables;       // per-direction pattern tables of the last call (depend on the grid and the direction list)
+  std::string tablesKey;
+  AmrBuffers buffers;
 };
 static std::vector<std::pair<Context*, AmrState*>> g_states;
 static AmrState* state_of(Context& c) {
@@ -347,6 +411,7 @@ void amr_release(Context& c) {
   for (size_t i = 0; i < g_states.size(); i++)
     if (g_states[i].first == &c) {
       for (int k = 0; k < 8; k++) cudaFree(g_states[i].second->plan.dSorted[k]);
+      g_states[i].second->buffers.release();
       delete g_states[i].second;
       g_states.erase(g_states.begin() + i);
       return;
@@ -359,6 +424,8 @@ static int ensure_plan(Context& c, AmrState& S) {
   if (S.key == buf) return RTB200_OK;
   for (int k = 0; k < 8; k++) { cudaFree(S.plan.dSorted[k]); S.plan.dSorted[k] = nullptr; }
   build_waves(c, S.plan);
+  S.plan.balanced = grid_is_balanced(c);
+  S.tablesKey.clear();
   for (int k = 0; k < 8; k++) {
     RTB_CUDA(cudaMalloc((void**)&S.plan.dSorted[k], (size_t)c.nleaf * sizeof(int32_t)));
     RTB_CUDA(cudaMemcpy(S.plan.dSorted[k], S.plan.sorted[k].data(), (size_t)c.nleaf * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -366,13 +433,6 @@ static int ensure_plan(Context& c, AmrState& S) {
   S.key = buf;
   return RTB200_OK;
 }
-
-struct DirTables {
-  std::vector<DevPattern> pats;
-  std::vector<AmrDir> dirs;
-  std::vector<int32_t> levelOff;
-  int perDir = 0;
-};
 
 static int build_dir_tables(Context& c, int nAngularLevel, const std::vector<Direction>& dirs, DirTables& T) {
   const int Lmax = c.maxLevel, n = c.nx;
@@ -428,25 +488,6 @@ static int build_dir_tables(Context& c, int nAngularLevel, const std::vector<Dir
   return RTB200_OK;
 }
 
-// device buffers of one batch of directions
-struct AmrBuffers {
-  DevPattern* pats = nullptr;
-  AmrDir* dirs = nullptr;
-  int32_t* levelOff = nullptr;
-  int32_t* nb = nullptr;
-  uint8_t* code = nullptr;
-  double* Iout = nullptr;
-  uint8_t* done = nullptr;
-  int64_t* defA = nullptr;
-  int64_t* defB = nullptr;
-  int32_t* defCount = nullptr;  // [2]
-  void release() {
-    cudaFree(pats); cudaFree(dirs); cudaFree(levelOff); cudaFree(nb); cudaFree(code); cudaFree(Iout); cudaFree(done);
-    cudaFree(defA); cudaFree(defB); cudaFree(defCount);
-    *this = AmrBuffers();
-  }
-};
-
 static int alloc_batch(AmrBuffers& B, const DirTables& T, int64_t N, int ndirBatch, int64_t defCap) {
   RTB_CUDA(cudaMalloc((void**)&B.pats, (size_t)T.perDir * ndirBatch * sizeof(DevPattern)));
   RTB_CUDA(cudaMalloc((void**)&B.dirs, (size_t)ndirBatch * sizeof(AmrDir)));
@@ -479,7 +520,7 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int d0, int nd
   for (int i = 0; i < nd; i++) dl[i].patBase = i * T.perDir;
   RTB_CUDA(cudaMemcpyAsync(B.dirs, dl.data(), (size_t)nd * sizeof(AmrDir), cudaMemcpyHostToDevice, s));
   RTB_CUDA(cudaMemcpyAsync(B.levelOff, T.levelOff.data(), T.levelOff.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-  RTB_CUDA(cudaMemsetAsync(B.done, 0, (size_t)nd * N, s));
+  if (!S.plan.balanced) RTB_CUDA(cudaMemsetAsync(B.done, 0, (size_t)nd * N, s));
   RTB_CUDA(cudaMemsetAsync(B.defCount, 0, 2 * sizeof(int32_t), s));
   RTB_CUDA(cudaStreamSynchronize(s));  // dl is a local
   AmrParams P;
@@ -511,10 +552,11 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int d0, int nd
     Wp.deferred = lists[cur];
     Wp.deferredCount = B.defCount + cur;
     dim3 grid((maxCount + 127) / 128, nd);
-    if (faithful) amr_wave_kernel<true><<<grid, 128, 0, s>>>(P, Wp, nd);
-    else amr_wave_kernel<false><<<grid, 128, 0, s>>>(P, Wp, nd);
+    const bool check = !S.plan.balanced;
+    if (faithful) { if (check) amr_wave_kernel<true, true><<<grid, 128, 0, s>>>(P, Wp, nd); else amr_wave_kernel<true, false><<<grid, 128, 0, s>>>(P, Wp, nd); }
+    else { if (check) amr_wave_kernel<false, true><<<grid, 128, 0, s>>>(P, Wp, nd); else amr_wave_kernel<false, false><<<grid, 128, 0, s>>>(P, Wp, nd); }
     (*launches)++;
-    if ((w & 15) == 15) {
+    if (check && (w & 15) == 15) {
       // retry what has been deferred so far (nothing on 2:1-balanced grids)
       RTB_CUDA(cudaMemsetAsync(B.defCount + (cur ^ 1), 0, sizeof(int32_t), s));
       if (faithful) amr_retry_kernel<true><<<64, 128, 0, s>>>(P, lists[cur], B.defCount + cur, lists[cur ^ 1], B.defCount + (cur ^ 1), defCap);
@@ -524,7 +566,7 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int d0, int nd
     }
   }
   // drain the deferred list
-  for (int iter = 0; iter < 100000; iter++) {
+  for (int iter = 0; iter < 100000 && !S.plan.balanced; iter++) {
     int32_t cnt = 0;
     RTB_CUDA(cudaMemcpyAsync(&cnt, B.defCount + cur, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     RTB_CUDA(cudaStreamSynchronize(s));
@@ -551,13 +593,36 @@ int diffuse_amr(Context& c, int nAngularLevel, const double* uvb, const std::vec
   c.lastLaunches = 2;
   if (nsegOut) *nsegOut = 0;
   if (dirs.empty()) return RTB200_OK;
-  DirTables T;
-  if (int st = build_dir_tables(c, nAngularLevel, dirs, T)) return st;
+  // pattern tables: a function of the grid and of the direction list -> kept across the outer iterations
+  std::string tkey = S.key;
+  {
+    char buf[48];
+    snprintf(buf, sizeof(buf), "|%d|%a|", nAngularLevel, c.boxSize);
+    tkey += buf;
+    for (const auto& d : dirs) { snprintf(buf, sizeof(buf), "%lld,", (long long)d.iray); tkey += buf; }
+  }
+  if (S.tablesKey != tkey) {
+    S.tables = DirTables();
+    if (int st = build_dir_tables(c, nAngularLevel, dirs, S.tables)) return st;
+    S.tablesKey = tkey;
+  }
+  DirTables& T = S.tables;
   const int ndir = (int)dirs.size();
-  const int batch = choose_batch(c, ndir);
+  AmrBuffers& B = S.buffers;
+  // the cached buffers count as used memory: keep their batch size instead of choosing a smaller one every call
+  const int batch = (B.batch > 0 && B.batchNdir == ndir) ? B.batch : choose_batch(c, ndir);
   const int64_t defCap = std::max<int64_t>(1 << 16, std::min<int64_t>((int64_t)batch * N, (int64_t)1 << 26));
-  AmrBuffers B;
-  int st = alloc_batch(B, T, N, batch, defCap);
+  int st = RTB200_OK;
+  {
+    char buf[96];
+    snprintf(buf, sizeof(buf), "%d:%lld:%d:%lld", T.perDir, (long long)N, batch, (long long)defCap);
+    if (B.sizeKey != buf) {
+      B.release();
+      st = alloc_batch(B, T, N, batch, defCap);
+      if (st) B.release();
+      else { B.sizeKey = buf; B.batch = batch; B.batchNdir = ndir; }
+    }
+  }
   int64_t launches = 0;
   const bool faithful = c.mathMode == RTB200_MATH_FAITHFUL;
   for (int d0 = 0; d0 < ndir && !st; d0 += batch)
@@ -591,7 +656,6 @@ int diffuse_amr(Context& c, int nAngularLevel, const double* uvb, const std::vec
     *nsegOut = nseg;
   }
   cudaStreamSynchronize(s);
-  B.release();
   c.lastSweepLaunches = launches;
   c.lastLaunches = launches + 2;
   return st;
