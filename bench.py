@@ -44,6 +44,9 @@ WORKLOADS = {
     "diffuse-256^3-uniform-192dir": 256,
     "diffuse-128^3-uniform-192dir": 128,
     "diffuse-64^3-uniform-192dir": 64,
+    # config-5 style nested grid: n^3 base + refinement levels around a synthetic disc (general octree path)
+    "diffuse-128^3-amr2-192dir": ("amr", 128, 2),
+    "diffuse-64^3-amr3-192dir": ("amr", 64, 3),
     # point sources: n^3 base grid + one refined level over the central (n/4)^3 base cells, sources inside it
     "point-128^3-amr-100src": (128, 100),
     "point-256^3-amr-1000src": (256, 1000),
@@ -51,9 +54,13 @@ WORKLOADS = {
 }
 
 
-def make_inputs(n, seed=1):
+def make_inputs(spec, seed=1):
+    """(n, grid dict, background) of a diffuse workload: uniform n^3 or a nested grid"""
     from radiativetransfer_b200 import workloads as W
-    return W.uniform_grid(n, seed=seed), W.uvb_background(3.0)
+    if isinstance(spec, tuple):
+        _, n, levels = spec
+        return n, W.nested_grid(n, levels, W.disc_refine(levels), seed=5), W.uvb_background(3.0)
+    return spec, W.uniform_grid(spec, seed=seed), W.uvb_background(3.0)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -182,12 +189,11 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
         return
-    n = WORKLOADS[args.workload]
-    grid, bg = make_inputs(n)
+    n, grid, bg = make_inputs(WORKLOADS[args.workload])
     import psutil
     cores = os.cpu_count() or 1
     avail = psutil.virtual_memory().available
-    per_copy = 200.0 * n ** 3 * 1.15          # bytes per private octree copy
+    per_copy = 200.0 * int(grid["level"].size) * 1.3          # bytes per private octree copy
     # all host cores (every thread sweeps its own directions on a private copy of the octree); measured on the 16-core
     # GPU box at 256^3: 4 threads 1.3e7, 8 threads 2.1e7, 16 threads 3.0e7 segment updates/s
     threads = int(max(1, min(cores, 32, (0.5 * avail) // per_copy)))
@@ -207,7 +213,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "grid": f"{n}^3 uniform", "directions": 192,
+        "config": {"workload": args.workload, "grid": f"{n}^3 base, {int(grid['level'].size)} leaves", "directions": 192,
                    "note": "each step = a bounded sample of directions of the workload, scaled per segment update"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -372,9 +378,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
 
-    n = WORKLOADS[args.workload]
-    grid, bg = make_inputs(n)
-    N = n ** 3
+    n, grid, bg = make_inputs(WORKLOADS[args.workload])
+    N = int(grid["level"].size)
+    uniform = not isinstance(WORKLOADS[args.workload], tuple)
     eng = rt.Transport(device=local)
     eng.set_grid(n, grid["level"], grid["HI"], grid["HeI"], grid["HeII"], grid["rho"], grid["abun2"], grid["box_size"])
     shards = sharding.shard_directions(world, n_angular_level=3, nx=n)
@@ -420,6 +426,8 @@ def main():
     # the library's own CUDA events (same stream) bracket the sweep-kernel launches of the LAST step
     st = eng.last_stats()
     sweep_ms, sweep_launches, launches = st["sweep_ms"], st["sweep_launches"], st["launches"]
+    if sweep_ms <= 0:                       # general octree path: the library times the whole call
+        sweep_ms = st["device_ms"]
     alg_bytes_rank = st["algorithmic_bytes"]
     barrier()
     t = torch.tensor([ms, float(nseg_rank), sweep_ms, alg_bytes_rank], dtype=torch.float64, device=dev)
@@ -477,7 +485,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "grid": f"{n}^3 uniform, lognormal tau", "directions": 192,
+            "config": {"workload": args.workload,
+                       "grid": f"{n}^3 uniform, lognormal tau" if uniform else f"{n}^3 base + nested levels (disc), {N} leaves",
+                       "directions": 192,
                        "n_angular_level": 3, "frequency_groups": 3, "leaves": N,
                        "segment_updates_per_step": nseg_total, "math": "fast",
                        "step": "computeOpacities + 192-direction sweep + merge [+ all-reduce of J] + diffuse photo-rates",
@@ -494,7 +504,8 @@ def main():
                          "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                          "algorithmic_bytes_per_launch": alg_bytes_rank / max(1, int(sweep_launches) - 1),
                          "peak_source": peak_src,
-                         "kernel": "rtb::sweep_cell_kernel", "launches_per_step": int(sweep_launches),
+                         "kernel": "rtb::sweep_cell_kernel" if uniform else "rtb::amr_wave_kernel",
+                         "launches_per_step": int(sweep_launches),
                          "algorithmic_bytes_per_step_this_rank": alg_bytes_rank, "kernel_ms_per_step": sweep_ms,
                          "kernel_ms_per_step_all_ranks": rank_kernel_ms,
                          "allreduce_ms_rank0_last_step": allreduce_ms,
