@@ -26,12 +26,15 @@
 
 namespace rtb {
 
-struct DevPattern {      // subset of RayPattern the device needs (64 B)
+struct DevPattern {      // subset of RayPattern the device needs (96 B)
   double len[3];         // xy, yz, xz   (ray id 0, 1, 2)
+  double dpath[3];       // cellSize(level) * len, multiplied on the host exactly as the kernel used to
+  double cellSize;       // of the table's level
   double e0[3], e1[3];   // entry point of each ray on its face: xy (x0,y0), yz (y0,z0), xz (x0,z0)
   int8_t top[3];         // xyTop, yzTop, xzTop: which ray (1 xy, 2 yz, 3 xz) leaves through the top / x=1 / y=1 face
   int8_t active[3];      // xy (always), yz, xz
-  int8_t pad[2];
+  int8_t level;          // refinement level of the table
+  int8_t pad[1];
 };
 
 struct AmrDir {          // one direction of the batch
@@ -52,6 +55,10 @@ struct AmrParams {
   const AmrDir* dirs;
   int32_t* nb;             // [ndir][3][N] upstream leaf per ray (xy, yz, xz): -1 boundary, -2 inactive
   uint8_t* code;           // [ndir][3][N] what to read from the upstream leaf
+  int32_t* nbc;            // [ndir][N][4] the same packed for the sweep: leaf << 3 | code (or -1 / -2) per ray, 16 B per item
+  const int32_t* patIdx;   // [6][N] levelOff[level] + coordinate along physical axis a (a = 0..2), then reflected (3..5)
+  const double* kappaA;    // [N][3] opacities, leaf-major (one gather instead of three)
+  double* JA;              // [N][3] accumulator, leaf-major (atomics), un-interleaved into J at the end
   double* Iout;            // [ndir][N][9]
   uint8_t* done;           // [ndir][N]
   double* J;               // [3][N] (atomics)
@@ -152,6 +159,22 @@ __global__ void amr_neighbour_kernel(AmrParams P, int ndir) {
     }
     P.nb[((int64_t)d * 3 + ray) * P.N + leaf] = result;
     P.code[((int64_t)d * 3 + ray) * P.N + leaf] = code;
+    if (P.nbc) P.nbc[((int64_t)d * P.N + leaf) * 4 + ray] = result >= 0 ? ((result << 3) | code) : result;
+  }
+}
+
+// leaf-major copies for the sweep's gathers
+__global__ void interleave3_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t N) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 3 * N; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t leaf = i / 3;
+    const int g = (int)(i - 3 * leaf);
+    out[i] = in[g * N + leaf];
+  }
+}
+__global__ void deinterleave3_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t N) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 3 * N; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = i / N, leaf = i - g * N;
+    out[i] = in[leaf * 3 + g];
   }
 }
 
@@ -163,10 +186,14 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
   const AmrDir& D = P.dirs[d];
   int32_t nbl[3];
   uint8_t cd[3];
+  {
+    const int4 q = *reinterpret_cast<const int4*>(P.nbc + ((int64_t)d * P.N + leaf) * 4);
+    const int32_t v[3] = {q.x, q.y, q.z};
 #pragma unroll
-  for (int ray = 0; ray < 3; ray++) {
-    nbl[ray] = P.nb[((int64_t)d * 3 + ray) * P.N + leaf];
-    cd[ray] = P.code[((int64_t)d * 3 + ray) * P.N + leaf];
+    for (int ray = 0; ray < 3; ray++) {
+      nbl[ray] = v[ray] >= 0 ? (v[ray] >> 3) : v[ray];
+      cd[ray] = (uint8_t)(v[ray] & 7);
+    }
   }
   if (CHECK) {
     const volatile uint8_t* done = P.done + (int64_t)d * P.N;
@@ -175,16 +202,15 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
       if (nbl[ray] >= 0 && !done[nbl[ray]]) return false;
     __threadfence();
   }
-  const int L = P.level[leaf];
-  int r[3];
-  rotated_coords(D, P.n << L, P.lx[leaf], P.ly[leaf], P.lz[leaf], r);
-  const DevPattern& pat = P.pats[D.patBase + P.levelOff[L] + r[0]];
-  const double cellSize = P.cellSize0 / (double)(1 << L);  // halved per level (transportRoutinesModule.f90:583)
+  // pattern of the leaf's (level, layer along the sweep axis): one gather of a precomputed index
+  const int sweepAxis = D.inv[0];
+  const DevPattern& pat = P.pats[D.patBase + P.patIdx[(int64_t)(sweepAxis + (D.refl[sweepAxis] ? 3 : 0)) * P.N + leaf]];
+  const int L = pat.level;
   const double uvb[3] = {P.u0, P.u1, P.u2};
   double kap[3], invk[3];
 #pragma unroll
   for (int g = 0; g < 3; g++) {
-    kap[g] = P.kappa[g * P.N + leaf];
+    kap[g] = P.kappaA[leaf * 3 + g];
     if (!FAITHFUL) {
       kap[g] = kap[g] > 0. ? kap[g] : 1e-200;
       invk[g] = 1.0 / kap[g];
@@ -219,7 +245,7 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
         else Iin[g] = __ldcg(nI + g);
       }
     }
-    const double dpath = __dmul_rn(cellSize, pat.len[ray]);
+    const double dpath = pat.dpath[ray];  // cellSize(level) * len (transportRoutinesModule.f90:583, 651)
     const double invd = FAITHFUL ? 0. : 1.0 / dpath;
 #pragma unroll
     for (int g = 0; g < 3; g++) {
@@ -240,7 +266,7 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
     for (int g = 0; g < 3; g++) mine[ray * 3 + g] = out[ray][g];
 #pragma unroll
   for (int g = 0; g < 3; g++)
-    atomicAdd(P.J + g * P.N + leaf, __dmul_rn(__ddiv_rn(Jm[g], (double)imean), D.w));
+    atomicAdd(P.JA + leaf * 3 + g, __dmul_rn(__ddiv_rn(Jm[g], (double)imean), D.w));
   if (CHECK) {
     __threadfence();
     ((volatile uint8_t*)P.done)[(int64_t)d * P.N + leaf] = 1;
@@ -289,10 +315,13 @@ __global__ void amr_retry_kernel(AmrParams P, const int64_t* in, const int32_t* 
 // ---------------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------------
-static DevPattern to_dev(const RayPattern& p) {
+static DevPattern to_dev(const RayPattern& p, double cellSize, int level) {
   DevPattern q;
   std::memset(&q, 0, sizeof(q));
   q.len[0] = p.xy_len; q.len[1] = p.yz_len; q.len[2] = p.xz_len;
+  q.cellSize = cellSize;
+  q.level = (int8_t)level;
+  for (int r = 0; r < 3; r++) q.dpath[r] = cellSize * q.len[r];
   q.e0[0] = p.xy_x0; q.e1[0] = p.xy_y0;
   q.e0[1] = p.yz_y0; q.e1[1] = p.yz_z0;
   q.e0[2] = p.xz_x0; q.e1[2] = p.xz_z0;
@@ -307,6 +336,7 @@ struct AmrPlan {
   std::vector<int32_t> waveStart[8];  // [nkeys + 1]
   int nkeys = 0;
   int32_t* dSorted[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int32_t* dPatIdx = nullptr;         // [6][N], see AmrParams
 };
 
 // wave key = sum over the rotated axes of the leaf centre in half-finest-cell units (see header comment)
@@ -379,6 +409,9 @@ struct AmrBuffers {
   int32_t* levelOff = nullptr;
   int32_t* nb = nullptr;
   uint8_t* code = nullptr;
+  int32_t* nbc = nullptr;
+  double* kappaA = nullptr;
+  double* JA = nullptr;
   double* Iout = nullptr;
   uint8_t* done = nullptr;
   int64_t* defA = nullptr;
@@ -386,8 +419,10 @@ struct AmrBuffers {
   int32_t* defCount = nullptr;  // [2]
   std::string sizeKey;
   int batch = 0, batchNdir = 0;   // batch size chosen when the buffers were allocated, and for how many directions
+  std::string nbKey;              // grid + direction list whose neighbour tables (nb, code, nbc) the buffers hold
   void release() {
     cudaFree(pats); cudaFree(dirs); cudaFree(levelOff); cudaFree(nb); cudaFree(code); cudaFree(Iout); cudaFree(done);
+    cudaFree(nbc); cudaFree(kappaA); cudaFree(JA);
     cudaFree(defA); cudaFree(defB); cudaFree(defCount);
     *this = AmrBuffers();
   }
@@ -411,6 +446,7 @@ void amr_release(Context& c) {
   for (size_t i = 0; i < g_states.size(); i++)
     if (g_states[i].first == &c) {
       for (int k = 0; k < 8; k++) cudaFree(g_states[i].second->plan.dSorted[k]);
+      cudaFree(g_states[i].second->plan.dPatIdx);
       g_states[i].second->buffers.release();
       delete g_states[i].second;
       g_states.erase(g_states.begin() + i);
@@ -426,6 +462,22 @@ static int ensure_plan(Context& c, AmrState& S) {
   build_waves(c, S.plan);
   S.plan.balanced = grid_is_balanced(c);
   S.tablesKey.clear();
+  {
+    std::vector<int32_t> levelOff(c.maxLevel + 2, 0);
+    for (int L = 0; L <= c.maxLevel; L++) levelOff[L + 1] = levelOff[L] + (c.nx << L);
+    std::vector<int32_t> idx((size_t)6 * c.nleaf);
+    for (int64_t l = 0; l < c.nleaf; l++) {
+      const int L = c.hLevel[l], nL = c.nx << L;
+      const int p[3] = {c.hLeafX[l], c.hLeafY[l], c.hLeafZ[l]};
+      for (int a = 0; a < 3; a++) {
+        idx[(size_t)a * c.nleaf + l] = levelOff[L] + p[a];
+        idx[(size_t)(3 + a) * c.nleaf + l] = levelOff[L] + nL - 1 - p[a];
+      }
+    }
+    cudaFree(S.plan.dPatIdx);
+    RTB_CUDA(cudaMalloc((void**)&S.plan.dPatIdx, idx.size() * sizeof(int32_t)));
+    RTB_CUDA(cudaMemcpy(S.plan.dPatIdx, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
   for (int k = 0; k < 8; k++) {
     RTB_CUDA(cudaMalloc((void**)&S.plan.dSorted[k], (size_t)c.nleaf * sizeof(int32_t)));
     RTB_CUDA(cudaMemcpy(S.plan.dSorted[k], S.plan.sorted[k].data(), (size_t)c.nleaf * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -477,7 +529,7 @@ static int build_dir_tables(Context& c, int nAngularLevel, const std::vector<Dir
           }
           if (needed) return p.status;
         }
-        T.pats[(size_t)A.patBase + T.levelOff[L] + i] = to_dev(p);
+        T.pats[(size_t)A.patBase + T.levelOff[L] + i] = to_dev(p, (c.boxSize / (double)c.nx) / (double)(1 << L), L);
       }
       if (L < Lmax) {
         layer_patterns_refine(dd.phi, dd.theta, cur, next);
@@ -494,6 +546,9 @@ static int alloc_batch(AmrBuffers& B, const DirTables& T, int64_t N, int ndirBat
   RTB_CUDA(cudaMalloc((void**)&B.levelOff, T.levelOff.size() * sizeof(int32_t)));
   RTB_CUDA(cudaMalloc((void**)&B.nb, (size_t)ndirBatch * 3 * N * sizeof(int32_t)));
   RTB_CUDA(cudaMalloc((void**)&B.code, (size_t)ndirBatch * 3 * N));
+  RTB_CUDA(cudaMalloc((void**)&B.nbc, (size_t)ndirBatch * 4 * N * sizeof(int32_t)));
+  RTB_CUDA(cudaMalloc((void**)&B.kappaA, (size_t)3 * N * sizeof(double)));
+  RTB_CUDA(cudaMalloc((void**)&B.JA, (size_t)3 * N * sizeof(double)));
   RTB_CUDA(cudaMalloc((void**)&B.Iout, (size_t)ndirBatch * N * 9 * sizeof(double)));
   RTB_CUDA(cudaMalloc((void**)&B.done, (size_t)ndirBatch * N));
   RTB_CUDA(cudaMalloc((void**)&B.defA, (size_t)defCap * sizeof(int64_t)));
@@ -505,7 +560,7 @@ static int alloc_batch(AmrBuffers& B, const DirTables& T, int64_t N, int ndirBat
 static int choose_batch(Context& c, int ndir) {
   size_t freeB = 0, totalB = 0;
   cudaMemGetInfo(&freeB, &totalB);
-  const double perDir = (double)c.nleaf * (9 * 8 + 1 + 3 * 4 + 3 + 16) + 1e6;
+  const double perDir = (double)c.nleaf * (9 * 8 + 1 + 3 * 4 + 3 + 16 + 16) + 1e6;
   int nb = (int)std::max(1.0, std::min((double)ndir, 0.5 * (double)freeB / perDir));
   if (c.tune.amrBatch > 0) nb = std::min(nb, c.tune.amrBatch);
   return nb;
@@ -527,12 +582,17 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int d0, int nd
   P.child = c.tree.child; P.lx = c.tree.leafX; P.ly = c.tree.leafY; P.lz = c.tree.leafZ; P.level = c.dLevel;
   P.kappa = c.dKappa; P.pats = B.pats; P.levelOff = B.levelOff; P.dirs = B.dirs; P.nb = B.nb; P.code = B.code;
   P.Iout = B.Iout; P.done = B.done; P.J = dJ; P.err = c.dErr; P.N = N; P.n = c.nx; P.maxLevel = c.maxLevel;
+  P.nbc = B.nbc; P.patIdx = S.plan.dPatIdx; P.kappaA = B.kappaA; P.JA = B.JA;
   P.u0 = uvb[0]; P.u1 = uvb[1]; P.u2 = uvb[2];
   P.cellSize0 = c.boxSize / (double)c.nx;  // equiSources.f90:1570
-  {
+  // neighbour threading is geometry only (grid + directions): when one batch holds every direction of the call, the
+  // tables stay valid across the outer transport <-> chemistry iterations
+  const bool wholeCall = d0 == 0 && nd == (int)T.dirs.size();
+  if (!(wholeCall && !S.tablesKey.empty() && B.nbKey == S.tablesKey)) {
     dim3 grid((unsigned)((N + 127) / 128), nd);
     amr_neighbour_kernel<<<grid, 128, 0, s>>>(P, nd);
     (*launches)++;
+    B.nbKey = wholeCall ? S.tablesKey : std::string();
   }
   WaveParams Wp;
   for (int k = 0; k < 8; k++) Wp.sorted[k] = S.plan.dSorted[k];
@@ -618,15 +678,25 @@ int diffuse_amr(Context& c, int nAngularLevel, const double* uvb, const std::vec
     snprintf(buf, sizeof(buf), "%d:%lld:%d:%lld", T.perDir, (long long)N, batch, (long long)defCap);
     if (B.sizeKey != buf) {
       B.release();
-      st = alloc_batch(B, T, N, batch, defCap);
+      st = alloc_batch(B, T, N, batch, defCap);  // (release() also forgets the cached neighbour tables)
       if (st) B.release();
       else { B.sizeKey = buf; B.batch = batch; B.batchNdir = ndir; }
     }
   }
   int64_t launches = 0;
   const bool faithful = c.mathMode == RTB200_MATH_FAITHFUL;
+  const int cpyBlocks = (int)std::min<int64_t>((3 * N + 255) / 256, (int64_t)c.smCount * 16);
+  if (!st) {
+    interleave3_kernel<<<cpyBlocks, 256, 0, s>>>(c.dKappa, B.kappaA, N);
+    RTB_CUDA(cudaMemsetAsync(B.JA, 0, 3 * N * sizeof(double), s));
+    launches += 1;
+  }
   for (int d0 = 0; d0 < ndir && !st; d0 += batch)
     st = run_batch(c, S, T, d0, std::min(batch, ndir - d0), uvb, dJout, s, faithful, B, defCap, &launches);
+  if (!st) {
+    deinterleave3_kernel<<<cpyBlocks, 256, 0, s>>>(B.JA, dJout, N);
+    launches += 1;
+  }
   if (!st && nsegOut) {
     // segment count: leaves per (level, layer) times the layer's segments -- from the host tables
     std::vector<std::vector<int64_t>> hist[3];  // per physical sweep axis: [level][layer] leaf counts
