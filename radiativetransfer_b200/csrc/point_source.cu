@@ -292,7 +292,7 @@ __device__ __forceinline__ void rates_fast(const PointParams& P, const double* _
 
 // --------------------------------------------------------------------------------------------------------------------
 template <bool FAITHFUL, bool PORTABLE, bool TRACE, bool SEGMENTED>
-__global__ void __launch_bounds__(128) point_march_kernel(const __grid_constant__ PointParams P, int pixelLevel) {
+__global__ void __launch_bounds__(128, 4) point_march_kernel(const __grid_constant__ PointParams P, int pixelLevel) {
   const int64_t npix = 12LL << (2 * (pixelLevel - 1));
   const int64_t ipix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int s = blockIdx.y;

@@ -100,3 +100,17 @@ def test_workload_leaf_order_matches_preorder(oracle):
             for k in range(4):
                 rec(0, i, j, k)
     assert np.array_equal(np.array(lv, dtype=np.int8), g["level"])
+
+
+def test_point_entry_points_reject_bad_arguments_without_a_device(build_product):
+    """argument checks that come before any CUDA call: usable on a CPU-only box"""
+    import ctypes as C
+    from radiativetransfer_b200 import _lib
+    L = _lib.lib()
+    n = C.c_int64(0)
+    assert L.rtb200_point(None, 0, None, None, None, 0.0, None, 0, 6, 0, None, None, None, None, None, None, None, None,
+                          None, None, None, None, C.byref(n)) == 12          # RTB200_ERR_ARG
+    assert L.rtb200_point_device(None, 0, None, None, None, 0.0, None, 0, 6, 0, None, None, None, None, None, None,
+                                 None, None, C.byref(n)) == 12
+    assert L.rtb200_point_tables(None, 0, None, None, None, 0.0, None, 1, 0.0, None) == 12
+    assert b"idepth" in L.rtb200_status_string(11)

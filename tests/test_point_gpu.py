@@ -269,3 +269,25 @@ def test_segmented_deposition_is_deterministic_and_atomic_free(rt, engine, porta
     with pytest.raises(rt.RTB200Error):
         engine.point(spectra, leaves, wts, dust_approximation=1)
     engine.set_tuning(point_record_cap=0, point_deposit=0)
+
+
+def test_edge_cases(rt, engine, spectra):
+    """empty source list, all weights zero, a single pixel level, a source in a corner leaf of a 1^3 grid, bad arguments"""
+    g = W.uniform_grid(6, seed=2, tau_lo=1e-2, tau_hi=1.0, beta24=S24)
+    _set(engine, g)
+    r = engine.point(spectra, [], [])
+    assert r["nseg"] == 0 and np.all(r["rates"] == 0) and r["ndot_remaining"].shape == (0, 7)
+    r = engine.point(spectra, [5, 7], [0, 0])
+    assert r["nseg"] == 0 and np.all(r["rates"] == 0) and np.all(r["ndot_boundary"] == 0)
+    r = engine.point(spectra, [100], [1], max_pixel_level=1)
+    assert r["nseg"] > 0 and np.isclose(r["ndot_boundary"][0, -1], 1.0, rtol=1e-12)
+    with pytest.raises(rt.RTB200Error):
+        engine.point(spectra, [6 ** 3], [1])                # leaf out of range
+    with pytest.raises(rt.RTB200Error):
+        engine.point(spectra, [0], [1], max_pixel_level=9)  # beyond the supported pixel levels
+    with pytest.raises(rt.RTB200Error):
+        engine.point(spectra, [0], [1], dust_approximation=3)
+    g1 = W.uniform_grid(1, seed=3, tau_lo=1e-2, tau_hi=1.0, beta24=S24)
+    _set(engine, g1)
+    r = engine.point(spectra, [0], [4])
+    assert r["nseg"] == 12 and np.isclose(r["ndot_boundary"][0, -1], 4.0, rtol=1e-12)   # 12 base rays, one cell each
