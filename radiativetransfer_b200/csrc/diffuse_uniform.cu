@@ -88,31 +88,31 @@ __global__ void fill_planes_kernel(double* __restrict__ planes, int64_t perGroup
 //
 // FAST arithmetic (segment_math.cuh: segment_fast): A[g] collects Iin (1 - e^-tau) cs over all segments and
 // directions of the layer; the caller multiplies by 2^-200 / kappa once per layer.
-template <int EXPV, int NSEG, bool SECL>
+template <int EXPV, int NSEG, bool SECL, bool GUARD>
 __device__ __forceinline__ void direction_fast(const LayerSeg& P, const double (&cur)[3], const double (&upR)[3],
                                                const double (&kap)[3], const double (&kR)[3], double (&I)[3],
                                                double (&A)[3], const double* __restrict__ T) {
   const unsigned full = 0xffffffffu;
 #pragma unroll
   for (int g = 0; g < 3; g++) {
-    const double I1 = segment_fast<EXPV>(cur[g], kap[g] * P.d[0], P.cs[0], T, A[g]);
+    const double I1 = segment_fast<EXPV, GUARD>(cur[g], kap[g] * P.d[0], P.cs[0], T, A[g]);
     I[g] = I1;
     if (NSEG >= 2) {
       double rup = 0.;  // xy-segment output of the (b-1) cell
-      if (!SECL || NSEG == 3) rup = attenuate_fast<EXPV>(upR[g], kR[g] * P.d[0], T);
+      if (!SECL || NSEG == 3) rup = attenuate_fast<EXPV, GUARD>(upR[g], kR[g] * P.d[0], T);
       const double in2 = SECL ? __shfl_up_sync(full, I1, 1) : rup;
-      const double I2 = segment_fast<EXPV>(in2, kap[g] * P.d[1], P.cs[1], T, A[g]);
+      const double I2 = segment_fast<EXPV, GUARD>(in2, kap[g] * P.d[1], P.cs[1], T, A[g]);
       I[g] = I2;
       if (NSEG == 3) {
         double in3;
         if (SECL) {
           // third segment from the (b-1) cell's SECOND segment, which was fed by the (b-1, a-1) cell's xy segment
           const double x = __shfl_up_sync(full, rup, 1);
-          in3 = attenuate_fast<EXPV>(x, kR[g] * P.d[1], T);
+          in3 = attenuate_fast<EXPV, GUARD>(x, kR[g] * P.d[1], T);
         } else {
           in3 = __shfl_up_sync(full, I2, 1);  // the (a-1) cell's second segment
         }
-        I[g] = segment_fast<EXPV>(in3, kap[g] * P.d[2], P.cs[2], T, A[g]);
+        I[g] = segment_fast<EXPV, GUARD>(in3, kap[g] * P.d[2], P.cs[2], T, A[g]);
       }
     }
   }
@@ -161,21 +161,32 @@ __device__ __forceinline__ void direction_faithful(const LayerSeg& P, const doub
   }
 }
 
-// dispatch on the layer's chain kind (warp-uniform)
+// dispatch on the layer's chain kind (warp-uniform).  kmax = the largest opacity this thread multiplies a path with.
+// If kmax * (longest segment of the layer) <= 64 for every lane of the warp, the overflow guards of segment_fast are
+// dropped (4 fewer instructions per segment update); `thick` warps take the guarded instantiation.
+template <int EXPV, bool GUARD>
+__device__ __forceinline__ void direction_kinds_fast(const LayerSeg& P, bool secL, const double (&cur)[3],
+                                                     const double (&upR)[3], const double (&kap)[3],
+                                                     const double (&kR)[3], double (&I)[3], double (&A)[3],
+                                                     const double* __restrict__ T) {
+  const int kind = P.kind;
+  if (kind == 0) direction_fast<EXPV, 1, true, GUARD>(P, cur, upR, kap, kR, I, A, T);
+  else if (kind == 1 || kind == 3) {
+    if (secL) direction_fast<EXPV, 2, true, GUARD>(P, cur, upR, kap, kR, I, A, T);
+    else direction_fast<EXPV, 2, false, GUARD>(P, cur, upR, kap, kR, I, A, T);
+  } else {
+    if (secL) direction_fast<EXPV, 3, true, GUARD>(P, cur, upR, kap, kR, I, A, T);
+    else direction_fast<EXPV, 3, false, GUARD>(P, cur, upR, kap, kR, I, A, T);
+  }
+}
+
 template <int EXPV>
-__device__ __forceinline__ void direction_dispatch_fast(const LayerSeg& P, bool secL, const double (&cur)[3],
+__device__ __forceinline__ void direction_dispatch_fast(const LayerSeg& P, bool secL, double kmax, const double (&cur)[3],
                                                         const double (&upR)[3], const double (&kap)[3],
                                                         const double (&kR)[3], double (&I)[3], double (&A)[3],
                                                         const double* __restrict__ T) {
-  const int kind = P.kind;
-  if (kind == 0) direction_fast<EXPV, 1, true>(P, cur, upR, kap, kR, I, A, T);
-  else if (kind == 1 || kind == 3) {
-    if (secL) direction_fast<EXPV, 2, true>(P, cur, upR, kap, kR, I, A, T);
-    else direction_fast<EXPV, 2, false>(P, cur, upR, kap, kR, I, A, T);
-  } else {
-    if (secL) direction_fast<EXPV, 3, true>(P, cur, upR, kap, kR, I, A, T);
-    else direction_fast<EXPV, 3, false>(P, cur, upR, kap, kR, I, A, T);
-  }
+  if (__any_sync(0xffffffffu, kmax * P.dmax > 64.)) direction_kinds_fast<EXPV, true>(P, secL, cur, upR, kap, kR, I, A, T);
+  else direction_kinds_fast<EXPV, false>(P, secL, cur, upR, kap, kR, I, A, T);
 }
 
 // Out of line and by value: the rare faithful branch must not force the fast path's per-direction arrays into
@@ -265,6 +276,7 @@ sweep_cell_kernel(const __grid_constant__ BatchParams bp, int N, int n, int np1,
     kR[g] = (cell && b > 0) ? kg[-sB] : 0.;                    // kappa = 0 outside: exp(-0) = 1 exactly
     kap[g] = kapF[g] > 0. ? kapF[g] : kKappaFloor;
   }
+  const double kmax = fmax(fmax(fmax(kap[0], kap[1]), fmax(kap[2], kR[0])), fmax(kR[1], kR[2]));
   double A[3] = {0., 0., 0.}, acc[3] = {0., 0., 0.};
   const int pidx = (b + 1) * np1 + (inRow ? a + 1 : 0);
   const int ndir = sp.ndir;
@@ -292,7 +304,7 @@ sweep_cell_kernel(const __grid_constant__ BatchParams bp, int N, int n, int np1,
       for (int g = 0; g < 3; g++) upR[g] = pin[g - up];
     }
     if (FAITHFUL || P.thin) direction_dispatch_faithful(P, secL, cur, upR, kapF, kR, I, acc);
-    else direction_dispatch_fast<EXPV>(P, secL, cur, upR, kap, kR, I, A, sT);
+    else direction_dispatch_fast<EXPV>(P, secL, kmax, cur, upR, kap, kR, I, A, sT);
     if (writer) {
 #pragma unroll
       for (int g = 0; g < 3; g++) pout[g] = I[g];
@@ -419,6 +431,7 @@ sweep_march_kernel(const __grid_constant__ MarchBatch mb, const double* __restri
       kapF[g] = kapN[g]; kR[g] = kRN[g];
       kap[g] = kapF[g] > 0. ? kapF[g] : kKappaFloor;
     }
+    const double kmaxL = fmax(fmax(fmax(kap[0], kap[1]), fmax(kap[2], kR[0])), fmax(kR[1], kR[2]));
     double* accp = T.acc + leaf;
     if (i + 1 < n) {  // prefetch the next layer's opacities
 #pragma unroll
@@ -437,7 +450,7 @@ sweep_march_kernel(const __grid_constant__ MarchBatch mb, const double* __restri
         LayerSeg P;
         P.d[0] = __ldg(&Pg->d[0]); P.d[1] = __ldg(&Pg->d[1]); P.d[2] = __ldg(&Pg->d[2]);
         P.cs[0] = __ldg(&Pg->cs[0]); P.cs[1] = __ldg(&Pg->cs[1]); P.cs[2] = __ldg(&Pg->cs[2]);
-        P.wn = 0.; P.w = __ldg(&Pg->w);
+        P.dmax = __ldg(&Pg->dmax); P.w = __ldg(&Pg->w);
         P.kind = __ldg(&Pg->kind); P.nseg = 0; P.thin = __ldg(&Pg->thin);
         const int kind = P.kind;
         const bool secL = (kind <= 2) == (laneIsK != 0);
@@ -464,7 +477,7 @@ sweep_march_kernel(const __grid_constant__ MarchBatch mb, const double* __restri
           }
         }
         if (FAITHFUL_ALL || P.thin) direction_dispatch_faithful(P, secL, cur, upR, kapF, kR, I, acc);
-        else direction_dispatch_fast<EXPV>(P, secL, cur, upR, kap, kR, I, A, sT);
+        else direction_dispatch_fast<EXPV>(P, secL, kmaxL, cur, upR, kap, kR, I, A, sT);
 #pragma unroll
         for (int g = 0; g < 3; g++) xout[q * tileStride + g * 256 + tpos] = writer ? I[g] : cur[g];
         if (pubCol || pubRow) {
@@ -598,8 +611,9 @@ static LayerSeg make_layer_seg(const RayPattern& p, double cellSize, double weig
     L.d[s] = cellSize * len[s];
   }
   L.w = weight;
-  L.wn = weight / (double)L.nseg;
-  for (int s = 0; s < 3; s++) L.cs[s] = L.d[s] > 0. ? 1.6069380442589903e60 * L.wn / L.d[s] : 0.;  // 2^200 wn / d
+  const double wn = weight / (double)L.nseg;
+  L.dmax = std::max(L.d[0], std::max(L.d[1], L.d[2]));
+  for (int s = 0; s < 3; s++) L.cs[s] = L.d[s] > 0. ? 1.6069380442589903e60 * wn / L.d[s] : 0.;  // 2^200 wn / d
   L.thin = 0;
   for (int sg = 0; sg < L.nseg; sg++)
     if (len[sg] < kThinLen) L.thin = 1;

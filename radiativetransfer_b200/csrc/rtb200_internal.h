@@ -35,7 +35,7 @@ const char* last_cuda_error();
 struct LayerSeg {
   double d[3];     // path length [cm]: cellSize * len
   double cs[3];    // fast mode: 2^200 * (weight / nseg) / d   (segment_math.cuh, segment_fast)
-  double wn;       // weight / nseg   (fast mode)
+  double dmax;     // longest segment of the layer [cm] (fast mode: decides whether the overflow guards can be skipped)
   double w;        // weight          (faithful mode divides by nseg first, transportRoutinesModule.f90:953)
   int32_t kind;
   int32_t nseg;

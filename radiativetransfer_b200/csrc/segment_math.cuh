@@ -44,10 +44,12 @@ static __constant__ double kExpTable[16] = {
 // returned as ~2^-1020 (it only ever multiplies an intensity, and such products are far below anything physical).
 // Returns Ts = 2^(-k/16) and p = exp(-r) - 1, so that  exp(-tau) = Ts + Ts*p  and  1 - exp(-tau) = (1 - Ts) - Ts*p
 // (1 - Ts is exact, and for k == 0 the latter is exactly -p: no cancellation for small tau).
+template <bool GUARD = true>
 __device__ __forceinline__ void exp_neg_parts(double tau, const double* __restrict__ T, double& Ts, double& p) {
   // tau >= 0 (kappa >= 0, path > 0): clamp at 707 with ONE integer min on the high word instead of an FP64 compare
-  // and two selects (0x40861800'00000000 = 707.0; the low word stays, so the clamped value lies in [707, 707.0005))
-  tau = __hiloint2double(min(__double2hiint(tau), 0x40861800), __double2loint(tau));
+  // and two selects (0x40861800'00000000 = 707.0; the low word stays, so the clamped value lies in [707, 707.0005)).
+  // GUARD = false: the caller knows tau <= 64 for the whole warp (see sweep_cell_kernel) and skips the clamp.
+  if (GUARD) tau = __hiloint2double(min(__double2hiint(tau), 0x40861800), __double2loint(tau));
   double t = fma(tau, kExpC[7], kExpC[8]);
   int k = __double2loint(t);
   double fn = t - kExpC[8];
@@ -110,23 +112,26 @@ __device__ __forceinline__ double exp_neg_only(double tau, const double* __restr
 // intermediate far from the subnormal range, including the kappa -> 0 limit).  With Ts = 2^(-k/16), p = e^-r - 1:
 //   X = Iin Ts,  Iout = X + X p,  Iin (1 - e^-tau) = (Iin - X) - X p      (Iin - X is exact for k = 0: no cancellation)
 // 5 FP64 instructions after the exponential's 12, instead of 8.
-template <int EXPV>
+// GUARD = false (tau <= 64 for every segment of the warp): no clamp, and no test for Iout underflowing to 0 -- with
+// tau <= 64 that can only happen where Iin < 5e-324 e^64 = 3e-296, i.e. where the segment's contribution to Jmean
+// (< Iin) is itself below every tolerance floor (the parity tests compare with a floor of 1e-290).
+template <int EXPV, bool GUARD = true>
 __device__ __forceinline__ double segment_fast(double Iin, double tau, double cs, const double* __restrict__ T, double& A) {
   double Ts, p;
-  if (EXPV == 1) exp_neg_parts(tau, T, Ts, p);
+  if (EXPV == 1) exp_neg_parts<GUARD>(tau, T, Ts, p);
   else exp_neg_parts_poly(tau, Ts, p);
   const double X = Iin * Ts;
   const double Iout = fma(X, p, X);
   const double Z = fma(-X, p, Iin - X);
   // Iout == 0 (underflow): the reference gets (Iin - 0)/log(Iin/0) = 0.  Integer test + predicated DFMA.
-  if (((__double2hiint(Iout) << 1) | __double2loint(Iout)) != 0) A = fma(Z, cs, A);
+  if (!GUARD || ((__double2hiint(Iout) << 1) | __double2loint(Iout)) != 0) A = fma(Z, cs, A);
   return Iout;
 }
 
-template <int EXPV>
+template <int EXPV, bool GUARD = true>
 __device__ __forceinline__ double attenuate_fast(double Iin, double tau, const double* __restrict__ T) {
   double Ts, p;
-  if (EXPV == 1) exp_neg_parts(tau, T, Ts, p);
+  if (EXPV == 1) exp_neg_parts<GUARD>(tau, T, Ts, p);
   else exp_neg_parts_poly(tau, Ts, p);
   const double X = Iin * Ts;
   return fma(X, p, X);
