@@ -37,6 +37,8 @@ static void free_grid(Context& c) {
   cudaFree(c.dKappa); cudaFree(c.tree.child); cudaFree(c.tree.leafX); cudaFree(c.tree.leafY); cudaFree(c.tree.leafZ);
   cudaFree(c.dJ); cudaFree(c.dRates); c.dRates = nullptr;
   cudaFree(c.dKappaT); c.dKappaT = nullptr; c.kappaTBytes = 0;
+  for (auto& sl : c.pointPool) cudaFree(sl.first);
+  c.pointPool.clear();
   c.dLevel = nullptr; c.dHI = c.dHeI = c.dHeII = c.dRho = c.dAbun2 = c.dKappa = c.dJ = nullptr;
   c.tree = DevTree();
   c.uniPlanKey.clear();

@@ -30,6 +30,7 @@
 #include "point_host.h"
 #include "portable_math.h"
 #include "rtb200_internal.h"
+#include "segment_math.cuh"
 
 namespace rtb {
 
@@ -254,9 +255,23 @@ __device__ __forceinline__ double face_sum(const double* __restrict__ T, int iAx
 // interpolant is piecewise linear with nodes at the integers (table spacing 10/10 = 1), so
 //   log R(end) - log R(start) = sum over the crossed table cells of  (length inside the cell) * (H - L),
 // L/H = face_sum at the cell's lower/upper node; the upper face of one cell is the lower face of the next.
+// e^x for |x| <= ~700 and 1 - e^-t for t >= 0 from the sweep's table-based exponential (segment_math.cuh: 16-entry
+// shared-memory table x degree-7 polynomial, ~1e-16 relative): 14 and 15 instructions instead of libm's ~45
+__device__ __forceinline__ double exp_tab(double x, const double* __restrict__ sT) {
+  double Ts, p;
+  exp_neg_parts<false>(-x, sT, Ts, p);
+  return fma(Ts, p, Ts);
+}
+__device__ __forceinline__ double one_minus_exp_neg_tab(double t, const double* __restrict__ sT) {
+  double Ts, p;
+  exp_neg_parts<true>(t, sT, Ts, p);
+  return fma(-Ts, p, 1.0 - Ts);   // exact 1 - Ts, and for t < ln2/32 simply -p: no cancellation
+}
+
 template <int AXIS>
 __device__ __forceinline__ void rates_fast(const PointParams& P, const double* __restrict__ LT, const DepthIdx& q,
-                                           double depthAxis, double tau, double& dnum, double& dheat) {
+                                           double depthAxis, double tau, const double* __restrict__ sT, double& dnum,
+                                           double& dheat) {
   const double* R = LT + (size_t)AXIS * P.planes * kPlane;
   const double* E = LT + (size_t)(3 + AXIS) * P.planes * kPlane;
   if (tau == 0.) { dnum = 0.; dheat = 0.; return; }  // R(d) - R(d) (e.g. no helium: tau2 = tau3 = 0)
@@ -264,7 +279,7 @@ __device__ __forceinline__ void rates_fast(const PointParams& P, const double* _
   const double c0 = AXIS == 0 ? q.c1 : (AXIS == 1 ? q.c2 : q.c3);
   double Lr = face_sum<AXIS>(R, i0, q, P.dust), Hr = face_sum<AXIS>(R, i0 + 1, q, P.dust);
   double Le = face_sum<AXIS>(E, i0, q, P.dust), He = face_sum<AXIS>(E, i0 + 1, q, P.dust);
-  const double n0 = exp(fma(c0, Hr - Lr, Lr)), h0 = exp(fma(c0, He - Le, Le));
+  const double n0 = exp_tab(fma(c0, Hr - Lr, Lr), sT), h0 = exp_tab(fma(c0, He - Le, Le), sT);
   const double end = depthAxis + tau;
   if (end > 10.) { dnum = n0; dheat = h0; return; }  // the table returns 0 beyond tau = 10
   int iEnd = (int)end;
@@ -286,13 +301,17 @@ __device__ __forceinline__ void rates_fast(const PointParams& P, const double* _
       dh = fma(len, He - Le, dh);
     }
   }
-  dnum = -n0 * expm1(dn);
-  dheat = -h0 * expm1(dh);
+  // the tables fall with depth (dn, dh <= 0); a rising table (never with physical spectra) takes the libm route
+  dnum = dn <= 0. ? n0 * one_minus_exp_neg_tab(-dn, sT) : -n0 * expm1(dn);
+  dheat = dh <= 0. ? h0 * one_minus_exp_neg_tab(-dh, sT) : -h0 * expm1(dh);
 }
 
 // --------------------------------------------------------------------------------------------------------------------
 template <bool FAITHFUL, bool PORTABLE, bool TRACE, bool SEGMENTED>
 __global__ void __launch_bounds__(128, 4) point_march_kernel(const __grid_constant__ PointParams P, int pixelLevel) {
+  __shared__ double sT[16];
+  if (threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
+  __syncthreads();
   const int64_t npix = 12LL << (2 * (pixelLevel - 1));
   const int64_t ipix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int s = blockIdx.y;
@@ -523,9 +542,9 @@ __global__ void __launch_bounds__(128, 4) point_march_kernel(const __grid_consta
           for (int i = 0; i < 6; i++) dep[i] = 0.;
         } else {
           double n, h;
-          rates_fast<0>(P, LT, q, d1, tau1, n, h); dep[0] = ndot * n; dep[3] = ndot * h;
-          rates_fast<1>(P, LT, q, d2, tau2, n, h); dep[2] = ndot * n; dep[5] = ndot * h;
-          rates_fast<2>(P, LT, q, d3, tau3, n, h); dep[1] = ndot * n; dep[4] = ndot * h;
+          rates_fast<0>(P, LT, q, d1, tau1, sT, n, h); dep[0] = ndot * n; dep[3] = ndot * h;
+          rates_fast<1>(P, LT, q, d2, tau2, sT, n, h); dep[2] = ndot * n; dep[5] = ndot * h;
+          rates_fast<2>(P, LT, q, d3, tau3, sT, n, h); dep[1] = ndot * n; dep[4] = ndot * h;
         }
       }
       if (SEGMENTED) {
@@ -656,13 +675,30 @@ int dev_alloc(T** p, size_t count) {
   return RTB200_OK;
 }
 
-struct Scratch {  // freed on every exit path
-  std::vector<void*> ptrs;
-  ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+// Scratch requests of one call, served from a pool the context keeps between calls (request i reuses slot i when it
+// is large enough): no cudaMalloc / cudaFree -- and no implicit device synchronisation -- in the steady state.
+struct Scratch {
+  std::vector<std::pair<void*, size_t>>& pool;
+  size_t cursor = 0;
+  explicit Scratch(std::vector<std::pair<void*, size_t>>& p) : pool(p) {}
   template <class T> int get(T** p, size_t count) {
-    int st = dev_alloc(p, count);
-    if (!st) ptrs.push_back(*p);
-    return st;
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    if (cursor == pool.size()) pool.push_back({nullptr, 0});
+    auto& sl = pool[cursor++];
+    if (sl.second < bytes) {
+      if (sl.first) cudaFree(sl.first);
+      sl = {nullptr, 0};
+      cudaError_t e = cudaMalloc(&sl.first, bytes);
+      if (e != cudaSuccess) {
+        set_cuda_error("cudaMalloc", e, __FILE__, __LINE__);
+        sl.first = nullptr;
+        *p = nullptr;
+        return e == cudaErrorMemoryAllocation ? RTB200_ERR_NOMEM : RTB200_ERR_CUDA;
+      }
+      sl.second = bytes;
+    }
+    *p = (T*)sl.first;
+    return RTB200_OK;
   }
 };
 
@@ -685,7 +721,7 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
   if (nsegOut) *nsegOut = 0;
   if (traceLen) *traceLen = 0;
   const int nsrc = in.nsrc;
-  Scratch sc;
+  Scratch sc(c.pointPool);
   const bool portable = c.mathMode == RTB200_MATH_FAITHFUL && c.tune.portableMath;
   const bool faithful = c.mathMode == RTB200_MATH_FAITHFUL;
   const int planes = in.dust ? 11 : 1;

@@ -140,6 +140,8 @@ struct Context {
   // scratch owned by the diffuse paths (sized lazily, reused across calls)
   double* dJ = nullptr;        // [3][nleaf] result buffer for the host-pointer API
   double* dRates = nullptr;    // [6][nleaf] rate buffer of the host-pointer point-source API (lazy)
+  // scratch of the point-source path, kept between calls (request i of a call reuses slot i; freed with the grid)
+  std::vector<std::pair<void*, size_t>> pointPool;
   double* dAcc = nullptr;      // slot accumulators
   size_t accBytes = 0;
   double* dPlanes = nullptr;   // ping-pong top-exit planes
