@@ -91,6 +91,7 @@ struct PointParams {
   unsigned long long* recCount;
   long long recCap;
   int raysPerSource;      // pixels of levels 1..maxPixelLevel
+  int* queue;             // [nsrc] next pixel of the last level to hand out (NULL: static pixel -> thread map)
   // optional traversal trace (parity checks)
   long long* trace;       // [cap][2]
   unsigned long long* traceLen;
@@ -313,24 +314,37 @@ __global__ void __launch_bounds__(128, 4) point_march_kernel(const __grid_consta
   if (threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
   __syncthreads();
   const int64_t npix = 12LL << (2 * (pixelLevel - 1));
-  const int64_t ipix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t ipix0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t ipix = ipix0;
   const int s = blockIdx.y;
   unsigned long long mySegs = 0;
   const bool last = pixelLevel == P.maxPixelLevel;
-  bool active = ipix < npix;
+  // Rays of the last pixel level run to the box boundary and differ in length (22 of 32 lanes were busy on average):
+  // there a lane that has finished its ray takes the next pixel of its source from a queue, the warp stays full until
+  // the queue is empty.  The earlier levels end at the split radius and keep the static pixel -> thread map.
+  const bool refill = last && P.queue != nullptr;
   const int weight = __ldg(P.srcWeight + s);
-  if (weight <= 0) active = false;
 
   Cell c{0, 0, 0, 0, 0};
   double px = 0.5, py = 0.5, pz = 0.5, radius = 0., d1 = 0., d2 = 0., d3 = 0., dD = 0.;
+  double prox = 0., proy = 0., proz = 1.;
   // ndot1 = float(weight) / 12.d0, then / 4.d0 per split level (exact)
-  double ndot = M(D((double)(float)weight, 12.), 1.0 / (double)(1LL << (2 * (pixelLevel - 1))));
+  const double ndot = M(D((double)(float)weight, 12.), 1.0 / (double)(1LL << (2 * (pixelLevel - 1))));
   double* diag = P.diag + (size_t)s * kDiagStride;
   const double fnx = (double)(float)P.nx;
-  int strategy = 1;
+  int strategy = 0;      // 0 = no ray, 1 = proceed, 2 = split, 3 = boundary / dead
   int irLow = 0;
+  unsigned raySeg = 0;   // index of the current segment along its ray
 
-  if (active) {
+  // start of ray `ip` of this level; false when the ray does not exist (parent not split, start outside the box, ...)
+  auto init_ray = [&](int64_t ip) -> bool {
+  ipix = ip;
+  bool active = true;
+  c = Cell{0, 0, 0, 0, 0};
+  px = 0.5; py = 0.5; pz = 0.5; radius = 0.; d1 = 0.; d2 = 0.; d3 = 0.; dD = 0.;
+  irLow = 0;
+  raySeg = 0;
+  {
     if (pixelLevel == 1) {
       c.leaf = __ldg(P.srcLeaf + s);
     } else {
@@ -409,11 +423,41 @@ __global__ void __launch_bounds__(128, 4) point_march_kernel(const __grid_consta
       c.X = __ldg(P.leafX + c.leaf); c.Y = __ldg(P.leafY + c.leaf); c.Z = __ldg(P.leafZ + c.leaf);
     }
     const double* dir = P.pixDir + 3 * (pix_offset(pixelLevel) + ipix);
-    const double prox = __ldg(dir), proy = __ldg(dir + 1), proz = __ldg(dir + 2);
-    const double* LT = P.logTab + (size_t)s * 6 * P.planes * kPlane;
-    const double rmaxL = P.rmax[pixelLevel];
+    prox = __ldg(dir); proy = __ldg(dir + 1); proz = __ldg(dir + 2);
+  }
+  return active;
+  };  // init_ray
 
-    while (strategy == 1) {
+  const double* LT = P.logTab + (size_t)s * 6 * P.planes * kPlane;
+  const double rmaxL = P.rmax[pixelLevel];
+  bool have0 = false;      // static map: this thread's own ray exists
+  bool exhausted = weight <= 0;
+  if (!refill) {
+    have0 = ipix0 < npix && weight > 0 && init_ray(ipix0);
+    strategy = have0 ? 1 : 0;
+  }
+  {
+    for (;;) {
+      if (refill) {
+        const unsigned full = 0xffffffffu;
+        const bool want = strategy != 1 && !exhausted;
+        const unsigned idle = __ballot_sync(full, want);
+        if (idle) {
+          const int lane = threadIdx.x & 31, leader = __ffs(idle) - 1;
+          int base = 0;
+          if (lane == leader) base = atomicAdd(P.queue + s, __popc(idle));
+          base = __shfl_sync(full, base, leader);
+          if (want) {
+            const int64_t ip = base + __popc(idle & ((1u << lane) - 1u));
+            if (ip < npix) strategy = init_ray(ip) ? 1 : 0;
+            else exhausted = true;
+          }
+        }
+        if (__ballot_sync(full, strategy == 1 || !exhausted) == 0) break;
+        if (strategy != 1) continue;
+      } else if (strategy != 1) {
+        break;
+      }
       const double oldRadius = radius;
       // ---- drawSegment (:2412-2595) ----
       const double tmp1 = proz > 0. ? D(S(1., pz), proz) : D(-pz, proz);
@@ -452,7 +496,8 @@ __global__ void __launch_bounds__(128, 4) point_march_kernel(const __grid_consta
         if (!inside) strategy = 3;
         else if (px < 0. || px > 1. || py < 0. || py > 1. || pz < 0. || pz > 1.) {
           atomicExch(P.err, RTB200_ERR_CHECKPOINT);
-          break;
+          strategy = 3;
+          continue;
         }
       } else if (M(radius, scale) >= rmaxL) {
         strategy = 2;
@@ -465,12 +510,13 @@ __global__ void __launch_bounds__(128, 4) point_march_kernel(const __grid_consta
         px = A(px, M(tmp, prox)); py = A(py, M(tmp, proy)); pz = A(pz, M(tmp, proz));
       }
       mySegs++;
+      raySeg++;
       if (TRACE) {
         const unsigned long long slot = atomicAdd(P.traceLen, 1ULL);
         if ((long long)slot < P.traceCap) {
           P.trace[2 * slot] = ((long long)here.leaf << 32) | ((long long)pixelLevel << 28) | ((long long)ipix << 8) | face;
           P.trace[2 * slot + 1] = ((long long)s << 52) | ((long long)pixelLevel << 48) | ((long long)ipix << 24) |
-                                  (long long)(mySegs - 1);
+                                  (long long)(raySeg - 1);
         }
       }
 
@@ -534,10 +580,10 @@ __global__ void __launch_bounds__(128, 4) point_march_kernel(const __grid_consta
         if (!st) st = rates_faithful<PORTABLE>(P, LT, 2, d1, d2, d3, dD, a, ea);
         if (!st) st = rates_faithful<PORTABLE>(P, LT, 2, d1, d2, A(d3, tau3), dD, b, eb);
         dep[1] = M(ndot, S(a, b)); dep[4] = M(ndot, S(ea, eb));
-        if (st) { atomicExch(P.err, st); break; }
+        if (st) { atomicExch(P.err, st); strategy = 3; continue; }
       } else {
         const DepthIdx q = depth_index_fast(d1, d2, d3, dD, P.dust);
-        if (q.status < 0) { atomicExch(P.err, RTB200_ERR_IDEPTH); break; }
+        if (q.status < 0) { atomicExch(P.err, RTB200_ERR_IDEPTH); strategy = 3; continue; }
         if (q.status == 1) {
           for (int i = 0; i < 6; i++) dep[i] = 0.;
         } else {
@@ -557,7 +603,7 @@ __global__ void __launch_bounds__(128, 4) point_march_kernel(const __grid_consta
         const long long slot = (long long)(base + __popc(m & ((1u << lane) - 1u)));
         if (slot < P.recCap) {
           const long long ray = (long long)s * P.raysPerSource + pix_offset(pixelLevel) + ipix;
-          const long long seg = mySegs - 1 < 4095 ? (long long)(mySegs - 1) : 4095;
+          const long long seg = raySeg - 1 < 4095 ? (long long)(raySeg - 1) : 4095;
           P.recKey[slot] = ((long long)lf << 32) | ((ray & 0xFFFFF) << 12) | seg;
 #pragma unroll
           for (int i = 0; i < 6; i++) P.recVal[(size_t)i * P.recCap + slot] = dep[i];
@@ -576,12 +622,12 @@ __global__ void __launch_bounds__(128, 4) point_march_kernel(const __grid_consta
   for (int o = 16; o; o >>= 1) mySegs += __shfl_down_sync(0xffffffffu, mySegs, o);
   if ((threadIdx.x & 31) == 0 && mySegs) atomicAdd(P.nseg, mySegs);
 
-  if (!last && ipix < npix) {
+  if (!last && ipix0 < npix) {
     RayState out;
     out.x = px; out.y = py; out.z = pz; out.radius = radius; out.d1 = d1; out.d2 = d2; out.d3 = d3; out.dD = dD;
-    out.leaf = c.leaf; out.strategy = (active && strategy == 2) ? 2 : 3;
+    out.leaf = c.leaf; out.strategy = (have0 && strategy == 2) ? 2 : 3;
     out.pad[0] = out.pad[1] = 0;
-    P.stateOut[(size_t)s * npix + ipix] = out;
+    P.stateOut[(size_t)s * npix + ipix0] = out;
   }
 }
 
@@ -806,6 +852,8 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
   if (int st = sc.get(&dStB, (size_t)batch * npixMax)) return st;
   long long* dTrace = nullptr;
   if (hTrace && traceCap > 0) { if (int st = sc.get(&dTrace, (size_t)traceCap * 2)) return st; }
+  int* dQueue = nullptr;   // per-source pixel cursor of the last level (lane refill)
+  if (int st = sc.get(&dQueue, (size_t)batch)) return st;
   // segmented deposition: record buffers sized from the free memory (76 B per record incl. the sort's double buffers)
   const bool segmented = c.tune.pointDeposit == 1 && !dTrace;
   long long recCap = 0;
@@ -879,6 +927,19 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
       const int64_t npix = 12LL << (2 * (L - 1));
       P.stateIn = stIn; P.stateOut = stOut;
       dim3 g((unsigned)((npix + 127) / 128), nb);
+      P.queue = nullptr;
+      if (L == in.maxPixelLevel && c.tune.pointRefill && npix >= 1024) {
+        // last level: fewer threads than rays, every lane takes pixels from its source's queue until it is empty;
+        // rays per thread ~ what keeps the device twice over-subscribed, at most 8
+        const double resident = (double)c.smCount * 512.0;
+        const int perThread = (int)std::max(1.0, std::min(8.0, (double)npix * nb / (2.0 * resident)));
+        if (perThread > 1) {
+          const int64_t threads = ((npix + perThread - 1) / perThread + 31) / 32 * 32;
+          g.x = (unsigned)((threads + 127) / 128);
+          RTB_CUDA(cudaMemsetAsync(dQueue, 0, (size_t)nb * sizeof(int), s));
+          P.queue = dQueue;
+        }
+      }
       if (dTrace) {
         if (portable) point_march_kernel<true, true, true, false><<<g, 128, 0, s>>>(P, L);
         else if (faithful) point_march_kernel<true, false, true, false><<<g, 128, 0, s>>>(P, L);

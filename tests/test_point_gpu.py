@@ -177,6 +177,12 @@ def test_sources_accumulate_and_shard(engine, portable, spectra):
     b = engine.point(spectra, leaves[3:], wts[3:], rates=a["rates"])
     assert b["nseg"] + a["nseg"] == full["nseg"]
     assert rel_err(b["rates"], full["rates"], floor=1e-300) < 1e-12
+    engine.set_tuning(point_refill=1)              # last level: lanes take pixels from a queue (other ray -> lane map)
+    d = engine.point(spectra, np.repeat(leaves, 3), np.repeat(wts, 3))   # enough rays for the queue to be used
+    engine.set_tuning(point_refill=0)
+    e = engine.point(spectra, np.repeat(leaves, 3), np.repeat(wts, 3))
+    assert d["nseg"] == e["nseg"] == 3 * full["nseg"]
+    assert rel_err(d["rates"], e["rates"], floor=1e-300) < 1e-12
     engine.set_tuning(point_batch=2)               # batching of sources does not change anything
     c = engine.point(spectra, leaves, wts)
     assert rel_err(c["rates"], full["rates"], floor=1e-300) < 1e-12
