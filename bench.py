@@ -37,7 +37,7 @@ UNIT = "segment-updates/s"
 # dram__bytes_write.sum of ONE launch, bytes (compare with roofline.algorithmic_bytes_per_launch)
 NCU_TRAFFIC_BYTES = {
     "diffuse-256^3-uniform-192dir": 324.15e6 + 312.43e6,   # sweep_cell_kernel, one layer of all 32 zone tasks (r01e)
-    "point-128^3-amr-100src": 5.62e6 + 2.70e6,             # point_march_kernel, pixel level 6 of 100 sources
+    "point-128^3-amr-100src": 5.51e6 + 2.66e6,             # point_march_kernel, pixel level 6 of 100 sources (r01b)
 }
 
 WORKLOADS = {
