@@ -710,17 +710,6 @@ __global__ void gather_kernel(const double* __restrict__ src, const int32_t* __r
   if (i < n) out[i] = src[idx[i]];
 }
 
-template <class T>
-int dev_alloc(T** p, size_t count) {
-  cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
-  if (e != cudaSuccess) {
-    set_cuda_error("cudaMalloc", e, __FILE__, __LINE__);
-    *p = nullptr;
-    return e == cudaErrorMemoryAllocation ? RTB200_ERR_NOMEM : RTB200_ERR_CUDA;
-  }
-  return RTB200_OK;
-}
-
 // Scratch requests of one call, served from a pool the context keeps between calls (request i reuses slot i when it
 // is large enough): no cudaMalloc / cudaFree -- and no implicit device synchronisation -- in the steady state.
 struct Scratch {
