@@ -165,3 +165,124 @@ def read_grid_dat(path, metals=False, kinematics=False):
     if next(it, None) is not None:
         raise ValueError("trailing records: wrong metals / kinematics flags?")
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# octree from the per-level cell lists of the input grid (equiSources.f90:425-618 + placeCellProjectWithVelocity :1870-1974)
+# ----------------------------------------------------------------------------------------------------------------------
+_F = np.float32
+_PSI = float(_F(0.76))                       # definitionsModule.f90:261
+_MP = float(_F(1.6726231e-24))
+_MN = float(_F(1.67492728e-24))
+_MHE = 2.0 * (_MP + _MN)
+_KPC = float(_F(1.e3)) * float(_F(3.08568025e18))
+_STATE = ("tgas", "rho", "HI", "HeI", "HeII", "abun2")
+
+
+def _pow10(a):
+    """10.**x through the C library's pow (what gfortran calls), element by element: numpy's vectorised power loop can
+    differ from it in the last bit"""
+    a = np.asarray(a, dtype=np.float32).astype(np.float64)
+    return np.frompyfunc(lambda v: 10.0 ** v, 1, 1)(a).astype(np.float64)
+
+
+def build_leaves(levels, metals=False):
+    """Leaf arrays in `writeCell` order from the per-level lists of `read_grid_dat` (positions in kpc).
+
+    Follows the driver: level 1 must hold n^3 cells (:427-436); the box is the level-1 min/max stretched by n/(n-1)
+    (:455-477) and positions are normalised and stored back in SINGLE precision (:483-489); a level-l cell is dropped
+    into the tree by descending l-1 times with `.lt.0.5` tests, and children created on the way inherit tgas, rho, HI,
+    HeI, HeII of their parent and get abun2 = 0 (:1882-1932); the target cell takes tgas = 10**lT, nH = 10**lnH,
+    HI = nH 10**lx, rho = nH mh/psi, HeI = (1-psi) rho/mhe, HeII = 0, abun2 = abun(:,2) or 0.02 (:1935-1959).
+    Returns the keyword arguments of `Transport.set_grid` plus `tgas`."""
+    n1 = levels[0]["pos"].shape[0]
+    nx = int(round(n1 ** (1.0 / 3.0)))
+    if nx ** 3 != n1:
+        raise ValueError("base grid needs to be of size n^3")
+    p1 = np.asarray(levels[0]["pos"], dtype=np.float32).astype(np.float64)
+    lo, hi = p1.min(axis=0), p1.max(axis=0)
+    mid, half = 0.5 * (lo + hi), 0.5 * (hi - lo) * float(nx) / float(nx - 1) if nx > 1 else 0.5 * (hi - lo)
+    a, b = mid - half, mid + half
+    box_size = abs(a[0] - b[0]) * _KPC
+    # per depth: packed integer coordinates -> row of the depth's state table
+    index = [dict() for _ in levels]
+    state = [dict((k, np.zeros(0)) for k in _STATE) for _ in levels]
+    refined = [set() for _ in levels]            # packed coordinates of refined nodes per depth
+
+    def pack(ix, iy, iz, depth):
+        m = nx << depth
+        return (ix * m + iy) * m + iz
+
+    def append(depth, keys, vals):
+        base = state[depth]["rho"].size
+        for j, k in enumerate(keys):
+            index[depth][int(k)] = base + j
+        for name in _STATE:
+            state[depth][name] = np.concatenate([state[depth][name], vals[name]])
+
+    # depth 0: every base cell exists, zero state (:495-520)
+    ii, jj, kk = np.meshgrid(np.arange(nx), np.arange(nx), np.arange(nx), indexing="ij")
+    append(0, pack(ii.ravel(), jj.ravel(), kk.ravel(), 0), dict((k, np.zeros(nx ** 3)) for k in _STATE))
+    for depth, lv in enumerate(levels):
+        pos = np.asarray(lv["pos"], dtype=np.float32).astype(np.float64)
+        pn = ((pos - a) / (b - a)).astype(np.float32).astype(np.float64)      # stored back as real*4
+        base_i = (pn * nx).astype(np.int64)                                    # int(x0*nx)
+        if np.any(base_i < 0) or np.any(base_i >= nx):
+            raise ValueError("cell outside the box")
+        frac = pn * float(nx) - base_i.astype(np.float64)
+        coords = [base_i.copy()]
+        for _ in range(depth):                                                 # `.lt.0.5` descents
+            bit = (frac >= 0.5).astype(np.int64)
+            frac = 2.0 * frac - bit
+            coords.append(2 * coords[-1] + bit)
+        # create the path: the ancestor at depth t-1 must be refined, missing children inherit its state
+        for t in range(1, depth + 1):
+            par = np.unique(pack(coords[t - 1][:, 0], coords[t - 1][:, 1], coords[t - 1][:, 2], t - 1))
+            new = np.array([p for p in par if int(p) not in refined[t - 1]], dtype=np.int64)
+            if new.size == 0:
+                continue
+            for p in new:
+                refined[t - 1].add(int(p))
+            m = nx << (t - 1)
+            px, py, pz = new // (m * m), (new // m) % m, new % m
+            rows = np.array([index[t - 1][int(p)] for p in new])
+            o = np.arange(8)
+            cx = (2 * px[:, None] + (o >> 2)).ravel(); cy = (2 * py[:, None] + ((o >> 1) & 1)).ravel()
+            cz = (2 * pz[:, None] + (o & 1)).ravel()
+            vals = dict((k, np.repeat(state[t - 1][k][rows], 8)) for k in _STATE)
+            vals["abun2"] = np.zeros(8 * new.size)                             # :1907 children start with abun2 = 0
+            append(t, pack(cx, cy, cz, t), vals)
+        # assign the cells of this level (a later duplicate overwrites an earlier one, as the sequential loop does)
+        nH = _pow10(lv["lnH"])
+        rho = nH * _MP / _PSI
+        vals = dict(tgas=_pow10(lv["lT"]), rho=rho, HI=nH * _pow10(lv["lx"]),
+                    HeI=(1.0 - _PSI) * rho / _MHE * 1.0, HeII=np.zeros(nH.size),
+                    abun2=np.asarray(lv["abun"], dtype=np.float32)[:, 1].astype(np.float64) if metals
+                    else np.full(nH.size, float(_F(0.02))))
+        keys = pack(coords[depth][:, 0], coords[depth][:, 1], coords[depth][:, 2], depth)
+        rows = np.array([index[depth][int(k)] for k in keys])
+        for name in _STATE:
+            state[depth][name][rows] = vals[name]
+    # leaves in pre-order: sort by (base cell, octant digits)
+    lmax = len(levels) - 1
+    out_keys, out_level, out_vals = [], [], dict((k, []) for k in _STATE)
+    for depth in range(len(levels)):
+        if not index[depth]:
+            continue
+        keys = np.array([k for k in index[depth] if k not in refined[depth]], dtype=np.int64)
+        if keys.size == 0:
+            continue
+        rows = np.array([index[depth][int(k)] for k in keys])
+        m = nx << depth
+        x, y, z = keys // (m * m), (keys // m) % m, keys % m
+        key = ((x >> depth) * nx + (y >> depth)) * nx + (z >> depth)
+        for d in range(depth - 1, -1, -1):
+            key = (key << 3) | ((((x >> d) & 1) << 2) | (((y >> d) & 1) << 1) | ((z >> d) & 1))
+        out_keys.append(key << (3 * (lmax - depth)))
+        out_level.append(np.full(keys.size, depth, dtype=np.int8))
+        for name in _STATE:
+            out_vals[name].append(state[depth][name][rows])
+    order = np.argsort(np.concatenate(out_keys), kind="stable")
+    res = dict((k, np.concatenate(v)[order]) for k, v in out_vals.items())
+    return dict(nx=nx, level=np.concatenate(out_level)[order], HI=res["HI"], HeI=res["HeI"], HeII=res["HeII"],
+                rho=res["rho"], abun2=res["abun2"], box_size=box_size, tgas=res["tgas"])

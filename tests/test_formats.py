@@ -54,3 +54,104 @@ def test_grid_dat_round_trip(tmp_path):
             assert np.array_equal(np.asarray(a[k], dtype=np.float32), b[k])
     with pytest.raises((ValueError, StopIteration)):
         F.read_grid_dat(p, metals=False, kinematics=False)
+
+
+class _Cell:
+    __slots__ = ("s", "kids", "level")
+
+    def __init__(self, level):
+        self.s = dict(tgas=0., rho=0., HI=0., HeI=0., HeII=0., abun2=0.)
+        self.kids, self.level = None, level
+
+
+def _reference_build(levels, metals):
+    """pointer-tree restatement of equiSources.f90:425-618 + placeCellProjectWithVelocity (:1870-1974), one cell at a time"""
+    f32 = np.float32
+    psi, mp, mn = float(f32(0.76)), float(f32(1.6726231e-24)), float(f32(1.67492728e-24))
+    mhe = 2.0 * (mp + mn)
+    n1 = levels[0]["pos"].shape[0]
+    nx = round(n1 ** (1 / 3))
+    p1 = levels[0]["pos"].astype(f32).astype(float)
+    lo, hi = p1.min(0), p1.max(0)
+    mid, half = 0.5 * (lo + hi), 0.5 * (hi - lo) * float(nx) / float(nx - 1)
+    a, b = mid - half, mid + half
+    base = [[[_Cell(0) for _ in range(nx)] for _ in range(nx)] for _ in range(nx)]
+
+    def place(cell, level, x, y, z, rec):
+        if level > 1:
+            if cell.kids is None:
+                cell.kids = [[[_Cell(cell.level + 1) for _ in range(2)] for _ in range(2)] for _ in range(2)]
+                for i in range(2):
+                    for j in range(2):
+                        for k in range(2):
+                            c = cell.kids[i][j][k]
+                            c.s.update(cell.s)
+                            c.s["abun2"] = 0.0
+            i, x = (0, 2 * x) if x < 0.5 else (1, 2 * x - 1)
+            j, y = (0, 2 * y) if y < 0.5 else (1, 2 * y - 1)
+            k, z = (0, 2 * z) if z < 0.5 else (1, 2 * z - 1)
+            place(cell.kids[i][j][k], level - 1, x, y, z, rec)
+        else:
+            nh = 10.0 ** float(rec["lnH"])
+            rho = nh * mp / psi
+            cell.s.update(tgas=10.0 ** float(rec["lT"]), rho=rho, HI=nh * 10.0 ** float(rec["lx"]),
+                          HeI=(1 - psi) * rho / mhe, HeII=0.0,
+                          abun2=float(rec["abun"][1]) if metals else float(f32(0.02)))
+
+    for l, lv in enumerate(levels):
+        pn = ((lv["pos"].astype(f32).astype(float) - a) / (b - a)).astype(f32).astype(float)
+        for c in range(pn.shape[0]):
+            x0, y0, z0 = pn[c]
+            i0, j0, k0 = int(x0 * nx), int(y0 * nx), int(z0 * nx)
+            rec = dict(lT=f32(lv["lT"][c]), lnH=f32(lv["lnH"][c]), lx=f32(lv["lx"][c]))
+            if metals:
+                rec["abun"] = lv["abun"][c].astype(f32)
+            place(base[i0][j0][k0], l + 1, x0 * float(nx) - i0, y0 * float(nx) - j0, z0 * float(nx) - k0, rec)
+    out = []
+
+    def walk(cell):
+        if cell.kids is None:
+            out.append((cell.level, cell.s))
+        else:
+            for i in range(2):
+                for j in range(2):
+                    for k in range(2):
+                        walk(cell.kids[i][j][k])
+
+    for i in range(nx):
+        for j in range(nx):
+            for k in range(nx):
+                walk(base[i][j][k])
+    return nx, out
+
+
+@pytest.mark.parametrize("metals", [False, True])
+def test_octree_from_level_lists(metals, tmp_path, oracle):
+    rng = np.random.default_rng(5)
+    nx = 4
+    g = (np.arange(nx) + 0.5) / nx * 80.0 - 40.0            # kpc
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+
+    def lv(pos):
+        n = pos.shape[0]
+        d = dict(pos=pos, lT=rng.uniform(3, 5, n), lnH=rng.uniform(-4, 0, n), lx=rng.uniform(-4, 0, n))
+        if metals:
+            d["abun"] = rng.uniform(0, 0.05, (n, 4))
+        return d
+
+    levels = [lv(np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1)),
+              lv(rng.uniform(-12, 12, (40, 3))),                 # level 2 cells near the centre (some share a parent)
+              lv(rng.uniform(-6, 6, (30, 3)))]                    # level 3 cells: parents partly created by inheritance
+    p = tmp_path / ("grid_met.dat" if metals else "grid.dat")
+    F.write_grid_dat(p, levels)
+    back = F.read_grid_dat(p, metals=metals)
+    kw = F.build_leaves(back, metals=metals)
+    nref, leaves = _reference_build(back, metals)
+    assert kw["nx"] == nref and kw["level"].size == len(leaves)
+    assert np.array_equal(kw["level"], np.array([l for l, _ in leaves], dtype=np.int8))
+    for name in ("HI", "HeI", "HeII", "rho", "abun2", "tgas"):
+        assert np.array_equal(kw[name], np.array([s[name] for _, s in leaves])), name
+    assert np.isclose(kw["box_size"], 80.0 * F._KPC, rtol=1e-6)
+    tgas = kw.pop("tgas")
+    og = oracle.OracleGrid(kw["nx"], kw["level"], kw["HI"], kw["HeI"], kw["HeII"], kw["rho"], kw["abun2"], kw["box_size"])
+    assert og.nleaf == tgas.size                                  # a consistent pre-order octree
