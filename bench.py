@@ -288,13 +288,15 @@ def run_point(args):
     value = nseg_total / (ms_per_step * 1e-3)
 
     # end to end through the host-buffer C-ABI call: H2D of the six rate arrays, D2H of them and of the diagnostics
-    hR = np.zeros((6, N))
+    hRt = torch.zeros(6, N, dtype=torch.float64).pin_memory()    # the caller's rate fields, pinned host memory
+    hR = hRt.numpy()
     e2e_steps = max(1, min(args.steps, 3))
-    eng.point(sp, src[mine], wt[mine], rates=hR)
+    eng.point(sp, src[mine], wt[mine], rates=hR, inplace=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        out = eng.point(sp, src[mine], wt[mine], rates=hR)
+        hR[:] = 0.0                                              # setZeroRates on the host copy
+        out = eng.point(sp, src[mine], wt[mine], rates=hR, inplace=True)
         if world > 1:
             Rt = torch.from_numpy(out["rates"]).to(dev)
             dist.all_reduce(Rt)

@@ -121,16 +121,25 @@ class Transport:
         return keep, [int(wl.size), _ptr(wl), _ptr(lum), _ptr(met), float(spectra["coef_spectrum"]), _ptr(ad)]
 
     def point(self, spectra, src_leaf, src_weight, dust_approximation=0, max_pixel_level=6, rates=None,
-              trace_cap=0):
+              trace_cap=0, inplace=False):
         """Host-buffer call.  `rates` [6, nleaf] (krate24, krate25, krate26, crate24, crate25, crate26) is accumulated
-        like the reference's cell fields (zeros when None).  Returns dict(rates, ndot_remaining[nsrc,7],
+        like the reference's cell fields (zeros when None; `inplace=True` accumulates into the caller's C-contiguous
+        fp64 array itself, e.g. a view of pinned memory, instead of a copy).  Returns dict(rates, ndot_remaining[nsrc,7],
         ndot_boundary[nsrc,7], ndot_dust[nsrc], ndot_spectrum[nsrc,300], nseg[, trace, trace_key])."""
         keep, sa = self._spectra_args(spectra)
         leaf = np.ascontiguousarray(src_leaf, dtype=np.int32); wt = np.ascontiguousarray(src_weight, dtype=np.int32)
         if leaf.size != wt.size:
             raise ValueError("src_leaf and src_weight differ in length")
         ns = int(leaf.size)
-        R = np.zeros((6, self.nleaf)) if rates is None else np.ascontiguousarray(rates, dtype=np.float64).copy()
+        if rates is None:
+            R = np.zeros((6, self.nleaf))
+        elif inplace:
+            R = rates
+            if not (isinstance(R, np.ndarray) and R.dtype == np.float64 and R.flags.c_contiguous
+                    and R.shape == (6, self.nleaf)):
+                raise ValueError("inplace rates must be a C-contiguous float64 array of shape (6, nleaf)")
+        else:
+            R = np.ascontiguousarray(rates, dtype=np.float64).copy()
         nseg = C.c_int64(0)
         out = dict(rates=R)
         if trace_cap:
