@@ -7,15 +7,17 @@
 //    loops over the zone's directions and adds all their contributions to J in registers -> one J update per
 //    cell per zone instead of one per direction.
 //  * Within a layer every cell carries the same 1..3 segments (its "pattern"); a characteristic that leaves a
-//    cell sideways continues in the k+1 and/or j+1 neighbour of the SAME layer.  That in-layer hand-over goes
-//    through shared memory: phase 1 computes every cell's bottom-entering (xy) segment, phase 2 the segment fed by
-//    a neighbour's phase-1 result, phase 3 the one fed by a phase-2 result.  Tiles overlap by one cell on the
-//    upstream sides (the halo cells are recomputed) so that no inter-block communication is needed.
-//  * The only inter-layer state is the intensity leaving each cell through its top face: one plane of
-//    3 doubles per cell per direction, ping-ponged in global memory and meant to stay L2-resident
-//    (the number of zones in flight is chosen from the L2 budget).
-//  * Zones run in `slots` concurrent lanes (gridDim.z); each slot owns a private J accumulator, so no atomics and a
-//    fixed summation order.  A final kernel sums the slot accumulators into J.
+//    cell sideways continues in the k+1 and/or j+1 neighbour of the SAME layer.  Along the lane axis that hand-over
+//    is a warp shuffle of the neighbour lane's own result (a warp covers 31 cells + 1 recomputed halo cell); along
+//    the row axis the thread recomputes what the (b-1) cell emits from the previous layer's plane value and that
+//    cell's kappa.  No shared-memory exchange, no barrier in the loop, no inter-block communication.
+//  * The only inter-layer state is the intensity leaving each cell through its top face: one padded plane of
+//    3 doubles per cell per direction ([row][column][group]), ping-ponged in global memory.
+//  * One launch per layer covers every zone task of the batch (gridDim.z); each task owns a private J accumulator
+//    ("slot"), so no atomics and a fixed summation order.  Final kernels sum the slot accumulators into J.
+//  * Zones that sweep along the contiguous axis of the leaf order read a z-major copy of kappa and accumulate in
+//    that layout (transpose_kappa_kernel / merge_transposed_kernel) so that their lanes stay coalesced.
+//  * sweep_march_kernel is an experimental persistent variant (plane tiles in shared memory), off by default.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
