@@ -38,7 +38,8 @@ enum rtb200_status {
   RTB200_ERR_IDEPTH = 11,         /* equiSources.f90:4196 'error in idepth123' */
   RTB200_ERR_ARG = 12,            /* bad argument (null pointer, size mismatch, grid not set ...) */
   RTB200_ERR_CUDA = 13,           /* CUDA runtime failure or no device: no CPU fallback exists */
-  RTB200_ERR_NOMEM = 14
+  RTB200_ERR_NOMEM = 14,
+  RTB200_ERR_CHEMISTRY = 15       /* equiSources.f90:3634-3655: ionisation fraction outside [0,1] (the reference prints and stops) */
 };
 
 /* arithmetic mode of the per-segment update (transportRoutinesModule.f90:651-698, 1036-1054) */
@@ -132,6 +133,27 @@ int rtb200_point_device(rtb200_ctx* ctx, int nWave, const double* wavelength, co
                         int maxPixelLevel, int32_t nsrc, const int32_t* srcLeaf, const int32_t* srcWeight,
                         double* rates_device, void* stream, double* ndotRemaining, double* ndotBoundary,
                         double* ndotDust, double* ndotSpectrum, int64_t* nseg);
+
+/* Ionisation equilibrium per leaf: replaces solveRateEquations (equiSources.f90:3459-3677), the consumer of the
+ * transport results, so that the outer transport <-> chemistry iteration can stay on the GPU.
+ *   rtb200_chemistry_tables       k1a..k6a of calc_rates.f (nratec bins in log T from logtem0 to logtem9, :174-190)
+ *   rtb200_chemistry_temperature  tgas per leaf (held fixed by the driver, :3671-3673); log(tgas) is taken here, with libm
+ *   rtb200_chemistry_device       rates_device [6][nleaf] as rtb200_point_device leaves them (NULL = no point sources);
+ *                                 J_device [3][nleaf] of rtb200_diffuse_device with ksi = {ksi24 of groups 1..3, ksi25
+ *                                 of group 3, ksi26 of groups 2, 3} (:3546-3553), or J_device = NULL and uniform =
+ *                                 {add24, add25, add26, selfShieldingThreshold [cm]} for the uniform background with the
+ *                                 mean-free-path switch (:3555-3562; addXX = 4 pi (uniformQuasar quasar%ksiXX +
+ *                                 uniformStellar stellar%ksiXX)).  Updates the context's HI, HeI, HeII in place;
+ *                                 maxChange (host, optional; forces a synchronisation) = largest change of a species
+ *                                 fraction, the quantity the reference computes as `tmp` (:3665-3669).
+ *   rtb200_grid_get_species       HI, HeI, HeII back to the host (any may be NULL)                                  */
+int rtb200_chemistry_tables(rtb200_ctx* ctx, int nratec, double logtem0, double logtem9, double dlogtem, const double* k1a,
+                            const double* k2a, const double* k3a, const double* k4a, const double* k5a,
+                            const double* k6a);
+int rtb200_chemistry_temperature(rtb200_ctx* ctx, const double* tgas);
+int rtb200_chemistry_device(rtb200_ctx* ctx, const double* rates_device, const double* J_device, const double* ksi,
+                            const double* uniform, double* maxChange, void* stream);
+int rtb200_grid_get_species(rtb200_ctx* ctx, double* HI, double* HeI, double* HeII);
 
 /* --- debugging / parity exports (bit-exact traversal checks) ------------------------------------------- */
 /* point-source pass that also records every ray-cell segment: trace[2*i] = leaf<<32 | pixelLevel<<28 | pixel<<8 | exit

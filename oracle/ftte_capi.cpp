@@ -69,6 +69,16 @@ int ftte_point(void* h, int nWave, const double* wavelength, const double* lum, 
 
 void ftte_set_portable_math(int on) { setPortableMath(on); }
 
+// solveRateEquations on flattened leaf arrays (HI, HeI, HeII are updated in place)
+int ftte_chemistry(int64_t nleaf, int nx, double box, const int8_t* level, const double* rho, const double* tgas, double* HI,
+                   double* HeI, double* HeII, const double* rates, const double* J, const double* ksi,
+                   const double* uniform, int nratec, double logtem0, double logtem9, double dlogtem, const double* k,
+                   double* maxChange) {
+  return chemistrySolve(nleaf, nx, box, level, rho, tgas, HI, HeI, HeII, rates, J, ksi, uniform, nratec, logtem0, logtem9,
+                        dlogtem, k, k + nratec, k + 2 * (size_t)nratec, k + 3 * (size_t)nratec, k + 4 * (size_t)nratec,
+                        k + 5 * (size_t)nratec, maxChange);
+}
+
 int ftte_point_tables(int nWave, const double* wavelength, const double* lum, const double* metallicity,
                       double coefSpectrum, const double* aDust, int iMetal, double coefMetal, double* out,
                       double* totalIntegral, double* outputSigma) {

@@ -152,6 +152,27 @@ def _point(self, spectra, src_leaf, src_weight, dust_approximation=0, max_pixel_
 OracleGrid.point = _point
 
 
+def chemistry(nx, box_size, level, rho, tgas, HI, HeI, HeII, ktab, rates=None, J=None, ksi=None, uniform=None):
+    """solveRateEquations (equiSources.f90:3459-3677) on leaf arrays.  ktab = dict(k=[6, nratec], logtem0, logtem9,
+    dlogtem).  Returns dict(HI, HeI, HeII, max_change, status)."""
+    L = lib()
+    level = np.ascontiguousarray(level, dtype=np.int8)
+    n = int(level.size)
+    out = [np.ascontiguousarray(a, dtype=np.float64).copy() for a in (HI, HeI, HeII)]
+    k = _f64(ktab["k"])
+    ksi_a = _f64(np.zeros(6) if ksi is None else ksi)
+    uni = _f64(np.zeros(4) if uniform is None else uniform)
+    mc = C.c_double(0)
+    L.ftte_chemistry.restype = C.c_int
+    L.ftte_chemistry.argtypes = [C.c_int64, C.c_int, C.c_double] + [C.c_void_p] * 10 + [C.c_int, C.c_double, C.c_double,
+                                                                                       C.c_double, C.c_void_p,
+                                                                                       C.POINTER(C.c_double)]
+    st = L.ftte_chemistry(n, int(nx), float(box_size), _p(level), _p(_f64(rho)), _p(_f64(tgas)), _p(out[0]), _p(out[1]),
+                          _p(out[2]), _p(_f64(rates)), _p(_f64(J)), _p(ksi_a), _p(uni), int(k.shape[1]),
+                          float(ktab["logtem0"]), float(ktab["logtem9"]), float(ktab["dlogtem"]), _p(k), C.byref(mc))
+    return dict(HI=out[0], HeI=out[1], HeII=out[2], max_change=mc.value, status=st)
+
+
 def set_portable_math(on):
     """point path: evaluate exp/log with radiativetransfer_b200/csrc/portable_math.h (IEEE +,*,/,fma only) instead
     of libm -- the same source the CUDA kernels use in FAITHFUL mode, so deposits can be compared bit for bit"""

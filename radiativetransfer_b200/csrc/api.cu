@@ -37,6 +37,7 @@ static void free_grid(Context& c) {
   cudaFree(c.dKappa); cudaFree(c.tree.child); cudaFree(c.tree.leafX); cudaFree(c.tree.leafY); cudaFree(c.tree.leafZ);
   cudaFree(c.dJ); cudaFree(c.dRates); c.dRates = nullptr;
   cudaFree(c.dKappaT); c.dKappaT = nullptr; c.kappaTBytes = 0;
+  cudaFree(c.dLogT); c.dLogT = nullptr;
   for (auto& sl : c.pointPool) cudaFree(sl.first);
   c.pointPool.clear();
   c.dLevel = nullptr; c.dHI = c.dHeI = c.dHeII = c.dRho = c.dAbun2 = c.dKappa = c.dJ = nullptr;
@@ -183,6 +184,7 @@ const char* rtb200_status_string(int status) {
     case RTB200_ERR_ARG: return "bad argument";
     case RTB200_ERR_CUDA: return last_cuda_error()[0] ? last_cuda_error() : "CUDA error or no CUDA device (no CPU fallback)";
     case RTB200_ERR_NOMEM: return "out of device memory";
+    case RTB200_ERR_CHEMISTRY: return "ionisation fraction outside [0,1]";
     default: return "unknown status";
   }
 }
@@ -229,6 +231,7 @@ int rtb200_destroy(rtb200_ctx* h) {
   cudaSetDevice(c.device);
   cudaDeviceSynchronize();
   free_grid(c);
+  cudaFree(c.dChemK);
   cudaFree(c.dAcc); cudaFree(c.dPlanes); cudaFree(c.dAmrScratch); cudaFree(c.dErr); cudaFree(c.dMarchSeg); cudaFree(c.dMarchProg);
   if (c.hPinned) cudaFreeHost(c.hPinned);
   if (c.evStart) cudaEventDestroy(c.evStart);
@@ -448,6 +451,37 @@ int rtb200_point_tables(rtb200_ctx* h, int nWave, const double* wavelength, cons
   const size_t nb = (size_t)c.nleaf * sizeof(double);
   if (!c.dRates) RTB_CUDA(cudaMalloc((void**)&c.dRates, 6 * nb));
   return point_solve(c, in, c.dRates, nullptr, nullptr, nullptr, 0, nullptr, tables, c.stream);
+}
+
+int rtb200_chemistry_tables(rtb200_ctx* h, int nratec, double logtem0, double logtem9, double dlogtem, const double* k1a,
+                            const double* k2a, const double* k3a, const double* k4a, const double* k5a,
+                            const double* k6a) {
+  if (!h) return RTB200_ERR_ARG;
+  const double* k[6] = {k1a, k2a, k3a, k4a, k5a, k6a};
+  return chemistry_set_tables(h->c, nratec, logtem0, logtem9, dlogtem, k);
+}
+
+int rtb200_chemistry_temperature(rtb200_ctx* h, const double* tgas) {
+  if (!h) return RTB200_ERR_ARG;
+  return chemistry_set_temperature(h->c, tgas);
+}
+
+int rtb200_chemistry_device(rtb200_ctx* h, const double* rates_device, const double* J_device, const double* ksi,
+                            const double* uniform, double* maxChange, void* stream) {
+  if (!h) return RTB200_ERR_ARG;
+  return chemistry_run(h->c, rates_device, J_device, ksi, uniform, maxChange, (cudaStream_t)stream);
+}
+
+int rtb200_grid_get_species(rtb200_ctx* h, double* HI, double* HeI, double* HeII) {
+  if (!h || h->c.nleaf == 0) return RTB200_ERR_ARG;
+  Context& c = h->c;
+  RTB_CUDA(cudaSetDevice(c.device));
+  RTB_CUDA(cudaDeviceSynchronize());
+  const size_t nb = (size_t)c.nleaf * sizeof(double);
+  if (HI) RTB_CUDA(cudaMemcpy(HI, c.dHI, nb, cudaMemcpyDeviceToHost));
+  if (HeI) RTB_CUDA(cudaMemcpy(HeI, c.dHeI, nb, cudaMemcpyDeviceToHost));
+  if (HeII) RTB_CUDA(cudaMemcpy(HeII, c.dHeII, nb, cudaMemcpyDeviceToHost));
+  return RTB200_OK;
 }
 
 int rtb200_device_error(rtb200_ctx* h) {  // status raised by device-side guards of asynchronous calls

@@ -129,6 +129,11 @@ struct Context {
   std::vector<int8_t> hLevel;
   int8_t* dLevel = nullptr;
   double *dHI = nullptr, *dHeI = nullptr, *dHeII = nullptr, *dRho = nullptr, *dAbun2 = nullptr;
+  // chemistry (solveRateEquations): rate-coefficient tables and log(tgas) per leaf
+  double* dChemK = nullptr;  // [6][nratec]
+  int chemNratec = 0;
+  double chemLogtem0 = 0, chemLogtem9 = 0, chemDlogtem = 0;
+  double* dLogT = nullptr;   // [nleaf]
   double* dKappa = nullptr;  // [3][nleaf]
   double* dKappaT = nullptr; // [3][nleaf] z-major copy (index (z*n + x)*n + y) for the uniform sweep, lazily allocated
   size_t kappaTBytes = 0;
@@ -189,6 +194,11 @@ int amr_neighbours(Context& c, const Direction& d, int32_t* nbHost);
 void amr_release(Context& c);
 int launch_diffuse_rates(Context& c, const double* J, const double* ksi24, const double* ksi25, const double* ksi26,
                          double* k24, double* k25, double* k26, cudaStream_t s);
+
+int chemistry_set_tables(Context& c, int nratec, double logtem0, double logtem9, double dlogtem, const double* const k[6]);
+int chemistry_set_temperature(Context& c, const double* tgas);
+int chemistry_run(Context& c, const double* dRates, const double* dJ, const double* ksi, const double* uniform,
+                  double* maxChange, cudaStream_t s);
 
 // point sources: dRates = device [6][nleaf] (krate24, krate25, krate26, crate24, crate25, crate26), accumulated;
 // hDiag = host [nsrc][320] (remaining[7], boundary[7], dust, pad, spectrum[300]) or NULL

@@ -190,6 +190,40 @@ class Transport:
                    "rtb200_point_tables")
         return out
 
+    # ---- chemistry (solveRateEquations, equiSources.f90:3459-3677) --------------------------------------------------
+    def set_rate_tables(self, ktab):
+        """ktab = dict(k[6, nratec] = k1a..k6a, logtem0, logtem9, dlogtem)"""
+        k = _f64(ktab["k"])
+        if k.ndim != 2 or k.shape[0] != 6:
+            raise ValueError("k must have shape (6, nratec)")
+        st = self.L.rtb200_chemistry_tables(self.h, int(k.shape[1]), float(ktab["logtem0"]), float(ktab["logtem9"]),
+                                            float(ktab["dlogtem"]), *[_ptr(k[i]) for i in range(6)])
+        _lib.check(st, "rtb200_chemistry_tables")
+
+    def set_temperature(self, tgas):
+        t = _f64(tgas)
+        if t.size != self.nleaf:
+            raise ValueError("tgas needs one value per leaf")
+        _lib.check(self.L.rtb200_chemistry_temperature(self.h, _ptr(t)), "rtb200_chemistry_temperature")
+
+    def chemistry_device(self, rates_ptr=0, J_ptr=0, ksi=None, uniform=None, stream=0, want_change=True):
+        """One solveRateEquations pass over all leaves, in place on the device copies of HI, HeI, HeII.  rates_ptr /
+        J_ptr: device pointers ([6][nleaf] / [3][nleaf]) or 0; ksi = (ksi24[3], ksi25, ksi26[2]) flattened; uniform =
+        (add24, add25, add26, selfShieldingThreshold).  Returns the largest change of a species fraction."""
+        k = None if ksi is None else _f64(np.concatenate([np.ravel(x) for x in ksi]) if not isinstance(ksi, np.ndarray) else ksi)
+        u = None if uniform is None else _f64(uniform)
+        mc = C.c_double(0)
+        st = self.L.rtb200_chemistry_device(self.h, C.c_void_p(int(rates_ptr)) if rates_ptr else None,
+                                            C.c_void_p(int(J_ptr)) if J_ptr else None, _ptr(k), _ptr(u),
+                                            C.byref(mc) if want_change else None, C.c_void_p(int(stream)))
+        _lib.check(st, "rtb200_chemistry_device")
+        return mc.value
+
+    def get_species(self):
+        HI, HeI, HeII = np.empty(self.nleaf), np.empty(self.nleaf), np.empty(self.nleaf)
+        _lib.check(self.L.rtb200_grid_get_species(self.h, _ptr(HI), _ptr(HeI), _ptr(HeII)), "rtb200_grid_get_species")
+        return HI, HeI, HeII
+
     def device_error(self):
         return self.L.rtb200_device_error(self.h)
 

@@ -265,3 +265,25 @@ def point_workload(n, nsrc, seed=3, uniform=False, box_kpc=100.0):
     if pick.size < nsrc:  # tiny grids: allow repeats
         pick = np.concatenate([pick, rng.choice(leaves, size=nsrc - pick.size)])
     return g, np.sort(pick).astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------------------------
+# chemistry
+# ------------------------------------------------------------------------------------------------------
+def rate_tables(nratec=5000, temstart=1.0, temend=1.0e9):
+    """Stand-in for the k1a..k6a tables of calc_rates.f (out of scope): collisional ionisation and
+    recombination coefficients of H and He in the analytic forms of Cen (1992), tabulated on the driver's log-T grid
+    (equiSources.f90:174-176: dlogtem uses real(nratec-1), a single-precision divisor).  Workload parameters, fed
+    identically to the GPU path and to the oracle."""
+    logtem0, logtem9 = float(np.log(temstart)), float(np.log(temend))
+    dlogtem = (logtem9 - logtem0) / float(np.float32(nratec - 1))
+    T = np.exp(logtem0 + np.arange(nratec) * dlogtem)
+    sq, t5 = np.sqrt(T), 1.0 / (1.0 + np.sqrt(T / 1.0e5))
+    k = np.zeros((6, nratec))
+    k[0] = 5.85e-11 * sq * np.exp(-157809.1 / T) * t5                      # HI  + e -> HII   + 2e
+    k[1] = 8.4e-11 / sq * (T / 1.0e3) ** -0.2 / (1.0 + (T / 1.0e6) ** 0.7)  # HII + e -> HI
+    k[2] = 2.38e-11 * sq * np.exp(-285335.4 / T) * t5                      # HeI + e -> HeII  + 2e
+    k[3] = 1.5e-10 * T ** -0.6353                                          # HeII + e -> HeI
+    k[4] = 5.68e-12 * sq * np.exp(-631515.0 / T) * t5                      # HeII + e -> HeIII + 2e
+    k[5] = 3.36e-10 / sq * (T / 1.0e3) ** -0.2 / (1.0 + (T / 1.0e6) ** 0.7)  # HeIII + e -> HeII
+    return dict(k=np.maximum(k, 1e-300), logtem0=logtem0, logtem9=logtem9, dlogtem=dlogtem)
