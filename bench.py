@@ -44,6 +44,9 @@ WORKLOADS = {
     "diffuse-256^3-uniform-192dir": 256,
     "diffuse-128^3-uniform-192dir": 128,
     "diffuse-64^3-uniform-192dir": 64,
+    # config 4 style: the reference's outer loop, sweep -> ionisation equilibrium, 10 passes per step, all on the device
+    "iterate10-256^3-uniform-192dir": ("iterate", 256, 10),
+    "iterate10-64^3-uniform-192dir": ("iterate", 64, 10),
     # config-5 style nested grid: n^3 base + refinement levels around a synthetic disc (general octree path)
     "diffuse-128^3-amr2-192dir": ("amr", 128, 2),
     "diffuse-64^3-amr3-192dir": ("amr", 64, 3),
@@ -57,6 +60,8 @@ WORKLOADS = {
 def make_inputs(spec, seed=1):
     """(n, grid dict, background) of a diffuse workload: uniform n^3 or a nested grid"""
     from radiativetransfer_b200 import workloads as W
+    if isinstance(spec, tuple) and spec[0] == "iterate":
+        return spec[1], W.uniform_grid(spec[1], seed=seed), W.uvb_background(3.0)
     if isinstance(spec, tuple):
         _, n, levels = spec
         return n, W.nested_grid(n, levels, W.disc_refine(levels), seed=5), W.uvb_background(3.0)
@@ -382,7 +387,9 @@ def main():
 
     n, grid, bg = make_inputs(WORKLOADS[args.workload])
     N = int(grid["level"].size)
-    uniform = not isinstance(WORKLOADS[args.workload], tuple)
+    spec = WORKLOADS[args.workload]
+    iterations = spec[2] if isinstance(spec, tuple) and spec[0] == "iterate" else 0
+    uniform = not isinstance(spec, tuple) or iterations > 0
     eng = rt.Transport(device=local)
     eng.set_grid(n, grid["level"], grid["HI"], grid["HeI"], grid["HeII"], grid["rho"], grid["abun2"], grid["box_size"])
     shards = sharding.shard_directions(world, n_angular_level=3, nx=n)
@@ -398,7 +405,24 @@ def main():
     ar0, ar1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     K = torch.zeros(3, N, dtype=torch.float64, device=dev)     # krate24, krate25, krate26
 
+    ksi_all = np.concatenate([bg["ksi24"], bg["ksi25"], bg["ksi26"]])
+    if iterations:
+        from radiativetransfer_b200 import workloads as Wk
+        eng.set_rate_tables(Wk.rate_tables(5000))
+        eng.set_temperature(10.0 ** np.random.default_rng(2).uniform(3.8, 4.6, N))
+
     def step_resident():
+        if iterations:
+            # the reference's outer loop (equiSources.f90:1230-1843) without its I/O: sweep -> solveRateEquations,
+            # `iterations` passes; HI, HeI, HeII, J never leave the device.  Every step starts from the same state.
+            eng.update_species(grid["HI"], grid["HeI"], grid["HeII"])
+            total = 0
+            for _ in range(iterations):
+                total += eng.diffuse_device(bg["uvb"], bg["beta"], J.data_ptr(), rays=rays, stream=stream)
+                if world > 1:
+                    dist.all_reduce(J)
+                eng.chemistry_device(0, J.data_ptr(), ksi=ksi_all, stream=stream, want_change=False)
+            return total
         nseg = eng.diffuse_device(bg["uvb"], bg["beta"], J.data_ptr(), rays=rays, stream=stream)
         if world > 1:
             ar0.record()
@@ -434,7 +458,7 @@ def main():
     barrier()
     t = torch.tensor([ms, float(nseg_rank), sweep_ms, alg_bytes_rank], dtype=torch.float64, device=dev)
     rank_kernel_ms = [sweep_ms]
-    allreduce_ms = ar0.elapsed_time(ar1) if world > 1 else 0.0   # last step; includes waiting for the slowest rank
+    allreduce_ms = ar0.elapsed_time(ar1) if (world > 1 and not iterations) else 0.0   # last step; incl. waiting for the slowest rank
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
@@ -456,6 +480,13 @@ def main():
 
     def step_e2e():
         eng.update_species(hHI.numpy(), hHeI.numpy(), hHeII.numpy())          # H2D from pinned host memory
+        if iterations:
+            for _ in range(iterations):
+                eng.diffuse_device(bg["uvb"], bg["beta"], Jd.data_ptr(), rays=rays, stream=stream)
+                if world > 1:
+                    dist.all_reduce(Jd)
+                eng.chemistry_device(0, Jd.data_ptr(), ksi=ksi_all, stream=stream, want_change=False)
+            return float(eng.get_species()[0][0])                             # D2H of the new HI, HeI, HeII
         if world > 1:
             eng.diffuse_device(bg["uvb"], bg["beta"], Jd.data_ptr(), rays=rays, stream=stream)
             dist.all_reduce(Jd)
@@ -492,14 +523,16 @@ def main():
                        "directions": 192,
                        "n_angular_level": 3, "frequency_groups": 3, "leaves": N,
                        "segment_updates_per_step": nseg_total, "math": "fast",
-                       "step": "computeOpacities + 192-direction sweep + merge [+ all-reduce of J] + diffuse photo-rates",
+                       "step": (f"{iterations} x (computeOpacities + 192-direction sweep + merge [+ all-reduce of J] + "
+                                "solveRateEquations), species re-uploaded at the start of the step") if iterations else
+                               "computeOpacities + 192-direction sweep + merge [+ all-reduce of J] + diffuse photo-rates",
                        "parallelism": f"directions sharded over {world} GPU(s), full grid per GPU, all-reduce of J",
                        "l2_policy": "inputs larger than L2 (kappa + J + planes >> 126 MB)" if n >= 200 else
                                     "working set comparable to L2; not flushed between steps"},
             "clocks": clocks_summary(samples),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 3 * N * 8,
                     "d2h_bytes_per_step": 3 * N * 8},
-            "gpu_launches": int(launches) * args.steps,
+            "gpu_launches": (int(launches) + 1) * max(iterations, 1) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
                          "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 else None,

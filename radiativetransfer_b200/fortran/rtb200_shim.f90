@@ -51,6 +51,27 @@ module rtb200_shim
        integer(c_int32_t), value :: nrays
        type(c_ptr), value :: J1, J2, J3, nseg
      end function rtb200_diffuse
+     integer(c_int) function rtb200_chemistry_tables(ctx, nratec, logtem0, logtem9, dlogtem, k1a, k2a, k3a, k4a, k5a, k6a) &
+          bind(C, name='rtb200_chemistry_tables')
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: nratec
+       real(c_double), value :: logtem0, logtem9, dlogtem
+       type(c_ptr), value :: k1a, k2a, k3a, k4a, k5a, k6a
+     end function rtb200_chemistry_tables
+     integer(c_int) function rtb200_chemistry_temperature(ctx, tgas) bind(C, name='rtb200_chemistry_temperature')
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx, tgas
+     end function rtb200_chemistry_temperature
+     integer(c_int) function rtb200_chemistry_device(ctx, rates_device, J_device, ksi, uniform, maxChange, stream) &
+          bind(C, name='rtb200_chemistry_device')
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx, rates_device, J_device, ksi, uniform, maxChange, stream
+     end function rtb200_chemistry_device
+     integer(c_int) function rtb200_grid_get_species(ctx, HI, HeI, HeII) bind(C, name='rtb200_grid_get_species')
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx, HI, HeI, HeII
+     end function rtb200_grid_get_species
      integer(c_int) function rtb200_point(ctx, nWave, wavelength, lum, metallicity, coefSpectrum, aDust, &
           dustApproximation, maxPixelLevel, nsrc, srcLeaf, srcWeight, k24, k25, k26, c24, c25, c26, &
           ndotRemaining, ndotBoundary, ndotDust, ndotSpectrum, nseg) bind(C, name='rtb200_point')
