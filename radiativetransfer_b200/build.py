@@ -30,17 +30,22 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
-    objs = []
     bdir = os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
-    for src in SOURCES:
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+
+    def compile_one(src):
         path = os.path.join(CSRC, src)
-        if not os.path.exists(path):
-            continue
         obj = os.path.join(bdir, src.rsplit(".", 1)[0] + ".o")
-        flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-        cmd = [_nvcc()] + flags + ["-x", "cu", "-c", path, "-o", obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
+        r = subprocess.run([_nvcc()] + flags + ["-x", "cu", "-c", path, "-o", obj], capture_output=True, text=True)
+        return src, obj, r
+
+    from concurrent.futures import ThreadPoolExecutor
+    sources = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    with ThreadPoolExecutor(max_workers=min(len(sources), os.cpu_count() or 1)) as ex:   # one nvcc per translation unit
+        results = list(ex.map(compile_one, sources))
+    objs = []
+    for src, obj, r in results:
         if verbose or r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
         if r.returncode:
