@@ -146,7 +146,12 @@ int rtb200_point_device(rtb200_ctx* ctx, int nWave, const double* wavelength, co
  *                                 uniformStellar stellar%ksiXX)).  Updates the context's HI, HeI, HeII in place;
  *                                 maxChange (host, optional; forces a synchronisation) = largest change of a species
  *                                 fraction, the quantity the reference computes as `tmp` (:3665-3669).
- *   rtb200_grid_get_species       HI, HeI, HeII back to the host (any may be NULL)                                  */
+ *   rtb200_grid_get_species       HI, HeI, HeII back to the host (any may be NULL)
+ *   rtb200_compute_mass           neutral and total hydrogen mass in solar masses from the context's current HI and
+ *                                 rho: replaces the computeMass recursion (equiSources.f90:4369-4393) the driver runs
+ *                                 after every chemistry pass (:1018, :1828) to print neutralHydrogenMass /
+ *                                 totalHydrogenMass.  Per-leaf terms in the reference's operation order; the sum is
+ *                                 a fixed-order tree (reproducible; differs from the serial sum by rounding only). */
 int rtb200_chemistry_tables(rtb200_ctx* ctx, int nratec, double logtem0, double logtem9, double dlogtem, const double* k1a,
                             const double* k2a, const double* k3a, const double* k4a, const double* k5a,
                             const double* k6a);
@@ -154,6 +159,7 @@ int rtb200_chemistry_temperature(rtb200_ctx* ctx, const double* tgas);
 int rtb200_chemistry_device(rtb200_ctx* ctx, const double* rates_device, const double* J_device, const double* ksi,
                             const double* uniform, double* maxChange, void* stream);
 int rtb200_grid_get_species(rtb200_ctx* ctx, double* HI, double* HeI, double* HeII);
+int rtb200_compute_mass(rtb200_ctx* ctx, double* neutralHydrogenMass, double* totalHydrogenMass, void* stream);
 
 /* --- debugging / parity exports (bit-exact traversal checks) ------------------------------------------- */
 /* point-source pass that also records every ray-cell segment: trace[2*i] = leaf<<32 | pixelLevel<<28 | pixel<<8 | exit

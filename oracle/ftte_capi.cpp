@@ -79,6 +79,20 @@ int ftte_chemistry(int64_t nleaf, int nx, double box, const int8_t* level, const
                         k + 5 * (size_t)nratec, maxChange);
 }
 
+// computeMass (equiSources.f90:4369-4393): serial accumulation in leaf order, the order the recursion visits leaves
+void ftte_compute_mass(int64_t nleaf, int nx, double box, const int8_t* level, const double* HI, const double* rho,
+                       double* out) {
+  double neutralHydrogenMass = 0., totalHydrogenMass = 0.;
+  for (int64_t c = 0; c < nleaf; c++) {
+    const double size = box / ((double)(float)(1 << level[c]) * (double)(float)nx);   // :4389, float() = real*4
+    const double physicalCellSizeCube = size * size * size;                           // x**3
+    neutralHydrogenMass = neutralHydrogenMass + HI[c] * mh * physicalCellSizeCube / msun;          // :4390
+    totalHydrogenMass = totalHydrogenMass + psi * rho[c] * physicalCellSizeCube / msun;            // :4391
+  }
+  out[0] = neutralHydrogenMass;
+  out[1] = totalHydrogenMass;
+}
+
 int ftte_point_tables(int nWave, const double* wavelength, const double* lum, const double* metallicity,
                       double coefSpectrum, const double* aDust, int iMetal, double coefMetal, double* out,
                       double* totalIntegral, double* outputSigma) {

@@ -32,6 +32,7 @@ static const double mp = (double)1.6726231e-24f;               // :25
 static const double mn = (double)1.67492728e-24f;              // :26
 static const double mh = mp;                                   // :27
 static const double mhe = 2.0 * (mp + mn);                     // :28
+static const double msun = (double)1.98892e33f;                // :29
 static const double hydrogenIonization = (double)13.598f;      // :30
 static const double singleHeliumIonization = (double)24.587f;  // :31
 static const double doubleHeliumIonization = (double)54.418f;  // :32

@@ -173,6 +173,18 @@ def chemistry(nx, box_size, level, rho, tgas, HI, HeI, HeII, ktab, rates=None, J
     return dict(HI=out[0], HeI=out[1], HeII=out[2], max_change=mc.value, status=st)
 
 
+def compute_mass(nx, box_size, level, HI, rho):
+    """computeMass (equiSources.f90:4369-4393): (neutralHydrogenMass, totalHydrogenMass) in solar masses, summed
+    serially in leaf order"""
+    L = lib()
+    level = np.ascontiguousarray(level, dtype=np.int8)
+    out = np.zeros(2)
+    L.ftte_compute_mass.restype = None
+    L.ftte_compute_mass.argtypes = [C.c_int64, C.c_int, C.c_double] + [C.c_void_p] * 4
+    L.ftte_compute_mass(int(level.size), int(nx), float(box_size), _p(level), _p(_f64(HI)), _p(_f64(rho)), _p(out))
+    return float(out[0]), float(out[1])
+
+
 def set_portable_math(on):
     """point path: evaluate exp/log with radiativetransfer_b200/csrc/portable_math.h (IEEE +,*,/,fma only) instead
     of libm -- the same source the CUDA kernels use in FAITHFUL mode, so deposits can be compared bit for bit"""

@@ -34,6 +34,7 @@ SIGNATURES = {
     "rtb200_point_tables": (C.c_int, [P, C.c_int, P, P, P, C.c_double, P, C.c_int, C.c_double, P]),
     "rtb200_chemistry_tables": (C.c_int, [P, C.c_int, C.c_double, C.c_double, C.c_double, P, P, P, P, P, P]),
     "rtb200_chemistry_temperature": (C.c_int, [P, P]),
+    "rtb200_compute_mass": (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(C.c_double), P]),
     "rtb200_chemistry_device": (C.c_int, [P, P, P, P, P, C.POINTER(C.c_double), P]),
     "rtb200_grid_get_species": (C.c_int, [P, P, P, P]),
     "rtb200_direction": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_double),

@@ -232,6 +232,7 @@ int rtb200_destroy(rtb200_ctx* h) {
   cudaDeviceSynchronize();
   free_grid(c);
   cudaFree(c.dChemK);
+  cudaFree(c.dMassPart);
   cudaFree(c.dAcc); cudaFree(c.dPlanes); cudaFree(c.dAmrScratch); cudaFree(c.dErr); cudaFree(c.dMarchSeg); cudaFree(c.dMarchProg);
   if (c.hPinned) cudaFreeHost(c.hPinned);
   if (c.evStart) cudaEventDestroy(c.evStart);
@@ -471,6 +472,11 @@ int rtb200_chemistry_device(rtb200_ctx* h, const double* rates_device, const dou
                             const double* uniform, double* maxChange, void* stream) {
   if (!h) return RTB200_ERR_ARG;
   return chemistry_run(h->c, rates_device, J_device, ksi, uniform, maxChange, (cudaStream_t)stream);
+}
+
+int rtb200_compute_mass(rtb200_ctx* h, double* neutralHydrogenMass, double* totalHydrogenMass, void* stream) {
+  if (!h) return RTB200_ERR_ARG;
+  return compute_mass(h->c, neutralHydrogenMass, totalHydrogenMass, (cudaStream_t)stream);
 }
 
 int rtb200_grid_get_species(rtb200_ctx* h, double* HI, double* HeI, double* HeII) {

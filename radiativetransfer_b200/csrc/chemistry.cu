@@ -195,4 +195,86 @@ int chemistry_run(Context& c, const double* dRates, const double* dJ, const doub
   return RTB200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// computeMass (equiSources.f90:4369-4393): neutral and total hydrogen mass of the grid in solar masses, from the
+// absorber densities the context holds now (i.e. after the last chemistry step).  Each leaf's two terms follow the
+// reference's operation order; the reference adds them serially in leaf order, here the sum is a fixed two-stage
+// tree (1024 blocks of 256 partial sums, then one block), so it is reproducible run to run and differs from the
+// serial sum only by rounding (~1e-16 sqrt(N) relative).
+// ---------------------------------------------------------------------------------------------------------
+struct MassParams {
+  const int8_t* level;
+  const double* HI;
+  const double* rho;
+  double cube[32];   // (physicalBoxSize / (float(2**level) * float(nx)))**3
+  double mh, msun, psi;
+  int64_t N;
+};
+constexpr int kMassBlocks = 1024;
+
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* sh) {
+  // fixed-order tree over the 256 threads of the block
+  const int t = threadIdx.x;
+  sh[t] = a; sh[256 + t] = b;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (t < w) {
+      sh[t] = __dadd_rn(sh[t], sh[t + w]);
+      sh[256 + t] = __dadd_rn(sh[256 + t], sh[256 + t + w]);
+    }
+    __syncthreads();
+  }
+  a = sh[0]; b = sh[256];
+}
+
+__global__ void __launch_bounds__(256) mass_partial_kernel(const __grid_constant__ MassParams P, double* __restrict__ part) {
+  __shared__ double sh[512];
+  double neutral = 0., total = 0.;
+  // a block owns one contiguous slab of leaves, a thread every 256th leaf of it: the order is fixed by (N) alone
+  const int64_t per = (P.N + kMassBlocks - 1) / kMassBlocks;
+  const int64_t lo = blockIdx.x * per, hi = lo + per < P.N ? lo + per : P.N;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
+    const double cube = P.cube[P.level[i]];
+    neutral = __dadd_rn(neutral, __ddiv_rn(__dmul_rn(__dmul_rn(P.HI[i], P.mh), cube), P.msun));
+    total = __dadd_rn(total, __ddiv_rn(__dmul_rn(__dmul_rn(P.psi, P.rho[i]), cube), P.msun));
+  }
+  block_sum2(neutral, total, sh);
+  if (threadIdx.x == 0) { part[blockIdx.x] = neutral; part[kMassBlocks + blockIdx.x] = total; }
+}
+
+__global__ void __launch_bounds__(256) mass_final_kernel(const double* __restrict__ part, double* __restrict__ out) {
+  __shared__ double sh[512];
+  double neutral = 0., total = 0.;
+  for (int i = threadIdx.x; i < kMassBlocks; i += 256) {
+    neutral = __dadd_rn(neutral, part[i]);
+    total = __dadd_rn(total, part[kMassBlocks + i]);
+  }
+  block_sum2(neutral, total, sh);
+  if (threadIdx.x == 0) { out[0] = neutral; out[1] = total; }
+}
+
+int compute_mass(Context& c, double* neutralHydrogenMass, double* totalHydrogenMass, cudaStream_t s) {
+  if (c.nleaf == 0 || !c.dRho || !c.dHI || !neutralHydrogenMass || !totalHydrogenMass) return RTB200_ERR_ARG;
+  RTB_CUDA(cudaSetDevice(c.device));
+  MassParams P{};
+  P.level = c.dLevel; P.HI = c.dHI; P.rho = c.dRho; P.N = c.nleaf;
+  for (int l = 0; l < 32; l++) {
+    const double size = l < 31 ? c.boxSize / ((double)(float)(1u << l) * (double)(float)c.nx) : 0.;
+    P.cube[l] = size * size * size;            // x**3 -> x*x*x
+  }
+  P.mh = (double)1.6726231e-24f;               // definitionsModule.f90:27 (single-precision literal)
+  P.msun = (double)1.98892e33f;                // :29
+  P.psi = (double)0.76f;                       // :261
+  if (!c.dMassPart) RTB_CUDA(cudaMalloc((void**)&c.dMassPart, (2 * kMassBlocks + 2) * sizeof(double)));
+  mass_partial_kernel<<<kMassBlocks, 256, 0, s>>>(P, c.dMassPart);
+  mass_final_kernel<<<1, 256, 0, s>>>(c.dMassPart, c.dMassPart + 2 * kMassBlocks);
+  RTB_CUDA(cudaGetLastError());
+  double out[2];
+  RTB_CUDA(cudaMemcpyAsync(out, c.dMassPart + 2 * kMassBlocks, sizeof(out), cudaMemcpyDeviceToHost, s));
+  RTB_CUDA(cudaStreamSynchronize(s));
+  *neutralHydrogenMass = out[0];
+  *totalHydrogenMass = out[1];
+  return RTB200_OK;
+}
+
 }  // namespace rtb

@@ -135,6 +135,7 @@ struct Context {
   int chemNratec = 0;
   double chemLogtem0 = 0, chemLogtem9 = 0, chemDlogtem = 0;
   double* dLogT = nullptr;   // [nleaf]
+  double* dMassPart = nullptr;  // computeMass partial sums
   double* dKappa = nullptr;  // [3][nleaf]
   double* dKappaT = nullptr; // [3][nleaf] z-major copy (index (z*n + x)*n + y) for the uniform sweep, lazily allocated
   size_t kappaTBytes = 0;
@@ -198,6 +199,7 @@ int launch_diffuse_rates(Context& c, const double* J, const double* ksi24, const
 
 int chemistry_set_tables(Context& c, int nratec, double logtem0, double logtem9, double dlogtem, const double* const k[6]);
 int chemistry_set_temperature(Context& c, const double* tgas);
+int compute_mass(Context& c, double* neutralHydrogenMass, double* totalHydrogenMass, cudaStream_t s);
 int chemistry_run(Context& c, const double* dRates, const double* dJ, const double* ksi, const double* uniform,
                   double* maxChange, cudaStream_t s);
 

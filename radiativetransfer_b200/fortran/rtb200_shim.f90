@@ -68,6 +68,12 @@ module rtb200_shim
        import :: c_int, c_ptr
        type(c_ptr), value :: ctx, rates_device, J_device, ksi, uniform, maxChange, stream
      end function rtb200_chemistry_device
+     integer(c_int) function rtb200_compute_mass(ctx, neutralMass, totalMass, stream) bind(C, name='rtb200_compute_mass')
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       real(c_double), intent(out) :: neutralMass, totalMass   ! neutralHydrogenMass, totalHydrogenMass [msun]
+       type(c_ptr), value :: stream
+     end function rtb200_compute_mass
      integer(c_int) function rtb200_grid_get_species(ctx, HI, HeI, HeII) bind(C, name='rtb200_grid_get_species')
        import :: c_int, c_ptr
        type(c_ptr), value :: ctx, HI, HeI, HeII

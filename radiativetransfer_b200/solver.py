@@ -224,6 +224,14 @@ class Transport:
         _lib.check(self.L.rtb200_grid_get_species(self.h, _ptr(HI), _ptr(HeI), _ptr(HeII)), "rtb200_grid_get_species")
         return HI, HeI, HeII
 
+    def compute_mass(self, stream=0):
+        """(neutralHydrogenMass, totalHydrogenMass) in solar masses from the device copies of HI and rho: computeMass,
+        equiSources.f90:4369-4393 (the driver prints their ratio after every chemistry pass, :1828-1836)."""
+        a, b = C.c_double(0), C.c_double(0)
+        _lib.check(self.L.rtb200_compute_mass(self.h, C.byref(a), C.byref(b), C.c_void_p(int(stream))),
+                   "rtb200_compute_mass")
+        return a.value, b.value
+
     def device_error(self):
         return self.L.rtb200_device_error(self.h)
 

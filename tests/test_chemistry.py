@@ -121,3 +121,45 @@ def test_outer_iteration_stays_on_the_device(build_product, oracle, uvbg):
     nh = W.PSI * g["rho"] / W.MP
     assert np.max(np.abs(gHI - HI) / nh) < 1e-9           # J agrees to ~1e-13; the bisection is Lipschitz in the rates
     assert np.max(np.abs(gHeI - HeI) / nh) < 1e-9
+
+
+def test_oracle_compute_mass_known_answer(oracle):
+    """computeMass (equiSources.f90:4369-4393): constant density in a nested grid -> mass = density x box volume,
+    whatever the refinement (the leaves tile the box); the neutral mass follows HI the same way"""
+    g = _gas(6, 21, levels=2)
+    N = g["level"].size
+    rho0, hi0 = 3.0e-25, 2.0e-3
+    neutral, total = oracle.compute_mass(6, g["box_size"], g["level"], np.full(N, hi0), np.full(N, rho0))
+    msun, mh, psi = float(np.float32(1.98892e33)), float(np.float32(1.6726231e-24)), float(np.float32(0.76))
+    vol = g["box_size"] ** 3
+    assert abs(total - psi * rho0 * vol / msun) <= 1e-12 * total
+    assert abs(neutral - hi0 * mh * vol / msun) <= 1e-12 * neutral
+    # and a direct numpy evaluation with random fields (pairwise summation: agreement to rounding)
+    size = g["box_size"] / (2.0 ** g["level"].astype(np.float64) * 6)
+    neutral, total = oracle.compute_mass(6, g["box_size"], g["level"], g["HI"], g["rho"])
+    assert abs(total - np.sum(psi * g["rho"] * size ** 3 / msun)) <= 1e-12 * total
+    assert abs(neutral - np.sum(g["HI"] * mh * size ** 3 / msun)) <= 1e-12 * neutral
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,levels", [(8, 0), (6, 2), (40, 0), (1, 0)])
+def test_gpu_compute_mass_matches_oracle(build_product, oracle, n, levels):
+    """rtb200_compute_mass: same per-leaf terms as the reference, summed as a fixed tree instead of serially ->
+    equal to rounding of the summation order, and reproducible; it sees the species the chemistry step left"""
+    import radiativetransfer_b200 as rt
+    g = _gas(n, 31 + n, levels)
+    t = rt.Transport(device=0)
+    t.set_grid(g["nx"], g["level"], g["HI"], g["HeI"], g["HeII"], g["rho"], g["abun2"], g["box_size"])
+    a = t.compute_mass()
+    assert a == t.compute_mass()
+    o = oracle.compute_mass(g["nx"], g["box_size"], g["level"], g["HI"], g["rho"])
+    assert abs(a[0] - o[0]) <= 1e-12 * o[0] and abs(a[1] - o[1]) <= 1e-12 * o[1]
+    t.update_species(HI=0.5 * g["HI"])
+    b = t.compute_mass()
+    o2 = oracle.compute_mass(g["nx"], g["box_size"], g["level"], 0.5 * g["HI"], g["rho"])
+    assert abs(b[0] - o2[0]) <= 1e-12 * o2[0] and b[1] == a[1]
+    t.close()
+    fresh = rt.Transport(device=0)
+    with pytest.raises(rt.RTB200Error):
+        fresh.compute_mass()                                  # no grid yet
+    fresh.close()
