@@ -273,6 +273,7 @@ int rtb200_set_tuning(rtb200_ctx* h, const char* key, double value) {
   else if (k == "march_debug") c.tune.marchDebug = (int)value;
   else if (k == "portable_math") c.tune.portableMath = (int)value;
   else if (k == "point_batch") c.tune.pointBatch = (int)value;
+  else if (k == "point_min_blocks") c.tune.pointMinBlocks = (int)value;
   else if (k == "point_refill") c.tune.pointRefill = (int)value;
   else if (k == "point_deposit") c.tune.pointDeposit = (int)value;
   else if (k == "point_record_cap") c.tune.pointRecordCap = (long long)value;

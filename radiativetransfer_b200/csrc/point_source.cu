@@ -308,8 +308,8 @@ __device__ __forceinline__ void rates_fast(const PointParams& P, const double* _
 }
 
 // --------------------------------------------------------------------------------------------------------------------
-template <bool FAITHFUL, bool PORTABLE, bool TRACE, bool SEGMENTED>
-__global__ void __launch_bounds__(128, 4) point_march_kernel(const __grid_constant__ PointParams P, int pixelLevel) {
+template <bool FAITHFUL, bool PORTABLE, bool TRACE, bool SEGMENTED, int MINB = 4>
+__global__ void __launch_bounds__(128, MINB) point_march_kernel(const __grid_constant__ PointParams P, int pixelLevel) {
   __shared__ double sT[16];
   if (threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
   __syncthreads();
@@ -940,7 +940,11 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
       } else {
         if (portable) point_march_kernel<true, true, false, false><<<g, 128, 0, s>>>(P, L);
         else if (faithful) point_march_kernel<true, false, false, false><<<g, 128, 0, s>>>(P, L);
-        else point_march_kernel<false, false, false, false><<<g, 128, 0, s>>>(P, L);
+        // FAST arithmetic, RED deposition: the register budget is a tuning knob ("point_min_blocks": 4 = 128
+        // registers, 5 = 96, 6 = 80 with spills)
+        else if (c.tune.pointMinBlocks >= 6) point_march_kernel<false, false, false, false, 6><<<g, 128, 0, s>>>(P, L);
+        else if (c.tune.pointMinBlocks == 5) point_march_kernel<false, false, false, false, 5><<<g, 128, 0, s>>>(P, L);
+        else point_march_kernel<false, false, false, false, 4><<<g, 128, 0, s>>>(P, L);
       }
       c.lastLaunches++;
       c.lastSweepLaunches++;

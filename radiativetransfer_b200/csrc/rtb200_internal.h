@@ -79,6 +79,7 @@ struct Tuning {
                          // radix sort by (leaf, ray, segment), one thread per cell adds its run (deterministic order)
   long long pointRecordCap = 0;  // upper limit of the record buffer of mode 1 (0 = 60% of the free memory)
   int pointRefill = 0;   // point path, last pixel level: 1 = lanes take further rays from a per-source queue (fuller warps but
+  int pointMinBlocks = 5;  // point march kernel (FAST, RED deposition): blocks of 128 threads per SM the register cap allows (5: 96 registers)
                          // incoherent gathers: measured slower)
   int pointBatch = 0;    // sources per batch of the point path (0 = as many as fit in half of the free memory)
 };

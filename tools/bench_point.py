@@ -20,6 +20,7 @@ ap.add_argument("--dust", type=int, default=0)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--uniform", action="store_true")
 ap.add_argument("--deposit", type=int, default=0)
+ap.add_argument("--min-blocks", type=int, nargs="+", default=[4])
 args = ap.parse_args()
 
 t0 = time.time()
@@ -32,8 +33,9 @@ t.set_tuning(point_deposit=args.deposit)
 R = torch.zeros(6, g["level"].size, dtype=torch.float64, device="cuda:0")
 s = torch.cuda.current_stream().cuda_stream
 wt = np.ones(args.nsrc, dtype=np.int32)
-for mode in args.modes:
+for mode, minb in [(m, b) for m in args.modes for b in (args.min_blocks if m == "fast" else [4])]:
     t.set_math(rt.MATH_FAST if mode == "fast" else rt.MATH_FAITHFUL)
+    t.set_tuning(point_min_blocks=minb)
     for rep in range(args.reps + 1):
         R.zero_()
         torch.cuda.synchronize()
@@ -42,7 +44,7 @@ for mode in args.modes:
         torch.cuda.synchronize()
         wall = (time.perf_counter() - w0) * 1e3
         st = t.last_stats()
-        print(f"n={args.n} nsrc={args.nsrc} dust={args.dust} deposit={args.deposit} mode={mode}: device_ms={st['device_ms']:.2f} wall_ms={wall:.2f} "
+        print(f"n={args.n} nsrc={args.nsrc} dust={args.dust} deposit={args.deposit} mode={mode} min_blocks={minb}: device_ms={st['device_ms']:.2f} wall_ms={wall:.2f} "
               f"nseg={nseg} seg/s={nseg / st['device_ms'] * 1e3:.3e} alg GB/s={st['algorithmic_bytes'] / st['device_ms'] / 1e6:.1f} "
               f"sum(krate24)={float(R[0].sum()):.6e}", flush=True)
 t.close()
