@@ -18,7 +18,7 @@
 // different rays add to the same cell differs.
 //
 // Data layout: the grid is the per-leaf SoA of the context (leaf order of the reference) + the linear octree
-// `child[]`; per-source log-tables [6][planes][11^3] (64 KB without dust: L1/L2 resident); ray end states
+// `child[]`; per-source log-tables [planes][11^3][8 slots] (85 KB without dust: L1/L2 resident); ray end states
 // [source][pixel] AoS of 80 B, ping-pong between levels; rates [6][nleaf] fp64, accumulated with fp64 RED
 // (atomicAdd, native on sm_100) -- the deterministic, atomic-free segmented variant sorts (leaf, deposit) records.
 #include <algorithm>
@@ -37,6 +37,10 @@ namespace rtb {
 namespace {
 
 constexpr int kPlane = 11 * 11 * 11;
+// log-tables are node-major: [source][dust plane][i3][i2][i1][kSlots], slot 2r = number table of reaction r (24, 26,
+// 25), slot 2r+1 = its energy table, slots 6,7 unused: a node is one 64-byte record, and the (number, energy) pair of
+// a reaction is one 16-byte load
+constexpr int kSlots = 8;
 constexpr int kDiagStride = 320;  // per source: remaining[7], boundary[7], dust, pad, spectrum[300]
 constexpr int kMaxPixelLevel = 8;
 
@@ -65,7 +69,7 @@ struct PointParams {
   // sources of this batch
   const int32_t* srcLeaf;
   const int32_t* srcWeight;
-  const double* logTab;   // [nsrc][6][planes][kPlane]
+  const double* logTab;   // [nsrc][planes][kPlane][kSlots]
   int planes;             // 1 without dust, 11 with
   int dust;
   int maxPixelLevel;
@@ -156,14 +160,36 @@ __device__ __forceinline__ bool step_neighbour(const PointParams& P, Cell& c, in
 template <bool PORTABLE>
 __device__ __forceinline__ double exp_ref(double x) { return PORTABLE ? rtb_pm::pm_exp(x) : exp(x); }
 
-__device__ __forceinline__ double interp_log(const double* __restrict__ T, int i1, int i2, int i3, double c1, double c2,
-                                             double c3) {
+struct Pair {
+  double n, e;  // number table, energy table
+};
+__device__ __forceinline__ Pair ld_pair(const double2* p) {
+  const double2 v = __ldg(p);
+  return Pair{v.x, v.y};
+}
+
+// both tables of one reaction at once: T points at slot 2r of node (0,0,0) of the dust plane; node stride = kSlots
+// doubles = 4 double2.  Each table's operation sequence is the reference's (equiSources.f90:4205-4238).
+__device__ __forceinline__ Pair interp_log(const double2* __restrict__ T, int i1, int i2, int i3, double c1, double c2,
+                                           double c3) {
+  constexpr int N = kSlots / 2;
   const double m3 = S(1., c3), m2 = S(1., c2), m1 = S(1., c1);
   const double w00 = M(m3, m2), w01 = M(c3, m2), w10 = M(c2, m3), w11 = M(c3, c2);
-  const double* p = T + (i3 * 11 + i2) * 11 + i1;
-  const double up = A(A(A(M(w00, __ldg(p + 1)), M(w01, __ldg(p + 122))), M(w10, __ldg(p + 12))), M(w11, __ldg(p + 133)));
-  const double lo = A(A(A(M(w00, __ldg(p)), M(w01, __ldg(p + 121))), M(w10, __ldg(p + 11))), M(w11, __ldg(p + 132)));
-  return A(M(c1, up), M(m1, lo));
+  const double2* p = T + ((i3 * 11 + i2) * 11 + i1) * N;
+  const Pair u0 = ld_pair(p + N), u1 = ld_pair(p + 122 * N), u2 = ld_pair(p + 12 * N), u3 = ld_pair(p + 133 * N);
+  const Pair l0 = ld_pair(p), l1 = ld_pair(p + 121 * N), l2 = ld_pair(p + 11 * N), l3 = ld_pair(p + 132 * N);
+  Pair r;
+  {
+    const double up = A(A(A(M(w00, u0.n), M(w01, u1.n)), M(w10, u2.n)), M(w11, u3.n));
+    const double lo = A(A(A(M(w00, l0.n), M(w01, l1.n)), M(w10, l2.n)), M(w11, l3.n));
+    r.n = A(M(c1, up), M(m1, lo));
+  }
+  {
+    const double up = A(A(A(M(w00, u0.e), M(w01, u1.e)), M(w10, u2.e)), M(w11, u3.e));
+    const double lo = A(A(A(M(w00, l0.e), M(w01, l1.e)), M(w10, l2.e)), M(w11, l3.e));
+    r.e = A(M(c1, up), M(m1, lo));
+  }
+  return r;
 }
 
 struct DepthIdx {
@@ -208,19 +234,16 @@ __device__ __forceinline__ int rates_faithful(const PointParams& P, const double
   const DepthIdx q = depth_index(t1, t2, t3, tD, P.dust);
   if (q.status == 1) { num = 0.; heat = 0.; return 0; }
   if (q.status < 0) return RTB200_ERR_IDEPTH;
-  const double* R = LT + (size_t)r * P.planes * kPlane + (size_t)q.iD * kPlane;
-  const double* E = LT + (size_t)(3 + r) * P.planes * kPlane + (size_t)q.iD * kPlane;
-  const double nr1 = interp_log(R, q.i1, q.i2, q.i3, q.c1, q.c2, q.c3);
-  const double hr1 = interp_log(E, q.i1, q.i2, q.i3, q.c1, q.c2, q.c3);
+  const double2* T = reinterpret_cast<const double2*>(LT + (size_t)q.iD * kPlane * kSlots + 2 * r);
+  const Pair v1 = interp_log(T, q.i1, q.i2, q.i3, q.c1, q.c2, q.c3);
   if (P.dust) {
-    const double nr2 = interp_log(R + kPlane, q.i1, q.i2, q.i3, q.c1, q.c2, q.c3);
-    const double hr2 = interp_log(E + kPlane, q.i1, q.i2, q.i3, q.c1, q.c2, q.c3);
+    const Pair v2 = interp_log(T + kPlane * (kSlots / 2), q.i1, q.i2, q.i3, q.c1, q.c2, q.c3);
     const double mD = S(1., q.cD);
-    num = exp_ref<PORTABLE>(A(M(mD, nr1), M(q.cD, nr2)));
-    heat = exp_ref<PORTABLE>(A(M(mD, hr1), M(q.cD, hr2)));
+    num = exp_ref<PORTABLE>(A(M(mD, v1.n), M(q.cD, v2.n)));
+    heat = exp_ref<PORTABLE>(A(M(mD, v1.e), M(q.cD, v2.e)));
   } else {  // cDust = 0: exp((1.-0.)*nr1 + 0.*nr2) == exp(nr1) exactly; the second dust plane is never needed
-    num = exp_ref<PORTABLE>(nr1);
-    heat = exp_ref<PORTABLE>(hr1);
+    num = exp_ref<PORTABLE>(v1.n);
+    heat = exp_ref<PORTABLE>(v1.e);
   }
   return 0;
 }
@@ -233,21 +256,36 @@ __device__ __forceinline__ int rates_faithful(const PointParams& P, const double
 // value of the log-interpolant restricted to the table nodes with index iAx along AXIS (0,1,2 = tau1,tau2,tau3), at
 // the transverse position of q: a bilinear (with dust: trilinear) combination of 4 (8) nodes
 template <int AXIS>
-__device__ __forceinline__ double face_sum(const double* __restrict__ T, int iAx, const DepthIdx& q, int dust) {
-  constexpr int sA = AXIS == 0 ? 1 : (AXIS == 1 ? 11 : 121);
-  constexpr int s1 = AXIS == 0 ? 11 : 1, s2 = AXIS == 2 ? 11 : 121;   // strides of the two transverse depth axes
+__device__ __forceinline__ Pair face_sum(const double2* __restrict__ T, int iAx, const DepthIdx& q, int dust) {
+  constexpr int N = kSlots / 2;                                        // node stride in double2
+  constexpr int sA = (AXIS == 0 ? 1 : (AXIS == 1 ? 11 : 121)) * N;
+  constexpr int s1 = (AXIS == 0 ? 11 : 1) * N, s2 = (AXIS == 2 ? 11 : 121) * N;   // the two transverse depth axes
   const int j1 = AXIS == 0 ? q.i2 : q.i1, j2 = AXIS == 2 ? q.i2 : q.i3;
   const double c1 = AXIS == 0 ? q.c2 : q.c1, c2 = AXIS == 2 ? q.c2 : q.c3;
-  const double* p = T + iAx * sA + j1 * s1 + j2 * s2 + q.iD * kPlane;
-  const double a0 = __ldg(p), a1 = __ldg(p + s1), b0 = __ldg(p + s2), b1 = __ldg(p + s1 + s2);
-  const double lo = fma(c1, a1 - a0, a0), hi = fma(c1, b1 - b0, b0);
-  double v = fma(c2, hi - lo, lo);
+  const double2* p = T + iAx * sA + j1 * s1 + j2 * s2 + q.iD * (kPlane * N);
+  const Pair a0 = ld_pair(p), a1 = ld_pair(p + s1), b0 = ld_pair(p + s2), b1 = ld_pair(p + s1 + s2);
+  Pair v;
+  {
+    const double lo = fma(c1, a1.n - a0.n, a0.n), hi = fma(c1, b1.n - b0.n, b0.n);
+    v.n = fma(c2, hi - lo, lo);
+  }
+  {
+    const double lo = fma(c1, a1.e - a0.e, a0.e), hi = fma(c1, b1.e - b0.e, b0.e);
+    v.e = fma(c2, hi - lo, lo);
+  }
   if (dust) {
-    const double* d = p + kPlane;
-    const double e0 = __ldg(d), e1 = __ldg(d + s1), f0 = __ldg(d + s2), f1 = __ldg(d + s1 + s2);
-    const double lo2 = fma(c1, e1 - e0, e0), hi2 = fma(c1, f1 - f0, f0);
-    const double v2 = fma(c2, hi2 - lo2, lo2);
-    v = fma(q.cD, v2 - v, v);
+    const double2* d = p + kPlane * N;
+    const Pair e0 = ld_pair(d), e1 = ld_pair(d + s1), f0 = ld_pair(d + s2), f1 = ld_pair(d + s1 + s2);
+    {
+      const double lo2 = fma(c1, e1.n - e0.n, e0.n), hi2 = fma(c1, f1.n - f0.n, f0.n);
+      const double v2 = fma(c2, hi2 - lo2, lo2);
+      v.n = fma(q.cD, v2 - v.n, v.n);
+    }
+    {
+      const double lo2 = fma(c1, e1.e - e0.e, e0.e), hi2 = fma(c1, f1.e - f0.e, f0.e);
+      const double v2 = fma(c2, hi2 - lo2, lo2);
+      v.e = fma(q.cD, v2 - v.e, v.e);
+    }
   }
   return v;
 }
@@ -273,33 +311,30 @@ template <int AXIS>
 __device__ __forceinline__ void rates_fast(const PointParams& P, const double* __restrict__ LT, const DepthIdx& q,
                                            double depthAxis, double tau, const double* __restrict__ sT, double& dnum,
                                            double& dheat) {
-  const double* R = LT + (size_t)AXIS * P.planes * kPlane;
-  const double* E = LT + (size_t)(3 + AXIS) * P.planes * kPlane;
+  const double2* T = reinterpret_cast<const double2*>(LT + 2 * AXIS);   // slot pair of this reaction
   if (tau == 0.) { dnum = 0.; dheat = 0.; return; }  // R(d) - R(d) (e.g. no helium: tau2 = tau3 = 0)
   const int i0 = AXIS == 0 ? q.i1 : (AXIS == 1 ? q.i2 : q.i3);
   const double c0 = AXIS == 0 ? q.c1 : (AXIS == 1 ? q.c2 : q.c3);
-  double Lr = face_sum<AXIS>(R, i0, q, P.dust), Hr = face_sum<AXIS>(R, i0 + 1, q, P.dust);
-  double Le = face_sum<AXIS>(E, i0, q, P.dust), He = face_sum<AXIS>(E, i0 + 1, q, P.dust);
-  const double n0 = exp_tab(fma(c0, Hr - Lr, Lr), sT), h0 = exp_tab(fma(c0, He - Le, Le), sT);
+  Pair L = face_sum<AXIS>(T, i0, q, P.dust), H = face_sum<AXIS>(T, i0 + 1, q, P.dust);
+  const double n0 = exp_tab(fma(c0, H.n - L.n, L.n), sT), h0 = exp_tab(fma(c0, H.e - L.e, L.e), sT);
   const double end = depthAxis + tau;
   if (end > 10.) { dnum = n0; dheat = h0; return; }  // the table returns 0 beyond tau = 10
   int iEnd = (int)end;
   if (iEnd > 9) iEnd = 9;
   double dn, dh;
   if (iEnd <= i0) {  // the step stays inside the start cell (the common case)
-    dn = tau * (Hr - Lr);
-    dh = tau * (He - Le);
+    dn = tau * (H.n - L.n);
+    dh = tau * (H.e - L.e);
   } else {
     const double first = (double)(i0 + 1) - depthAxis;
-    dn = first * (Hr - Lr);
-    dh = first * (He - Le);
+    dn = first * (H.n - L.n);
+    dh = first * (H.e - L.e);
     for (int c = i0 + 1; c <= iEnd; c++) {
-      Lr = Hr; Le = He;
-      Hr = face_sum<AXIS>(R, c + 1, q, P.dust);
-      He = face_sum<AXIS>(E, c + 1, q, P.dust);
+      L = H;
+      H = face_sum<AXIS>(T, c + 1, q, P.dust);
       const double len = c == iEnd ? end - (double)c : 1.0;
-      dn = fma(len, Hr - Lr, dn);
-      dh = fma(len, He - Le, dh);
+      dn = fma(len, H.n - L.n, dn);
+      dh = fma(len, H.e - L.e, dh);
     }
   }
   // the tables fall with depth (dn, dh <= 0); a rising table (never with physical spectra) takes the libm route
@@ -428,7 +463,7 @@ __global__ void __launch_bounds__(128, MINB) point_march_kernel(const __grid_con
   return active;
   };  // init_ray
 
-  const double* LT = P.logTab + (size_t)s * 6 * P.planes * kPlane;
+  const double* LT = P.logTab + (size_t)s * P.planes * kPlane * kSlots;
   const double rmaxL = P.rmax[pixelLevel];
   bool have0 = false;      // static map: this thread's own ray exists
   bool exhausted = weight <= 0;
@@ -639,7 +674,7 @@ struct TableParams {
   const double* freq;   // [7][400]: r24, r26, r25, rD, ew1, ew2, ew3   (ew_r = (nu - nu_r) * eV_to_erg)
   int thr[3];           // first frequency index with nu >= nu_r
   const double* dtmp;   // [nsrc][400] photons/s per bin
-  double* logTab;       // [nsrc][6][planes][kPlane]
+  double* logTab;       // [nsrc][planes][kPlane][kSlots]
   double* rawTab;       // optional [nsrc][6][planes][kPlane]
   int planes;
 };
@@ -668,13 +703,15 @@ __global__ void __launch_bounds__(128) point_table_kernel(const __grid_constant_
         E[r] = A(E[r], M(sh[4 + r][i], a));
       }
   }
-  const size_t base = (size_t)s * 6 * T.planes * kPlane;
+  const size_t base = (size_t)s * 6 * T.planes * kPlane;                          // raw copy: the reference's layout
+  double* node = T.logTab + ((size_t)s * T.planes * kPlane + e) * kSlots;         // node-major log-tables
   for (int r = 0; r < 3; r++) {
     const size_t oR = base + (size_t)r * T.planes * kPlane + e, oE = base + (size_t)(3 + r) * T.planes * kPlane + e;
-    T.logTab[oR] = PORTABLE ? rtb_pm::pm_log(R[r]) : log(R[r]);
-    T.logTab[oE] = PORTABLE ? rtb_pm::pm_log(E[r]) : log(E[r]);
+    node[2 * r] = PORTABLE ? rtb_pm::pm_log(R[r]) : log(R[r]);
+    node[2 * r + 1] = PORTABLE ? rtb_pm::pm_log(E[r]) : log(E[r]);
     if (T.rawTab) { T.rawTab[oR] = R[r]; T.rawTab[oE] = E[r]; }
   }
+  node[6] = 0.; node[7] = 0.;
 }
 
 // Segmented, atomic-free deposition.  The march kernel emits one (leaf, 6 deposits) record per segment; the records'
@@ -822,7 +859,7 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
 
   // ---- batches of sources ----
   int64_t npixMax = 12LL << (2 * (std::max(in.maxPixelLevel, 2) - 2));  // states of level maxPixelLevel-1
-  const size_t perSrc = (size_t)6 * planes * kPlane * 8 + 2 * (size_t)npixMax * sizeof(RayState) + kDiagStride * 8 + kNfreq * 8;
+  const size_t perSrc = (size_t)kSlots * planes * kPlane * 8 + 2 * (size_t)npixMax * sizeof(RayState) + kDiagStride * 8 + kNfreq * 8;
   size_t freeB = 0, totalB = 0;
   RTB_CUDA(cudaMemGetInfo(&freeB, &totalB));
   int batch = (int)std::min<size_t>((size_t)nsrc, std::max<size_t>(1, (freeB / 2) / perSrc));
@@ -834,7 +871,7 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
   double *dDtmp, *dLogTab, *dRaw = nullptr, *dDiag;
   RayState *dStA, *dStB;
   if (int st = sc.get(&dDtmp, (size_t)batch * kNfreq)) return st;
-  if (int st = sc.get(&dLogTab, (size_t)batch * 6 * planes * kPlane)) return st;
+  if (int st = sc.get(&dLogTab, (size_t)batch * kSlots * planes * kPlane)) return st;
   if (hRawTables) { if (int st = sc.get(&dRaw, (size_t)batch * 6 * planes * kPlane)) return st; }
   if (int st = sc.get(&dDiag, (size_t)batch * kDiagStride)) return st;
   if (int st = sc.get(&dStA, (size_t)batch * npixMax)) return st;
