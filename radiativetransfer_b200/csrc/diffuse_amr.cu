@@ -14,7 +14,13 @@
 //    along every dependency edge when neighbouring leaves differ by at most one level; one launch per wave for all
 //    directions of the batch.  Grids that violate the 2:1 balance are still handled exactly: a leaf whose upstream
 //    leaf has not been published yet is put on a deferred list that is retried after every wave.
-//  * J is accumulated with fp64 atomics (several directions update a leaf concurrently); everything else is the
+//  * Items are stored DIRECTION-fastest: the directions of a batch are grouped by zone (up to 8 per group: same index
+//    rotation, hence the same upstream leaves away from refinement boundaries), 8 adjacent lanes of a warp work on
+//    the 8 directions of one leaf, and the per-item arrays are [group][leaf][8]: what a warp gathers for a leaf --
+//    neighbour records, upstream intensities -- is contiguous, and per-leaf data (opacity, pattern index) is read
+//    once per 8 lanes.  (A wave is a diagonal plane of the grid: leaf-fastest items shared no sectors at all.)
+//  * J is accumulated with fp64 atomics (several directions update a leaf concurrently), after a fixed-order
+//    shuffle sum over the 8 directions of a group; everything else is the
 //    reference's arithmetic (segment_math.cuh), incl. the coarse-neighbour averaging fallback
 //    (transportRoutinesModule.f90:612-634) and the intensity guard (:680-688).
 #include <algorithm>
@@ -26,24 +32,30 @@
 
 namespace rtb {
 
-struct DevPattern {      // subset of RayPattern the device needs (96 B)
-  double len[3];         // xy, yz, xz   (ray id 0, 1, 2)
-  double dpath[3];       // cellSize(level) * len, multiplied on the host exactly as the kernel used to
-  double cellSize;       // of the table's level
-  double e0[3], e1[3];   // entry point of each ray on its face: xy (x0,y0), yz (y0,z0), xz (x0,z0)
+struct alignas(32) DevPattern {   // subset of RayPattern the device needs, 96 B = three 32-byte sectors
+  // first sector: all the sweep reads
+  double dpath[3];       // cellSize(level) * len per ray (xy, yz, xz = ray id 0, 1, 2), multiplied on the host
   int8_t top[3];         // xyTop, yzTop, xzTop: which ray (1 xy, 2 yz, 3 xz) leaves through the top / x=1 / y=1 face
   int8_t active[3];      // xy (always), yz, xz
   int8_t level;          // refinement level of the table
   int8_t pad[1];
+  // neighbour threading only
+  double e0[3], e1[3];   // entry point of each ray on its face: xy (x0,y0), yz (y0,z0), xz (x0,z0)
+  double pad2[2];
 };
+static_assert(sizeof(DevPattern) == 96, "DevPattern is three sectors");
 
 struct AmrDir {          // one direction of the batch
   int8_t src[3], refl[3];  // zone map: physical component c takes rotated index src[c], reflected if refl[c]
   int8_t inv[3];           // rotated axis r is physical component inv[r]
   int8_t combo;            // reflection combination 0..7 -> wave order
+  int8_t patRow;           // row of patIdx[6][N] this direction reads: sweep axis (0..2), +3 if that axis is reflected
   int32_t patBase;         // offset of this direction's pattern tables
+  int32_t group, lane;     // where the direction's items live: group of the batch, lane 0..7 inside it
   double w;                // weight
 };
+static_assert(sizeof(AmrDir) == 32, "one sector per direction");
+constexpr int kGroup = 8;  // directions per group (a zone has 8 at nAngularLevel = 3)
 
 struct AmrParams {
   const int32_t* child;
@@ -53,14 +65,15 @@ struct AmrParams {
   const DevPattern* pats;
   const int32_t* levelOff; // [maxLevel+2] offsets of the per-level tables inside one direction's block
   const AmrDir* dirs;
-  int32_t* nb;             // [ndir][3][N] upstream leaf per ray (xy, yz, xz): -1 boundary, -2 inactive
-  uint8_t* code;           // [ndir][3][N] what to read from the upstream leaf
-  int32_t* nbc;            // [ndir][N][4] the same packed for the sweep: leaf << 3 | code (or -1 / -2) per ray, 16 B per item
+  const int2* groups;      // [ngroups] (first direction of the batch, number of directions <= 8)
+  int32_t* nb;             // debugging export only: [ndir][3][N] upstream leaf per ray (xy, yz, xz): -1 boundary, -2 inactive
+  uint8_t* code;           // debugging export only: [ndir][3][N] what to read from the upstream leaf
+  int32_t* nbc;            // [group][N][8][4] the same packed for the sweep: leaf << 3 | code (or -1 / -2) per ray, 16 B per item
   const int32_t* patIdx;   // [6][N] levelOff[level] + coordinate along physical axis a (a = 0..2), then reflected (3..5)
   const double* kappaA;    // [N][3] opacities, leaf-major (one gather instead of three)
   double* JA;              // [N][3] accumulator, leaf-major (atomics), un-interleaved into J at the end
-  double* Iout;            // [ndir][N][9]
-  uint8_t* done;           // [ndir][N]
+  double* Iout;            // [group][3 rays][N][8][4]: 3 frequency groups + pad, one 32-byte sector per record
+  uint8_t* done;           // [group][N][8]
   double* J;               // [3][N] (atomics)
   int32_t* err;
   int64_t N;
@@ -87,10 +100,19 @@ __device__ __forceinline__ int node_at(const int32_t* __restrict__ child, int n,
   return node;
 }
 
-__global__ void amr_neighbour_kernel(AmrParams P, int ndir) {
-  const int64_t leaf = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int d = blockIdx.y;
-  if (leaf >= P.N || d >= ndir) return;
+// item (direction lane of a group, leaf) -> index into the [group][N][8] arrays
+__device__ __forceinline__ int64_t item_index(const AmrParams& P, int group, int lane, int64_t leaf) {
+  return ((int64_t)group * P.N + leaf) * kGroup + lane;
+}
+
+// block = 16 leaves x 8 direction lanes, blockIdx.y = group
+__global__ void amr_neighbour_kernel(AmrParams P, int ngroups) {
+  const int64_t leaf = blockIdx.x * (int64_t)(blockDim.x / kGroup) + threadIdx.x / kGroup;
+  const int gi = blockIdx.y, lane = threadIdx.x % kGroup;
+  if (leaf >= P.N || gi >= ngroups) return;
+  const int2 grp = P.groups[gi];
+  if (lane >= grp.y) return;
+  const int d = grp.x + lane;
   const AmrDir D = P.dirs[d];
   const int L = P.level[leaf];
   const int nL = P.n << L;
@@ -157,9 +179,11 @@ __global__ void amr_neighbour_kernel(AmrParams P, int ndir) {
         b = cb ? b / 2. + 0.5 : b / 2.;
       }
     }
-    P.nb[((int64_t)d * 3 + ray) * P.N + leaf] = result;
-    P.code[((int64_t)d * 3 + ray) * P.N + leaf] = code;
-    if (P.nbc) P.nbc[((int64_t)d * P.N + leaf) * 4 + ray] = result >= 0 ? ((result << 3) | code) : result;
+    if (P.nb) {
+      P.nb[((int64_t)d * 3 + ray) * P.N + leaf] = result;
+      P.code[((int64_t)d * 3 + ray) * P.N + leaf] = code;
+    }
+    if (P.nbc) P.nbc[item_index(P, gi, lane, leaf) * 4 + ray] = result >= 0 ? ((result << 3) | code) : result;
   }
 }
 
@@ -181,36 +205,85 @@ __global__ void deinterleave3_kernel(const double* __restrict__ in, double* __re
 // one (leaf, direction): returns false if an upstream leaf is not published yet.  CHECK = false: the grid is 2:1
 // balanced, the wave order alone guarantees that every upstream leaf was finished by an earlier launch, so the
 // per-leaf `done` flags (three dependent gathers, two fences and a store per item) are not needed.
+//
+// The item is latency-bound (ncu r01b: 28 of 36 stall cycles per issue are long-scoreboard), so every gather is
+// issued before the arithmetic starts: the packed neighbour record first, then -- independent of each other --
+// opacity, pattern and the three upstream intensities.  Iout records are 32 bytes (3 groups + pad) per (direction,
+// ray, leaf): one sector per upstream read, and only the active rays of a leaf are written.
+__device__ __forceinline__ int64_t iout_record(const AmrParams& P, int group, int lane, int ray, int64_t leaf) {
+  return ((((int64_t)group * 3 + ray) * P.N + leaf) * kGroup + lane) * 4;
+}
+
+template <bool CHECK>
+__device__ __forceinline__ void load_record(const double* p, double (&v)[3]) {
+  if (CHECK) {  // possibly written by another block of this launch: read through L2
+    const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
+    v[0] = a.x; v[1] = a.y; v[2] = __ldcg(p + 2);
+  } else {      // written by an earlier launch
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    v[0] = a.x; v[1] = a.y; v[2] = __ldg(p + 2);
+  }
+}
+
+// Jc = this direction's contribution to the leaf's mean intensity (the caller adds it up)
 template <bool FAITHFUL, bool CHECK>
-__device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, int64_t leaf) {
+__device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, int gi, int lane, int64_t leaf,
+                                                   double (&Jc)[3]) {
   const AmrDir& D = P.dirs[d];
+  const int64_t item = item_index(P, gi, lane, leaf);
   int32_t nbl[3];
-  uint8_t cd[3];
+  int cd[3];
   {
-    const int4 q = *reinterpret_cast<const int4*>(P.nbc + ((int64_t)d * P.N + leaf) * 4);
+    const int4 q = *reinterpret_cast<const int4*>(P.nbc + item * 4);
     const int32_t v[3] = {q.x, q.y, q.z};
 #pragma unroll
     for (int ray = 0; ray < 3; ray++) {
       nbl[ray] = v[ray] >= 0 ? (v[ray] >> 3) : v[ray];
-      cd[ray] = (uint8_t)(v[ray] & 7);
+      cd[ray] = v[ray] & 7;
     }
   }
   if (CHECK) {
-    const volatile uint8_t* done = P.done + (int64_t)d * P.N;
+    const volatile uint8_t* done = P.done;
 #pragma unroll
     for (int ray = 0; ray < 3; ray++)
-      if (nbl[ray] >= 0 && !done[nbl[ray]]) return false;
+      if (nbl[ray] >= 0 && !done[item_index(P, gi, lane, nbl[ray])]) return false;
     __threadfence();
   }
+  // ---- gathers -----------------------------------------------------------------------------------------------
   // pattern of the leaf's (level, layer along the sweep axis): one gather of a precomputed index
-  const int sweepAxis = D.inv[0];
-  const DevPattern& pat = P.pats[D.patBase + P.patIdx[(int64_t)(sweepAxis + (D.refl[sweepAxis] ? 3 : 0)) * P.N + leaf]];
+  const int32_t pidx = P.patIdx[(int64_t)D.patRow * P.N + leaf];
+  double kap[3];
+#pragma unroll
+  for (int g = 0; g < 3; g++) kap[g] = P.kappaA[leaf * 3 + g];
+  double Iin[3][3];
+#pragma unroll
+  for (int ray = 0; ray < 3; ray++) {
+    Iin[ray][0] = P.u0; Iin[ray][1] = P.u1; Iin[ray][2] = P.u2;      // no upstream leaf: the background
+    if (nbl[ray] >= 0) {
+      // codes 0..2: that ray of the neighbour; 3, 4: mean with its xy ray (below); 5: its xy ray
+      const int c = cd[ray];
+      load_record<CHECK>(P.Iout + iout_record(P, gi, lane, c <= 2 ? c : 0, nbl[ray]), Iin[ray]);
+    }
+  }
+  const DevPattern& pat = P.pats[D.patBase + pidx];
   const int L = pat.level;
-  const double uvb[3] = {P.u0, P.u1, P.u2};
-  double kap[3], invk[3];
+  double dpath[3];
+#pragma unroll
+  for (int ray = 0; ray < 3; ray++) dpath[ray] = pat.dpath[ray];     // cellSize(level) * len (:583, 651)
+  // coarse-neighbour averaging fallback (transportRoutinesModule.f90:612-634): rare, a second record
+#pragma unroll
+  for (int ray = 0; ray < 3; ray++) {
+    if (nbl[ray] >= 0 && (cd[ray] == 3 || cd[ray] == 4)) {
+      double side[3];
+      load_record<CHECK>(P.Iout + iout_record(P, gi, lane, cd[ray] == 3 ? 2 : 1, nbl[ray]), side);
+#pragma unroll
+      for (int g = 0; g < 3; g++) Iin[ray][g] = __dmul_rn(0.5, __dadd_rn(side[g], Iin[ray][g]));
+    }
+  }
+  // ---- arithmetic --------------------------------------------------------------------------------------------
+  double invk[3];
 #pragma unroll
   for (int g = 0; g < 3; g++) {
-    kap[g] = P.kappaA[leaf * 3 + g];
     if (!FAITHFUL) {
       kap[g] = kap[g] > 0. ? kap[g] : 1e-200;
       invk[g] = 1.0 / kap[g];
@@ -218,58 +291,38 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
       invk[g] = 0.;
     }
   }
-  double out[3][3];
   double Jm[3] = {0., 0., 0.};
+  double xy[3] = {0., 0., 0.};
   int imean = 0;
-  const double* IoutD = P.Iout + (int64_t)d * P.N * 9;
   // the reference processes xy, then xz, then yz
   const int order[3] = {0, 2, 1};
 #pragma unroll
   for (int q = 0; q < 3; q++) {
     const int ray = order[q];
-    if (nbl[ray] == -2) {
-      out[ray][0] = out[ray][1] = out[ray][2] = 0.;
-      continue;
-    }
-    double Iin[3];
-    if (nbl[ray] < 0) {
-      Iin[0] = uvb[0]; Iin[1] = uvb[1]; Iin[2] = uvb[2];
-    } else {
-      const double* nI = IoutD + (int64_t)nbl[ray] * 9;  // written by another block, possibly in this launch: read via L2
-      const int c = cd[ray];
-#pragma unroll
-      for (int g = 0; g < 3; g++) {
-        if (c <= 2) Iin[g] = __ldcg(nI + c * 3 + g);
-        else if (c == 3) Iin[g] = __dmul_rn(0.5, __dadd_rn(__ldcg(nI + 2 * 3 + g), __ldcg(nI + g)));
-        else if (c == 4) Iin[g] = __dmul_rn(0.5, __dadd_rn(__ldcg(nI + 1 * 3 + g), __ldcg(nI + g)));
-        else Iin[g] = __ldcg(nI + g);
-      }
-    }
-    const double dpath = pat.dpath[ray];  // cellSize(level) * len (transportRoutinesModule.f90:583, 651)
-    const double invd = FAITHFUL ? 0. : 1.0 / dpath;
+    if (nbl[ray] == -2) continue;                                    // inactive ray: nobody reads its record
+    const double invd = FAITHFUL ? 0. : 1.0 / dpath[ray];
+    double out[3];
 #pragma unroll
     for (int g = 0; g < 3; g++) {
-      SegResult sr = segment_update<FAITHFUL, 0>(Iin[g], kap[g], dpath, invk[g] * invd, nullptr);
-      out[ray][g] = sr.Iout;
+      SegResult sr = segment_update<FAITHFUL, 0>(Iin[ray][g], kap[g], dpath[ray], invk[g] * invd, nullptr);
+      out[g] = sr.Iout;
       Jm[g] = __dadd_rn(Jm[g], sr.J);
     }
+    if (ray == 0) { xy[0] = out[0]; xy[1] = out[1]; xy[2] = out[2]; }
     imean++;
-    if (L > 0) {  // refined path only: guard on the xy ray's sum (transportRoutinesModule.f90:680,803,926)
-      const double tmp = __dadd_rn(__dadd_rn(out[0][0], out[0][1]), out[0][2]);
-      if (!(tmp < 1.e-20 && tmp > -1.e-20)) atomicMax(P.err, RTB200_ERR_INTENSITY_GUARD);
-    }
+    double* mine = P.Iout + iout_record(P, gi, lane, ray, leaf);
+    *reinterpret_cast<double2*>(mine) = make_double2(out[0], out[1]);
+    mine[2] = out[2];
   }
-  double* mine = P.Iout + ((int64_t)d * P.N + leaf) * 9;
+  if (L > 0) {  // refined path only: guard on the xy ray's sum (transportRoutinesModule.f90:680,803,926)
+    const double tmp = __dadd_rn(__dadd_rn(xy[0], xy[1]), xy[2]);
+    if (!(tmp < 1.e-20 && tmp > -1.e-20)) atomicMax(P.err, RTB200_ERR_INTENSITY_GUARD);
+  }
 #pragma unroll
-  for (int ray = 0; ray < 3; ray++)
-#pragma unroll
-    for (int g = 0; g < 3; g++) mine[ray * 3 + g] = out[ray][g];
-#pragma unroll
-  for (int g = 0; g < 3; g++)
-    atomicAdd(P.JA + leaf * 3 + g, __dmul_rn(__ddiv_rn(Jm[g], (double)imean), D.w));
+  for (int g = 0; g < 3; g++) Jc[g] = __dmul_rn(__ddiv_rn(Jm[g], (double)imean), D.w);
   if (CHECK) {
     __threadfence();
-    ((volatile uint8_t*)P.done)[(int64_t)d * P.N + leaf] = 1;
+    ((volatile uint8_t*)P.done)[item] = 1;
   }
   return true;
 }
@@ -282,18 +335,36 @@ struct WaveParams {
   int64_t deferredCap;
 };
 
+// block = 16 leaves of the wave x 8 direction lanes; blockIdx.y = group of the batch
 template <bool FAITHFUL, bool CHECK>
-__global__ void amr_wave_kernel(AmrParams P, WaveParams Wp, int ndir) {
-  const int d = blockIdx.y;
-  if (d >= ndir) return;
-  const int combo = P.dirs[d].combo;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Wp.count[combo]) return;
-  const int64_t leaf = Wp.sorted[combo][Wp.begin[combo] + i];
-  if (!amr_transport_leaf<FAITHFUL, CHECK>(P, d, leaf)) {
-    int slot = atomicAdd(Wp.deferredCount, 1);
-    if (slot < Wp.deferredCap) Wp.deferred[slot] = ((int64_t)d << 32) | leaf;
-    else atomicMax(P.err, RTB200_ERR_NOMEM);
+__global__ void __launch_bounds__(128, 8) amr_wave_kernel(AmrParams P, WaveParams Wp, int ngroups) {
+  const int gi = blockIdx.y;
+  const int2 grp = P.groups[gi];
+  const int lane = threadIdx.x % kGroup;
+  const int combo = P.dirs[grp.x].combo;                         // the same for the whole group (one zone)
+  const int i = blockIdx.x * (blockDim.x / kGroup) + threadIdx.x / kGroup;
+  const bool have = i < Wp.count[combo];                         // uniform over the 8 lanes of a leaf
+  const bool mine = have && lane < grp.y;
+  double Jc[3] = {0., 0., 0.};
+  int64_t leaf = 0;
+  if (have) leaf = Wp.sorted[combo][Wp.begin[combo] + i];
+  if (mine) {
+    const int d = grp.x + lane;
+    if (!amr_transport_leaf<FAITHFUL, CHECK>(P, d, gi, lane, leaf, Jc)) {
+      Jc[0] = Jc[1] = Jc[2] = 0.;
+      int slot = atomicAdd(Wp.deferredCount, 1);
+      if (slot < Wp.deferredCap) Wp.deferred[slot] = ((int64_t)d << 32) | leaf;
+      else atomicMax(P.err, RTB200_ERR_NOMEM);
+    }
+  }
+  // the 8 directions of the leaf: butterfly sum (fixed order), one atomic per frequency group
+#pragma unroll
+  for (int g = 0; g < 3; g++) {
+    double v = Jc[g];
+    v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
+    if (have && lane == 0) atomicAdd(P.JA + leaf * 3 + g, v);
   }
 }
 
@@ -305,9 +376,13 @@ __global__ void amr_retry_kernel(AmrParams P, const int64_t* in, const int32_t* 
     const int64_t item = in[i];
     const int d = (int)(item >> 32);
     const int64_t leaf = item & 0xffffffffLL;
-    if (!amr_transport_leaf<FAITHFUL, true>(P, d, leaf)) {
+    double Jc[3];
+    if (!amr_transport_leaf<FAITHFUL, true>(P, d, P.dirs[d].group, P.dirs[d].lane, leaf, Jc)) {
       int slot = atomicAdd(outCount, 1);
       if (slot < cap) out[slot] = item;
+    } else {
+#pragma unroll
+      for (int g = 0; g < 3; g++) atomicAdd(P.JA + leaf * 3 + g, Jc[g]);
     }
   }
 }
@@ -318,10 +393,9 @@ __global__ void amr_retry_kernel(AmrParams P, const int64_t* in, const int32_t* 
 static DevPattern to_dev(const RayPattern& p, double cellSize, int level) {
   DevPattern q;
   std::memset(&q, 0, sizeof(q));
-  q.len[0] = p.xy_len; q.len[1] = p.yz_len; q.len[2] = p.xz_len;
-  q.cellSize = cellSize;
+  const double len[3] = {p.xy_len, p.yz_len, p.xz_len};
   q.level = (int8_t)level;
-  for (int r = 0; r < 3; r++) q.dpath[r] = cellSize * q.len[r];
+  for (int r = 0; r < 3; r++) q.dpath[r] = cellSize * len[r];
   q.e0[0] = p.xy_x0; q.e1[0] = p.xy_y0;
   q.e0[1] = p.yz_y0; q.e1[1] = p.yz_z0;
   q.e0[2] = p.xz_x0; q.e1[2] = p.xz_z0;
@@ -397,7 +471,8 @@ static bool grid_is_balanced(const Context& c) {
 
 struct DirTables {
   std::vector<DevPattern> pats;
-  std::vector<AmrDir> dirs;
+  std::vector<AmrDir> dirs;           // sorted by zone
+  std::vector<int2> groups;           // (first direction, count <= kGroup): consecutive directions of one zone
   std::vector<int32_t> levelOff;
   int perDir = 0;
 };
@@ -406,6 +481,7 @@ struct DirTables {
 struct AmrBuffers {
   DevPattern* pats = nullptr;
   AmrDir* dirs = nullptr;
+  int2* groups = nullptr;
   int32_t* levelOff = nullptr;
   int32_t* nb = nullptr;
   uint8_t* code = nullptr;
@@ -418,10 +494,10 @@ struct AmrBuffers {
   int64_t* defB = nullptr;
   int32_t* defCount = nullptr;  // [2]
   std::string sizeKey;
-  int batch = 0, batchNdir = 0;   // batch size chosen when the buffers were allocated, and for how many directions
+  int batch = 0, batchNdir = 0;   // batch size (in groups) chosen when the buffers were allocated, and for how many directions
   std::string nbKey;              // grid + direction list whose neighbour tables (nb, code, nbc) the buffers hold
   void release() {
-    cudaFree(pats); cudaFree(dirs); cudaFree(levelOff); cudaFree(nb); cudaFree(code); cudaFree(Iout); cudaFree(done);
+    cudaFree(pats); cudaFree(dirs); cudaFree(groups); cudaFree(levelOff); cudaFree(nb); cudaFree(code); cudaFree(Iout); cudaFree(done);
     cudaFree(nbc); cudaFree(kappaA); cudaFree(JA);
     cudaFree(defA); cudaFree(defB); cudaFree(defCount);
     *this = AmrBuffers();
@@ -495,9 +571,19 @@ static int build_dir_tables(Context& c, int nAngularLevel, const std::vector<Dir
   T.perDir = T.levelOff[Lmax + 1];
   T.pats.resize((size_t)T.perDir * dirs.size());
   T.dirs.resize(dirs.size());
+  // directions of one zone next to each other (stable), cut into groups of at most kGroup
+  std::vector<int> order(dirs.size());
+  for (size_t d = 0; d < dirs.size(); d++) order[d] = (int)d;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return dirs[a].izone < dirs[b].izone; });
+  T.groups.clear();
+  for (size_t d = 0; d < dirs.size(); d++) {
+    if (d == 0 || dirs[order[d]].izone != dirs[order[d - 1]].izone || T.groups.back().y == kGroup)
+      T.groups.push_back(make_int2((int)d, 0));
+    T.groups.back().y++;
+  }
   std::vector<RayPattern> cur, next;
   for (size_t d = 0; d < dirs.size(); d++) {
-    const Direction& dd = dirs[d];
+    const Direction& dd = dirs[order[d]];
     if (dd.status) return dd.status;
     ZoneMap m = zone_map(dd.izone);
     AmrDir& A = T.dirs[d];
@@ -508,6 +594,7 @@ static int build_dir_tables(Context& c, int nAngularLevel, const std::vector<Dir
       if (m.refl[cc]) combo |= 1 << cc;
     }
     A.combo = (int8_t)combo;
+    A.patRow = (int8_t)(A.inv[0] + (A.refl[A.inv[0]] ? 3 : 0));
     A.patBase = (int32_t)(d * T.perDir);
     A.w = weight;
     // which physical axis is the sweep axis, and is it reflected: decides which sub-layers exist in the reference
@@ -540,57 +627,78 @@ static int build_dir_tables(Context& c, int nAngularLevel, const std::vector<Dir
   return RTB200_OK;
 }
 
-static int alloc_batch(AmrBuffers& B, const DirTables& T, int64_t N, int ndirBatch, int64_t defCap) {
-  RTB_CUDA(cudaMalloc((void**)&B.pats, (size_t)T.perDir * ndirBatch * sizeof(DevPattern)));
-  RTB_CUDA(cudaMalloc((void**)&B.dirs, (size_t)ndirBatch * sizeof(AmrDir)));
+// ngroups groups of kGroup item lanes each; debugNb: also the per-direction nb / code arrays of the debugging export
+static int alloc_batch(AmrBuffers& B, const DirTables& T, int64_t N, int ngroups, int64_t defCap, bool debugNb) {
+  const size_t slots = (size_t)ngroups * kGroup;
+  RTB_CUDA(cudaMalloc((void**)&B.pats, (size_t)T.perDir * slots * sizeof(DevPattern)));
+  RTB_CUDA(cudaMalloc((void**)&B.dirs, slots * sizeof(AmrDir)));
+  RTB_CUDA(cudaMalloc((void**)&B.groups, (size_t)ngroups * sizeof(int2)));
   RTB_CUDA(cudaMalloc((void**)&B.levelOff, T.levelOff.size() * sizeof(int32_t)));
-  RTB_CUDA(cudaMalloc((void**)&B.nb, (size_t)ndirBatch * 3 * N * sizeof(int32_t)));
-  RTB_CUDA(cudaMalloc((void**)&B.code, (size_t)ndirBatch * 3 * N));
-  RTB_CUDA(cudaMalloc((void**)&B.nbc, (size_t)ndirBatch * 4 * N * sizeof(int32_t)));
+  if (debugNb) {
+    RTB_CUDA(cudaMalloc((void**)&B.nb, slots * 3 * N * sizeof(int32_t)));
+    RTB_CUDA(cudaMalloc((void**)&B.code, slots * 3 * N));
+    return RTB200_OK;
+  }
+  RTB_CUDA(cudaMalloc((void**)&B.nbc, slots * 4 * N * sizeof(int32_t)));
   RTB_CUDA(cudaMalloc((void**)&B.kappaA, (size_t)3 * N * sizeof(double)));
   RTB_CUDA(cudaMalloc((void**)&B.JA, (size_t)3 * N * sizeof(double)));
-  RTB_CUDA(cudaMalloc((void**)&B.Iout, (size_t)ndirBatch * N * 9 * sizeof(double)));
-  RTB_CUDA(cudaMalloc((void**)&B.done, (size_t)ndirBatch * N));
+  RTB_CUDA(cudaMalloc((void**)&B.Iout, slots * N * 12 * sizeof(double)));
+  RTB_CUDA(cudaMalloc((void**)&B.done, slots * N));
   RTB_CUDA(cudaMalloc((void**)&B.defA, (size_t)defCap * sizeof(int64_t)));
   RTB_CUDA(cudaMalloc((void**)&B.defB, (size_t)defCap * sizeof(int64_t)));
   RTB_CUDA(cudaMalloc((void**)&B.defCount, 2 * sizeof(int32_t)));
   return RTB200_OK;
 }
 
-static int choose_batch(Context& c, int ndir) {
+// groups per batch
+static int choose_batch(Context& c, int ngroups) {
   size_t freeB = 0, totalB = 0;
   cudaMemGetInfo(&freeB, &totalB);
-  const double perDir = (double)c.nleaf * (9 * 8 + 1 + 3 * 4 + 3 + 16 + 16) + 1e6;
-  int nb = (int)std::max(1.0, std::min((double)ndir, 0.5 * (double)freeB / perDir));
-  if (c.tune.amrBatch > 0) nb = std::min(nb, c.tune.amrBatch);
+  const double perGroup = (double)kGroup * ((double)c.nleaf * (12 * 8 + 16 + 1) + 1e6);
+  int nb = (int)std::max(1.0, std::min((double)ngroups, 0.5 * (double)freeB / perGroup));
+  if (c.tune.amrBatch > 0) nb = std::min(nb, std::max(1, c.tune.amrBatch / kGroup));   // the knob counts directions
   return nb;
 }
 
-static int run_batch(Context& c, AmrState& S, const DirTables& T, int d0, int nd, const double* uvb, double* dJ,
+// groups [g0, g0 + ng) of the tables
+static int run_batch(Context& c, AmrState& S, const DirTables& T, int g0, int ng, const double* uvb, double* dJ,
                      cudaStream_t s, bool faithful, AmrBuffers& B, int64_t defCap, int64_t* launches) {
   const int64_t N = c.nleaf;
+  const int d0 = T.groups[g0].x;
+  const int nd = T.groups[g0 + ng - 1].x + T.groups[g0 + ng - 1].y - d0;
   RTB_CUDA(cudaMemcpyAsync(B.pats, T.pats.data() + (size_t)d0 * T.perDir, (size_t)T.perDir * nd * sizeof(DevPattern),
                            cudaMemcpyHostToDevice, s));
   std::vector<AmrDir> dl(T.dirs.begin() + d0, T.dirs.begin() + d0 + nd);
-  for (int i = 0; i < nd; i++) dl[i].patBase = i * T.perDir;
+  std::vector<int2> gl(T.groups.begin() + g0, T.groups.begin() + g0 + ng);
+  for (int g = 0; g < ng; g++) {
+    gl[g].x -= d0;
+    for (int k = 0; k < gl[g].y; k++) {
+      AmrDir& A = dl[gl[g].x + k];
+      A.patBase = (gl[g].x + k) * T.perDir;
+      A.group = g;
+      A.lane = k;
+    }
+  }
   RTB_CUDA(cudaMemcpyAsync(B.dirs, dl.data(), (size_t)nd * sizeof(AmrDir), cudaMemcpyHostToDevice, s));
+  RTB_CUDA(cudaMemcpyAsync(B.groups, gl.data(), (size_t)ng * sizeof(int2), cudaMemcpyHostToDevice, s));
   RTB_CUDA(cudaMemcpyAsync(B.levelOff, T.levelOff.data(), T.levelOff.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-  if (!S.plan.balanced) RTB_CUDA(cudaMemsetAsync(B.done, 0, (size_t)nd * N, s));
+  if (!S.plan.balanced) RTB_CUDA(cudaMemsetAsync(B.done, 0, (size_t)ng * kGroup * N, s));
   RTB_CUDA(cudaMemsetAsync(B.defCount, 0, 2 * sizeof(int32_t), s));
   RTB_CUDA(cudaStreamSynchronize(s));  // dl is a local
   AmrParams P;
   P.child = c.tree.child; P.lx = c.tree.leafX; P.ly = c.tree.leafY; P.lz = c.tree.leafZ; P.level = c.dLevel;
-  P.kappa = c.dKappa; P.pats = B.pats; P.levelOff = B.levelOff; P.dirs = B.dirs; P.nb = B.nb; P.code = B.code;
+  P.kappa = c.dKappa; P.pats = B.pats; P.levelOff = B.levelOff; P.dirs = B.dirs; P.nb = nullptr; P.code = nullptr;
+  P.groups = B.groups;
   P.Iout = B.Iout; P.done = B.done; P.J = dJ; P.err = c.dErr; P.N = N; P.n = c.nx; P.maxLevel = c.maxLevel;
   P.nbc = B.nbc; P.patIdx = S.plan.dPatIdx; P.kappaA = B.kappaA; P.JA = B.JA;
   P.u0 = uvb[0]; P.u1 = uvb[1]; P.u2 = uvb[2];
   P.cellSize0 = c.boxSize / (double)c.nx;  // equiSources.f90:1570
   // neighbour threading is geometry only (grid + directions): when one batch holds every direction of the call, the
   // tables stay valid across the outer transport <-> chemistry iterations
-  const bool wholeCall = d0 == 0 && nd == (int)T.dirs.size();
+  const bool wholeCall = g0 == 0 && ng == (int)T.groups.size();
   if (!(wholeCall && !S.tablesKey.empty() && B.nbKey == S.tablesKey)) {
-    dim3 grid((unsigned)((N + 127) / 128), nd);
-    amr_neighbour_kernel<<<grid, 128, 0, s>>>(P, nd);
+    dim3 grid((unsigned)((N + 15) / 16), ng);
+    amr_neighbour_kernel<<<grid, 128, 0, s>>>(P, ng);
     (*launches)++;
     B.nbKey = wholeCall ? S.tablesKey : std::string();
   }
@@ -611,10 +719,10 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int d0, int nd
     if (maxCount == 0) continue;
     Wp.deferred = lists[cur];
     Wp.deferredCount = B.defCount + cur;
-    dim3 grid((maxCount + 127) / 128, nd);
+    dim3 grid((maxCount + 15) / 16, ng);
     const bool check = !S.plan.balanced;
-    if (faithful) { if (check) amr_wave_kernel<true, true><<<grid, 128, 0, s>>>(P, Wp, nd); else amr_wave_kernel<true, false><<<grid, 128, 0, s>>>(P, Wp, nd); }
-    else { if (check) amr_wave_kernel<false, true><<<grid, 128, 0, s>>>(P, Wp, nd); else amr_wave_kernel<false, false><<<grid, 128, 0, s>>>(P, Wp, nd); }
+    if (faithful) { if (check) amr_wave_kernel<true, true><<<grid, 128, 0, s>>>(P, Wp, ng); else amr_wave_kernel<true, false><<<grid, 128, 0, s>>>(P, Wp, ng); }
+    else { if (check) amr_wave_kernel<false, true><<<grid, 128, 0, s>>>(P, Wp, ng); else amr_wave_kernel<false, false><<<grid, 128, 0, s>>>(P, Wp, ng); }
     (*launches)++;
     if (check && (w & 15) == 15) {
       // retry what has been deferred so far (nothing on 2:1-balanced grids)
@@ -668,17 +776,18 @@ int diffuse_amr(Context& c, int nAngularLevel, const double* uvb, const std::vec
   }
   DirTables& T = S.tables;
   const int ndir = (int)dirs.size();
+  const int ngroups = (int)T.groups.size();
   AmrBuffers& B = S.buffers;
   // the cached buffers count as used memory: keep their batch size instead of choosing a smaller one every call
-  const int batch = (B.batch > 0 && B.batchNdir == ndir) ? B.batch : choose_batch(c, ndir);
-  const int64_t defCap = std::max<int64_t>(1 << 16, std::min<int64_t>((int64_t)batch * N, (int64_t)1 << 26));
+  const int batch = (B.batch > 0 && B.batchNdir == ndir) ? std::min(B.batch, ngroups) : choose_batch(c, ngroups);
+  const int64_t defCap = std::max<int64_t>(1 << 16, std::min<int64_t>((int64_t)batch * kGroup * N, (int64_t)1 << 26));
   int st = RTB200_OK;
   {
     char buf[96];
     snprintf(buf, sizeof(buf), "%d:%lld:%d:%lld", T.perDir, (long long)N, batch, (long long)defCap);
     if (B.sizeKey != buf) {
       B.release();
-      st = alloc_batch(B, T, N, batch, defCap);  // (release() also forgets the cached neighbour tables)
+      st = alloc_batch(B, T, N, batch, defCap, false);  // (release() also forgets the cached neighbour tables)
       if (st) B.release();
       else { B.sizeKey = buf; B.batch = batch; B.batchNdir = ndir; }
     }
@@ -691,8 +800,8 @@ int diffuse_amr(Context& c, int nAngularLevel, const double* uvb, const std::vec
     RTB_CUDA(cudaMemsetAsync(B.JA, 0, 3 * N * sizeof(double), s));
     launches += 1;
   }
-  for (int d0 = 0; d0 < ndir && !st; d0 += batch)
-    st = run_batch(c, S, T, d0, std::min(batch, ndir - d0), uvb, dJout, s, faithful, B, defCap, &launches);
+  for (int g0 = 0; g0 < ngroups && !st; g0 += batch)
+    st = run_batch(c, S, T, g0, std::min(batch, ngroups - g0), uvb, dJout, s, faithful, B, defCap, &launches);
   if (!st) {
     deinterleave3_kernel<<<cpyBlocks, 256, 0, s>>>(B.JA, dJout, N);
     launches += 1;
@@ -756,17 +865,20 @@ int amr_neighbours(Context& c, const Direction& d, int32_t* nbHost) {
   DirTables T;
   if (int st = build_dir_tables(c, 3, one, T)) return st;
   AmrBuffers B;
-  if (int st = alloc_batch(B, T, N, 1, 16)) { B.release(); return st; }
+  if (int st = alloc_batch(B, T, N, 1, 16, true)) { B.release(); return st; }
   cudaStream_t s = c.stream;
   RTB_CUDA(cudaMemcpyAsync(B.pats, T.pats.data(), T.pats.size() * sizeof(DevPattern), cudaMemcpyHostToDevice, s));
+  T.dirs[0].group = 0; T.dirs[0].lane = 0;
   RTB_CUDA(cudaMemcpyAsync(B.dirs, T.dirs.data(), sizeof(AmrDir), cudaMemcpyHostToDevice, s));
+  RTB_CUDA(cudaMemcpyAsync(B.groups, T.groups.data(), sizeof(int2), cudaMemcpyHostToDevice, s));
   RTB_CUDA(cudaMemcpyAsync(B.levelOff, T.levelOff.data(), T.levelOff.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   AmrParams P;
   std::memset(&P, 0, sizeof(P));
+  P.groups = B.groups;
   P.child = c.tree.child; P.lx = c.tree.leafX; P.ly = c.tree.leafY; P.lz = c.tree.leafZ; P.level = c.dLevel;
   P.pats = B.pats; P.levelOff = B.levelOff; P.dirs = B.dirs; P.nb = B.nb; P.code = B.code; P.err = c.dErr;
   P.N = N; P.n = c.nx; P.maxLevel = c.maxLevel;
-  dim3 grid((unsigned)((N + 127) / 128), 1);
+  dim3 grid((unsigned)((N + 15) / 16), 1);
   amr_neighbour_kernel<<<grid, 128, 0, s>>>(P, 1);
   RTB_CUDA(cudaMemcpyAsync(nbHost, B.nb, (size_t)3 * N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   RTB_CUDA(cudaStreamSynchronize(s));
