@@ -32,18 +32,20 @@
 
 namespace rtb {
 
-struct alignas(32) DevPattern {   // subset of RayPattern the device needs, 96 B = three 32-byte sectors
-  // first sector: all the sweep reads
+struct alignas(32) DevPattern {   // subset of RayPattern the device needs, 128 B = four 32-byte sectors
+  // first two sectors: all the sweep reads
   double dpath[3];       // cellSize(level) * len per ray (xy, yz, xz = ray id 0, 1, 2), multiplied on the host
   int8_t top[3];         // xyTop, yzTop, xzTop: which ray (1 xy, 2 yz, 3 xz) leaves through the top / x=1 / y=1 face
   int8_t active[3];      // xy (always), yz, xz
   int8_t level;          // refinement level of the table
   int8_t pad[1];
+  double cs[3];          // FAST arithmetic: weight / (number of active rays * dpath), see amr_transport_leaf
+  double pad1;
   // neighbour threading only
   double e0[3], e1[3];   // entry point of each ray on its face: xy (x0,y0), yz (y0,z0), xz (x0,z0)
   double pad2[2];
 };
-static_assert(sizeof(DevPattern) == 96, "DevPattern is three sectors");
+static_assert(sizeof(DevPattern) == 128, "DevPattern is four sectors");
 
 struct AmrDir {          // one direction of the batch
   int8_t src[3], refl[3];  // zone map: physical component c takes rotated index src[c], reflected if refl[c]
@@ -70,7 +72,7 @@ struct AmrParams {
   uint8_t* code;           // debugging export only: [ndir][3][N] what to read from the upstream leaf
   int32_t* nbc;            // [group][N][8][4] the same packed for the sweep: leaf << 3 | code (or -1 / -2) per ray, 16 B per item
   const int32_t* patIdx;   // [6][N] levelOff[level] + coordinate along physical axis a (a = 0..2), then reflected (3..5)
-  const double* kappaA;    // [N][3] opacities, leaf-major (one gather instead of three)
+  const double* kappaA;    // [N][6] leaf-major: opacity of the 3 groups, then 1 / max(opacity, floor) (FAST arithmetic)
   double* JA;              // [N][3] accumulator, leaf-major (atomics), un-interleaved into J at the end
   double* Iout;            // [group][3 rays][N][8][4]: 3 frequency groups + pad, one 32-byte sector per record
   uint8_t* done;           // [group][N][8]
@@ -188,11 +190,14 @@ __global__ void amr_neighbour_kernel(AmrParams P, int ngroups) {
 }
 
 // leaf-major copies for the sweep's gathers
-__global__ void interleave3_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t N) {
+constexpr double kAmrKappaFloor = 1e-100;  // FAST arithmetic: kappa = 0 is evaluated as this (every formula takes its limit)
+__global__ void interleave_kappa_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t N) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 3 * N; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t leaf = i / 3;
     const int g = (int)(i - 3 * leaf);
-    out[i] = in[g * N + leaf];
+    const double k = in[g * N + leaf];
+    out[leaf * 6 + g] = k;
+    out[leaf * 6 + 3 + g] = 1.0 / (k > 0. ? k : kAmrKappaFloor);
   }
 }
 __global__ void deinterleave3_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t N) {
@@ -228,7 +233,7 @@ __device__ __forceinline__ void load_record(const double* p, double (&v)[3]) {
 // Jc = this direction's contribution to the leaf's mean intensity (the caller adds it up)
 template <bool FAITHFUL, bool CHECK>
 __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, int gi, int lane, int64_t leaf,
-                                                   double (&Jc)[3]) {
+                                                   double (&Jc)[3], const double* __restrict__ sT) {
   const AmrDir& D = P.dirs[d];
   const int64_t item = item_index(P, gi, lane, leaf);
   int32_t nbl[3];
@@ -252,9 +257,12 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
   // ---- gathers -----------------------------------------------------------------------------------------------
   // pattern of the leaf's (level, layer along the sweep axis): one gather of a precomputed index
   const int32_t pidx = P.patIdx[(int64_t)D.patRow * P.N + leaf];
-  double kap[3];
+  double kap[3], invk[3];
 #pragma unroll
-  for (int g = 0; g < 3; g++) kap[g] = P.kappaA[leaf * 3 + g];
+  for (int g = 0; g < 3; g++) {
+    kap[g] = P.kappaA[leaf * 6 + g];
+    invk[g] = FAITHFUL ? 0. : P.kappaA[leaf * 6 + 3 + g];
+  }
   double Iin[3][3];
 #pragma unroll
   for (int ray = 0; ray < 3; ray++) {
@@ -281,32 +289,35 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
     }
   }
   // ---- arithmetic --------------------------------------------------------------------------------------------
-  double invk[3];
-#pragma unroll
-  for (int g = 0; g < 3; g++) {
-    if (!FAITHFUL) {
-      kap[g] = kap[g] > 0. ? kap[g] : 1e-200;
-      invk[g] = 1.0 / kap[g];
-    } else {
-      invk[g] = 0.;
-    }
-  }
+  // FAITHFUL: the reference's sequence per segment, J = (sum of the segments' J) / (number of segments) * weight.
+  // FAST (segment_math.cuh, as the uniform sweep): J_seg weight / nseg = Iin (1 - e^-tau) / (kappa dpath) * weight / nseg
+  //   = [Iin (1 - e^-tau)] * cs / kappa with cs = weight / (nseg dpath) from the host tables and 1 / kappa per leaf:
+  //   one table exponential and no division per segment.
   double Jm[3] = {0., 0., 0.};
   double xy[3] = {0., 0., 0.};
   int imean = 0;
+  if (!FAITHFUL) {
+#pragma unroll
+    for (int g = 0; g < 3; g++) kap[g] = kap[g] > 0. ? kap[g] : kAmrKappaFloor;
+  }
   // the reference processes xy, then xz, then yz
   const int order[3] = {0, 2, 1};
 #pragma unroll
   for (int q = 0; q < 3; q++) {
     const int ray = order[q];
     if (nbl[ray] == -2) continue;                                    // inactive ray: nobody reads its record
-    const double invd = FAITHFUL ? 0. : 1.0 / dpath[ray];
     double out[3];
+    if (FAITHFUL) {
 #pragma unroll
-    for (int g = 0; g < 3; g++) {
-      SegResult sr = segment_update<FAITHFUL, 0>(Iin[ray][g], kap[g], dpath[ray], invk[g] * invd, nullptr);
-      out[g] = sr.Iout;
-      Jm[g] = __dadd_rn(Jm[g], sr.J);
+      for (int g = 0; g < 3; g++) {
+        SegResult sr = segment_update<true, 0>(Iin[ray][g], kap[g], dpath[ray], 0., nullptr);
+        out[g] = sr.Iout;
+        Jm[g] = __dadd_rn(Jm[g], sr.J);
+      }
+    } else {
+      const double cs = pat.cs[ray];
+#pragma unroll
+      for (int g = 0; g < 3; g++) out[g] = segment_fast<1, true>(Iin[ray][g], kap[g] * dpath[ray], cs, sT, Jm[g]);
     }
     if (ray == 0) { xy[0] = out[0]; xy[1] = out[1]; xy[2] = out[2]; }
     imean++;
@@ -319,7 +330,7 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
     if (!(tmp < 1.e-20 && tmp > -1.e-20)) atomicMax(P.err, RTB200_ERR_INTENSITY_GUARD);
   }
 #pragma unroll
-  for (int g = 0; g < 3; g++) Jc[g] = __dmul_rn(__ddiv_rn(Jm[g], (double)imean), D.w);
+  for (int g = 0; g < 3; g++) Jc[g] = FAITHFUL ? __dmul_rn(__ddiv_rn(Jm[g], (double)imean), D.w) : Jm[g] * invk[g];
   if (CHECK) {
     __threadfence();
     ((volatile uint8_t*)P.done)[item] = 1;
@@ -338,6 +349,11 @@ struct WaveParams {
 // block = 16 leaves of the wave x 8 direction lanes; blockIdx.y = group of the batch
 template <bool FAITHFUL, bool CHECK>
 __global__ void __launch_bounds__(128, 8) amr_wave_kernel(AmrParams P, WaveParams Wp, int ngroups) {
+  __shared__ double sT[16];
+  if (!FAITHFUL) {
+    if (threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
+    __syncthreads();
+  }
   const int gi = blockIdx.y;
   const int2 grp = P.groups[gi];
   const int lane = threadIdx.x % kGroup;
@@ -350,7 +366,7 @@ __global__ void __launch_bounds__(128, 8) amr_wave_kernel(AmrParams P, WaveParam
   if (have) leaf = Wp.sorted[combo][Wp.begin[combo] + i];
   if (mine) {
     const int d = grp.x + lane;
-    if (!amr_transport_leaf<FAITHFUL, CHECK>(P, d, gi, lane, leaf, Jc)) {
+    if (!amr_transport_leaf<FAITHFUL, CHECK>(P, d, gi, lane, leaf, Jc, sT)) {
       Jc[0] = Jc[1] = Jc[2] = 0.;
       int slot = atomicAdd(Wp.deferredCount, 1);
       if (slot < Wp.deferredCap) Wp.deferred[slot] = ((int64_t)d << 32) | leaf;
@@ -371,13 +387,18 @@ __global__ void __launch_bounds__(128, 8) amr_wave_kernel(AmrParams P, WaveParam
 template <bool FAITHFUL>
 __global__ void amr_retry_kernel(AmrParams P, const int64_t* in, const int32_t* inCount, int64_t* out, int32_t* outCount,
                                  int64_t cap) {
+  __shared__ double sT[16];
+  if (!FAITHFUL) {
+    if (threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
+    __syncthreads();
+  }
   const int n = min((int64_t)*inCount, cap);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int64_t item = in[i];
     const int d = (int)(item >> 32);
     const int64_t leaf = item & 0xffffffffLL;
     double Jc[3];
-    if (!amr_transport_leaf<FAITHFUL, true>(P, d, P.dirs[d].group, P.dirs[d].lane, leaf, Jc)) {
+    if (!amr_transport_leaf<FAITHFUL, true>(P, d, P.dirs[d].group, P.dirs[d].lane, leaf, Jc, sT)) {
       int slot = atomicAdd(outCount, 1);
       if (slot < cap) out[slot] = item;
     } else {
@@ -390,7 +411,7 @@ __global__ void amr_retry_kernel(AmrParams P, const int64_t* in, const int32_t* 
 // ---------------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------------
-static DevPattern to_dev(const RayPattern& p, double cellSize, int level) {
+static DevPattern to_dev(const RayPattern& p, double cellSize, int level, double weight) {
   DevPattern q;
   std::memset(&q, 0, sizeof(q));
   const double len[3] = {p.xy_len, p.yz_len, p.xz_len};
@@ -401,6 +422,8 @@ static DevPattern to_dev(const RayPattern& p, double cellSize, int level) {
   q.e0[2] = p.xz_x0; q.e1[2] = p.xz_z0;
   q.top[0] = p.xyTop; q.top[1] = p.yzTop; q.top[2] = p.xzTop;
   q.active[0] = 1; q.active[1] = p.yzActive; q.active[2] = p.xzActive;
+  const int nseg = 1 + (p.yzActive ? 1 : 0) + (p.xzActive ? 1 : 0);
+  for (int r = 0; r < 3; r++) q.cs[r] = q.active[r] && q.dpath[r] > 0. ? weight / ((double)nseg * q.dpath[r]) : 0.;
   return q;
 }
 
@@ -616,7 +639,7 @@ static int build_dir_tables(Context& c, int nAngularLevel, const std::vector<Dir
           }
           if (needed) return p.status;
         }
-        T.pats[(size_t)A.patBase + T.levelOff[L] + i] = to_dev(p, (c.boxSize / (double)c.nx) / (double)(1 << L), L);
+        T.pats[(size_t)A.patBase + T.levelOff[L] + i] = to_dev(p, (c.boxSize / (double)c.nx) / (double)(1 << L), L, weight);
       }
       if (L < Lmax) {
         layer_patterns_refine(dd.phi, dd.theta, cur, next);
@@ -640,7 +663,7 @@ static int alloc_batch(AmrBuffers& B, const DirTables& T, int64_t N, int ngroups
     return RTB200_OK;
   }
   RTB_CUDA(cudaMalloc((void**)&B.nbc, slots * 4 * N * sizeof(int32_t)));
-  RTB_CUDA(cudaMalloc((void**)&B.kappaA, (size_t)3 * N * sizeof(double)));
+  RTB_CUDA(cudaMalloc((void**)&B.kappaA, (size_t)6 * N * sizeof(double)));
   RTB_CUDA(cudaMalloc((void**)&B.JA, (size_t)3 * N * sizeof(double)));
   RTB_CUDA(cudaMalloc((void**)&B.Iout, slots * N * 12 * sizeof(double)));
   RTB_CUDA(cudaMalloc((void**)&B.done, slots * N));
@@ -796,7 +819,7 @@ int diffuse_amr(Context& c, int nAngularLevel, const double* uvb, const std::vec
   const bool faithful = c.mathMode == RTB200_MATH_FAITHFUL;
   const int cpyBlocks = (int)std::min<int64_t>((3 * N + 255) / 256, (int64_t)c.smCount * 16);
   if (!st) {
-    interleave3_kernel<<<cpyBlocks, 256, 0, s>>>(c.dKappa, B.kappaA, N);
+    interleave_kappa_kernel<<<cpyBlocks, 256, 0, s>>>(c.dKappa, B.kappaA, N);
     RTB_CUDA(cudaMemsetAsync(B.JA, 0, 3 * N * sizeof(double), s));
     launches += 1;
   }
