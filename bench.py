@@ -38,6 +38,7 @@ UNIT = "segment-updates/s"
 NCU_TRAFFIC_BYTES = {
     "diffuse-256^3-uniform-192dir": 324.15e6 + 312.43e6,   # sweep_cell_kernel, one layer of all 32 zone tasks (r01e)
     "point-128^3-amr-100src": 5.51e6 + 2.66e6,             # point_march_kernel, pixel level 6 of 100 sources (r01b)
+    "diffuse-128^3-amr2-192dir": 95.38e6 + 27.42e6,        # amr_wave_kernel, one mid-sweep wave of 878 (r01d); waves differ in size
 }
 
 WORKLOADS = {
