@@ -120,6 +120,21 @@ def test_amr_direction_batches_and_shards(rt, engine, uvbg):
     assert na + nb_ == nfull and np.allclose(a + b, full, rtol=1e-13, atol=0)
 
 
+@pytest.mark.parametrize("name,lo,hi", [("unbalanced-corner", 37, 59), ("disc-3-levels", 100, 101),
+                                        ("single-deep-cell", 0, 13)])
+def test_amr_ragged_direction_subset_vs_oracle(rt, engine, oracle, uvbg, name, lo, hi):
+    """direction subsets that fill the 8-lane zone groups only partly (the items of a leaf are stored per group of up
+    to 8 directions of one zone), on balanced and unbalanced grids, against the oracle's ray range"""
+    g = GRIDS[name]
+    _set(engine, g)
+    uvb = uvbg["uvb"] * 1e-3
+    J, nseg = engine.diffuse(uvb, uvbg["beta"], rays=np.arange(lo, hi, dtype=np.int32))
+    og = oracle.OracleGrid(g["nx"], g["level"], g["HI"], g["HeI"], g["HeII"], box_size=g["box_size"])
+    o = og.diffuse(uvb, uvbg["beta"], ray_begin=lo, ray_end=hi)
+    assert o["status"] == 0 and nseg == o["nseg"]
+    assert rel_err(J, o["J"]) < TOL, (name, rel_err(J, o["J"]))
+
+
 def test_cell_array_file_feeds_the_gpu_path(rt, oracle, uvbg, tmp_path):
     """a `cellArray.dat` written in the reference's layout (hdf42bin.f90:208-218) goes through set_grid unchanged:
     same leaf order, tree rebuilt from `level` alone; compared with the oracle on the file's (single-precision) values"""
