@@ -120,57 +120,6 @@ __device__ __forceinline__ void direction_fast(const LayerSeg& P, const double (
   }
 }
 
-// Same arithmetic with the row-axis hand-over taken from shared memory instead of recomputed: every warp of the
-// block publishes the intermediate its (b+1) neighbour needs (its xy output, or with SECL its second-segment output),
-// the block synchronises once, and rows 1..7 read the row above.  Only the block's top row (`top`, warp-uniform)
-// still recomputes from upR / kR.  The value read is the very number the neighbour thread computed, so the result
-// is the same as direction_fast's.  Must be called by ALL threads of the block (one __syncthreads inside); only
-// instantiated for the chains that have a row-axis hand-over (not NSEG == 1, not SECL with NSEG == 2).
-//   sw: this thread's slot [g * 256]; sr: the slot of the thread one row up.
-template <int EXPV, int NSEG, bool SECL, bool GUARD>
-__device__ __forceinline__ void direction_fast_xrow(const LayerSeg& P, const double (&cur)[3], const double (&upR)[3],
-                                                    const double (&kap)[3], const double (&kR)[3], double (&I)[3],
-                                                    double (&A)[3], const double* __restrict__ T, bool top,
-                                                    double* __restrict__ sw, const double* __restrict__ sr) {
-  static_assert(NSEG >= 2 && !(SECL && NSEG == 2), "no row-axis hand-over in this chain");
-  const unsigned full = 0xffffffffu;
-  double mine[3];
-#pragma unroll
-  for (int g = 0; g < 3; g++) {
-    const double I1 = segment_fast<EXPV, GUARD>(cur[g], kap[g] * P.d[0], P.cs[0], T, A[g]);
-    if (SECL) {
-      const double in2 = __shfl_up_sync(full, I1, 1);
-      mine[g] = segment_fast<EXPV, GUARD>(in2, kap[g] * P.d[1], P.cs[1], T, A[g]);
-    } else {
-      mine[g] = I1;
-    }
-    sw[g * 256] = mine[g];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int g = 0; g < 3; g++) {
-    if (SECL) {  // NSEG == 3: third segment from the (b-1) cell's second segment
-      double in3;
-      if (top) {
-        const double rup = attenuate_fast<EXPV, GUARD>(upR[g], kR[g] * P.d[0], T);
-        const double x = __shfl_up_sync(full, rup, 1);
-        in3 = attenuate_fast<EXPV, GUARD>(x, kR[g] * P.d[1], T);
-      } else {
-        in3 = sr[g * 256];
-      }
-      I[g] = segment_fast<EXPV, GUARD>(in3, kap[g] * P.d[2], P.cs[2], T, A[g]);
-    } else {
-      const double rup = top ? attenuate_fast<EXPV, GUARD>(upR[g], kR[g] * P.d[0], T) : sr[g * 256];
-      const double I2 = segment_fast<EXPV, GUARD>(rup, kap[g] * P.d[1], P.cs[1], T, A[g]);
-      I[g] = I2;
-      if (NSEG == 3) {
-        const double in3 = __shfl_up_sync(full, I2, 1);
-        I[g] = segment_fast<EXPV, GUARD>(in3, kap[g] * P.d[2], P.cs[2], T, A[g]);
-      }
-    }
-  }
-}
-
 // The reference's own operation sequence (RTB200_MATH_FAITHFUL, and the thin layers of FAST mode): adds
 // (sum of the segments' J) / nseg * weight to acc (transportRoutinesModule.f90:953-955).
 template <int NSEG, bool SECL>
@@ -242,51 +191,6 @@ __device__ __forceinline__ void direction_dispatch_fast(const LayerSeg& P, bool 
   else direction_kinds_fast<EXPV, false>(P, secL, cur, upR, kap, kR, I, A, T);
 }
 
-// true if the layer's chain hands over along the row axis (block-uniform: kind and secL are per (task, direction))
-__device__ __forceinline__ bool chain_has_row_handover(int kind, bool secL) {
-  return kind != 0 && !(secL && (kind == 1 || kind == 3));
-}
-
-template <int EXPV, bool GUARD>
-__device__ __forceinline__ void direction_kinds_fast_xrow(const LayerSeg& P, bool secL, const double (&cur)[3],
-                                                          const double (&upR)[3], const double (&kap)[3],
-                                                          const double (&kR)[3], double (&I)[3], double (&A)[3],
-                                                          const double* __restrict__ T, bool top, double* sw,
-                                                          const double* sr) {
-  const int kind = P.kind;
-  if (kind == 1 || kind == 3) direction_fast_xrow<EXPV, 2, false, GUARD>(P, cur, upR, kap, kR, I, A, T, top, sw, sr);
-  else if (secL) direction_fast_xrow<EXPV, 3, true, GUARD>(P, cur, upR, kap, kR, I, A, T, top, sw, sr);
-  else direction_fast_xrow<EXPV, 3, false, GUARD>(P, cur, upR, kap, kR, I, A, T, top, sw, sr);
-}
-
-// only for chains with chain_has_row_handover(); every thread of the block must call it, and `thick` (guarded
-// arithmetic) must be block-uniform because the hand-over's __syncthreads sits inside the instantiation
-template <int EXPV>
-__device__ __forceinline__ void direction_dispatch_fast_xrow(const LayerSeg& P, bool secL, bool thick,
-                                                             const double (&cur)[3], const double (&upR)[3],
-                                                             const double (&kap)[3], const double (&kR)[3],
-                                                             double (&I)[3], double (&A)[3],
-                                                             const double* __restrict__ T, bool top, double* sw,
-                                                             const double* sr) {
-  if (thick) direction_kinds_fast_xrow<EXPV, true>(P, secL, cur, upR, kap, kR, I, A, T, top, sw, sr);
-  else direction_kinds_fast_xrow<EXPV, false>(P, secL, cur, upR, kap, kR, I, A, T, top, sw, sr);
-}
-
-// the chains WITHOUT a row-axis hand-over (one segment, or two with the second fed along the lane axis)
-template <int EXPV>
-__device__ __forceinline__ void direction_dispatch_fast_norow(const LayerSeg& P, bool thick, const double (&cur)[3],
-                                                              const double (&upR)[3], const double (&kap)[3],
-                                                              const double (&kR)[3], double (&I)[3], double (&A)[3],
-                                                              const double* __restrict__ T) {
-  if (P.kind == 0) {
-    if (thick) direction_fast<EXPV, 1, true, true>(P, cur, upR, kap, kR, I, A, T);
-    else direction_fast<EXPV, 1, true, false>(P, cur, upR, kap, kR, I, A, T);
-  } else {
-    if (thick) direction_fast<EXPV, 2, true, true>(P, cur, upR, kap, kR, I, A, T);
-    else direction_fast<EXPV, 2, true, false>(P, cur, upR, kap, kR, I, A, T);
-  }
-}
-
 // Out of line and by value: the rare faithful branch must not force the fast path's per-direction arrays into
 // local memory (a by-reference call would).
 struct Tri {
@@ -348,7 +252,7 @@ struct BatchParams {
 // pairs) is evaluated with the reference's own operation sequence even in FAST mode: there tau is tiny and the
 // rounding noise of the reference's (Iin-Iout)/log(Iin/Iout), ~1.1e-16/tau, would otherwise show up as a parity
 // difference.  That branch is warp-uniform (P.thin is a per-layer table entry) and kept out of line.
-template <bool FAITHFUL, int EXPV, int MINB, bool XROW>
+template <bool FAITHFUL, int EXPV, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 sweep_cell_kernel(const __grid_constant__ BatchParams bp, int N, int n, int np1, int npl3) {
   // n, np1 = n + 1 and npl3 = 3 (n+1)^2 are the same for every task: as top-level parameters they are constant-bank
@@ -356,29 +260,23 @@ sweep_cell_kernel(const __grid_constant__ BatchParams bp, int N, int n, int np1,
   const StepParams& sp = bp.t[blockIdx.z];
   const double* __restrict__ kappa = sp.kappa;
   __shared__ double sT[16];
-  // XROW: row-axis hand-over through shared memory, [2 buffers][3 groups][8 rows][32 lanes]
-  __shared__ double sX[XROW ? 2 * 768 : 1];
   if (threadIdx.y == 0 && threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
   __syncthreads();
-  const int a = blockIdx.x * 31 - 1 + (int)threadIdx.x, bRaw = blockIdx.y * 8 + threadIdx.y;
-  if (!XROW && bRaw >= n) return;                              // warp-uniform
-  // XROW: rows beyond the domain stay for the block barriers; they compute on the last row's addresses, write nothing
-  const bool rowIn = bRaw < n;
-  const int b = rowIn ? bRaw : n - 1;
+  const int a = blockIdx.x * 31 - 1 + (int)threadIdx.x, b = blockIdx.y * 8 + threadIdx.y;
+  if (b >= n) return;                                          // warp-uniform
   const bool inRow = a < n;                                    // lanes beyond the row only take part in the shuffles
-  const bool writer = inRow && threadIdx.x >= 1 && rowIn;
+  const bool writer = inRow && threadIdx.x >= 1;
   const bool cell = inRow && a >= 0;                           // a real cell (not the pad column)
   const int laneIsK = sp.laneIsK;
   const int sA = laneIsK ? sp.sk : sp.sj, sB = laneIsK ? sp.sj : sp.sk;
   const int leaf = sp.origin + a * sA + b * sB;
-  double kap[3], kR[3];
+  double kap[3], kapF[3], kR[3];
 #pragma unroll
   for (int g = 0; g < 3; g++) {
     const double* kg = kappa + (int64_t)g * N + leaf;
-    const double kF = cell ? kg[0] : 0.;
+    kapF[g] = cell ? kg[0] : 0.;
     kR[g] = (cell && b > 0) ? kg[-sB] : 0.;                    // kappa = 0 outside: exp(-0) = 1 exactly
-    // FAST: an exact zero is evaluated as the floor; the reference-sequence branch maps the floor back to zero
-    kap[g] = (FAITHFUL || kF > 0.) ? kF : kKappaFloor;
+    kap[g] = kapF[g] > 0. ? kapF[g] : kKappaFloor;
   }
   const double kmax = fmax(fmax(fmax(kap[0], kap[1]), fmax(kap[2], kR[0])), fmax(kR[1], kR[2]));
   double A[3] = {0., 0., 0.}, acc[3] = {0., 0., 0.};
@@ -388,55 +286,26 @@ sweep_cell_kernel(const __grid_constant__ BatchParams bp, int N, int n, int np1,
   const int up = 3 * np1;                                      // one row up
   const double* pin = sp.planeIn + 3 * pidx;
   double* pout = sp.planeOut + 3 * pidx;
-  // XROW only
-  const bool top = threadIdx.y == 0;                           // the block's first row still recomputes the hand-over
-  bool thick = false;
-  int xbuf = 0;
-  double* const sw = sX + (XROW ? threadIdx.y * 32 + threadIdx.x : 0);
-  if (XROW && !FAITHFUL) {
-    double dmaxAll = 0.;
-    for (int q = 0; q < ndir; q++) dmaxAll = fmax(dmaxAll, sp.P[q].dmax);
-    thick = __syncthreads_or(kmax * dmaxAll > 64.) != 0;       // block-uniform: the barrier sits inside the branch
-  }
   for (int q = 0; q < ndir; q++, pin += dstride, pout += dstride) {
     const LayerSeg& P = sp.P[q];
     const int kind = P.kind;
-    // kinds 1,2: second segment fed from k-1, third (kind 2) from j-1; kinds 3,4 the other way round
-    const bool secL = (kind <= 2) == (laneIsK != 0);
-    const bool needUp = kind == 2 || kind == 4 || (kind != 0 && !secL);
-    const bool xrow = XROW && !FAITHFUL && !P.thin && needUp;  // needUp == chain_has_row_handover(kind, secL)
     // Pull the NEXT direction's plane values towards L1 with prefetch instructions: they hold no destination
     // register (at 64 registers per thread a register prefetch is spilled at once, and the spill store then waits
     // for the load -- 35% of all stall samples in the r01 profile).
     if (q + 1 < ndir) {
       prefetch_l1(pin + dstride);
-      if (!XROW || top) prefetch_l1(pin + dstride - up);
+      prefetch_l1(pin + dstride - up);
     }
     double cur[3], upR[3] = {0., 0., 0.}, I[3];
 #pragma unroll
     for (int g = 0; g < 3; g++) cur[g] = pin[g];
-    if (needUp && (!xrow || top)) {
+    // kinds 1,2: second segment fed from k-1, third (kind 2) from j-1; kinds 3,4 the other way round
+    const bool secL = (kind <= 2) == (laneIsK != 0);
+    if (kind == 2 || kind == 4 || (kind != 0 && !secL)) {
 #pragma unroll
       for (int g = 0; g < 3; g++) upR[g] = pin[g - up];
-      if (XROW) {
-        // only the block's top row (and the rare thin layers) needs the (b-1) cell's opacity here: re-read it
-        // (an L1 hit) instead of holding six registers through the loop
-#pragma unroll
-        for (int g = 0; g < 3; g++) kR[g] = (cell && b > 0) ? kappa[(int64_t)g * N + leaf - sB] : 0.;
-      }
     }
-    if (FAITHFUL || P.thin) {
-      double kapF[3];
-#pragma unroll
-      for (int g = 0; g < 3; g++) kapF[g] = (!FAITHFUL && (kap[g] == kKappaFloor || !cell)) ? 0. : kap[g];
-      direction_dispatch_faithful(P, secL, cur, upR, kapF, kR, I, acc);
-    } else if (xrow) {
-      // the buffer alternates with every hand-over, so that one barrier per direction is enough: a warp can only
-      // be writing buffer x again after every warp has passed the barrier of the hand-over in between
-      double* w = sw + xbuf * 768;
-      direction_dispatch_fast_xrow<EXPV>(P, secL, thick, cur, upR, kap, kR, I, A, sT, top, w, w - 32);
-      xbuf ^= 1;
-    } else if (XROW) direction_dispatch_fast_norow<EXPV>(P, thick, cur, upR, kap, kR, I, A, sT);
+    if (FAITHFUL || P.thin) direction_dispatch_faithful(P, secL, cur, upR, kapF, kR, I, acc);
     else direction_dispatch_fast<EXPV>(P, secL, kmax, cur, upR, kap, kR, I, A, sT);
     if (writer) {
 #pragma unroll
@@ -784,21 +653,16 @@ static int march_capacity(Context& c, size_t smemBytes, int* blocks) {
   return RTB200_OK;
 }
 
-static void launch_cells(int dense, int expv, bool faithful, bool xrow, dim3 grid, cudaStream_t s,
-                         const BatchParams& bp, int N, int n) {
+static void launch_cells(int dense, int expv, bool faithful, dim3 grid, cudaStream_t s, const BatchParams& bp, int N,
+                         int n) {
   dim3 block(32, 8);
   // `dense`: 0 = compiler's choice of registers (2 blocks per SM), 1 = cap for 3 blocks, 2 = cap for 4 blocks
-  // `xrow`: row-axis hand-over through shared memory instead of recomputed (FAST arithmetic only)
-  if (faithful) { sweep_cell_kernel<true, 0, 2, false><<<grid, block, 0, s>>>(bp, N, n, n + 1, 3 * (n + 1) * (n + 1)); return; }
-#define RTB_LAUNCH(E, X)                                                                                                 \
-  if (dense == 1) sweep_cell_kernel<false, E, 3, X><<<grid, block, 0, s>>>(bp, N, n, n + 1, 3 * (n + 1) * (n + 1));      \
-  else if (dense >= 2) sweep_cell_kernel<false, E, 4, X><<<grid, block, 0, s>>>(bp, N, n, n + 1, 3 * (n + 1) * (n + 1)); \
-  else sweep_cell_kernel<false, E, 2, X><<<grid, block, 0, s>>>(bp, N, n, n + 1, 3 * (n + 1) * (n + 1))
-  if (xrow) {
-    if (expv == 1) { RTB_LAUNCH(1, true); } else { RTB_LAUNCH(0, true); }
-  } else {
-    if (expv == 1) { RTB_LAUNCH(1, false); } else { RTB_LAUNCH(0, false); }
-  }
+  if (faithful) { sweep_cell_kernel<true, 0, 2><<<grid, block, 0, s>>>(bp, N, n, n + 1, 3 * (n + 1) * (n + 1)); return; }
+#define RTB_LAUNCH(E)                                                                       \
+  if (dense == 1) sweep_cell_kernel<false, E, 3><<<grid, block, 0, s>>>(bp, N, n, n + 1, 3 * (n + 1) * (n + 1));      \
+  else if (dense >= 2) sweep_cell_kernel<false, E, 4><<<grid, block, 0, s>>>(bp, N, n, n + 1, 3 * (n + 1) * (n + 1)); \
+  else sweep_cell_kernel<false, E, 2><<<grid, block, 0, s>>>(bp, N, n, n + 1, 3 * (n + 1) * (n + 1))
+  if (expv == 1) { RTB_LAUNCH(1); } else { RTB_LAUNCH(0); }
 #undef RTB_LAUNCH
 }
 
@@ -1089,7 +953,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
           }
           dim3 gz = grid;
           gz.z = nb;
-          launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, c.tune.rowExchange != 0, gz, st, bp, (int)N, n);
+          launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, gz, st, bp, (int)N, n);
           nLaunched++;
         }
       }
@@ -1104,7 +968,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
         if (T.slot != k) continue;
         for (int step = 0; step < n; step++) {
           fill(bp.t[0], T, step, T.firstInSlot);
-          launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, c.tune.rowExchange != 0, grid, cs, bp, (int)N, n);
+          launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, grid, cs, bp, (int)N, n);
           nLaunched++;
         }
       }

@@ -70,7 +70,6 @@ struct Tuning {
   int expVariant = 1;    // exp(-tau) of the fast path: 0 = polynomial, 1 = 16-entry shared-memory table
   double l2BudgetMB = 96.0;
   int march = 0;         // uniform sweep: 1 = persistent layer-marching kernel (experimental, slower: DESIGN.md)
-  int rowExchange = 0;   // uniform sweep: row-axis hand-over through shared memory instead of recomputed
   int transposeZ = 1;    // uniform sweep: zones sweeping along the contiguous axis use a z-major copy of kappa / J
   int dirsPerTask = 0;   // directions of one zone swept together (0 = kMaxDirPerTask)
   int marchDebug = 0;    // experiments only: 1 = skip the neighbour polling (wrong results), 2 = spin without nanosleep

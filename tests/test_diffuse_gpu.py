@@ -60,22 +60,6 @@ def test_uniform_result_independent_of_launch_tuning(rt, engine, oracle, uvbg, s
     assert rel_err(J, o["J"]) < TOL
 
 
-@pytest.mark.parametrize("n,dense,expv,tau_hi", [(20, 2, 1, 3.0), (33, 1, 1, 3.0), (48, 2, 0, 3.0), (24, 2, 1, 150.0),
-                                                 (7, 0, 1, 3.0)])
-def test_row_exchange_gives_the_same_bits(rt, engine, oracle, uvbg, n, dense, expv, tau_hi):
-    """set_tuning(row_exchange=1): rows 1..7 of a block take the row-axis hand-over from shared memory (what the
-    neighbour thread computed) instead of recomputing it -- the same numbers, so the result must not change at all."""
-    g = W.uniform_grid(n, seed=31, tau_lo=1e-3, tau_hi=tau_hi)
-    _set(engine, g)
-    engine.set_tuning(dense=dense, expv=expv, row_exchange=0)
-    J0, n0 = engine.diffuse(uvbg["uvb"], uvbg["beta"])
-    engine.set_tuning(row_exchange=1)
-    J1, n1 = engine.diffuse(uvbg["uvb"], uvbg["beta"])
-    assert n0 == n1 and np.array_equal(J0, J1)
-    o = _oracle_J(oracle, g, uvbg)
-    assert rel_err(J1, o["J"], floor=1e-250) < TOL
-
-
 def test_uniform_optically_thick_and_thin_extremes(rt, engine, oracle, uvbg):
     # optically thick: per-segment tau up to ~450, intensities underflow to zero deep inside
     g = W.uniform_grid(24, seed=12, tau_lo=1e-3, tau_hi=150.0)
