@@ -186,13 +186,33 @@ def _pow10(a):
     return np.frompyfunc(lambda v: 10.0 ** v, 1, 1)(a).astype(np.float64)
 
 
+def smooth_level1_abundance(abun2, idx, nx):
+    """Level-1 smoothing of the second abundance (equiSources.f90:527-578): the values are scattered onto the n^3 base
+    grid (a later duplicate overwrites), filtered twice with (1/4, 1/2, 1/4) along i, then j, then k -- nothing comes
+    in across the box faces -- and gathered back into the real*4 list.  Each output adds its three terms in the order
+    the reference's scatter loop produces them: 0.25 u(i-1), then 0.5 u(i), then 0.25 u(i+1), starting from 0."""
+    u = np.zeros((nx, nx, nx))
+    u[idx[:, 0], idx[:, 1], idx[:, 2]] = np.asarray(abun2, dtype=np.float32).astype(np.float64)
+    for _ in range(2):
+        for ax in range(3):
+            t = np.zeros_like(u)
+            lo = [slice(None)] * 3; hi = [slice(None)] * 3
+            lo[ax] = slice(0, nx - 1); hi[ax] = slice(1, nx)
+            t[tuple(hi)] = t[tuple(hi)] + 0.25 * u[tuple(lo)]      # from i-1
+            t = t + 0.5 * u                                        # own
+            t[tuple(lo)] = t[tuple(lo)] + 0.25 * u[tuple(hi)]      # from i+1
+            u = t
+    return u[idx[:, 0], idx[:, 1], idx[:, 2]].astype(np.float32)
+
+
 def build_leaves(levels, metals=False):
     """Leaf arrays in `writeCell` order from the per-level lists of `read_grid_dat` (positions in kpc).
 
     Follows the driver: level 1 must hold n^3 cells (:427-436); the box is the level-1 min/max stretched by n/(n-1)
     (:455-477) and positions are normalised and stored back in SINGLE precision (:483-489); a level-l cell is dropped
     into the tree by descending l-1 times with `.lt.0.5` tests, and children created on the way inherit tgas, rho, HI,
-    HeI, HeII of their parent and get abun2 = 0 (:1882-1932); the target cell takes tgas = 10**lT, nH = 10**lnH,
+    HeI, HeII of their parent and get abun2 = 0 (:1882-1932); with metals the level-1 abun(:,2) is smoothed on the
+    base grid first (:527-578, `smooth_level1_abundance`); the target cell takes tgas = 10**lT, nH = 10**lnH,
     HI = nH 10**lx, rho = nH mh/psi, HeI = (1-psi) rho/mhe, HeII = 0, abun2 = abun(:,2) or 0.02 (:1935-1959).
     Returns the keyword arguments of `Transport.set_grid` plus `tgas`."""
     n1 = levels[0]["pos"].shape[0]
@@ -253,11 +273,15 @@ def build_leaves(levels, metals=False):
             vals["abun2"] = np.zeros(8 * new.size)                             # :1907 children start with abun2 = 0
             append(t, pack(cx, cy, cz, t), vals)
         # assign the cells of this level (a later duplicate overwrites an earlier one, as the sequential loop does)
+        abun = np.asarray(lv["abun"], dtype=np.float32) if metals else None
+        if metals and depth == 0:
+            abun = abun.copy()
+            abun[:, 1] = smooth_level1_abundance(abun[:, 1], base_i, nx)
         nH = _pow10(lv["lnH"])
         rho = nH * _MP / _PSI
         vals = dict(tgas=_pow10(lv["lT"]), rho=rho, HI=nH * _pow10(lv["lx"]),
                     HeI=(1.0 - _PSI) * rho / _MHE * 1.0, HeII=np.zeros(nH.size),
-                    abun2=np.asarray(lv["abun"], dtype=np.float32)[:, 1].astype(np.float64) if metals
+                    abun2=abun[:, 1].astype(np.float64) if metals
                     else np.full(nH.size, float(_F(0.02))))
         keys = pack(coords[depth][:, 0], coords[depth][:, 1], coords[depth][:, 2], depth)
         rows = np.array([index[depth][int(k)] for k in keys])

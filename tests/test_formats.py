@@ -98,6 +98,32 @@ def _reference_build(levels, metals):
                           HeI=(1 - psi) * rho / mhe, HeII=0.0,
                           abun2=float(rec["abun"][1]) if metals else float(f32(0.02)))
 
+    smoothed = None
+    if metals:
+        # smoothing level 1 abundancies (equiSources.f90:527-578), the reference's scatter loops as they stand
+        lv = levels[0]
+        pn = ((lv["pos"].astype(f32).astype(float) - a) / (b - a)).astype(f32).astype(float)
+        uni = np.zeros((nx, nx, nx))
+        cellIdx = [(int(x * nx), int(y * nx), int(z * nx)) for x, y, z in pn]
+        for c, ijk in enumerate(cellIdx):
+            uni[ijk] = float(f32(lv["abun"][c][1]))
+        for _ in range(2):
+            for ax in range(3):
+                tmp = np.zeros((nx, nx, nx))
+                for i in range(nx):
+                    for j in range(nx):
+                        for k in range(nx):
+                            tmp[i, j, k] = tmp[i, j, k] + 0.5 * uni[i, j, k]
+                            m = [i, j, k]
+                            if m[ax] > 0:
+                                q = list(m); q[ax] -= 1
+                                tmp[tuple(q)] = tmp[tuple(q)] + 0.25 * uni[i, j, k]
+                            if m[ax] < nx - 1:
+                                q = list(m); q[ax] += 1
+                                tmp[tuple(q)] = tmp[tuple(q)] + 0.25 * uni[i, j, k]
+                uni = tmp
+        smoothed = [f32(uni[ijk]) for ijk in cellIdx]
+
     for l, lv in enumerate(levels):
         pn = ((lv["pos"].astype(f32).astype(float) - a) / (b - a)).astype(f32).astype(float)
         for c in range(pn.shape[0]):
@@ -106,6 +132,8 @@ def _reference_build(levels, metals):
             rec = dict(lT=f32(lv["lT"][c]), lnH=f32(lv["lnH"][c]), lx=f32(lv["lx"][c]))
             if metals:
                 rec["abun"] = lv["abun"][c].astype(f32)
+                if l == 0:
+                    rec["abun"][1] = smoothed[c]
             place(base[i0][j0][k0], l + 1, x0 * float(nx) - i0, y0 * float(nx) - j0, z0 * float(nx) - k0, rec)
     out = []
 
