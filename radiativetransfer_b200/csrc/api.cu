@@ -268,6 +268,7 @@ int rtb200_set_tuning(rtb200_ctx* h, const char* key, double value) {
   else if (k == "l2_mb") c.tune.l2BudgetMB = value;
   else if (k == "march") c.tune.march = (int)value;
   else if (k == "transpose_z") c.tune.transposeZ = (int)value;
+  else if (k == "pdl") c.tune.pdl = (int)value;
   else if (k == "dirs_per_task") c.tune.dirsPerTask = (int)value;
   else if (k == "march_debug") c.tune.marchDebug = (int)value;
   else if (k == "portable_math") c.tune.portableMath = (int)value;

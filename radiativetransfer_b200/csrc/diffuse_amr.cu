@@ -248,6 +248,7 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
     }
   }
   if (CHECK) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");             // the flags are written by the launches before
     const volatile uint8_t* done = P.done;
 #pragma unroll
     for (int ray = 0; ray < 3; ray++)
@@ -263,6 +264,9 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
     kap[g] = P.kappaA[leaf * 6 + g];
     invk[g] = FAITHFUL ? 0. : P.kappaA[leaf * 6 + 3 + g];
   }
+  // Programmatic dependent launch: everything above is geometry or per-sweep input; the upstream intensities below
+  // come from the waves before this one (no-op for a grid launched without the attribute)
+  if (!CHECK) asm volatile("griddepcontrol.wait;" ::: "memory");
   double Iin[3][3];
 #pragma unroll
   for (int ray = 0; ray < 3; ray++) {
@@ -350,6 +354,7 @@ struct WaveParams {
 template <bool FAITHFUL, bool CHECK>
 __global__ void __launch_bounds__(128, 8) amr_wave_kernel(AmrParams P, WaveParams Wp, int ngroups) {
   __shared__ double sT[16];
+  asm volatile("griddepcontrol.launch_dependents;");               // the next wave may start its prologue early
   if (!FAITHFUL) {
     if (threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
     __syncthreads();
@@ -373,6 +378,7 @@ __global__ void __launch_bounds__(128, 8) amr_wave_kernel(AmrParams P, WaveParam
       else atomicMax(P.err, RTB200_ERR_NOMEM);
     }
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");               // lanes that had no item: before the atomics
   // the 8 directions of the leaf: butterfly sum (fixed order), one atomic per frequency group
 #pragma unroll
   for (int g = 0; g < 3; g++) {
@@ -534,23 +540,19 @@ struct AmrState {
   std::string tablesKey;
   AmrBuffers buffers;
 };
-static std::vector<std::pair<Context*, AmrState*>> g_states;
+// the nested-grid state lives in its context (opaque there: rtb200_internal.h only knows the pointer)
 static AmrState* state_of(Context& c) {
-  for (auto& p : g_states)
-    if (p.first == &c) return p.second;
-  g_states.push_back({&c, new AmrState()});
-  return g_states.back().second;
+  if (!c.amrState) c.amrState = new AmrState();
+  return static_cast<AmrState*>(c.amrState);
 }
 void amr_release(Context& c) {
-  for (size_t i = 0; i < g_states.size(); i++)
-    if (g_states[i].first == &c) {
-      for (int k = 0; k < 8; k++) cudaFree(g_states[i].second->plan.dSorted[k]);
-      cudaFree(g_states[i].second->plan.dPatIdx);
-      g_states[i].second->buffers.release();
-      delete g_states[i].second;
-      g_states.erase(g_states.begin() + i);
-      return;
-    }
+  AmrState* S = static_cast<AmrState*>(c.amrState);
+  if (!S) return;
+  for (int k = 0; k < 8; k++) cudaFree(S->plan.dSorted[k]);
+  cudaFree(S->plan.dPatIdx);
+  S->buffers.release();
+  delete S;
+  c.amrState = nullptr;
 }
 
 static int ensure_plan(Context& c, AmrState& S) {
@@ -732,6 +734,7 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int g0, int ng
   int64_t* lists[2] = {B.defA, B.defB};
   bool used[8] = {false, false, false, false, false, false, false, false};
   for (int i = 0; i < nd; i++) used[dl[i].combo] = true;
+  bool prevWasWave = false;
   for (int w = 0; w < S.plan.nkeys; w++) {
     int maxCount = 0;
     for (int k = 0; k < 8; k++) {
@@ -744,8 +747,22 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int g0, int ng
     Wp.deferredCount = B.defCount + cur;
     dim3 grid((maxCount + 15) / 16, ng);
     const bool check = !S.plan.balanced;
-    if (faithful) { if (check) amr_wave_kernel<true, true><<<grid, 128, 0, s>>>(P, Wp, ng); else amr_wave_kernel<true, false><<<grid, 128, 0, s>>>(P, Wp, ng); }
-    else { if (check) amr_wave_kernel<false, true><<<grid, 128, 0, s>>>(P, Wp, ng); else amr_wave_kernel<false, false><<<grid, 128, 0, s>>>(P, Wp, ng); }
+    // programmatic dependent launch on the previous wave (not for the first wave, nor right after a retry kernel)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (c.tune.pdl && prevWasWave) ? 1 : 0;
+    if (faithful) {
+      if (check) RTB_CUDA(cudaLaunchKernelEx(&cfg, amr_wave_kernel<true, true>, P, Wp, ng));
+      else RTB_CUDA(cudaLaunchKernelEx(&cfg, amr_wave_kernel<true, false>, P, Wp, ng));
+    } else {
+      if (check) RTB_CUDA(cudaLaunchKernelEx(&cfg, amr_wave_kernel<false, true>, P, Wp, ng));
+      else RTB_CUDA(cudaLaunchKernelEx(&cfg, amr_wave_kernel<false, false>, P, Wp, ng));
+    }
+    prevWasWave = true;
     (*launches)++;
     if (check && (w & 15) == 15) {
       // retry what has been deferred so far (nothing on 2:1-balanced grids)
@@ -754,6 +771,7 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int g0, int ng
       else amr_retry_kernel<false><<<64, 128, 0, s>>>(P, lists[cur], B.defCount + cur, lists[cur ^ 1], B.defCount + (cur ^ 1), defCap);
       (*launches)++;
       cur ^= 1;
+      prevWasWave = false;
     }
   }
   // drain the deferred list

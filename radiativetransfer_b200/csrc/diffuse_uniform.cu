@@ -260,6 +260,11 @@ sweep_cell_kernel(const __grid_constant__ BatchParams bp, int N, int n, int np1,
   const StepParams& sp = bp.t[blockIdx.z];
   const double* __restrict__ kappa = sp.kappa;
   __shared__ double sT[16];
+  // Programmatic dependent launch (set_tuning "pdl"): the next layer's grid may start as soon as every block of this
+  // one is running, do its own prologue (table, indices, opacities -- nothing a sweep kernel writes) and then wait at
+  // griddepcontrol.wait below until this grid has completed and flushed.  Both instructions are no-ops for a grid
+  // launched without the attribute.
+  asm volatile("griddepcontrol.launch_dependents;");
   if (threadIdx.y == 0 && threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
   __syncthreads();
   const int a = blockIdx.x * 31 - 1 + (int)threadIdx.x, b = blockIdx.y * 8 + threadIdx.y;
@@ -286,6 +291,7 @@ sweep_cell_kernel(const __grid_constant__ BatchParams bp, int N, int n, int np1,
   const int up = 3 * np1;                                      // one row up
   const double* pin = sp.planeIn + 3 * pidx;
   double* pout = sp.planeOut + 3 * pidx;
+  asm volatile("griddepcontrol.wait;" ::: "memory");           // the previous layer's planes and accumulators
   for (int q = 0; q < ndir; q++, pin += dstride, pout += dstride) {
     const LayerSeg& P = sp.P[q];
     const int kind = P.kind;
@@ -653,15 +659,31 @@ static int march_capacity(Context& c, size_t smemBytes, int* blocks) {
   return RTB200_OK;
 }
 
-static void launch_cells(int dense, int expv, bool faithful, dim3 grid, cudaStream_t s, const BatchParams& bp, int N,
-                         int n) {
-  dim3 block(32, 8);
+template <class Kernel>
+static cudaError_t launch_layer(Kernel kern, dim3 grid, cudaStream_t s, bool pdl, const BatchParams& bp, int N, int n) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(32, 8);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, bp, N, n, n + 1, 3 * (n + 1) * (n + 1));
+}
+
+// `pdl`: programmatic dependent launch on the previous launch of the stream (only for a layer whose predecessor in
+// the stream is the previous layer's sweep kernel)
+static cudaError_t launch_cells(int dense, int expv, bool faithful, bool pdl, dim3 grid, cudaStream_t s,
+                                const BatchParams& bp, int N, int n) {
   // `dense`: 0 = compiler's choice of registers (2 blocks per SM), 1 = cap for 3 blocks, 2 = cap for 4 blocks
-  if (faithful) { sweep_cell_kernel<true, 0, 2><<<grid, block, 0, s>>>(bp, N, n, n + 1, 3 * (n + 1) * (n + 1)); return; }
-#define RTB_LAUNCH(E)                                                                       \
-  if (dense == 1) sweep_cell_kernel<false, E, 3><<<grid, block, 0, s>>>(bp, N, n, n + 1, 3 * (n + 1) * (n + 1));      \
-  else if (dense >= 2) sweep_cell_kernel<false, E, 4><<<grid, block, 0, s>>>(bp, N, n, n + 1, 3 * (n + 1) * (n + 1)); \
-  else sweep_cell_kernel<false, E, 2><<<grid, block, 0, s>>>(bp, N, n, n + 1, 3 * (n + 1) * (n + 1))
+  if (faithful) return launch_layer(sweep_cell_kernel<true, 0, 2>, grid, s, pdl, bp, N, n);
+#define RTB_LAUNCH(E)                                                                             \
+  if (dense == 1) return launch_layer(sweep_cell_kernel<false, E, 3>, grid, s, pdl, bp, N, n);    \
+  else if (dense >= 2) return launch_layer(sweep_cell_kernel<false, E, 4>, grid, s, pdl, bp, N, n); \
+  else return launch_layer(sweep_cell_kernel<false, E, 2>, grid, s, pdl, bp, N, n)
   if (expv == 1) { RTB_LAUNCH(1); } else { RTB_LAUNCH(0); }
 #undef RTB_LAUNCH
 }
@@ -953,7 +975,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
           }
           dim3 gz = grid;
           gz.z = nb;
-          launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, gz, st, bp, (int)N, n);
+          RTB_CUDA(launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, c.tune.pdl && step > 0, gz, st, bp, (int)N, n));
           nLaunched++;
         }
       }
@@ -968,7 +990,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
         if (T.slot != k) continue;
         for (int step = 0; step < n; step++) {
           fill(bp.t[0], T, step, T.firstInSlot);
-          launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, grid, cs, bp, (int)N, n);
+          RTB_CUDA(launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, c.tune.pdl && step > 0, grid, cs, bp, (int)N, n));
           nLaunched++;
         }
       }
@@ -984,7 +1006,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
     // The launch sequence depends only on the plan, the mode and the buffers: capture once, replay afterwards.
     char key[256];
     snprintf(key, sizeof(key), "u:%d:%d:%d:%d:%p:%p:%p:%a:%a:%a", n, ntask, slots,
-             (int)faithful * 64 + c.tune.minBlocks * 4 + c.tune.expVariant + 1000 * c.tune.lockstep,
+             (int)faithful * 64 + c.tune.minBlocks * 4 + c.tune.expVariant + 1000 * c.tune.lockstep + 10000 * c.tune.pdl,
              (void*)c.dAcc, (void*)c.dPlanes, (void*)c.dKappa, uvb[0], uvb[1], uvb[2]);
     if (!c.graphExec || c.graphKey != key) {
       if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }

@@ -70,6 +70,7 @@ struct Tuning {
   int expVariant = 1;    // exp(-tau) of the fast path: 0 = polynomial, 1 = 16-entry shared-memory table
   double l2BudgetMB = 96.0;
   int march = 0;         // uniform sweep: 1 = persistent layer-marching kernel (experimental, slower: DESIGN.md)
+  int pdl = 1;           // uniform sweep: programmatic dependent launch of layer l+1 on layer l (its prologue overlaps the tail)
   int transposeZ = 1;    // uniform sweep: zones sweeping along the contiguous axis use a z-major copy of kappa / J
   int dirsPerTask = 0;   // directions of one zone swept together (0 = kMaxDirPerTask)
   int marchDebug = 0;    // experiments only: 1 = skip the neighbour polling (wrong results), 2 = spin without nanosleep
@@ -151,6 +152,7 @@ struct Context {
   double* dRates = nullptr;    // [6][nleaf] rate buffer of the host-pointer point-source API (lazy)
   // scratch of the point-source path, kept between calls (request i of a call reuses slot i; freed with the grid)
   std::vector<std::pair<void*, size_t>> pointPool;
+  void* amrState = nullptr;  // diffuse_amr.cu: wave plan, pattern tables and batch buffers of this context (amr_release frees it)
   double* dAcc = nullptr;      // slot accumulators
   size_t accBytes = 0;
   double* dPlanes = nullptr;   // ping-pong top-exit planes

@@ -46,13 +46,14 @@ def test_uniform_parity_vs_oracle(rt, engine, oracle, uvbg, n, seed, mode):
     assert rel_err(J, o["J"]) < TOL, rel_err(J, o["J"])
 
 
-@pytest.mark.parametrize("slots,graph,dense,expv,lockstep", [(1, 0, 0, 0, 0), (5, 1, 1, 1, 0), (24, 1, 0, 1, 0),
-                                                             (2, 0, 1, 0, 1), (32, 1, 2, 0, 1), (0, 1, 2, 1, 1),
-                                                             (7, 1, 2, 1, 1)])
-def test_uniform_result_independent_of_launch_tuning(rt, engine, oracle, uvbg, slots, graph, dense, expv, lockstep):
+@pytest.mark.parametrize("slots,graph,dense,expv,lockstep,pdl", [(1, 0, 0, 0, 0, 1), (5, 1, 1, 1, 0, 1),
+                                                                 (24, 1, 0, 1, 0, 0), (2, 0, 1, 0, 1, 0),
+                                                                 (32, 1, 2, 0, 1, 1), (0, 1, 2, 1, 1, 0),
+                                                                 (0, 0, 2, 1, 1, 1), (7, 1, 2, 1, 1, 1)])
+def test_uniform_result_independent_of_launch_tuning(rt, engine, oracle, uvbg, slots, graph, dense, expv, lockstep, pdl):
     g = W.uniform_grid(20, seed=11)
     _set(engine, g)
-    engine.set_tuning(slots=slots, graph=graph, dense=dense, expv=expv, lockstep=lockstep)
+    engine.set_tuning(slots=slots, graph=graph, dense=dense, expv=expv, lockstep=lockstep, pdl=pdl)
     J, _ = engine.diffuse(uvbg["uvb"], uvbg["beta"])
     J2, _ = engine.diffuse(uvbg["uvb"], uvbg["beta"])   # second call replays the cached plan / graph
     assert np.array_equal(J, J2)

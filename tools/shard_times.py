@@ -15,11 +15,11 @@ J = torch.zeros(3, n ** 3, dtype=torch.float64, device="cuda:0")
 s = torch.cuda.current_stream().cuda_stream
 shards = sharding.shard_directions(world, n_angular_level=3, nx=n)
 for rank in (0, world // 2, world - 1):
-    for dpt in (0, 8, 6, 4, 3, 2):
-        t.set_tuning(dirs_per_task=dpt)
+    for dpt, pdl in ((0, 0), (0, 1)):
+        t.set_tuning(dirs_per_task=dpt, pdl=pdl)
         for rep in range(3):
             t.diffuse_device(bg["uvb"], bg["beta"], J.data_ptr(), rays=shards[rank], stream=s)
             torch.cuda.synchronize()
             st = t.last_stats()
-        print(f"world {world} rank {rank} ndir {len(shards[rank])} dpt {dpt}: sweep_ms {st['sweep_ms']:.3f} total_ms {st['device_ms']:.3f} launches {st['launches']}", flush=True)
+        print(f"world {world} rank {rank} ndir {len(shards[rank])} dpt {dpt} pdl {pdl}: sweep_ms {st['sweep_ms']:.3f} total_ms {st['device_ms']:.3f} launches {st['launches']}", flush=True)
 t.close()

@@ -32,8 +32,9 @@ for n in args.n:
         march = int(f[5]) if len(f) > 5 else 0
         mdbg = int(f[6]) if len(f) > 6 else 0
         dpt = int(f[7]) if len(f) > 7 else 0
+        pdl = int(f[8]) if len(f) > 8 else 0
         t.set_math(rt.MATH_FAST if mode == "fast" else rt.MATH_FAITHFUL)
-        t.set_tuning(slots=int(slots), dense=int(dense), expv=int(expv), lockstep=int(lockstep), march=march, march_debug=mdbg, dirs_per_task=dpt)
+        t.set_tuning(slots=int(slots), dense=int(dense), expv=int(expv), lockstep=int(lockstep), march=march, march_debug=mdbg, dirs_per_task=dpt, pdl=pdl)
         ms = []
         for rep in range(args.reps + 1):
             nseg = t.diffuse_device(bg["uvb"], bg["beta"], J.data_ptr(), stream=s)
@@ -41,7 +42,7 @@ for n in args.n:
             st = t.last_stats()
             ms.append(st["sweep_ms"])
         best = min(ms[1:])
-        print(f"n={n} slots={slots} dense={dense} expv={expv} lockstep={lockstep} march={march}/{mdbg} dpt={dpt} math={mode}: ms={['%.2f' % m for m in ms]} "
+        print(f"n={n} slots={slots} dense={dense} expv={expv} lockstep={lockstep} march={march}/{mdbg} dpt={dpt} pdl={pdl} math={mode}: ms={['%.2f' % m for m in ms]} "
               f"seg/s={nseg / best * 1e3:.3e} alg GB/s={st['algorithmic_bytes'] / best / 1e6:.1f} "
               f"total_ms={st['device_ms']:.2f} launches={st['launches']}", flush=True)
     t.close()
