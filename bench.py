@@ -71,6 +71,26 @@ def make_inputs(spec, seed=1):
 
 # ------------------------------------------------------------------------------------------------------------------
 def sample_clocks(stop, out, dev):
+    """SM clock and throttle reasons of GPU `dev` every 20 ms until `stop` is set.  NVML in-process (nvidia_ml_py): a
+    query costs microseconds and does not fork -- spawning nvidia-smi from a process with a CUDA context stalls the
+    launching thread for milliseconds, which is visible in short timed regions.  nvidia-smi is the fallback."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(int(dev))
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        bits = [0x8, 0x40, 0x20, 0x4]          # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        while True:
+            r = int(reasons_fn(h))
+            out.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx)] +
+                       ["Active" if r & b else "Not Active" for b in bits])
+            if stop.wait(0.02):
+                break
+        return
+    except Exception:
+        pass
     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     while not stop.is_set():
