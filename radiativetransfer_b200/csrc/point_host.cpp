@@ -5,6 +5,7 @@
 // Everything here is O(400) or O(16380) work per call; the 400 x 11^4 table sums and the ray march run on the GPU.
 #include "point_host.h"
 
+#include <algorithm>
 #include <cmath>
 
 #include "geometry.h"
@@ -77,8 +78,10 @@ void point_source_spectrum(const PointFreq& F, int nWave, const double* waveleng
   for (int i = 1; i < kNfreq; i++) {
     const double freq = F.nu[i], dnu = F.nu[i] - F.nu[i - 1];
     const double wl = kClight / (freq * kEvToHz);
-    int w = 0;  // 0-based index of the bracket's lower edge
-    while (wl > wavelength[w + 1]) w++;
+    // 0-based index of the bracket's lower edge: the reference scans `while (wl > wavelength(w+1)) w++` from the
+    // first entry; the table ascends, so that is the first entry from the second on that is not below wl
+    int w = (int)(std::lower_bound(wavelength + 1, wavelength + nWave, wl) - (wavelength + 1));
+    if (w > nWave - 2) w = nWave - 2;   // (the reference would run off the table)
     double cw = (wl - wavelength[w]) / (wavelength[w + 1] - wavelength[w]);
     cw = std::fmin(std::fmax(0., cw), 1.);
     auto L = [&](int m, int t, int k) { return lum[((size_t)m * 2 + t) * nWave + k]; };

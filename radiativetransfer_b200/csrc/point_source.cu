@@ -813,8 +813,13 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
     while (i < kNfreq && !(F.nu[i] >= thrE[r])) i++;
     tp.thr[r] = i;
   }
-  std::vector<double> dirs;
-  if (int st = point_pixel_directions(in.maxPixelLevel, dirs)) return st;
+  // pixel directions of levels 1..maxPixelLevel: a constant table, computed once per context
+  if (c.pointDirsLevel != in.maxPixelLevel) {
+    c.pointDirs.clear();
+    if (int st = point_pixel_directions(in.maxPixelLevel, c.pointDirs)) return st;
+    c.pointDirsLevel = in.maxPixelLevel;
+  }
+  const std::vector<double>& dirs = c.pointDirs;
   std::vector<double> outSig(4 * kNenergy);
   for (int e = 0; e < kNenergy; e++) {
     outSig[e] = F.out24[e]; outSig[kNenergy + e] = F.out26[e]; outSig[2 * kNenergy + e] = F.out25[e];
@@ -849,6 +854,8 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
   std::vector<double> hAb((size_t)nsrc);
   RTB_CUDA(cudaMemcpyAsync(hAb.data(), dAb, (size_t)nsrc * 8, cudaMemcpyDeviceToHost, s));
   RTB_CUDA(cudaStreamSynchronize(s));
+  // (the GPU idles while the host prepares the spectra: keep this short -- binary search for the wavelength bracket,
+  // the pixel directions cached above.  Host threads made the typical call faster still but the slow calls slower.)
   std::vector<double> dtmp((size_t)nsrc * kNfreq);
   for (int i = 0; i < nsrc; i++) {
     int iMetal; double coefMetal;

@@ -152,6 +152,8 @@ struct Context {
   double* dRates = nullptr;    // [6][nleaf] rate buffer of the host-pointer point-source API (lazy)
   // scratch of the point-source path, kept between calls (request i of a call reuses slot i; freed with the grid)
   std::vector<std::pair<void*, size_t>> pointPool;
+  std::vector<double> pointDirs;   // HEALPix pixel directions of levels 1..pointDirsLevel (host copy)
+  int pointDirsLevel = 0;
   void* amrState = nullptr;  // diffuse_amr.cu: wave plan, pattern tables and batch buffers of this context (amr_release frees it)
   double* dAcc = nullptr;      // slot accumulators
   size_t accBytes = 0;
