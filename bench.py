@@ -70,8 +70,11 @@ def make_inputs(spec, seed=1):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+CLOCK_PERIOD_S = float(os.environ.get("RTB_BENCH_CLOCK_PERIOD", "0.05"))   # seconds between NVML clock samples
+
+
 def sample_clocks(stop, out, dev):
-    """SM clock and throttle reasons of GPU `dev` every 20 ms until `stop` is set.  NVML in-process (nvidia_ml_py): a
+    """SM clock and throttle reasons of GPU `dev` every CLOCK_PERIOD_S until `stop` is set.  NVML in-process (nvidia_ml_py): a
     query costs microseconds and does not fork -- spawning nvidia-smi from a process with a CUDA context stalls the
     launching thread for milliseconds, which is visible in short timed regions.  nvidia-smi is the fallback."""
     try:
@@ -86,7 +89,7 @@ def sample_clocks(stop, out, dev):
             r = int(reasons_fn(h))
             out.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx)] +
                        ["Active" if r & b else "Not Active" for b in bits])
-            if stop.wait(0.02):
+            if stop.wait(CLOCK_PERIOD_S):
                 break
         return
     except Exception:
