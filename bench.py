@@ -70,7 +70,7 @@ def make_inputs(spec, seed=1):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-CLOCK_PERIOD_S = float(os.environ.get("RTB_BENCH_CLOCK_PERIOD", "0.05"))   # seconds between NVML clock samples
+CLOCK_PERIOD_S = float(os.environ.get("RTB_BENCH_CLOCK_PERIOD", "0.1"))   # seconds between NVML clock samples
 
 
 def sample_clocks(stop, out, dev):
