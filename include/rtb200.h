@@ -57,7 +57,18 @@ const char* rtb200_status_string(int status);
 int rtb200_create(int device, rtb200_ctx** ctx);
 int rtb200_destroy(rtb200_ctx* ctx);
 int rtb200_set_math(rtb200_ctx* ctx, int math_mode);
-/* launch tuning knobs ("slots", "graph", "dense", "point_batch", ...); results do not depend on them.
+/* Launch tuning knobs; results do not depend on them (tests/test_diffuse_gpu.py, test_point_gpu.py).  Keys:
+ *   uniform sweep  "slots" (zone tasks per launch, 0 = all), "graph" (CUDA graph replay, 1), "dense" (register cap:
+ *                  0/1/2 = 2/3/4 blocks per SM, 2), "expv" (1 = table exponential), "lockstep" (one launch per layer
+ *                  for all tasks, 1), "dirs_per_task" (0 = chosen from a wave model), "transpose_z" (z-major copy for
+ *                  the zones sweeping along the contiguous axis, 1), "pdl" (programmatic dependent launch of layer
+ *                  l+1 on layer l, also used by the nested-grid waves, 1), "march"/"march_debug" (experimental
+ *                  persistent kernel, 0), "l2_mb"
+ *   nested grids   "force_amr" (general octree path on a uniform grid), "amr_batch" (directions per batch, 0 = as many
+ *                  as fit in memory)
+ *   point sources  "point_batch" (sources per batch), "point_min_blocks" (register cap of the march kernel, 5),
+ *                  "point_deposit" (0 = fp64 RED, 1 = records + sort + segmented reduction), "point_record_cap",
+ *                  "point_refill" (lane refill on the last pixel level, 0)
  * "portable_math" (default 1) selects, for the FAITHFUL point-source path, exp/log built from IEEE +,*,/,fma
  * (csrc/portable_math.h) instead of CUDA libm, so that a host build of the same header reproduces it bit for bit. */
 int rtb200_set_tuning(rtb200_ctx* ctx, const char* key, double value);
