@@ -48,6 +48,7 @@ WORKLOADS = {
     # config 4 style: the reference's outer loop, sweep -> ionisation equilibrium, 10 passes per step, all on the device
     "iterate10-256^3-uniform-192dir": ("iterate", 256, 10),
     "iterate10-64^3-uniform-192dir": ("iterate", 64, 10),
+    "iterate10-64^3-amr3-192dir": ("iterate", 64, 10, 3),     # the same loop on the config-5 style nested grid
     # config-5 style nested grid: n^3 base + refinement levels around a synthetic disc (general octree path)
     "diffuse-128^3-amr2-192dir": ("amr", 128, 2),
     "diffuse-64^3-amr3-192dir": ("amr", 64, 3),
@@ -62,6 +63,8 @@ def make_inputs(spec, seed=1):
     """(n, grid dict, background) of a diffuse workload: uniform n^3 or a nested grid"""
     from radiativetransfer_b200 import workloads as W
     if isinstance(spec, tuple) and spec[0] == "iterate":
+        if len(spec) > 3:   # nested grid: spec[3] refinement levels around the synthetic disc
+            return spec[1], W.nested_grid(spec[1], spec[3], W.disc_refine(spec[3]), seed=5), W.uvb_background(3.0)
         return spec[1], W.uniform_grid(spec[1], seed=seed), W.uvb_background(3.0)
     if isinstance(spec, tuple):
         _, n, levels = spec
@@ -413,7 +416,7 @@ def main():
     N = int(grid["level"].size)
     spec = WORKLOADS[args.workload]
     iterations = spec[2] if isinstance(spec, tuple) and spec[0] == "iterate" else 0
-    uniform = not isinstance(spec, tuple) or iterations > 0
+    uniform = not isinstance(spec, tuple) or (iterations > 0 and len(spec) == 3)
     eng = rt.Transport(device=local)
     eng.set_grid(n, grid["level"], grid["HI"], grid["HeI"], grid["HeII"], grid["rho"], grid["abun2"], grid["box_size"])
     shards = sharding.shard_directions(world, n_angular_level=3, nx=n)
