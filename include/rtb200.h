@@ -112,6 +112,20 @@ int rtb200_diffuse_rates_device(rtb200_ctx* ctx, const double* J_device, const d
                                 const double* ksi26, double* k24_device, double* k25_device, double* k26_device,
                                 void* stream);
 
+/* UV-background tables that feed the sweep (host only, no device needed): the band amplitudes uvb1..3 with the
+ * effective slopes alpha(3) (equiSources.f90:198-246 + powerSpectrumIndex :4985-5043) and uvbBetaTable.f90:31-296.
+ *   rtb200_uvb_amplitudes   uvb[3], alpha[3] for a redshift and the `uvbCoefficient` of inputParameters
+ *   rtb200_uvb_beta_table   table57 = [group 1..3][beta24, beta25, beta26, beta27..31, ksi24, ksi25, ksi26, ksi27..31,
+ *                           gammaHI, gammaHeI, gammaHeII] (the fields of group1..3, definitionsModule.f90)
+ *   rtb200_uvb_background   both, returned in the shapes the calls above take: beta[9] = [group][beta24, beta26,
+ *                           beta25], ksi24[3], ksi25[1] (group 3), ksi26[2] (groups 2, 3); any output may be NULL.
+ * nfreq = nfbins = 400, freqdel = frequencyBinWidth = (double)0.02f in the reference (definitionsModule.f90:239-241).
+ * Returns RTB200_ERR_ARG where powerSpectrumIndex prints 'wrong sign' and stops. */
+int rtb200_uvb_amplitudes(double currentRedshift, double uvbCoefficient, double* uvb, double* alpha);
+int rtb200_uvb_beta_table(int nfreq, double freqdel, const double* alpha, double* table57);
+int rtb200_uvb_background(double currentRedshift, double uvbCoefficient, int nfreq, double freqdel, double* uvb,
+                          double* alpha, double* beta, double* ksi24, double* ksi25, double* ksi26, double* table57);
+
 /* Point-source pass: replaces the source loop equiSources.f90:1256-1370 with its internal procedures
  * startNewLongRay (:3120-3385), drawSegment (:2412-2595), find/zoom??Neighbour (:2647-2960),
  * getRatesHydrogenHelium (:4157-4311) and the per-source table build stellarBetaTable.f90 (+ stellarPopulationModule.f90,
@@ -128,6 +142,8 @@ int rtb200_diffuse_rates_device(rtb200_ctx* ctx, const double* J_device, const d
  *   krate24,25,26, crate24,25,26 [nleaf]   ACCUMULATED (+=) like the reference's cell fields (zeroed by setZeroRates)
  *   ndotRemaining[nsrc][7], ndotBoundary[nsrc][7], ndotDust[nsrc], ndotSpectrum[nsrc][300]  per-source escape
  *                               diagnostics (:3198-3233); each may be NULL
+ *   highestPixelLevel[nsrc]     deepest HEALPix level a split of the source has opened (:1266, :3316; 0 = no ray
+ *                               split), the fourth column of the driver's 'src:' line (:1353-1357); may be NULL
  *   nseg                        optional: ray-cell segment updates performed (iterations of the loop at :3168)
  * rtb200_set_math: RTB200_MATH_FAITHFUL evaluates every table lookup with the reference's operation sequence;
  * RTB200_MATH_FAST evaluates the same interpolant without the R(d) - R(d+tau) cancellation.                        */
@@ -135,7 +151,7 @@ int rtb200_point(rtb200_ctx* ctx, int nWave, const double* wavelength, const dou
                  double coefSpectrum, const double* aDust, int dustApproximation, int maxPixelLevel, int32_t nsrc,
                  const int32_t* srcLeaf, const int32_t* srcWeight, double* krate24, double* krate25, double* krate26,
                  double* crate24, double* crate25, double* crate26, double* ndotRemaining, double* ndotBoundary,
-                 double* ndotDust, double* ndotSpectrum, int64_t* nseg);
+                 double* ndotDust, double* ndotSpectrum, int32_t* highestPixelLevel, int64_t* nseg);
 
 /* Same pass with the rates left on the GPU: rates_device = device pointer to [6][nleaf] doubles in the order krate24,
  * krate25, krate26, crate24, crate25, crate26 (accumulated); the diagnostics are host pointers (NULL = not wanted). */
@@ -143,7 +159,7 @@ int rtb200_point_device(rtb200_ctx* ctx, int nWave, const double* wavelength, co
                         const double* metallicity, double coefSpectrum, const double* aDust, int dustApproximation,
                         int maxPixelLevel, int32_t nsrc, const int32_t* srcLeaf, const int32_t* srcWeight,
                         double* rates_device, void* stream, double* ndotRemaining, double* ndotBoundary,
-                        double* ndotDust, double* ndotSpectrum, int64_t* nseg);
+                        double* ndotDust, double* ndotSpectrum, int32_t* highestPixelLevel, int64_t* nseg);
 
 /* Ionisation equilibrium per leaf: replaces solveRateEquations (equiSources.f90:3459-3677), the consumer of the
  * transport results, so that the outer transport <-> chemistry iteration can stay on the GPU.
@@ -192,6 +208,10 @@ int rtb200_patterns(int nAngularLevel, int64_t iray, int nx, double* out);
 /* upstream leaf of every leaf for one direction, [3][nleaf] = xy, yz, xz; -1 boundary, -2 ray inactive
  * (transportRoutinesModule.f90:264-418) */
 int rtb200_neighbours(rtb200_ctx* ctx, int nAngularLevel, int64_t iray, int32_t* nb);
+
+/* exp / log of csrc/portable_math.h evaluated on the device for n host values (bit-identity with a host build of the
+ * same header is what makes the FAITHFUL point-source deposits comparable bit for bit, tests/test_portable_math.py) */
+int rtb200_debug_portable_math(rtb200_ctx* ctx, int64_t n, const double* x, double* expOut, double* logOut);
 
 /* timing of the last rtb200_diffuse* call, from CUDA events on the launch stream: device milliseconds of the whole
  * call (opacities + sweep + merge) and of the sweep kernels alone, kernel launches issued (all / sweep kernel), and

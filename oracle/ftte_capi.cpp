@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY (see ftte_common.h).  extern "C" entry points of the CPU oracle, loaded with ctypes
 // by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.  Never by the product.
 #include "ftte_common.h"
+#include "../radiativetransfer_b200/csrc/portable_math.h"
 
 using namespace ftte;
 
@@ -65,6 +66,21 @@ int ftte_point(void* h, int nWave, const double* wavelength, const double* lum, 
   PointSpectra S{nWave, wavelength, lum, metallicity, coefSpectrum, aDust};
   return pointSolve(*(Grid*)h, S, dustApproximation, maxPixelLevel, nsrc, srcLeaf, srcWeight, rates, ndotRemaining,
                     ndotBoundary, ndotDust, ndotSpectrum, nseg, trace, traceCap, traceLen);
+}
+
+// highestPixelLevel of the sources of the calling thread's last ftte_point call (equiSources.f90:1353-1357, 'src:' line)
+int ftte_point_highest_pixel_level(int32_t* out, int n) {
+  const auto& v = ftte::lastHighestPixelLevel();
+  for (int i = 0; i < n; i++) out[i] = i < (int)v.size() ? v[i] : 0;
+  return (int)v.size();
+}
+
+// host build of the portable exp/log (checked against a 50-digit evaluation in tests/test_portable_math.py)
+void ftte_pm_eval(int64_t n, const double* x, double* expOut, double* logOut) {
+  for (int64_t i = 0; i < n; i++) {
+    if (expOut) expOut[i] = rtb_pm::pm_exp(x[i]);
+    if (logOut) logOut[i] = rtb_pm::pm_log(x[i]);
+  }
 }
 
 void ftte_set_portable_math(int on) { setPortableMath(on); }

@@ -118,6 +118,7 @@ int pointSolve(Grid& g, const PointSpectra& S, int dustApproximation, int maxPix
                const int32_t* srcWeight, double* rates, double* ndotRemaining, double* ndotBoundary, double* ndotDust,
                double* ndotSpectrum, int64_t* nsegOut, int64_t* trace, int64_t traceCap, int64_t* traceLen);
 void setPortableMath(int on);
+const std::vector<int32_t>& lastHighestPixelLevel();   // per source of the calling thread's last pointSolve
 int chemistrySolve(int64_t nleaf, int nx, double physicalBoxSize, const int8_t* level, const double* rho,
                    const double* tgas, double* HI, double* HeI, double* HeII, const double* rates, const double* J,
                    const double* ksi, const double* uniform, int nratec, double logtem0, double logtem9, double dlogtem,

@@ -46,6 +46,8 @@ def lib():
                                  C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_int64,
                                  C.POINTER(C.c_int64)]
+        L.ftte_point_highest_pixel_level.restype = C.c_int
+        L.ftte_point_highest_pixel_level.argtypes = [C.c_void_p, C.c_int]
         L.ftte_point_tables.restype = C.c_int
         L.ftte_point_tables.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
                                         C.c_double, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]
@@ -142,8 +144,10 @@ def _point(self, spectra, src_leaf, src_weight, dust_approximation=0, max_pixel_
     st = self.L.ftte_point(self.h, int(wl.size), _p(wl), _p(lum), _p(met), float(spectra["coef_spectrum"]), _p(ad),
                            int(dust_approximation), int(max_pixel_level), ns, _p(leaf), _p(wt), _p(R), _p(rem), _p(bnd),
                            _p(dust), _p(spec), C.byref(nseg), _p(tr) if trace_cap else None, int(trace_cap), C.byref(tl))
+    hpl = np.zeros(ns, dtype=np.int32)
+    self.L.ftte_point_highest_pixel_level(_p(hpl), ns)     # same thread: the call above filled it
     out = dict(rates=R, ndot_remaining=rem, ndot_boundary=bnd, ndot_dust=dust, ndot_spectrum=spec, nseg=nseg.value,
-               status=st)
+               status=st, highest_pixel_level=hpl)
     if trace_cap:
         out["trace"] = tr[:tl.value].copy()
     return out
@@ -191,6 +195,17 @@ def set_portable_math(on):
     lib().ftte_set_portable_math(int(bool(on)))
 
 
+def pm_eval(x):
+    """(pm_exp(x), pm_log(x)) of csrc/portable_math.h compiled for the host"""
+    L = lib()
+    L.ftte_pm_eval.restype = None
+    L.ftte_pm_eval.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    x = _f64(x)
+    e, l = np.empty_like(x), np.empty_like(x)
+    L.ftte_pm_eval(int(x.size), _p(x), _p(e), _p(l))
+    return e, l
+
+
 def point_tables(spectra, i_metal, coef_metal):
     wl = _f64(spectra["wavelength"]); lum = _f64(spectra["lum"]); met = _f64(spectra["metallicity"])
     ad = _f64(spectra["a_dust"])
@@ -198,6 +213,28 @@ def point_tables(spectra, i_metal, coef_metal):
     st = lib().ftte_point_tables(int(wl.size), _p(wl), _p(lum), _p(met), float(spectra["coef_spectrum"]), _p(ad),
                                  int(i_metal), float(coef_metal), _p(out), C.byref(tot), _p(sig))
     return dict(tables=out, total_integral=tot.value, output_sigma=sig, status=st)
+
+
+def uvb_tables(redshift=3.0, uvb_coefficient=1.0, nfreq=400, freqdel=float(np.float32(0.02))):
+    """equiSources.f90:198-246 + powerSpectrumIndex (:4985-5043) + uvbBetaTable.f90: dict(uvb[3], alpha[3], extra[8] =
+    uvbStellar1..3, uvbQuasar1..3, uniformQuasar, uniformStellar; table[3, 19] = beta24..31, ksi24..31, gammaHI, gammaHeI,
+    gammaHeII per group; status)"""
+    L = lib()
+    L.ftte_uvb.restype = C.c_int
+    L.ftte_uvb.argtypes = [C.c_double, C.c_double, C.c_int, C.c_double] + [C.c_void_p] * 4
+    uvb, alpha, extra, tab = np.zeros(3), np.zeros(3), np.zeros(8), np.zeros((3, 19))
+    st = L.ftte_uvb(float(redshift), float(uvb_coefficient), int(nfreq), float(freqdel), _p(uvb), _p(alpha), _p(extra),
+                    _p(tab))
+    return dict(uvb=uvb, alpha=alpha, extra=extra, table=tab, status=st)
+
+
+def power_spectrum_index(uvb1, alpha1, uvb2, alpha2, nug, nugplus, bound):
+    L = lib()
+    L.ftte_power_spectrum_index.restype = C.c_int
+    L.ftte_power_spectrum_index.argtypes = [C.c_double] * 6 + [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    tot, al = C.c_double(0), C.c_double(0)
+    st = L.ftte_power_spectrum_index(uvb1, alpha1, uvb2, alpha2, nug, nugplus, int(bool(bound)), C.byref(tot), C.byref(al))
+    return st, tot.value, al.value
 
 
 def direction(n_angular_level, iray):

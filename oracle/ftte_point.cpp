@@ -6,6 +6,8 @@
 //   :4157-4311 (getRatesHydrogenHelium); stellarBetaTable.f90:31-285; stellarPopulationModule.f90:7-50;
 //   dustModule.f90:30-73.
 // Single thread, libm, no FMA contraction.
+#include <algorithm>
+
 #include "ftte_common.h"
 // exp/log built from IEEE +,*,/,fma only; lives with the product because the device kernels use the same source.
 // With ftte_set_portable_math(1) the oracle evaluates the table sums, the table lookups and the escape diagnostics
@@ -457,6 +459,10 @@ struct PointSolver {
   }
 };
 
+// highestPixelLevel (equiSources.f90:1266, :3316) of every source of the last pointSolve call on this thread
+static thread_local std::vector<int32_t> g_lastHighestPixelLevel;
+const std::vector<int32_t>& lastHighestPixelLevel() { return g_lastHighestPixelLevel; }
+
 // equiSources.f90:1256-1370 for a list of sources given by host leaf and multiplicity
 int pointSolve(Grid& g, const PointSpectra& S, int dustApproximation, int maxPixelLevel, int nsrc, const int32_t* srcLeaf,
                const int32_t* srcWeight, double* rates /* [6][nleaf] accumulated */, double* ndotRemaining /* [nsrc][7] */,
@@ -469,6 +475,7 @@ int pointSolve(Grid& g, const PointSpectra& S, int dustApproximation, int maxPix
   ps.maxPixelLevel = maxPixelLevel;
   ps.trace = trace; ps.traceCap = traceCap;
   PointTables T;
+  g_lastHighestPixelLevel.assign((size_t)std::max(nsrc, 0), 0);
   for (int s = 0; s < nsrc; s++) {
     if (srcWeight[s] <= 0) continue;
     for (int i = 0; i < 7; i++) ps.ndotRemaining[i] = ps.ndotBoundary[i] = 0.;
@@ -504,6 +511,7 @@ int pointSolve(Grid& g, const PointSpectra& S, int dustApproximation, int maxPix
     for (int i = 0; i < 7; i++) { ndotRemaining[s * 7 + i] = ps.ndotRemaining[i]; ndotBoundary[s * 7 + i] = ps.ndotBoundary[i]; }
     ndotDust[s] = ps.ndotDust;
     for (int i = 0; i < 300; i++) ndotSpectrum[(size_t)s * 300 + i] = ps.ndotSpectrum[i];
+    g_lastHighestPixelLevel[s] = ps.highestPixelLevel;
   }
   std::memcpy(rates, g.rate.data(), sizeof(double) * 6 * nl);
   if (nsegOut) *nsegOut = ps.nseg;

@@ -25,10 +25,13 @@ SIGNATURES = {
     "rtb200_diffuse": (C.c_int, [P, C.c_int, P, P, P, C.c_int32, P, P, P, C.POINTER(C.c_int64)]),
     "rtb200_diffuse_device": (C.c_int, [P, C.c_int, P, P, P, C.c_int32, P, P, C.POINTER(C.c_int64)]),
     "rtb200_diffuse_rates_device": (C.c_int, [P, P, P, P, P, P, P, P, P]),
+    "rtb200_uvb_amplitudes": (C.c_int, [C.c_double, C.c_double, P, P]),
+    "rtb200_uvb_beta_table": (C.c_int, [C.c_int, C.c_double, P, P]),
+    "rtb200_uvb_background": (C.c_int, [C.c_double, C.c_double, C.c_int, C.c_double, P, P, P, P, P, P, P]),
     "rtb200_point": (C.c_int, [P, C.c_int, P, P, P, C.c_double, P, C.c_int, C.c_int, C.c_int32, P, P, P, P, P, P, P, P,
-                              P, P, P, P, C.POINTER(C.c_int64)]),
+                              P, P, P, P, P, C.POINTER(C.c_int64)]),
     "rtb200_point_device": (C.c_int, [P, C.c_int, P, P, P, C.c_double, P, C.c_int, C.c_int, C.c_int32, P, P, P, P, P,
-                                     P, P, P, C.POINTER(C.c_int64)]),
+                                     P, P, P, P, C.POINTER(C.c_int64)]),
     "rtb200_point_trace": (C.c_int, [P, C.c_int, P, P, P, C.c_double, P, C.c_int, C.c_int, C.c_int32, P, P, P,
                                     C.POINTER(C.c_int64), P, C.c_int64, C.POINTER(C.c_int64)]),
     "rtb200_point_tables": (C.c_int, [P, C.c_int, P, P, P, C.c_double, P, C.c_int, C.c_double, P]),
@@ -41,6 +44,7 @@ SIGNATURES = {
                                    C.POINTER(C.c_double)]),
     "rtb200_patterns": (C.c_int, [C.c_int, C.c_int64, C.c_int, P]),
     "rtb200_neighbours": (C.c_int, [P, C.c_int, C.c_int64, P]),
+    "rtb200_debug_portable_math": (C.c_int, [P, C.c_int64, P, P, P]),
     "rtb200_last_stats": (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                     C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
 }

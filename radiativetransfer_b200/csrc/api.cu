@@ -6,9 +6,18 @@
 #include <algorithm>
 #include <string>
 
+#include "portable_math.h"
 #include "rtb200_internal.h"
 
 namespace rtb {
+
+// device evaluation of the portable exp/log (csrc/portable_math.h) for the bit-identity check against the host build
+__global__ void portable_math_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ e, double* __restrict__ l) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    e[i] = rtb_pm::pm_exp(x[i]);
+    l[i] = rtb_pm::pm_log(x[i]);
+  }
+}
 
 static thread_local char g_cudaErr[512] = "";
 
@@ -371,13 +380,15 @@ static PointInputs make_point_inputs(int nWave, const double* wavelength, const 
   return in;
 }
 
-static void split_diag(const std::vector<double>& d, int nsrc, double* rem, double* bnd, double* dust, double* spec) {
+static void split_diag(const std::vector<double>& d, int nsrc, double* rem, double* bnd, double* dust, double* spec,
+                       int32_t* hpl) {
   for (int s = 0; s < nsrc; s++) {
     const double* p = d.data() + (size_t)s * 320;
     if (rem) memcpy(rem + (size_t)s * 7, p, 56);
     if (bnd) memcpy(bnd + (size_t)s * 7, p + 7, 56);
     if (dust) dust[s] = p[14];
     if (spec) memcpy(spec + (size_t)s * 300, p + 16, 2400);
+    if (hpl) hpl[s] = (int32_t)p[15];
   }
 }
 
@@ -385,21 +396,22 @@ int rtb200_point_device(rtb200_ctx* h, int nWave, const double* wavelength, cons
                         double coefSpectrum, const double* aDust, int dustApproximation, int maxPixelLevel, int32_t nsrc,
                         const int32_t* srcLeaf, const int32_t* srcWeight, double* rates_device, void* stream,
                         double* ndotRemaining, double* ndotBoundary, double* ndotDust, double* ndotSpectrum,
-                        int64_t* nseg) {
+                        int32_t* highestPixelLevel, int64_t* nseg) {
   if (!h || !rates_device) return RTB200_ERR_ARG;
   PointInputs in = make_point_inputs(nWave, wavelength, lum, metallicity, coefSpectrum, aDust, dustApproximation,
                                      maxPixelLevel, nsrc, srcLeaf, srcWeight);
-  const bool wantDiag = ndotRemaining || ndotBoundary || ndotDust || ndotSpectrum;
+  const bool wantDiag = ndotRemaining || ndotBoundary || ndotDust || ndotSpectrum || highestPixelLevel;
   std::vector<double> diag(wantDiag ? (size_t)std::max(nsrc, 0) * 320 : 0);
   int st = point_solve(h->c, in, rates_device, wantDiag ? diag.data() : nullptr, nseg, nullptr, 0, nullptr, nullptr,
                        (cudaStream_t)stream);
   if (st) return st;
-  if (wantDiag) split_diag(diag, nsrc, ndotRemaining, ndotBoundary, ndotDust, ndotSpectrum);
+  if (wantDiag) split_diag(diag, nsrc, ndotRemaining, ndotBoundary, ndotDust, ndotSpectrum, highestPixelLevel);
   return RTB200_OK;
 }
 
 static int point_host_call(Context& c, const PointInputs& in, double* const k[6], double* rem, double* bnd, double* dust,
-                           double* spec, int64_t* nseg, long long* trace, long long traceCap, long long* traceLen) {
+                           double* spec, int32_t* hpl, int64_t* nseg, long long* trace, long long traceCap,
+                           long long* traceLen) {
   for (int i = 0; i < 6; i++)
     if (!k[i]) return RTB200_ERR_ARG;
   if (c.nleaf == 0) return RTB200_ERR_ARG;
@@ -412,7 +424,7 @@ static int point_host_call(Context& c, const PointInputs& in, double* const k[6]
   if (st) return st;
   for (int i = 0; i < 6; i++) RTB_CUDA(cudaMemcpyAsync(k[i], c.dRates + (size_t)i * c.nleaf, nb, cudaMemcpyDeviceToHost, c.stream));
   RTB_CUDA(cudaStreamSynchronize(c.stream));
-  split_diag(diag, in.nsrc, rem, bnd, dust, spec);
+  split_diag(diag, in.nsrc, rem, bnd, dust, spec, hpl);
   return RTB200_OK;
 }
 
@@ -420,12 +432,13 @@ int rtb200_point(rtb200_ctx* h, int nWave, const double* wavelength, const doubl
                  double coefSpectrum, const double* aDust, int dustApproximation, int maxPixelLevel, int32_t nsrc,
                  const int32_t* srcLeaf, const int32_t* srcWeight, double* krate24, double* krate25, double* krate26,
                  double* crate24, double* crate25, double* crate26, double* ndotRemaining, double* ndotBoundary,
-                 double* ndotDust, double* ndotSpectrum, int64_t* nseg) {
+                 double* ndotDust, double* ndotSpectrum, int32_t* highestPixelLevel, int64_t* nseg) {
   if (!h) return RTB200_ERR_ARG;
   PointInputs in = make_point_inputs(nWave, wavelength, lum, metallicity, coefSpectrum, aDust, dustApproximation,
                                      maxPixelLevel, nsrc, srcLeaf, srcWeight);
   double* k[6] = {krate24, krate25, krate26, crate24, crate25, crate26};
-  return point_host_call(h->c, in, k, ndotRemaining, ndotBoundary, ndotDust, ndotSpectrum, nseg, nullptr, 0, nullptr);
+  return point_host_call(h->c, in, k, ndotRemaining, ndotBoundary, ndotDust, ndotSpectrum, highestPixelLevel, nseg,
+                         nullptr, 0, nullptr);
 }
 
 int rtb200_point_trace(rtb200_ctx* h, int nWave, const double* wavelength, const double* lum, const double* metallicity,
@@ -438,7 +451,7 @@ int rtb200_point_trace(rtb200_ctx* h, int nWave, const double* wavelength, const
   double* k[6];
   for (int i = 0; i < 6; i++) k[i] = rates6 + (size_t)i * h->c.nleaf;
   long long tl = 0;
-  int st = point_host_call(h->c, in, k, nullptr, nullptr, nullptr, nullptr, nseg, (long long*)trace, traceCap, &tl);
+  int st = point_host_call(h->c, in, k, nullptr, nullptr, nullptr, nullptr, nullptr, nseg, (long long*)trace, traceCap, &tl);
   *traceLen = tl;
   return st;
 }
@@ -532,6 +545,26 @@ int rtb200_neighbours(rtb200_ctx* h, int nAngularLevel, int64_t iray, int32_t* n
   if (d.status) return d.status;
   RTB_CUDA(cudaSetDevice(h->c.device));
   return amr_neighbours(h->c, d, nb);
+}
+
+int rtb200_debug_portable_math(rtb200_ctx* h, int64_t n, const double* x, double* expOut, double* logOut) {
+  if (!h || n < 0 || !x || !expOut || !logOut) return RTB200_ERR_ARG;
+  if (n == 0) return RTB200_OK;
+  Context& c = h->c;
+  RTB_CUDA(cudaSetDevice(c.device));
+  double* d = nullptr;
+  RTB_CUDA(cudaMalloc((void**)&d, (size_t)3 * n * sizeof(double)));
+  cudaError_t e = cudaMemcpyAsync(d, x, (size_t)n * 8, cudaMemcpyHostToDevice, c.stream);
+  if (e == cudaSuccess) {
+    portable_math_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 4096), 256, 0, c.stream>>>(d, n, d + n, d + 2 * n);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(expOut, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost, c.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(logOut, d + 2 * n, (size_t)n * 8, cudaMemcpyDeviceToHost, c.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+  cudaFree(d);
+  RTB_CUDA(e);
+  return RTB200_OK;
 }
 
 int rtb200_last_stats(rtb200_ctx* h, double* ms, double* sweepMs, int64_t* launches, int64_t* sweepLaunches,

@@ -41,7 +41,7 @@ constexpr int kPlane = 11 * 11 * 11;
 // 25), slot 2r+1 = its energy table, slots 6,7 unused: a node is one 64-byte record, and the (number, energy) pair of
 // a reaction is one 16-byte load
 constexpr int kSlots = 8;
-constexpr int kDiagStride = 320;  // per source: remaining[7], boundary[7], dust, pad, spectrum[300]
+constexpr int kDiagStride = 320;  // per source: remaining[7], boundary[7], dust, highestPixelLevel, spectrum[300]
 constexpr int kMaxPixelLevel = 8;
 
 __device__ __forceinline__ double M(double a, double b) { return __dmul_rn(a, b); }
@@ -656,6 +656,12 @@ __global__ void __launch_bounds__(128, MINB) point_march_kernel(const __grid_con
   // warp-aggregated segment count
   for (int o = 16; o; o >>= 1) mySegs += __shfl_down_sync(0xffffffffu, mySegs, o);
   if ((threadIdx.x & 31) == 0 && mySegs) atomicAdd(P.nseg, mySegs);
+
+  // highestPixelLevel (equiSources.f90:3316): the deepest pixel level a split of this source has opened.  Slot 15 of
+  // the diagnostics holds it as a double; the bit patterns of non-negative doubles order like integers.
+  if (!last && have0 && strategy == 2)
+    atomicMax(reinterpret_cast<unsigned long long*>(diag + 15),
+              (unsigned long long)__double_as_longlong((double)(pixelLevel + 1)));
 
   if (!last && ipix0 < npix) {
     RayState out;

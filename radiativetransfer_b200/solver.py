@@ -125,7 +125,8 @@ class Transport:
         """Host-buffer call.  `rates` [6, nleaf] (krate24, krate25, krate26, crate24, crate25, crate26) is accumulated
         like the reference's cell fields (zeros when None; `inplace=True` accumulates into the caller's C-contiguous
         fp64 array itself, e.g. a view of pinned memory, instead of a copy).  Returns dict(rates, ndot_remaining[nsrc,7],
-        ndot_boundary[nsrc,7], ndot_dust[nsrc], ndot_spectrum[nsrc,300], nseg[, trace, trace_key])."""
+        ndot_boundary[nsrc,7], ndot_dust[nsrc], ndot_spectrum[nsrc,300], highest_pixel_level[nsrc], nseg[, trace,
+        trace_key])."""
         keep, sa = self._spectra_args(spectra)
         leaf = np.ascontiguousarray(src_leaf, dtype=np.int32); wt = np.ascontiguousarray(src_weight, dtype=np.int32)
         if leaf.size != wt.size:
@@ -155,11 +156,13 @@ class Transport:
             out.update(trace=tr[order, 0].copy(), trace_key=tr[order, 1].copy())
         else:
             rem = np.zeros((ns, 7)); bnd = np.zeros((ns, 7)); dust = np.zeros(ns); spec = np.zeros((ns, 300))
+            hpl = np.zeros(ns, dtype=np.int32)
             st = self.L.rtb200_point(self.h, *sa, int(dust_approximation), int(max_pixel_level), ns, _ptr(leaf),
                                      _ptr(wt), *[_ptr(R[i]) for i in range(6)], _ptr(rem), _ptr(bnd), _ptr(dust),
-                                     _ptr(spec), C.byref(nseg))
+                                     _ptr(spec), _ptr(hpl), C.byref(nseg))
             _lib.check(st, "rtb200_point")
-            out.update(ndot_remaining=rem, ndot_boundary=bnd, ndot_dust=dust, ndot_spectrum=spec)
+            out.update(ndot_remaining=rem, ndot_boundary=bnd, ndot_dust=dust, ndot_spectrum=spec,
+                       highest_pixel_level=hpl)
         out["nseg"] = nseg.value
         return out
 
@@ -171,15 +174,17 @@ class Transport:
         leaf = np.ascontiguousarray(src_leaf, dtype=np.int32); wt = np.ascontiguousarray(src_weight, dtype=np.int32)
         ns = int(leaf.size)
         nseg = C.c_int64(0)
-        rem = bnd = dust = spec = None
+        rem = bnd = dust = spec = hpl = None
         if diagnostics:
             rem = np.zeros((ns, 7)); bnd = np.zeros((ns, 7)); dust = np.zeros(ns); spec = np.zeros((ns, 300))
+            hpl = np.zeros(ns, dtype=np.int32)
         st = self.L.rtb200_point_device(self.h, *sa, int(dust_approximation), int(max_pixel_level), ns, _ptr(leaf),
                                         _ptr(wt), C.c_void_p(int(rates_ptr)), C.c_void_p(int(stream)), _ptr(rem),
-                                        _ptr(bnd), _ptr(dust), _ptr(spec), C.byref(nseg))
+                                        _ptr(bnd), _ptr(dust), _ptr(spec), _ptr(hpl), C.byref(nseg))
         _lib.check(st, "rtb200_point_device")
         if diagnostics:
-            return nseg.value, dict(ndot_remaining=rem, ndot_boundary=bnd, ndot_dust=dust, ndot_spectrum=spec)
+            return nseg.value, dict(ndot_remaining=rem, ndot_boundary=bnd, ndot_dust=dust, ndot_spectrum=spec,
+                                    highest_pixel_level=hpl)
         return nseg.value
 
     def point_tables(self, spectra, i_metal, coef_metal):

@@ -2,9 +2,9 @@
 
 Grids are produced directly in the reference's flattened leaf order (`writeCell` pre-order,
 equiSources.f90:4044-4079): base cells x outer / y / z inner, the 8 children of a refined cell x, y, z.
-The UV-background amplitudes and group cross-sections follow the reference formulas
-(equiSources.f90:198-255, :4985-5043; uvbBetaTable.f90) evaluated with numpy -- they are workload parameters
-fed identically to the GPU path and to the CPU oracle, not part of the parity claim.
+The UV-background amplitudes and group cross-sections come from the library's host-side restatement of the
+reference set-up (rtb200_uvb_background; checked against the oracle and an independent numpy evaluation in
+tests/test_uvb_tables.py).
 """
 import numpy as np
 
@@ -39,74 +39,23 @@ def _sigmas(nu):
     return s24, s25, s26
 
 
-def _power_index(u1, a1, u2, a2, nug, nugplus, bound):
-    """equiSources.f90:4985-5043: slope of the single power law matching the two-component band integral."""
-    tot = u1 + u2
-    r = nug / nugplus
+def uvb_background(redshift=3.0, uvb_coefficient=1.0, nfreq=400, freqdel=None):
+    """uvb[3], beta[3][3] = [group][beta24, beta26, beta25], ksi24[3], ksi25[1], ksi26[2], alpha[3], table[3][19] from the
+    library's host-side restatement of the reference set-up (rtb200_uvb_background: equiSources.f90:198-246,
+    :4985-5043, uvbBetaTable.f90:31-296).  nfreq / freqdel default to the reference's nfbins = 400 and
+    frequencyBinWidth = 0.02 (a single-precision literal, definitionsModule.f90:239-241)."""
+    import ctypes as C
 
-    def band(u, a):
-        return u / (a - 1.0) * (1.0 - r ** (a - 1.0)) if bound else u / (a - 1.0)
-
-    target = band(u1, a1) + band(u2, a2)
-    t1, t2 = 1.1 * a1 - 0.1 * a2, 1.1 * a2 - 0.1 * a1
-    f1, f2 = band(tot, t1) - target, band(tot, t2) - target
-    told, t = t1, t2
-    while abs(t - told) >= 1e-8:
-        told = t
-        t = (t1 * abs(f2) + t2 * abs(f1)) / (abs(f1) + abs(f2))
-        f = band(tot, t) - target
-        if (f > 0 > f1) or (f < 0 < f1):
-            t2, f2 = t, f
-        else:
-            t1, f1 = t, f
-    return tot, t
-
-
-def uvb_background(redshift=3.0, uvb_coefficient=1.0, nfreq=400, freqdel=0.02):
-    """uvb[3], beta[3][3] = [group][beta24, beta26, beta25], ksi24[3], ksi25[1], ksi26[2], alpha[3]."""
-    z = redshift
-    stellar99 = 1.0 / (1.0 + (7.0 / (1.0 + z)) ** 4) * np.exp(-((z / 4.0) ** 3))
-    pascal02 = 0.0188 * np.exp(-((z - 0.5) ** 2) / (1.0 + 0.0625 * (z + 2.09) ** 2.075)) * (1.0 + z) ** 3.35
-    step = 0.5 * (np.tanh((z - 4.2) * 1.5) + 1.0)
-    stellar02 = (1.0 - step) * stellar99 + step * pascal02
-    quasar02 = 10.0 / (1.0 + (7.0 / (1.0 + z)) ** 4) * np.exp(-((z / 2.5) ** 3))
-    gaussian = np.exp(-(((z - 4.5) / 2.0) ** 2)) * 0.3
-    newQ = gaussian * stellar02 + (1.0 - gaussian) * quasar02
-    newS = (1.0 - gaussian) * stellar02 + gaussian * quasar02
-    step = 0.5 * (np.tanh((z - 14.0) * 0.5) + 1.0)
-    newS = (1.0 - step) * newS
-    aQ, aS = 1.8, 5.0
-    s1 = newS * 1e-21 * uvb_coefficient
-    s2 = s1 * (NU2 / NU1) ** (-aS)
-    s3 = s2 * (NU3 / NU2) ** (-aS)
-    q1 = newQ * 1e-21 * uvb_coefficient
-    q2 = q1 * (NU2 / NU1) ** (-aQ)
-    q3 = q2 * (NU3 / NU2) ** (-aQ)
-    u1, al1 = _power_index(s1, aS, q1, aQ, NU1, NU2, True)
-    u2, al2 = _power_index(s2, aS, q2, aQ, NU2, NU3, True)
-    u3, al3 = _power_index(s3, aS, q3, aQ, NU3, NU3, False)
-    alpha = [al1, al2, al3]
-    nu = 10.0 ** (np.arange(nfreq) * freqdel)
-    s24, s25, s26 = _sigmas(nu)
-    dnu = np.diff(nu, prepend=nu[0])
-    bands = [(NU1, NU2), (NU2, NU3), (NU3, np.inf)]
-    thr = [NU1, NU2, NU3]
-    beta = np.zeros((3, 3))
-    ksi = np.zeros((3, 3))  # [group][24, 26, 25]
-    for g, (lo, hi) in enumerate(bands):
-        m = (nu >= lo) & (nu <= hi)
-        m[0] = False
-        dt = (nu[m] / thr[g]) ** (-alpha[g]) * dnu[m]
-        doe = dt * EV_TO_HZ / (nu[m] * EV_TO_ERG)
-        for c, sg in enumerate((s24, s26, s25)):
-            beta[g, c] = np.sum(dt * sg[m])
-            ksi[g, c] = np.sum(doe * sg[m])
-    shape = [(1.0 - (NU2 / NU1) ** (1.0 - al1)) / (al1 - 1.0), (1.0 - (NU3 / NU2) ** (1.0 - al2)) / (al2 - 1.0),
-             1.0 / (al3 - 1.0)]
-    for g in range(3):
-        beta[g] /= shape[g] * thr[g]
-    return dict(uvb=np.array([u1, u2, u3]), beta=beta, alpha=np.array(alpha),
-                ksi24=ksi[:, 0].copy(), ksi25=np.array([ksi[2, 2]]), ksi26=np.array([ksi[1, 1], ksi[2, 1]]))
+    from . import _lib
+    if freqdel is None:
+        freqdel = float(_f(0.02))
+    uvb, alpha, beta = np.zeros(3), np.zeros(3), np.zeros((3, 3))
+    k24, k25, k26, tab = np.zeros(3), np.zeros(1), np.zeros(2), np.zeros((3, 19))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    st = _lib.lib().rtb200_uvb_background(float(redshift), float(uvb_coefficient), int(nfreq), float(freqdel), p(uvb),
+                                          p(alpha), p(beta), p(k24), p(k25), p(k26), p(tab))
+    _lib.check(st, "rtb200_uvb_background")
+    return dict(uvb=uvb, beta=beta, alpha=alpha, ksi24=k24, ksi25=k25, ksi26=k26, table=tab)
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -109,8 +109,8 @@ def test_point_entry_points_reject_bad_arguments_without_a_device(build_product)
     L = _lib.lib()
     n = C.c_int64(0)
     assert L.rtb200_point(None, 0, None, None, None, 0.0, None, 0, 6, 0, None, None, None, None, None, None, None, None,
-                          None, None, None, None, C.byref(n)) == 12          # RTB200_ERR_ARG
+                          None, None, None, None, None, C.byref(n)) == 12    # RTB200_ERR_ARG
     assert L.rtb200_point_device(None, 0, None, None, None, 0.0, None, 0, 6, 0, None, None, None, None, None, None,
-                                 None, None, C.byref(n)) == 12
+                                 None, None, None, C.byref(n)) == 12
     assert L.rtb200_point_tables(None, 0, None, None, None, 0.0, None, 1, 0.0, None) == 12
     assert b"idepth" in L.rtb200_status_string(11)
