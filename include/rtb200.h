@@ -62,8 +62,8 @@ int rtb200_set_math(rtb200_ctx* ctx, int math_mode);
  *                  0/1/2 = 2/3/4 blocks per SM, 2), "expv" (1 = table exponential), "lockstep" (one launch per layer
  *                  for all tasks, 1), "dirs_per_task" (0 = chosen from a wave model), "transpose_z" (z-major copy for
  *                  the zones sweeping along the contiguous axis, 1), "pdl" (programmatic dependent launch of layer
- *                  l+1 on layer l, also used by the nested-grid waves, 1), "march"/"march_debug" (experimental
- *                  persistent kernel, 0), "l2_mb"
+ *                  l+1 on layer l, also used by the nested-grid waves, 1), "march" (experimental persistent kernel, 0; its "march_debug" switches
+ *                  exist only with RTB200_EXPERIMENTAL set in the environment), "l2_mb"
  *   nested grids   "force_amr" (general octree path on a uniform grid), "amr_batch" (directions per batch, 0 = as many
  *                  as fit in memory)
  *   point sources  "point_batch" (sources per batch), "point_min_blocks" (register cap of the march kernel, 5),
@@ -78,13 +78,16 @@ int rtb200_device_error(rtb200_ctx* ctx);
 /* Replaces the pointer-linked octree (definitionsModule.f90:163-182; built at equiSources.f90:1870-1974) with
  * structure-of-arrays device buffers plus a linear octree rebuilt from `level` alone, exactly as
  * readCellArray.f90:154-187 does.  nx = ny = nz (equiSources.f90:427-436 requires a cubic level-1 grid).
- * rho and abun2 may be NULL when only the diffuse path is used.  Arrays are copied. */
+ * HeI / HeII may be NULL (taken as zero: a hydrogen-only grid); rho and abun2 may be NULL when only the diffuse path is
+ * used -- rtb200_point*, rtb200_chemistry_device and rtb200_compute_mass then return RTB200_ERR_ARG.  Arrays are copied. */
 int rtb200_grid_set(rtb200_ctx* ctx, int nx, int64_t nleaf, const int8_t* level, const double* HI,
                     const double* HeI, const double* HeII, const double* rho, const double* abun2,
                     double physicalBoxSize);
 
 /* New absorber densities after a chemistry step (solveRateEquations writes back HI, HeI, HeII only:
- * equiSources.f90:3671-3673).  NULL keeps the current array. */
+ * equiSources.f90:3671-3673).  NULL keeps the current array.  Ordering: the call first waits for ALL work queued on the
+ * context's device (including what *_device calls put on the caller's streams), then copies, then returns when the
+ * copies are complete -- work issued afterwards on any stream sees the new arrays. */
 int rtb200_grid_update_species(rtb200_ctx* ctx, const double* HI, const double* HeI, const double* HeII);
 
 /* Diffuse (UV background) sweep: replaces equiSources.f90:1372-1808 (computeOpacities :4956, the loop over

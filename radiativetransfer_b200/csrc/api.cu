@@ -213,19 +213,26 @@ int rtb200_create(int device, rtb200_ctx** out) {
   if (!h) return RTB200_ERR_NOMEM;
   Context& c = h->c;
   c.device = device;
-  cudaDeviceProp prop;
-  RTB_CUDA(cudaGetDeviceProperties(&prop, device));
-  c.smCount = prop.multiProcessorCount;
-  c.l2Bytes = (size_t)prop.l2CacheSize;
-  if (c.l2Bytes) c.tune.l2BudgetMB = 0.75 * (double)c.l2Bytes / 1048576.0;
-  RTB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-  RTB_CUDA(cudaEventCreate(&c.evStart));
-  RTB_CUDA(cudaEventCreate(&c.evStop));
-  RTB_CUDA(cudaEventCreate(&c.evSweep0));
-  RTB_CUDA(cudaEventCreate(&c.evSweep1));
-  RTB_CUDA(cudaEventCreateWithFlags(&c.evFork, cudaEventDisableTiming));
-  RTB_CUDA(cudaMalloc((void**)&c.dErr, 64));
-  RTB_CUDA(cudaMemset(c.dErr, 0, 64));
+  auto init = [&]() -> int {
+    cudaDeviceProp prop;
+    RTB_CUDA(cudaGetDeviceProperties(&prop, device));
+    c.smCount = prop.multiProcessorCount;
+    c.l2Bytes = (size_t)prop.l2CacheSize;
+    if (c.l2Bytes) c.tune.l2BudgetMB = 0.75 * (double)c.l2Bytes / 1048576.0;
+    RTB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    RTB_CUDA(cudaEventCreate(&c.evStart));
+    RTB_CUDA(cudaEventCreate(&c.evStop));
+    RTB_CUDA(cudaEventCreate(&c.evSweep0));
+    RTB_CUDA(cudaEventCreate(&c.evSweep1));
+    RTB_CUDA(cudaEventCreateWithFlags(&c.evFork, cudaEventDisableTiming));
+    RTB_CUDA(cudaMalloc((void**)&c.dErr, 64));
+    RTB_CUDA(cudaMemset(c.dErr, 0, 64));
+    return RTB200_OK;
+  };
+  if (int st = init()) {   // nothing of a half-built context survives
+    rtb200_destroy(h);
+    return st;
+  }
   if (const char* v = getenv("RTB200_DENSE")) c.tune.minBlocks = atoi(v);
   if (const char* v = getenv("RTB200_SLOTS")) c.tune.slots = atoi(v);
   if (const char* v = getenv("RTB200_GRAPH")) c.tune.useGraph = atoi(v);
@@ -279,7 +286,11 @@ int rtb200_set_tuning(rtb200_ctx* h, const char* key, double value) {
   else if (k == "transpose_z") c.tune.transposeZ = (int)value;
   else if (k == "pdl") c.tune.pdl = (int)value;
   else if (k == "dirs_per_task") c.tune.dirsPerTask = (int)value;
-  else if (k == "march_debug") c.tune.marchDebug = (int)value;
+  else if (k == "march_debug") {
+    // experiments only (mode 1 skips the neighbour polling and gives WRONG results): not reachable from product code
+    if (!getenv("RTB200_EXPERIMENTAL")) return RTB200_ERR_ARG;
+    c.tune.marchDebug = (int)value;
+  }
   else if (k == "portable_math") c.tune.portableMath = (int)value;
   else if (k == "point_batch") c.tune.pointBatch = (int)value;
   else if (k == "point_min_blocks") c.tune.pointMinBlocks = (int)value;
@@ -313,8 +324,10 @@ int rtb200_grid_set(rtb200_ctx* h, int nx, int64_t nleaf, const int8_t* level, c
   if (!st) st = upload((void**)&c.dHI, HI, nb, s);
   if (!st) st = upload((void**)&c.dHeI, HeI, nb, s);
   if (!st) st = upload((void**)&c.dHeII, HeII, nb, s);
-  if (!st) st = upload((void**)&c.dRho, rho, nb, s);
-  if (!st) st = upload((void**)&c.dAbun2, abun2, nb, s);
+  // rho / abun2 are optional (diffuse-only use): without them the point-source and chemistry entry points return
+  // RTB200_ERR_ARG instead of working on zero-filled arrays
+  if (!st && rho) st = upload((void**)&c.dRho, rho, nb, s);
+  if (!st && abun2) st = upload((void**)&c.dAbun2, abun2, nb, s);
   if (!st) st = upload((void**)&c.dKappa, nullptr, 3 * nb, s);
   if (!st) st = upload((void**)&c.dJ, nullptr, 3 * nb, s);
   if (!st) {
@@ -332,6 +345,9 @@ int rtb200_grid_update_species(rtb200_ctx* h, const double* HI, const double* He
   if (!h || h->c.nleaf == 0) return RTB200_ERR_ARG;
   Context& c = h->c;
   RTB_CUDA(cudaSetDevice(c.device));
+  // Work queued by the *_device entry points on the caller's streams (sweeps, chemistry, ray casting) reads and
+  // writes the species arrays: it has to be complete before they are overwritten (as rtb200_grid_get_species does).
+  RTB_CUDA(cudaDeviceSynchronize());
   const size_t nb = (size_t)c.nleaf * sizeof(double);
   if (HI) RTB_CUDA(cudaMemcpyAsync(c.dHI, HI, nb, cudaMemcpyHostToDevice, c.stream));
   if (HeI) RTB_CUDA(cudaMemcpyAsync(c.dHeI, HeI, nb, cudaMemcpyHostToDevice, c.stream));

@@ -56,6 +56,8 @@ def count_base_cells(level):
     lmax = int(level.max()) if level.size else 0
     if level.size and int(level.min()) < 0:
         raise ValueError("error in levels")
+    _check_volume_range(lmax, level.size)
+    _check_preorder(level)
     w = np.left_shift(np.int64(1), 3 * (lmax - level))   # volume of each leaf in finest-cell units
     full = np.int64(1) << (3 * lmax)
     c = np.cumsum(w)
@@ -69,10 +71,45 @@ def count_base_cells(level):
     return nbase
 
 
+def _check_volume_range(lmax, nleaf):
+    """leaf volumes are counted in int64 units of 8^-lmax and summed over all leaves: 3*lmax + log2(nleaf) must stay
+    below 63 bits (e.g. 128^3 base cells allow 13 levels; the reference tools size for levels 0..15)"""
+    if 3 * lmax + max(int(nleaf), 1).bit_length() >= 63:
+        raise ValueError(f"levels up to {lmax} with {nleaf} leaves overflow the 64-bit volume count")
+
+
+def _check_preorder(level):
+    """pre-order nesting of a leaf-level sequence (the walk of readCellArray.f90:154-187): after a leaf of level l the
+    walk stands at a sibling slot of some level <= l; the next leaf can open deeper levels only by refining that slot"""
+    lv = np.asarray(level, dtype=np.int64)
+    if lv.size == 0:
+        return
+    # remaining[k] = children still missing at level k of the current path (k >= 1); a vectorised check is not possible
+    # for the nesting itself, but the necessary condition below is cheap and the exact walk is only run when it holds
+    remaining = [0] * (int(lv.max()) + 2)
+    depth = 0
+    for l in lv.tolist():
+        if l < depth and any(remaining[k] for k in range(l + 1, depth + 1)):
+            raise ValueError("error in levels: a refined cell is closed before its 8 children are complete")
+        while depth < l:            # refine the current slot down to level l
+            depth += 1
+            remaining[depth] = 8
+        if l > 0:
+            remaining[l] -= 1
+        depth = l
+        while depth > 0 and remaining[depth] == 0:   # a completed octet closes its parent slot
+            depth -= 1
+            if depth > 0:
+                remaining[depth] -= 1
+    if depth != 0:
+        raise ValueError("error in levels: the last refined cell is incomplete")
+
+
 def leaf_centres(nx, level):
     """cell centres in box units [0,1] per leaf, as computeCellCoordinates (hdf42bin.f90:225-269) assigns them"""
     level = np.asarray(level, dtype=np.int64)
     lmax = int(level.max()) if level.size else 0
+    _check_volume_range(lmax, level.size)
     w = np.left_shift(np.int64(1), 3 * (lmax - level))
     start = np.cumsum(w) - w                       # Morton-like position of the leaf in finest-cell units
     full = np.int64(1) << (3 * lmax)

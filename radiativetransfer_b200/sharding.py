@@ -19,7 +19,7 @@ def direction_costs(n_angular_level=3, nx=32):
     for r in range(nrays):
         zone[r] = solver.direction(n_angular_level, r)[0]
         p = solver.patterns(n_angular_level, r, nx)
-        cost[r] = np.sum(1 + (p[:, 10] != 0) + (p[:, 11] != 0))
+        cost[r] = np.sum(1 + (p[:, 5] != 0) + (p[:, 8] != 0))     # xy + active xz (len != 0) + active yz (len != 0)
     return zone, cost
 
 

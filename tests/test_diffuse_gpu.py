@@ -202,3 +202,69 @@ def test_bad_arguments(rt, engine, uvbg):
     _set(engine, g)
     with pytest.raises(rt.RTB200Error):
         engine.diffuse(uvbg["uvb"], uvbg["beta"], rays=np.array([192], dtype=np.int32))
+
+
+def _oracle_threads(nleaf, want):
+    """host threads for the threaded oracle: every thread sweeps a private copy of the octree (~260 B per leaf)"""
+    import os
+    import psutil
+    return int(max(1, min(want, os.cpu_count() or 1, (0.5 * psutil.virtual_memory().available) // (260.0 * nleaf))))
+
+
+def test_config2_full_128cube_192dir_vs_oracle(rt, engine, oracle, uvbg):
+    """BASELINE config 2 at its full size against the oracle: 128^3 uniform grid (seed 1, the bench workload's grid),
+    all 192 directions, both arithmetic modes.  The oracle runs on all host threads (each thread its own directions on a
+    private octree; ~7.4e8 segment updates)."""
+    n = 128
+    g = W.uniform_grid(n, seed=1)
+    og = oracle.OracleGrid(n, g["level"], g["HI"], g["HeI"], g["HeII"], box_size=g["box_size"])
+    o = og.diffuse_mt(uvbg["uvb"], uvbg["beta"], np.arange(192, dtype=np.int32), nthreads=_oracle_threads(n ** 3, 32))
+    assert o["status"] == 0
+    _set(engine, g)
+    for mode in (rt.MATH_FAST, rt.MATH_FAITHFUL):
+        engine.set_math(mode)
+        J, nseg = engine.diffuse(uvbg["uvb"], uvbg["beta"])
+        assert nseg == o["nseg"]
+        err = rel_err(J, o["J"])
+        print(f"128^3 x 192 vs oracle, math mode {mode}: rel L-inf {err:.3e}")
+        assert err < TOL
+    # the photo-rates that consume J (equiSources.f90:3546-3553), from the oracle's J with numpy
+    import torch
+    engine.set_math(rt.MATH_FAST)
+    Jd = torch.zeros(3, n ** 3, dtype=torch.float64, device="cuda")
+    K = torch.zeros(3, n ** 3, dtype=torch.float64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    engine.diffuse_device(uvbg["uvb"], uvbg["beta"], Jd.data_ptr(), stream=s)
+    engine.diffuse_rates_device(Jd.data_ptr(), uvbg["ksi24"], uvbg["ksi25"], uvbg["ksi26"], K[0].data_ptr(),
+                                K[1].data_ptr(), K[2].data_ptr(), stream=s)
+    torch.cuda.synchronize()
+    fourpi = 4.0 * float(np.float32(3.141592654))
+    Jo = o["J"]
+    k24 = fourpi * Jo[0] * uvbg["ksi24"][0] + fourpi * Jo[1] * uvbg["ksi24"][1] + fourpi * Jo[2] * uvbg["ksi24"][2]
+    k25 = fourpi * Jo[2] * uvbg["ksi25"][0]
+    k26 = fourpi * Jo[1] * uvbg["ksi26"][0] + fourpi * Jo[2] * uvbg["ksi26"][1]
+    Kh = K.cpu().numpy()
+    assert rel_err(Kh[0], k24) < TOL and rel_err(Kh[1], k25) < TOL and rel_err(Kh[2], k26) < TOL
+
+
+def test_headline_256cube_direction_subset_vs_oracle(rt, engine, oracle, uvbg):
+    """The benchmarked configuration (256^3 uniform, seed 1 = bench.py's grid): a subset of directions that covers all
+    three sweep axes and both signs, swept by the oracle and by the GPU (`rays=`), FAST (the benchmarked mode) and
+    FAITHFUL.  Each direction is ~3.1e7 segment updates on the oracle."""
+    n = 256
+    g = W.uniform_grid(n, seed=1)
+    rays = np.array([0, 37, 74, 111, 148, 185, 30, 67], dtype=np.int32)
+    zones = {rt.direction(3, int(r))[0] for r in rays}
+    assert len(zones) >= 6
+    og = oracle.OracleGrid(n, g["level"], g["HI"], g["HeI"], g["HeII"], box_size=g["box_size"])
+    o = og.diffuse_mt(uvbg["uvb"], uvbg["beta"], rays, nthreads=_oracle_threads(n ** 3, rays.size))
+    assert o["status"] == 0
+    del og
+    _set(engine, g)
+    for mode in (rt.MATH_FAST, rt.MATH_FAITHFUL):
+        engine.set_math(mode)
+        J, nseg = engine.diffuse(uvbg["uvb"], uvbg["beta"], rays=rays)
+        assert nseg == o["nseg"]
+        err = rel_err(J, o["J"])
+        print(f"256^3 x {rays.size} directions vs oracle, math mode {mode}: rel L-inf {err:.3e}")
+        assert err < TOL

@@ -297,3 +297,119 @@ def test_edge_cases(rt, engine, spectra):
     _set(engine, g1)
     r = engine.point(spectra, [0], [4])
     assert r["nseg"] == 12 and np.isclose(r["ndot_boundary"][0, -1], 4.0, rtol=1e-12)   # 12 base rays, one cell each
+
+
+def _floor_stats(r, o, T):
+    """strict per-cell relative error against the libm oracle and the share of cells that need the conditioning floor
+    2e-13 * R_r(0) on top of 1e-9 (the noise of exp(interpolated log) that R(d) - R(d+tau) exposes)"""
+    worst, need, cells = 0.0, 0, 0
+    for i, t in zip(range(6), (0, 2, 1, 3, 5, 4)):
+        m = o["rates"][i] != 0
+        d = np.abs(r["rates"][i][m] - o["rates"][i][m])
+        strict = d / np.abs(o["rates"][i][m])
+        assert np.all(d <= TOL * np.abs(o["rates"][i][m]) + 2e-13 * T[t, 0]), (i, float(strict.max()))
+        worst = max(worst, float(strict.max()) if strict.size else 0.0)
+        need += int(np.sum(strict > TOL)); cells += int(m.sum())
+    return worst, need, cells
+
+
+def test_config1_exact_32cube_h_only(rt, engine, oracle, spectra):
+    """BASELINE config 1 as SURVEY.md 8d states it: 32^3, one level, 100 kpc box, HI log-uniform with tau_cell(nu1) in
+    [1e-3, 1], HeI = HeII = 0, no dust, one source of weight 1 at the centre of leaf (17,17,17), maxPixelLevel 6,
+    numpy default_rng(20240601).  Portable math: bit-identical deposits.  libm oracle: 1e-9 + the floor, with the share
+    of cells that need the floor and the worst strict error reported."""
+    n = 32
+    g = W.uniform_grid(n, seed=20240601, box_kpc=100.0, tau_lo=1e-3, tau_hi=1.0, beta24=S24, helium=False)
+    assert not g["HeI"].any() and not g["HeII"].any()
+    _set(engine, g)
+    leaf = (16 * n + 16) * n + 16                      # (17,17,17), 1-based
+    og = _ograd(oracle, g)
+    oracle.set_portable_math(True)
+    try:
+        op = og.point(spectra, [leaf], [1])
+    finally:
+        oracle.set_portable_math(False)
+    ol = og.point(spectra, [leaf], [1])
+    assert op["status"] == 0 and ol["status"] == 0
+    r = engine.point(spectra, [leaf], [1])             # FAITHFUL + portable exp/log
+    assert r["nseg"] == op["nseg"] == ol["nseg"]
+    assert 1.5e5 < r["nseg"] < 3e5                     # SURVEY 8(a12): ~2.1e5 segment updates
+    for i in (0, 3):
+        assert _cell_err(r["rates"][i], op["rates"][i]) < 1e-12
+    assert np.all(r["rates"][[1, 2, 4, 5]] == 0) and np.all(ol["rates"][[1, 2, 4, 5]] == 0)   # H only
+    assert np.array_equal(r["highest_pixel_level"], op["highest_pixel_level"])
+    assert rel_err(r["ndot_remaining"], op["ndot_remaining"], floor=1e-300) < 1e-12
+    assert rel_err(r["ndot_boundary"], op["ndot_boundary"], floor=1e-300) < 1e-12
+    T = engine.point_tables(spectra, *_bracket(spectra, g["abun2"][leaf])).reshape(6, -1)
+    stats = {}
+    for name, mode in (("faithful", rt.MATH_FAITHFUL), ("fast", rt.MATH_FAST)):
+        engine.set_math(mode)
+        rr = engine.point(spectra, [leaf], [1])
+        assert rr["nseg"] == ol["nseg"]
+        worst, need, cells = _floor_stats(rr, ol, T)
+        stats[name] = (worst, need, cells)
+        assert rel_err(rr["ndot_remaining"], ol["ndot_remaining"], floor=1e-300) < 1e-11
+        assert np.allclose(rr["rates"].sum(axis=1), ol["rates"].sum(axis=1), rtol=1e-11, atol=0)
+    print("config 1 vs libm oracle (worst strict rel err, cells above 1e-9, cells):", stats)
+    for worst, need, cells in stats.values():
+        assert need <= 0.02 * cells                    # the floor is an exception, not the rule
+
+
+def test_escaping_spectrum_and_highest_pixel_level(rt, engine, oracle, spectra):
+    """ndotSpectrum(300) is only filled where a segment straddles the last output radius, 100 kpc
+    (equiSources.f90:3206-3224): a 400 kpc box with sources near the centre makes every leaf ray cross it.  Also
+    ndotDust, and highestPixelLevel (:3316), on a uniform and a nested grid, with and without dust."""
+    cases = []
+    g = W.uniform_grid(16, seed=31, box_kpc=400.0, tau_lo=1e-3, tau_hi=0.3, beta24=S24)
+    g["abun2"] = np.random.default_rng(3).uniform(1e-3, 4e-2, 16 ** 3)
+    cases.append((g, [(8 * 16 + 7) * 16 + 8, (6 * 16 + 9) * 16 + 7], [1, 2]))
+    g = W.nested_grid(8, 2, W.central_box_refine(0.3, 0.7, levels=2), seed=32, box_kpc=400.0, tau_lo=1e-3, tau_hi=0.3,
+                      beta24=S24)
+    cx, cy, cz = g["centres"]
+    cases.append((g, [int(np.argmin((cx - 0.52) ** 2 + (cy - 0.47) ** 2 + (cz - 0.5) ** 2))], [3]))
+    for g, srcs, wts in cases:
+        _set(engine, g)
+        og = _ograd(oracle, g)
+        for dust in (0, 1):
+            for maxlev in (6, 3):
+                oracle.set_portable_math(True)
+                try:
+                    op = og.point(spectra, srcs, wts, dust_approximation=dust, max_pixel_level=maxlev)
+                finally:
+                    oracle.set_portable_math(False)
+                ol = og.point(spectra, srcs, wts, dust_approximation=dust, max_pixel_level=maxlev)
+                engine.set_math(rt.MATH_FAITHFUL)
+                r = engine.point(spectra, srcs, wts, dust_approximation=dust, max_pixel_level=maxlev)
+                assert r["nseg"] == op["nseg"]
+                assert op["ndot_spectrum"].min() > 0           # every energy bin received photons
+                assert rel_err(r["ndot_spectrum"], op["ndot_spectrum"], floor=1e-300) < 1e-12
+                assert rel_err(r["ndot_dust"], op["ndot_dust"], floor=1e-300) < 1e-12
+                assert rel_err(r["ndot_spectrum"], ol["ndot_spectrum"], floor=1e-300) < 1e-11   # libm oracle
+                assert np.array_equal(r["highest_pixel_level"], op["highest_pixel_level"])
+                assert np.all(r["highest_pixel_level"] == maxlev)   # rays of this size always reach the last level
+                engine.set_math(rt.MATH_FAST)
+                rf = engine.point(spectra, srcs, wts, dust_approximation=dust, max_pixel_level=maxlev)
+                assert rel_err(rf["ndot_spectrum"], ol["ndot_spectrum"], floor=1e-300) < 1e-11
+                assert np.array_equal(rf["highest_pixel_level"], ol["highest_pixel_level"])
+                # no dust: the dust term is exp(0) per ray -> ndotDust = photons that reach 100 kpc unattenuated by dust
+                if dust == 0:
+                    assert np.allclose(r["ndot_dust"], np.array(wts, dtype=float) - ol["ndot_boundary"][:, -1], rtol=1e-12)
+    # a source that never splits: one pixel level
+    r = engine.point(spectra, srcs, wts, max_pixel_level=1)
+    assert np.all(r["highest_pixel_level"] == 0)
+
+
+def test_golden_spectrum_fixture(rt, engine, spectra):
+    """committed libm-oracle output for the escaping spectrum (tests/golden/point_spectrum_12.npz)"""
+    import os
+    from conftest import ROOT
+    f = np.load(os.path.join(ROOT, "tests", "golden", "point_spectrum_12.npz"))
+    g = W.uniform_grid(12, seed=int(f["seed"]), box_kpc=float(f["box_kpc"]), tau_lo=1e-3, tau_hi=0.3, beta24=S24)
+    _set(engine, g)
+    for mode in (rt.MATH_FAITHFUL, rt.MATH_FAST):
+        engine.set_math(mode)
+        r = engine.point(spectra, f["src"], f["wt"], dust_approximation=int(f["dust"]))
+        assert r["nseg"] == int(f["nseg"])
+        assert rel_err(r["ndot_spectrum"], f["ndot_spectrum"], floor=1e-300) < 1e-11
+        assert rel_err(r["ndot_dust"], f["ndot_dust"], floor=1e-300) < 1e-11
+        assert np.array_equal(r["highest_pixel_level"], f["highest_pixel_level"])
