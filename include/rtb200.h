@@ -53,9 +53,61 @@ typedef struct rtb200_ctx rtb200_ctx;
 int rtb200_version(void);
 const char* rtb200_status_string(int status);
 
-/* One context per process and GPU.  `device` is the CUDA ordinal (LOCAL_RANK under torchrun). */
+/* One context for one GPU.  `device` is the CUDA ordinal. */
 int rtb200_create(int device, rtb200_ctx** ctx);
 int rtb200_destroy(rtb200_ctx* ctx);
+
+/* Device groups: ONE handle for all GPUs of a node, accepted by every call below that takes a context.
+ *   rtb200_create_multi    one process drives `ngpus` devices (devices = NULL: 0..ngpus-1): what the reference's serial
+ *                          driver needs (the "init(ngpus)" entry SURVEY.md 8b proposes): rtbSetGrid / rtbDiffuse / rtbPoint of the
+ *                          Fortran shim are unchanged, the directions and sources are sharded inside the library.
+ *   rtb200_create_rank     the same group with one process per GPU (torchrun): every process passes the 128-byte id
+ *                          that rank 0 obtained from rtb200_comm_unique_id (broadcast by the launcher) and calls every
+ *                          function collectively.  Per-leaf host arrays are then read and written SLAB-WISE: rank r
+ *                          touches leaves [r*slab, (r+1)*slab) of the caller's arrays only (rtb200_multi_info).
+ * Data path (csrc/multi.cu): slab H2D + NVLink all-gather of the species, direction / source shards on full grids,
+ * reduce-scatter of the per-leaf sums (a peer-memory kernel of this library with the photo-rate epilogue fused, or
+ * NCCL: set_tuning "multi_reduce" 1 / 0), slab D2H.  NCCL (libnccl.so.2) is loaded with dlopen when a group of more
+ * than one device is created (RTB200_NCCL_LIB overrides the search path).  Results are bit-identical from run to run
+ * and independent of multi_reduce only in mode 1 (fixed summation order rank 0, 1, ...). */
+int rtb200_comm_unique_id(char* id128);
+int rtb200_create_multi(int ngpus, const int* devices, rtb200_ctx** ctx);
+int rtb200_create_rank(int device, int nranks, int rank, const char* id128, rtb200_ctx** ctx);
+/* nranks, devices of this process, first global rank of this process, leaves per slab, active reduction (1 peer kernel,
+ * 0 NCCL, -1 single device); any output may be NULL */
+int rtb200_multi_info(rtb200_ctx* ctx, int32_t* nranks, int32_t* nlocal, int32_t* firstRank, int64_t* slab,
+                      int32_t* reduceMode);
+/* the direction shard of a rank (HEALPix NESTED pixel numbers; whole zones, longest-processing-time-first on segment
+ * counts x "zone_cost_x/y/z" tuning factors); host only */
+int rtb200_multi_shard(rtb200_ctx* ctx, int nAngularLevel, int rank, int32_t* rays, int32_t cap, int32_t* nrays);
+/* the same rule without a handle (zoneCost3 = NULL: 1, 1, 1): what a one-process-per-GPU caller of the single-GPU entry
+ * points (rays = its shard) would use */
+int rtb200_shard_directions(int nranks, int nAngularLevel, int nx, const double* zoneCost3, int rank, int32_t* rays,
+                            int32_t cap, int32_t* nrays);
+/* Resident steps of a device group (results stay in the library's slab buffers, asynchronous; streams[i] = cudaStream_t
+ * of local device i, NULL = internal streams):
+ *   rtb200_multi_diffuse_resident  computeOpacities + sweep of each rank's direction shard + reduce-scatter of Jmean1..3
+ *                                  [+ diffuse photo-rates into K when ksi6 = {ksi24[3], ksi25, ksi26[2]} is given]
+ *                                  [+ solveRateEquations on the slab + all-gather of HI, HeI, HeII when chemistry != 0;
+ *                                  uses the point-source rates of a preceding rtb200_multi_point_resident]
+ *   rtb200_multi_point_resident    setZeroRates + ray casting of each rank's sources + reduce-scatter of the 6 rate fields
+ *   rtb200_multi_slab              this process's slab of local device `local`: leaves [offset, offset + count), device
+ *                                  pointers J [3][slab], K [3][slab] (krate24, krate25, krate26), R [6][slab]
+ *   rtb200_multi_sync              waits for all devices of the group; returns a pending device-side status */
+int rtb200_multi_diffuse_resident(rtb200_ctx* ctx, int nAngularLevel, const double* uvb, const double* beta,
+                                  const double* ksi6, int chemistry, void* const* streams, int64_t* nseg);
+int rtb200_multi_point_resident(rtb200_ctx* ctx, int nWave, const double* wavelength, const double* lum,
+                                const double* metallicity, double coefSpectrum, const double* aDust, int dustApproximation,
+                                int maxPixelLevel, int32_t nsrc, const int32_t* srcLeaf, const int32_t* srcWeight,
+                                void* const* streams, double* ndotRemaining, double* ndotBoundary, double* ndotDust,
+                                double* ndotSpectrum, int32_t* highestPixelLevel, int64_t* nseg);
+int rtb200_multi_slab(rtb200_ctx* ctx, int local, int64_t* offset, int64_t* count, double** J_device, double** K_device,
+                      double** R_device);
+int rtb200_multi_sync(rtb200_ctx* ctx);
+/* copies of the slab buffers of local device `local` to the host after a synchronisation: J3 [3][slab], K3 [3][slab],
+ * R6 [6][slab] (any may be NULL); entries beyond the slab's leaf count are padding */
+int rtb200_multi_slab_get(rtb200_ctx* ctx, int local, double* J3, double* K3, double* R6);
+
 int rtb200_set_math(rtb200_ctx* ctx, int math_mode);
 /* Launch tuning knobs; results do not depend on them (tests/test_diffuse_gpu.py, test_point_gpu.py).  Keys:
  *   uniform sweep  "slots" (zone tasks per launch, 0 = all), "graph" (CUDA graph replay, 1), "dense" (register cap:
@@ -66,6 +118,8 @@ int rtb200_set_math(rtb200_ctx* ctx, int math_mode);
  *                  exist only with RTB200_EXPERIMENTAL set in the environment), "l2_mb"
  *   nested grids   "force_amr" (general octree path on a uniform grid), "amr_batch" (directions per batch, 0 = as many
  *                  as fit in memory)
+ *   device groups  "multi_reduce" (1 = peer-memory reduce-scatter kernel, 0 = NCCL), "zone_cost_x" / "_y" / "_z"
+ *                  (relative time per segment of zones sweeping along x / y / z, for the direction sharding)
  *   point sources  "point_batch" (sources per batch), "point_min_blocks" (register cap of the march kernel, 5),
  *                  "point_deposit" (0 = fp64 RED, 1 = records + sort + segmented reduction), "point_record_cap",
  *                  "point_refill" (lane refill on the last pixel level, 0)

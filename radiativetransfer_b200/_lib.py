@@ -17,6 +17,20 @@ SIGNATURES = {
     "rtb200_status_string": (C.c_char_p, [C.c_int]),
     "rtb200_create": (C.c_int, [C.c_int, C.POINTER(P)]),
     "rtb200_destroy": (C.c_int, [P]),
+    "rtb200_comm_unique_id": (C.c_int, [P]),
+    "rtb200_create_multi": (C.c_int, [C.c_int, P, C.POINTER(P)]),
+    "rtb200_create_rank": (C.c_int, [C.c_int, C.c_int, C.c_int, P, C.POINTER(P)]),
+    "rtb200_multi_info": (C.c_int, [P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "rtb200_shard_directions": (C.c_int, [C.c_int, C.c_int, C.c_int, P, C.c_int, P, C.c_int32, C.POINTER(C.c_int32)]),
+    "rtb200_multi_shard": (C.c_int, [P, C.c_int, C.c_int, P, C.c_int32, C.POINTER(C.c_int32)]),
+    "rtb200_multi_diffuse_resident": (C.c_int, [P, C.c_int, P, P, P, C.c_int, P, C.POINTER(C.c_int64)]),
+    "rtb200_multi_point_resident": (C.c_int, [P, C.c_int, P, P, P, C.c_double, P, C.c_int, C.c_int, C.c_int32, P, P, P, P,
+                                              P, P, P, P, C.POINTER(C.c_int64)]),
+    "rtb200_multi_slab": (C.c_int, [P, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(P), C.POINTER(P),
+                                    C.POINTER(P)]),
+    "rtb200_multi_sync": (C.c_int, [P]),
+    "rtb200_multi_slab_get": (C.c_int, [P, C.c_int, P, P, P]),
     "rtb200_set_math": (C.c_int, [P, C.c_int]),
     "rtb200_set_tuning": (C.c_int, [P, C.c_char_p, C.c_double]),
     "rtb200_device_error": (C.c_int, [P]),

@@ -113,11 +113,12 @@ static int build_tree(Context& c, const int8_t* level) {
   return RTB200_OK;
 }
 
-static int upload(void** dst, const void* src, size_t bytes, cudaStream_t s) {
-  cudaError_t e = cudaMalloc(dst, bytes ? bytes : 8);
+static int upload(void** dst, const void* src, size_t bytes, size_t padBytes, cudaStream_t s) {
+  cudaError_t e = cudaMalloc(dst, bytes + padBytes ? bytes + padBytes : 8);
   if (e != cudaSuccess) { set_cuda_error("cudaMalloc", e, __FILE__, __LINE__); return e == cudaErrorMemoryAllocation ? RTB200_ERR_NOMEM : RTB200_ERR_CUDA; }
   if (src) RTB_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, s));
   else RTB_CUDA(cudaMemsetAsync(*dst, 0, bytes ? bytes : 8, s));
+  if (padBytes) RTB_CUDA(cudaMemsetAsync((char*)*dst + bytes, 0, padBytes, s));
   return RTB200_OK;
 }
 
@@ -142,7 +143,7 @@ static int resolve_directions(int nAngularLevel, const int32_t* rays, int32_t nr
   return RTB200_OK;
 }
 
-static int run_diffuse(Context& c, int nAngularLevel, const double* uvb, const double* beta, const int32_t* rays,
+int run_diffuse(Context& c, int nAngularLevel, const double* uvb, const double* beta, const int32_t* rays,
                        int32_t nrays, double* dJ, cudaStream_t s, int64_t* nseg) {
   if (!uvb || !beta || !dJ) return RTB200_ERR_ARG;
   if (c.nleaf == 0) return RTB200_ERR_ARG;
@@ -164,13 +165,131 @@ static int run_diffuse(Context& c, int nAngularLevel, const double* uvb, const d
   return RTB200_OK;
 }
 
+int context_init(Context& c, int device) {
+  c.device = device;
+  RTB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  RTB_CUDA(cudaGetDeviceProperties(&prop, device));
+  c.smCount = prop.multiProcessorCount;
+  c.l2Bytes = (size_t)prop.l2CacheSize;
+  if (c.l2Bytes) c.tune.l2BudgetMB = 0.75 * (double)c.l2Bytes / 1048576.0;
+  RTB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  RTB_CUDA(cudaEventCreate(&c.evStart));
+  RTB_CUDA(cudaEventCreate(&c.evStop));
+  RTB_CUDA(cudaEventCreate(&c.evSweep0));
+  RTB_CUDA(cudaEventCreate(&c.evSweep1));
+  RTB_CUDA(cudaEventCreateWithFlags(&c.evFork, cudaEventDisableTiming));
+  RTB_CUDA(cudaMalloc((void**)&c.dErr, 64));
+  RTB_CUDA(cudaMemset(c.dErr, 0, 64));
+  if (const char* v = getenv("RTB200_DENSE")) c.tune.minBlocks = atoi(v);
+  if (const char* v = getenv("RTB200_SLOTS")) c.tune.slots = atoi(v);
+  if (const char* v = getenv("RTB200_GRAPH")) c.tune.useGraph = atoi(v);
+  if (const char* v = getenv("RTB200_L2_MB")) c.tune.l2BudgetMB = atof(v);
+  return RTB200_OK;
+}
+
+void context_destroy(Context& c) {
+  cudaSetDevice(c.device);
+  cudaDeviceSynchronize();
+  free_grid(c);
+  cudaFree(c.dChemK);
+  cudaFree(c.dMassPart);
+  cudaFree(c.dAcc); cudaFree(c.dPlanes); cudaFree(c.dAmrScratch); cudaFree(c.dErr); cudaFree(c.dMarchSeg); cudaFree(c.dMarchProg);
+  if (c.hPinned) cudaFreeHost(c.hPinned);
+  if (c.evStart) cudaEventDestroy(c.evStart);
+  if (c.evStop) cudaEventDestroy(c.evStop);
+  if (c.evSweep0) cudaEventDestroy(c.evSweep0);
+  if (c.evSweep1) cudaEventDestroy(c.evSweep1);
+  if (c.evFork) cudaEventDestroy(c.evFork);
+  for (auto e : c.chainEvents) cudaEventDestroy(e);
+  for (auto st : c.chainStreams) cudaStreamDestroy(st);
+  if (c.stream) cudaStreamDestroy(c.stream);
+  c = Context();
+}
+
+int device_error(Context& c) {  // status raised by device-side guards of asynchronous calls; clears it
+  int32_t err = 0;
+  RTB_CUDA(cudaSetDevice(c.device));
+  RTB_CUDA(cudaMemcpy(&err, c.dErr, sizeof(err), cudaMemcpyDeviceToHost));
+  if (err) cudaMemset(c.dErr, 0, 64);
+  return err;
+}
+
+int set_math(Context& c, int mode) {
+  if (c.mathMode != mode && c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
+  c.mathMode = mode;
+  return RTB200_OK;
+}
+
+int set_tuning(Context& c, const char* key, double value) {
+  std::string k(key);
+  if (k == "dense") c.tune.minBlocks = (int)value;
+  else if (k == "expv") c.tune.expVariant = (int)value;
+  else if (k == "lockstep") c.tune.lockstep = (int)value;
+  else if (k == "amr_batch") c.tune.amrBatch = (int)value;
+  else if (k == "force_amr") c.tune.forceAmr = (int)value;
+  else if (k == "slots") c.tune.slots = (int)value;
+  else if (k == "graph") c.tune.useGraph = (int)value;
+  else if (k == "l2_mb") c.tune.l2BudgetMB = value;
+  else if (k == "march") c.tune.march = (int)value;
+  else if (k == "transpose_z") c.tune.transposeZ = (int)value;
+  else if (k == "pdl") c.tune.pdl = (int)value;
+  else if (k == "dirs_per_task") c.tune.dirsPerTask = (int)value;
+  else if (k == "march_debug") {
+    // experiments only (mode 1 skips the neighbour polling and gives WRONG results): not reachable from product code
+    if (!getenv("RTB200_EXPERIMENTAL")) return RTB200_ERR_ARG;
+    c.tune.marchDebug = (int)value;
+  }
+  else if (k == "portable_math") c.tune.portableMath = (int)value;
+  else if (k == "point_batch") c.tune.pointBatch = (int)value;
+  else if (k == "point_min_blocks") c.tune.pointMinBlocks = (int)value;
+  else if (k == "point_refill") c.tune.pointRefill = (int)value;
+  else if (k == "point_deposit") c.tune.pointDeposit = (int)value;
+  else if (k == "point_record_cap") c.tune.pointRecordCap = (long long)value;
+  else return RTB200_ERR_ARG;
+  c.uniPlanKey.clear();
+  if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
+  return RTB200_OK;
+}
+
+int grid_set(Context& c, int nx, int64_t nleaf, const int8_t* level, const double* HI, const double* HeI,
+             const double* HeII, const double* rho, const double* abun2, double physicalBoxSize) {
+  RTB_CUDA(cudaSetDevice(c.device));
+  RTB_CUDA(cudaDeviceSynchronize());
+  free_grid(c);
+  c.nx = nx; c.nleaf = nleaf; c.boxSize = physicalBoxSize;
+  c.hLevel.assign(level, level + nleaf);
+  c.uniform = true;
+  for (int64_t i = 0; i < nleaf; i++)
+    if (level[i] != 0) { c.uniform = false; break; }
+  if (c.uniform && nleaf != (int64_t)nx * nx * nx) { c.nleaf = 0; return RTB200_ERR_LEVELS; }
+  if (int st = build_tree(c, level)) { c.nleaf = 0; return st; }
+  cudaStream_t s = c.stream;
+  const size_t nb = (size_t)nleaf * sizeof(double), pad = (size_t)c.padLeaves * sizeof(double);
+  int st = upload((void**)&c.dLevel, level, (size_t)nleaf, 0, s);
+  if (!st) st = upload((void**)&c.dHI, HI, nb, pad, s);
+  if (!st) st = upload((void**)&c.dHeI, HeI, nb, pad, s);
+  if (!st) st = upload((void**)&c.dHeII, HeII, nb, pad, s);
+  // rho / abun2 are optional (diffuse-only use): without them the point-source and chemistry entry points return
+  // RTB200_ERR_ARG instead of working on zero-filled arrays
+  if (!st && rho) st = upload((void**)&c.dRho, rho, nb, 0, s);
+  if (!st && abun2) st = upload((void**)&c.dAbun2, abun2, nb, 0, s);
+  if (!st) st = upload((void**)&c.dKappa, nullptr, 3 * nb, 0, s);
+  if (!st) st = upload((void**)&c.dJ, nullptr, 3 * nb, 0, s);
+  if (!st) {
+    st = upload((void**)&c.tree.child, c.hChild.data(), c.hChild.size() * sizeof(int32_t), 0, s);
+    if (!st) st = upload((void**)&c.tree.leafX, c.hLeafX.data(), (size_t)nleaf * sizeof(int32_t), 0, s);
+    if (!st) st = upload((void**)&c.tree.leafY, c.hLeafY.data(), (size_t)nleaf * sizeof(int32_t), 0, s);
+    if (!st) st = upload((void**)&c.tree.leafZ, c.hLeafZ.data(), (size_t)nleaf * sizeof(int32_t), 0, s);
+  }
+  if (st) { free_grid(c); c.nleaf = 0; return st; }
+  RTB_CUDA(cudaStreamSynchronize(s));
+  return RTB200_OK;
+}
+
 }  // namespace rtb
 
 using namespace rtb;
-
-struct rtb200_ctx {
-  Context c;
-};
 
 extern "C" {
 
@@ -208,141 +327,49 @@ int rtb200_create(int device, rtb200_ctx** out) {
     return RTB200_ERR_CUDA;
   }
   if (device < 0 || device >= ndev) return RTB200_ERR_ARG;
-  RTB_CUDA(cudaSetDevice(device));
   rtb200_ctx* h = new (std::nothrow) rtb200_ctx();
   if (!h) return RTB200_ERR_NOMEM;
-  Context& c = h->c;
-  c.device = device;
-  auto init = [&]() -> int {
-    cudaDeviceProp prop;
-    RTB_CUDA(cudaGetDeviceProperties(&prop, device));
-    c.smCount = prop.multiProcessorCount;
-    c.l2Bytes = (size_t)prop.l2CacheSize;
-    if (c.l2Bytes) c.tune.l2BudgetMB = 0.75 * (double)c.l2Bytes / 1048576.0;
-    RTB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    RTB_CUDA(cudaEventCreate(&c.evStart));
-    RTB_CUDA(cudaEventCreate(&c.evStop));
-    RTB_CUDA(cudaEventCreate(&c.evSweep0));
-    RTB_CUDA(cudaEventCreate(&c.evSweep1));
-    RTB_CUDA(cudaEventCreateWithFlags(&c.evFork, cudaEventDisableTiming));
-    RTB_CUDA(cudaMalloc((void**)&c.dErr, 64));
-    RTB_CUDA(cudaMemset(c.dErr, 0, 64));
-    return RTB200_OK;
-  };
-  if (int st = init()) {   // nothing of a half-built context survives
-    rtb200_destroy(h);
+  if (int st = context_init(h->c, device)) {   // nothing of a half-built context survives
+    context_destroy(h->c);
+    delete h;
     return st;
   }
-  if (const char* v = getenv("RTB200_DENSE")) c.tune.minBlocks = atoi(v);
-  if (const char* v = getenv("RTB200_SLOTS")) c.tune.slots = atoi(v);
-  if (const char* v = getenv("RTB200_GRAPH")) c.tune.useGraph = atoi(v);
-  if (const char* v = getenv("RTB200_L2_MB")) c.tune.l2BudgetMB = atof(v);
   *out = h;
   return RTB200_OK;
 }
 
 int rtb200_destroy(rtb200_ctx* h) {
   if (!h) return RTB200_OK;
-  Context& c = h->c;
-  cudaSetDevice(c.device);
-  cudaDeviceSynchronize();
-  free_grid(c);
-  cudaFree(c.dChemK);
-  cudaFree(c.dMassPart);
-  cudaFree(c.dAcc); cudaFree(c.dPlanes); cudaFree(c.dAmrScratch); cudaFree(c.dErr); cudaFree(c.dMarchSeg); cudaFree(c.dMarchProg);
-  if (c.hPinned) cudaFreeHost(c.hPinned);
-  if (c.evStart) cudaEventDestroy(c.evStart);
-  if (c.evStop) cudaEventDestroy(c.evStop);
-  if (c.evSweep0) cudaEventDestroy(c.evSweep0);
-  if (c.evSweep1) cudaEventDestroy(c.evSweep1);
-  if (c.evFork) cudaEventDestroy(c.evFork);
-  for (auto e : c.chainEvents) cudaEventDestroy(e);
-  for (auto st : c.chainStreams) cudaStreamDestroy(st);
-  if (c.stream) cudaStreamDestroy(c.stream);
+  if (h->m) multi_destroy(h->m);
+  else context_destroy(h->c);
   delete h;
   return RTB200_OK;
 }
 
 int rtb200_set_math(rtb200_ctx* h, int mode) {
   if (!h || (mode != RTB200_MATH_FAST && mode != RTB200_MATH_FAITHFUL)) return RTB200_ERR_ARG;
-  if (h->c.mathMode != mode && h->c.graphExec) { cudaGraphExecDestroy(h->c.graphExec); h->c.graphExec = nullptr; }
-  h->c.mathMode = mode;
-  return RTB200_OK;
+  if (h->m) return multi_set_math(h->m, mode);
+  return set_math(h->c, mode);
 }
 
 int rtb200_set_tuning(rtb200_ctx* h, const char* key, double value) {
   if (!h || !key) return RTB200_ERR_ARG;
-  Context& c = h->c;
-  std::string k(key);
-  if (k == "dense") c.tune.minBlocks = (int)value;
-  else if (k == "expv") c.tune.expVariant = (int)value;
-  else if (k == "lockstep") c.tune.lockstep = (int)value;
-  else if (k == "amr_batch") c.tune.amrBatch = (int)value;
-  else if (k == "force_amr") c.tune.forceAmr = (int)value;
-  else if (k == "slots") c.tune.slots = (int)value;
-  else if (k == "graph") c.tune.useGraph = (int)value;
-  else if (k == "l2_mb") c.tune.l2BudgetMB = value;
-  else if (k == "march") c.tune.march = (int)value;
-  else if (k == "transpose_z") c.tune.transposeZ = (int)value;
-  else if (k == "pdl") c.tune.pdl = (int)value;
-  else if (k == "dirs_per_task") c.tune.dirsPerTask = (int)value;
-  else if (k == "march_debug") {
-    // experiments only (mode 1 skips the neighbour polling and gives WRONG results): not reachable from product code
-    if (!getenv("RTB200_EXPERIMENTAL")) return RTB200_ERR_ARG;
-    c.tune.marchDebug = (int)value;
-  }
-  else if (k == "portable_math") c.tune.portableMath = (int)value;
-  else if (k == "point_batch") c.tune.pointBatch = (int)value;
-  else if (k == "point_min_blocks") c.tune.pointMinBlocks = (int)value;
-  else if (k == "point_refill") c.tune.pointRefill = (int)value;
-  else if (k == "point_deposit") c.tune.pointDeposit = (int)value;
-  else if (k == "point_record_cap") c.tune.pointRecordCap = (long long)value;
-  else return RTB200_ERR_ARG;
-  c.uniPlanKey.clear();
-  if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
-  return RTB200_OK;
+  if (h->m) return multi_set_tuning(h->m, key, value);
+  return set_tuning(h->c, key, value);
 }
 
 int rtb200_grid_set(rtb200_ctx* h, int nx, int64_t nleaf, const int8_t* level, const double* HI, const double* HeI,
                     const double* HeII, const double* rho, const double* abun2, double physicalBoxSize) {
   if (!h || nx < 1 || nx > 4096 || !level || !HI || nleaf < (int64_t)nx * nx * nx || nleaf > (int64_t)INT32_MAX)
     return RTB200_ERR_ARG;
-  Context& c = h->c;
-  RTB_CUDA(cudaSetDevice(c.device));
-  RTB_CUDA(cudaDeviceSynchronize());
-  free_grid(c);
-  c.nx = nx; c.nleaf = nleaf; c.boxSize = physicalBoxSize;
-  c.hLevel.assign(level, level + nleaf);
-  c.uniform = true;
-  for (int64_t i = 0; i < nleaf; i++)
-    if (level[i] != 0) { c.uniform = false; break; }
-  if (c.uniform && nleaf != (int64_t)nx * nx * nx) { c.nleaf = 0; return RTB200_ERR_LEVELS; }
-  if (int st = build_tree(c, level)) { c.nleaf = 0; return st; }
-  cudaStream_t s = c.stream;
-  const size_t nb = (size_t)nleaf * sizeof(double);
-  int st = upload((void**)&c.dLevel, level, (size_t)nleaf, s);
-  if (!st) st = upload((void**)&c.dHI, HI, nb, s);
-  if (!st) st = upload((void**)&c.dHeI, HeI, nb, s);
-  if (!st) st = upload((void**)&c.dHeII, HeII, nb, s);
-  // rho / abun2 are optional (diffuse-only use): without them the point-source and chemistry entry points return
-  // RTB200_ERR_ARG instead of working on zero-filled arrays
-  if (!st && rho) st = upload((void**)&c.dRho, rho, nb, s);
-  if (!st && abun2) st = upload((void**)&c.dAbun2, abun2, nb, s);
-  if (!st) st = upload((void**)&c.dKappa, nullptr, 3 * nb, s);
-  if (!st) st = upload((void**)&c.dJ, nullptr, 3 * nb, s);
-  if (!st) {
-    st = upload((void**)&c.tree.child, c.hChild.data(), c.hChild.size() * sizeof(int32_t), s);
-    if (!st) st = upload((void**)&c.tree.leafX, c.hLeafX.data(), (size_t)nleaf * sizeof(int32_t), s);
-    if (!st) st = upload((void**)&c.tree.leafY, c.hLeafY.data(), (size_t)nleaf * sizeof(int32_t), s);
-    if (!st) st = upload((void**)&c.tree.leafZ, c.hLeafZ.data(), (size_t)nleaf * sizeof(int32_t), s);
-  }
-  if (st) { free_grid(c); c.nleaf = 0; return st; }
-  RTB_CUDA(cudaStreamSynchronize(s));
-  return RTB200_OK;
+  if (h->m) return multi_grid_set(h->m, nx, nleaf, level, HI, HeI, HeII, rho, abun2, physicalBoxSize);
+  return grid_set(h->c, nx, nleaf, level, HI, HeI, HeII, rho, abun2, physicalBoxSize);
 }
 
 int rtb200_grid_update_species(rtb200_ctx* h, const double* HI, const double* HeI, const double* HeII) {
-  if (!h || h->c.nleaf == 0) return RTB200_ERR_ARG;
+  if (!h) return RTB200_ERR_ARG;
+  if (h->m) return multi_update_species(h->m, HI, HeI, HeII);
+  if (h->c.nleaf == 0) return RTB200_ERR_ARG;
   Context& c = h->c;
   RTB_CUDA(cudaSetDevice(c.device));
   // Work queued by the *_device entry points on the caller's streams (sweeps, chemistry, ray casting) reads and
@@ -358,13 +385,14 @@ int rtb200_grid_update_species(rtb200_ctx* h, const double* HI, const double* He
 
 int rtb200_diffuse_device(rtb200_ctx* h, int nAngularLevel, const double* uvb, const double* beta, const int32_t* rays,
                           int32_t nrays, double* J_device, void* stream, int64_t* nseg) {
-  if (!h) return RTB200_ERR_ARG;
+  if (!h || h->m) return RTB200_ERR_ARG;   // a device group leaves its results in slabs: rtb200_multi_diffuse_resident
   return run_diffuse(h->c, nAngularLevel, uvb, beta, rays, nrays, J_device, (cudaStream_t)stream, nseg);
 }
 
 int rtb200_diffuse(rtb200_ctx* h, int nAngularLevel, const double* uvb, const double* beta, const int32_t* rays,
                    int32_t nrays, double* J1, double* J2, double* J3, int64_t* nseg) {
   if (!h || !J1 || !J2 || !J3) return RTB200_ERR_ARG;
+  if (h->m) return multi_diffuse_host(h->m, nAngularLevel, uvb, beta, rays, nrays, J1, J2, J3, nseg);
   Context& c = h->c;
   int st = run_diffuse(c, nAngularLevel, uvb, beta, rays, nrays, c.dJ, c.stream, nseg);
   if (st) return st;
@@ -381,7 +409,7 @@ int rtb200_diffuse(rtb200_ctx* h, int nAngularLevel, const double* uvb, const do
 
 int rtb200_diffuse_rates_device(rtb200_ctx* h, const double* J, const double* ksi24, const double* ksi25,
                                 const double* ksi26, double* k24, double* k25, double* k26, void* stream) {
-  if (!h || !J || !ksi24 || !ksi25 || !ksi26 || !k24 || !k25 || !k26 || h->c.nleaf == 0) return RTB200_ERR_ARG;
+  if (!h || h->m || !J || !ksi24 || !ksi25 || !ksi26 || !k24 || !k25 || !k26 || h->c.nleaf == 0) return RTB200_ERR_ARG;
   RTB_CUDA(cudaSetDevice(h->c.device));
   return launch_diffuse_rates(h->c, J, ksi24, ksi25, ksi26, k24, k25, k26, (cudaStream_t)stream);
 }
@@ -413,7 +441,7 @@ int rtb200_point_device(rtb200_ctx* h, int nWave, const double* wavelength, cons
                         const int32_t* srcLeaf, const int32_t* srcWeight, double* rates_device, void* stream,
                         double* ndotRemaining, double* ndotBoundary, double* ndotDust, double* ndotSpectrum,
                         int32_t* highestPixelLevel, int64_t* nseg) {
-  if (!h || !rates_device) return RTB200_ERR_ARG;
+  if (!h || h->m || !rates_device) return RTB200_ERR_ARG;
   PointInputs in = make_point_inputs(nWave, wavelength, lum, metallicity, coefSpectrum, aDust, dustApproximation,
                                      maxPixelLevel, nsrc, srcLeaf, srcWeight);
   const bool wantDiag = ndotRemaining || ndotBoundary || ndotDust || ndotSpectrum || highestPixelLevel;
@@ -453,6 +481,8 @@ int rtb200_point(rtb200_ctx* h, int nWave, const double* wavelength, const doubl
   PointInputs in = make_point_inputs(nWave, wavelength, lum, metallicity, coefSpectrum, aDust, dustApproximation,
                                      maxPixelLevel, nsrc, srcLeaf, srcWeight);
   double* k[6] = {krate24, krate25, krate26, crate24, crate25, crate26};
+  if (h->m)
+    return multi_point_host(h->m, in, k, ndotRemaining, ndotBoundary, ndotDust, ndotSpectrum, highestPixelLevel, nseg);
   return point_host_call(h->c, in, k, ndotRemaining, ndotBoundary, ndotDust, ndotSpectrum, highestPixelLevel, nseg,
                          nullptr, 0, nullptr);
 }
@@ -461,7 +491,7 @@ int rtb200_point_trace(rtb200_ctx* h, int nWave, const double* wavelength, const
                        double coefSpectrum, const double* aDust, int dustApproximation, int maxPixelLevel, int32_t nsrc,
                        const int32_t* srcLeaf, const int32_t* srcWeight, double* rates6, int64_t* nseg, int64_t* trace,
                        int64_t traceCap, int64_t* traceLen) {
-  if (!h || !rates6 || !trace || traceCap <= 0 || !traceLen) return RTB200_ERR_ARG;
+  if (!h || h->m || !rates6 || !trace || traceCap <= 0 || !traceLen) return RTB200_ERR_ARG;
   PointInputs in = make_point_inputs(nWave, wavelength, lum, metallicity, coefSpectrum, aDust, dustApproximation,
                                      maxPixelLevel, nsrc, srcLeaf, srcWeight);
   double* k[6];
@@ -474,8 +504,9 @@ int rtb200_point_trace(rtb200_ctx* h, int nWave, const double* wavelength, const
 
 int rtb200_point_tables(rtb200_ctx* h, int nWave, const double* wavelength, const double* lum, const double* metallicity,
                         double coefSpectrum, const double* aDust, int iMetal, double coefMetal, double* tables) {
-  if (!h || !tables || iMetal < 1 || iMetal > 4 || h->c.nleaf == 0) return RTB200_ERR_ARG;
-  Context& c = h->c;
+  if (!h || !tables || iMetal < 1 || iMetal > 4) return RTB200_ERR_ARG;
+  Context& c = h->m ? multi_primary(h->m) : h->c;
+  if (c.nleaf == 0) return RTB200_ERR_ARG;
   const int32_t leaf = 0, weight = 0;  // a source of weight 0 casts no rays: only its tables are built
   PointInputs in = make_point_inputs(nWave, wavelength, lum, metallicity, coefSpectrum, aDust, 1, 1, 1, &leaf, &weight);
   in.forceMetal = iMetal; in.forceCoefMetal = coefMetal;
@@ -490,27 +521,36 @@ int rtb200_chemistry_tables(rtb200_ctx* h, int nratec, double logtem0, double lo
                             const double* k6a) {
   if (!h) return RTB200_ERR_ARG;
   const double* k[6] = {k1a, k2a, k3a, k4a, k5a, k6a};
+  if (h->m) return multi_chemistry_tables(h->m, nratec, logtem0, logtem9, dlogtem, k);
   return chemistry_set_tables(h->c, nratec, logtem0, logtem9, dlogtem, k);
 }
 
 int rtb200_chemistry_temperature(rtb200_ctx* h, const double* tgas) {
   if (!h) return RTB200_ERR_ARG;
+  if (h->m) return multi_chemistry_temperature(h->m, tgas);
   return chemistry_set_temperature(h->c, tgas);
 }
 
 int rtb200_chemistry_device(rtb200_ctx* h, const double* rates_device, const double* J_device, const double* ksi,
                             const double* uniform, double* maxChange, void* stream) {
-  if (!h) return RTB200_ERR_ARG;
+  if (!h || h->m) return RTB200_ERR_ARG;
   return chemistry_run(h->c, rates_device, J_device, ksi, uniform, maxChange, (cudaStream_t)stream);
 }
 
 int rtb200_compute_mass(rtb200_ctx* h, double* neutralHydrogenMass, double* totalHydrogenMass, void* stream) {
   if (!h) return RTB200_ERR_ARG;
+  if (h->m) {  // a device group holds the same species on every device after each step: any member can do the sum
+    if (int st = rtb200_multi_sync(h)) return st;
+    Context& c = multi_primary(h->m);
+    return compute_mass(c, neutralHydrogenMass, totalHydrogenMass, c.stream);
+  }
   return compute_mass(h->c, neutralHydrogenMass, totalHydrogenMass, (cudaStream_t)stream);
 }
 
 int rtb200_grid_get_species(rtb200_ctx* h, double* HI, double* HeI, double* HeII) {
-  if (!h || h->c.nleaf == 0) return RTB200_ERR_ARG;
+  if (!h) return RTB200_ERR_ARG;
+  if (h->m) return multi_get_species(h->m, HI, HeI, HeII);
+  if (h->c.nleaf == 0) return RTB200_ERR_ARG;
   Context& c = h->c;
   RTB_CUDA(cudaSetDevice(c.device));
   RTB_CUDA(cudaDeviceSynchronize());
@@ -523,11 +563,8 @@ int rtb200_grid_get_species(rtb200_ctx* h, double* HI, double* HeI, double* HeII
 
 int rtb200_device_error(rtb200_ctx* h) {  // status raised by device-side guards of asynchronous calls
   if (!h) return RTB200_ERR_ARG;
-  int32_t err = 0;
-  RTB_CUDA(cudaSetDevice(h->c.device));
-  RTB_CUDA(cudaMemcpy(&err, h->c.dErr, sizeof(err), cudaMemcpyDeviceToHost));
-  if (err) cudaMemset(h->c.dErr, 0, 64);
-  return err;
+  if (h->m) return multi_device_error(h->m);
+  return device_error(h->c);
 }
 
 int rtb200_direction(int nAngularLevel, int64_t iray, int32_t* izone, double* phi, double* theta) {
@@ -556,17 +593,19 @@ int rtb200_patterns(int nAngularLevel, int64_t iray, int nx, double* out) {
 }
 
 int rtb200_neighbours(rtb200_ctx* h, int nAngularLevel, int64_t iray, int32_t* nb) {
-  if (!h || !nb || h->c.nleaf == 0) return RTB200_ERR_ARG;
+  if (!h || !nb) return RTB200_ERR_ARG;
+  Context& c = h->m ? multi_primary(h->m) : h->c;
+  if (c.nleaf == 0) return RTB200_ERR_ARG;
   Direction d = classify_direction(nAngularLevel, iray);
   if (d.status) return d.status;
-  RTB_CUDA(cudaSetDevice(h->c.device));
-  return amr_neighbours(h->c, d, nb);
+  RTB_CUDA(cudaSetDevice(c.device));
+  return amr_neighbours(c, d, nb);
 }
 
 int rtb200_debug_portable_math(rtb200_ctx* h, int64_t n, const double* x, double* expOut, double* logOut) {
   if (!h || n < 0 || !x || !expOut || !logOut) return RTB200_ERR_ARG;
   if (n == 0) return RTB200_OK;
-  Context& c = h->c;
+  Context& c = h->m ? multi_primary(h->m) : h->c;
   RTB_CUDA(cudaSetDevice(c.device));
   double* d = nullptr;
   RTB_CUDA(cudaMalloc((void**)&d, (size_t)3 * n * sizeof(double)));
@@ -586,7 +625,7 @@ int rtb200_debug_portable_math(rtb200_ctx* h, int64_t n, const double* x, double
 int rtb200_last_stats(rtb200_ctx* h, double* ms, double* sweepMs, int64_t* launches, int64_t* sweepLaunches,
                       double* algBytes) {
   if (!h) return RTB200_ERR_ARG;
-  Context& c = h->c;
+  Context& c = h->m ? multi_primary(h->m) : h->c;
   if (c.statsPending) {
     RTB_CUDA(cudaSetDevice(c.device));
     RTB_CUDA(cudaEventSynchronize(c.evStop));

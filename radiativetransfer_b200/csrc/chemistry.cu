@@ -30,7 +30,9 @@ struct ChemParams {
   double ksi[6], uniform[4];
   double cellSize[32];   // physicalBoxSize / (float(2**level) * float(nx))
   double logtem0, logtem9, dlogtem, psi, mh, mhe, fourPi;
-  int64_t N;
+  int64_t N;             // leaves of the grid
+  int64_t first, count;  // leaves [first, first + count) are solved (a rank's slab; the whole grid by default)
+  int64_t rStride, jStride;  // field strides of `rates` / `J`; their element (f, leaf c) sits at f * stride + c - first
   int nratec;
   unsigned long long* maxChangeBits;
   int32_t* err;
@@ -39,8 +41,9 @@ struct ChemParams {
 __device__ __forceinline__ bool opposite(double a, double b) { return ((a > 0.) && (b < 0.)) || ((a < 0.) && (b > 0.)); }
 
 __global__ void __launch_bounds__(128) chemistry_kernel(const __grid_constant__ ChemParams P) {
-  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (c >= P.N) return;
+  const int64_t local = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (local >= P.count) return;
+  const int64_t c = P.first + local;
   const double rho = P.rho[c];
   const double nh = D(M(P.psi, rho), P.mh);
   const double onemPsi = S(1., P.psi);
@@ -60,13 +63,14 @@ __global__ void __launch_bounds__(128) chemistry_kernel(const __grid_constant__ 
   const double vol = M(M(pcs, pcs), pcs);
   double krate24 = 0., krate25 = 0., krate26 = 0.;
   if (P.rates) {
-    if (HI > 0.) krate24 = D(P.rates[c], M(vol, HI));
-    if (HeII > 0.) krate25 = D(P.rates[P.N + c], M(vol, HeII));
-    if (HeI > 0.) krate26 = D(P.rates[2 * P.N + c], M(vol, HeI));
+    if (HI > 0.) krate24 = D(P.rates[local], M(vol, HI));
+    if (HeII > 0.) krate25 = D(P.rates[P.rStride + local], M(vol, HeII));
+    if (HeI > 0.) krate26 = D(P.rates[2 * P.rStride + local], M(vol, HeI));
   }
   krate24 = fmax(krate24, 0.); krate25 = fmax(krate25, 0.); krate26 = fmax(krate26, 0.);
   if (P.J) {
-    const double t1 = M(P.fourPi, P.J[c]), t2 = M(P.fourPi, P.J[P.N + c]), t3 = M(P.fourPi, P.J[2 * P.N + c]);
+    const double t1 = M(P.fourPi, P.J[local]), t2 = M(P.fourPi, P.J[P.jStride + local]),
+                 t3 = M(P.fourPi, P.J[2 * P.jStride + local]);
     krate24 = A(A(A(krate24, M(t1, P.ksi[0])), M(t2, P.ksi[1])), M(t3, P.ksi[2]));
     krate25 = A(krate25, M(t3, P.ksi[3]));
     krate26 = A(A(krate26, M(t2, P.ksi[4])), M(t3, P.ksi[5]));
@@ -159,13 +163,31 @@ int chemistry_set_temperature(Context& c, const double* tgas) {
   return RTB200_OK;
 }
 
+static int chemistry_launch(Context& c, int64_t first, int64_t count, const double* dRates, int64_t rStride,
+                            const double* dJ, int64_t jStride, const double* ksi, const double* uniform,
+                            double* maxChange, cudaStream_t s);
+
 int chemistry_run(Context& c, const double* dRates, const double* dJ, const double* ksi, const double* uniform,
                   double* maxChange, cudaStream_t s) {
+  return chemistry_launch(c, 0, c.nleaf, dRates, c.nleaf, dJ, c.nleaf, ksi, uniform, maxChange, s);
+}
+
+int chemistry_run_slab(Context& c, int64_t first, int64_t count, const double* dRates, int64_t rStride, const double* dJ,
+                       int64_t jStride, const double* ksi, const double* uniform, cudaStream_t s) {
+  if (first < 0 || count < 0 || first + count > c.nleaf) return RTB200_ERR_ARG;
+  if (count == 0) return RTB200_OK;
+  return chemistry_launch(c, first, count, dRates, rStride, dJ, jStride, ksi, uniform, nullptr, s);
+}
+
+static int chemistry_launch(Context& c, int64_t first, int64_t count, const double* dRates, int64_t rStride,
+                            const double* dJ, int64_t jStride, const double* ksi, const double* uniform,
+                            double* maxChange, cudaStream_t s) {
   if (c.nleaf == 0 || !c.dRho || !c.dChemK || !c.dLogT) return RTB200_ERR_ARG;
   if (dJ && !ksi) return RTB200_ERR_ARG;
   if (!dJ && !uniform) return RTB200_ERR_ARG;
   RTB_CUDA(cudaSetDevice(c.device));
   ChemParams P{};
+  P.first = first; P.count = count; P.rStride = rStride; P.jStride = jStride;
   P.level = c.dLevel; P.rho = c.dRho; P.logT = c.dLogT; P.HI = c.dHI; P.HeI = c.dHeI; P.HeII = c.dHeII;
   P.rates = dRates; P.J = dJ; P.k = c.dChemK;
   for (int i = 0; i < 6; i++) P.ksi[i] = ksi ? ksi[i] : 0.;
@@ -179,7 +201,7 @@ int chemistry_run(Context& c, const double* dRates, const double* dJ, const doub
   unsigned long long* dMax = (unsigned long long*)(c.dErr + 8);   // the error block holds 64 bytes: [0] status, [8..9] max change
   RTB_CUDA(cudaMemsetAsync(dMax, 0, 8, s));
   P.maxChangeBits = dMax; P.err = c.dErr;
-  chemistry_kernel<<<(unsigned)((c.nleaf + 127) / 128), 128, 0, s>>>(P);
+  chemistry_kernel<<<(unsigned)((count + 127) / 128), 128, 0, s>>>(P);
   RTB_CUDA(cudaGetLastError());
   if (maxChange) {
     unsigned long long bits = 0;

@@ -129,6 +129,7 @@ struct Context {
   double boxSize = 0;
   bool uniform = true;
   std::vector<int8_t> hLevel;
+  int64_t padLeaves = 0;      // extra entries allocated behind every species array (multi-GPU: slabs of equal size)
   int8_t* dLevel = nullptr;
   double *dHI = nullptr, *dHeI = nullptr, *dHeII = nullptr, *dRho = nullptr, *dAbun2 = nullptr;
   // chemistry (solveRateEquations): rate-coefficient tables and log(tgas) per leaf
@@ -189,6 +190,13 @@ struct Context {
 };
 
 int ensure_buffer(void** p, size_t* have, size_t need);
+int context_init(Context& c, int device);
+void context_destroy(Context& c);
+int grid_set(Context& c, int nx, int64_t nleaf, const int8_t* level, const double* HI, const double* HeI, const double* HeII,
+             const double* rho, const double* abun2, double physicalBoxSize);
+int set_tuning(Context& c, const char* key, double value);
+int run_diffuse(Context& c, int nAngularLevel, const double* uvb, const double* beta, const int32_t* rays, int32_t nrays,
+                double* dJ, cudaStream_t s, int64_t* nseg);
 
 // kernels / launchers --------------------------------------------------------------------------------
 int launch_compute_opacities(Context& c, const double* beta, cudaStream_t s);
@@ -206,10 +214,41 @@ int chemistry_set_temperature(Context& c, const double* tgas);
 int compute_mass(Context& c, double* neutralHydrogenMass, double* totalHydrogenMass, cudaStream_t s);
 int chemistry_run(Context& c, const double* dRates, const double* dJ, const double* ksi, const double* uniform,
                   double* maxChange, cudaStream_t s);
+// the same pass over leaves [first, first + count) only, with the rate / J arrays given as slabs: element (field f,
+// leaf c) at rates[f * rStride + c - first] and J[g * jStride + c - first]   (multi-GPU: every rank solves its slab)
+int chemistry_run_slab(Context& c, int64_t first, int64_t count, const double* dRates, int64_t rStride, const double* dJ,
+                       int64_t jStride, const double* ksi, const double* uniform, cudaStream_t s);
 
 // point sources: dRates = device [6][nleaf] (krate24, krate25, krate26, crate24, crate25, crate26), accumulated;
 // hDiag = host [nsrc][320] (remaining[7], boundary[7], dust, pad, spectrum[300]) or NULL
 int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag, int64_t* nseg, long long* hTrace,
                 long long traceCap, long long* traceLen, double* hRawTables, cudaStream_t s);
 
+int set_math(Context& c, int mode);
+int device_error(Context& c);
+
+// ---- multi-GPU (multi.cu) -----------------------------------------------------------------------------------------
+struct Multi;
+void multi_destroy(Multi* m);
+Context& multi_primary(Multi* m);
+int multi_set_math(Multi* m, int mode);
+int multi_set_tuning(Multi* m, const char* key, double value);
+int multi_grid_set(Multi* m, int nx, int64_t nleaf, const int8_t* level, const double* HI, const double* HeI,
+                   const double* HeII, const double* rho, const double* abun2, double physicalBoxSize);
+int multi_update_species(Multi* m, const double* HI, const double* HeI, const double* HeII);
+int multi_get_species(Multi* m, double* HI, double* HeI, double* HeII);
+int multi_diffuse_host(Multi* m, int nAngularLevel, const double* uvb, const double* beta, const int32_t* rays,
+                       int32_t nrays, double* J1, double* J2, double* J3, int64_t* nseg);
+int multi_point_host(Multi* m, const PointInputs& in, double* const k[6], double* rem, double* bnd, double* dust,
+                     double* spec, int32_t* hpl, int64_t* nseg);
+int multi_chemistry_tables(Multi* m, int nratec, double logtem0, double logtem9, double dlogtem, const double* const k[6]);
+int multi_chemistry_temperature(Multi* m, const double* tgas);
+int multi_device_error(Multi* m);
+
 }  // namespace rtb
+
+// the opaque handle of the C-ABI: one context (rtb200_create) or a group of them (rtb200_create_multi / _rank)
+struct rtb200_ctx {
+  rtb::Context c;            // single-GPU handle; unused when m != nullptr
+  rtb::Multi* m = nullptr;
+};

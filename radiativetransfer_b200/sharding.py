@@ -1,14 +1,18 @@
-"""Direction sharding for the multi-GPU diffuse sweep (one process per GPU, every GPU holds the full grid).
+"""Direction sharding for the multi-GPU diffuse sweep (every GPU holds the full grid).
 
-Directions are independent, so the path shards with no data-path exchange; the per-leaf Jmean fields of the ranks
-are summed afterwards with one all-reduce.  Whole zones are kept together where possible because the uniform-grid
-kernel sweeps the directions of a zone in one pass (zone = one of the 24 index rotations,
-rotateIndicesModule.f90); the assignment is deterministic (longest-processing-time first on the exact segment
-counts), so every run sums the same partial results.
+Directions are independent, so the path shards with no data-path exchange; the per-leaf Jmean fields of the ranks are
+summed afterwards (reduce-scatter, csrc/multi.cu).  The rule lives in the library (rtb200_shard_directions, used by the
+device groups internally): whole zones are kept together where possible because the uniform-grid kernel sweeps the
+directions of a zone in one pass (zone = one of the 24 index rotations, rotateIndicesModule.f90); zones are cut until
+there are three pieces per rank, then assigned longest-processing-time-first on their segment counts (times an optional
+per-sweep-axis cost factor).  The assignment is a pure function of (world, nAngularLevel, nx, factors): every run and
+every rank computes the same shards.  This module is the Python view of it.
 """
+import ctypes as C
+
 import numpy as np
 
-from . import solver
+from . import _lib, solver
 
 
 def direction_costs(n_angular_level=3, nx=32):
@@ -23,25 +27,18 @@ def direction_costs(n_angular_level=3, nx=32):
     return zone, cost
 
 
-def shard_directions(world, n_angular_level=3, nx=32, zone=None, cost=None):
+def shard_directions(world, n_angular_level=3, nx=32, zone_cost=None):
     """list (length `world`) of int32 arrays of HEALPix pixel numbers; every direction appears exactly once."""
-    if zone is None or cost is None:
-        zone, cost = direction_costs(n_angular_level, nx)
-    nrays = zone.size
-    groups = [np.where(zone == z)[0] for z in range(1, 25)]
-    groups = [g for g in groups if g.size]
-    # split zones until there are at least 3 pieces per rank, so LPT can balance
-    while len(groups) < 3 * world and max(g.size for g in groups) > 1:
-        groups.sort(key=lambda g: -cost[g].sum())
-        g = groups.pop(0)
-        groups += [g[: g.size // 2], g[g.size // 2:]]
-    groups.sort(key=lambda g: (-cost[g].sum(), int(g[0])))
-    load = np.zeros(world)
-    out = [[] for _ in range(world)]
-    for g in groups:
-        r = int(np.argmin(load))
-        out[r].append(g)
-        load[r] += cost[g].sum()
-    shards = [np.sort(np.concatenate(o)).astype(np.int32) if o else np.zeros(0, dtype=np.int32) for o in out]
-    assert sum(s.size for s in shards) == nrays
-    return shards
+    nrays = 12 * 4 ** (n_angular_level - 1)
+    zc = None if zone_cost is None else np.ascontiguousarray(zone_cost, dtype=np.float64)
+    out = []
+    for rank in range(world):
+        r = np.zeros(nrays, dtype=np.int32)
+        n = C.c_int32(0)
+        st = _lib.lib().rtb200_shard_directions(int(world), int(n_angular_level), int(nx),
+                                                None if zc is None else zc.ctypes.data_as(C.c_void_p), rank,
+                                                r.ctypes.data_as(C.c_void_p), nrays, C.byref(n))
+        _lib.check(st, "rtb200_shard_directions")
+        out.append(r[:n.value].copy())
+    assert sum(s.size for s in out) == nrays
+    return out

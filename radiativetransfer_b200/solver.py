@@ -36,17 +36,134 @@ def patterns(n_angular_level, iray, nx):
     return out
 
 
-class Transport:
-    """One GPU's transport engine (one per process; `device` = LOCAL_RANK)."""
+def comm_unique_id():
+    """128-byte id that joins the ranks of a one-process-per-GPU device group (rank 0 creates it, the launcher
+    broadcasts it: e.g. torch.distributed.broadcast_object_list)"""
+    _preload_nccl()
+    buf = C.create_string_buffer(128)
+    _lib.check(_lib.lib().rtb200_comm_unique_id(buf), "rtb200_comm_unique_id")
+    return buf.raw
 
-    def __init__(self, device=0, math=MATH_FAST):
+
+def _preload_nccl():
+    """point the library's dlopen at the NCCL of the nvidia-nccl-cu12 wheel when no other one is configured"""
+    import os
+    if os.environ.get("RTB200_NCCL_LIB"):
+        return
+    try:
+        import nvidia.nccl as _n
+        for base in _n.__path__:
+            p = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(p):
+                os.environ["RTB200_NCCL_LIB"] = p
+                return
+    except Exception:
+        pass
+
+
+class Transport:
+    """The transport engine behind one C-ABI handle:
+        Transport(device=d)                      one GPU
+        Transport(devices=[0, 1, ...])           one process driving several GPUs (rtb200_create_multi)
+        Transport(device=d, comm=(nranks, rank, unique_id))   one process per GPU (rtb200_create_rank)
+    Device groups accept the same set_grid / update_species / diffuse / point calls; the library shards the directions
+    and sources and leaves / returns per-leaf results slab-wise (see include/rtb200.h)."""
+
+    def __init__(self, device=0, math=MATH_FAST, devices=None, comm=None):
         self.L = _lib.lib()
         h = C.c_void_p()
-        _lib.check(self.L.rtb200_create(int(device), C.byref(h)), "rtb200_create")
+        self.multi = devices is not None or comm is not None
+        if devices is not None:
+            _preload_nccl()
+            d = np.ascontiguousarray(devices, dtype=np.int32)
+            _lib.check(self.L.rtb200_create_multi(int(d.size), _ptr(d), C.byref(h)), "rtb200_create_multi")
+        elif comm is not None:
+            _preload_nccl()
+            nranks, rank, uid = comm
+            _lib.check(self.L.rtb200_create_rank(int(device), int(nranks), int(rank), uid, C.byref(h)),
+                       "rtb200_create_rank")
+        else:
+            _lib.check(self.L.rtb200_create(int(device), C.byref(h)), "rtb200_create")
         self.h = h
         self.nleaf = 0
         self.nx = 0
         self.set_math(math)
+
+    # ---- device groups -------------------------------------------------------------------------------------------
+    def info(self):
+        """dict(nranks, nlocal, first_rank, slab, reduce_mode): reduce_mode 1 = peer-memory kernel, 0 = NCCL, -1 = one GPU"""
+        a, b, c, e = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        d = C.c_int64(0)
+        _lib.check(self.L.rtb200_multi_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e)),
+                   "rtb200_multi_info")
+        return dict(nranks=a.value, nlocal=b.value, first_rank=c.value, slab=d.value, reduce_mode=e.value)
+
+    def shard(self, rank, n_angular_level=3):
+        """HEALPix pixel numbers of the directions rank `rank` sweeps"""
+        n = C.c_int32(0)
+        cap = 12 * 4 ** (n_angular_level - 1)
+        r = np.zeros(cap, dtype=np.int32)
+        _lib.check(self.L.rtb200_multi_shard(self.h, int(n_angular_level), int(rank), _ptr(r), cap, C.byref(n)),
+                   "rtb200_multi_shard")
+        return r[:n.value].copy()
+
+    def slab(self, local=0):
+        """(offset, count, J_ptr, K_ptr, R_ptr) of local device `local`: device pointers to [3][slab], [3][slab], [6][slab]"""
+        off, cnt = C.c_int64(0), C.c_int64(0)
+        J, K, R = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _lib.check(self.L.rtb200_multi_slab(self.h, int(local), C.byref(off), C.byref(cnt), C.byref(J), C.byref(K),
+                                            C.byref(R)), "rtb200_multi_slab")
+        return off.value, cnt.value, J.value, K.value, R.value
+
+    @staticmethod
+    def _streams(streams):
+        if streams is None:
+            return None, None
+        arr = (C.c_void_p * len(streams))(*[C.c_void_p(int(x)) for x in streams])
+        return arr, arr
+
+    def diffuse_resident(self, uvb, beta, ksi=None, chemistry=False, n_angular_level=3, streams=None):
+        """resident step of a device group (asynchronous): sweep + reduce-scatter [+ photo-rates] [+ chemistry on the
+        slab + all-gather]; returns this process's segment updates"""
+        uvb, beta = _f64(uvb), _f64(np.asarray(beta).reshape(9))
+        k = None if ksi is None else _f64(np.concatenate([np.ravel(x) for x in ksi]) if not isinstance(ksi, np.ndarray) else ksi)
+        nseg = C.c_int64(0)
+        keep, sp = self._streams(streams)
+        st = self.L.rtb200_multi_diffuse_resident(self.h, int(n_angular_level), _ptr(uvb), _ptr(beta), _ptr(k),
+                                                  int(bool(chemistry)), sp, C.byref(nseg))
+        _lib.check(st, "rtb200_multi_diffuse_resident")
+        return nseg.value
+
+    def point_resident(self, spectra, src_leaf, src_weight, dust_approximation=0, max_pixel_level=6, streams=None,
+                       diagnostics=False):
+        keep, sa = self._spectra_args(spectra)
+        leaf = np.ascontiguousarray(src_leaf, dtype=np.int32); wt = np.ascontiguousarray(src_weight, dtype=np.int32)
+        ns = int(leaf.size)
+        nseg = C.c_int64(0)
+        rem = bnd = dust = spec = hpl = None
+        if diagnostics:
+            rem = np.zeros((ns, 7)); bnd = np.zeros((ns, 7)); dust = np.zeros(ns); spec = np.zeros((ns, 300))
+            hpl = np.zeros(ns, dtype=np.int32)
+        keeps, sp = self._streams(streams)
+        st = self.L.rtb200_multi_point_resident(self.h, *sa, int(dust_approximation), int(max_pixel_level), ns, _ptr(leaf),
+                                                _ptr(wt), sp, _ptr(rem), _ptr(bnd), _ptr(dust), _ptr(spec), _ptr(hpl),
+                                                C.byref(nseg))
+        _lib.check(st, "rtb200_multi_point_resident")
+        if diagnostics:
+            return nseg.value, dict(ndot_remaining=rem, ndot_boundary=bnd, ndot_dust=dust, ndot_spectrum=spec,
+                                    highest_pixel_level=hpl)
+        return nseg.value
+
+    def sync(self):
+        _lib.check(self.L.rtb200_multi_sync(self.h), "rtb200_multi_sync")
+
+    def slab_get(self, local=0):
+        """host copies (offset, count, J[3, count], K[3, count], R[6, count]) of a local device's slab results"""
+        off, cnt, _, _, _ = self.slab(local)
+        slab = self.info()["slab"]
+        J, K, R = np.zeros((3, slab)), np.zeros((3, slab)), np.zeros((6, slab))
+        _lib.check(self.L.rtb200_multi_slab_get(self.h, int(local), _ptr(J), _ptr(K), _ptr(R)), "rtb200_multi_slab_get")
+        return off, cnt, J[:, :cnt].copy(), K[:, :cnt].copy(), R[:, :cnt].copy()
 
     def close(self):
         if getattr(self, "h", None):

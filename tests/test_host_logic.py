@@ -72,11 +72,18 @@ def test_sharding_partitions_all_directions(build_product):
     from radiativetransfer_b200 import sharding
     zone, cost = sharding.direction_costs(3, 16)
     for world in (1, 2, 3, 4, 8):
-        shards = sharding.shard_directions(world, zone=zone, cost=cost)
+        shards = sharding.shard_directions(world, nx=16)
         allr = np.concatenate(shards)
         assert np.array_equal(np.sort(allr), np.arange(192))
         loads = np.array([cost[s].sum() for s in shards])
         assert loads.max() / loads.mean() < 1.06, (world, loads)
+        again = sharding.shard_directions(world, nx=16)
+        assert all(np.array_equal(a, b) for a, b in zip(shards, again))       # a pure function of its arguments
+    # a cost factor for the zones sweeping along z moves directions away from the ranks that hold them
+    a = sharding.shard_directions(4, nx=16)
+    b = sharding.shard_directions(4, nx=16, zone_cost=[1.0, 1.0, 1.5])
+    assert np.array_equal(np.sort(np.concatenate(b)), np.arange(192))
+    assert any(not np.array_equal(x, y) for x, y in zip(a, b))
 
 
 def test_workload_leaf_order_matches_preorder(oracle):

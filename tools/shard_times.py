@@ -1,4 +1,5 @@
-"""times one rank's direction shard of an N-GPU run on a single GPU, for several directions-per-task settings"""
+"""times every rank's direction shard of an N-GPU run on ONE GPU (the sweep of a shard does not depend on the other
+ranks), for the zone-class cost factors of the sharding rule: python tools/shard_times.py [world] [zx zy zz]"""
 import os, sys
 import numpy as np
 import torch
@@ -7,19 +8,24 @@ import radiativetransfer_b200 as rt
 from radiativetransfer_b200 import sharding, workloads as W
 n = 256
 world = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+zc = [float(x) for x in sys.argv[2:5]] if len(sys.argv) >= 5 else None
 bg = W.uvb_background(3.0)
 g = W.uniform_grid(n, seed=1)
 t = rt.Transport(device=0)
 t.set_grid(g["nx"], g["level"], g["HI"], g["HeI"], g["HeII"], g["rho"], g["abun2"], g["box_size"])
 J = torch.zeros(3, n ** 3, dtype=torch.float64, device="cuda:0")
 s = torch.cuda.current_stream().cuda_stream
-shards = sharding.shard_directions(world, n_angular_level=3, nx=n)
-for rank in (0, world // 2, world - 1):
-    for dpt, pdl in ((0, 0), (0, 1)):
-        t.set_tuning(dirs_per_task=dpt, pdl=pdl)
-        for rep in range(3):
-            t.diffuse_device(bg["uvb"], bg["beta"], J.data_ptr(), rays=shards[rank], stream=s)
-            torch.cuda.synchronize()
-            st = t.last_stats()
-        print(f"world {world} rank {rank} ndir {len(shards[rank])} dpt {dpt} pdl {pdl}: sweep_ms {st['sweep_ms']:.3f} total_ms {st['device_ms']:.3f} launches {st['launches']}", flush=True)
+shards = sharding.shard_directions(world, n_angular_level=3, nx=n, zone_cost=zc)
+zone, cost = sharding.direction_costs(3, 64)
+times = []
+for rank in range(world):
+    for rep in range(4):
+        t.diffuse_device(bg["uvb"], bg["beta"], J.data_ptr(), rays=shards[rank], stream=s)
+        torch.cuda.synchronize()
+        st = t.last_stats()
+    zs = sorted(set(int(zone[r]) for r in shards[rank]))
+    times.append(st["sweep_ms"])
+    print(f"world {world} zone_cost {zc} rank {rank} ndir {len(shards[rank])} zones {zs} segs/col {cost[shards[rank]].sum():.0f}: "
+          f"sweep_ms {st['sweep_ms']:.3f} total_ms {st['device_ms']:.3f} launches {st['launches']}", flush=True)
+print(f"world {world} zone_cost {zc}: sweep max {max(times):.3f} mean {np.mean(times):.3f} max/mean {max(times) / np.mean(times):.4f}")
 t.close()
