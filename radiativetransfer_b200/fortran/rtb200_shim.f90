@@ -10,14 +10,14 @@ module rtb200_shim
 
   implicit none
   type(c_ptr), save :: rtbContext = c_null_ptr
+  integer(c_int), save :: rtbGpus = 1          ! GPUs of this node the library drives (rtbInit); one process, one handle
   integer(c_int64_t), save :: rtbLeaves = 0
   integer(c_int8_t), dimension(:), allocatable, target, save :: flatLevel
   real(c_double), dimension(:), allocatable, target, save :: flatHI, flatHeI, flatHeII, flatRho, flatAbun2, &
        flatJ1, flatJ2, flatJ3
   integer(c_int64_t), save :: icursor
-  ! point sources: six rate fields, leaf number of the first leaf of every base cell
+  ! point sources: six rate fields
   real(c_double), dimension(:), allocatable, target, save :: flatK24, flatK25, flatK26, flatC24, flatC25, flatC26
-  integer(c_int64_t), dimension(:,:,:), allocatable, save :: baseFirstLeaf
 
   interface
      integer(c_int) function rtb200_create(device, ctx) bind(C, name='rtb200_create')
@@ -25,6 +25,14 @@ module rtb200_shim
        integer(c_int), value :: device
        type(c_ptr) :: ctx
      end function rtb200_create
+     ! one handle for `ngpus` devices of this node (devices = c_null_ptr: 0..ngpus-1); every call below accepts it and
+     ! shards the directions / sources inside the library (include/rtb200.h, "Device groups")
+     integer(c_int) function rtb200_create_multi(ngpus, devices, ctx) bind(C, name='rtb200_create_multi')
+       import :: c_int, c_ptr
+       integer(c_int), value :: ngpus
+       type(c_ptr), value :: devices
+       type(c_ptr) :: ctx
+     end function rtb200_create_multi
      integer(c_int) function rtb200_destroy(ctx) bind(C, name='rtb200_destroy')
        import :: c_int, c_ptr
        type(c_ptr), value :: ctx
@@ -80,7 +88,7 @@ module rtb200_shim
      end function rtb200_grid_get_species
      integer(c_int) function rtb200_point(ctx, nWave, wavelength, lum, metallicity, coefSpectrum, aDust, &
           dustApproximation, maxPixelLevel, nsrc, srcLeaf, srcWeight, k24, k25, k26, c24, c25, c26, &
-          ndotRemaining, ndotBoundary, ndotDust, ndotSpectrum, nseg) bind(C, name='rtb200_point')
+          ndotRemaining, ndotBoundary, ndotDust, ndotSpectrum, highestPixelLevel, nseg) bind(C, name='rtb200_point')
        import :: c_int, c_int32_t, c_ptr, c_double
        type(c_ptr), value :: ctx
        integer(c_int), value :: nWave
@@ -90,7 +98,7 @@ module rtb200_shim
        integer(c_int), value :: dustApproximation, maxPixelLevel
        integer(c_int32_t), value :: nsrc
        type(c_ptr), value :: srcLeaf, srcWeight, k24, k25, k26, c24, c25, c26
-       type(c_ptr), value :: ndotRemaining, ndotBoundary, ndotDust, ndotSpectrum, nseg
+       type(c_ptr), value :: ndotRemaining, ndotBoundary, ndotDust, ndotSpectrum, highestPixelLevel, nseg
      end function rtb200_point
   end interface
 
@@ -165,17 +173,38 @@ contains
     endif
   end subroutine scatterJ
 
+  ! optional, before rtbSetGrid: how many GPUs of this node to use (default: environment variable RTB200_GPUS, else 1).
+  ! The driver stays ONE serial process; the library opens all devices behind one handle.
+  subroutine rtbInit(ngpus)
+    integer, intent(in) :: ngpus
+    if (c_associated(rtbContext)) then
+       call rtbCheck(rtb200_destroy(rtbContext), 'rtb200_destroy')
+       rtbContext = c_null_ptr
+    endif
+    rtbGpus = int(max(1, ngpus), c_int)
+  end subroutine rtbInit
+
   ! once, after the octree is built (equiSources.f90:628) -- and again whenever its topology changes
   subroutine rtbSetGrid(nx, ny, nz)
     integer, intent(in) :: nx, ny, nz
-    integer :: i, j, k
-    integer(c_int) :: device
+    integer :: i, j, k, ios, envGpus
+    character(len=16) :: envValue
     if (nx.ne.ny .or. nx.ne.nz) then
        write(*,*) 'rtb200: cubic base grid required'
        stop
     endif
-    device = 0
-    if (.not.c_associated(rtbContext)) call rtbCheck(rtb200_create(device, rtbContext), 'rtb200_create')
+    if (.not.c_associated(rtbContext)) then
+       call get_environment_variable('RTB200_GPUS', envValue, status=ios)
+       if (ios.eq.0) then
+          read(envValue, *, iostat=ios) envGpus
+          if (ios.eq.0 .and. envGpus.ge.1) rtbGpus = int(envGpus, c_int)
+       endif
+       if (rtbGpus.gt.1) then
+          call rtbCheck(rtb200_create_multi(rtbGpus, c_null_ptr, rtbContext), 'rtb200_create_multi')
+       else
+          call rtbCheck(rtb200_create(0_c_int, rtbContext), 'rtb200_create')
+       endif
+    endif
     rtbLeaves = 0
     do i = 1, nx
        do j = 1, ny
@@ -258,32 +287,25 @@ contains
     endif
   end subroutine scatterRates
 
-  ! leaf number (0-based, writeCell order) of a star's host cell from its call sequence star%position
-  ! (equiSources.f90:753-756): leaves of the preceding base cells + leaves of the preceding siblings on every level
-  function rtbLeafOfStar(currentStar) result(leaf)
-    type(starType), intent(in) :: currentStar
-    integer(c_int64_t) :: leaf, n
-    type(zoneType), pointer :: cell
-    integer :: l, i, j, k, ii, jj, kk
-    i = currentStar%position(1); j = currentStar%position(2); k = currentStar%position(3)
-    leaf = baseFirstLeaf(i,j,k)
-    cell => baseGrid%cell(i,j,k)
-    do l = 1, currentStar%level
-       i = currentStar%position(3*l+1); j = currentStar%position(3*l+2); k = currentStar%position(3*l+3)
-       do ii = 1, 2
-          do jj = 1, 2
-             do kk = 1, 2
-                if ((ii-1)*4+(jj-1)*2+kk-1 .lt. (i-1)*4+(j-1)*2+k-1) then
-                   n = 0
-                   call countLeaves(cell%cell(ii,jj,kk), n)
-                   leaf = leaf + n
-                endif
+  ! Leaf numbers (0-based, writeCell order) of the stars' host cells in O(leaves + stars): one walk writes every
+  ! leaf's number into its krate24 field -- free at this point, setZeroRates (equiSources.f90:1246) has just cleared the
+  ! rate fields and scatterRates overwrites them below -- and star%hostCell (:753-756) reads it back.
+  recursive subroutine markLeafNumbers(currentCell)
+    type(zoneType) :: currentCell
+    integer :: i, j, k
+    if (currentCell%refined) then
+       do i = 1, 2
+          do j = 1, 2
+             do k = 1, 2
+                call markLeafNumbers(currentCell%cell(i,j,k))
              enddo
           enddo
        enddo
-       cell => cell%cell(i,j,k)
-    enddo
-  end function rtbLeafOfStar
+    else
+       currentCell%krate24 = real(icursor, kind=RealKind)   ! exact: leaf numbers are below 2**31
+       icursor = icursor + 1
+    endif
+  end subroutine markLeafNumbers
 
   ! replaces equiSources.f90:1256-1370 (runStellarTransfer block): all sources with weight > 0 in one call.
   ! iSpectrum / coefSpectrum are the driver's locals computed at :1236-1242.
@@ -291,8 +313,7 @@ contains
     integer, intent(in) :: nx, ny, nz, iSpectrum, maxPixelLevel, nStarsSpecificAge
     real(kind=RealKind), intent(in) :: coefSpectrum
     integer :: i, j, k, iStar, nsrc, iradius, im
-    integer(c_int64_t) :: n
-    integer(c_int32_t), dimension(:), allocatable, target :: srcLeaf, srcWeight
+    integer(c_int32_t), dimension(:), allocatable, target :: srcLeaf, srcWeight, highestLevel
     real(c_double), dimension(:,:), allocatable, target :: remaining, boundary, spectrum   ! (7,nsrc), (7,nsrc), (300,nsrc)
     real(c_double), dimension(:), allocatable, target :: dustEscape
     real(c_double), dimension(nWavelengths,2,nMetallicity), target :: lumPack   ! = C [5][2][nWave]
@@ -301,30 +322,30 @@ contains
     real(c_double), dimension(nMetallicity), target :: met
     real(kind=RealKind) :: ndot1, fraction(7)
 
-    if (.not.allocated(baseFirstLeaf)) then
-       allocate(baseFirstLeaf(nx,ny,nz))
-       allocate(flatK24(rtbLeaves), flatK25(rtbLeaves), flatK26(rtbLeaves), flatC24(rtbLeaves), flatC25(rtbLeaves), &
-            flatC26(rtbLeaves))
-       n = 0
-       do i = 1, nx
-          do j = 1, ny
-             do k = 1, nz
-                baseFirstLeaf(i,j,k) = n
-                call countLeaves(baseGrid%cell(i,j,k), n)
-             enddo
+    if (allocated(flatK24)) then
+       if (size(flatK24).ne.rtbLeaves) deallocate(flatK24, flatK25, flatK26, flatC24, flatC25, flatC26)
+    endif
+    if (.not.allocated(flatK24)) allocate(flatK24(rtbLeaves), flatK25(rtbLeaves), flatK26(rtbLeaves), &
+         flatC24(rtbLeaves), flatC25(rtbLeaves), flatC26(rtbLeaves))
+    icursor = 0
+    do i = 1, nx
+       do j = 1, ny
+          do k = 1, nz
+             call markLeafNumbers(baseGrid%cell(i,j,k))
           enddo
        enddo
-    endif
+    enddo
     nsrc = 0
     do iStar = 1, nStars
        if (star(iStar)%weight.gt.0) nsrc = nsrc + 1
     enddo
-    allocate(srcLeaf(nsrc), srcWeight(nsrc), remaining(7,nsrc), boundary(7,nsrc), spectrum(300,nsrc), dustEscape(nsrc))
+    allocate(srcLeaf(nsrc), srcWeight(nsrc), highestLevel(nsrc), remaining(7,nsrc), boundary(7,nsrc), &
+         spectrum(300,nsrc), dustEscape(nsrc))
     nsrc = 0
     do iStar = 1, nStars
        if (star(iStar)%weight.gt.0) then
           nsrc = nsrc + 1
-          srcLeaf(nsrc) = int(rtbLeafOfStar(star(iStar)), c_int32_t)
+          srcLeaf(nsrc) = int(star(iStar)%hostCell%krate24, c_int32_t)
           srcWeight(nsrc) = star(iStar)%weight
        endif
     enddo
@@ -351,7 +372,7 @@ contains
          real(coefSpectrum, c_double), c_loc(dustPack), int(dustApproximation, c_int), int(maxPixelLevel, c_int), &
          int(nsrc, c_int32_t), c_loc(srcLeaf), c_loc(srcWeight), c_loc(flatK24), c_loc(flatK25), c_loc(flatK26), &
          c_loc(flatC24), c_loc(flatC25), c_loc(flatC26), c_loc(remaining), c_loc(boundary), c_loc(dustEscape), &
-         c_loc(spectrum), c_null_ptr), 'rtb200_point')
+         c_loc(spectrum), c_loc(highestLevel), c_null_ptr), 'rtb200_point')
     icursor = 0
     do i = 1, nx
        do j = 1, ny
@@ -375,12 +396,15 @@ contains
              endif
           enddo
           cosmicSpectrum = cosmicSpectrum + float(star(iStar)%weight) * spectrum(:,nsrc)/(ndot1-boundary(7,nsrc))
-          write(*,1015) iStar, star(iStar)%level, fraction, star(iStar)%weight
+          ! the driver's own line and format (equiSources.f90:1353-1357)
+          write(*,1015) iStar, star(iStar)%level, &
+               star(iStar)%hostCell%HI * mh / (psi * star(iStar)%hostCell%rho), &
+               highestLevel(nsrc), fraction, star(iStar)%weight
        endif
     enddo
-1015 format('src: ', i5, i3, 7f9.5, i8)
+1015 format('src: ', i5, i3, es13.5, i3, 7f9.5, i8)
     cosmicSpectrum = cosmicSpectrum / float(nStarsSpecificAge)
-    deallocate(srcLeaf, srcWeight, remaining, boundary, spectrum, dustEscape)
+    deallocate(srcLeaf, srcWeight, highestLevel, remaining, boundary, spectrum, dustEscape)
   end subroutine rtbPoint
 
 end module rtb200_shim
