@@ -80,7 +80,7 @@ int rtb200_multi_info(rtb200_ctx* ctx, int32_t* nranks, int32_t* nlocal, int32_t
 /* the direction shard of a rank (HEALPix NESTED pixel numbers; whole zones, longest-processing-time-first on segment
  * counts x "zone_cost_x/y/z" tuning factors); host only */
 int rtb200_multi_shard(rtb200_ctx* ctx, int nAngularLevel, int rank, int32_t* rays, int32_t cap, int32_t* nrays);
-/* the same rule without a handle (zoneCost3 = NULL: 1, 1, 1): what a one-process-per-GPU caller of the single-GPU entry
+/* the same rule without a handle (zoneCost3 = NULL: the library's measured defaults): what a one-process-per-GPU caller of the single-GPU entry
  * points (rays = its shard) would use */
 int rtb200_shard_directions(int nranks, int nAngularLevel, int nx, const double* zoneCost3, int rank, int32_t* rays,
                             int32_t cap, int32_t* nrays);
@@ -112,7 +112,7 @@ int rtb200_set_math(rtb200_ctx* ctx, int math_mode);
 /* Launch tuning knobs; results do not depend on them (tests/test_diffuse_gpu.py, test_point_gpu.py).  Keys:
  *   uniform sweep  "slots" (zone tasks per launch, 0 = all), "graph" (CUDA graph replay, 1), "dense" (register cap:
  *                  0/1/2 = 2/3/4 blocks per SM, 2), "expv" (1 = table exponential), "lockstep" (one launch per layer
- *                  for all tasks, 1), "dirs_per_task" (0 = chosen from a wave model), "transpose_z" (z-major copy for
+ *                  for all tasks, 1), "dirs_per_task" (0 = chosen from a wave model), "cells" (cells of a layer per thread, 2), "transpose_z" (z-major copy for
  *                  the zones sweeping along the contiguous axis, 1), "pdl" (programmatic dependent launch of layer
  *                  l+1 on layer l, also used by the nested-grid waves, 1), "march" (experimental persistent kernel, 0; its "march_debug" switches
  *                  exist only with RTB200_EXPERIMENTAL set in the environment), "l2_mb"

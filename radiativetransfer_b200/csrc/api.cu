@@ -42,6 +42,7 @@ int ensure_buffer(void** p, size_t* have, size_t need) {
 
 static void free_grid(Context& c) {
   amr_release(c);
+  point_release(c);
   cudaFree(c.dLevel); cudaFree(c.dHI); cudaFree(c.dHeI); cudaFree(c.dHeII); cudaFree(c.dRho); cudaFree(c.dAbun2);
   cudaFree(c.dKappa); cudaFree(c.tree.child); cudaFree(c.tree.leafX); cudaFree(c.tree.leafY); cudaFree(c.tree.leafZ);
   cudaFree(c.dJ); cudaFree(c.dRates); c.dRates = nullptr;
@@ -233,6 +234,7 @@ int set_tuning(Context& c, const char* key, double value) {
   else if (k == "l2_mb") c.tune.l2BudgetMB = value;
   else if (k == "march") c.tune.march = (int)value;
   else if (k == "transpose_z") c.tune.transposeZ = (int)value;
+  else if (k == "cells") c.tune.cells = (int)value;
   else if (k == "pdl") c.tune.pdl = (int)value;
   else if (k == "dirs_per_task") c.tune.dirsPerTask = (int)value;
   else if (k == "march_debug") {

@@ -19,9 +19,16 @@
 //    the 8 directions of one leaf, and the per-item arrays are [group][leaf][8]: what a warp gathers for a leaf --
 //    neighbour records, upstream intensities -- is contiguous, and per-leaf data (opacity, pattern index) is read
 //    once per 8 lanes.  (A wave is a diagonal plane of the grid: leaf-fastest items shared no sectors at all.)
-//  * J is accumulated with fp64 atomics (several directions update a leaf concurrently), after a fixed-order
-//    shuffle sum over the 8 directions of a group; everything else is the
-//    reference's arithmetic (segment_math.cuh), incl. the coarse-neighbour averaging fallback
+//  * Per-item arrays are indexed by the leaf's POSITION IN THE WAVE ORDER ("slot"), not by its leaf number: a wave
+//    writes one contiguous stretch of neighbour records and intensities, and what it reads -- the records of its
+//    upstream leaves, which lie one to three waves back and are ordered the same way -- is close to a stream as well
+//    (leaf-indexed records put every leaf of a diagonal wave in its own 256-byte island).  Intensity records are 24
+//    bytes (three frequency groups, no pad).
+//  * J has a fixed summation order and no atomics: the 8 directions of a group are added by a butterfly, every
+//    (group, leaf) writes its sum once into a per-group array, and the groups are added to the result one after the
+//    other in group order (independent of how the groups are batched).  On grids that violate the 2:1 balance, where
+//    items may be deferred, every item stores its own contribution and the same fixed order is applied afterwards.
+//    Everything else is the reference's arithmetic (segment_math.cuh), incl. the coarse-neighbour averaging fallback
 //    (transportRoutinesModule.f90:612-634) and the intensity guard (:680-688).
 #include <algorithm>
 #include <cstdio>
@@ -38,7 +45,8 @@ struct alignas(32) DevPattern {   // subset of RayPattern the device needs, 128 
   int8_t top[3];         // xyTop, yzTop, xzTop: which ray (1 xy, 2 yz, 3 xz) leaves through the top / x=1 / y=1 face
   int8_t active[3];      // xy (always), yz, xz
   int8_t level;          // refinement level of the table
-  int8_t pad[1];
+  int8_t thin;           // an active ray is shorter than 1e-3 cell: FAST arithmetic evaluates this layer's items with the
+                         // reference's operation sequence (same rule and reason as the uniform sweep, diffuse_uniform.cu)
   double cs[3];          // FAST arithmetic: weight / (number of active rays * dpath), see amr_transport_leaf
   double pad1;
   // neighbour threading only
@@ -70,13 +78,17 @@ struct AmrParams {
   const int2* groups;      // [ngroups] (first direction of the batch, number of directions <= 8)
   int32_t* nb;             // debugging export only: [ndir][3][N] upstream leaf per ray (xy, yz, xz): -1 boundary, -2 inactive
   uint8_t* code;           // debugging export only: [ndir][3][N] what to read from the upstream leaf
-  int32_t* nbc;            // [group][N][8][4] the same packed for the sweep: leaf << 3 | code (or -1 / -2) per ray, 16 B per item
+  int32_t* nbc;            // [group][slot][8][4] the same packed for the sweep: upstream SLOT << 3 | code (or -1 / -2) per ray, 16 B per item
   const int32_t* patIdx;   // [6][N] levelOff[level] + coordinate along physical axis a (a = 0..2), then reflected (3..5)
   const double* kappaA;    // [N][6] leaf-major: opacity of the 3 groups, then 1 / max(opacity, floor) (FAST arithmetic)
-  double* JA;              // [N][3] accumulator, leaf-major (atomics), un-interleaved into J at the end
-  double* Iout;            // [group][3 rays][N][8][4]: 3 frequency groups + pad, one 32-byte sector per record
-  uint8_t* done;           // [group][N][8]
-  double* J;               // [3][N] (atomics)
+  double* JA;              // [N][3] running sum over the groups, leaf-major, un-interleaved into J at the end
+  double* JS;              // balanced grids: [group][N][4] sum over the 8 directions of a group per leaf (one sector)
+  double* JI;              // unbalanced grids: [group][slot][8][3] contribution of every item
+  double* Iout;            // [group][3 rays][slot][8][3]: the three frequency groups of a (direction, ray, leaf), 24 B
+  uint8_t* done;           // [group][slot][8]
+  const int32_t* slotOf[8];  // per reflection combination: position of every leaf in the wave order
+  const int32_t* sorted[8];  // ... and its inverse
+  double* J;               // [3][N]
   int32_t* err;
   int64_t N;
   int n, maxLevel;
@@ -102,9 +114,9 @@ __device__ __forceinline__ int node_at(const int32_t* __restrict__ child, int n,
   return node;
 }
 
-// item (direction lane of a group, leaf) -> index into the [group][N][8] arrays
-__device__ __forceinline__ int64_t item_index(const AmrParams& P, int group, int lane, int64_t leaf) {
-  return ((int64_t)group * P.N + leaf) * kGroup + lane;
+// item (direction lane of a group, slot of the leaf in the group's wave order) -> index into the [group][N][8] arrays
+__device__ __forceinline__ int64_t item_index(const AmrParams& P, int group, int lane, int64_t slot) {
+  return ((int64_t)group * P.N + slot) * kGroup + lane;
 }
 
 // block = 16 leaves x 8 direction lanes, blockIdx.y = group
@@ -185,7 +197,10 @@ __global__ void amr_neighbour_kernel(AmrParams P, int ngroups) {
       P.nb[((int64_t)d * 3 + ray) * P.N + leaf] = result;
       P.code[((int64_t)d * 3 + ray) * P.N + leaf] = code;
     }
-    if (P.nbc) P.nbc[item_index(P, gi, lane, leaf) * 4 + ray] = result >= 0 ? ((result << 3) | code) : result;
+    if (P.nbc) {
+      const int32_t* so = P.slotOf[D.combo];
+      P.nbc[item_index(P, gi, lane, so[leaf]) * 4 + ray] = result >= 0 ? ((so[result] << 3) | code) : result;
+    }
   }
 }
 
@@ -215,27 +230,53 @@ __global__ void deinterleave3_kernel(const double* __restrict__ in, double* __re
 // issued before the arithmetic starts: the packed neighbour record first, then -- independent of each other --
 // opacity, pattern and the three upstream intensities.  Iout records are 32 bytes (3 groups + pad) per (direction,
 // ray, leaf): one sector per upstream read, and only the active rays of a leaf are written.
-__device__ __forceinline__ int64_t iout_record(const AmrParams& P, int group, int lane, int ray, int64_t leaf) {
-  return ((((int64_t)group * 3 + ray) * P.N + leaf) * kGroup + lane) * 4;
+__device__ __forceinline__ int64_t iout_record(const AmrParams& P, int group, int lane, int ray, int64_t slot) {
+  return ((((int64_t)group * 3 + ray) * P.N + slot) * kGroup + lane) * 3;
 }
 
 template <bool CHECK>
 __device__ __forceinline__ void load_record(const double* p, double (&v)[3]) {
   if (CHECK) {  // possibly written by another block of this launch: read through L2
-    const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
-    v[0] = a.x; v[1] = a.y; v[2] = __ldcg(p + 2);
+    v[0] = __ldcg(p); v[1] = __ldcg(p + 1); v[2] = __ldcg(p + 2);
   } else {      // written by an earlier launch
-    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
-    v[0] = a.x; v[1] = a.y; v[2] = __ldg(p + 2);
+    v[0] = __ldg(p); v[1] = __ldg(p + 1); v[2] = __ldg(p + 2);
   }
+}
+
+// one item with the reference's operation sequence (the thin layers of FAST arithmetic), out of line
+struct ThinIn {
+  double Iin[3][3], kap[3], dpath[3], w;
+  bool active[3];
+};
+struct ThinOut {
+  double out[3][3], Jc[3];
+};
+__device__ __noinline__ ThinOut amr_item_reference_sequence(ThinIn in) {
+  ThinOut o;
+  double Jm[3] = {0., 0., 0.};
+  int imean = 0;
+  const int order[3] = {0, 2, 1};                                    // the reference processes xy, then xz, then yz
+  for (int q = 0; q < 3; q++) {
+    const int ray = order[q];
+    for (int g = 0; g < 3; g++) o.out[ray][g] = 0.;
+    if (!in.active[ray]) continue;
+    for (int g = 0; g < 3; g++) {
+      SegResult sr = segment_update<true, 0>(in.Iin[ray][g], in.kap[g], in.dpath[ray], 0., nullptr);
+      o.out[ray][g] = sr.Iout;
+      Jm[g] = __dadd_rn(Jm[g], sr.J);
+    }
+    imean++;
+  }
+  for (int g = 0; g < 3; g++) o.Jc[g] = __dmul_rn(__ddiv_rn(Jm[g], (double)imean), in.w);
+  return o;
 }
 
 // Jc = this direction's contribution to the leaf's mean intensity (the caller adds it up)
 template <bool FAITHFUL, bool CHECK>
-__device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, int gi, int lane, int64_t leaf,
+__device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, int gi, int lane, int64_t leaf, int64_t slot,
                                                    double (&Jc)[3], const double* __restrict__ sT) {
   const AmrDir& D = P.dirs[d];
-  const int64_t item = item_index(P, gi, lane, leaf);
+  const int64_t item = item_index(P, gi, lane, slot);
   int32_t nbl[3];
   int cd[3];
   {
@@ -300,6 +341,39 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
   double Jm[3] = {0., 0., 0.};
   double xy[3] = {0., 0., 0.};
   int imean = 0;
+  if (!FAITHFUL && pat.thin) {
+    // rare (0.2% of the layers): the reference's operation sequence, out of line so that it costs the common path no
+    // registers
+    ThinIn in;
+#pragma unroll
+    for (int ray = 0; ray < 3; ray++) {
+      in.dpath[ray] = dpath[ray];
+      in.active[ray] = nbl[ray] != -2;
+#pragma unroll
+      for (int g = 0; g < 3; g++) in.Iin[ray][g] = Iin[ray][g];
+    }
+#pragma unroll
+    for (int g = 0; g < 3; g++) in.kap[g] = kap[g];
+    in.w = D.w;
+    const ThinOut o = amr_item_reference_sequence(in);
+#pragma unroll
+    for (int ray = 0; ray < 3; ray++) {
+      if (nbl[ray] == -2) continue;
+      double* mine = P.Iout + iout_record(P, gi, lane, ray, slot);
+      mine[0] = o.out[ray][0]; mine[1] = o.out[ray][1]; mine[2] = o.out[ray][2];
+    }
+    if (L > 0) {
+      const double tmp = __dadd_rn(__dadd_rn(o.out[0][0], o.out[0][1]), o.out[0][2]);
+      if (!(tmp < 1.e-20 && tmp > -1.e-20)) atomicMax(P.err, RTB200_ERR_INTENSITY_GUARD);
+    }
+#pragma unroll
+    for (int g = 0; g < 3; g++) Jc[g] = o.Jc[g];
+    if (CHECK) {
+      __threadfence();
+      ((volatile uint8_t*)P.done)[item] = 1;
+    }
+    return true;
+  }
   if (!FAITHFUL) {
 #pragma unroll
     for (int g = 0; g < 3; g++) kap[g] = kap[g] > 0. ? kap[g] : kAmrKappaFloor;
@@ -325,9 +399,8 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
     }
     if (ray == 0) { xy[0] = out[0]; xy[1] = out[1]; xy[2] = out[2]; }
     imean++;
-    double* mine = P.Iout + iout_record(P, gi, lane, ray, leaf);
-    *reinterpret_cast<double2*>(mine) = make_double2(out[0], out[1]);
-    mine[2] = out[2];
+    double* mine = P.Iout + iout_record(P, gi, lane, ray, slot);
+    mine[0] = out[0]; mine[1] = out[1]; mine[2] = out[2];
   }
   if (L > 0) {  // refined path only: guard on the xy ray's sum (transportRoutinesModule.f90:680,803,926)
     const double tmp = __dadd_rn(__dadd_rn(xy[0], xy[1]), xy[2]);
@@ -368,25 +441,39 @@ __global__ void __launch_bounds__(128, 8) amr_wave_kernel(AmrParams P, WaveParam
   const bool mine = have && lane < grp.y;
   double Jc[3] = {0., 0., 0.};
   int64_t leaf = 0;
-  if (have) leaf = Wp.sorted[combo][Wp.begin[combo] + i];
+  const int64_t slot = Wp.begin[combo] + i;
+  if (have) leaf = Wp.sorted[combo][slot];
+  bool deferred = false;
   if (mine) {
     const int d = grp.x + lane;
-    if (!amr_transport_leaf<FAITHFUL, CHECK>(P, d, gi, lane, leaf, Jc, sT)) {
-      Jc[0] = Jc[1] = Jc[2] = 0.;
-      int slot = atomicAdd(Wp.deferredCount, 1);
-      if (slot < Wp.deferredCap) Wp.deferred[slot] = ((int64_t)d << 32) | leaf;
+    if (!amr_transport_leaf<FAITHFUL, CHECK>(P, d, gi, lane, leaf, slot, Jc, sT)) {
+      deferred = true;
+      int q = atomicAdd(Wp.deferredCount, 1);
+      if (q < Wp.deferredCap) Wp.deferred[q] = ((int64_t)d << 32) | slot;
       else atomicMax(P.err, RTB200_ERR_NOMEM);
     }
   }
-  asm volatile("griddepcontrol.wait;" ::: "memory");               // lanes that had no item: before the atomics
-  // the 8 directions of the leaf: butterfly sum (fixed order), one atomic per frequency group
+  if (CHECK) {
+    // items may finish later (retry kernel): every item keeps its own contribution, added up in fixed order afterwards
+    if (have && !deferred) {
+      double* q = P.JI + item_index(P, gi, lane, slot) * 3;
+      q[0] = Jc[0]; q[1] = Jc[1]; q[2] = Jc[2];                     // lanes without a direction store zeros
+    }
+    return;
+  }
+  // the 8 directions of the leaf: butterfly sum (fixed order), one store per (group, leaf)
+  double v[3];
 #pragma unroll
   for (int g = 0; g < 3; g++) {
-    double v = Jc[g];
-    v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 1));
-    v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 2));
-    v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
-    if (have && lane == 0) atomicAdd(P.JA + leaf * 3 + g, v);
+    v[g] = Jc[g];
+    v[g] = __dadd_rn(v[g], __shfl_xor_sync(0xffffffffu, v[g], 1));
+    v[g] = __dadd_rn(v[g], __shfl_xor_sync(0xffffffffu, v[g], 2));
+    v[g] = __dadd_rn(v[g], __shfl_xor_sync(0xffffffffu, v[g], 4));
+  }
+  if (have && lane == 0) {
+    double* q = P.JS + ((int64_t)gi * P.N + leaf) * 4;
+    *reinterpret_cast<double2*>(q) = make_double2(v[0], v[1]);
+    q[2] = v[2];
   }
 }
 
@@ -402,15 +489,43 @@ __global__ void amr_retry_kernel(AmrParams P, const int64_t* in, const int32_t* 
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int64_t item = in[i];
     const int d = (int)(item >> 32);
-    const int64_t leaf = item & 0xffffffffLL;
+    const int64_t slot = item & 0xffffffffLL;
+    const int64_t leaf = P.sorted[P.dirs[d].combo][slot];
     double Jc[3];
-    if (!amr_transport_leaf<FAITHFUL, true>(P, d, P.dirs[d].group, P.dirs[d].lane, leaf, Jc, sT)) {
-      int slot = atomicAdd(outCount, 1);
-      if (slot < cap) out[slot] = item;
+    if (!amr_transport_leaf<FAITHFUL, true>(P, d, P.dirs[d].group, P.dirs[d].lane, leaf, slot, Jc, sT)) {
+      int q = atomicAdd(outCount, 1);
+      if (q < cap) out[q] = item;
     } else {
-#pragma unroll
-      for (int g = 0; g < 3; g++) atomicAdd(P.JA + leaf * 3 + g, Jc[g]);
+      double* q = P.JI + item_index(P, P.dirs[d].group, P.dirs[d].lane, slot) * 3;
+      q[0] = Jc[0]; q[1] = Jc[1]; q[2] = Jc[2];
     }
+  }
+}
+
+// JA[leaf] += the batch's groups, one after the other in group order (thread = leaf): the summation order of a leaf is
+// group 0, 1, 2, ... of the whole call whatever the batching.  ITEMS: the per-item contributions of the unbalanced
+// path, the 8 lanes added in the butterfly's order ((0+1)+(2+3))+((4+5)+(6+7)).
+template <bool ITEMS>
+__global__ void amr_merge_kernel(AmrParams P, int ngroups) {
+  for (int64_t leaf = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; leaf < P.N; leaf += (int64_t)gridDim.x * blockDim.x) {
+    double s[3] = {P.JA[leaf * 3], P.JA[leaf * 3 + 1], P.JA[leaf * 3 + 2]};
+    for (int gi = 0; gi < ngroups; gi++) {
+      if (ITEMS) {
+        const int combo = P.dirs[P.groups[gi].x].combo;
+        const double* q = P.JI + item_index(P, gi, 0, P.slotOf[combo][leaf]) * 3;
+#pragma unroll
+        for (int g = 0; g < 3; g++) {
+          const double a = __dadd_rn(__dadd_rn(q[g], q[3 + g]), __dadd_rn(q[6 + g], q[9 + g]));
+          const double b = __dadd_rn(__dadd_rn(q[12 + g], q[15 + g]), __dadd_rn(q[18 + g], q[21 + g]));
+          s[g] = __dadd_rn(s[g], __dadd_rn(a, b));
+        }
+      } else {
+        const double* q = P.JS + ((int64_t)gi * P.N + leaf) * 4;
+        const double2 ab = *reinterpret_cast<const double2*>(q);
+        s[0] = __dadd_rn(s[0], ab.x); s[1] = __dadd_rn(s[1], ab.y); s[2] = __dadd_rn(s[2], q[2]);
+      }
+    }
+    P.JA[leaf * 3] = s[0]; P.JA[leaf * 3 + 1] = s[1]; P.JA[leaf * 3 + 2] = s[2];
   }
 }
 
@@ -429,6 +544,8 @@ static DevPattern to_dev(const RayPattern& p, double cellSize, int level, double
   q.top[0] = p.xyTop; q.top[1] = p.yzTop; q.top[2] = p.xzTop;
   q.active[0] = 1; q.active[1] = p.yzActive; q.active[2] = p.xzActive;
   const int nseg = 1 + (p.yzActive ? 1 : 0) + (p.xzActive ? 1 : 0);
+  for (int r = 0; r < 3; r++)
+    if (q.active[r] && len[r] < 1e-3) q.thin = 1;
   for (int r = 0; r < 3; r++) q.cs[r] = q.active[r] && q.dpath[r] > 0. ? weight / ((double)nseg * q.dpath[r]) : 0.;
   return q;
 }
@@ -439,6 +556,7 @@ struct AmrPlan {
   std::vector<int32_t> waveStart[8];  // [nkeys + 1]
   int nkeys = 0;
   int32_t* dSorted[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int32_t* dSlotOf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // inverse of dSorted
   int32_t* dPatIdx = nullptr;         // [6][N], see AmrParams
 };
 
@@ -517,6 +635,8 @@ struct AmrBuffers {
   int32_t* nbc = nullptr;
   double* kappaA = nullptr;
   double* JA = nullptr;
+  double* JS = nullptr;
+  double* JI = nullptr;
   double* Iout = nullptr;
   uint8_t* done = nullptr;
   int64_t* defA = nullptr;
@@ -527,7 +647,7 @@ struct AmrBuffers {
   std::string nbKey;              // grid + direction list whose neighbour tables (nb, code, nbc) the buffers hold
   void release() {
     cudaFree(pats); cudaFree(dirs); cudaFree(groups); cudaFree(levelOff); cudaFree(nb); cudaFree(code); cudaFree(Iout); cudaFree(done);
-    cudaFree(nbc); cudaFree(kappaA); cudaFree(JA);
+    cudaFree(nbc); cudaFree(kappaA); cudaFree(JA); cudaFree(JS); cudaFree(JI);
     cudaFree(defA); cudaFree(defB); cudaFree(defCount);
     *this = AmrBuffers();
   }
@@ -548,7 +668,7 @@ static AmrState* state_of(Context& c) {
 void amr_release(Context& c) {
   AmrState* S = static_cast<AmrState*>(c.amrState);
   if (!S) return;
-  for (int k = 0; k < 8; k++) cudaFree(S->plan.dSorted[k]);
+  for (int k = 0; k < 8; k++) { cudaFree(S->plan.dSorted[k]); cudaFree(S->plan.dSlotOf[k]); }
   cudaFree(S->plan.dPatIdx);
   S->buffers.release();
   delete S;
@@ -559,7 +679,10 @@ static int ensure_plan(Context& c, AmrState& S) {
   char buf[64];
   snprintf(buf, sizeof(buf), "%p:%lld:%d", (void*)c.tree.child, (long long)c.nleaf, c.maxLevel);
   if (S.key == buf) return RTB200_OK;
-  for (int k = 0; k < 8; k++) { cudaFree(S.plan.dSorted[k]); S.plan.dSorted[k] = nullptr; }
+  for (int k = 0; k < 8; k++) {
+    cudaFree(S.plan.dSorted[k]); S.plan.dSorted[k] = nullptr;
+    cudaFree(S.plan.dSlotOf[k]); S.plan.dSlotOf[k] = nullptr;
+  }
   build_waves(c, S.plan);
   S.plan.balanced = grid_is_balanced(c);
   S.tablesKey.clear();
@@ -579,9 +702,13 @@ static int ensure_plan(Context& c, AmrState& S) {
     RTB_CUDA(cudaMalloc((void**)&S.plan.dPatIdx, idx.size() * sizeof(int32_t)));
     RTB_CUDA(cudaMemcpy(S.plan.dPatIdx, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
+  std::vector<int32_t> inv((size_t)c.nleaf);
   for (int k = 0; k < 8; k++) {
     RTB_CUDA(cudaMalloc((void**)&S.plan.dSorted[k], (size_t)c.nleaf * sizeof(int32_t)));
     RTB_CUDA(cudaMemcpy(S.plan.dSorted[k], S.plan.sorted[k].data(), (size_t)c.nleaf * sizeof(int32_t), cudaMemcpyHostToDevice));
+    for (int64_t q = 0; q < c.nleaf; q++) inv[(size_t)S.plan.sorted[k][(size_t)q]] = (int32_t)q;
+    RTB_CUDA(cudaMalloc((void**)&S.plan.dSlotOf[k], (size_t)c.nleaf * sizeof(int32_t)));
+    RTB_CUDA(cudaMemcpy(S.plan.dSlotOf[k], inv.data(), (size_t)c.nleaf * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
   S.key = buf;
   return RTB200_OK;
@@ -653,7 +780,8 @@ static int build_dir_tables(Context& c, int nAngularLevel, const std::vector<Dir
 }
 
 // ngroups groups of kGroup item lanes each; debugNb: also the per-direction nb / code arrays of the debugging export
-static int alloc_batch(AmrBuffers& B, const DirTables& T, int64_t N, int ngroups, int64_t defCap, bool debugNb) {
+static int alloc_batch(AmrBuffers& B, const DirTables& T, int64_t N, int ngroups, int64_t defCap, bool debugNb,
+                       bool balanced) {
   const size_t slots = (size_t)ngroups * kGroup;
   RTB_CUDA(cudaMalloc((void**)&B.pats, (size_t)T.perDir * slots * sizeof(DevPattern)));
   RTB_CUDA(cudaMalloc((void**)&B.dirs, slots * sizeof(AmrDir)));
@@ -667,7 +795,9 @@ static int alloc_batch(AmrBuffers& B, const DirTables& T, int64_t N, int ngroups
   RTB_CUDA(cudaMalloc((void**)&B.nbc, slots * 4 * N * sizeof(int32_t)));
   RTB_CUDA(cudaMalloc((void**)&B.kappaA, (size_t)6 * N * sizeof(double)));
   RTB_CUDA(cudaMalloc((void**)&B.JA, (size_t)3 * N * sizeof(double)));
-  RTB_CUDA(cudaMalloc((void**)&B.Iout, slots * N * 12 * sizeof(double)));
+  if (balanced) RTB_CUDA(cudaMalloc((void**)&B.JS, (size_t)ngroups * N * 4 * sizeof(double)));
+  else RTB_CUDA(cudaMalloc((void**)&B.JI, slots * N * 3 * sizeof(double)));
+  RTB_CUDA(cudaMalloc((void**)&B.Iout, slots * N * 9 * sizeof(double)));
   RTB_CUDA(cudaMalloc((void**)&B.done, slots * N));
   RTB_CUDA(cudaMalloc((void**)&B.defA, (size_t)defCap * sizeof(int64_t)));
   RTB_CUDA(cudaMalloc((void**)&B.defB, (size_t)defCap * sizeof(int64_t)));
@@ -679,7 +809,7 @@ static int alloc_batch(AmrBuffers& B, const DirTables& T, int64_t N, int ngroups
 static int choose_batch(Context& c, int ngroups) {
   size_t freeB = 0, totalB = 0;
   cudaMemGetInfo(&freeB, &totalB);
-  const double perGroup = (double)kGroup * ((double)c.nleaf * (12 * 8 + 16 + 1) + 1e6);
+  const double perGroup = (double)kGroup * ((double)c.nleaf * (9 * 8 + 16 + 1 + 24) + 1e6);
   int nb = (int)std::max(1.0, std::min((double)ngroups, 0.5 * (double)freeB / perGroup));
   if (c.tune.amrBatch > 0) nb = std::min(nb, std::max(1, c.tune.amrBatch / kGroup));   // the knob counts directions
   return nb;
@@ -715,7 +845,8 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int g0, int ng
   P.kappa = c.dKappa; P.pats = B.pats; P.levelOff = B.levelOff; P.dirs = B.dirs; P.nb = nullptr; P.code = nullptr;
   P.groups = B.groups;
   P.Iout = B.Iout; P.done = B.done; P.J = dJ; P.err = c.dErr; P.N = N; P.n = c.nx; P.maxLevel = c.maxLevel;
-  P.nbc = B.nbc; P.patIdx = S.plan.dPatIdx; P.kappaA = B.kappaA; P.JA = B.JA;
+  P.nbc = B.nbc; P.patIdx = S.plan.dPatIdx; P.kappaA = B.kappaA; P.JA = B.JA; P.JS = B.JS; P.JI = B.JI;
+  for (int k = 0; k < 8; k++) { P.slotOf[k] = S.plan.dSlotOf[k]; P.sorted[k] = S.plan.dSorted[k]; }
   P.u0 = uvb[0]; P.u1 = uvb[1]; P.u2 = uvb[2];
   P.cellSize0 = c.boxSize / (double)c.nx;  // equiSources.f90:1570
   // neighbour threading is geometry only (grid + directions): when one batch holds every direction of the call, the
@@ -788,6 +919,12 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int g0, int ng
     cur ^= 1;
     if (iter == 99999) return RTB200_ERR_ARG;
   }
+  {
+    const int blocks = (int)std::min<int64_t>((N + 127) / 128, (int64_t)c.smCount * 16);
+    if (S.plan.balanced) amr_merge_kernel<false><<<blocks, 128, 0, s>>>(P, ng);
+    else amr_merge_kernel<true><<<blocks, 128, 0, s>>>(P, ng);
+    (*launches)++;
+  }
   RTB_CUDA(cudaGetLastError());
   return RTB200_OK;
 }
@@ -828,7 +965,7 @@ int diffuse_amr(Context& c, int nAngularLevel, const double* uvb, const std::vec
     snprintf(buf, sizeof(buf), "%d:%lld:%d:%lld", T.perDir, (long long)N, batch, (long long)defCap);
     if (B.sizeKey != buf) {
       B.release();
-      st = alloc_batch(B, T, N, batch, defCap, false);  // (release() also forgets the cached neighbour tables)
+      st = alloc_batch(B, T, N, batch, defCap, false, S.plan.balanced);  // (release() also forgets the cached neighbour tables)
       if (st) B.release();
       else { B.sizeKey = buf; B.batch = batch; B.batchNdir = ndir; }
     }
@@ -906,7 +1043,7 @@ int amr_neighbours(Context& c, const Direction& d, int32_t* nbHost) {
   DirTables T;
   if (int st = build_dir_tables(c, 3, one, T)) return st;
   AmrBuffers B;
-  if (int st = alloc_batch(B, T, N, 1, 16, true)) { B.release(); return st; }
+  if (int st = alloc_batch(B, T, N, 1, 16, true, true)) { B.release(); return st; }
   cudaStream_t s = c.stream;
   RTB_CUDA(cudaMemcpyAsync(B.pats, T.pats.data(), T.pats.size() * sizeof(DevPattern), cudaMemcpyHostToDevice, s));
   T.dirs[0].group = 0; T.dirs[0].lane = 0;

@@ -329,6 +329,161 @@ sweep_cell_kernel(const __grid_constant__ BatchParams bp, int N, int n, int np1,
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Two cells per thread (FAST arithmetic; set_tuning "cells" = 2, the default): a thread owns the cells (a, b0) and
+// (a, b0 + 1) of the layer, b0 even.  What the upper cell needs from the row below it -- the previous layer's plane
+// value of (a, b0) and the intensity the lower cell hands over along the row axis -- is already in the thread's
+// registers: no recomputed (b-1) segment and no second plane load for the upper cell, and the per-direction
+// bookkeeping (table reads, kind dispatch, pointer updates, prefetches) is paid once per two cells.  The arithmetic
+// of every cell is unchanged: the handed-over value is bit for bit what the single-cell kernel recomputes.
+//   r01 ncu of the single-cell kernel: 318 warp instructions per direction, 194 of them not FP64 (issue-bound).
+// ---------------------------------------------------------------------------------------------------------
+template <int EXPV, int NSEG, bool SECL, bool GUARD>
+__device__ __forceinline__ void direction_fast2(const LayerSeg& P, const double (&cur0)[3], const double (&cur1)[3],
+                                                const double (&upR)[3], const double (&kap0)[3], const double (&kap1)[3],
+                                                const double (&kR)[3], double (&I0)[3], double (&I1)[3], double (&A0)[3],
+                                                double (&A1)[3], const double* __restrict__ T) {
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int g = 0; g < 3; g++) {
+    const double a1 = segment_fast<EXPV, GUARD>(cur0[g], kap0[g] * P.d[0], P.cs[0], T, A0[g]);
+    const double b1 = segment_fast<EXPV, GUARD>(cur1[g], kap1[g] * P.d[0], P.cs[0], T, A1[g]);
+    I0[g] = a1; I1[g] = b1;
+    if (NSEG >= 2) {
+      double rup = 0.;  // xy-segment output of the (b0 - 1) cell, recomputed (lower cell only)
+      if (!SECL || NSEG == 3) rup = attenuate_fast<EXPV, GUARD>(upR[g], kR[g] * P.d[0], T);
+      const double a_in2 = SECL ? __shfl_up_sync(full, a1, 1) : rup;
+      const double b_in2 = SECL ? __shfl_up_sync(full, b1, 1) : a1;   // the lower cell's own xy output
+      const double a2 = segment_fast<EXPV, GUARD>(a_in2, kap0[g] * P.d[1], P.cs[1], T, A0[g]);
+      const double b2 = segment_fast<EXPV, GUARD>(b_in2, kap1[g] * P.d[1], P.cs[1], T, A1[g]);
+      I0[g] = a2; I1[g] = b2;
+      if (NSEG == 3) {
+        double a_in3, b_in3;
+        if (SECL) {
+          const double x = __shfl_up_sync(full, rup, 1);
+          a_in3 = attenuate_fast<EXPV, GUARD>(x, kR[g] * P.d[1], T);
+          b_in3 = a2;                                                 // the lower cell's second segment
+        } else {
+          a_in3 = __shfl_up_sync(full, a2, 1);
+          b_in3 = __shfl_up_sync(full, b2, 1);
+        }
+        I0[g] = segment_fast<EXPV, GUARD>(a_in3, kap0[g] * P.d[2], P.cs[2], T, A0[g]);
+        I1[g] = segment_fast<EXPV, GUARD>(b_in3, kap1[g] * P.d[2], P.cs[2], T, A1[g]);
+      }
+    }
+  }
+}
+
+template <int EXPV, bool GUARD>
+__device__ __forceinline__ void direction_kinds_fast2(const LayerSeg& P, bool secL, const double (&cur0)[3],
+                                                      const double (&cur1)[3], const double (&upR)[3],
+                                                      const double (&kap0)[3], const double (&kap1)[3],
+                                                      const double (&kR)[3], double (&I0)[3], double (&I1)[3],
+                                                      double (&A0)[3], double (&A1)[3], const double* __restrict__ T) {
+  const int kind = P.kind;
+  if (kind == 0) direction_fast2<EXPV, 1, true, GUARD>(P, cur0, cur1, upR, kap0, kap1, kR, I0, I1, A0, A1, T);
+  else if (kind == 1 || kind == 3) {
+    if (secL) direction_fast2<EXPV, 2, true, GUARD>(P, cur0, cur1, upR, kap0, kap1, kR, I0, I1, A0, A1, T);
+    else direction_fast2<EXPV, 2, false, GUARD>(P, cur0, cur1, upR, kap0, kap1, kR, I0, I1, A0, A1, T);
+  } else {
+    if (secL) direction_fast2<EXPV, 3, true, GUARD>(P, cur0, cur1, upR, kap0, kap1, kR, I0, I1, A0, A1, T);
+    else direction_fast2<EXPV, 3, false, GUARD>(P, cur0, cur1, upR, kap0, kap1, kR, I0, I1, A0, A1, T);
+  }
+}
+
+// block = 8 warps; a warp covers 31 cells (+ the recomputed halo cell in lane 0) of TWO rows
+template <int EXPV, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+sweep_cell2_kernel(const __grid_constant__ BatchParams bp, int N, int n, int np1, int npl3) {
+  const StepParams& sp = bp.t[blockIdx.z];
+  const double* __restrict__ kappa = sp.kappa;
+  __shared__ double sT[16];
+  asm volatile("griddepcontrol.launch_dependents;");
+  if (threadIdx.y == 0 && threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
+  __syncthreads();
+  const int a = blockIdx.x * 31 - 1 + (int)threadIdx.x, b0 = 2 * (blockIdx.y * 8 + threadIdx.y);
+  if (b0 >= n) return;                                         // warp-uniform
+  const bool row1 = b0 + 1 < n;                                // warp-uniform: the upper row exists
+  const bool inRow = a < n;
+  const bool writer0 = inRow && threadIdx.x >= 1, writer1 = writer0 && row1;
+  const bool cell0 = inRow && a >= 0, cell1 = cell0 && row1;
+  const int laneIsK = sp.laneIsK;
+  const int sA = laneIsK ? sp.sk : sp.sj, sB = laneIsK ? sp.sj : sp.sk;
+  const int leaf0 = sp.origin + a * sA + b0 * sB;
+  double kap0[3], kap1[3], kF0[3], kF1[3], kR[3];
+#pragma unroll
+  for (int g = 0; g < 3; g++) {
+    const double* kg = kappa + (int64_t)g * N + leaf0;
+    kF0[g] = cell0 ? kg[0] : 0.;
+    kF1[g] = cell1 ? kg[sB] : 0.;
+    kR[g] = (cell0 && b0 > 0) ? kg[-sB] : 0.;                  // kappa = 0 outside: exp(-0) = 1 exactly
+    kap0[g] = kF0[g] > 0. ? kF0[g] : kKappaFloor;
+    kap1[g] = kF1[g] > 0. ? kF1[g] : kKappaFloor;
+  }
+  const double kmax = fmax(fmax(fmax(fmax(kap0[0], kap0[1]), fmax(kap0[2], kR[0])), fmax(kR[1], kR[2])),
+                           fmax(fmax(kap1[0], kap1[1]), kap1[2]));
+  double A0[3] = {0., 0., 0.}, A1[3] = {0., 0., 0.}, acc0[3] = {0., 0., 0.}, acc1[3] = {0., 0., 0.};
+  const int pidx = (b0 + 1) * np1 + (inRow ? a + 1 : 0);
+  const int ndir = sp.ndir;
+  const int dstride = npl3;
+  const int up = 3 * np1;                                      // one row up in the plane
+  const int up1 = row1 ? up : 0;                               // the upper row's plane values (stay in bounds without it)
+  const double* pin = sp.planeIn + 3 * pidx;
+  double* pout = sp.planeOut + 3 * pidx;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  for (int q = 0; q < ndir; q++, pin += dstride, pout += dstride) {
+    const LayerSeg& P = sp.P[q];
+    const int kind = P.kind;
+    if (q + 1 < ndir) {
+      prefetch_l1(pin + dstride);
+      prefetch_l1(pin + dstride + up1);
+      prefetch_l1(pin + dstride - up);
+    }
+    double cur0[3], cur1[3], upR[3] = {0., 0., 0.}, I0[3], I1[3];
+#pragma unroll
+    for (int g = 0; g < 3; g++) { cur0[g] = pin[g]; cur1[g] = pin[g + up1]; }
+    const bool secL = (kind <= 2) == (laneIsK != 0);
+    if (kind == 2 || kind == 4 || (kind != 0 && !secL)) {
+#pragma unroll
+      for (int g = 0; g < 3; g++) upR[g] = pin[g - up];
+    }
+    if (P.thin) {
+      // rare (0.2% of the direction-layers): the reference's operation sequence, cell by cell; the upper cell takes
+      // the lower one as its (b-1) cell exactly as the single-cell kernel does
+      direction_dispatch_faithful(P, secL, cur0, upR, kF0, kR, I0, acc0);
+      direction_dispatch_faithful(P, secL, cur1, cur0, kF1, kF0, I1, acc1);
+    } else if (__any_sync(0xffffffffu, kmax * P.dmax > 64.)) {
+      direction_kinds_fast2<EXPV, true>(P, secL, cur0, cur1, upR, kap0, kap1, kR, I0, I1, A0, A1, sT);
+    } else {
+      direction_kinds_fast2<EXPV, false>(P, secL, cur0, cur1, upR, kap0, kap1, kR, I0, I1, A0, A1, sT);
+    }
+    if (writer0) {
+#pragma unroll
+      for (int g = 0; g < 3; g++) pout[g] = I0[g];
+    }
+    if (writer1) {
+#pragma unroll
+      for (int g = 0; g < 3; g++) pout[g + up] = I1[g];
+    }
+  }
+  if (writer0) {
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      const double v = fma(A0[g], kTwoM200 / kap0[g], acc0[g]);
+      double* p = sp.acc + (int64_t)g * N + leaf0;
+      *p = sp.firstInSlot ? v : __dadd_rn(*p, v);
+    }
+  }
+  if (writer1) {
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      const double v = fma(A1[g], kTwoM200 / kap1[g], acc1[g]);
+      double* p = sp.acc + (int64_t)g * N + leaf0 + sB;
+      *p = sp.firstInSlot ? v : __dadd_rn(*p, v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Persistent layer-marching kernel
 //
 // The per-layer launches above stream every direction's top-exit plane through HBM twice per layer (read + write):
@@ -677,9 +832,17 @@ static cudaError_t launch_layer(Kernel kern, dim3 grid, cudaStream_t s, bool pdl
 // `pdl`: programmatic dependent launch on the previous launch of the stream (only for a layer whose predecessor in
 // the stream is the previous layer's sweep kernel)
 static cudaError_t launch_cells(int dense, int expv, bool faithful, bool pdl, dim3 grid, cudaStream_t s,
-                                const BatchParams& bp, int N, int n) {
+                                const BatchParams& bp, int N, int n, int cells) {
   // `dense`: 0 = compiler's choice of registers (2 blocks per SM), 1 = cap for 3 blocks, 2 = cap for 4 blocks
   if (faithful) return launch_layer(sweep_cell_kernel<true, 0, 2>, grid, s, pdl, bp, N, n);
+  if (cells == 2 && expv == 1) {   // two cells per thread: half the rows per block
+    grid.y = (unsigned)((n + 15) / 16);
+    // register budget: default 2 blocks of 256 threads per SM (119 registers, no spills; as many cells in flight as
+    // the single-cell kernel at 4 blocks); "dense" 3 / 4 cap the registers for 3 / 4 blocks
+    if (dense >= 4) return launch_layer(sweep_cell2_kernel<1, 4>, grid, s, pdl, bp, N, n);
+    if (dense == 3) return launch_layer(sweep_cell2_kernel<1, 3>, grid, s, pdl, bp, N, n);
+    return launch_layer(sweep_cell2_kernel<1, 2>, grid, s, pdl, bp, N, n);
+  }
 #define RTB_LAUNCH(E)                                                                             \
   if (dense == 1) return launch_layer(sweep_cell_kernel<false, E, 3>, grid, s, pdl, bp, N, n);    \
   else if (dense >= 2) return launch_layer(sweep_cell_kernel<false, E, 4>, grid, s, pdl, bp, N, n); \
@@ -975,7 +1138,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
           }
           dim3 gz = grid;
           gz.z = nb;
-          RTB_CUDA(launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, c.tune.pdl && step > 0, gz, st, bp, (int)N, n));
+          RTB_CUDA(launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, c.tune.pdl && step > 0, gz, st, bp, (int)N, n, c.tune.cells));
           nLaunched++;
         }
       }
@@ -990,7 +1153,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
         if (T.slot != k) continue;
         for (int step = 0; step < n; step++) {
           fill(bp.t[0], T, step, T.firstInSlot);
-          RTB_CUDA(launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, c.tune.pdl && step > 0, grid, cs, bp, (int)N, n));
+          RTB_CUDA(launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, c.tune.pdl && step > 0, grid, cs, bp, (int)N, n, c.tune.cells));
           nLaunched++;
         }
       }
@@ -1006,7 +1169,8 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
     // The launch sequence depends only on the plan, the mode and the buffers: capture once, replay afterwards.
     char key[256];
     snprintf(key, sizeof(key), "u:%d:%d:%d:%d:%p:%p:%p:%a:%a:%a", n, ntask, slots,
-             (int)faithful * 64 + c.tune.minBlocks * 4 + c.tune.expVariant + 1000 * c.tune.lockstep + 10000 * c.tune.pdl,
+             (int)faithful * 64 + c.tune.minBlocks * 4 + c.tune.expVariant + 1000 * c.tune.lockstep + 10000 * c.tune.pdl +
+                 100000 * c.tune.cells,
              (void*)c.dAcc, (void*)c.dPlanes, (void*)c.dKappa, uvb[0], uvb[1], uvb[2]);
     if (!c.graphExec || c.graphKey != key) {
       if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }

@@ -106,6 +106,7 @@ int nccl_load() {
   } while (0)
 
 constexpr int kMaxRanks = 16;
+constexpr double kZoneCostX = 1.0, kZoneCostY = 1.03, kZoneCostZ = 1.10;
 
 // ---- peer-memory reduce-scatter with fused epilogue -------------------------------------------------------------------
 struct PeerReduceParams {
@@ -285,7 +286,9 @@ struct Multi {
   // direction shards of the last (nAngularLevel, ray list, nx): cached
   std::string shardKey;
   std::vector<std::vector<int32_t>> shards;
-  double zoneClassCost[3] = {1.0, 1.0, 1.0};   // relative time per segment of zones sweeping along x, y, z
+  // relative time per segment of zones sweeping along x, y, z (same fit: y +3%, z +10%: the z-major copy and its
+  // transposed merge); set_tuning "zone_cost_x/y/z"
+  double zoneClassCost[3] = {kZoneCostX, kZoneCostY, kZoneCostZ};
 };
 
 namespace {
@@ -475,7 +478,10 @@ int shard_directions(int nranks, int nAngularLevel, const int32_t* rays, int32_t
     Direction d = classify_direction(nAngularLevel, list[i]);
     if (d.status) return d.status;
     layer_patterns_level0(d.phi, d.theta, np, pat);
-    double cst = 0;
+    // measured on B200 (profiles/r02_zone_times_256.log, least squares over the 24 zones): time of a zone task =
+    // const + 0.056 ms per direction + 3.9e-4 ms per segment of a 256-cell column, i.e. a direction costs what 0.14
+    // segments per layer cost, on top of its segments
+    double cst = 0.14 * np;
     for (const auto& p : pat) cst += 1 + (p.xzActive ? 1 : 0) + (p.yzActive ? 1 : 0);
     const ZoneMap zm = zone_map(d.izone);
     int sweepAxis = 0;
@@ -1039,9 +1045,9 @@ int rtb200_multi_slab_get(rtb200_ctx* h, int local, double* J3, double* K3, doub
 int rtb200_shard_directions(int nranks, int nAngularLevel, int nx, const double* zoneCost3, int rank, int32_t* rays,
                             int32_t cap, int32_t* nrays) {
   if (!nrays || rank < 0 || rank >= nranks) return RTB200_ERR_ARG;
-  const double one[3] = {1., 1., 1.};
+  const double dflt[3] = {kZoneCostX, kZoneCostY, kZoneCostZ};
   std::vector<std::vector<int32_t>> shards;
-  if (int st = shard_directions(nranks, nAngularLevel, nullptr, 0, nx, zoneCost3 ? zoneCost3 : one, shards)) return st;
+  if (int st = shard_directions(nranks, nAngularLevel, nullptr, 0, nx, zoneCost3 ? zoneCost3 : dflt, shards)) return st;
   const auto& s = shards[(size_t)rank];
   *nrays = (int32_t)s.size();
   if (rays)

@@ -95,6 +95,12 @@ struct PointParams {
   unsigned long long* recCount;
   long long recCap;
   int raysPerSource;      // pixels of levels 1..maxPixelLevel
+  // planned deposition (deposit mode 2): the ray geometry of a source batch is cached, every segment of every ray has a
+  // fixed slot in a leaf-ordered record array
+  unsigned int* rayCount;       // plan pass only: [rays of the batch] segments of every ray object
+  const long long* rayBase;     // [rays of the batch] first index of the ray's segments in slotMap
+  const unsigned int* slotMap;  // [records] (rayBase[ray] + segment) -> position in leaf order
+  double* recVal6;              // [records][6] deposits in leaf order
   int* queue;             // [nsrc] next pixel of the last level to hand out (NULL: static pixel -> thread map)
   // optional traversal trace (parity checks)
   long long* trace;       // [cap][2]
@@ -343,7 +349,8 @@ __device__ __forceinline__ void rates_fast(const PointParams& P, const double* _
 }
 
 // --------------------------------------------------------------------------------------------------------------------
-template <bool FAITHFUL, bool PORTABLE, bool TRACE, bool SEGMENTED, int MINB = 4>
+// DEPOSIT: 0 = fp64 RED.ADD into the rate fields, 1 = (key, 6 deposits) records for the sort, 2 = planned slots
+template <bool FAITHFUL, bool PORTABLE, bool TRACE, int DEPOSIT, int MINB = 4>
 __global__ void __launch_bounds__(128, MINB) point_march_kernel(const __grid_constant__ PointParams P, int pixelLevel) {
   __shared__ double sT[16];
   if (threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
@@ -628,7 +635,13 @@ __global__ void __launch_bounds__(128, MINB) point_march_kernel(const __grid_con
           rates_fast<2>(P, LT, q, d3, tau3, sT, n, h); dep[1] = ndot * n; dep[4] = ndot * h;
         }
       }
-      if (SEGMENTED) {
+      if (DEPOSIT == 2) {
+        // planned: this segment's slot in the leaf-ordered record array is known from the plan pass
+        const long long ray = (long long)s * P.raysPerSource + pix_offset(pixelLevel) + ipix;
+        const unsigned int slot = __ldg(P.slotMap + __ldg(P.rayBase + ray) + (raySeg - 1));
+        double2* rec = reinterpret_cast<double2*>(P.recVal6 + (size_t)slot * 6);
+        rec[0] = make_double2(dep[0], dep[1]); rec[1] = make_double2(dep[2], dep[3]); rec[2] = make_double2(dep[4], dep[5]);
+      } else if (DEPOSIT == 1) {
         // one record per segment; slots are handed out per warp (one counter update for the active lanes)
         const unsigned m = __activemask();
         const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
@@ -639,6 +652,8 @@ __global__ void __launch_bounds__(128, MINB) point_march_kernel(const __grid_con
         if (slot < P.recCap) {
           const long long ray = (long long)s * P.raysPerSource + pix_offset(pixelLevel) + ipix;
           const long long seg = raySeg - 1 < 4095 ? (long long)(raySeg - 1) : 4095;
+          // the plan needs one key per segment: a ray of more than 4095 segments cannot be planned (use mode 1)
+          if (P.rayCount && raySeg - 1 >= 4095) atomicExch(P.err, RTB200_ERR_ARG);
           P.recKey[slot] = ((long long)lf << 32) | ((ray & 0xFFFFF) << 12) | seg;
 #pragma unroll
           for (int i = 0; i < 6; i++) P.recVal[(size_t)i * P.recCap + slot] = dep[i];
@@ -652,6 +667,9 @@ __global__ void __launch_bounds__(128, MINB) point_march_kernel(const __grid_con
       d1 = A(d1, tau1); d2 = A(d2, tau2); d3 = A(d3, tau3); dD = A(dD, tauD);
     }
   }
+
+  if (DEPOSIT == 1 && P.rayCount && !refill && ipix0 < npix)   // plan pass: segments of this ray object
+    P.rayCount[(long long)s * P.raysPerSource + pix_offset(pixelLevel) + ipix0] = have0 ? raySeg : 0u;
 
   // warp-aggregated segment count
   for (int o = 16; o; o >>= 1) mySegs += __shfl_down_sync(0xffffffffu, mySegs, o);
@@ -748,6 +766,63 @@ __global__ void segmented_reduce_kernel(const long long* __restrict__ key, const
   }
 }
 
+// ---- planned deposition --------------------------------------------------------------------------------------------
+// The ray geometry (which leaves a ray crosses, where it splits) depends on the grid and the sources only -- not on the
+// absorber densities, which change from one outer iteration to the next (without dust no ray ends early:
+// equiSources.f90:3241 takes the minimum over four depths, one of which stays 0).  The first pass over a source batch
+// sorts its (leaf, ray, segment) keys once and keeps, for every segment of every ray, its position in that order; later
+// passes write every deposit straight to its slot and add up each leaf's contiguous run: no atomics, no sort, and the
+// same fixed summation order every time.
+__global__ void plan_slot_kernel(const long long* __restrict__ sortedKey, long long n, int raysPerBatchBits,
+                                 const long long* __restrict__ rayBase, unsigned int* __restrict__ slotMap,
+                                 int32_t* __restrict__ sortedLeaf) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+    const long long k = sortedKey[p];
+    const long long ray = (k >> 12) & 0xFFFFF, seg = k & 0xFFF;
+    slotMap[rayBase[ray] + seg] = (unsigned int)p;
+    sortedLeaf[p] = (int32_t)(k >> 32);
+  }
+}
+
+// one thread per run of equal leaves (the head of the run does the work), records [n][6] in leaf order
+__global__ void planned_reduce_kernel(const int32_t* __restrict__ sortedLeaf, const double* __restrict__ val6, long long n,
+                                      double* __restrict__ rates, int64_t nleaf) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int leaf = sortedLeaf[i];
+    if (i > 0 && sortedLeaf[i - 1] == leaf) continue;
+    double sum[6] = {0., 0., 0., 0., 0., 0.};
+    for (long long j = i; j < n && sortedLeaf[j] == leaf; j++) {
+      const double2* r = reinterpret_cast<const double2*>(val6 + (size_t)j * 6);
+      const double2 a = r[0], b = r[1], c = r[2];
+      sum[0] = __dadd_rn(sum[0], a.x); sum[1] = __dadd_rn(sum[1], a.y); sum[2] = __dadd_rn(sum[2], b.x);
+      sum[3] = __dadd_rn(sum[3], b.y); sum[4] = __dadd_rn(sum[4], c.x); sum[5] = __dadd_rn(sum[5], c.y);
+    }
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+      double* p = rates + (size_t)f * nleaf + leaf;
+      *p = __dadd_rn(*p, sum[f]);
+    }
+  }
+}
+
+// exclusive scan of the per-ray segment counts (a batch has at most ~1e6 ray objects: one block, sequential chunks)
+__global__ void ray_base_kernel(const unsigned int* __restrict__ count, long long n, long long* __restrict__ base) {
+  __shared__ long long part[1024];
+  const long long per = (n + 1023) / 1024;
+  const long long lo = threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+  long long s = 0;
+  for (long long i = lo; i < hi; i++) s += count[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long run = 0;
+    for (int t = 0; t < 1024; t++) { const long long v = part[t]; part[t] = run; run += v; }
+  }
+  __syncthreads();
+  long long run = part[threadIdx.x];
+  for (long long i = lo; i < hi; i++) { base[i] = run; run += count[i]; }
+}
+
 __global__ void gather_kernel(const double* __restrict__ src, const int32_t* __restrict__ idx, int n, double* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = src[idx[i]];
@@ -780,7 +855,34 @@ struct Scratch {
   }
 };
 
+// cached ray geometry of the planned deposition: per source batch the slot of every (ray, segment) and the leaf of
+// every slot
+struct PointPlan {
+  std::string key;
+  int batch = 0;
+  struct Batch {
+    long long nrec = 0;
+    long long* rayBase = nullptr;
+    unsigned int* slotMap = nullptr;
+    int32_t* sortedLeaf = nullptr;
+  };
+  std::vector<Batch> batches;
+  void release() {
+    for (auto& b : batches) { cudaFree(b.rayBase); cudaFree(b.slotMap); cudaFree(b.sortedLeaf); }
+    batches.clear();
+    key.clear();
+  }
+};
+
 }  // namespace
+
+void point_release(Context& c) {
+  PointPlan* pl = static_cast<PointPlan*>(c.pointPlan);
+  if (!pl) return;
+  pl->release();
+  delete pl;
+  c.pointPlan = nullptr;
+}
 
 // --------------------------------------------------------------------------------------------------------------------
 int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag, int64_t* nsegOut, long long* hTrace,
@@ -879,8 +981,34 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
   batch = std::min(batch, 16384);
   if (c.tune.pointBatch > 0) batch = std::min(batch, c.tune.pointBatch);
   const int raysPerSource = (int)(4 * ((1LL << (2 * in.maxPixelLevel)) - 1));
-  // segmented deposition: 20-bit ray index in the sort key; 16 sources per batch keep the record buffers at a few GB
-  if (c.tune.pointDeposit == 1) batch = std::max(1, std::min(std::min(batch, 16), (1 << 20) / raysPerSource));
+  // deposit mode: 0 RED.ADD, 1 records + sort every pass, 2 planned (sort once per geometry; needs rays that never end
+  // early, i.e. no dust: equiSources.f90:3241)
+  int depositMode = (hTrace && traceCap > 0) ? 0 : c.tune.pointDeposit;
+  if (depositMode == 2 && in.dust != 0) depositMode = 1;
+  // record modes: 20-bit ray index in the sort key; the batch size bounds the record buffers
+  if (depositMode == 1) batch = std::max(1, std::min(std::min(batch, 16), (1 << 20) / raysPerSource));
+  if (depositMode == 2) batch = std::max(1, std::min(std::min(batch, 64), (1 << 20) / raysPerSource));
+  PointPlan* plan = nullptr;
+  bool planning = false;
+  if (depositMode == 2) {
+    if (!c.pointPlan) c.pointPlan = new PointPlan();
+    plan = static_cast<PointPlan*>(c.pointPlan);
+    // the geometry depends on the octree, the sources that cast rays, the pixel levels and the batching
+    unsigned long long h = 1469598103934665603ULL;
+    for (int i = 0; i < nsrc; i++) {
+      h = (h ^ (unsigned long long)(unsigned)in.srcLeaf[i]) * 1099511628211ULL;
+      h = (h ^ (unsigned long long)(in.srcWeight[i] > 0)) * 1099511628211ULL;
+    }
+    char kb[160];
+    snprintf(kb, sizeof(kb), "%p:%lld:%d:%d:%d:%d:%llx", (void*)c.tree.child, (long long)c.nleaf, c.maxLevel, in.maxPixelLevel, nsrc,
+             batch, h);
+    if (plan->key != kb) {
+      plan->release();
+      plan->key = kb;
+      plan->batch = batch;
+      planning = true;
+    }
+  }
   double *dDtmp, *dLogTab, *dRaw = nullptr, *dDiag;
   RayState *dStA, *dStB;
   if (int st = sc.get(&dDtmp, (size_t)batch * kNfreq)) return st;
@@ -894,8 +1022,17 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
   int* dQueue = nullptr;   // per-source pixel cursor of the last level (lane refill)
   if (int st = sc.get(&dQueue, (size_t)batch)) return st;
   // segmented deposition: record buffers sized from the free memory (76 B per record incl. the sort's double buffers)
-  const bool segmented = c.tune.pointDeposit == 1 && !dTrace;
+  const bool segmented = depositMode == 1 || planning;      // the plan pass is a sort pass that also records the geometry
+  const bool planned = depositMode == 2 && !planning;
   long long recCap = 0;
+  unsigned int* dRayCount = nullptr;
+  double* dRecVal6 = nullptr;
+  if (planning) { if (int st = sc.get(&dRayCount, (size_t)batch * raysPerSource)) return st; }
+  if (planned) {
+    long long mx = 1;
+    for (const auto& b : plan->batches) mx = std::max(mx, b.nrec);
+    if (int st = sc.get(&dRecVal6, (size_t)mx * 6)) return st;
+  }
   long long *dRecKey = nullptr, *dRecKeyOut = nullptr;
   uint32_t *dRecIdx = nullptr, *dRecIdxOut = nullptr;
   double* dRecVal = nullptr;
@@ -944,6 +1081,7 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
   P.trace = dTrace; P.traceLen = dCounters + 1; P.traceCap = dTrace ? traceCap : 0;
   P.recKey = segmented ? dRecKey : nullptr; P.recVal = dRecVal; P.recCount = dRecCount; P.recCap = recCap;
   P.raysPerSource = raysPerSource;
+  P.rayCount = dRayCount; P.recVal6 = dRecVal6;
   int leafBits = 1;
   while ((1LL << leafBits) < c.nleaf) leafBits++;
 
@@ -961,13 +1099,20 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
                                cudaMemcpyDeviceToHost, s));
     P.srcLeaf = dSrcLeaf + b0; P.srcWeight = dSrcWeight + b0; P.logTab = dLogTab; P.diag = dDiag;
     if (segmented) RTB_CUDA(cudaMemsetAsync(dRecCount, 0, 8, s));
+    if (planning) RTB_CUDA(cudaMemsetAsync(dRayCount, 0, (size_t)nb * raysPerSource * sizeof(unsigned int), s));
+    const int bi = b0 / batch;
+    if (planned) {
+      const PointPlan::Batch& pb = plan->batches[(size_t)bi];
+      P.rayBase = pb.rayBase; P.slotMap = pb.slotMap;
+      RTB_CUDA(cudaMemsetAsync(dRecVal6, 0, (size_t)pb.nrec * 6 * sizeof(double), s));
+    }
     RayState *stIn = dStA, *stOut = dStB;
     for (int L = 1; L <= in.maxPixelLevel; L++) {
       const int64_t npix = 12LL << (2 * (L - 1));
       P.stateIn = stIn; P.stateOut = stOut;
       dim3 g((unsigned)((npix + 127) / 128), nb);
       P.queue = nullptr;
-      if (L == in.maxPixelLevel && c.tune.pointRefill && npix >= 1024) {
+      if (L == in.maxPixelLevel && c.tune.pointRefill && npix >= 1024 && depositMode != 2) {
         // last level: fewer threads than rays, every lane takes pixels from its source's queue until it is empty;
         // rays per thread ~ what keeps the device twice over-subscribed, at most 8
         const double resident = (double)c.smCount * 512.0;
@@ -980,21 +1125,26 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
         }
       }
       if (dTrace) {
-        if (portable) point_march_kernel<true, true, true, false><<<g, 128, 0, s>>>(P, L);
-        else if (faithful) point_march_kernel<true, false, true, false><<<g, 128, 0, s>>>(P, L);
-        else point_march_kernel<false, false, true, false><<<g, 128, 0, s>>>(P, L);
+        if (portable) point_march_kernel<true, true, true, 0><<<g, 128, 0, s>>>(P, L);
+        else if (faithful) point_march_kernel<true, false, true, 0><<<g, 128, 0, s>>>(P, L);
+        else point_march_kernel<false, false, true, 0><<<g, 128, 0, s>>>(P, L);
       } else if (segmented) {
-        if (portable) point_march_kernel<true, true, false, true><<<g, 128, 0, s>>>(P, L);
-        else if (faithful) point_march_kernel<true, false, false, true><<<g, 128, 0, s>>>(P, L);
-        else point_march_kernel<false, false, false, true><<<g, 128, 0, s>>>(P, L);
+        if (portable) point_march_kernel<true, true, false, 1><<<g, 128, 0, s>>>(P, L);
+        else if (faithful) point_march_kernel<true, false, false, 1><<<g, 128, 0, s>>>(P, L);
+        else point_march_kernel<false, false, false, 1><<<g, 128, 0, s>>>(P, L);
+      } else if (planned) {
+        if (portable) point_march_kernel<true, true, false, 2><<<g, 128, 0, s>>>(P, L);
+        else if (faithful) point_march_kernel<true, false, false, 2><<<g, 128, 0, s>>>(P, L);
+        else if (c.tune.pointMinBlocks >= 5) point_march_kernel<false, false, false, 2, 5><<<g, 128, 0, s>>>(P, L);
+        else point_march_kernel<false, false, false, 2, 4><<<g, 128, 0, s>>>(P, L);
       } else {
-        if (portable) point_march_kernel<true, true, false, false><<<g, 128, 0, s>>>(P, L);
-        else if (faithful) point_march_kernel<true, false, false, false><<<g, 128, 0, s>>>(P, L);
+        if (portable) point_march_kernel<true, true, false, 0><<<g, 128, 0, s>>>(P, L);
+        else if (faithful) point_march_kernel<true, false, false, 0><<<g, 128, 0, s>>>(P, L);
         // FAST arithmetic, RED deposition: the register budget is a tuning knob ("point_min_blocks": 4 = 128
         // registers, 5 = 96, 6 = 80 with spills)
-        else if (c.tune.pointMinBlocks >= 6) point_march_kernel<false, false, false, false, 6><<<g, 128, 0, s>>>(P, L);
-        else if (c.tune.pointMinBlocks == 5) point_march_kernel<false, false, false, false, 5><<<g, 128, 0, s>>>(P, L);
-        else point_march_kernel<false, false, false, false, 4><<<g, 128, 0, s>>>(P, L);
+        else if (c.tune.pointMinBlocks >= 6) point_march_kernel<false, false, false, 0, 6><<<g, 128, 0, s>>>(P, L);
+        else if (c.tune.pointMinBlocks == 5) point_march_kernel<false, false, false, 0, 5><<<g, 128, 0, s>>>(P, L);
+        else point_march_kernel<false, false, false, 0, 4><<<g, 128, 0, s>>>(P, L);
       }
       c.lastLaunches++;
       c.lastSweepLaunches++;
@@ -1017,6 +1167,32 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
         c.lastLaunches += 3;
         RTB_CUDA(cudaGetLastError());
       }
+      if (planning) {
+        // keep the geometry: slot of every (ray, segment) in the sorted order, leaf of every slot
+        PointPlan::Batch pb;
+        pb.nrec = (long long)nrec;
+        const size_t nrays = (size_t)nb * raysPerSource;
+        RTB_CUDA(cudaMalloc((void**)&pb.rayBase, nrays * sizeof(long long)));
+        RTB_CUDA(cudaMalloc((void**)&pb.slotMap, std::max<size_t>(nrec, 1) * sizeof(unsigned int)));
+        RTB_CUDA(cudaMalloc((void**)&pb.sortedLeaf, std::max<size_t>(nrec, 1) * sizeof(int32_t)));
+        ray_base_kernel<<<1, 1024, 0, s>>>(dRayCount, (long long)nrays, pb.rayBase);
+        if (nrec > 0) {
+          const int blocks = (int)std::min<long long>(((long long)nrec + 255) / 256, (long long)c.smCount * 16);
+          plan_slot_kernel<<<blocks, 256, 0, s>>>(dRecKeyOut, (long long)nrec, 20, pb.rayBase, pb.slotMap, pb.sortedLeaf);
+        }
+        RTB_CUDA(cudaGetLastError());
+        plan->batches.push_back(pb);
+        c.lastLaunches += 2;
+      }
+    }
+    if (planned) {
+      const PointPlan::Batch& pb = plan->batches[(size_t)bi];
+      if (pb.nrec > 0) {
+        const int blocks = (int)std::min<long long>((pb.nrec + 255) / 256, (long long)c.smCount * 16);
+        planned_reduce_kernel<<<blocks, 256, 0, s>>>(pb.sortedLeaf, dRecVal6, pb.nrec, dRates, c.nleaf);
+        c.lastLaunches += 1;
+        RTB_CUDA(cudaGetLastError());
+      }
     }
     if (hDiag)
       RTB_CUDA(cudaMemcpyAsync(hDiag + (size_t)b0 * kDiagStride, dDiag, (size_t)nb * kDiagStride * 8, cudaMemcpyDeviceToHost, s));
@@ -1030,6 +1206,12 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
     const long long n = std::min<long long>((long long)counters[1], traceCap);
     RTB_CUDA(cudaMemcpy(hTrace, dTrace, (size_t)n * 16, cudaMemcpyDeviceToHost));
     if (traceLen) *traceLen = (long long)counters[1];
+  }
+  if (planning) {
+    // the sort buffers of the plan pass are not needed again: give them back (the next call sizes its own scratch)
+    RTB_CUDA(cudaStreamSynchronize(s));
+    for (auto& sl : c.pointPool) cudaFree(sl.first);
+    c.pointPool.clear();
   }
   c.lastAlgBytes = 136.0 * (double)counters[0];  // 5 reads + 6 read-modify-writes per segment
   c.statsPending = true;

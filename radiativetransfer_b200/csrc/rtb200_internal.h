@@ -71,12 +71,15 @@ struct Tuning {
   double l2BudgetMB = 96.0;
   int march = 0;         // uniform sweep: 1 = persistent layer-marching kernel (experimental, slower: DESIGN.md)
   int pdl = 1;           // uniform sweep: programmatic dependent launch of layer l+1 on layer l (its prologue overlaps the tail)
+  int cells = 2;         // uniform sweep, FAST arithmetic: cells of a layer per thread (2: two rows per warp, see sweep_cell2_kernel)
   int transposeZ = 1;    // uniform sweep: zones sweeping along the contiguous axis use a z-major copy of kappa / J
   int dirsPerTask = 0;   // directions of one zone swept together (0 = kMaxDirPerTask)
   int marchDebug = 0;    // experiments only: 1 = skip the neighbour polling (wrong results), 2 = spin without nanosleep
   int portableMath = 1;  // point path, FAITHFUL mode: exp/log from portable_math.h (bit-identical on host and device)
   int pointDeposit = 0;  // point path: 0 = fp64 RED.ADD into the rate fields, 1 = atomic-free: (leaf, deposit) records,
-                         // radix sort by (leaf, ray, segment), one thread per cell adds its run (deterministic order)
+                         // radix sort by (leaf, ray, segment), one thread per cell adds its run (deterministic order),
+                         // 2 = planned: as 1, but the sort is done once per (grid, sources) and every later pass writes
+                         // its deposits to their cached leaf-ordered slots (falls back to 1 with dust)
   long long pointRecordCap = 0;  // upper limit of the record buffer of mode 1 (0 = 60% of the free memory)
   int pointRefill = 0;   // point path, last pixel level: 1 = lanes take further rays from a per-source queue (fuller warps but
   int pointMinBlocks = 5;  // point march kernel (FAST, RED deposition): blocks of 128 threads per SM the register cap allows (5: 96 registers)
@@ -155,6 +158,7 @@ struct Context {
   std::vector<std::pair<void*, size_t>> pointPool;
   std::vector<double> pointDirs;   // HEALPix pixel directions of levels 1..pointDirsLevel (host copy)
   int pointDirsLevel = 0;
+  void* pointPlan = nullptr; // point_source.cu: cached ray geometry of the planned deposition (point_release frees it)
   void* amrState = nullptr;  // diffuse_amr.cu: wave plan, pattern tables and batch buffers of this context (amr_release frees it)
   double* dAcc = nullptr;      // slot accumulators
   size_t accBytes = 0;
@@ -206,6 +210,7 @@ int diffuse_amr(Context& c, int nAngularLevel, const double* uvb, const std::vec
                 double* dJout, cudaStream_t s, int64_t* nseg);
 int amr_neighbours(Context& c, const Direction& d, int32_t* nbHost);
 void amr_release(Context& c);
+void point_release(Context& c);
 int launch_diffuse_rates(Context& c, const double* J, const double* ksi24, const double* ksi25, const double* ksi26,
                          double* k24, double* k25, double* k26, cudaStream_t s);
 

@@ -347,3 +347,66 @@ def build_leaves(levels, metals=False):
     res = dict((k, np.concatenate(v)[order]) for k, v in out_vals.items())
     return dict(nx=nx, level=np.concatenate(out_level)[order], HI=res["HI"], HeI=res["HeI"], HeII=res["HeII"],
                 rho=res["rho"], abun2=res["abun2"], box_size=box_size, tgas=res["tgas"])
+
+
+# ------------------------------------------------------------------------------------------------------
+# flat dataset container of oracle/ref_harness/hdf4_stub.c (stands in for HDF4 SD files where the unmodified reference
+# driver is built without libmfhdf): "RTBSD001" | int32 nsds | nsds x { name[64] | type | rank | dims[4] | nbytes | data }
+# ------------------------------------------------------------------------------------------------------
+_SD_TYPES = {np.dtype("<i4"): 24, np.dtype("<f4"): 5, np.dtype("<f8"): 6}
+_SD_DTYPES = {24: "<i4", 25: "<u4", 5: "<f4", 6: "<f8", 20: "i1", 21: "u1"}
+
+
+def write_sd_container(path, datasets):
+    """datasets = list of (name, array); arrays are stored in Fortran (column-major) order with dims as Fortran sees them"""
+    with open(path, "wb") as f:
+        f.write(b"RTBSD001")
+        f.write(np.array([len(datasets)], dtype="<i4").tobytes())
+        for name, a in datasets:
+            a = np.asarray(a)
+            if a.dtype not in _SD_TYPES:
+                raise ValueError(f"dataset {name}: unsupported dtype {a.dtype}")
+            if a.ndim < 1 or a.ndim > 4:
+                raise ValueError("rank 1..4 expected")
+            dims = list(a.shape) + [0] * (4 - a.ndim)
+            data = np.asfortranarray(a).tobytes(order="F")
+            f.write(name.encode()[:63].ljust(64, b"\0"))
+            f.write(np.array([_SD_TYPES[a.dtype], a.ndim] + dims, dtype="<i4").tobytes())
+            f.write(np.array([len(data)], dtype="<i8").tobytes())
+            f.write(data)
+
+
+def read_sd_container(path):
+    """list of (name, array) in file order"""
+    out = []
+    with open(path, "rb") as f:
+        if f.read(8) != b"RTBSD001":
+            raise ValueError("not a dataset container")
+        n = int(np.frombuffer(f.read(4), dtype="<i4")[0])
+        for _ in range(n):
+            name = f.read(64).split(b"\0", 1)[0].decode()
+            hdr = np.frombuffer(f.read(24), dtype="<i4")
+            nbytes = int(np.frombuffer(f.read(8), dtype="<i8")[0])
+            typ, rank = int(hdr[0]), int(hdr[1])
+            dims = [int(x) for x in hdr[2:2 + rank]]
+            a = np.frombuffer(f.read(nbytes), dtype=_SD_DTYPES[typ])
+            if int(np.prod(dims)) == a.size:
+                a = a.reshape(dims, order="F")
+            out.append((name, a.copy()))
+    return out
+
+
+def write_grid_container(path, levels, metals=True, kinematics=False):
+    """the reference's input grid `<grid>.h4` (equiSources.f90:316-423; written by bin2hdf4.f90:106-165) as a container:
+    dataset 0 `nlevels`, then per level pos[ncell,3], lT, lnH, lx (float32) [, abun[ncell,4]] [, vel[ncell,3]].
+    levels = list of dicts with those keys (level 1 first, exactly n^3 cells)."""
+    ds = [("nlevels", np.array([len(levels)], dtype="<i4"))]
+    for i, lv in enumerate(levels, 1):
+        ds.append((f"pos{i}", np.asarray(lv["pos"], dtype="<f4")))
+        for k in ("lT", "lnH", "lx"):
+            ds.append((f"{k}{i}", np.asarray(lv[k], dtype="<f4")))
+        if metals:
+            ds.append((f"abun{i}", np.asarray(lv["abun"], dtype="<f4")))
+        if kinematics:
+            ds.append((f"vel{i}", np.asarray(lv["vel"], dtype="<f4")))
+    write_sd_container(path, ds)

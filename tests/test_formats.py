@@ -183,3 +183,52 @@ def test_octree_from_level_lists(metals, tmp_path, oracle):
     tgas = kw.pop("tgas")
     og = oracle.OracleGrid(kw["nx"], kw["level"], kw["HI"], kw["HeI"], kw["HeII"], kw["rho"], kw["abun2"], kw["box_size"])
     assert og.nleaf == tgas.size                                  # a consistent pre-order octree
+
+
+def test_hdf4_stub_container_round_trip(tmp_path):
+    """oracle/ref_harness/hdf4_stub.c (the HDF4 stand-in of the gfortran recipe) against formats.write_sd_container /
+    read_sd_container: datasets written by Python are read through the Fortran-callable entry points and back"""
+    import ctypes as C
+    import os
+    import subprocess
+    from conftest import ROOT
+    so = str(tmp_path / "libhdf4stub.so")
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "oracle", "ref_harness", "hdf4_stub.c")])
+    L = C.CDLL(so)
+    rng = np.random.default_rng(3)
+    pos = rng.normal(size=(27, 3)).astype("<f4")
+    lT = rng.normal(size=27).astype("<f4")
+    path = str(tmp_path / "grid_met.h4")
+    F.write_sd_container(path, [("nlevels", np.array([1], dtype="<i4")), ("pos1", pos), ("lT1", lT)])
+    back = F.read_sd_container(path)
+    assert [n for n, _ in back] == ["nlevels", "pos1", "lT1"] and np.array_equal(back[1][1], pos)
+    i = lambda v: C.byref(C.c_int(v))
+    name = (path + "   ").encode()                        # Fortran strings are blank padded, length passed by value
+    sd = L.sfstart_(name, i(1), C.c_long(len(name)))
+    assert sd > 0
+    nds, nat = C.c_int(0), C.c_int(0)
+    assert L.sffinfo_(i(sd), C.byref(nds), C.byref(nat)) == 0 and nds.value == 3
+    sds = L.sfselect_(i(sd), i(1))
+    nm = C.create_string_buffer(64)
+    rank, typ, na = C.c_int(0), C.c_int(0), C.c_int(0)
+    dims = (C.c_int * 4)()
+    assert L.sfginfo_(i(sds), nm, C.byref(rank), dims, C.byref(typ), C.byref(na), C.c_long(64)) == 0
+    assert rank.value == 2 and dims[0] == 27 and dims[1] == 3 and typ.value == 5 and nm.raw.startswith(b"pos1 ")
+    out = np.zeros((27, 3), dtype="<f4", order="F")      # a Fortran array pos(27,3)
+    start, stride, edges = (C.c_int * 4)(0, 0, 0, 0), (C.c_int * 4)(1, 1, 1, 1), (C.c_int * 4)(27, 3, 0, 0)
+    assert L.sfrdata_(i(sds), start, stride, edges, out.ctypes.data_as(C.c_void_p)) == 0
+    assert np.array_equal(out, pos)
+    assert L.sfendacc_(i(sds)) == 0 and L.sfend_(i(sd)) == 0
+    # writing, as writeIonization does (equiSources.f90:4843-4905)
+    path2 = (str(tmp_path / "cellArray0001.h4")).encode()
+    sd = L.sfstart_(path2, i(4), C.c_long(len(path2)))
+    lev = np.arange(10, dtype="<i4")
+    e1 = (C.c_int * 4)(10, 0, 0, 0)
+    sds = L.sfcreate_(i(sd), b"level", i(24), i(1), e1, C.c_long(5))
+    assert L.sfwdata_(i(sds), start, stride, e1, lev.ctypes.data_as(C.c_void_p)) == 0
+    hi = rng.normal(size=10).astype("<f4")
+    sds = L.sfcreate_(i(sd), b"HI", i(5), i(1), e1, C.c_long(2))
+    assert L.sfwdata_(i(sds), start, stride, e1, hi.ctypes.data_as(C.c_void_p)) == 0
+    assert L.sfend_(i(sd)) == 0
+    back = F.read_sd_container(path2.decode())
+    assert back[0][0] == "level" and np.array_equal(back[0][1], lev) and np.array_equal(back[1][1], hi)

@@ -150,7 +150,7 @@ def test_outer_iteration_on_slabs(rt, uvbg, ndev):
     g = W.nested_grid(6, 2, W.central_box_refine(0.2, 0.7, levels=2), seed=5, tau_lo=1e-2, tau_hi=2.0, beta24=S24)
     N = g["level"].size
     ktab = W.rate_tables(500)
-    tgas = 10.0 ** np.random.default_rng(2).uniform(3.8, 4.6, N)
+    tgas = 10.0 ** np.random.default_rng(2).uniform(4.0, 4.1, N)
     spectra = W.synthetic_spectra()
     src = np.array([N // 2, 17, N - 3], dtype=np.int32); wt = np.array([2, 1, 1], dtype=np.int32)
     ksi = np.concatenate([uvbg["ksi24"], uvbg["ksi25"], uvbg["ksi26"]])

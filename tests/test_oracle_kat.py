@@ -130,3 +130,29 @@ def test_direction_shards_add_up(oracle, uvbg):
 def test_level_array_errors(oracle):
     with pytest.raises(RuntimeError):
         oracle.OracleGrid(2, np.array([0] * 7 + [1] * 7, dtype=np.int8), np.ones(14))  # incomplete octet
+
+
+def test_reference_harness_pieces(tmp_path):
+    """oracle/ref_harness (the gfortran recipe that would pin the oracle against the reference itself): what can run
+    without a Fortran compiler -- the dump reader / comparer on a dump the oracle writes in the harness layout, and the
+    case generator's files"""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    h = os.path.join(ROOT, "oracle", "ref_harness")
+    r = subprocess.run([sys.executable, os.path.join(h, "compare.py"), "--selftest", str(tmp_path / "st")], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "PINNED" in r.stdout, r.stdout + r.stderr
+    r = subprocess.run([sys.executable, os.path.join(h, "make_case.py"), str(tmp_path / "run"), "--case", "nested"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    from radiativetransfer_b200 import formats as F
+    ds = F.read_sd_container(str(tmp_path / "run" / "case_met.h4"))
+    assert ds[0][0] == "nlevels" and int(ds[0][1][0]) == 3
+    assert ds[1][1].shape == (512, 3) and len(ds) == 1 + 3 * 5          # 8^3 level-1 cells; pos, lT, lnH, lx, abun per level
+    # the spectrum table parses with the driver's fixed columns (equiSources.f90:861-879)
+    lines = open(tmp_path / "run" / "model41-salpeter-burst34" / "spectrum.out").read().splitlines()
+    data = [l for l in lines if len(l) >= 41 and l[1:10] != "TIME [YR]" and l[1:6] != "MODEL" and l.strip()]
+    assert len(data) == 37 * 1221
+    assert float(data[0][1:13]) == 1.0e6 and abs(float(data[0][13:28]) - 91.0) < 1e-4 and float(data[0][28:41]) > 0

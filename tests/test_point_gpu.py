@@ -413,3 +413,50 @@ def test_golden_spectrum_fixture(rt, engine, spectra):
         assert rel_err(r["ndot_spectrum"], f["ndot_spectrum"], floor=1e-300) < 1e-11
         assert rel_err(r["ndot_dust"], f["ndot_dust"], floor=1e-300) < 1e-11
         assert np.array_equal(r["highest_pixel_level"], f["highest_pixel_level"])
+
+
+def test_planned_deposition_atomic_free_and_reproducible(rt, engine, portable, spectra):
+    """set_tuning(point_deposit=2): the (leaf, ray, segment) sort is done once per (grid, sources); later passes write
+    every deposit to its cached leaf-ordered slot and add up each leaf's run -- no atomics, no sort.  Bit-identical to
+    the sort-every-pass mode (same summation order), from call to call, and after the species change; with dust (rays
+    may end early) the mode falls back to sorting every pass."""
+    n = 12
+    g = W.nested_grid(n, 1, W.central_box_refine(0.25, 0.75, levels=1), seed=21, tau_lo=1e-2, tau_hi=1.0, beta24=S24)
+    _set(engine, g)
+    rng = np.random.default_rng(8)
+    leaves = rng.choice(g["level"].size, 70, replace=False).astype(np.int32)      # more than one batch of 64 sources
+    wts = rng.integers(0, 3, 70).astype(np.int32)
+    atom = engine.point(spectra, leaves, wts)
+    engine.set_tuning(point_deposit=1)
+    srt = engine.point(spectra, leaves, wts)
+    engine.set_tuning(point_deposit=2)
+    p1 = engine.point(spectra, leaves, wts)          # plan pass
+    p2 = engine.point(spectra, leaves, wts)          # planned pass
+    p3 = engine.point(spectra, leaves, wts)
+    assert p1["nseg"] == p2["nseg"] == atom["nseg"]
+    for r in (p1, p2, p3):
+        for i in range(6):
+            assert _cell_err(r["rates"][i], atom["rates"][i]) < 1e-12
+    assert np.array_equal(p2["rates"], p3["rates"])
+    assert np.array_equal(p1["rates"], p2["rates"])
+    assert np.array_equal(p2["ndot_boundary"], atom["ndot_boundary"])
+    # same sources, other densities: the plan stays valid
+    engine.update_species(HI=g["HI"] * 0.3, HeI=g["HeI"] * 2.0)
+    q2 = engine.point(spectra, leaves, wts)
+    engine.set_tuning(point_deposit=0)
+    q0 = engine.point(spectra, leaves, wts)
+    for i in range(6):
+        assert _cell_err(q2["rates"][i], q0["rates"][i]) < 1e-12
+    o = _ograd(portable, dict(g, HI=g["HI"] * 0.3, HeI=g["HeI"] * 2.0)).point(spectra, leaves, wts)
+    for i in range(6):
+        assert _cell_err(q2["rates"][i], o["rates"][i]) < 1e-12
+    # other sources: a new plan; accumulation into existing rates
+    engine.set_tuning(point_deposit=2)
+    r1 = engine.point(spectra, leaves[:5], wts[:5] + 1)
+    r2 = engine.point(spectra, leaves[:5], wts[:5] + 1, rates=r1["rates"])
+    assert rel_err(r2["rates"], 2 * r1["rates"], floor=1e-300) < 1e-12
+    # dust: falls back to the sort-every-pass mode, still reproducible
+    d1 = engine.point(spectra, leaves[:5], wts[:5] + 1, dust_approximation=2)
+    d2 = engine.point(spectra, leaves[:5], wts[:5] + 1, dust_approximation=2)
+    assert np.array_equal(d1["rates"], d2["rates"])
+    engine.set_tuning(point_deposit=0)
