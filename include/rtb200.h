@@ -245,6 +245,21 @@ int rtb200_chemistry_device(rtb200_ctx* ctx, const double* rates_device, const d
 int rtb200_grid_get_species(rtb200_ctx* ctx, double* HI, double* HeI, double* HeII);
 int rtb200_compute_mass(rtb200_ctx* ctx, double* neutralHydrogenMass, double* totalHydrogenMass, void* stream);
 
+/* Octree build on the device: from the per-level cell lists of the driver's input grid (equiSources.f90:316-423: pos
+ * [ncell][3] in kpc, lT, lnH, lx, and the second abundance abun(:,2) or NULL, all real*4, level 1 first with exactly n^3
+ * cells) to the leaf arrays in writeCell order that rtb200_grid_set takes.  Replaces the driver's cell-by-cell tree
+ * construction for the data path (box :455-489, level-1 abundance smoothing :527-578, placement with inheritance
+ * :580-618 + :1870-1974) with sorted key sets (csrc/octree_build.cu).
+ *   rtb200_octree_build  builds on `device`; returns the leaf count, nx, physicalBoxSize [cm] and a handle
+ *   rtb200_octree_get    copies level[nleaf] and HI, HeI, HeII, rho, abun2, tgas [nleaf] (any may be NULL) to the host
+ *   rtb200_octree_free   releases the handle */
+int rtb200_octree_build(int device, int nlevels, const int64_t* ncell, const float* const* pos, const float* const* lT,
+                        const float* const* lnH, const float* const* lx, const float* const* abun2, int64_t* nleaf,
+                        int32_t* nx, double* physicalBoxSize, void** handle);
+int rtb200_octree_get(void* handle, int8_t* level, double* HI, double* HeI, double* HeII, double* rho, double* abun2,
+                      double* tgas);
+int rtb200_octree_free(void* handle);
+
 /* --- debugging / parity exports (bit-exact traversal checks) ------------------------------------------- */
 /* point-source pass that also records every ray-cell segment: trace[2*i] = leaf<<32 | pixelLevel<<28 | pixel<<8 | exit
  * face (2*plane + side; 0 = the ray split inside the cell), trace[2*i+1] = source<<52 | pixelLevel<<48 | pixel<<24 |

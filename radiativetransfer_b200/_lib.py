@@ -54,6 +54,10 @@ SIGNATURES = {
     "rtb200_compute_mass": (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(C.c_double), P]),
     "rtb200_chemistry_device": (C.c_int, [P, P, P, P, P, C.POINTER(C.c_double), P]),
     "rtb200_grid_get_species": (C.c_int, [P, P, P, P]),
+    "rtb200_octree_build": (C.c_int, [C.c_int, C.c_int, P, P, P, P, P, P, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_double), C.POINTER(P)]),
+    "rtb200_octree_get": (C.c_int, [P, P, P, P, P, P, P, P]),
+    "rtb200_octree_free": (C.c_int, [P]),
     "rtb200_direction": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_double),
                                    C.POINTER(C.c_double)]),
     "rtb200_patterns": (C.c_int, [C.c_int, C.c_int64, C.c_int, P]),

@@ -410,3 +410,48 @@ def write_grid_container(path, levels, metals=True, kinematics=False):
         if kinematics:
             ds.append((f"vel{i}", np.asarray(lv["vel"], dtype="<f4")))
     write_sd_container(path, ds)
+
+
+def build_leaves_device(levels, metals=False, device=0, _library=None, _prefix="rtb200_octree_"):
+    """`build_leaves` on the GPU: rtb200_octree_build (csrc/octree_build.cu) -- the same octree from the same per-level
+    lists, built with sorted key sets instead of cell-by-cell insertion.  Returns the keyword arguments of
+    `Transport.set_grid` plus `tgas`.  (`_library` / `_prefix`: the test suite's host-backend build of the same source.)"""
+    import ctypes as C
+    if _library is None:
+        from . import _lib
+        L = _lib.lib()
+    else:
+        L = _library
+    nl = len(levels)
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    pos = [f32(lv["pos"]) for lv in levels]
+    lT = [f32(lv["lT"]) for lv in levels]
+    lnH = [f32(lv["lnH"]) for lv in levels]
+    lx = [f32(lv["lx"]) for lv in levels]
+    ab = [f32(np.asarray(lv["abun"])[:, 1]) for lv in levels] if metals else None
+    ncell = np.array([p.shape[0] for p in pos], dtype=np.int64)
+    arr = lambda lst: (C.c_void_p * nl)(*[a.ctypes.data_as(C.c_void_p) for a in lst])
+    nleaf, nx, box, h = C.c_int64(0), C.c_int32(0), C.c_double(0), C.c_void_p()
+    build = getattr(L, _prefix + "build"); get = getattr(L, _prefix + "get"); free = getattr(L, _prefix + "free")
+    build.restype = get.restype = free.restype = C.c_int
+    build.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                      C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_void_p)]
+    get.argtypes = [C.c_void_p] * 8
+    free.argtypes = [C.c_void_p]
+    st = build(int(device), nl, ncell.ctypes.data_as(C.c_void_p), arr(pos), arr(lT), arr(lnH), arr(lx),
+               arr(ab) if metals else None, C.byref(nleaf), C.byref(nx), C.byref(box), C.byref(h))
+    if st:
+        if _library is None:
+            from . import _lib
+            _lib.check(st, "rtb200_octree_build")
+        raise RuntimeError(f"octree build failed: status {st}")
+    N = nleaf.value
+    out = dict(nx=nx.value, box_size=box.value, level=np.zeros(N, dtype=np.int8))
+    for k in ("HI", "HeI", "HeII", "rho", "abun2", "tgas"):
+        out[k] = np.zeros(N)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    st = get(h, p(out["level"]), p(out["HI"]), p(out["HeI"]), p(out["HeII"]), p(out["rho"]), p(out["abun2"]), p(out["tgas"]))
+    free(h)
+    if st:
+        raise RuntimeError(f"octree get failed: status {st}")
+    return out

@@ -232,3 +232,98 @@ def test_hdf4_stub_container_round_trip(tmp_path):
     assert L.sfend_(i(sd)) == 0
     back = F.read_sd_container(path2.decode())
     assert back[0][0] == "level" and np.array_equal(back[0][1], lev) and np.array_equal(back[1][1], hi)
+
+
+def _host_backend_octree(tmp_path):
+    """csrc/octree_build.cu compiled with thrust's HOST backend (g++, THRUST_DEVICE_SYSTEM_CPP): the same source the
+    product builds for the GPU, runnable without one.  A test artefact: its entry points carry another prefix."""
+    import ctypes as C
+    import os
+    import subprocess
+    from conftest import ROOT
+    so = str(tmp_path / "liboctree_hostcheck.so")
+    inc = "/usr/local/cuda/include"
+    if not os.path.exists(os.path.join(inc, "thrust", "sort.h")):
+        pytest.skip("thrust headers not found")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-x", "c++", "-DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP", "-I", inc,
+                           "-fPIC", "-ffp-contract=off", "-shared", "-o", so,
+                           os.path.join(ROOT, "radiativetransfer_b200", "csrc", "octree_build.cu")])
+    return C.CDLL(so)
+
+
+def _random_levels(rng, nx, metals, counts=(40, 30), spans=(12.0, 6.0), duplicates=True):
+    g = (np.arange(nx) + 0.5) / nx * 80.0 - 40.0            # kpc
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+
+    def lv(pos):
+        n = pos.shape[0]
+        d = dict(pos=pos, lT=rng.uniform(3, 5, n), lnH=rng.uniform(-4, 0, n), lx=rng.uniform(-4, 0, n))
+        if metals:
+            d["abun"] = rng.uniform(0, 0.05, (n, 4))
+        return d
+
+    levels = [lv(np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1))]
+    for c, s in zip(counts, spans):
+        pos = rng.uniform(-s, s, (c, 3))
+        if duplicates and c > 4:
+            pos[-2:] = pos[:2] + 1e-4          # two cells that land in the same node: the later one wins
+        levels.append(lv(pos))
+    return levels
+
+
+@pytest.mark.parametrize("metals", [False, True])
+def test_octree_build_sorted_key_sets_equal_sequential_insertion(metals, tmp_path):
+    """the device formulation of the octree build (sorted key sets, csrc/octree_build.cu), run through thrust's host
+    backend, against formats.build_leaves (itself checked against the pointer-tree restatement above): same leaves,
+    same order, same bits"""
+    L = _host_backend_octree(tmp_path)
+    rng = np.random.default_rng(11)
+    for nx, counts, spans in ((4, (40, 30), (12.0, 6.0)), (3, (25,), (20.0,)), (5, (60, 50, 40), (16.0, 9.0, 5.0)), (2, (), ())):
+        levels = _random_levels(rng, nx, metals, counts, spans)
+        for lv in levels:                      # what read_grid_dat hands over: real*4 lists
+            for k in lv:
+                lv[k] = np.asarray(lv[k], dtype=np.float32)
+        ref = F.build_leaves(levels, metals=metals)
+        got = F.build_leaves_device(levels, metals=metals, _library=L, _prefix="rtb200_hostcheck_octree_")
+        assert got["nx"] == ref["nx"] and got["box_size"] == ref["box_size"]
+        assert np.array_equal(got["level"], ref["level"])
+        for name in ("HI", "HeI", "HeII", "rho", "abun2", "tgas"):
+            assert np.array_equal(got[name], ref[name]), (nx, name)
+    # a level-1 list that is not a cube, and a cell outside the box, are refused
+    bad = _random_levels(rng, 3, metals, (), ())
+    bad[0] = {k: v[:-1] for k, v in bad[0].items()}
+    with pytest.raises(RuntimeError):
+        F.build_leaves_device(bad, metals=metals, _library=L, _prefix="rtb200_hostcheck_octree_")
+    out = _random_levels(rng, 3, metals, (5,), (10.0,))
+    out[1]["pos"][0] = [500.0, 0.0, 0.0]
+    with pytest.raises(RuntimeError):
+        F.build_leaves_device(out, metals=metals, _library=L, _prefix="rtb200_hostcheck_octree_")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("metals", [False, True])
+def test_octree_build_on_device(metals, build_product):
+    """rtb200_octree_build on the GPU against formats.build_leaves: tree, leaf order and every integer bit-exact; the
+    state differs only by the device's pow(10, x) (<= 2 ulp from the C library's) -- 4e-16 relative; and the result feeds
+    rtb200_grid_set"""
+    rng = np.random.default_rng(12)
+    import radiativetransfer_b200 as rt
+    for nx, counts, spans in ((4, (40, 30), (12.0, 6.0)), (16, (3000, 2000, 800), (20.0, 10.0, 4.0))):
+        levels = _random_levels(rng, nx, metals, counts, spans)
+        for lv in levels:
+            for k in lv:
+                lv[k] = np.asarray(lv[k], dtype=np.float32)
+        ref = F.build_leaves(levels, metals=metals)
+        got = F.build_leaves_device(levels, metals=metals)
+        assert got["nx"] == ref["nx"] and got["box_size"] == ref["box_size"]
+        assert np.array_equal(got["level"], ref["level"])
+        assert np.array_equal(got["HeII"], ref["HeII"]) and np.array_equal(got["abun2"], ref["abun2"])
+        for name in ("HI", "HeI", "rho", "tgas"):
+            m = ref[name] != 0
+            assert np.array_equal(got[name] == 0, ~m)
+            assert np.max(np.abs(got[name][m] / ref[name][m] - 1.0)) < 4e-16, name
+        t = rt.Transport(device=0)
+        tg = got.pop("tgas")
+        t.set_grid(**got)
+        assert t.nleaf == tg.size
+        t.close()
