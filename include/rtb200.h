@@ -112,7 +112,8 @@ int rtb200_set_math(rtb200_ctx* ctx, int math_mode);
 /* Launch tuning knobs; results do not depend on them (tests/test_diffuse_gpu.py, test_point_gpu.py).  Keys:
  *   uniform sweep  "slots" (zone tasks per launch, 0 = all), "graph" (CUDA graph replay, 1), "dense" (register cap:
  *                  0/1/2 = 2/3/4 blocks per SM, 2), "expv" (1 = table exponential), "lockstep" (one launch per layer
- *                  for all tasks, 1), "dirs_per_task" (0 = chosen from a wave model), "cells" (cells of a layer per thread, 2), "transpose_z" (z-major copy for
+ *                  for all tasks, 1), "dirs_per_task" (0 = chosen from a wave model), "cells" (cells of a layer per thread: 1, 2, or 0 = by grid size), "block_warps" (rows per block 8 / 4 / 2,
+ *                  0 = by the number of blocks a launch has), "transpose_z" (z-major copy for
  *                  the zones sweeping along the contiguous axis, 1), "pdl" (programmatic dependent launch of layer
  *                  l+1 on layer l, also used by the nested-grid waves, 1), "march" (experimental persistent kernel, 0; its "march_debug" switches
  *                  exist only with RTB200_EXPERIMENTAL set in the environment), "l2_mb"
@@ -121,7 +122,10 @@ int rtb200_set_math(rtb200_ctx* ctx, int math_mode);
  *   device groups  "multi_reduce" (1 = peer-memory reduce-scatter kernel, 0 = NCCL), "zone_cost_x" / "_y" / "_z"
  *                  (relative time per segment of zones sweeping along x / y / z, for the direction sharding)
  *   point sources  "point_batch" (sources per batch), "point_min_blocks" (register cap of the march kernel, 5),
- *                  "point_deposit" (0 = fp64 RED, 1 = records + sort + segmented reduction), "point_record_cap",
+ *                  "point_deposit" (atomic-free and reproducible: 2 = planned, the default -- the (leaf, ray, segment) sort is done
+ *                  once per grid and source list, later passes write every deposit to its cached leaf-ordered slot and add up
+ *                  each leaf's run; 1 = records + sort + segmented reduction every pass (what 2 falls back to with dust);
+ *                  0 = fp64 RED.ADD, the ablation: fastest, summation order not fixed), "point_record_cap",
  *                  "point_refill" (lane refill on the last pixel level, 0)
  * "portable_math" (default 1) selects, for the FAITHFUL point-source path, exp/log built from IEEE +,*,/,fma
  * (csrc/portable_math.h) instead of CUDA libm, so that a host build of the same header reproduces it bit for bit. */

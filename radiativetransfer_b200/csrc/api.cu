@@ -229,12 +229,16 @@ int set_tuning(Context& c, const char* key, double value) {
   else if (k == "lockstep") c.tune.lockstep = (int)value;
   else if (k == "amr_batch") c.tune.amrBatch = (int)value;
   else if (k == "force_amr") c.tune.forceAmr = (int)value;
+  else if (k == "amr_slots") c.tune.amrSlots = (int)value;
+  else if (k == "amr_thin") c.tune.amrThin = (int)value;
+  else if (k == "amr_min_blocks") c.tune.amrMinBlocks = (int)value;
   else if (k == "slots") c.tune.slots = (int)value;
   else if (k == "graph") c.tune.useGraph = (int)value;
   else if (k == "l2_mb") c.tune.l2BudgetMB = value;
   else if (k == "march") c.tune.march = (int)value;
   else if (k == "transpose_z") c.tune.transposeZ = (int)value;
   else if (k == "cells") c.tune.cells = (int)value;
+  else if (k == "block_warps") c.tune.blockWarps = (int)value;
   else if (k == "pdl") c.tune.pdl = (int)value;
   else if (k == "dirs_per_task") c.tune.dirsPerTask = (int)value;
   else if (k == "march_debug") {

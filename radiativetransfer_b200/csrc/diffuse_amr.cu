@@ -45,7 +45,7 @@ struct alignas(32) DevPattern {   // subset of RayPattern the device needs, 128 
   int8_t top[3];         // xyTop, yzTop, xzTop: which ray (1 xy, 2 yz, 3 xz) leaves through the top / x=1 / y=1 face
   int8_t active[3];      // xy (always), yz, xz
   int8_t level;          // refinement level of the table
-  int8_t thin;           // an active ray is shorter than 1e-3 cell: FAST arithmetic evaluates this layer's items with the
+  int8_t thin;           // bit r: active ray r is shorter than 1e-3 cell -- FAST arithmetic evaluates THAT segment with the
                          // reference's operation sequence (same rule and reason as the uniform sweep, diffuse_uniform.cu)
   double cs[3];          // FAST arithmetic: weight / (number of active rays * dpath), see amr_transport_leaf
   double pad1;
@@ -88,6 +88,8 @@ struct AmrParams {
   uint8_t* done;           // [group][slot][8]
   const int32_t* slotOf[8];  // per reflection combination: position of every leaf in the wave order
   const int32_t* sorted[8];  // ... and its inverse
+  int noThin;                // experiments: FAST arithmetic on thin layers as well
+  int slotIsLeaf;            // tuning "amr_slots" = 0: per-item arrays indexed by leaf number instead (the round-1 layout)
   double* J;               // [3][N]
   int32_t* err;
   int64_t N;
@@ -199,7 +201,9 @@ __global__ void amr_neighbour_kernel(AmrParams P, int ngroups) {
     }
     if (P.nbc) {
       const int32_t* so = P.slotOf[D.combo];
-      P.nbc[item_index(P, gi, lane, so[leaf]) * 4 + ray] = result >= 0 ? ((so[result] << 3) | code) : result;
+      const int64_t mySlot = P.slotIsLeaf ? leaf : so[leaf];
+      const int32_t nbSlot = result >= 0 ? (P.slotIsLeaf ? result : so[result]) : result;
+      P.nbc[item_index(P, gi, lane, mySlot) * 4 + ray] = result >= 0 ? ((nbSlot << 3) | code) : result;
     }
   }
 }
@@ -243,31 +247,19 @@ __device__ __forceinline__ void load_record(const double* p, double (&v)[3]) {
   }
 }
 
-// one item with the reference's operation sequence (the thin layers of FAST arithmetic), out of line
-struct ThinIn {
-  double Iin[3][3], kap[3], dpath[3], w;
-  bool active[3];
+// one segment (three frequency groups) with the reference's operation sequence: the thin segments of FAST arithmetic,
+// out of line so that the libm exp / log and the two divisions cost the common path no registers
+struct ThinSeg {
+  double out[3], J[3];
 };
-struct ThinOut {
-  double out[3][3], Jc[3];
-};
-__device__ __noinline__ ThinOut amr_item_reference_sequence(ThinIn in) {
-  ThinOut o;
-  double Jm[3] = {0., 0., 0.};
-  int imean = 0;
-  const int order[3] = {0, 2, 1};                                    // the reference processes xy, then xz, then yz
-  for (int q = 0; q < 3; q++) {
-    const int ray = order[q];
-    for (int g = 0; g < 3; g++) o.out[ray][g] = 0.;
-    if (!in.active[ray]) continue;
-    for (int g = 0; g < 3; g++) {
-      SegResult sr = segment_update<true, 0>(in.Iin[ray][g], in.kap[g], in.dpath[ray], 0., nullptr);
-      o.out[ray][g] = sr.Iout;
-      Jm[g] = __dadd_rn(Jm[g], sr.J);
-    }
-    imean++;
+__device__ __noinline__ ThinSeg amr_thin_segment(double i0, double i1, double i2, double k0, double k1, double k2, double dpath) {
+  ThinSeg o;
+  const double Iin[3] = {i0, i1, i2}, kap[3] = {k0, k1, k2};
+  for (int g = 0; g < 3; g++) {
+    const SegResult sr = segment_update<true, 0>(Iin[g], kap[g], dpath, 0., nullptr);
+    o.out[g] = sr.Iout;
+    o.J[g] = sr.J;
   }
-  for (int g = 0; g < 3; g++) o.Jc[g] = __dmul_rn(__ddiv_rn(Jm[g], (double)imean), in.w);
   return o;
 }
 
@@ -341,39 +333,9 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
   double Jm[3] = {0., 0., 0.};
   double xy[3] = {0., 0., 0.};
   int imean = 0;
-  if (!FAITHFUL && pat.thin) {
-    // rare (0.2% of the layers): the reference's operation sequence, out of line so that it costs the common path no
-    // registers
-    ThinIn in;
-#pragma unroll
-    for (int ray = 0; ray < 3; ray++) {
-      in.dpath[ray] = dpath[ray];
-      in.active[ray] = nbl[ray] != -2;
-#pragma unroll
-      for (int g = 0; g < 3; g++) in.Iin[ray][g] = Iin[ray][g];
-    }
-#pragma unroll
-    for (int g = 0; g < 3; g++) in.kap[g] = kap[g];
-    in.w = D.w;
-    const ThinOut o = amr_item_reference_sequence(in);
-#pragma unroll
-    for (int ray = 0; ray < 3; ray++) {
-      if (nbl[ray] == -2) continue;
-      double* mine = P.Iout + iout_record(P, gi, lane, ray, slot);
-      mine[0] = o.out[ray][0]; mine[1] = o.out[ray][1]; mine[2] = o.out[ray][2];
-    }
-    if (L > 0) {
-      const double tmp = __dadd_rn(__dadd_rn(o.out[0][0], o.out[0][1]), o.out[0][2]);
-      if (!(tmp < 1.e-20 && tmp > -1.e-20)) atomicMax(P.err, RTB200_ERR_INTENSITY_GUARD);
-    }
-#pragma unroll
-    for (int g = 0; g < 3; g++) Jc[g] = o.Jc[g];
-    if (CHECK) {
-      __threadfence();
-      ((volatile uint8_t*)P.done)[item] = 1;
-    }
-    return true;
-  }
+  const int thinMask = (!FAITHFUL && !P.noThin) ? pat.thin : 0;
+  const double kapRaw[3] = {kap[0], kap[1], kap[2]};
+  double Jthin[3] = {0., 0., 0.};   // thin segments: sum of the reference-formula segment means (divided by nseg, times w below)
   if (!FAITHFUL) {
 #pragma unroll
     for (int g = 0; g < 3; g++) kap[g] = kap[g] > 0. ? kap[g] : kAmrKappaFloor;
@@ -392,6 +354,10 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
         out[g] = sr.Iout;
         Jm[g] = __dadd_rn(Jm[g], sr.J);
       }
+    } else if (thinMask & (1 << ray)) {
+      const ThinSeg t = amr_thin_segment(Iin[ray][0], Iin[ray][1], Iin[ray][2], kapRaw[0], kapRaw[1], kapRaw[2], dpath[ray]);
+#pragma unroll
+      for (int g = 0; g < 3; g++) { out[g] = t.out[g]; Jthin[g] = __dadd_rn(Jthin[g], t.J[g]); }
     } else {
       const double cs = pat.cs[ray];
 #pragma unroll
@@ -407,7 +373,13 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
     if (!(tmp < 1.e-20 && tmp > -1.e-20)) atomicMax(P.err, RTB200_ERR_INTENSITY_GUARD);
   }
 #pragma unroll
-  for (int g = 0; g < 3; g++) Jc[g] = FAITHFUL ? __dmul_rn(__ddiv_rn(Jm[g], (double)imean), D.w) : Jm[g] * invk[g];
+  for (int g = 0; g < 3; g++) {
+    if (FAITHFUL) Jc[g] = __dmul_rn(__ddiv_rn(Jm[g], (double)imean), D.w);
+    else {
+      Jc[g] = Jm[g] * invk[g];
+      if (thinMask) Jc[g] += __dmul_rn(__ddiv_rn(Jthin[g], (double)imean), D.w);   // the thin segments' share of sum(J) / nseg * w
+    }
+  }
   if (CHECK) {
     __threadfence();
     ((volatile uint8_t*)P.done)[item] = 1;
@@ -424,8 +396,8 @@ struct WaveParams {
 };
 
 // block = 16 leaves of the wave x 8 direction lanes; blockIdx.y = group of the batch
-template <bool FAITHFUL, bool CHECK>
-__global__ void __launch_bounds__(128, 8) amr_wave_kernel(AmrParams P, WaveParams Wp, int ngroups) {
+template <bool FAITHFUL, bool CHECK, int MINB = 8>
+__global__ void __launch_bounds__(128, MINB) amr_wave_kernel(AmrParams P, WaveParams Wp, int ngroups) {
   __shared__ double sT[16];
   asm volatile("griddepcontrol.launch_dependents;");               // the next wave may start its prologue early
   if (!FAITHFUL) {
@@ -441,8 +413,9 @@ __global__ void __launch_bounds__(128, 8) amr_wave_kernel(AmrParams P, WaveParam
   const bool mine = have && lane < grp.y;
   double Jc[3] = {0., 0., 0.};
   int64_t leaf = 0;
-  const int64_t slot = Wp.begin[combo] + i;
+  int64_t slot = Wp.begin[combo] + i;
   if (have) leaf = Wp.sorted[combo][slot];
+  if (P.slotIsLeaf) slot = leaf;
   bool deferred = false;
   if (mine) {
     const int d = grp.x + lane;
@@ -490,7 +463,7 @@ __global__ void amr_retry_kernel(AmrParams P, const int64_t* in, const int32_t* 
     const int64_t item = in[i];
     const int d = (int)(item >> 32);
     const int64_t slot = item & 0xffffffffLL;
-    const int64_t leaf = P.sorted[P.dirs[d].combo][slot];
+    const int64_t leaf = P.slotIsLeaf ? slot : P.sorted[P.dirs[d].combo][slot];
     double Jc[3];
     if (!amr_transport_leaf<FAITHFUL, true>(P, d, P.dirs[d].group, P.dirs[d].lane, leaf, slot, Jc, sT)) {
       int q = atomicAdd(outCount, 1);
@@ -512,7 +485,7 @@ __global__ void amr_merge_kernel(AmrParams P, int ngroups) {
     for (int gi = 0; gi < ngroups; gi++) {
       if (ITEMS) {
         const int combo = P.dirs[P.groups[gi].x].combo;
-        const double* q = P.JI + item_index(P, gi, 0, P.slotOf[combo][leaf]) * 3;
+        const double* q = P.JI + item_index(P, gi, 0, P.slotIsLeaf ? leaf : P.slotOf[combo][leaf]) * 3;
 #pragma unroll
         for (int g = 0; g < 3; g++) {
           const double a = __dadd_rn(__dadd_rn(q[g], q[3 + g]), __dadd_rn(q[6 + g], q[9 + g]));
@@ -545,7 +518,7 @@ static DevPattern to_dev(const RayPattern& p, double cellSize, int level, double
   q.active[0] = 1; q.active[1] = p.yzActive; q.active[2] = p.xzActive;
   const int nseg = 1 + (p.yzActive ? 1 : 0) + (p.xzActive ? 1 : 0);
   for (int r = 0; r < 3; r++)
-    if (q.active[r] && len[r] < 1e-3) q.thin = 1;
+    if (q.active[r] && len[r] < 1e-3) q.thin |= (int8_t)(1 << r);
   for (int r = 0; r < 3; r++) q.cs[r] = q.active[r] && q.dpath[r] > 0. ? weight / ((double)nseg * q.dpath[r]) : 0.;
   return q;
 }
@@ -847,6 +820,7 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int g0, int ng
   P.Iout = B.Iout; P.done = B.done; P.J = dJ; P.err = c.dErr; P.N = N; P.n = c.nx; P.maxLevel = c.maxLevel;
   P.nbc = B.nbc; P.patIdx = S.plan.dPatIdx; P.kappaA = B.kappaA; P.JA = B.JA; P.JS = B.JS; P.JI = B.JI;
   for (int k = 0; k < 8; k++) { P.slotOf[k] = S.plan.dSlotOf[k]; P.sorted[k] = S.plan.dSorted[k]; }
+  P.slotIsLeaf = c.tune.amrSlots == 0; P.noThin = c.tune.amrThin == 0;
   P.u0 = uvb[0]; P.u1 = uvb[1]; P.u2 = uvb[2];
   P.cellSize0 = c.boxSize / (double)c.nx;  // equiSources.f90:1570
   // neighbour threading is geometry only (grid + directions): when one batch holds every direction of the call, the
@@ -891,7 +865,8 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int g0, int ng
       else RTB_CUDA(cudaLaunchKernelEx(&cfg, amr_wave_kernel<true, false>, P, Wp, ng));
     } else {
       if (check) RTB_CUDA(cudaLaunchKernelEx(&cfg, amr_wave_kernel<false, true>, P, Wp, ng));
-      else RTB_CUDA(cudaLaunchKernelEx(&cfg, amr_wave_kernel<false, false>, P, Wp, ng));
+      else if (c.tune.amrMinBlocks <= 6) RTB_CUDA(cudaLaunchKernelEx(&cfg, amr_wave_kernel<false, false, 6>, P, Wp, ng));
+      else RTB_CUDA(cudaLaunchKernelEx(&cfg, amr_wave_kernel<false, false, 8>, P, Wp, ng));
     }
     prevWasWave = true;
     (*launches)++;
@@ -943,7 +918,7 @@ int diffuse_amr(Context& c, int nAngularLevel, const double* uvb, const std::vec
   std::string tkey = S.key;
   {
     char buf[48];
-    snprintf(buf, sizeof(buf), "|%d|%a|", nAngularLevel, c.boxSize);
+    snprintf(buf, sizeof(buf), "|%d|%a|%d|", nAngularLevel, c.boxSize, c.tune.amrSlots);
     tkey += buf;
     for (const auto& d : dirs) { snprintf(buf, sizeof(buf), "%lld,", (long long)d.iray); tkey += buf; }
   }

@@ -267,7 +267,7 @@ sweep_cell_kernel(const __grid_constant__ BatchParams bp, int N, int n, int np1,
   asm volatile("griddepcontrol.launch_dependents;");
   if (threadIdx.y == 0 && threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
   __syncthreads();
-  const int a = blockIdx.x * 31 - 1 + (int)threadIdx.x, b = blockIdx.y * 8 + threadIdx.y;
+  const int a = blockIdx.x * 31 - 1 + (int)threadIdx.x, b = blockIdx.y * blockDim.y + threadIdx.y;
   if (b >= n) return;                                          // warp-uniform
   const bool inRow = a < n;                                    // lanes beyond the row only take part in the shuffles
   const bool writer = inRow && threadIdx.x >= 1;
@@ -400,7 +400,7 @@ sweep_cell2_kernel(const __grid_constant__ BatchParams bp, int N, int n, int np1
   asm volatile("griddepcontrol.launch_dependents;");
   if (threadIdx.y == 0 && threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
   __syncthreads();
-  const int a = blockIdx.x * 31 - 1 + (int)threadIdx.x, b0 = 2 * (blockIdx.y * 8 + threadIdx.y);
+  const int a = blockIdx.x * 31 - 1 + (int)threadIdx.x, b0 = 2 * (blockIdx.y * blockDim.y + threadIdx.y);
   if (b0 >= n) return;                                         // warp-uniform
   const bool row1 = b0 + 1 < n;                                // warp-uniform: the upper row exists
   const bool inRow = a < n;
@@ -814,11 +814,15 @@ static int march_capacity(Context& c, size_t smemBytes, int* blocks) {
   return RTB200_OK;
 }
 
+// `warps` = rows of the layer a block covers with one warp each (8, 4 or 2): small direction shards (multi-GPU ranks) put
+// only a few hundred 8-warp blocks on the device per layer, 1.5 "waves" of which cost as much as 2; smaller blocks
+// spread the same rows evenly over the SMs
 template <class Kernel>
-static cudaError_t launch_layer(Kernel kern, dim3 grid, cudaStream_t s, bool pdl, const BatchParams& bp, int N, int n) {
+static cudaError_t launch_layer(Kernel kern, dim3 grid, cudaStream_t s, bool pdl, const BatchParams& bp, int N, int n,
+                                int warps = 8) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(32, 8);
+  cfg.blockDim = dim3(32, warps);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = s;
   cudaLaunchAttribute at[1];
@@ -832,21 +836,30 @@ static cudaError_t launch_layer(Kernel kern, dim3 grid, cudaStream_t s, bool pdl
 // `pdl`: programmatic dependent launch on the previous launch of the stream (only for a layer whose predecessor in
 // the stream is the previous layer's sweep kernel)
 static cudaError_t launch_cells(int dense, int expv, bool faithful, bool pdl, dim3 grid, cudaStream_t s,
-                                const BatchParams& bp, int N, int n, int cells) {
+                                const BatchParams& bp, int N, int n, int cells, int warps, int smCount) {
   // `dense`: 0 = compiler's choice of registers (2 blocks per SM), 1 = cap for 3 blocks, 2 = cap for 4 blocks
-  if (faithful) return launch_layer(sweep_cell_kernel<true, 0, 2>, grid, s, pdl, bp, N, n);
-  if (cells == 2 && expv == 1) {   // two cells per thread: half the rows per block
-    grid.y = (unsigned)((n + 15) / 16);
+  if (cells == 0) cells = n >= 192 ? 2 : 1;
+  if (faithful || expv != 1) cells = 1;
+  const int rowsTotal = cells == 2 ? (n + 1) / 2 : n;           // rows of threads per task and layer
+  if (warps != 8 && warps != 4 && warps != 2) {
+    // automatic: the largest block that still gives the device ~6 blocks per resident 8-warp slot
+    const long long slots = (long long)smCount * (cells == 2 ? 2 : 4);
+    warps = 8;
+    while (warps > 2 && (long long)grid.x * ((rowsTotal + warps - 1) / warps) * grid.z < 6 * slots) warps /= 2;
+  }
+  grid.y = (unsigned)((rowsTotal + warps - 1) / warps);
+  if (faithful) return launch_layer(sweep_cell_kernel<true, 0, 2>, grid, s, pdl, bp, N, n, warps);
+  if (cells == 2) {   // two cells per thread
     // register budget: default 2 blocks of 256 threads per SM (119 registers, no spills; as many cells in flight as
     // the single-cell kernel at 4 blocks); "dense" 3 / 4 cap the registers for 3 / 4 blocks
-    if (dense >= 4) return launch_layer(sweep_cell2_kernel<1, 4>, grid, s, pdl, bp, N, n);
-    if (dense == 3) return launch_layer(sweep_cell2_kernel<1, 3>, grid, s, pdl, bp, N, n);
-    return launch_layer(sweep_cell2_kernel<1, 2>, grid, s, pdl, bp, N, n);
+    if (dense >= 4) return launch_layer(sweep_cell2_kernel<1, 4>, grid, s, pdl, bp, N, n, warps);
+    if (dense == 3) return launch_layer(sweep_cell2_kernel<1, 3>, grid, s, pdl, bp, N, n, warps);
+    return launch_layer(sweep_cell2_kernel<1, 2>, grid, s, pdl, bp, N, n, warps);
   }
-#define RTB_LAUNCH(E)                                                                             \
-  if (dense == 1) return launch_layer(sweep_cell_kernel<false, E, 3>, grid, s, pdl, bp, N, n);    \
-  else if (dense >= 2) return launch_layer(sweep_cell_kernel<false, E, 4>, grid, s, pdl, bp, N, n); \
-  else return launch_layer(sweep_cell_kernel<false, E, 2>, grid, s, pdl, bp, N, n)
+#define RTB_LAUNCH(E)                                                                                    \
+  if (dense == 1) return launch_layer(sweep_cell_kernel<false, E, 3>, grid, s, pdl, bp, N, n, warps);    \
+  else if (dense >= 2) return launch_layer(sweep_cell_kernel<false, E, 4>, grid, s, pdl, bp, N, n, warps); \
+  else return launch_layer(sweep_cell_kernel<false, E, 2>, grid, s, pdl, bp, N, n, warps)
   if (expv == 1) { RTB_LAUNCH(1); } else { RTB_LAUNCH(0); }
 #undef RTB_LAUNCH
 }
@@ -944,8 +957,8 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
   std::string planKey;
   {
     char buf[128];
-    snprintf(buf, sizeof(buf), "%d:%a:%d:%d:%d:%d:%d:%d:", n, c.boxSize, nAngularLevel, c.tune.slots, c.tune.lockstep, c.tune.dirsPerTask,
-             c.tune.transposeZ, c.tune.march);
+    snprintf(buf, sizeof(buf), "%d:%a:%d:%d:%d:%d:%d:%d:%d:", n, c.boxSize, nAngularLevel, c.tune.slots, c.tune.lockstep, c.tune.dirsPerTask,
+             c.tune.transposeZ, c.tune.march, c.tune.blockWarps);
     planKey = buf;
     for (const auto& d : dirs) { snprintf(buf, sizeof(buf), "%lld,", (long long)d.iray); planKey += buf; }
   }
@@ -974,7 +987,9 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
             maxPiece = std::max(maxPiece, (perZone[z] + pieces - 1) / pieces);
           }
         if (T == 0 || T > kMaxBatch) continue;
-        const double waves = std::ceil((double)(T * bpt) / (double)cap);
+        // with the block size chosen per launch (block_warps = 0) a partly filled last wave costs its share only
+        const double fill = (double)(T * bpt) / (double)cap;
+        const double waves = c.tune.blockWarps == 0 ? std::max(1.0, fill) : std::ceil(fill);
         const double cost = waves * (maxPiece + 1.5);
         if (cost < best * 0.97) { best = cost; dpt = d; }   // prefer larger pieces unless clearly better
       }
@@ -1138,7 +1153,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
           }
           dim3 gz = grid;
           gz.z = nb;
-          RTB_CUDA(launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, c.tune.pdl && step > 0, gz, st, bp, (int)N, n, c.tune.cells));
+          RTB_CUDA(launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, c.tune.pdl && step > 0, gz, st, bp, (int)N, n, c.tune.cells, c.tune.blockWarps, c.smCount));
           nLaunched++;
         }
       }
@@ -1153,7 +1168,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
         if (T.slot != k) continue;
         for (int step = 0; step < n; step++) {
           fill(bp.t[0], T, step, T.firstInSlot);
-          RTB_CUDA(launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, c.tune.pdl && step > 0, grid, cs, bp, (int)N, n, c.tune.cells));
+          RTB_CUDA(launch_cells(c.tune.minBlocks, c.tune.expVariant, faithful, c.tune.pdl && step > 0, grid, cs, bp, (int)N, n, c.tune.cells, c.tune.blockWarps, c.smCount));
           nLaunched++;
         }
       }
@@ -1170,7 +1185,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
     char key[256];
     snprintf(key, sizeof(key), "u:%d:%d:%d:%d:%p:%p:%p:%a:%a:%a", n, ntask, slots,
              (int)faithful * 64 + c.tune.minBlocks * 4 + c.tune.expVariant + 1000 * c.tune.lockstep + 10000 * c.tune.pdl +
-                 100000 * c.tune.cells,
+                 100000 * c.tune.cells + 1000000 * c.tune.blockWarps,
              (void*)c.dAcc, (void*)c.dPlanes, (void*)c.dKappa, uvb[0], uvb[1], uvb[2]);
     if (!c.graphExec || c.graphKey != key) {
       if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }

@@ -100,7 +100,7 @@ struct PointParams {
   unsigned int* rayCount;       // plan pass only: [rays of the batch] segments of every ray object
   const long long* rayBase;     // [rays of the batch] first index of the ray's segments in slotMap
   const unsigned int* slotMap;  // [records] (rayBase[ray] + segment) -> position in leaf order
-  double* recVal6;              // [records][6] deposits in leaf order
+  double* recVal6;              // [records][8] deposits in leaf order: six values + pad = one aligned 64-byte DRAM atom
   int* queue;             // [nsrc] next pixel of the last level to hand out (NULL: static pixel -> thread map)
   // optional traversal trace (parity checks)
   long long* trace;       // [cap][2]
@@ -377,6 +377,7 @@ __global__ void __launch_bounds__(128, MINB) point_march_kernel(const __grid_con
   int strategy = 0;      // 0 = no ray, 1 = proceed, 2 = split, 3 = boundary / dead
   int irLow = 0;
   unsigned raySeg = 0;   // index of the current segment along its ray
+  long long myRayBase = 0;   // planned deposition: first slot-map entry of this thread's ray
 
   // start of ray `ip` of this level; false when the ray does not exist (parent not split, start outside the box, ...)
   auto init_ray = [&](int64_t ip) -> bool {
@@ -477,6 +478,7 @@ __global__ void __launch_bounds__(128, MINB) point_march_kernel(const __grid_con
   if (!refill) {
     have0 = ipix0 < npix && weight > 0 && init_ray(ipix0);
     strategy = have0 ? 1 : 0;
+    if (DEPOSIT == 2 && have0) myRayBase = __ldg(P.rayBase + (long long)s * P.raysPerSource + pix_offset(pixelLevel) + ipix0);
   }
   {
     for (;;) {
@@ -637,10 +639,10 @@ __global__ void __launch_bounds__(128, MINB) point_march_kernel(const __grid_con
       }
       if (DEPOSIT == 2) {
         // planned: this segment's slot in the leaf-ordered record array is known from the plan pass
-        const long long ray = (long long)s * P.raysPerSource + pix_offset(pixelLevel) + ipix;
-        const unsigned int slot = __ldg(P.slotMap + __ldg(P.rayBase + ray) + (raySeg - 1));
-        double2* rec = reinterpret_cast<double2*>(P.recVal6 + (size_t)slot * 6);
+        const unsigned int slot = __ldg(P.slotMap + myRayBase + (raySeg - 1));
+        double2* rec = reinterpret_cast<double2*>(P.recVal6 + (size_t)slot * 8);
         rec[0] = make_double2(dep[0], dep[1]); rec[1] = make_double2(dep[2], dep[3]); rec[2] = make_double2(dep[4], dep[5]);
+        rec[3] = make_double2(0., 0.);   // the whole 64-byte record is written: no read-modify-write of a partial DRAM atom
       } else if (DEPOSIT == 1) {
         // one record per segment; slots are handed out per warp (one counter update for the active lanes)
         const unsigned m = __activemask();
@@ -792,7 +794,7 @@ __global__ void planned_reduce_kernel(const int32_t* __restrict__ sortedLeaf, co
     if (i > 0 && sortedLeaf[i - 1] == leaf) continue;
     double sum[6] = {0., 0., 0., 0., 0., 0.};
     for (long long j = i; j < n && sortedLeaf[j] == leaf; j++) {
-      const double2* r = reinterpret_cast<const double2*>(val6 + (size_t)j * 6);
+      const double2* r = reinterpret_cast<const double2*>(val6 + (size_t)j * 8);
       const double2 a = r[0], b = r[1], c = r[2];
       sum[0] = __dadd_rn(sum[0], a.x); sum[1] = __dadd_rn(sum[1], a.y); sum[2] = __dadd_rn(sum[2], b.x);
       sum[3] = __dadd_rn(sum[3], b.y); sum[4] = __dadd_rn(sum[4], c.x); sum[5] = __dadd_rn(sum[5], c.y);
@@ -1031,7 +1033,7 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
   if (planned) {
     long long mx = 1;
     for (const auto& b : plan->batches) mx = std::max(mx, b.nrec);
-    if (int st = sc.get(&dRecVal6, (size_t)mx * 6)) return st;
+    if (int st = sc.get(&dRecVal6, (size_t)mx * 8)) return st;
   }
   long long *dRecKey = nullptr, *dRecKeyOut = nullptr;
   uint32_t *dRecIdx = nullptr, *dRecIdxOut = nullptr;
@@ -1103,8 +1105,8 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
     const int bi = b0 / batch;
     if (planned) {
       const PointPlan::Batch& pb = plan->batches[(size_t)bi];
+      // (no clearing of the records: without dust no ray ends early, so every slot of the plan is written again)
       P.rayBase = pb.rayBase; P.slotMap = pb.slotMap;
-      RTB_CUDA(cudaMemsetAsync(dRecVal6, 0, (size_t)pb.nrec * 6 * sizeof(double), s));
     }
     RayState *stIn = dStA, *stOut = dStB;
     for (int L = 1; L <= in.maxPixelLevel; L++) {

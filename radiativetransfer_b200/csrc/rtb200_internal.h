@@ -64,6 +64,9 @@ struct Tuning {
   int slots = 0;         // zones swept concurrently (independent streams), each with its own J accumulator (0 = 24)
   int useGraph = 1;
   int forceAmr = 0;      // route uniform grids through the general (AMR) path as well (cross-check)
+  int amrSlots = 1;      // nested grids: per-item arrays indexed by the leaf's position in the wave order (1) or by leaf number (0)
+  int amrMinBlocks = 8;  // nested grids, FAST arithmetic: blocks of 128 threads per SM the wave kernel's register cap allows (8: 64, 6: 80 registers)
+  int amrThin = 1;       // nested grids, FAST arithmetic: thin layers use the reference's operation sequence (1)
   int amrBatch = 0;      // directions per AMR batch (0 = as many as fit in half of the free memory)
   int lockstep = 1;      // 1: one launch per layer for all zones of a batch; 0: every slot an independent stream
   int minBlocks = 2;     // 0: compiler's register choice (2 blocks per SM); 1: cap for 3 blocks; 2: cap for 4 blocks
@@ -71,12 +74,14 @@ struct Tuning {
   double l2BudgetMB = 96.0;
   int march = 0;         // uniform sweep: 1 = persistent layer-marching kernel (experimental, slower: DESIGN.md)
   int pdl = 1;           // uniform sweep: programmatic dependent launch of layer l+1 on layer l (its prologue overlaps the tail)
-  int cells = 2;         // uniform sweep, FAST arithmetic: cells of a layer per thread (2: two rows per warp, see sweep_cell2_kernel)
+  int blockWarps = 0;    // uniform sweep: rows (warps) per block: 8, 4, 2, or 0 = chosen from the number of blocks per launch
+  int cells = 0;         // uniform sweep, FAST arithmetic: cells of a layer per thread (2: two rows per warp, see
+                         // sweep_cell2_kernel; 0 = 2 from n = 192 on, where it measured 1-2% faster, else 1: 6% faster at 128^3)
   int transposeZ = 1;    // uniform sweep: zones sweeping along the contiguous axis use a z-major copy of kappa / J
   int dirsPerTask = 0;   // directions of one zone swept together (0 = kMaxDirPerTask)
   int marchDebug = 0;    // experiments only: 1 = skip the neighbour polling (wrong results), 2 = spin without nanosleep
   int portableMath = 1;  // point path, FAITHFUL mode: exp/log from portable_math.h (bit-identical on host and device)
-  int pointDeposit = 0;  // point path: 0 = fp64 RED.ADD into the rate fields, 1 = atomic-free: (leaf, deposit) records,
+  int pointDeposit = 2;  // point path: 0 = fp64 RED.ADD into the rate fields, 1 = atomic-free: (leaf, deposit) records,
                          // radix sort by (leaf, ray, segment), one thread per cell adds its run (deterministic order),
                          // 2 = planned: as 1, but the sort is done once per (grid, sources) and every later pass writes
                          // its deposits to their cached leaf-ordered slots (falls back to 1 with dust)

@@ -21,9 +21,13 @@ def main():
 
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("gloo")          # plumbing only: broadcasts the NCCL unique id of the library's own group
-    uid = [rt.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
+    dist.init_process_group("gloo")          # plumbing only: broadcasts the NCCL unique ids of the library's own groups
+
+    def new_uid():                            # every communicator needs a fresh id
+        uid = [rt.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        return uid[0]
+
     bg = W.uvb_background(3.0)
     ksi = np.concatenate([bg["ksi24"], bg["ksi25"], bg["ksi26"]])
     spectra = W.synthetic_spectra()
@@ -36,7 +40,7 @@ def main():
         p1 = one.point(spectra, src, wt)
         one.close()
         for mode in (1, 0):
-            grp = rt.Transport(device=local, comm=(world, rank, uid[0]))
+            grp = rt.Transport(device=local, comm=(world, rank, new_uid()))
             grp.set_tuning(multi_reduce=mode)
             grp.set_grid(g["nx"], g["level"], g["HI"], g["HeI"], g["HeII"], g["rho"], g["abun2"], g["box_size"])
             info = grp.info()

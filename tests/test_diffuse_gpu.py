@@ -61,6 +61,29 @@ def test_uniform_result_independent_of_launch_tuning(rt, engine, oracle, uvbg, s
     assert rel_err(J, o["J"]) < TOL
 
 
+@pytest.mark.parametrize("n", [20, 33, 47])
+def test_cells_per_thread_and_block_size_do_not_change_a_bit(rt, engine, oracle, uvbg, n):
+    """FAST arithmetic: one or two cells of a layer per thread (the upper cell takes the row hand-over from registers
+    instead of recomputing it), 8 / 4 / 2 rows per block: identical bits, odd and even row counts, ragged last strip"""
+    g = W.uniform_grid(n, seed=n)
+    _set(engine, g)
+    ref = None
+    for cells, warps, dense in ((1, 8, 2), (2, 8, 2), (2, 4, 2), (2, 2, 3), (1, 2, 0), (2, 8, 4), (0, 0, 2)):
+        engine.set_tuning(cells=cells, block_warps=warps, dense=dense)
+        J, _ = engine.diffuse(uvbg["uvb"], uvbg["beta"])
+        if ref is None:
+            ref = J
+            assert rel_err(J, _oracle_J(oracle, g, uvbg)["J"]) < TOL
+        assert np.array_equal(J, ref), (cells, warps, dense)
+    # a direction shard (few zone tasks per launch) takes the automatic small blocks
+    engine.set_tuning(cells=0, block_warps=0, dense=2)
+    rays = np.arange(40, 64, dtype=np.int32)
+    Ja, _ = engine.diffuse(uvbg["uvb"], uvbg["beta"], rays=rays)
+    engine.set_tuning(cells=1, block_warps=8)
+    Jb, _ = engine.diffuse(uvbg["uvb"], uvbg["beta"], rays=rays)
+    assert rel_err(Ja, Jb) < 1e-13        # the zone pieces (summation order) may be cut differently
+
+
 def test_uniform_optically_thick_and_thin_extremes(rt, engine, oracle, uvbg):
     # optically thick: per-segment tau up to ~450, intensities underflow to zero deep inside
     g = W.uniform_grid(24, seed=12, tau_lo=1e-3, tau_hi=150.0)

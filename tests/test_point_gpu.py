@@ -257,6 +257,7 @@ def test_segmented_deposition_is_deterministic_and_atomic_free(rt, engine, porta
     rng = np.random.default_rng(8)
     leaves = rng.choice(g["level"].size, 5, replace=False).astype(np.int32)
     wts = np.array([1, 2, 0, 3, 1], dtype=np.int32)
+    engine.set_tuning(point_deposit=0)
     atom = engine.point(spectra, leaves, wts, dust_approximation=1)
     engine.set_tuning(point_deposit=1)
     seg1 = engine.point(spectra, leaves, wts, dust_approximation=1)
@@ -426,6 +427,7 @@ def test_planned_deposition_atomic_free_and_reproducible(rt, engine, portable, s
     rng = np.random.default_rng(8)
     leaves = rng.choice(g["level"].size, 70, replace=False).astype(np.int32)      # more than one batch of 64 sources
     wts = rng.integers(0, 3, 70).astype(np.int32)
+    engine.set_tuning(point_deposit=0)
     atom = engine.point(spectra, leaves, wts)
     engine.set_tuning(point_deposit=1)
     srt = engine.point(spectra, leaves, wts)

@@ -1,5 +1,6 @@
 """times every rank's direction shard of an N-GPU run on ONE GPU (the sweep of a shard does not depend on the other
-ranks), for the zone-class cost factors of the sharding rule: python tools/shard_times.py [world] [zx zy zz]"""
+ranks), for the zone-class cost factors of the sharding rule and the block size of small shards:
+python tools/shard_times.py [world] [block_warps ...]"""
 import os, sys
 import numpy as np
 import torch
@@ -8,24 +9,27 @@ import radiativetransfer_b200 as rt
 from radiativetransfer_b200 import sharding, workloads as W
 n = 256
 world = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-zc = [float(x) for x in sys.argv[2:5]] if len(sys.argv) >= 5 else None
+variants = [int(x) for x in sys.argv[2:]] or [0]
 bg = W.uvb_background(3.0)
 g = W.uniform_grid(n, seed=1)
 t = rt.Transport(device=0)
 t.set_grid(g["nx"], g["level"], g["HI"], g["HeI"], g["HeII"], g["rho"], g["abun2"], g["box_size"])
 J = torch.zeros(3, n ** 3, dtype=torch.float64, device="cuda:0")
 s = torch.cuda.current_stream().cuda_stream
-shards = sharding.shard_directions(world, n_angular_level=3, nx=n, zone_cost=zc)
+shards = sharding.shard_directions(world, n_angular_level=3, nx=n)
 zone, cost = sharding.direction_costs(3, 64)
-times = []
-for rank in range(world):
-    for rep in range(4):
-        t.diffuse_device(bg["uvb"], bg["beta"], J.data_ptr(), rays=shards[rank], stream=s)
-        torch.cuda.synchronize()
-        st = t.last_stats()
-    zs = sorted(set(int(zone[r]) for r in shards[rank]))
-    times.append(st["sweep_ms"])
-    print(f"world {world} zone_cost {zc} rank {rank} ndir {len(shards[rank])} zones {zs} segs/col {cost[shards[rank]].sum():.0f}: "
-          f"sweep_ms {st['sweep_ms']:.3f} total_ms {st['device_ms']:.3f} launches {st['launches']}", flush=True)
-print(f"world {world} zone_cost {zc}: sweep max {max(times):.3f} mean {np.mean(times):.3f} max/mean {max(times) / np.mean(times):.4f}")
+for bw in variants:
+    t.set_tuning(block_warps=bw)
+    times, totals = [], []
+    for rank in range(world):
+        for rep in range(4):
+            t.diffuse_device(bg["uvb"], bg["beta"], J.data_ptr(), rays=shards[rank], stream=s)
+            torch.cuda.synchronize()
+            st = t.last_stats()
+        zs = sorted(set(int(zone[r]) for r in shards[rank]))
+        times.append(st["sweep_ms"]); totals.append(st["device_ms"])
+        print(f"world {world} block_warps {bw} rank {rank} ndir {len(shards[rank])} zones {zs} segs/col {cost[shards[rank]].sum():.0f}: "
+              f"sweep_ms {st['sweep_ms']:.3f} total_ms {st['device_ms']:.3f} launches {st['launches']}", flush=True)
+    print(f"world {world} block_warps {bw}: sweep max {max(times):.3f} mean {np.mean(times):.3f} max/mean {max(times) / np.mean(times):.4f}; "
+          f"call (opacities + sweep + merge) max {max(totals):.3f}", flush=True)
 t.close()
