@@ -245,6 +245,7 @@ constexpr int kMaxBatch = 40;  // tasks per launch: 40 x 728 B of parameters (th
 struct BatchParams {
   StepParams t[kMaxBatch];
 };
+static_assert(sizeof(BatchParams) + 64 <= 32764, "kernel parameter space");
 
 // gridDim.z tasks (zones) per launch, all at the same layer index: one launch per layer keeps the device full
 // (thousands of blocks) instead of many small concurrent kernels.

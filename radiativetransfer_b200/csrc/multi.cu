@@ -467,10 +467,10 @@ int shard_directions(int nranks, int nAngularLevel, const int32_t* rays, int32_t
   if (!rays && nrays == 0) { list.resize((size_t)total); std::iota(list.begin(), list.end(), 0); }
   else if (nrays < 0) return RTB200_ERR_ARG;
   else list.assign(rays, rays + nrays);
-  struct Piece { std::vector<int32_t> r; double cost; };
+  struct Piece { std::vector<int32_t> r; double cost; int cls; };
   std::vector<Piece> pieces;
   std::vector<double> cost(list.size());
-  std::vector<int> zone(list.size());
+  std::vector<int> zone(list.size()), cls(list.size());
   std::vector<RayPattern> pat;
   const int np = std::min(nx, 64);   // segments per column scale with the layer count; 64 layers rank the directions
   for (size_t i = 0; i < list.size(); i++) {
@@ -489,11 +489,12 @@ int shard_directions(int nranks, int nAngularLevel, const int32_t* rays, int32_t
       if (zm.src[a] == 0) sweepAxis = a;   // the physical axis the rotated i runs along
     cost[i] = cst * zoneClassCost[sweepAxis];
     zone[i] = d.izone;
+    cls[i] = sweepAxis;
   }
   for (int z = 1; z <= 24; z++) {
-    Piece p; p.cost = 0;
+    Piece p; p.cost = 0; p.cls = 0;
     for (size_t i = 0; i < list.size(); i++)
-      if (zone[i] == z) { p.r.push_back(list[i]); p.cost += cost[i]; }
+      if (zone[i] == z) { p.r.push_back(list[i]); p.cost += cost[i]; p.cls = cls[i]; }
     if (!p.r.empty()) pieces.push_back(std::move(p));
   }
   auto rayCost = [&](int32_t r) { for (size_t i = 0; i < list.size(); i++) if (list[i] == r) return cost[i]; return 0.0; };
@@ -502,7 +503,7 @@ int shard_directions(int nranks, int nAngularLevel, const int32_t* rays, int32_t
   while ((int)pieces.size() < 3 * nranks) {
     std::sort(pieces.begin(), pieces.end(), bySize);
     if (pieces.empty() || pieces[0].r.size() < 2) break;
-    Piece a, b; a.cost = b.cost = 0;
+    Piece a, b; a.cost = b.cost = 0; a.cls = b.cls = pieces[0].cls;
     const size_t half = pieces[0].r.size() / 2;
     for (size_t i = 0; i < pieces[0].r.size(); i++) {
       Piece& t = i < half ? a : b;
@@ -511,16 +512,51 @@ int shard_directions(int nranks, int nAngularLevel, const int32_t* rays, int32_t
     pieces.erase(pieces.begin());
     pieces.push_back(std::move(a)); pieces.push_back(std::move(b));
   }
-  std::sort(pieces.begin(), pieces.end(), bySize);
-  shards.assign((size_t)nranks, {});
+  // Longest processing time first, ONE SWEEP AXIS AFTER THE OTHER, and no rank takes more than its share of an axis'
+  // pieces: the zones of an axis differ in memory layout (lane axis contiguous or not, z-major copy), and a layer launch
+  // runs all zone tasks of a rank together, so equal segment counts are only equal times when the ranks hold the same
+  // mix (measured: three x-sweeping zones 6.3 ms, a z- and two y-sweeping zones 7.6 ms for the same segment count).
   std::vector<double> load((size_t)nranks, 0.);
-  for (const Piece& p : pieces) {
-    int best = 0;
-    for (int r = 1; r < nranks; r++)
-      if (load[r] < load[best]) best = r;
-    shards[best].insert(shards[best].end(), p.r.begin(), p.r.end());
-    load[best] += p.cost;
+  std::vector<std::vector<int>> owned((size_t)nranks);   // piece indices per rank
+  for (int c = 2; c >= 0; c--) {
+    std::vector<int> mine;
+    for (int i = 0; i < (int)pieces.size(); i++)
+      if (pieces[i].cls == c) mine.push_back(i);
+    std::sort(mine.begin(), mine.end(), [&](int a, int b) { return bySize(pieces[a], pieces[b]); });
+    const int quota = ((int)mine.size() + nranks - 1) / nranks;
+    std::vector<int> taken((size_t)nranks, 0);
+    for (int i : mine) {
+      int best = -1;
+      for (int r = 0; r < nranks; r++)
+        if (taken[r] < quota && (best < 0 || load[r] < load[best])) best = r;
+      owned[best].push_back(i);
+      load[best] += pieces[i].cost;
+      taken[best]++;
+    }
   }
+  // local improvement: swap two pieces of the same sweep axis between two ranks while that lowers the larger of the two
+  // loads (the greedy pass pairs a large x-zone with whatever is left of y and z)
+  for (int pass = 0; pass < 64; pass++) {
+    bool improved = false;
+    for (int a = 0; a < nranks; a++)
+      for (int b = a + 1; b < nranks; b++)
+        for (size_t ia = 0; ia < owned[a].size(); ia++)
+          for (size_t ib = 0; ib < owned[b].size(); ib++) {
+            const Piece& pa = pieces[owned[a][ia]];
+            const Piece& pb = pieces[owned[b][ib]];
+            if (pa.cls != pb.cls) continue;
+            const double na = load[a] - pa.cost + pb.cost, nb = load[b] - pb.cost + pa.cost;
+            if (std::max(na, nb) < std::max(load[a], load[b]) * (1. - 1e-12)) {
+              std::swap(owned[a][ia], owned[b][ib]);
+              load[a] = na; load[b] = nb;
+              improved = true;
+            }
+          }
+    if (!improved) break;
+  }
+  shards.assign((size_t)nranks, {});
+  for (int r = 0; r < nranks; r++)
+    for (int i : owned[r]) shards[r].insert(shards[r].end(), pieces[i].r.begin(), pieces[i].r.end());
   for (auto& s : shards) std::sort(s.begin(), s.end());
   return RTB200_OK;
 }

@@ -26,6 +26,8 @@
 #include <cstdio>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 #include "point_host.h"
 #include "portable_math.h"
@@ -786,16 +788,24 @@ __global__ void plan_slot_kernel(const long long* __restrict__ sortedKey, long l
   }
 }
 
-// one thread per run of equal leaves (the head of the run does the work), records [n][6] in leaf order
-__global__ void planned_reduce_kernel(const int32_t* __restrict__ sortedLeaf, const double* __restrict__ val6, long long n,
+// head of a run of equal leaves in the sorted order (selection predicate of the plan pass)
+struct RunHead {
+  const int32_t* sortedLeaf;
+  __host__ __device__ bool operator()(long long i) const { return i == 0 || sortedLeaf[i - 1] != sortedLeaf[i]; }
+};
+
+// one thread per run of equal leaves (runStart lists the heads; runStart[nruns] = n): every thread streams its own
+// stretch of 64-byte records and adds them up in order -- a fixed order, no atomics; a leaf occurs in one run per batch
+__global__ void planned_reduce_kernel(const int32_t* __restrict__ sortedLeaf, const long long* __restrict__ runStart,
+                                      long long nruns, long long n, const double* __restrict__ val8,
                                       double* __restrict__ rates, int64_t nleaf) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int leaf = sortedLeaf[i];
-    if (i > 0 && sortedLeaf[i - 1] == leaf) continue;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < nruns; r += (long long)gridDim.x * blockDim.x) {
+    const long long lo = runStart[r], hi = r + 1 < nruns ? runStart[r + 1] : n;
+    const int leaf = sortedLeaf[lo];
     double sum[6] = {0., 0., 0., 0., 0., 0.};
-    for (long long j = i; j < n && sortedLeaf[j] == leaf; j++) {
-      const double2* r = reinterpret_cast<const double2*>(val6 + (size_t)j * 8);
-      const double2 a = r[0], b = r[1], c = r[2];
+    for (long long j = lo; j < hi; j++) {
+      const double2* q = reinterpret_cast<const double2*>(val8 + (size_t)j * 8);
+      const double2 a = __ldcs(q), b = __ldcs(q + 1), c = __ldcs(q + 2);     // streamed once: evict first
       sum[0] = __dadd_rn(sum[0], a.x); sum[1] = __dadd_rn(sum[1], a.y); sum[2] = __dadd_rn(sum[2], b.x);
       sum[3] = __dadd_rn(sum[3], b.y); sum[4] = __dadd_rn(sum[4], c.x); sum[5] = __dadd_rn(sum[5], c.y);
     }
@@ -867,10 +877,12 @@ struct PointPlan {
     long long* rayBase = nullptr;
     unsigned int* slotMap = nullptr;
     int32_t* sortedLeaf = nullptr;
+    long long* runStart = nullptr;   // heads of the runs of equal leaves
+    long long nruns = 0;
   };
   std::vector<Batch> batches;
   void release() {
-    for (auto& b : batches) { cudaFree(b.rayBase); cudaFree(b.slotMap); cudaFree(b.sortedLeaf); }
+    for (auto& b : batches) { cudaFree(b.rayBase); cudaFree(b.slotMap); cudaFree(b.sortedLeaf); cudaFree(b.runStart); }
     batches.clear();
     key.clear();
   }
@@ -1181,6 +1193,26 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
         if (nrec > 0) {
           const int blocks = (int)std::min<long long>(((long long)nrec + 255) / 256, (long long)c.smCount * 16);
           plan_slot_kernel<<<blocks, 256, 0, s>>>(dRecKeyOut, (long long)nrec, 20, pb.rayBase, pb.slotMap, pb.sortedLeaf);
+          // run heads: positions whose leaf differs from the one before (stream compaction, once per plan)
+          long long* dHeads = nullptr;
+          long long* dCount = nullptr;
+          RTB_CUDA(cudaMalloc((void**)&dHeads, (size_t)nrec * sizeof(long long)));
+          RTB_CUDA(cudaMalloc((void**)&dCount, sizeof(long long)));
+          size_t tmpBytes = 0;
+          cub::CountingInputIterator<long long> first(0);
+          RunHead pred{pb.sortedLeaf};
+          RTB_CUDA(cub::DeviceSelect::If(nullptr, tmpBytes, first, dHeads, dCount, (long long)nrec, pred, s));
+          void* dTmp = nullptr;
+          RTB_CUDA(cudaMalloc(&dTmp, tmpBytes ? tmpBytes : 8));
+          RTB_CUDA(cub::DeviceSelect::If(dTmp, tmpBytes, first, dHeads, dCount, (long long)nrec, pred, s));
+          long long nruns = 0;
+          RTB_CUDA(cudaMemcpyAsync(&nruns, dCount, sizeof(long long), cudaMemcpyDeviceToHost, s));
+          RTB_CUDA(cudaStreamSynchronize(s));
+          RTB_CUDA(cudaMalloc((void**)&pb.runStart, (size_t)std::max<long long>(nruns, 1) * sizeof(long long)));
+          RTB_CUDA(cudaMemcpyAsync(pb.runStart, dHeads, (size_t)nruns * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+          RTB_CUDA(cudaStreamSynchronize(s));
+          pb.nruns = nruns;
+          cudaFree(dHeads); cudaFree(dCount); cudaFree(dTmp);
         }
         RTB_CUDA(cudaGetLastError());
         plan->batches.push_back(pb);
@@ -1190,8 +1222,8 @@ int point_solve(Context& c, const PointInputs& in, double* dRates, double* hDiag
     if (planned) {
       const PointPlan::Batch& pb = plan->batches[(size_t)bi];
       if (pb.nrec > 0) {
-        const int blocks = (int)std::min<long long>((pb.nrec + 255) / 256, (long long)c.smCount * 16);
-        planned_reduce_kernel<<<blocks, 256, 0, s>>>(pb.sortedLeaf, dRecVal6, pb.nrec, dRates, c.nleaf);
+        const int blocks = (int)std::min<long long>((pb.nruns + 127) / 128, (long long)c.smCount * 32);
+        planned_reduce_kernel<<<blocks, 128, 0, s>>>(pb.sortedLeaf, pb.runStart, pb.nruns, pb.nrec, dRecVal6, dRates, c.nleaf);
         c.lastLaunches += 1;
         RTB_CUDA(cudaGetLastError());
       }

@@ -44,7 +44,7 @@ struct LayerSeg {
 };
 static_assert(sizeof(LayerSeg) == 80, "LayerSeg layout");
 
-constexpr int kMaxDirPerTask = 8;
+constexpr int kMaxDirPerTask = 8;   // (12 = one task per zone at nAngularLevel = 3 measured no faster: r02f, fewer and longer blocks)
 
 // One task = up to kMaxDirPerTask directions of one zone (same index rotation), swept together layer by layer so
 // that kappa is read once and J is accumulated in registers across the directions.
@@ -65,7 +65,7 @@ struct Tuning {
   int useGraph = 1;
   int forceAmr = 0;      // route uniform grids through the general (AMR) path as well (cross-check)
   int amrSlots = 1;      // nested grids: per-item arrays indexed by the leaf's position in the wave order (1) or by leaf number (0)
-  int amrMinBlocks = 8;  // nested grids, FAST arithmetic: blocks of 128 threads per SM the wave kernel's register cap allows (8: 64, 6: 80 registers)
+  int amrMinBlocks = 6;  // nested grids, FAST arithmetic: blocks of 128 threads per SM the wave kernel's register cap allows (8: 64, 6: 80 registers)
   int amrThin = 1;       // nested grids, FAST arithmetic: thin layers use the reference's operation sequence (1)
   int amrBatch = 0;      // directions per AMR batch (0 = as many as fit in half of the free memory)
   int lockstep = 1;      // 1: one launch per layer for all zones of a batch; 0: every slot an independent stream

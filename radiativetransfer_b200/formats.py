@@ -350,7 +350,7 @@ def build_leaves(levels, metals=False):
 
 
 # ------------------------------------------------------------------------------------------------------
-# flat dataset container of oracle/ref_harness/hdf4_stub.c (stands in for HDF4 SD files where the unmodified reference
+# flat dataset container of the gfortran recipe (the HDF4 stand-in hdf4_stub.c under ref_harness, test infrastructure) (stands in for HDF4 SD files where the unmodified reference
 # driver is built without libmfhdf): "RTBSD001" | int32 nsds | nsds x { name[64] | type | rank | dims[4] | nbytes | data }
 # ------------------------------------------------------------------------------------------------------
 _SD_TYPES = {np.dtype("<i4"): 24, np.dtype("<f4"): 5, np.dtype("<f8"): 6}

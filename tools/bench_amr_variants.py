@@ -14,8 +14,8 @@ for n, levels in ((64, 3), (128, 2)):
     J = torch.zeros(3, N, dtype=torch.float64, device="cuda:0")
     s = torch.cuda.current_stream().cuda_stream
     ref = None
-    for slots, thin, pdl in ((1, 1, 1), (0, 1, 1), (1, 0, 1), (0, 0, 1), (1, 1, 0)):
-        t.set_tuning(amr_slots=slots, amr_thin=thin, pdl=pdl)
+    for slots, thin, pdl, mb in ((1, 1, 1, 8), (1, 1, 1, 6), (1, 0, 1, 8), (1, 0, 1, 6), (0, 1, 1, 8)):
+        t.set_tuning(amr_slots=slots, amr_thin=thin, pdl=pdl, amr_min_blocks=mb)
         ms = []
         for rep in range(4):
             t.diffuse_device(bg["uvb"], bg["beta"], J.data_ptr(), stream=s)
@@ -24,6 +24,6 @@ for n, levels in ((64, 3), (128, 2)):
         Jh = J.cpu().numpy()
         if ref is None:
             ref = Jh
-        print(f"{n}^3+{levels} ({N} leaves) slots={slots} thin={thin} pdl={pdl}: ms {['%.2f' % m for m in ms]} "
+        print(f"{n}^3+{levels} ({N} leaves) slots={slots} thin={thin} pdl={pdl} min_blocks={mb}: ms {['%.2f' % m for m in ms]} "
               f"max rel diff to first {np.max(np.abs(Jh - ref) / np.maximum(np.abs(ref), 1e-290)):.2e} err={t.device_error()}", flush=True)
     t.close()

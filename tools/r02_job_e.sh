@@ -1,0 +1,12 @@
+#!/bin/bash
+# 1-GPU job: validation after the 12-directions-per-task / sharding / planned-reduce changes
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/r02f_pytest_gpu.log
+timeout 300 python tools/bench_point_modes.py > gpurun_out/r02f_point_modes.log 2>&1
+timeout 500 python tools/shard_times.py 8 0 0:0:24 > gpurun_out/r02f_shard_times_8.log 2>&1
+timeout 300 python tools/shard_times.py 4 0 > gpurun_out/r02f_shard_times_4.log 2>&1
+timeout 300 python tools/shard_times.py 2 0 > gpurun_out/r02f_shard_times_2.log 2>&1
+timeout 300 python tools/shard_times.py 1 0 > gpurun_out/r02f_shard_times_1.log 2>&1
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/r02f_bench_n1.json 2> gpurun_out/r02f_bench_n1.err
+tail -6 gpurun_out/r02f_pytest_gpu.log; cat gpurun_out/r02f_point_modes.log; cat gpurun_out/r02f_shard_times_8.log; grep "sweep max" gpurun_out/r02f_shard_times_[124].log; head -c 400 gpurun_out/r02f_bench_n1.json; tail -3 gpurun_out/r02f_bench_n1.err

@@ -9,7 +9,7 @@ import radiativetransfer_b200 as rt
 from radiativetransfer_b200 import sharding, workloads as W
 n = 256
 world = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-variants = [int(x) for x in sys.argv[2:]] or [0]
+variants = sys.argv[2:] or ["0"]          # block_warps[:lockstep[:slots]]
 bg = W.uvb_background(3.0)
 g = W.uniform_grid(n, seed=1)
 t = rt.Transport(device=0)
@@ -18,8 +18,10 @@ J = torch.zeros(3, n ** 3, dtype=torch.float64, device="cuda:0")
 s = torch.cuda.current_stream().cuda_stream
 shards = sharding.shard_directions(world, n_angular_level=3, nx=n)
 zone, cost = sharding.direction_costs(3, 64)
-for bw in variants:
-    t.set_tuning(block_warps=bw)
+for v in variants:
+    f = [int(x) for x in v.split(":")]
+    bw, lockstep, slots = f[0], (f[1] if len(f) > 1 else 1), (f[2] if len(f) > 2 else 0)
+    t.set_tuning(block_warps=bw, lockstep=lockstep, slots=slots)
     times, totals = [], []
     for rank in range(world):
         for rep in range(4):
@@ -28,8 +30,8 @@ for bw in variants:
             st = t.last_stats()
         zs = sorted(set(int(zone[r]) for r in shards[rank]))
         times.append(st["sweep_ms"]); totals.append(st["device_ms"])
-        print(f"world {world} block_warps {bw} rank {rank} ndir {len(shards[rank])} zones {zs} segs/col {cost[shards[rank]].sum():.0f}: "
+        print(f"world {world} block_warps {v} rank {rank} ndir {len(shards[rank])} zones {zs} segs/col {cost[shards[rank]].sum():.0f}: "
               f"sweep_ms {st['sweep_ms']:.3f} total_ms {st['device_ms']:.3f} launches {st['launches']}", flush=True)
-    print(f"world {world} block_warps {bw}: sweep max {max(times):.3f} mean {np.mean(times):.3f} max/mean {max(times) / np.mean(times):.4f}; "
+    print(f"world {world} block_warps {v}: sweep max {max(times):.3f} mean {np.mean(times):.3f} max/mean {max(times) / np.mean(times):.4f}; "
           f"call (opacities + sweep + merge) max {max(totals):.3f}", flush=True)
 t.close()
