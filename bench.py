@@ -376,6 +376,8 @@ class Env:
         uid = [rt.comm_unique_id() if self.rank == 0 else None]
         self.dist.broadcast_object_list(uid, src=0)
         eng = rt.Transport(device=self.local, comm=(self.world, self.rank, uid[0]))
+        if os.environ.get("RTB200_MULTI_REDUCE"):      # ablation: 0 = NCCL reduce-scatter instead of the peer-memory kernel
+            eng.set_tuning(multi_reduce=int(os.environ["RTB200_MULTI_REDUCE"]))
         return eng, "group"
 
     def close(self):

@@ -239,6 +239,7 @@ int set_tuning(Context& c, const char* key, double value) {
   else if (k == "transpose_z") c.tune.transposeZ = (int)value;
   else if (k == "cells") c.tune.cells = (int)value;
   else if (k == "block_warps") c.tune.blockWarps = (int)value;
+  else if (k == "persistent") c.tune.persistent = (int)value;
   else if (k == "pdl") c.tune.pdl = (int)value;
   else if (k == "dirs_per_task") c.tune.dirsPerTask = (int)value;
   else if (k == "march_debug") {

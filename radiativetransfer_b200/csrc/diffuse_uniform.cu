@@ -18,6 +18,7 @@
 //  * Zones that sweep along the contiguous axis of the leaf order read a z-major copy of kappa and accumulate in
 //    that layout (transpose_kappa_kernel / merge_transposed_kernel) so that their lanes stay coalesced.
 //  * sweep_march_kernel is an experimental persistent variant (plane tiles in shared memory), off by default.
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -485,6 +486,176 @@ sweep_cell2_kernel(const __grid_constant__ BatchParams bp, int N, int n, int np1
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Persistent layer loop (FAST arithmetic; set_tuning "persistent": 1 on, 0 off, -1 = for small direction shards).
+//
+// A multi-GPU rank sweeps 3 zones: a layer launch of 3 zone tasks is ~16 us of fp64 work, but costs ~28 us -- its
+// 98K threads are 1.3 "waves" of the 75K the device holds, and the hand-over from one launch to the next (drain of
+// the whole grid, ramp-up of the next) is paid 256 times per sweep.  Here ONE launch runs the whole sweep: blocks
+// take work items (layer, task, tile) in that order from a counter; a tile of layer L waits until the tiles it
+// exchanges plane values with -- itself and its 8 neighbours in the task -- have completed layer L-1 (one progress
+// word per tile, release/acquire), so layers overlap wherever the dependencies allow and the device stays full.  Items are handed out in dependency order, so the
+// oldest unfinished item never waits: no co-residency requirement, no grid-wide barrier.  The planes stay in global
+// memory (L2-resident for a shard's ~24 directions); a plane buffer is rewritten every second layer, and the
+// acquire load that ends the wait is what makes the SM's L1 forget the older contents.  The per-cell code and the
+// order of every sum are those of sweep_cell2_kernel: results are bit-identical to the per-layer launches.
+// ---------------------------------------------------------------------------------------------------------
+struct PersistTask {
+  const double* kappa;   // [3][N] in the task's layout
+  double* acc;           // slot accumulator [3][N]
+  int64_t planeOff;      // offset of the task's first direction in a plane buffer (doubles)
+  int32_t origin, si, sj, sk, ndir, laneIsK, firstInSlot, tileBase;   // tileBase: first work item of the task in a layer
+};
+struct PersistParams {
+  PersistTask t[kMaxBatch];
+  const LayerSeg* seg;   // [task][layer][kMaxDirPerTask]
+  double *planeA, *planeB;
+  int32_t* counters;     // [0] work counter, [1 + task * tilesPerTask + tile] layers the tile has completed; zero at launch
+  int32_t ntask, n, np1, npl3, N, gx, gyT, itemsPerLayer, tilesPerTask;
+};
+
+template <int EXPV>
+__device__ __forceinline__ void persistent_tile(const PersistParams& pp, const PersistTask& T, const LayerSeg* __restrict__ sP,
+                                                int layer, int bx, int byWarp, const double* __restrict__ sT) {
+  const int n = pp.n, np1 = pp.np1, N = pp.N;
+  const int a = bx * 31 - 1 + (int)threadIdx.x, b0 = 2 * byWarp;
+  if (b0 >= n) return;                                         // warp-uniform
+  const bool row1 = b0 + 1 < n;
+  const bool inRow = a < n;
+  const bool writer0 = inRow && threadIdx.x >= 1, writer1 = writer0 && row1;
+  const bool cell0 = inRow && a >= 0, cell1 = cell0 && row1;
+  const int laneIsK = T.laneIsK;
+  const int sA = laneIsK ? T.sk : T.sj, sB = laneIsK ? T.sj : T.sk;
+  const int leaf0 = T.origin + layer * T.si + a * sA + b0 * sB;
+  double kap0[3], kap1[3], kF0[3], kF1[3], kR[3];
+#pragma unroll
+  for (int g = 0; g < 3; g++) {
+    const double* kg = T.kappa + (int64_t)g * N + leaf0;
+    kF0[g] = cell0 ? __ldg(kg) : 0.;
+    kF1[g] = cell1 ? __ldg(kg + sB) : 0.;
+    kR[g] = (cell0 && b0 > 0) ? __ldg(kg - sB) : 0.;
+    kap0[g] = kF0[g] > 0. ? kF0[g] : kKappaFloor;
+    kap1[g] = kF1[g] > 0. ? kF1[g] : kKappaFloor;
+  }
+  const double kmax = fmax(fmax(fmax(fmax(kap0[0], kap0[1]), fmax(kap0[2], kR[0])), fmax(kR[1], kR[2])),
+                           fmax(fmax(kap1[0], kap1[1]), kap1[2]));
+  double A0[3] = {0., 0., 0.}, A1[3] = {0., 0., 0.}, acc0[3] = {0., 0., 0.}, acc1[3] = {0., 0., 0.};
+  const int pidx = (b0 + 1) * np1 + (inRow ? a + 1 : 0);
+  const int ndir = T.ndir;
+  const int dstride = pp.npl3;
+  const int up = 3 * np1;
+  const int up1 = row1 ? up : 0;
+  const double* pin = ((layer & 1) ? pp.planeA : pp.planeB) + T.planeOff + 3 * pidx;
+  double* pout = ((layer & 1) ? pp.planeB : pp.planeA) + T.planeOff + 3 * pidx;
+  for (int q = 0; q < ndir; q++, pin += dstride, pout += dstride) {
+    const LayerSeg& P = sP[q];
+    const int kind = P.kind;
+    if (q + 1 < ndir) {
+      prefetch_l1(pin + dstride);
+      prefetch_l1(pin + dstride + up1);
+      prefetch_l1(pin + dstride - up);
+    }
+    double cur0[3], cur1[3], upR[3] = {0., 0., 0.}, I0[3], I1[3];
+#pragma unroll
+    for (int g = 0; g < 3; g++) { cur0[g] = pin[g]; cur1[g] = pin[g + up1]; }
+    const bool secL = (kind <= 2) == (laneIsK != 0);
+    if (kind == 2 || kind == 4 || (kind != 0 && !secL)) {
+#pragma unroll
+      for (int g = 0; g < 3; g++) upR[g] = pin[g - up];
+    }
+    if (P.thin) {
+      direction_dispatch_faithful(P, secL, cur0, upR, kF0, kR, I0, acc0);
+      direction_dispatch_faithful(P, secL, cur1, cur0, kF1, kF0, I1, acc1);
+    } else if (__any_sync(0xffffffffu, kmax * P.dmax > 64.)) {
+      direction_kinds_fast2<EXPV, true>(P, secL, cur0, cur1, upR, kap0, kap1, kR, I0, I1, A0, A1, sT);
+    } else {
+      direction_kinds_fast2<EXPV, false>(P, secL, cur0, cur1, upR, kap0, kap1, kR, I0, I1, A0, A1, sT);
+    }
+    if (writer0) {
+#pragma unroll
+      for (int g = 0; g < 3; g++) pout[g] = I0[g];
+    }
+    if (writer1) {
+#pragma unroll
+      for (int g = 0; g < 3; g++) pout[g + up] = I1[g];
+    }
+  }
+  if (writer0) {
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      const double v = fma(A0[g], kTwoM200 / kap0[g], acc0[g]);
+      double* p = T.acc + (int64_t)g * N + leaf0;
+      *p = T.firstInSlot ? v : __dadd_rn(*p, v);
+    }
+  }
+  if (writer1) {
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      const double v = fma(A1[g], kTwoM200 / kap1[g], acc1[g]);
+      double* p = T.acc + (int64_t)g * N + leaf0 + sB;
+      *p = T.firstInSlot ? v : __dadd_rn(*p, v);
+    }
+  }
+}
+
+__device__ __forceinline__ int ld_relaxed_gpu(const int32_t* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) sweep_persistent_kernel(const __grid_constant__ PersistParams pp, int32_t* err) {
+  extern __shared__ double smem[];
+  double* sT = smem;                                           // 16-entry exp table
+  LayerSeg* sSeg = reinterpret_cast<LayerSeg*>(smem + 16);     // [kMaxDirPerTask] tables of the item's task and layer
+  __shared__ int sItem;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (tid < 16) sT[tid] = kExpTable[tid];
+  constexpr int segDoubles = (int)(sizeof(LayerSeg) / sizeof(double)) * kMaxDirPerTask;
+  const int warps = blockDim.y;
+  const int total = pp.n * pp.itemsPerLayer;
+  int32_t* prog = pp.counters + 1;
+  for (;;) {
+    if (tid == 0) sItem = atomicAdd(pp.counters, 1);
+    __syncthreads();
+    const int item = sItem;
+    if (item >= total) break;
+    const int layer = item / pp.itemsPerLayer, inLayer = item - layer * pp.itemsPerLayer;
+    int task = 0;
+    while (task + 1 < pp.ntask && inLayer >= pp.t[task + 1].tileBase) task++;
+    const int local = inLayer - pp.t[task].tileBase;
+    const int bx = local % pp.gx, by = local / pp.gx;
+    for (int i = tid; i < segDoubles; i += blockDim.x * blockDim.y)
+      reinterpret_cast<double*>(sSeg)[i] =
+          __ldg(reinterpret_cast<const double*>(pp.seg + ((size_t)task * pp.n + layer) * kMaxDirPerTask) + i);
+    if (threadIdx.y == 0 && layer > 0) {
+      // the tile's inputs are the previous layer's planes of itself and its upstream neighbours, and the buffer it
+      // writes was read in the previous layer by itself and its downstream neighbours: wait until those (up to) 9
+      // tiles have completed `layer` layers.  Polls are relaxed loads (they leave the SM's L1 alone); the acquire
+      // fence after them is what invalidates it.
+      if (threadIdx.x < 9) {
+        const int nx = bx + (int)(threadIdx.x % 3) - 1, ny = by + (int)(threadIdx.x / 3) - 1;
+        if (nx >= 0 && nx < pp.gx && ny >= 0 && ny < pp.gyT) {
+          const int32_t* flag = prog + task * pp.tilesPerTask + ny * pp.gx + nx;
+          unsigned spins = 0;
+          while (ld_relaxed_gpu(flag) < layer) {
+            __nanosleep(32);
+            if (++spins > (1u << 26)) { atomicExch(err, RTB200_ERR_CUDA); break; }
+          }
+        }
+      }
+      __syncwarp();
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    __syncthreads();
+    persistent_tile<1>(pp, pp.t[task], sSeg, layer, bx, by * warps + (int)threadIdx.y, sT);
+    __syncthreads();                       // every thread's plane and accumulator stores are issued
+    if (tid == 0)
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(prog + task * pp.tilesPerTask + local), "r"(layer + 1) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Persistent layer-marching kernel
 //
 // The per-layer launches above stream every direction's top-exit plane through HBM twice per layer (read + write):
@@ -839,7 +1010,10 @@ static cudaError_t launch_layer(Kernel kern, dim3 grid, cudaStream_t s, bool pdl
 static cudaError_t launch_cells(int dense, int expv, bool faithful, bool pdl, dim3 grid, cudaStream_t s,
                                 const BatchParams& bp, int N, int n, int cells, int warps, int smCount) {
   // `dense`: 0 = compiler's choice of registers (2 blocks per SM), 1 = cap for 3 blocks, 2 = cap for 4 blocks
-  if (cells == 0) cells = n >= 192 ? 2 : 1;
+  // automatic: two cells per thread pay (1-2%) when the launch has many zone tasks; a small direction shard (3 zone
+  // tasks on each of 8 GPUs) is 1.3 waves of two-cell threads but fills the device evenly with one-cell threads
+  // (measured on the shards of an 8-GPU run: 7.03 against 7.21 ms mean, 7.31 against 7.93 ms for the slowest rank)
+  if (cells == 0) cells = (n >= 192 && grid.z >= 6) ? 2 : 1;
   if (faithful || expv != 1) cells = 1;
   const int rowsTotal = cells == 2 ? (n + 1) / 2 : n;           // rows of threads per task and layer
   if (warps != 8 && warps != 4 && warps != 2) {
@@ -941,6 +1115,80 @@ static int run_march(Context& c, int n, const double* uvb, double* dJout, cudaSt
   c.uniLaunches = launches;
   c.lastSweepLaunches = launches;
   c.lastLaunches = launches + 2 + (ntask + B - 1) / B;  // + compute_opacities + merge + the counter memsets
+  return RTB200_OK;
+}
+
+// Runs the sweep as one launch (see sweep_persistent_kernel).  Returns -1 when it does not apply.
+static int run_persistent(Context& c, int n, const double* uvb, double* dJout, cudaStream_t s, int ndir) {
+  const int64_t N = c.nleaf, npl = (int64_t)(n + 1) * (n + 1);
+  const int ntask = (int)c.uniTasks.size();
+  if (ntask < 1 || ntask > kMaxBatch || c.uniSlots < ntask) return -1;   // every task needs its own accumulator slot
+  const int warps = (c.tune.blockWarps == 8 || c.tune.blockWarps == 4) ? c.tune.blockWarps : 2;   // small tiles by default
+  const int gx = (n + 30) / 31, rowsTotal = (n + 1) / 2, gyT = (rowsTotal + warps - 1) / warps;
+  static thread_local PersistParams pp;
+  // per-layer tables of all tasks on the device (kept while the plan is the same)
+  const size_t segPerTask = (size_t)n * kMaxDirPerTask;
+  if (c.marchSegKey != c.uniPlanKey) {
+    if (int e = ensure_buffer((void**)&c.dMarchSeg, &c.marchSegBytes, (size_t)ntask * segPerTask * sizeof(LayerSeg))) return e;
+    for (int t = 0; t < ntask; t++)
+      RTB_CUDA(cudaMemcpyAsync((LayerSeg*)c.dMarchSeg + (size_t)t * segPerTask, c.uniTasks[t].seg.data(),
+                               segPerTask * sizeof(LayerSeg), cudaMemcpyHostToDevice, s));
+    RTB_CUDA(cudaStreamSynchronize(s));
+    c.marchSegKey = c.uniPlanKey;
+  }
+  const size_t counterBytes = ((size_t)ntask * gx * gyT + 1) * sizeof(int32_t);
+  if (int e = ensure_buffer((void**)&c.dMarchProg, &c.marchProgBytes, counterBytes)) return e;
+  const size_t smemBytes = 16 * sizeof(double) + (size_t)kMaxDirPerTask * sizeof(LayerSeg);
+  auto kern = sweep_persistent_kernel<2>;
+  if (smemBytes > 48 * 1024) RTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+  int perSm = 0;
+  RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 32 * warps, smemBytes));
+  if (perSm < 1) return -1;
+  int items = 0;
+  for (int t = 0; t < ntask; t++) {
+    const UniTaskHost& T = c.uniTasks[t];
+    PersistTask& q = pp.t[t];
+    q.kappa = T.transposed ? c.dKappaT : c.dKappa;
+    q.acc = c.dAcc + (size_t)T.slot * 3 * N;
+    q.planeOff = (int64_t)T.planeFirst * 3 * npl;
+    q.origin = (int32_t)T.origin; q.si = (int32_t)T.si; q.sj = (int32_t)T.sj; q.sk = (int32_t)T.sk;
+    q.ndir = T.ndir; q.laneIsK = T.laneIsK; q.firstInSlot = T.firstInSlot; q.tileBase = items;
+    items += gx * gyT;
+  }
+  pp.seg = (const LayerSeg*)c.dMarchSeg;
+  pp.planeA = c.dPlanes; pp.planeB = c.dPlanes + (size_t)ndir * 3 * npl;
+  pp.counters = c.dMarchProg;
+  pp.ntask = ntask; pp.n = n; pp.np1 = n + 1; pp.npl3 = (int32_t)(3 * npl); pp.N = (int32_t)N; pp.gx = gx; pp.gyT = gyT;
+  pp.itemsPerLayer = items;
+  pp.tilesPerTask = gx * gyT;
+  const int blocks = (int)std::min<int64_t>((int64_t)perSm * c.smCount, (int64_t)items * n);
+  RTB_CUDA(cudaEventRecord(c.evSweep0, s));
+  if (c.uniStdSlots < ntask && c.uniStdSlots < c.uniSlots) {
+    dim3 tg((n + 31) / 32, (n + 31) / 32, 3 * n);
+    transpose_kappa_kernel<<<tg, dim3(32, 8), 0, s>>>(c.dKappa, c.dKappaT, n);
+  }
+  {
+    const int64_t total = (int64_t)2 * ndir * 3 * npl;
+    int fb = (int)std::min<int64_t>((total + 255) / 256, (int64_t)c.smCount * 16);
+    fill_planes_kernel<<<fb, 256, 0, s>>>(c.dPlanes, npl, total, uvb[0], uvb[1], uvb[2]);
+  }
+  RTB_CUDA(cudaMemsetAsync(c.dMarchProg, 0, counterBytes, s));
+  kern<<<dim3(blocks), dim3(32, warps), smemBytes, s>>>(pp, c.dErr);
+  RTB_CUDA(cudaEventRecord(c.evSweep1, s));
+  {
+    const int nStd = std::min(c.uniStdSlots, c.uniSlots);
+    int mb = std::min<int64_t>((3 * N + 255) / 256, (int64_t)c.smCount * 16);
+    if (nStd > 0) merge_slots_kernel<<<mb, 256, 0, s>>>(c.dAcc, nStd, 3 * N, dJout);
+    else RTB_CUDA(cudaMemsetAsync(dJout, 0, 3 * N * sizeof(double), s));
+    if (nStd < c.uniSlots) {
+      dim3 tg((n + 31) / 32, (n + 31) / 32, 3 * n);
+      merge_transposed_kernel<<<tg, dim3(32, 8), 0, s>>>(c.dAcc, nStd, c.uniSlots - nStd, n, dJout);
+    }
+  }
+  RTB_CUDA(cudaGetLastError());
+  c.uniLaunches = 4;
+  c.lastSweepLaunches = 1;
+  c.lastLaunches = 7;
   return RTB200_OK;
 }
 
@@ -1099,6 +1347,18 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
   // the march path may have re-sized the shared scratch buffers for its own layout
   if (int st = ensure_buffer((void**)&c.dAcc, &c.accBytes, (size_t)c.uniSlots * 3 * N * sizeof(double))) return st;
   if (int st = ensure_buffer((void**)&c.dPlanes, &c.planeBytes, (size_t)2 * std::max(ndir, 1) * 3 * npl * sizeof(double))) return st;
+  {
+    // one launch for the whole sweep: on request only.  Measured on one B200 (profiles/r02h_*): the shards of an
+    // 8-GPU run take 6.99-7.22 ms mean / 7.26-7.50 ms max against 7.03 / 7.31 ms with per-layer launches of one-cell
+    // threads, and 4-, 2- and 1-GPU shards are 9-16% SLOWER (the layer tables come from shared memory instead of the
+    // constant bank, 128 registers with spills, an L1 invalidation per tile), so per-layer launches stay the default
+    const bool fast = c.mathMode != RTB200_MATH_FAITHFUL && c.tune.expVariant == 1 && c.tune.lockstep && !c.tune.march;
+    const bool want = c.tune.persistent == 1 || (c.tune.persistent < 0 && ntask <= 6 && n >= 64);
+    if (fast && want) {
+      const int pst = run_persistent(c, n, uvb, dJout, s, ndir);
+      if (pst >= 0) return pst;
+    }
+  }
 
   dim3 grid((n + 30) / 31, (n + 7) / 8, 1);
   double* planeA = c.dPlanes;

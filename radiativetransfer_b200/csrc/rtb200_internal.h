@@ -74,6 +74,8 @@ struct Tuning {
   double l2BudgetMB = 96.0;
   int march = 0;         // uniform sweep: 1 = persistent layer-marching kernel (experimental, slower: DESIGN.md)
   int pdl = 1;           // uniform sweep: programmatic dependent launch of layer l+1 on layer l (its prologue overlaps the tail)
+  int persistent = 0;    // uniform sweep, FAST arithmetic: 1 = the whole sweep as one launch (sweep_persistent_kernel),
+                         // -1 = for small direction shards only, 0 = per-layer launches (measured: not slower)
   int blockWarps = 0;    // uniform sweep: rows (warps) per block: 8, 4, 2, or 0 = chosen from the number of blocks per launch
   int cells = 0;         // uniform sweep, FAST arithmetic: cells of a layer per thread (2: two rows per warp, see
                          // sweep_cell2_kernel; 0 = 2 from n = 192 on, where it measured 1-2% faster, else 1: 6% faster at 128^3)

@@ -73,7 +73,8 @@ def main():
             p = grp.point(spectra, src, wt)
             assert rel_err(p["rates"][:, off:off + cnt], p1["rates"][:, off:off + cnt], floor=1e-300) < 1e-12
             mine_src = np.arange(rank, src.size, world)
-            assert rel_err(p["ndot_remaining"][mine_src], p1["ndot_remaining"][mine_src], floor=1e-300) < 1e-12
+            if mine_src.size:       # fewer sources than ranks: this rank casts none
+                assert rel_err(p["ndot_remaining"][mine_src], p1["ndot_remaining"][mine_src], floor=1e-300) < 1e-12
             grp.close()
     dist.barrier()
     print("RANK-OK", rank, flush=True)

@@ -76,6 +76,14 @@ def test_cells_per_thread_and_block_size_do_not_change_a_bit(rt, engine, oracle,
             ref = J
             assert rel_err(J, _oracle_J(oracle, g, uvbg)["J"]) < TOL
         assert np.array_equal(J, ref), (cells, warps, dense)
+    # the whole sweep as ONE launch (tiles handed out by a counter, neighbour progress words instead of kernel
+    # boundaries): same per-cell code and summation order, so the same bits
+    for warps in (0, 4, 8):
+        engine.set_tuning(cells=0, block_warps=warps, dense=0, dirs_per_task=8, persistent=1)
+        J, _ = engine.diffuse(uvbg["uvb"], uvbg["beta"])
+        assert engine.last_stats()["launches"] < 16, "the one-launch path did not run"
+        assert np.array_equal(J, ref), ("persistent", warps)
+    engine.set_tuning(persistent=0)
     # a direction shard (few zone tasks per launch) takes the automatic small blocks
     engine.set_tuning(cells=0, block_warps=0, dense=2, dirs_per_task=0)
     rays = np.arange(40, 64, dtype=np.int32)
