@@ -55,6 +55,16 @@ struct alignas(32) DevPattern {   // subset of RayPattern the device needs, 128 
 };
 static_assert(sizeof(DevPattern) == 128, "DevPattern is four sectors");
 
+// What the sweep reads of the patterns, for the (up to) 8 directions of a group side by side: the 8 lanes of a leaf
+// (same group = same zone = same table index) read 64 contiguous bytes per field, not 8 structs 128 bytes apart
+// (the pattern gathers were ~60% of the sweep's L1 sector requests).
+struct alignas(32) GroupPattern {
+  double dpath[3][8];
+  double cs[3][8];
+  int32_t flags[8];      // level | thin << 8
+};
+static_assert(sizeof(GroupPattern) == 416, "13 sectors");
+
 struct AmrDir {          // one direction of the batch
   int8_t src[3], refl[3];  // zone map: physical component c takes rotated index src[c], reflected if refl[c]
   int8_t inv[3];           // rotated axis r is physical component inv[r]
@@ -73,6 +83,8 @@ struct AmrParams {
   const int8_t* level;
   const double* kappa;     // [3][N]
   const DevPattern* pats;
+  const GroupPattern* gpats; // [group][perDir]
+  int32_t perDir;
   const int32_t* levelOff; // [maxLevel+2] offsets of the per-level tables inside one direction's block
   const AmrDir* dirs;
   const int2* groups;      // [ngroups] (first direction of the batch, number of directions <= 8)
@@ -84,10 +96,14 @@ struct AmrParams {
   double* JA;              // [N][3] running sum over the groups, leaf-major, un-interleaved into J at the end
   double* JS;              // balanced grids: [group][N][4] sum over the 8 directions of a group per leaf (one sector)
   double* JI;              // unbalanced grids: [group][slot][8][3] contribution of every item
-  double* Iout;            // [group][3 rays][slot][8][3]: the three frequency groups of a (direction, ray, leaf), 24 B
+  double* Iout;            // [group][3 rays][slot][3][8]: the three frequency groups of a (direction, ray, leaf), 8 lanes side by side
   uint8_t* done;           // [group][slot][8]
   const int32_t* slotOf[8];  // per reflection combination: position of every leaf in the wave order
   const int32_t* sorted[8];  // ... and its inverse
+  const int32_t* patIdxS;    // streamed sweep: [8 combos][3 axes][N] patIdx in wave order (slot) per reflection combination
+  const double* kappaS;      // streamed sweep: [8 combos][N][6] kappaA in wave order
+  uint64_t epochSign;        // streamed sweep: sign bit this sweep's intensity records carry (0 or 1 << 63), see amr_stream_kernel
+  int32_t* abortFlag;        // streamed sweep: set by the first poll that gave up, ends every other poll
   int noThin;                // experiments: FAST arithmetic on thin layers as well
   int slotIsLeaf;            // tuning "amr_slots" = 0: per-item arrays indexed by leaf number instead (the round-1 layout)
   double* J;               // [3][N]
@@ -226,6 +242,29 @@ __global__ void deinterleave3_kernel(const double* __restrict__ in, double* __re
   }
 }
 
+// streamed sweep: the same per-leaf inputs in wave order, one copy per reflection combination
+__global__ void kappa_slots_kernel(const double* __restrict__ in, double* __restrict__ out, AmrParams P) {
+  const int64_t N = P.N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 8 * N; i += (int64_t)gridDim.x * blockDim.x) {
+    const int combo = (int)(i / N);
+    const int64_t slot = i - combo * N, leaf = P.sorted[combo][slot];
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      const double k = in[g * N + leaf];
+      out[i * 6 + g] = k;
+      out[i * 6 + 3 + g] = 1.0 / (k > 0. ? k : kAmrKappaFloor);
+    }
+  }
+}
+__global__ void patidx_slots_kernel(const int32_t* __restrict__ patIdx, int32_t* __restrict__ out, AmrParams P) {
+  const int64_t N = P.N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 24 * N; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ca = (int)(i / N), combo = ca / 3, a = ca - 3 * combo;
+    const int64_t leaf = P.sorted[combo][i - (int64_t)ca * N];
+    out[i] = patIdx[(int64_t)(((combo >> a) & 1) ? 3 + a : a) * N + leaf];
+  }
+}
+
 // one (leaf, direction): returns false if an upstream leaf is not published yet.  CHECK = false: the grid is 2:1
 // balanced, the wave order alone guarantees that every upstream leaf was finished by an earlier launch, so the
 // per-leaf `done` flags (three dependent gathers, two fences and a store per item) are not needed.
@@ -234,16 +273,42 @@ __global__ void deinterleave3_kernel(const double* __restrict__ in, double* __re
 // issued before the arithmetic starts: the packed neighbour record first, then -- independent of each other --
 // opacity, pattern and the three upstream intensities.  Iout records are 32 bytes (3 groups + pad) per (direction,
 // ray, leaf): one sector per upstream read, and only the active rays of a leaf are written.
+// word g of the record lies at + g * kGroup: the 8 lanes of a leaf read / write 64 contiguous bytes (two full sectors)
+// per frequency group, instead of every third word of 192 bytes
 __device__ __forceinline__ int64_t iout_record(const AmrParams& P, int group, int lane, int ray, int64_t slot) {
-  return ((((int64_t)group * 3 + ray) * P.N + slot) * kGroup + lane) * 3;
+  return (((int64_t)group * 3 + ray) * P.N + slot) * (3 * kGroup) + lane;
 }
 
-template <bool CHECK>
-__device__ __forceinline__ void load_record(const double* p, double (&v)[3]) {
-  if (CHECK) {  // possibly written by another block of this launch: read through L2
-    v[0] = __ldcg(p); v[1] = __ldcg(p + 1); v[2] = __ldcg(p + 2);
-  } else {      // written by an earlier launch
-    v[0] = __ldg(p); v[1] = __ldg(p + 1); v[2] = __ldg(p + 2);
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const double* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// MODE 0: the record was written by an earlier launch.  1: possibly by another block of this launch, guarded by the
+// `done` flags: read through L2.  2 (streamed sweep): written by an earlier work item of THIS launch, and valid once
+// its sign bit is the sweep's (`first` = the words of a first attempt issued earlier, so that a thread's gathers overlap)
+template <int MODE>
+__device__ __forceinline__ void load_record(const AmrParams& P, const double* p, double (&v)[3]) {
+  if (MODE == 1) {
+    v[0] = __ldcg(p); v[1] = __ldcg(p + kGroup); v[2] = __ldcg(p + 2 * kGroup);
+  } else if (MODE == 0) {
+    v[0] = __ldg(p); v[1] = __ldg(p + kGroup); v[2] = __ldg(p + 2 * kGroup);
+  } else {
+    uint64_t a = ld_relaxed_u64(p), b = ld_relaxed_u64(p + kGroup), c = ld_relaxed_u64(p + 2 * kGroup);
+    unsigned spins = 0;
+    // every word validates itself (a 64-bit store is indivisible), so no fence and no ordering between the words
+    while ((((a ^ P.epochSign) | (b ^ P.epochSign) | (c ^ P.epochSign)) >> 63) != 0) {
+      __nanosleep(40);
+      if ((++spins & 63) == 0) {
+        if (*(volatile int32_t*)P.abortFlag) break;
+        if (spins > (1u << 21)) { atomicExch(P.abortFlag, 1); atomicMax(P.err, RTB200_ERR_CUDA); break; }
+      }
+      a = ld_relaxed_u64(p); b = ld_relaxed_u64(p + kGroup); c = ld_relaxed_u64(p + 2 * kGroup);
+    }
+    const uint64_t m = ~(1ull << 63);
+    v[0] = __longlong_as_double((long long)(a & m)); v[1] = __longlong_as_double((long long)(b & m));
+    v[2] = __longlong_as_double((long long)(c & m));
   }
 }
 
@@ -264,10 +329,9 @@ __device__ __noinline__ ThinSeg amr_thin_segment(double i0, double i1, double i2
 }
 
 // Jc = this direction's contribution to the leaf's mean intensity (the caller adds it up)
-template <bool FAITHFUL, bool CHECK>
-__device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, int gi, int lane, int64_t leaf, int64_t slot,
-                                                   double (&Jc)[3], const double* __restrict__ sT) {
-  const AmrDir& D = P.dirs[d];
+template <bool FAITHFUL, int MODE>
+__device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, const AmrDir& D, int gi, int lane, int64_t leaf,
+                                                   int64_t slot, double (&Jc)[3], const double* __restrict__ sT) {
   const int64_t item = item_index(P, gi, lane, slot);
   int32_t nbl[3];
   int cd[3];
@@ -280,6 +344,7 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
       cd[ray] = v[ray] & 7;
     }
   }
+  constexpr bool CHECK = MODE == 1;
   if (CHECK) {
     asm volatile("griddepcontrol.wait;" ::: "memory");             // the flags are written by the launches before
     const volatile uint8_t* done = P.done;
@@ -290,16 +355,19 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
   }
   // ---- gathers -----------------------------------------------------------------------------------------------
   // pattern of the leaf's (level, layer along the sweep axis): one gather of a precomputed index
-  const int32_t pidx = P.patIdx[(int64_t)D.patRow * P.N + leaf];
+  // (streamed sweep: from the copies in wave order -- no leaf number, nothing to wait for but the neighbour record)
+  const int32_t pidx = MODE == 2 ? __ldg(P.patIdxS + ((int64_t)D.combo * 3 + D.patRow % 3) * P.N + slot)
+                                 : P.patIdx[(int64_t)D.patRow * P.N + leaf];
+  const double* kA = MODE == 2 ? P.kappaS + ((int64_t)D.combo * P.N + slot) * 6 : P.kappaA + leaf * 6;
   double kap[3], invk[3];
 #pragma unroll
   for (int g = 0; g < 3; g++) {
-    kap[g] = P.kappaA[leaf * 6 + g];
-    invk[g] = FAITHFUL ? 0. : P.kappaA[leaf * 6 + 3 + g];
+    kap[g] = kA[g];
+    invk[g] = FAITHFUL ? 0. : kA[3 + g];
   }
   // Programmatic dependent launch: everything above is geometry or per-sweep input; the upstream intensities below
   // come from the waves before this one (no-op for a grid launched without the attribute)
-  if (!CHECK) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (MODE == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
   double Iin[3][3];
 #pragma unroll
   for (int ray = 0; ray < 3; ray++) {
@@ -307,20 +375,21 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
     if (nbl[ray] >= 0) {
       // codes 0..2: that ray of the neighbour; 3, 4: mean with its xy ray (below); 5: its xy ray
       const int c = cd[ray];
-      load_record<CHECK>(P.Iout + iout_record(P, gi, lane, c <= 2 ? c : 0, nbl[ray]), Iin[ray]);
+      load_record<MODE>(P, P.Iout + iout_record(P, gi, lane, c <= 2 ? c : 0, nbl[ray]), Iin[ray]);
     }
   }
-  const DevPattern& pat = P.pats[D.patBase + pidx];
-  const int L = pat.level;
+  const GroupPattern& pat = P.gpats[(int64_t)gi * P.perDir + pidx];
+  const int patFlags = pat.flags[lane];
+  const int L = patFlags & 0xff;
   double dpath[3];
 #pragma unroll
-  for (int ray = 0; ray < 3; ray++) dpath[ray] = pat.dpath[ray];     // cellSize(level) * len (:583, 651)
+  for (int ray = 0; ray < 3; ray++) dpath[ray] = pat.dpath[ray][lane];     // cellSize(level) * len (:583, 651)
   // coarse-neighbour averaging fallback (transportRoutinesModule.f90:612-634): rare, a second record
 #pragma unroll
   for (int ray = 0; ray < 3; ray++) {
     if (nbl[ray] >= 0 && (cd[ray] == 3 || cd[ray] == 4)) {
       double side[3];
-      load_record<CHECK>(P.Iout + iout_record(P, gi, lane, cd[ray] == 3 ? 2 : 1, nbl[ray]), side);
+      load_record<MODE>(P, P.Iout + iout_record(P, gi, lane, cd[ray] == 3 ? 2 : 1, nbl[ray]), side);
 #pragma unroll
       for (int g = 0; g < 3; g++) Iin[ray][g] = __dmul_rn(0.5, __dadd_rn(side[g], Iin[ray][g]));
     }
@@ -333,7 +402,7 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
   double Jm[3] = {0., 0., 0.};
   double xy[3] = {0., 0., 0.};
   int imean = 0;
-  const int thinMask = (!FAITHFUL && !P.noThin) ? pat.thin : 0;
+  const int thinMask = (!FAITHFUL && !P.noThin) ? (patFlags >> 8) : 0;
   const double kapRaw[3] = {kap[0], kap[1], kap[2]};
   double Jthin[3] = {0., 0., 0.};   // thin segments: sum of the reference-formula segment means (divided by nseg, times w below)
   if (!FAITHFUL) {
@@ -359,14 +428,21 @@ __device__ __forceinline__ bool amr_transport_leaf(const AmrParams& P, int d, in
 #pragma unroll
       for (int g = 0; g < 3; g++) { out[g] = t.out[g]; Jthin[g] = __dadd_rn(Jthin[g], t.J[g]); }
     } else {
-      const double cs = pat.cs[ray];
+      const double cs = pat.cs[ray][lane];
 #pragma unroll
       for (int g = 0; g < 3; g++) out[g] = segment_fast<1, true>(Iin[ray][g], kap[g] * dpath[ray], cs, sT, Jm[g]);
     }
     if (ray == 0) { xy[0] = out[0]; xy[1] = out[1]; xy[2] = out[2]; }
     imean++;
     double* mine = P.Iout + iout_record(P, gi, lane, ray, slot);
-    mine[0] = out[0]; mine[1] = out[1]; mine[2] = out[2];
+    if (MODE == 2) {   // intensities are >= 0: the sign bit is free to say which sweep wrote the record
+#pragma unroll
+      for (int g = 0; g < 3; g++)
+        __stcg(reinterpret_cast<unsigned long long*>(mine) + g * kGroup,
+               (unsigned long long)((uint64_t)__double_as_longlong(out[g]) & ~(1ull << 63)) | P.epochSign);
+    } else {
+      mine[0] = out[0]; mine[kGroup] = out[1]; mine[2 * kGroup] = out[2];
+    }
   }
   if (L > 0) {  // refined path only: guard on the xy ray's sum (transportRoutinesModule.f90:680,803,926)
     const double tmp = __dadd_rn(__dadd_rn(xy[0], xy[1]), xy[2]);
@@ -419,7 +495,7 @@ __global__ void __launch_bounds__(128, MINB) amr_wave_kernel(AmrParams P, WavePa
   bool deferred = false;
   if (mine) {
     const int d = grp.x + lane;
-    if (!amr_transport_leaf<FAITHFUL, CHECK>(P, d, gi, lane, leaf, slot, Jc, sT)) {
+    if (!amr_transport_leaf<FAITHFUL, CHECK ? 1 : 0>(P, P.dirs[d], gi, lane, leaf, slot, Jc, sT)) {
       deferred = true;
       int q = atomicAdd(Wp.deferredCount, 1);
       if (q < Wp.deferredCap) Wp.deferred[q] = ((int64_t)d << 32) | slot;
@@ -450,6 +526,102 @@ __global__ void __launch_bounds__(128, MINB) amr_wave_kernel(AmrParams P, WavePa
   }
 }
 
+// Streamed sweep (2:1-balanced grids): the whole batch in ONE launch.  The per-wave launches above are latency-bound
+// -- a diagonal wave of a 64^3 + 3 levels grid holds ~20K items and takes ~20 us whatever its size, 573 times per
+// sweep.  Here resident blocks take work items -- 16 leaves of one wave and group, in wave order -- from a counter, and
+// an item simply waits for the upstream intensity records it reads: a record is valid once its three words carry the
+// sweep's sign bit (intensities are >= 0, so the sign is free; sweeps alternate it, and every sweep rewrites every
+// record that is ever read, so at the start of a sweep all of them carry the other sign).  Work is handed out in wave
+// order and a record's writer lies in an earlier wave, so the oldest unfinished item never waits: no deadlock, no
+// co-residency requirement, no flags, no fences.  The arithmetic and every summation order are those of the wave
+// kernel: results are bit-identical.
+struct StreamParams {
+  const int2* items;        // (group | leaves << 8, first slot): 1..16 consecutive slots of one wave in the group's order
+  int32_t nitems;
+  int32_t* counter;         // zero at launch
+};
+
+constexpr int kStreamDirs = 192;   // directions of a batch the streamed kernel keeps in shared memory
+
+__device__ __forceinline__ void prefetch_l1_amr(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// Every WARP is a worker of its own (4 leaves x 8 direction lanes = a quarter of a work item): no block barrier couples
+// fast and slow leaves.  Lane 0 runs three quarters ahead with the work counter and two ahead with the item record
+// (a small per-warp ring in shared memory), and the quarter after the current one has its streaming inputs --
+// neighbour record, opacities, pattern index: always DRAM misses -- prefetched while the current one is computed.
+template <bool FAITHFUL, int MINB>
+__global__ void __launch_bounds__(128, MINB) amr_stream_kernel(AmrParams P, StreamParams Q, int ndirs, int ngroups) {
+  __shared__ double sT[16];
+  __shared__ AmrDir sDirs[kStreamDirs];
+  __shared__ int2 sGroups[kStreamDirs / kGroup * 2];
+  __shared__ int4 sRing[4][4];       // per warp: (group | leaves << 8, first slot, quarter, valid)
+  if (threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
+  if (threadIdx.x < ngroups) sGroups[threadIdx.x] = P.groups[threadIdx.x];
+  for (int q = threadIdx.x; q < ndirs * 4; q += blockDim.x)    // 32-byte records, 8 bytes at a time
+    reinterpret_cast<double*>(sDirs)[q] = __ldg(reinterpret_cast<const double*>(P.dirs) + q);
+  __syncthreads();
+  const int w = threadIdx.x >> 5, l32 = threadIdx.x & 31;
+  const int lane = l32 % kGroup, li = l32 / kGroup;
+  const int total = Q.nitems * 4;
+  int cB = 0;
+  if (l32 == 0) {
+    for (int k = 0; k < 2; k++) {
+      const int c = atomicAdd(Q.counter, 1);
+      int4 r = make_int4(0, 0, 0, 0);
+      if (c < total) { const int2 e = __ldg(Q.items + (c >> 2)); r = make_int4(e.x, e.y, c & 3, 1); }
+      sRing[w][k] = r;
+    }
+    cB = atomicAdd(Q.counter, 1);
+  }
+  __syncwarp();
+  for (int k = 0;; k++) {
+    int2 eB = make_int2(0, 0);
+    int cA = 0;
+    if (l32 == 0) {                          // issued now, consumed after this quarter's work
+      if (cB < total) eB = __ldg(Q.items + (cB >> 2));
+      cA = atomicAdd(Q.counter, 1);
+    }
+    const int4 cur = sRing[w][k & 3], nxt = sRing[w][(k + 1) & 3];
+    if (!cur.w) break;
+    if (nxt.w) {
+      const int giN = nxt.x & 0xff, cntN = nxt.x >> 8, iN = nxt.z * 4 + li;
+      if (iN < cntN) {
+        const int64_t slotN = nxt.y + iN;
+        const AmrDir& DN = sDirs[sGroups[giN].x];
+        prefetch_l1_amr(P.nbc + item_index(P, giN, lane, slotN) * 4);
+        if (lane == 0) prefetch_l1_amr(P.kappaS + ((int64_t)DN.combo * P.N + slotN) * 6);
+        if (lane == 1) prefetch_l1_amr(P.kappaS + ((int64_t)DN.combo * P.N + slotN) * 6 + 4);
+        if (lane == 2) prefetch_l1_amr(P.patIdxS + ((int64_t)DN.combo * 3 + DN.patRow % 3) * P.N + slotN);
+      }
+    }
+    const int gi = cur.x & 0xff, count = cur.x >> 8, i = cur.z * 4 + li;
+    const int2 grp = sGroups[gi];
+    const bool have = i < count, mine = have && lane < grp.y;
+    const int64_t slot = cur.y + i;
+    double Jc[3] = {0., 0., 0.};
+    if (mine) amr_transport_leaf<FAITHFUL, 2>(P, sDirs[grp.x + lane], gi, lane, 0, slot, Jc, sT);
+    __syncwarp();
+    double v[3];
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      v[g] = Jc[g];
+      v[g] = __dadd_rn(v[g], __shfl_xor_sync(0xffffffffu, v[g], 1));
+      v[g] = __dadd_rn(v[g], __shfl_xor_sync(0xffffffffu, v[g], 2));
+      v[g] = __dadd_rn(v[g], __shfl_xor_sync(0xffffffffu, v[g], 4));
+    }
+    if (have && lane == 0) {                 // per (group, SLOT): the merge looks the leaf's slot up
+      double* q = P.JS + ((int64_t)gi * P.N + slot) * 4;
+      *reinterpret_cast<double2*>(q) = make_double2(v[0], v[1]);
+      q[2] = v[2];
+    }
+    if (l32 == 0) {
+      sRing[w][(k + 2) & 3] = cB < total ? make_int4(eB.x, eB.y, cB & 3, 1) : make_int4(0, 0, 0, 0);
+      cB = cA;
+    }
+    __syncwarp();
+  }
+}
+
 template <bool FAITHFUL>
 __global__ void amr_retry_kernel(AmrParams P, const int64_t* in, const int32_t* inCount, int64_t* out, int32_t* outCount,
                                  int64_t cap) {
@@ -465,7 +637,7 @@ __global__ void amr_retry_kernel(AmrParams P, const int64_t* in, const int32_t* 
     const int64_t slot = item & 0xffffffffLL;
     const int64_t leaf = P.slotIsLeaf ? slot : P.sorted[P.dirs[d].combo][slot];
     double Jc[3];
-    if (!amr_transport_leaf<FAITHFUL, true>(P, d, P.dirs[d].group, P.dirs[d].lane, leaf, slot, Jc, sT)) {
+    if (!amr_transport_leaf<FAITHFUL, 1>(P, P.dirs[d], P.dirs[d].group, P.dirs[d].lane, leaf, slot, Jc, sT)) {
       int q = atomicAdd(outCount, 1);
       if (q < cap) out[q] = item;
     } else {
@@ -478,7 +650,7 @@ __global__ void amr_retry_kernel(AmrParams P, const int64_t* in, const int32_t* 
 // JA[leaf] += the batch's groups, one after the other in group order (thread = leaf): the summation order of a leaf is
 // group 0, 1, 2, ... of the whole call whatever the batching.  ITEMS: the per-item contributions of the unbalanced
 // path, the 8 lanes added in the butterfly's order ((0+1)+(2+3))+((4+5)+(6+7)).
-template <bool ITEMS>
+template <bool ITEMS, bool BYSLOT = false>
 __global__ void amr_merge_kernel(AmrParams P, int ngroups) {
   for (int64_t leaf = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; leaf < P.N; leaf += (int64_t)gridDim.x * blockDim.x) {
     double s[3] = {P.JA[leaf * 3], P.JA[leaf * 3 + 1], P.JA[leaf * 3 + 2]};
@@ -493,7 +665,7 @@ __global__ void amr_merge_kernel(AmrParams P, int ngroups) {
           s[g] = __dadd_rn(s[g], __dadd_rn(a, b));
         }
       } else {
-        const double* q = P.JS + ((int64_t)gi * P.N + leaf) * 4;
+        const double* q = P.JS + ((int64_t)gi * P.N + (BYSLOT ? P.slotOf[P.dirs[P.groups[gi].x].combo][leaf] : leaf)) * 4;
         const double2 ab = *reinterpret_cast<const double2*>(q);
         s[0] = __dadd_rn(s[0], ab.x); s[1] = __dadd_rn(s[1], ab.y); s[2] = __dadd_rn(s[2], q[2]);
       }
@@ -531,6 +703,7 @@ struct AmrPlan {
   int32_t* dSorted[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int32_t* dSlotOf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // inverse of dSorted
   int32_t* dPatIdx = nullptr;         // [6][N], see AmrParams
+  int32_t* dPatIdxS = nullptr;        // [8][3][N] the same in wave order (streamed sweep), built on first use
 };
 
 // wave key = sum over the rotated axes of the leaf centre in half-finest-cell units (see header comment)
@@ -600,6 +773,8 @@ struct DirTables {
 // device buffers of one batch of directions (kept across calls while the sizes fit)
 struct AmrBuffers {
   DevPattern* pats = nullptr;
+  GroupPattern* gpats = nullptr;
+  std::string uploadKey;        // tables + group range whose patterns / directions / groups the device copies hold
   AmrDir* dirs = nullptr;
   int2* groups = nullptr;
   int32_t* levelOff = nullptr;
@@ -607,6 +782,7 @@ struct AmrBuffers {
   uint8_t* code = nullptr;
   int32_t* nbc = nullptr;
   double* kappaA = nullptr;
+  double* kappaS = nullptr;     // streamed sweep: [8][N][6]
   double* JA = nullptr;
   double* JS = nullptr;
   double* JI = nullptr;
@@ -615,13 +791,21 @@ struct AmrBuffers {
   int64_t* defA = nullptr;
   int64_t* defB = nullptr;
   int32_t* defCount = nullptr;  // [2]
+  int2* items = nullptr;        // streamed sweep: work list of the batch (see StreamParams)
+  size_t itemsCap = 0;
+  int32_t nitems = 0;
+  std::string itemsKey;         // tables + group range the list was built for
+  std::string epochKey;         // tables whose records all carry the sign of sweep `epoch` (empty: unknown, re-initialise)
+  uint64_t epoch = 0;
   std::string sizeKey;
   int batch = 0, batchNdir = 0;   // batch size (in groups) chosen when the buffers were allocated, and for how many directions
+  int batchTune = 0;              // ... under which "amr_batch" setting
+  int64_t batchN = 0;             // ... and leaf count
   std::string nbKey;              // grid + direction list whose neighbour tables (nb, code, nbc) the buffers hold
   void release() {
-    cudaFree(pats); cudaFree(dirs); cudaFree(groups); cudaFree(levelOff); cudaFree(nb); cudaFree(code); cudaFree(Iout); cudaFree(done);
-    cudaFree(nbc); cudaFree(kappaA); cudaFree(JA); cudaFree(JS); cudaFree(JI);
-    cudaFree(defA); cudaFree(defB); cudaFree(defCount);
+    cudaFree(pats); cudaFree(gpats); cudaFree(dirs); cudaFree(groups); cudaFree(levelOff); cudaFree(nb); cudaFree(code); cudaFree(Iout); cudaFree(done);
+    cudaFree(nbc); cudaFree(kappaA); cudaFree(kappaS); cudaFree(JA); cudaFree(JS); cudaFree(JI);
+    cudaFree(defA); cudaFree(defB); cudaFree(defCount); cudaFree(items);
     *this = AmrBuffers();
   }
 };
@@ -643,6 +827,7 @@ void amr_release(Context& c) {
   if (!S) return;
   for (int k = 0; k < 8; k++) { cudaFree(S->plan.dSorted[k]); cudaFree(S->plan.dSlotOf[k]); }
   cudaFree(S->plan.dPatIdx);
+  cudaFree(S->plan.dPatIdxS);
   S->buffers.release();
   delete S;
   c.amrState = nullptr;
@@ -671,6 +856,7 @@ static int ensure_plan(Context& c, AmrState& S) {
         idx[(size_t)(3 + a) * c.nleaf + l] = levelOff[L] + nL - 1 - p[a];
       }
     }
+    cudaFree(S.plan.dPatIdxS); S.plan.dPatIdxS = nullptr;
     cudaFree(S.plan.dPatIdx);
     RTB_CUDA(cudaMalloc((void**)&S.plan.dPatIdx, idx.size() * sizeof(int32_t)));
     RTB_CUDA(cudaMemcpy(S.plan.dPatIdx, idx.data(), idx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -757,6 +943,7 @@ static int alloc_batch(AmrBuffers& B, const DirTables& T, int64_t N, int ngroups
                        bool balanced) {
   const size_t slots = (size_t)ngroups * kGroup;
   RTB_CUDA(cudaMalloc((void**)&B.pats, (size_t)T.perDir * slots * sizeof(DevPattern)));
+  RTB_CUDA(cudaMalloc((void**)&B.gpats, (size_t)T.perDir * ngroups * sizeof(GroupPattern)));
   RTB_CUDA(cudaMalloc((void**)&B.dirs, slots * sizeof(AmrDir)));
   RTB_CUDA(cudaMalloc((void**)&B.groups, (size_t)ngroups * sizeof(int2)));
   RTB_CUDA(cudaMalloc((void**)&B.levelOff, T.levelOff.size() * sizeof(int32_t)));
@@ -794,8 +981,6 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int g0, int ng
   const int64_t N = c.nleaf;
   const int d0 = T.groups[g0].x;
   const int nd = T.groups[g0 + ng - 1].x + T.groups[g0 + ng - 1].y - d0;
-  RTB_CUDA(cudaMemcpyAsync(B.pats, T.pats.data() + (size_t)d0 * T.perDir, (size_t)T.perDir * nd * sizeof(DevPattern),
-                           cudaMemcpyHostToDevice, s));
   std::vector<AmrDir> dl(T.dirs.begin() + d0, T.dirs.begin() + d0 + nd);
   std::vector<int2> gl(T.groups.begin() + g0, T.groups.begin() + g0 + ng);
   for (int g = 0; g < ng; g++) {
@@ -807,20 +992,42 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int g0, int ng
       A.lane = k;
     }
   }
-  RTB_CUDA(cudaMemcpyAsync(B.dirs, dl.data(), (size_t)nd * sizeof(AmrDir), cudaMemcpyHostToDevice, s));
-  RTB_CUDA(cudaMemcpyAsync(B.groups, gl.data(), (size_t)ng * sizeof(int2), cudaMemcpyHostToDevice, s));
-  RTB_CUDA(cudaMemcpyAsync(B.levelOff, T.levelOff.data(), T.levelOff.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  char ub[64];
+  snprintf(ub, sizeof(ub), "|%d:%d", g0, ng);
+  const std::string ukey = S.tablesKey + ub;
+  if (B.uploadKey != ukey || S.tablesKey.empty()) {
+    // tables of the batch: a function of the grid and the direction list, kept across the outer iterations
+    std::vector<GroupPattern> gp((size_t)ng * T.perDir);
+    std::memset(gp.data(), 0, gp.size() * sizeof(GroupPattern));
+    for (int g = 0; g < ng; g++)
+      for (int k = 0; k < gl[g].y; k++) {
+        const DevPattern* src = T.pats.data() + (size_t)(d0 + gl[g].x + k) * T.perDir;
+        for (int i = 0; i < T.perDir; i++) {
+          GroupPattern& q = gp[(size_t)g * T.perDir + i];
+          for (int r = 0; r < 3; r++) { q.dpath[r][k] = src[i].dpath[r]; q.cs[r][k] = src[i].cs[r]; }
+          q.flags[k] = (int32_t)(uint8_t)src[i].level | ((int32_t)(uint8_t)src[i].thin << 8);
+        }
+      }
+    RTB_CUDA(cudaMemcpyAsync(B.pats, T.pats.data() + (size_t)d0 * T.perDir, (size_t)T.perDir * nd * sizeof(DevPattern),
+                             cudaMemcpyHostToDevice, s));
+    RTB_CUDA(cudaMemcpyAsync(B.gpats, gp.data(), gp.size() * sizeof(GroupPattern), cudaMemcpyHostToDevice, s));
+    RTB_CUDA(cudaMemcpyAsync(B.dirs, dl.data(), (size_t)nd * sizeof(AmrDir), cudaMemcpyHostToDevice, s));
+    RTB_CUDA(cudaMemcpyAsync(B.groups, gl.data(), (size_t)ng * sizeof(int2), cudaMemcpyHostToDevice, s));
+    RTB_CUDA(cudaMemcpyAsync(B.levelOff, T.levelOff.data(), T.levelOff.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    RTB_CUDA(cudaStreamSynchronize(s));  // the sources are locals
+    B.uploadKey = ukey;
+  }
   if (!S.plan.balanced) RTB_CUDA(cudaMemsetAsync(B.done, 0, (size_t)ng * kGroup * N, s));
   RTB_CUDA(cudaMemsetAsync(B.defCount, 0, 2 * sizeof(int32_t), s));
-  RTB_CUDA(cudaStreamSynchronize(s));  // dl is a local
   AmrParams P;
   P.child = c.tree.child; P.lx = c.tree.leafX; P.ly = c.tree.leafY; P.lz = c.tree.leafZ; P.level = c.dLevel;
-  P.kappa = c.dKappa; P.pats = B.pats; P.levelOff = B.levelOff; P.dirs = B.dirs; P.nb = nullptr; P.code = nullptr;
+  P.kappa = c.dKappa; P.pats = B.pats; P.gpats = B.gpats; P.perDir = T.perDir; P.levelOff = B.levelOff; P.dirs = B.dirs; P.nb = nullptr; P.code = nullptr;
   P.groups = B.groups;
   P.Iout = B.Iout; P.done = B.done; P.J = dJ; P.err = c.dErr; P.N = N; P.n = c.nx; P.maxLevel = c.maxLevel;
   P.nbc = B.nbc; P.patIdx = S.plan.dPatIdx; P.kappaA = B.kappaA; P.JA = B.JA; P.JS = B.JS; P.JI = B.JI;
   for (int k = 0; k < 8; k++) { P.slotOf[k] = S.plan.dSlotOf[k]; P.sorted[k] = S.plan.dSorted[k]; }
   P.slotIsLeaf = c.tune.amrSlots == 0; P.noThin = c.tune.amrThin == 0;
+  P.epochSign = 0; P.abortFlag = B.defCount + 1; P.patIdxS = nullptr; P.kappaS = nullptr;
   P.u0 = uvb[0]; P.u1 = uvb[1]; P.u2 = uvb[2];
   P.cellSize0 = c.boxSize / (double)c.nx;  // equiSources.f90:1570
   // neighbour threading is geometry only (grid + directions): when one batch holds every direction of the call, the
@@ -832,6 +1039,68 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int g0, int ng
     (*launches)++;
     B.nbKey = wholeCall ? S.tablesKey : std::string();
   }
+  if (S.plan.balanced && c.tune.amrStream && !P.slotIsLeaf && nd <= kStreamDirs && ng <= kStreamDirs / kGroup * 2) {
+    // ---- one launch for the whole batch (amr_stream_kernel) ----
+    char kb[64];
+    snprintf(kb, sizeof(kb), "|%d:%d", g0, ng);
+    const std::string ikey = S.tablesKey + kb;
+    if (B.itemsKey != ikey) {
+      std::vector<int2> items;
+      for (int w = 0; w < S.plan.nkeys; w++)
+        for (int g = 0; g < ng; g++) {
+          const int combo = dl[gl[g].x].combo;
+          const int begin = S.plan.waveStart[combo][w], cnt = S.plan.waveStart[combo][w + 1] - begin;
+          for (int off = 0; off < cnt; off += 16) items.push_back(make_int2(g | (std::min(16, cnt - off) << 8), begin + off));
+        }
+      if (items.size() > B.itemsCap) {
+        cudaFree(B.items);
+        B.items = nullptr; B.itemsCap = 0;
+        RTB_CUDA(cudaMalloc((void**)&B.items, items.size() * sizeof(int2)));
+        B.itemsCap = items.size();
+      }
+      RTB_CUDA(cudaMemcpyAsync(B.items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+      RTB_CUDA(cudaStreamSynchronize(s));
+      B.nitems = (int32_t)items.size();
+      B.itemsKey = ikey;
+    }
+    // sign epoch of the intensity records: alternates from sweep to sweep while the same records are rewritten
+    if (wholeCall && !S.tablesKey.empty() && B.epochKey == S.tablesKey) B.epoch++;
+    else {
+      RTB_CUDA(cudaMemsetAsync(B.Iout, 0, (size_t)ng * kGroup * N * 9 * sizeof(double), s));   // sign 0 everywhere
+      B.epoch = 1;
+      B.epochKey = wholeCall ? S.tablesKey : std::string();
+    }
+    P.epochSign = (B.epoch & 1) ? (1ull << 63) : 0ull;
+    P.abortFlag = B.defCount + 1;
+    // per-leaf inputs in wave order: pattern indices once per grid, opacities every sweep
+    const int cb = (int)std::min<int64_t>((8 * N + 255) / 256, (int64_t)c.smCount * 16);
+    if (!S.plan.dPatIdxS) {
+      RTB_CUDA(cudaMalloc((void**)&S.plan.dPatIdxS, (size_t)24 * N * sizeof(int32_t)));
+      patidx_slots_kernel<<<cb, 256, 0, s>>>(S.plan.dPatIdx, S.plan.dPatIdxS, P);
+      (*launches)++;
+    }
+    if (!B.kappaS) RTB_CUDA(cudaMalloc((void**)&B.kappaS, (size_t)8 * N * 6 * sizeof(double)));
+    kappa_slots_kernel<<<cb, 256, 0, s>>>(c.dKappa, B.kappaS, P);
+    (*launches)++;
+    P.patIdxS = S.plan.dPatIdxS; P.kappaS = B.kappaS;
+    StreamParams Q;
+    Q.items = B.items; Q.nitems = B.nitems; Q.counter = B.defCount;
+    int perSm = 0;
+    if (faithful) {
+      RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, amr_stream_kernel<true, 4>, 128, 0));
+      amr_stream_kernel<true, 4><<<std::min(perSm * c.smCount, (int)B.nitems), 128, 0, s>>>(P, Q, nd, ng);
+    } else {
+      RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, amr_stream_kernel<false, 6>, 128, 0));
+      amr_stream_kernel<false, 6><<<std::min(perSm * c.smCount, (int)B.nitems), 128, 0, s>>>(P, Q, nd, ng);
+    }
+    (*launches)++;
+    const int blocks = (int)std::min<int64_t>((N + 127) / 128, (int64_t)c.smCount * 16);
+    amr_merge_kernel<false, true><<<blocks, 128, 0, s>>>(P, ng);
+    (*launches)++;
+    RTB_CUDA(cudaGetLastError());
+    return RTB200_OK;
+  }
+  B.epochKey.clear();   // the launches below write plain (unsigned) records
   WaveParams Wp;
   for (int k = 0; k < 8; k++) Wp.sorted[k] = S.plan.dSorted[k];
   Wp.deferredCap = defCap;
@@ -932,7 +1201,9 @@ int diffuse_amr(Context& c, int nAngularLevel, const double* uvb, const std::vec
   const int ngroups = (int)T.groups.size();
   AmrBuffers& B = S.buffers;
   // the cached buffers count as used memory: keep their batch size instead of choosing a smaller one every call
-  const int batch = (B.batch > 0 && B.batchNdir == ndir) ? std::min(B.batch, ngroups) : choose_batch(c, ngroups);
+  const bool keep = B.batch > 0 && B.batchNdir == ndir && B.batchTune == c.tune.amrBatch && B.batchN == N;
+  if (!keep) B.release();   // so that the new choice sees the memory they held
+  const int batch = keep ? std::min(B.batch, ngroups) : choose_batch(c, ngroups);
   const int64_t defCap = std::max<int64_t>(1 << 16, std::min<int64_t>((int64_t)batch * kGroup * N, (int64_t)1 << 26));
   int st = RTB200_OK;
   {
@@ -942,7 +1213,7 @@ int diffuse_amr(Context& c, int nAngularLevel, const double* uvb, const std::vec
       B.release();
       st = alloc_batch(B, T, N, batch, defCap, false, S.plan.balanced);  // (release() also forgets the cached neighbour tables)
       if (st) B.release();
-      else { B.sizeKey = buf; B.batch = batch; B.batchNdir = ndir; }
+      else { B.sizeKey = buf; B.batch = batch; B.batchNdir = ndir; B.batchTune = c.tune.amrBatch; B.batchN = N; }
     }
   }
   int64_t launches = 0;
@@ -988,6 +1259,11 @@ int diffuse_amr(Context& c, int nAngularLevel, const double* uvb, const std::vec
     *nsegOut = nseg;
   }
   cudaStreamSynchronize(s);
+  if (!B.epochKey.empty()) {   // a streamed sweep that gave up leaves records of both signs behind
+    int32_t gaveUp = 0;
+    if (cudaMemcpy(&gaveUp, B.defCount + 1, sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess || gaveUp) B.epochKey.clear();
+  }
+  if (st) B.epochKey.clear();
   c.lastSweepLaunches = launches;
   c.lastLaunches = launches + 2;
   return st;

@@ -120,6 +120,46 @@ def test_amr_direction_batches_and_shards(rt, engine, uvbg):
     assert na + nb_ == nfull and np.allclose(a + b, full, rtol=1e-13, atol=0)
 
 
+@pytest.mark.parametrize("name", ["one-level-box", "two-level-box", "disc-3-levels"])
+@pytest.mark.parametrize("mode", ["faithful", "fast"])
+def test_amr_streamed_sweep_equals_wave_launches_bit_for_bit(rt, engine, uvbg, name, mode):
+    """2:1-balanced grids run the whole sweep as ONE launch whose work items wait for their upstream intensity records
+    (validity = the sweep's sign bit on the record).  Same arithmetic and summation order as one launch per wave:
+    identical bits, sweep after sweep (the sign alternates), across mode switches, direction batches and shards"""
+    g = GRIDS[name]
+    engine.set_math(rt.MATH_FAITHFUL if mode == "faithful" else rt.MATH_FAST)
+    _set(engine, g)
+    uvb = uvbg["uvb"] * 1e-3
+    engine.set_tuning(amr_stream=0)
+    Jw, nw = engine.diffuse(uvb, uvbg["beta"])
+    waves = engine.last_stats()["launches"]
+    engine.set_tuning(amr_stream=1)
+    for rep in range(4):
+        J, ns = engine.diffuse(uvb, uvbg["beta"])
+        if name != "two-level-box":      # (its level-2 box touches level-0 cells: not 2:1 balanced, per-wave launches)
+            assert engine.last_stats()["launches"] < min(waves, 12), "the streamed path did not run"
+        assert ns == nw and np.array_equal(J, Jw), rep
+    engine.set_tuning(amr_stream=0)
+    assert np.array_equal(engine.diffuse(uvb, uvbg["beta"])[0], Jw)
+    engine.set_tuning(amr_stream=1)
+    assert np.array_equal(engine.diffuse(uvb, uvbg["beta"])[0], Jw)      # records re-initialised after the plain launches
+    engine.update_species(g["HI"] * 0.5, g["HeI"], g["HeII"])            # another sweep on other opacities, and back
+    J2, _ = engine.diffuse(uvb, uvbg["beta"])
+    assert not np.array_equal(J2, Jw)
+    engine.update_species(g["HI"], g["HeI"], g["HeII"])
+    assert np.array_equal(engine.diffuse(uvb, uvbg["beta"])[0], Jw)
+    engine.set_tuning(amr_batch=16)                                       # several batches share the buffers
+    for rep in range(2):
+        assert np.array_equal(engine.diffuse(uvb, uvbg["beta"])[0], Jw)
+    engine.set_tuning(amr_batch=0)
+    rays = np.arange(37, 101, dtype=np.int32)                             # a shard with ragged groups
+    a, _ = engine.diffuse(uvb, uvbg["beta"], rays=rays)
+    engine.set_tuning(amr_stream=0)
+    b, _ = engine.diffuse(uvb, uvbg["beta"], rays=rays)
+    assert np.array_equal(a, b)
+    engine.set_tuning(amr_stream=1)
+
+
 @pytest.mark.parametrize("name,lo,hi", [("unbalanced-corner", 37, 59), ("disc-3-levels", 100, 101),
                                         ("single-deep-cell", 0, 13)])
 def test_amr_ragged_direction_subset_vs_oracle(rt, engine, oracle, uvbg, name, lo, hi):

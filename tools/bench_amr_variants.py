@@ -1,4 +1,5 @@
-"""GPU experiment: nested-grid sweep with the per-item arrays in wave order / leaf order, thin rule on / off"""
+"""GPU experiment: nested-grid sweep as one streamed launch / one launch per wave, per-item arrays in wave order / leaf
+order, thin rule on / off"""
 import os, sys
 import numpy as np
 import torch
@@ -14,16 +15,16 @@ for n, levels in ((64, 3), (128, 2)):
     J = torch.zeros(3, N, dtype=torch.float64, device="cuda:0")
     s = torch.cuda.current_stream().cuda_stream
     ref = None
-    for slots, thin, pdl, mb in ((1, 1, 1, 8), (1, 1, 1, 6), (1, 0, 1, 8), (1, 0, 1, 6), (0, 1, 1, 8)):
-        t.set_tuning(amr_slots=slots, amr_thin=thin, pdl=pdl, amr_min_blocks=mb)
+    for stream, slots, thin, pdl, mb in ((0, 1, 1, 1, 6), (1, 1, 1, 1, 6), (1, 1, 0, 1, 6), (0, 1, 1, 1, 8), (0, 0, 1, 1, 8)):
+        t.set_tuning(amr_stream=stream, amr_slots=slots, amr_thin=thin, pdl=pdl, amr_min_blocks=mb)
         ms = []
-        for rep in range(4):
+        for rep in range(5):
             t.diffuse_device(bg["uvb"], bg["beta"], J.data_ptr(), stream=s)
             torch.cuda.synchronize()
             ms.append(t.last_stats()["device_ms"])
         Jh = J.cpu().numpy()
         if ref is None:
             ref = Jh
-        print(f"{n}^3+{levels} ({N} leaves) slots={slots} thin={thin} pdl={pdl} min_blocks={mb}: ms {['%.2f' % m for m in ms]} "
+        print(f"{n}^3+{levels} ({N} leaves) stream={stream} slots={slots} thin={thin} pdl={pdl} min_blocks={mb}: ms {['%.2f' % m for m in ms]} "
               f"max rel diff to first {np.max(np.abs(Jh - ref) / np.maximum(np.abs(ref), 1e-290)):.2e} err={t.device_error()}", flush=True)
     t.close()

@@ -36,7 +36,15 @@ def main():
         out.append(e)
     if not out:
         raise SystemExit("no matching kernel rows")
-    best = max(out, key=lambda e: e.get("duration", 0.0))        # the longest captured launch of the kernel
+    # mean over the captured launches of the kernel (mid-sweep layers / waves / passes), with the spread
+    best = {"kernel": out[0]["kernel"]}
+    for key in WANT.values():
+        vals = [e[key] for e in out if key in e]
+        if vals:
+            best[key] = sum(vals) / len(vals)
+    d_ = [e["duration"] for e in out if "duration" in e]
+    if d_:
+        best["duration_min"], best["duration_max"] = min(d_), max(d_)
     best["launches_captured"] = len(out)
     best["source"] = os.path.basename(path)
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
