@@ -698,9 +698,13 @@ def roofline_dict(res, world):
     peak, peak_src = measured_peak()
     kind = res["kind"]
     achieved = res["alg_bytes_rank"] / (res["sweep_ms"] * 1e-3) / 1e9 if res["sweep_ms"] > 0 else None
-    kernel = {"diffuse": "rtb::sweep_cell_kernel" if res["uniform"] else "rtb::amr_wave_kernel",
-              "iterate": "rtb::sweep_cell_kernel" if res["uniform"] else "rtb::amr_wave_kernel",
-              "point": "rtb::point_march_kernel", "combined": "rtb::amr_wave_kernel"}[kind]
+    # the library picks the kernel by shard / wave size: many zone tasks per launch -> two cells per thread; small
+    # waves on a 2:1-balanced nested grid -> the one-launch streamed sweep (a handful of launches per step)
+    per_pass = res["sweep_launches"]          # of the last sweep call
+    uni = "rtb::sweep_cell2_kernel" if world <= 4 else "rtb::sweep_cell_kernel"
+    amr = "rtb::amr_stream_kernel" if per_pass < 20 else "rtb::amr_wave_kernel"
+    kernel = {"diffuse": uni if res["uniform"] else amr, "iterate": uni if res["uniform"] else amr,
+              "point": "rtb::point_march_kernel", "combined": amr}[kind]
     rk = res["rank_kernel_ms"]
     d = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
          "traffic": ncu_traffic(res["workload"]) if world == 1 else None,
@@ -711,7 +715,9 @@ def roofline_dict(res, world):
          "note": ("72 B per leaf per direction (SURVEY.md 8d); zones are swept with their directions fused, so DRAM traffic "
                   "differs from the algorithmic bytes (profiles/)") if kind != "point" else
                  "136 B per segment (5 reads + 6 read-modify-writes, SURVEY.md 8d); bound by fp64 issue and gather latency"}
-    if kind in ("diffuse", "iterate") and res["sweep_launches"] > 1:
+    if kernel == "rtb::amr_stream_kernel":
+        d["algorithmic_bytes_per_launch"] = res["alg_bytes_rank"]      # the whole sweep is one launch of this kernel
+    elif kind in ("diffuse", "iterate") and res["sweep_launches"] > 1:
         d["algorithmic_bytes_per_launch"] = res["alg_bytes_rank"] / max(1, res["sweep_launches"] - 1)
     return d
 

@@ -120,9 +120,10 @@ int rtb200_set_math(rtb200_ctx* ctx, int math_mode);
  *                  exist only with RTB200_EXPERIMENTAL set in the environment), "l2_mb"
  *   nested grids   "force_amr" (general octree path on a uniform grid), "amr_batch" (directions per batch, 0 = as many
  *                  as fit in memory), "amr_stream" (2:1-balanced grids: 1 = the whole sweep as one launch whose work items wait
- *                  for their upstream intensity records, 0 = one launch per wave; identical bits), "amr_slots" (per-item arrays
+ *                  for their upstream intensity records, 0 = one launch per wave, -1 = by the size of the waves, the default;
+ *                  identical bits), "amr_slots" (per-item arrays
  *                  in wave order, 1), "amr_thin" (thin segments with the reference's operation sequence, 1), "amr_min_blocks"
- *                  (register cap of the wave kernel: 6 or 8 blocks per SM)
+ *                  (register cap of the wave kernel: 6 or 8 blocks per SM, 0 = by the size of the waves)
  *   device groups  "multi_reduce" (1 = peer-memory reduce-scatter kernel, 0 = NCCL), "zone_cost_x" / "_y" / "_z"
  *                  (relative time per segment of zones sweeping along x / y / z, for the direction sharding)
  *   point sources  "point_batch" (sources per batch), "point_min_blocks" (register cap of the march kernel, 5),

@@ -299,10 +299,10 @@ __device__ __forceinline__ void load_record(const AmrParams& P, const double* p,
     unsigned spins = 0;
     // every word validates itself (a 64-bit store is indivisible), so no fence and no ordering between the words
     while ((((a ^ P.epochSign) | (b ^ P.epochSign) | (c ^ P.epochSign)) >> 63) != 0) {
-      __nanosleep(40);
+      __nanosleep(100);
       if ((++spins & 63) == 0) {
         if (*(volatile int32_t*)P.abortFlag) break;
-        if (spins > (1u << 21)) { atomicExch(P.abortFlag, 1); atomicMax(P.err, RTB200_ERR_CUDA); break; }
+        if (spins > (1u << 20)) { atomicExch(P.abortFlag, 1); atomicMax(P.err, RTB200_ERR_CUDA); break; }
       }
       a = ld_relaxed_u64(p); b = ld_relaxed_u64(p + kGroup); c = ld_relaxed_u64(p + 2 * kGroup);
     }
@@ -543,12 +543,11 @@ struct StreamParams {
 
 constexpr int kStreamDirs = 192;   // directions of a batch the streamed kernel keeps in shared memory
 
-__device__ __forceinline__ void prefetch_l1_amr(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 // Every WARP is a worker of its own (4 leaves x 8 direction lanes = a quarter of a work item): no block barrier couples
 // fast and slow leaves.  Lane 0 runs three quarters ahead with the work counter and two ahead with the item record
-// (a small per-warp ring in shared memory), and the quarter after the current one has its streaming inputs --
-// neighbour record, opacities, pattern index: always DRAM misses -- prefetched while the current one is computed.
+// (a small per-warp ring in shared memory).  (Prefetching the next quarter's neighbour record, opacities and pattern
+// index into L1 was tried: 6% more instructions, no gain -- the kernel is bound by instruction issue at ~24 warps per
+// SM, ncu profiles/r02k2_*: IPC 1.75, 1130 warp instructions per quarter, not by the latency of those loads.)
 template <bool FAITHFUL, int MINB>
 __global__ void __launch_bounds__(128, MINB) amr_stream_kernel(AmrParams P, StreamParams Q, int ndirs, int ngroups) {
   __shared__ double sT[16];
@@ -581,19 +580,8 @@ __global__ void __launch_bounds__(128, MINB) amr_stream_kernel(AmrParams P, Stre
       if (cB < total) eB = __ldg(Q.items + (cB >> 2));
       cA = atomicAdd(Q.counter, 1);
     }
-    const int4 cur = sRing[w][k & 3], nxt = sRing[w][(k + 1) & 3];
+    const int4 cur = sRing[w][k & 3];
     if (!cur.w) break;
-    if (nxt.w) {
-      const int giN = nxt.x & 0xff, cntN = nxt.x >> 8, iN = nxt.z * 4 + li;
-      if (iN < cntN) {
-        const int64_t slotN = nxt.y + iN;
-        const AmrDir& DN = sDirs[sGroups[giN].x];
-        prefetch_l1_amr(P.nbc + item_index(P, giN, lane, slotN) * 4);
-        if (lane == 0) prefetch_l1_amr(P.kappaS + ((int64_t)DN.combo * P.N + slotN) * 6);
-        if (lane == 1) prefetch_l1_amr(P.kappaS + ((int64_t)DN.combo * P.N + slotN) * 6 + 4);
-        if (lane == 2) prefetch_l1_amr(P.patIdxS + ((int64_t)DN.combo * 3 + DN.patRow % 3) * P.N + slotN);
-      }
-    }
     const int gi = cur.x & 0xff, count = cur.x >> 8, i = cur.z * 4 + li;
     const int2 grp = sGroups[gi];
     const bool have = i < count, mine = have && lane < grp.y;
@@ -1039,7 +1027,17 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int g0, int ng
     (*launches)++;
     B.nbKey = wholeCall ? S.tablesKey : std::string();
   }
-  if (S.plan.balanced && c.tune.amrStream && !P.slotIsLeaf && nd <= kStreamDirs && ng <= kStreamDirs / kGroup * 2) {
+  // One launch for the whole batch, or one per wave?  Measured (profiles/r02k_*): 64^3 + 3 levels (21K leaf-groups per
+  // wave) 8.45 against 9.15 ms, 128^3 + 2 levels (87K per wave) 49.1 against 43.9 ms -- the streamed path saves the
+  // launch hand-overs of small waves and pays for its wave-ordered opacity copies and the merge's slot look-up.
+  int nonEmpty = 0;
+  for (int w = 0; w < S.plan.nkeys; w++)
+    for (int k = 0; k < 8; k++)
+      if (S.plan.waveStart[k][w + 1] > S.plan.waveStart[k][w]) { nonEmpty++; break; }
+  const double perWave = (double)N * ng / std::max(1, nonEmpty);
+  const bool smallWaves = perWave < 40000.;
+  const bool wantStream = c.tune.amrStream > 0 || (c.tune.amrStream < 0 && smallWaves);
+  if (S.plan.balanced && wantStream && !P.slotIsLeaf && nd <= kStreamDirs && ng <= kStreamDirs / kGroup * 2) {
     // ---- one launch for the whole batch (amr_stream_kernel) ----
     char kb[64];
     snprintf(kb, sizeof(kb), "|%d:%d", g0, ng);
@@ -1134,7 +1132,8 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int g0, int ng
       else RTB_CUDA(cudaLaunchKernelEx(&cfg, amr_wave_kernel<true, false>, P, Wp, ng));
     } else {
       if (check) RTB_CUDA(cudaLaunchKernelEx(&cfg, amr_wave_kernel<false, true>, P, Wp, ng));
-      else if (c.tune.amrMinBlocks <= 6) RTB_CUDA(cudaLaunchKernelEx(&cfg, amr_wave_kernel<false, false, 6>, P, Wp, ng));
+      else if (c.tune.amrMinBlocks > 0 ? c.tune.amrMinBlocks <= 6 : smallWaves)
+        RTB_CUDA(cudaLaunchKernelEx(&cfg, amr_wave_kernel<false, false, 6>, P, Wp, ng));
       else RTB_CUDA(cudaLaunchKernelEx(&cfg, amr_wave_kernel<false, false, 8>, P, Wp, ng));
     }
     prevWasWave = true;

@@ -65,8 +65,10 @@ struct Tuning {
   int useGraph = 1;
   int forceAmr = 0;      // route uniform grids through the general (AMR) path as well (cross-check)
   int amrSlots = 1;      // nested grids: per-item arrays indexed by the leaf's position in the wave order (1) or by leaf number (0)
-  int amrMinBlocks = 6;  // nested grids, FAST arithmetic: blocks of 128 threads per SM the wave kernel's register cap allows (8: 64, 6: 80 registers)
-  int amrStream = 1;     // nested grids, 2:1 balanced: the whole sweep as one launch ordered by the records' sign epoch (1) or one launch per wave (0)
+  int amrMinBlocks = 0;  // nested grids, FAST arithmetic: blocks of 128 threads per SM the wave kernel's register cap allows (8: 64,
+                         // 6: 80 registers; 0 = 6 for small waves, 8 for large ones)
+  int amrStream = -1;    // nested grids, 2:1 balanced: the whole sweep as one launch ordered by the records' sign epoch (1), one launch
+                         // per wave (0), or by the size of the waves (-1)
   int amrThin = 1;       // nested grids, FAST arithmetic: thin layers use the reference's operation sequence (1)
   int amrBatch = 0;      // directions per AMR batch (0 = as many as fit in half of the free memory)
   int lockstep = 1;      // 1: one launch per layer for all zones of a batch; 0: every slot an independent stream
