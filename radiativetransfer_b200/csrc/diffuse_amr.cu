@@ -474,10 +474,10 @@ struct WaveParams {
 // block = 16 leaves of the wave x 8 direction lanes; blockIdx.y = group of the batch
 template <bool FAITHFUL, bool CHECK, int MINB = 8>
 __global__ void __launch_bounds__(128, MINB) amr_wave_kernel(AmrParams P, WaveParams Wp, int ngroups) {
-  __shared__ double sT[16];
+  __shared__ double sT[kExpTableSize];
   asm volatile("griddepcontrol.launch_dependents;");               // the next wave may start its prologue early
   if (!FAITHFUL) {
-    if (threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
+    if (threadIdx.x < kExpTableSize) sT[threadIdx.x] = kExpTable32[threadIdx.x];
     __syncthreads();
   }
   const int gi = blockIdx.y;
@@ -550,11 +550,11 @@ constexpr int kStreamDirs = 192;   // directions of a batch the streamed kernel 
 // SM, ncu profiles/r02k2_*: IPC 1.75, 1130 warp instructions per quarter, not by the latency of those loads.)
 template <bool FAITHFUL, int MINB>
 __global__ void __launch_bounds__(128, MINB) amr_stream_kernel(AmrParams P, StreamParams Q, int ndirs, int ngroups) {
-  __shared__ double sT[16];
+  __shared__ double sT[kExpTableSize];
   __shared__ AmrDir sDirs[kStreamDirs];
   __shared__ int2 sGroups[kStreamDirs / kGroup * 2];
   __shared__ int4 sRing[4][4];       // per warp: (group | leaves << 8, first slot, quarter, valid)
-  if (threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
+  if (threadIdx.x < kExpTableSize) sT[threadIdx.x] = kExpTable32[threadIdx.x];
   if (threadIdx.x < ngroups) sGroups[threadIdx.x] = P.groups[threadIdx.x];
   for (int q = threadIdx.x; q < ndirs * 4; q += blockDim.x)    // 32-byte records, 8 bytes at a time
     reinterpret_cast<double*>(sDirs)[q] = __ldg(reinterpret_cast<const double*>(P.dirs) + q);
@@ -613,9 +613,9 @@ __global__ void __launch_bounds__(128, MINB) amr_stream_kernel(AmrParams P, Stre
 template <bool FAITHFUL>
 __global__ void amr_retry_kernel(AmrParams P, const int64_t* in, const int32_t* inCount, int64_t* out, int32_t* outCount,
                                  int64_t cap) {
-  __shared__ double sT[16];
+  __shared__ double sT[kExpTableSize];
   if (!FAITHFUL) {
-    if (threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
+    if (threadIdx.x < kExpTableSize) sT[threadIdx.x] = kExpTable32[threadIdx.x];
     __syncthreads();
   }
   const int n = min((int64_t)*inCount, cap);

@@ -261,13 +261,13 @@ sweep_cell_kernel(const __grid_constant__ BatchParams bp, int N, int n, int np1,
   // operands instead of values re-derived from the task table for every direction
   const StepParams& sp = bp.t[blockIdx.z];
   const double* __restrict__ kappa = sp.kappa;
-  __shared__ double sT[16];
+  __shared__ double sT[kExpTableSize];
   // Programmatic dependent launch (set_tuning "pdl"): the next layer's grid may start as soon as every block of this
   // one is running, do its own prologue (table, indices, opacities -- nothing a sweep kernel writes) and then wait at
   // griddepcontrol.wait below until this grid has completed and flushed.  Both instructions are no-ops for a grid
   // launched without the attribute.
   asm volatile("griddepcontrol.launch_dependents;");
-  if (threadIdx.y == 0 && threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
+  if (threadIdx.y * 32 + threadIdx.x < kExpTableSize) sT[threadIdx.y * 32 + threadIdx.x] = kExpTable32[threadIdx.y * 32 + threadIdx.x];
   __syncthreads();
   const int a = blockIdx.x * 31 - 1 + (int)threadIdx.x, b = blockIdx.y * blockDim.y + threadIdx.y;
   if (b >= n) return;                                          // warp-uniform
@@ -398,9 +398,9 @@ __global__ void __launch_bounds__(256, MINB)
 sweep_cell2_kernel(const __grid_constant__ BatchParams bp, int N, int n, int np1, int npl3) {
   const StepParams& sp = bp.t[blockIdx.z];
   const double* __restrict__ kappa = sp.kappa;
-  __shared__ double sT[16];
+  __shared__ double sT[kExpTableSize];
   asm volatile("griddepcontrol.launch_dependents;");
-  if (threadIdx.y == 0 && threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
+  if (threadIdx.y * 32 + threadIdx.x < kExpTableSize) sT[threadIdx.y * 32 + threadIdx.x] = kExpTable32[threadIdx.y * 32 + threadIdx.x];
   __syncthreads();
   const int a = blockIdx.x * 31 - 1 + (int)threadIdx.x, b0 = 2 * (blockIdx.y * blockDim.y + threadIdx.y);
   if (b0 >= n) return;                                         // warp-uniform
@@ -606,11 +606,11 @@ __device__ __forceinline__ int ld_relaxed_gpu(const int32_t* p) {
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB) sweep_persistent_kernel(const __grid_constant__ PersistParams pp, int32_t* err) {
   extern __shared__ double smem[];
-  double* sT = smem;                                           // 16-entry exp table
-  LayerSeg* sSeg = reinterpret_cast<LayerSeg*>(smem + 16);     // [kMaxDirPerTask] tables of the item's task and layer
+  double* sT = smem;                                           // exp table (kExpTableSize entries)
+  LayerSeg* sSeg = reinterpret_cast<LayerSeg*>(smem + kExpTableSize);     // [kMaxDirPerTask] tables of the item's task and layer
   __shared__ int sItem;
   const int tid = threadIdx.y * 32 + threadIdx.x;
-  if (tid < 16) sT[tid] = kExpTable[tid];
+  if (tid < kExpTableSize) sT[tid] = kExpTable32[tid];
   constexpr int segDoubles = (int)(sizeof(LayerSeg) / sizeof(double)) * kMaxDirPerTask;
   const int warps = blockDim.y;
   const int total = pp.n * pp.itemsPerLayer;
@@ -699,9 +699,9 @@ sweep_march_kernel(const __grid_constant__ MarchBatch mb, const double* __restri
                    double u1, double u2, int32_t* __restrict__ err, int dbg) {
   const MarchTask& T = mb.t[blockIdx.z];
   extern __shared__ double smem[];
-  double* sT = smem;                // 16-entry exp table
-  double* sX = smem + 16;           // plane tile [2][ndir][3][8][32]
-  if (threadIdx.y == 0 && threadIdx.x < 16) sT[threadIdx.x] = kExpTable[threadIdx.x];
+  double* sT = smem;                // exp table (kExpTableSize entries)
+  double* sX = smem + kExpTableSize;           // plane tile [2][ndir][3][8][32]
+  if (threadIdx.y * 32 + threadIdx.x < kExpTableSize) sT[threadIdx.y * 32 + threadIdx.x] = kExpTable32[threadIdx.y * 32 + threadIdx.x];
   const int ndir = T.ndir;
   const int lane = threadIdx.x, row = threadIdx.y;
   const int a = blockIdx.x * 31 - 1 + lane, b = blockIdx.y * 8 + row;
@@ -1047,7 +1047,7 @@ static int run_march(Context& c, int n, const double* uvb, double* dJout, cudaSt
   const int ntask = (int)c.uniTasks.size();
   int maxNd = 1;
   for (const auto& T : c.uniTasks) maxNd = std::max(maxNd, T.ndir);
-  const size_t smemBytes = (16 + (size_t)2 * maxNd * 768) * sizeof(double);
+  const size_t smemBytes = (kExpTableSize + (size_t)2 * maxNd * 768) * sizeof(double);
   const int expv = c.tune.expVariant;
   int cap = 0;
   // register budget: 2 blocks per SM (128 registers) unless the tile buffers allow 4 (64 registers)
@@ -1138,7 +1138,7 @@ static int run_persistent(Context& c, int n, const double* uvb, double* dJout, c
   }
   const size_t counterBytes = ((size_t)ntask * gx * gyT + 1) * sizeof(int32_t);
   if (int e = ensure_buffer((void**)&c.dMarchProg, &c.marchProgBytes, counterBytes)) return e;
-  const size_t smemBytes = 16 * sizeof(double) + (size_t)kMaxDirPerTask * sizeof(LayerSeg);
+  const size_t smemBytes = kExpTableSize * sizeof(double) + (size_t)kMaxDirPerTask * sizeof(LayerSeg);
   auto kern = sweep_persistent_kernel<2>;
   if (smemBytes > 48 * 1024) RTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
   int perSm = 0;

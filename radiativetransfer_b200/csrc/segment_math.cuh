@@ -63,6 +63,87 @@ __device__ __forceinline__ void exp_neg_parts(double tau, const double* __restri
   Ts = __hiloint2double(__double2hiint(Tj) - ((k >> 4) << 20), __double2loint(Tj));
 }
 
+// The sweeps' exponential (round 2).  The uniform sweep runs into the board's power cap, so its time follows the fp64
+// instruction count: a larger table shortens the polynomial.  64 entries: |r| <= ln2/128 = 0.0054, p = e^-r - 1 through
+// r^4 -- 3 of the 12 FP64 instructions less per exponential.  Truncation: |dp / p| <= r^4 / 120 = 7.2e-12, i.e. 3.9e-14
+// of e^-tau per segment, < 2e-11 after the 512 segments of the longest ray, and 7.2e-12 of a segment's contribution to
+// J: two orders of magnitude inside the 1e-9 that FAST arithmetic is held to (measured FAST vs FAITHFUL on the full
+// 256^3 x 192 solve: 4.1e-10, unchanged -- that difference is the reference formula's own rounding noise).
+// Measured at 256^3 on one box, 20 solves back to back under the power cap: 16 entries / r^7 53.8 ms, 32 / r^5
+// 50.7 ms, 64 / r^4 49.8 ms (the 4-way bank conflicts of the larger table cost less than the DFMA saves).
+// (The point-source kernels keep the 16-entry / r^7 version above: their deposits are differences of exponentials.)
+#ifndef RTB_EXP_TABLE
+#define RTB_EXP_TABLE 64
+#endif
+constexpr int kExpTableSize = RTB_EXP_TABLE;
+#if RTB_EXP_TABLE == 32   // 32 entries, |r| <= ln2/64, polynomial through r^5
+static __constant__ double kExpC32[12] = {
+    -8.33333333333333333333e-03,  // [0] -1/5!
+    4.16666666666666666667e-02,   // [1]  1/4!
+    -1.66666666666666666667e-01,  // [2] -1/3!
+    0.5,                          // [3]
+    -1.0,                         // [4]
+    46.16624130844683,            // [5]  32/ln2
+    6755399441055744.0,           // [6]  1.5 * 2^52
+    -0.02166084898635745,         // [7]  -ln2/32, high part (28 trailing zero bits)
+    -4.06140840434059e-10,        // [8]  -ln2/32, low part
+    0., 0., 0.};
+constexpr int kExpDeg = 4;       // Horner steps after the leading coefficient
+constexpr int kExpShift = 5;
+static __constant__ double kExpTable32[32] = {
+    1.00000000000000000000e+00, 9.78572062087700089705e-01, 9.57603280698573700036e-01, 9.37083817055149981279e-01,
+    9.17004043204671215328e-01, 8.97354537501553584100e-01, 8.78126080186649726755e-01, 8.59309649061238967072e-01,
+    8.40896415253714502036e-01, 8.22877739076982472888e-01, 8.05245165974627141736e-01, 7.87990422553943248296e-01,
+    7.71105412703970372057e-01, 7.54582213796711420706e-01, 7.38413072969749673113e-01, 7.22590403488523325137e-01,
+    7.07106781186547572737e-01, 6.91954940981916011289e-01, 6.77127773468446325644e-01, 6.62618321579870661608e-01,
+    6.48419777325504820276e-01, 6.34525478595866609943e-01, 6.20928906036742001007e-01, 6.07623679990234477621e-01,
+    5.94603557501360513449e-01, 5.81862429388788737761e-01, 5.69394317378345782288e-01, 5.57193371297946216103e-01,
+    5.45253866332628844837e-01, 5.33570200338411848584e-01, 5.22136891213706877402e-01, 5.10948574327058313571e-01};
+#else   // 64 entries, |r| <= ln2/128, polynomial through r^4 (default)
+static __constant__ double kExpC32[12] = {
+    0., 4.16666666666666666667e-02, -1.66666666666666666667e-01, 0.5, -1.0,
+    92.33248261689366,            // [5]  64/ln2
+    6755399441055744.0,
+    -0.010830424493178725,        // [7]  -ln2/64 hi
+    -2.030704202170295e-10,       // [8]  -ln2/64 lo
+    0., 0., 0.};
+constexpr int kExpDeg = 3;
+constexpr int kExpShift = 6;
+static __constant__ double kExpTable32[64] = {
+    1.00000000000000000000e+00, 9.89228013193975463935e-01, 9.78572062087700089705e-01, 9.68030896746147173637e-01,
+    9.57603280698573700036e-01, 9.47287990793482803653e-01, 9.37083817055149981279e-01, 9.26989562541692735387e-01,
+    9.17004043204671215328e-01, 9.07126087750199427973e-01, 8.97354537501553584100e-01, 8.87688246263260594127e-01,
+    8.78126080186649726755e-01, 8.68666917636853108675e-01, 8.59309649061238967072e-01, 8.50053176859261738763e-01,
+    8.40896415253714502036e-01, 8.31838290163368188068e-01, 8.22877739076982472888e-01, 8.14013710928673916989e-01,
+    8.05245165974627141736e-01, 7.96571075671133499441e-01, 7.87990422553943248296e-01, 7.79502200118918464611e-01,
+    7.71105412703970372057e-01, 7.62799075372269208550e-01, 7.54582213796711420706e-01, 7.46453864145632417504e-01,
+    7.38413072969749673113e-01, 7.30458897090323522328e-01, 7.22590403488523325137e-01, 7.14806669195985011633e-01,
+    7.07106781186547572737e-01, 6.99489836269155618176e-01, 6.91954940981916011289e-01, 6.84501211487295257996e-01,
+    6.77127773468446325644e-01, 6.69833762026651458044e-01, 6.62618321579870661608e-01, 6.55480605762382206869e-01,
+    6.48419777325504820276e-01, 6.41435008039389131795e-01, 6.34525478595866609943e-01, 6.27690378512345548145e-01,
+    6.20928906036742001007e-01, 6.14240268053435012341e-01, 6.07623679990234477621e-01, 6.01078365726351537823e-01,
+    5.94603557501360513449e-01, 5.88198495825140610371e-01, 5.81862429388788737761e-01, 5.75594614976491336655e-01,
+    5.69394317378345782288e-01, 5.63260809304120924068e-01, 5.57193371297946216103e-01, 5.51191291653920445448e-01,
+    5.45253866332628844837e-01, 5.39380398878559930154e-01, 5.33570200338411848584e-01, 5.27822589180278578525e-01,
+    5.22136891213706877402e-01, 5.16512439510614207450e-01, 5.10948574327058313571e-01, 5.05444643025850237628e-01};
+#endif
+
+template <bool GUARD = true>
+__device__ __forceinline__ void exp_neg_parts32(double tau, const double* __restrict__ T, double& Ts, double& p) {
+  if (GUARD) tau = __hiloint2double(min(__double2hiint(tau), 0x40861800), __double2loint(tau));
+  double t = fma(tau, kExpC32[5], kExpC32[6]);
+  int k = __double2loint(t);
+  double fn = t - kExpC32[6];
+  double r = fma(fn, kExpC32[7], tau);
+  r = fma(fn, kExpC32[8], r);
+  double q = kExpC32[4 - kExpDeg];
+#pragma unroll
+  for (int i = 5 - kExpDeg; i <= 4; i++) q = fma(q, r, kExpC32[i]);
+  p = q * r;
+  double Tj = T[k & (kExpTableSize - 1)];
+  Ts = __hiloint2double(__double2hiint(Tj) - ((k >> kExpShift) << 20), __double2loint(Tj));
+}
+
 // Table-free variant (T == nullptr at compile time is not needed: chosen by the EXPV template parameter):
 // exp(-tau) = 2^n * exp(r), n = round(-tau/ln2), |r| <= ln2/2, Taylor through r^12.  ~20 FP64 instructions.
 static __constant__ double kExpP[16] = {
@@ -118,7 +199,7 @@ __device__ __forceinline__ double exp_neg_only(double tau, const double* __restr
 template <int EXPV, bool GUARD = true>
 __device__ __forceinline__ double segment_fast(double Iin, double tau, double cs, const double* __restrict__ T, double& A) {
   double Ts, p;
-  if (EXPV == 1) exp_neg_parts<GUARD>(tau, T, Ts, p);
+  if (EXPV == 1) exp_neg_parts32<GUARD>(tau, T, Ts, p);
   else exp_neg_parts_poly(tau, Ts, p);
   const double X = Iin * Ts;
   const double Iout = fma(X, p, X);
@@ -131,7 +212,7 @@ __device__ __forceinline__ double segment_fast(double Iin, double tau, double cs
 template <int EXPV, bool GUARD = true>
 __device__ __forceinline__ double attenuate_fast(double Iin, double tau, const double* __restrict__ T) {
   double Ts, p;
-  if (EXPV == 1) exp_neg_parts<GUARD>(tau, T, Ts, p);
+  if (EXPV == 1) exp_neg_parts32<GUARD>(tau, T, Ts, p);
   else exp_neg_parts_poly(tau, Ts, p);
   const double X = Iin * Ts;
   return fma(X, p, X);
