@@ -294,6 +294,11 @@ int rtb200_neighbours(rtb200_ctx* ctx, int nAngularLevel, int64_t iray, int32_t*
  * same header is what makes the FAITHFUL point-source deposits comparable bit for bit, tests/test_portable_math.py) */
 int rtb200_debug_portable_math(rtb200_ctx* ctx, int64_t n, const double* x, double* expOut, double* logOut);
 
+/* the FAST arithmetic's exponential of the diffuse sweeps (csrc/segment_math.cuh: 64-entry table, degree-4 polynomial)
+ * evaluated on the device for n host values tau >= 0: e^-tau and 1 - e^-tau (the latter without cancellation).  Its
+ * truncation error is part of FAST mode's error budget; tests/test_diffuse_gpu.py holds it to 1e-11. */
+int rtb200_debug_fast_exp(rtb200_ctx* ctx, int64_t n, const double* tau, double* expOut, double* oneMinusOut);
+
 /* timing of the last rtb200_diffuse* call, from CUDA events on the launch stream: device milliseconds of the whole
  * call (opacities + sweep + merge) and of the sweep kernels alone, kernel launches issued (all / sweep kernel), and
  * the algorithmic bytes of the call (72 B per leaf per direction). */

@@ -8,6 +8,7 @@
 
 #include "portable_math.h"
 #include "rtb200_internal.h"
+#include "segment_math.cuh"
 
 namespace rtb {
 
@@ -16,6 +17,19 @@ __global__ void portable_math_kernel(const double* __restrict__ x, int64_t n, do
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     e[i] = rtb_pm::pm_exp(x[i]);
     l[i] = rtb_pm::pm_log(x[i]);
+  }
+}
+
+// the sweeps' FAST exponential (segment_math.cuh: table + short polynomial) for n host values: e^-tau and 1 - e^-tau
+__global__ void fast_exp_kernel(const double* __restrict__ tau, int64_t n, double* __restrict__ e, double* __restrict__ ome) {
+  __shared__ double sT[kExpTableSize];
+  if (threadIdx.x < kExpTableSize) sT[threadIdx.x] = kExpTable32[threadIdx.x];
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double Ts, p;
+    exp_neg_parts32<true>(tau[i], sT, Ts, p);
+    e[i] = fma(Ts, p, Ts);
+    ome[i] = fma(-Ts, p, 1.0 - Ts);
   }
 }
 
@@ -624,6 +638,26 @@ int rtb200_debug_portable_math(rtb200_ctx* h, int64_t n, const double* x, double
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(expOut, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost, c.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(logOut, d + 2 * n, (size_t)n * 8, cudaMemcpyDeviceToHost, c.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+  cudaFree(d);
+  RTB_CUDA(e);
+  return RTB200_OK;
+}
+
+int rtb200_debug_fast_exp(rtb200_ctx* h, int64_t n, const double* tau, double* expOut, double* oneMinusOut) {
+  if (!h || n < 0 || !tau || !expOut || !oneMinusOut) return RTB200_ERR_ARG;
+  if (n == 0) return RTB200_OK;
+  Context& c = h->m ? multi_primary(h->m) : h->c;
+  RTB_CUDA(cudaSetDevice(c.device));
+  double* d = nullptr;
+  RTB_CUDA(cudaMalloc((void**)&d, (size_t)3 * n * sizeof(double)));
+  cudaError_t e = cudaMemcpyAsync(d, tau, (size_t)n * 8, cudaMemcpyHostToDevice, c.stream);
+  if (e == cudaSuccess) {
+    fast_exp_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 4096), 256, 0, c.stream>>>(d, n, d + n, d + 2 * n);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(expOut, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost, c.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(oneMinusOut, d + 2 * n, (size_t)n * 8, cudaMemcpyDeviceToHost, c.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
   cudaFree(d);
   RTB_CUDA(e);

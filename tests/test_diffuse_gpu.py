@@ -336,3 +336,26 @@ def test_headline_256cube_full_192dir_vs_oracle(rt, engine, oracle, uvbg):
         err = rel_err(J, o["J"])
         print(f"256^3 x 192 vs oracle, {name}: rel L-inf {err:.3e}")
         assert err < TOL
+
+
+def test_fast_exponential_error_budget(rt, engine):
+    """FAST arithmetic's exponential (64-entry table, degree-4 polynomial) against libm in extended precision: the
+    truncation error DESIGN.md 4.1 budgets (7.2e-12 of 1 - e^-tau, 3.9e-14 of e^-tau per segment), over the whole range
+    of optical depths incl. the table's interval ends, tiny tau (no cancellation in 1 - e^-tau) and the clamp"""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    tau = np.concatenate([10.0 ** rng.uniform(-12, 2.8, 200000), np.arange(0, 4096) * (np.log(2) / 128),
+                          np.array([0.0, 1e-300, 5e-324, 700.0, 707.0, 1e4])])
+    e, ome = np.empty_like(tau), np.empty_like(tau)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert engine.L.rtb200_debug_fast_exp(engine.h, int(tau.size), p(tau), p(e), p(ome)) == 0
+    t = tau.astype(np.longdouble)
+    ref_e, ref_ome = np.exp(-t), -np.expm1(-t)
+    ok = tau <= 700.0                                   # beyond: clamped (e^-tau < 1e-304 multiplies an intensity)
+    rel_e = np.abs((e[ok] - ref_e[ok]) / ref_e[ok]).astype(np.float64)
+    nz = ok & (tau > 0)
+    rel_ome = np.abs((ome[nz] - ref_ome[nz]) / ref_ome[nz]).astype(np.float64)
+    assert rel_e.max() < 1e-13, rel_e.max()
+    assert rel_ome.max() < 1e-11, rel_ome.max()
+    assert ome[tau == 0.0][0] == 0.0 and e[tau == 0.0][0] == 1.0
+    assert np.all(e[~ok] >= 0) and np.all(e[~ok] < 1e-300) and np.all(ome[~ok] == 1.0)
