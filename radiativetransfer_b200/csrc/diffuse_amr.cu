@@ -1087,6 +1087,12 @@ static int run_batch(Context& c, AmrState& S, const DirTables& T, int g0, int ng
     if (faithful) {
       RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, amr_stream_kernel<true, 4>, 128, 0));
       amr_stream_kernel<true, 4><<<std::min(perSm * c.smCount, (int)B.nitems), 128, 0, s>>>(P, Q, nd, ng);
+    } else if (c.tune.amrMinBlocks >= 8) {
+      RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, amr_stream_kernel<false, 8>, 128, 0));
+      amr_stream_kernel<false, 8><<<std::min(perSm * c.smCount, (int)B.nitems), 128, 0, s>>>(P, Q, nd, ng);
+    } else if (c.tune.amrMinBlocks == 5) {
+      RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, amr_stream_kernel<false, 5>, 128, 0));
+      amr_stream_kernel<false, 5><<<std::min(perSm * c.smCount, (int)B.nitems), 128, 0, s>>>(P, Q, nd, ng);
     } else {
       RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, amr_stream_kernel<false, 6>, 128, 0));
       amr_stream_kernel<false, 6><<<std::min(perSm * c.smCount, (int)B.nitems), 128, 0, s>>>(P, Q, nd, ng);

@@ -15,7 +15,7 @@ for n, levels in ((64, 3), (128, 2)):
     J = torch.zeros(3, N, dtype=torch.float64, device="cuda:0")
     s = torch.cuda.current_stream().cuda_stream
     ref = None
-    for stream, slots, thin, pdl, mb in ((0, 1, 1, 1, 6), (1, 1, 1, 1, 6), (1, 1, 0, 1, 6), (0, 1, 1, 1, 8), (0, 0, 1, 1, 8)):
+    for stream, slots, thin, pdl, mb in ((0, 1, 1, 1, 6), (1, 1, 1, 1, 6), (1, 1, 1, 1, 8), (1, 1, 1, 1, 5), (0, 1, 1, 1, 8)):
         t.set_tuning(amr_stream=stream, amr_slots=slots, amr_thin=thin, pdl=pdl, amr_min_blocks=mb)
         ms = []
         for rep in range(5):
