@@ -547,7 +547,10 @@ constexpr int kStreamDirs = 192;   // directions of a batch the streamed kernel 
 // fast and slow leaves.  Lane 0 runs three quarters ahead with the work counter and two ahead with the item record
 // (a small per-warp ring in shared memory).  (Prefetching the next quarter's neighbour record, opacities and pattern
 // index into L1 was tried: 6% more instructions, no gain -- the kernel is bound by instruction issue at ~24 warps per
-// SM, ncu profiles/r02k2_*: IPC 1.75, 1130 warp instructions per quarter, not by the latency of those loads.)
+// SM, ncu profiles/r02k2_*: IPC 1.75, 1130 warp instructions per quarter, not by the latency of those loads.  Also
+// tried: register caps for 5 / 6 / 8 blocks per SM (8.15 / 8.15 / 8.65 ms at 64^3 + 3 levels), and completing the
+// partly written 32-byte sectors of the record rows of leaves with inactive lanes so that L2 evicts whole sectors
+// (8.56 against 8.37 ms: the extra stores cost more than the avoided fills).)
 template <bool FAITHFUL, int MINB>
 __global__ void __launch_bounds__(128, MINB) amr_stream_kernel(AmrParams P, StreamParams Q, int ndirs, int ngroups) {
   __shared__ double sT[kExpTableSize];
