@@ -121,7 +121,9 @@ int rtb200_set_math(rtb200_ctx* ctx, int math_mode);
  *   nested grids   "force_amr" (general octree path on a uniform grid), "amr_batch" (directions per batch, 0 = as many
  *                  as fit in memory), "amr_stream" (2:1-balanced grids: 1 = the whole sweep as one launch whose work items wait
  *                  for their upstream intensity records, 0 = one launch per wave, -1 = by the size of the waves, the default;
- *                  identical bits), "amr_slots" (per-item arrays
+ *                  identical bits), "amr_order" (waves of the sweep: -1 = centre-sum key on 2:1-balanced grids and the leaf's depth in the dependency
+ *                  graph elsewhere, 1 = depth always, 0 = centre-sum key with per-leaf flags and a deferred list on grids that
+ *                  are not balanced: the round-1 scheme; identical bits), "amr_slots" (per-item arrays
  *                  in wave order, 1), "amr_thin" (thin segments with the reference's operation sequence, 1), "amr_min_blocks"
  *                  (register cap of the wave kernel: 6 or 8 blocks per SM, 0 = by the size of the waves)
  *   device groups  "multi_reduce" (1 = peer-memory reduce-scatter kernel, 0 = NCCL), "zone_cost_x" / "_y" / "_z"

@@ -246,6 +246,7 @@ int set_tuning(Context& c, const char* key, double value) {
   else if (k == "amr_slots") c.tune.amrSlots = (int)value;
   else if (k == "amr_thin") c.tune.amrThin = (int)value;
   else if (k == "amr_stream") c.tune.amrStream = (int)value;
+  else if (k == "amr_order") c.tune.amrOrder = (int)value;
   else if (k == "amr_min_blocks") c.tune.amrMinBlocks = (int)value;
   else if (k == "slots") c.tune.slots = (int)value;
   else if (k == "graph") c.tune.useGraph = (int)value;

@@ -10,10 +10,13 @@
 //    low face of its parent, step to the sibling / base neighbour, descend the linear octree with the `.le.0.5`
 //    tests on the exactly halved/doubled entry point).  One thread per (leaf, direction).
 //  * Transport order: the reference visits leaves in rotated i/j/k order so that upstream leaves are finished.  Here
-//    leaves are grouped in waves by the sum of their centre coordinates in rotated space, which increases strictly
-//    along every dependency edge when neighbouring leaves differ by at most one level; one launch per wave for all
-//    directions of the batch.  Grids that violate the 2:1 balance are still handled exactly: a leaf whose upstream
-//    leaf has not been published yet is put on a deferred list that is retried after every wave.
+//    leaves are grouped in waves; all leaves a leaf reads from lie in earlier waves.  On 2:1-balanced grids the wave
+//    is the sum of the leaf's centre coordinates in rotated space, which increases strictly along every dependency
+//    edge when neighbouring leaves differ by at most one level; on any other octree it is the leaf's depth in the
+//    dependency graph (build_waves).  One launch per wave for all directions of the batch, or one launch for the
+//    whole batch whose work items wait for the records they read (amr_stream_kernel).  (tuning amr_order = 0: the
+//    round-1 scheme for unbalanced grids -- centre-sum waves, a leaf whose upstream leaf has not been published yet
+//    is put on a deferred list that is retried after every 16th wave.)
 //  * Items are stored DIRECTION-fastest: the directions of a batch are grouped by zone (up to 8 per group: same index
 //    rotation, hence the same upstream leaves away from refinement boundaries), 8 adjacent lanes of a warp work on
 //    the 8 directions of one leaf, and the per-item arrays are [group][leaf][8]: what a warp gathers for a leaf --
@@ -697,33 +700,112 @@ struct AmrPlan {
   int32_t* dPatIdxS = nullptr;        // [8][3][N] the same in wave order (streamed sweep), built on first use
 };
 
-// wave key = sum over the rotated axes of the leaf centre in half-finest-cell units (see header comment)
-static void build_waves(Context& c, AmrPlan& plan) {
+// leaf that contains the finest-level cell p (physical coordinates at level Lmax)
+static int32_t leaf_at_finest(const Context& c, const int (&p)[3]) {
+  const int n = c.nx, Lmax = c.maxLevel;
+  int node = ((p[0] >> Lmax) * n + (p[1] >> Lmax)) * n + (p[2] >> Lmax);
+  for (int t = Lmax - 1; c.hChild[node] >= 0; t--)
+    node = c.hChild[node] + (((p[0] >> t) & 1) << 2) + (((p[1] >> t) & 1) << 1) + ((p[2] >> t) & 1);
+  return -(c.hChild[node] + 1);
+}
+
+// Waves of the sweep, per reflection combination: `sorted` = leaves ordered by wave, `waveStart` = first position of
+// every wave.  All leaves a leaf reads from -- its neighbours across the three low faces in reflected coordinates --
+// must lie in earlier waves.
+//  * 2:1-balanced grids: wave = sum over the axes of the leaf centre in half-finest-cell units, which increases strictly
+//    along every dependency when face neighbours differ by at most one level (see header comment).
+//  * any other octree (`byDepth`): no linear function of position and size orders every face pair (a coarse leaf
+//    next to leaves two or more levels finer breaks the centre sum either way), so the wave is the leaf's DEPTH in
+//    the dependency graph, 1 + max over its upstream face neighbours.  It is computed in one pass over the leaves in
+//    Morton order of the reflected coordinates -- the order in which the reference itself visits the tree, and a
+//    topological order of the dependencies for ANY octree (a leaf and its upstream face neighbour sit in two children
+//    of their lowest common ancestor that differ only in the bit of the crossed axis).  A neighbour of the same size
+//    or coarser is looked up and its depth pulled; finer neighbours were visited before and have pushed theirs.
+static void build_waves(Context& c, AmrPlan& plan, bool byDepth) {
   const int Lmax = c.maxLevel;
   const int64_t N = c.nleaf;
   const int span = (c.nx << Lmax) * 2;  // centre coordinate range per axis
-  plan.nkeys = 3 * span + 1;
+  const int fine = c.nx << Lmax;        // finest cells per axis
   std::vector<int32_t> key((size_t)N);
+  std::vector<int32_t> depth, cand, order;
+  std::vector<uint64_t> morton;
+  int nkeys = byDepth ? 0 : 3 * span + 1;
+  std::vector<std::vector<int32_t>> keys(8);
   for (int combo = 0; combo < 8; combo++) {
+    if (!byDepth) {
+      for (int64_t l = 0; l < N; l++) {
+        const int L = c.hLevel[l];
+        const int sc = 1 << (Lmax - L);
+        const int nL = c.nx << L;
+        const int p[3] = {c.hLeafX[l], c.hLeafY[l], c.hLeafZ[l]};
+        int k = 0;
+        for (int a = 0; a < 3; a++) {
+          const int r = (combo >> a) & 1 ? nL - 1 - p[a] : p[a];
+          k += (2 * r + 1) * sc;
+        }
+        key[l] = k;
+      }
+    } else {
+      // reflected low corner at the finest level, Morton code of it
+      morton.resize((size_t)N); order.resize((size_t)N);
+      auto rlo = [&](int64_t l, int (&r)[3], int& sz) {
+        const int L = c.hLevel[l];
+        sz = 1 << (Lmax - L);
+        const int p[3] = {c.hLeafX[l] * sz, c.hLeafY[l] * sz, c.hLeafZ[l] * sz};
+        for (int a = 0; a < 3; a++) r[a] = (combo >> a) & 1 ? fine - sz - p[a] : p[a];
+      };
+      for (int64_t l = 0; l < N; l++) {
+        int r[3], sz;
+        rlo(l, r, sz);
+        uint64_t m = 0;
+        for (int b = 0; b < 21; b++)
+          m |= ((uint64_t)((r[0] >> b) & 1) << (3 * b + 2)) | ((uint64_t)((r[1] >> b) & 1) << (3 * b + 1)) |
+               ((uint64_t)((r[2] >> b) & 1) << (3 * b));
+        morton[(size_t)l] = m;
+        order[(size_t)l] = (int32_t)l;
+      }
+      std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return morton[(size_t)x] < morton[(size_t)y]; });
+      depth.assign((size_t)N, 0); cand.assign((size_t)N, 0);
+      auto physical = [&](const int (&r)[3], int (&p)[3]) {   // reflected finest cell -> physical finest cell
+        for (int a = 0; a < 3; a++) p[a] = (combo >> a) & 1 ? fine - 1 - r[a] : r[a];
+      };
+      for (int64_t i = 0; i < N; i++) {
+        const int32_t l = order[(size_t)i];
+        int r[3], sz;
+        rlo(l, r, sz);
+        int d = cand[(size_t)l];
+        for (int a = 0; a < 3; a++) {          // upstream: the leaf behind the low face, if it is not finer
+          if (r[a] == 0) continue;
+          int q[3] = {r[0], r[1], r[2]}, p[3];
+          q[a] = r[a] - 1;
+          physical(q, p);
+          const int32_t u = leaf_at_finest(c, p);
+          if (c.hLevel[u] <= c.hLevel[l]) d = std::max(d, depth[(size_t)u] + 1);
+        }
+        depth[(size_t)l] = d;
+        for (int a = 0; a < 3; a++) {          // downstream: a coarser leaf behind the high face learns about this one
+          if (r[a] + sz >= fine) continue;
+          int q[3] = {r[0], r[1], r[2]}, p[3];
+          q[a] = r[a] + sz;
+          physical(q, p);
+          const int32_t dn = leaf_at_finest(c, p);
+          if (c.hLevel[dn] < c.hLevel[l]) cand[(size_t)dn] = std::max(cand[(size_t)dn], d + 1);
+        }
+      }
+      for (int64_t l = 0; l < N; l++) { key[l] = depth[(size_t)l]; nkeys = std::max(nkeys, depth[(size_t)l] + 1); }
+    }
+    keys[combo] = key;
+  }
+  plan.nkeys = nkeys;
+  for (int combo = 0; combo < 8; combo++) {
+    const std::vector<int32_t>& k = keys[combo];
     std::vector<int32_t>& start = plan.waveStart[combo];
     start.assign(plan.nkeys + 1, 0);
-    for (int64_t l = 0; l < N; l++) {
-      const int L = c.hLevel[l];
-      const int sc = 1 << (Lmax - L);
-      const int nL = c.nx << L;
-      const int p[3] = {c.hLeafX[l], c.hLeafY[l], c.hLeafZ[l]};
-      int k = 0;
-      for (int a = 0; a < 3; a++) {
-        const int r = (combo >> a) & 1 ? nL - 1 - p[a] : p[a];
-        k += (2 * r + 1) * sc;
-      }
-      key[l] = k;
-      start[k + 1]++;
-    }
-    for (int k = 0; k < plan.nkeys; k++) start[k + 1] += start[k];
+    for (int64_t l = 0; l < N; l++) start[k[l] + 1]++;
+    for (int w = 0; w < plan.nkeys; w++) start[w + 1] += start[w];
     std::vector<int32_t> cursor(start.begin(), start.end() - 1);
     plan.sorted[combo].resize((size_t)N);
-    for (int64_t l = 0; l < N; l++) plan.sorted[combo][cursor[key[l]]++] = (int32_t)l;
+    for (int64_t l = 0; l < N; l++) plan.sorted[combo][cursor[k[l]]++] = (int32_t)l;
   }
 }
 
@@ -826,14 +908,19 @@ void amr_release(Context& c) {
 
 static int ensure_plan(Context& c, AmrState& S) {
   char buf[64];
-  snprintf(buf, sizeof(buf), "%p:%lld:%d", (void*)c.tree.child, (long long)c.nleaf, c.maxLevel);
+  snprintf(buf, sizeof(buf), "%p:%lld:%d:%d", (void*)c.tree.child, (long long)c.nleaf, c.maxLevel, c.tune.amrOrder);
   if (S.key == buf) return RTB200_OK;
   for (int k = 0; k < 8; k++) {
     cudaFree(S.plan.dSorted[k]); S.plan.dSorted[k] = nullptr;
     cudaFree(S.plan.dSlotOf[k]); S.plan.dSlotOf[k] = nullptr;
   }
-  build_waves(c, S.plan);
-  S.plan.balanced = grid_is_balanced(c);
+  // `balanced` from here on means "the wave order alone guarantees finished upstream leaves": true for the centre-sum
+  // waves of a 2:1-balanced grid and for the depth waves of any other grid; the per-leaf `done` flags and the deferred
+  // list remain for tuning "amr_order" = 0 (centre-sum waves whatever the grid: the round-1 scheme, for comparison)
+  const bool geomBalanced = grid_is_balanced(c);
+  const bool byDepth = c.tune.amrOrder > 0 || (c.tune.amrOrder < 0 && !geomBalanced);
+  build_waves(c, S.plan, byDepth);
+  S.plan.balanced = geomBalanced || byDepth;
   S.tablesKey.clear();
   {
     std::vector<int32_t> levelOff(c.maxLevel + 2, 0);
@@ -1216,7 +1303,7 @@ int diffuse_amr(Context& c, int nAngularLevel, const double* uvb, const std::vec
   int st = RTB200_OK;
   {
     char buf[96];
-    snprintf(buf, sizeof(buf), "%d:%lld:%d:%lld", T.perDir, (long long)N, batch, (long long)defCap);
+    snprintf(buf, sizeof(buf), "%d:%lld:%d:%lld:%d", T.perDir, (long long)N, batch, (long long)defCap, (int)S.plan.balanced);   // (J per group or per item)
     if (B.sizeKey != buf) {
       B.release();
       st = alloc_batch(B, T, N, batch, defCap, false, S.plan.balanced);  // (release() also forgets the cached neighbour tables)

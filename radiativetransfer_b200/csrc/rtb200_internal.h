@@ -69,6 +69,8 @@ struct Tuning {
                          // 6: 80 registers; 0 = 6 for small waves, 8 for large ones)
   int amrStream = -1;    // nested grids, 2:1 balanced: the whole sweep as one launch ordered by the records' sign epoch (1), one launch
                          // per wave (0), or by the size of the waves (-1)
+  int amrOrder = -1;     // nested grids, waves of the sweep: centre-sum key (0), depth in the dependency graph (1), or the key on
+                         // 2:1-balanced grids and the depth elsewhere (-1)
   int amrThin = 1;       // nested grids, FAST arithmetic: thin layers use the reference's operation sequence (1)
   int amrBatch = 0;      // directions per AMR batch (0 = as many as fit in half of the free memory)
   int lockstep = 1;      // 1: one launch per layer for all zones of a batch; 0: every slot an independent stream

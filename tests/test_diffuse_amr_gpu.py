@@ -136,8 +136,7 @@ def test_amr_streamed_sweep_equals_wave_launches_bit_for_bit(rt, engine, uvbg, n
     engine.set_tuning(amr_stream=1)
     for rep in range(4):
         J, ns = engine.diffuse(uvb, uvbg["beta"])
-        if name != "two-level-box":      # (its level-2 box touches level-0 cells: not 2:1 balanced, per-wave launches)
-            assert engine.last_stats()["launches"] < min(waves, 12), "the streamed path did not run"
+        assert engine.last_stats()["launches"] < min(waves, 12), "the streamed path did not run"
         assert ns == nw and np.array_equal(J, Jw), rep
     engine.set_tuning(amr_stream=0)
     assert np.array_equal(engine.diffuse(uvb, uvbg["beta"])[0], Jw)
@@ -158,6 +157,62 @@ def test_amr_streamed_sweep_equals_wave_launches_bit_for_bit(rt, engine, uvbg, n
     b, _ = engine.diffuse(uvb, uvbg["beta"], rays=rays)
     assert np.array_equal(a, b)
     engine.set_tuning(amr_stream=1)
+
+
+@pytest.mark.parametrize("name", sorted(GRIDS))
+@pytest.mark.parametrize("mode", ["faithful", "fast"])
+def test_amr_wave_order_by_depth_equals_flag_guarded_sweep_bit_for_bit(rt, engine, uvbg, name, mode):
+    """Grids that violate the 2:1 balance get their waves from the depth of every leaf in the dependency graph (one
+    pass in Morton order) instead of the centre-sum key, after which the wave order alone guarantees finished upstream
+    leaves: no `done` flags, no deferred list, and the one-launch streamed path applies.  Same arithmetic and summation
+    order as the flag-guarded sweep on centre-sum waves (tuning amr_order = 0): identical bits on every grid"""
+    g = GRIDS[name]
+    engine.set_math(rt.MATH_FAITHFUL if mode == "faithful" else rt.MATH_FAST)
+    _set(engine, g)
+    uvb = uvbg["uvb"] * 1e-3
+    engine.set_tuning(amr_order=0, amr_stream=0)
+    ref, nref = engine.diffuse(uvb, uvbg["beta"])
+    for order, stream in ((1, 0), (1, 1), (-1, -1), (-1, 1)):
+        engine.set_tuning(amr_order=order, amr_stream=stream)
+        for rep in range(2):
+            J, ns = engine.diffuse(uvb, uvbg["beta"])
+            assert ns == nref and np.array_equal(J, ref), (order, stream, rep)
+        if stream == 1:
+            assert engine.last_stats()["launches"] < 12, "the streamed path did not run"
+    rays = np.arange(61, 140, dtype=np.int32)
+    a, _ = engine.diffuse(uvb, uvbg["beta"], rays=rays)
+    engine.set_tuning(amr_order=0, amr_stream=0)
+    b, _ = engine.diffuse(uvb, uvbg["beta"], rays=rays)
+    assert np.array_equal(a, b)
+    engine.set_tuning(amr_order=-1, amr_stream=-1)
+
+
+def test_amr_strongly_unbalanced_grid_vs_oracle(rt, engine, oracle, uvbg):
+    """a box refined three levels at once inside level-0 cells (level 3 next to level 0 on every face of the box):
+    waves by dependency depth, one streamed launch; against the oracle's ray range and against the flag-guarded
+    scheme of round 1, which needed a deferred list (and overflowed it at 64^3: status 14)"""
+    g = W.nested_grid(16, 3, W.central_box_refine(0.375, 0.625, levels=3), seed=8)
+    assert g["level"].max() == 3 and not np.any((g["level"] == 1) | (g["level"] == 2))
+    _set(engine, g)
+    uvb = uvbg["uvb"] * 1e-3
+    rays = np.array([3, 40, 77, 101, 150, 188], dtype=np.int32)
+    og = oracle.OracleGrid(g["nx"], g["level"], g["HI"], g["HeI"], g["HeII"], box_size=g["box_size"])
+    Jo = np.zeros((3, g["level"].size)); nso = 0
+    for r in rays:
+        o = og.diffuse(uvb, uvbg["beta"], ray_begin=int(r), ray_end=int(r) + 1)
+        assert o["status"] == 0
+        Jo += o["J"]; nso += o["nseg"]
+    for mode in (rt.MATH_FAITHFUL, rt.MATH_FAST):
+        engine.set_math(mode)
+        engine.set_tuning(amr_order=-1, amr_stream=-1)
+        J, ns = engine.diffuse(uvb, uvbg["beta"], rays=rays)
+        assert engine.last_stats()["launches"] < 12
+        assert ns == nso and rel_err(J, Jo) < (TOL if mode == rt.MATH_FAITHFUL else 1e-8)
+        full, _ = engine.diffuse(uvb, uvbg["beta"])
+        engine.set_tuning(amr_order=0, amr_stream=0)
+        old, _ = engine.diffuse(uvb, uvbg["beta"])
+        assert np.array_equal(full, old)
+    engine.set_tuning(amr_order=-1, amr_stream=-1)
 
 
 @pytest.mark.parametrize("name,lo,hi", [("unbalanced-corner", 37, 59), ("disc-3-levels", 100, 101),
