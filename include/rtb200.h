@@ -291,6 +291,10 @@ int rtb200_patterns(int nAngularLevel, int64_t iray, int nx, double* out);
 /* upstream leaf of every leaf for one direction, [3][nleaf] = xy, yz, xz; -1 boundary, -2 ray inactive
  * (transportRoutinesModule.f90:264-418) */
 int rtb200_neighbours(rtb200_ctx* ctx, int nAngularLevel, int64_t iray, int32_t* nb);
+/* wave of every leaf in the nested-grid sweep order of that direction, [nleaf], and the number of waves: every upstream
+ * leaf rtb200_neighbours reports must lie in an earlier wave (centre-sum key on 2:1-balanced grids, dependency depth
+ * elsewhere; set_tuning "amr_order") -- the property tests/test_diffuse_amr_gpu.py checks at sizes no oracle run reaches */
+int rtb200_debug_waves(rtb200_ctx* ctx, int nAngularLevel, int64_t iray, int32_t* waveOfLeaf, int32_t* nwaves);
 
 /* exp / log of csrc/portable_math.h evaluated on the device for n host values (bit-identity with a host build of the
  * same header is what makes the FAITHFUL point-source deposits comparable bit for bit, tests/test_portable_math.py) */

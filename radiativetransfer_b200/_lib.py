@@ -62,6 +62,7 @@ SIGNATURES = {
                                    C.POINTER(C.c_double)]),
     "rtb200_patterns": (C.c_int, [C.c_int, C.c_int64, C.c_int, P]),
     "rtb200_neighbours": (C.c_int, [P, C.c_int, C.c_int64, P]),
+    "rtb200_debug_waves": (C.c_int, [P, C.c_int, C.c_int64, P, P]),
     "rtb200_debug_portable_math": (C.c_int, [P, C.c_int64, P, P, P]),
     "rtb200_debug_fast_exp": (C.c_int, [P, C.c_int64, P, P, P]),
     "rtb200_last_stats": (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64),

@@ -625,6 +625,16 @@ int rtb200_neighbours(rtb200_ctx* h, int nAngularLevel, int64_t iray, int32_t* n
   return amr_neighbours(c, d, nb);
 }
 
+int rtb200_debug_waves(rtb200_ctx* h, int nAngularLevel, int64_t iray, int32_t* waveOfLeaf, int32_t* nwaves) {
+  if (!h || !waveOfLeaf) return RTB200_ERR_ARG;
+  Context& c = h->m ? multi_primary(h->m) : h->c;
+  if (c.nleaf == 0) return RTB200_ERR_ARG;
+  Direction d = classify_direction(nAngularLevel, iray);
+  if (d.status) return d.status;
+  RTB_CUDA(cudaSetDevice(c.device));
+  return amr_waves(c, d, waveOfLeaf, nwaves);
+}
+
 int rtb200_debug_portable_math(rtb200_ctx* h, int64_t n, const double* x, double* expOut, double* logOut) {
   if (!h || n < 0 || !x || !expOut || !logOut) return RTB200_ERR_ARG;
   if (n == 0) return RTB200_OK;

@@ -1412,4 +1412,19 @@ int amr_neighbours(Context& c, const Direction& d, int32_t* nbHost) {
   return RTB200_OK;
 }
 
+// debugging export: the wave of every leaf in the sweep order of one direction (its reflection combination)
+int amr_waves(Context& c, const Direction& d, int32_t* waveOfLeaf, int32_t* nwaves) {
+  AmrState& S = *state_of(c);
+  if (int st = ensure_plan(c, S)) return st;
+  const ZoneMap m = zone_map(d.izone);
+  int combo = 0;
+  for (int cc = 0; cc < 3; cc++)
+    if (m.refl[cc]) combo |= 1 << cc;
+  const std::vector<int32_t>& start = S.plan.waveStart[combo];
+  for (int w = 0; w < S.plan.nkeys; w++)
+    for (int32_t q = start[w]; q < start[w + 1]; q++) waveOfLeaf[S.plan.sorted[combo][(size_t)q]] = w;
+  if (nwaves) *nwaves = S.plan.nkeys;
+  return RTB200_OK;
+}
+
 }  // namespace rtb

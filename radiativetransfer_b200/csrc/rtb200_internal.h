@@ -221,6 +221,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
 int diffuse_amr(Context& c, int nAngularLevel, const double* uvb, const std::vector<Direction>& dirs,
                 double* dJout, cudaStream_t s, int64_t* nseg);
 int amr_neighbours(Context& c, const Direction& d, int32_t* nbHost);
+int amr_waves(Context& c, const Direction& d, int32_t* waveOfLeaf, int32_t* nwaves);
 void amr_release(Context& c);
 void point_release(Context& c);
 int launch_diffuse_rates(Context& c, const double* J, const double* ksi24, const double* ksi25, const double* ksi26,
