@@ -36,6 +36,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <thread>
 
 #include "rtb200_internal.h"
 #include "segment_math.cuh"
@@ -726,12 +727,11 @@ static void build_waves(Context& c, AmrPlan& plan, bool byDepth) {
   const int64_t N = c.nleaf;
   const int span = (c.nx << Lmax) * 2;  // centre coordinate range per axis
   const int fine = c.nx << Lmax;        // finest cells per axis
-  std::vector<int32_t> key((size_t)N);
-  std::vector<int32_t> depth, cand, order;
-  std::vector<uint64_t> morton;
-  int nkeys = byDepth ? 0 : 3 * span + 1;
   std::vector<std::vector<int32_t>> keys(8);
-  for (int combo = 0; combo < 8; combo++) {
+  int maxKey[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto one_combo = [&](int combo) {
+    std::vector<int32_t>& key = keys[combo];
+    key.resize((size_t)N);
     if (!byDepth) {
       for (int64_t l = 0; l < N; l++) {
         const int L = c.hLevel[l];
@@ -745,56 +745,70 @@ static void build_waves(Context& c, AmrPlan& plan, bool byDepth) {
         }
         key[l] = k;
       }
-    } else {
-      // reflected low corner at the finest level, Morton code of it
-      morton.resize((size_t)N); order.resize((size_t)N);
-      auto rlo = [&](int64_t l, int (&r)[3], int& sz) {
-        const int L = c.hLevel[l];
-        sz = 1 << (Lmax - L);
-        const int p[3] = {c.hLeafX[l] * sz, c.hLeafY[l] * sz, c.hLeafZ[l] * sz};
-        for (int a = 0; a < 3; a++) r[a] = (combo >> a) & 1 ? fine - sz - p[a] : p[a];
-      };
-      for (int64_t l = 0; l < N; l++) {
-        int r[3], sz;
-        rlo(l, r, sz);
-        uint64_t m = 0;
-        for (int b = 0; b < 21; b++)
-          m |= ((uint64_t)((r[0] >> b) & 1) << (3 * b + 2)) | ((uint64_t)((r[1] >> b) & 1) << (3 * b + 1)) |
-               ((uint64_t)((r[2] >> b) & 1) << (3 * b));
-        morton[(size_t)l] = m;
-        order[(size_t)l] = (int32_t)l;
-      }
-      std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return morton[(size_t)x] < morton[(size_t)y]; });
-      depth.assign((size_t)N, 0); cand.assign((size_t)N, 0);
-      auto physical = [&](const int (&r)[3], int (&p)[3]) {   // reflected finest cell -> physical finest cell
-        for (int a = 0; a < 3; a++) p[a] = (combo >> a) & 1 ? fine - 1 - r[a] : r[a];
-      };
-      for (int64_t i = 0; i < N; i++) {
-        const int32_t l = order[(size_t)i];
-        int r[3], sz;
-        rlo(l, r, sz);
-        int d = cand[(size_t)l];
-        for (int a = 0; a < 3; a++) {          // upstream: the leaf behind the low face, if it is not finer
-          if (r[a] == 0) continue;
-          int q[3] = {r[0], r[1], r[2]}, p[3];
-          q[a] = r[a] - 1;
-          physical(q, p);
-          const int32_t u = leaf_at_finest(c, p);
-          if (c.hLevel[u] <= c.hLevel[l]) d = std::max(d, depth[(size_t)u] + 1);
-        }
-        depth[(size_t)l] = d;
-        for (int a = 0; a < 3; a++) {          // downstream: a coarser leaf behind the high face learns about this one
-          if (r[a] + sz >= fine) continue;
-          int q[3] = {r[0], r[1], r[2]}, p[3];
-          q[a] = r[a] + sz;
-          physical(q, p);
-          const int32_t dn = leaf_at_finest(c, p);
-          if (c.hLevel[dn] < c.hLevel[l]) cand[(size_t)dn] = std::max(cand[(size_t)dn], d + 1);
-        }
-      }
-      for (int64_t l = 0; l < N; l++) { key[l] = depth[(size_t)l]; nkeys = std::max(nkeys, depth[(size_t)l] + 1); }
+      return;
     }
-    keys[combo] = key;
+    // reflected low corner at the finest level, Morton code of it
+    std::vector<uint64_t> morton((size_t)N);
+    std::vector<int32_t> order((size_t)N), cand((size_t)N, 0);
+    std::vector<int32_t>& depth = key;
+    auto rlo = [&](int64_t l, int (&r)[3], int& sz) {
+      const int L = c.hLevel[l];
+      sz = 1 << (Lmax - L);
+      const int p[3] = {c.hLeafX[l] * sz, c.hLeafY[l] * sz, c.hLeafZ[l] * sz};
+      for (int a = 0; a < 3; a++) r[a] = (combo >> a) & 1 ? fine - sz - p[a] : p[a];
+    };
+    for (int64_t l = 0; l < N; l++) {
+      int r[3], sz;
+      rlo(l, r, sz);
+      uint64_t m = 0;
+      for (int b = 0; b < 21; b++)
+        m |= ((uint64_t)((r[0] >> b) & 1) << (3 * b + 2)) | ((uint64_t)((r[1] >> b) & 1) << (3 * b + 1)) |
+             ((uint64_t)((r[2] >> b) & 1) << (3 * b));
+      morton[(size_t)l] = m;
+      order[(size_t)l] = (int32_t)l;
+    }
+    std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return morton[(size_t)x] < morton[(size_t)y]; });
+    auto physical = [&](const int (&r)[3], int (&p)[3]) {   // reflected finest cell -> physical finest cell
+      for (int a = 0; a < 3; a++) p[a] = (combo >> a) & 1 ? fine - 1 - r[a] : r[a];
+    };
+    int top = 0;
+    for (int64_t i = 0; i < N; i++) {
+      const int32_t l = order[(size_t)i];
+      int r[3], sz;
+      rlo(l, r, sz);
+      int d = cand[(size_t)l];
+      for (int a = 0; a < 3; a++) {          // upstream: the leaf behind the low face, if it is not finer
+        if (r[a] == 0) continue;
+        int q[3] = {r[0], r[1], r[2]}, p[3];
+        q[a] = r[a] - 1;
+        physical(q, p);
+        const int32_t u = leaf_at_finest(c, p);
+        if (c.hLevel[u] <= c.hLevel[l]) d = std::max(d, depth[(size_t)u] + 1);
+      }
+      depth[(size_t)l] = d;
+      top = std::max(top, d);
+      for (int a = 0; a < 3; a++) {          // downstream: a coarser leaf behind the high face learns about this one
+        if (r[a] + sz >= fine) continue;
+        int q[3] = {r[0], r[1], r[2]}, p[3];
+        q[a] = r[a] + sz;
+        physical(q, p);
+        const int32_t dn = leaf_at_finest(c, p);
+        if (c.hLevel[dn] < c.hLevel[l]) cand[(size_t)dn] = std::max(cand[(size_t)dn], d + 1);
+      }
+    }
+    maxKey[combo] = top;
+  };
+  if (byDepth && N > 100000) {   // the eight passes are independent: one host thread each
+    std::vector<std::thread> th;
+    for (int combo = 0; combo < 8; combo++) th.emplace_back(one_combo, combo);
+    for (auto& t : th) t.join();
+  } else {
+    for (int combo = 0; combo < 8; combo++) one_combo(combo);
+  }
+  int nkeys = 3 * span + 1;
+  if (byDepth) {
+    nkeys = 1;
+    for (int combo = 0; combo < 8; combo++) nkeys = std::max(nkeys, maxKey[combo] + 1);
   }
   plan.nkeys = nkeys;
   for (int combo = 0; combo < 8; combo++) {
