@@ -116,8 +116,7 @@ int rtb200_set_math(rtb200_ctx* ctx, int math_mode);
  *                  0 = by the number of blocks a launch has), "transpose_z" (z-major copy for
  *                  the zones sweeping along the contiguous axis, 1), "persistent" (1 = the whole sweep as ONE launch, tiles handed out by a counter and
  *                  ordered by per-tile progress words; bit-identical, measured no faster: 0 = per-layer launches is the default), "pdl" (programmatic dependent launch of layer
- *                  l+1 on layer l, also used by the nested-grid waves, 1), "march" (experimental persistent kernel, 0; its "march_debug" switches
- *                  exist only with RTB200_EXPERIMENTAL set in the environment), "l2_mb"
+ *                  l+1 on layer l, also used by the nested-grid waves, 1), "l2_mb"
  *   nested grids   "force_amr" (general octree path on a uniform grid), "amr_batch" (directions per batch, 0 = as many
  *                  as fit in memory), "amr_stream" (2:1-balanced grids: 1 = the whole sweep as one launch whose work items wait
  *                  for their upstream intensity records, 0 = one launch per wave, -1 = by the size of the waves, the default;

@@ -251,18 +251,12 @@ int set_tuning(Context& c, const char* key, double value) {
   else if (k == "slots") c.tune.slots = (int)value;
   else if (k == "graph") c.tune.useGraph = (int)value;
   else if (k == "l2_mb") c.tune.l2BudgetMB = value;
-  else if (k == "march") c.tune.march = (int)value;
   else if (k == "transpose_z") c.tune.transposeZ = (int)value;
   else if (k == "cells") c.tune.cells = (int)value;
   else if (k == "block_warps") c.tune.blockWarps = (int)value;
   else if (k == "persistent") c.tune.persistent = (int)value;
   else if (k == "pdl") c.tune.pdl = (int)value;
   else if (k == "dirs_per_task") c.tune.dirsPerTask = (int)value;
-  else if (k == "march_debug") {
-    // experiments only (mode 1 skips the neighbour polling and gives WRONG results): not reachable from product code
-    if (!getenv("RTB200_EXPERIMENTAL")) return RTB200_ERR_ARG;
-    c.tune.marchDebug = (int)value;
-  }
   else if (k == "portable_math") c.tune.portableMath = (int)value;
   else if (k == "point_batch") c.tune.pointBatch = (int)value;
   else if (k == "point_min_blocks") c.tune.pointMinBlocks = (int)value;

@@ -17,7 +17,7 @@
 //    ("slot"), so no atomics and a fixed summation order.  Final kernels sum the slot accumulators into J.
 //  * Zones that sweep along the contiguous axis of the leaf order read a z-major copy of kappa and accumulate in
 //    that layout (transpose_kappa_kernel / merge_transposed_kernel) so that their lanes stay coalesced.
-//  * sweep_march_kernel is an experimental persistent variant (plane tiles in shared memory), off by default.
+//  * sweep_persistent_kernel runs the whole layer loop in one launch (tiles ordered by progress words); off by default.
 
 #include <algorithm>
 #include <cmath>
@@ -655,188 +655,6 @@ __global__ void __launch_bounds__(256, MINB) sweep_persistent_kernel(const __gri
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Persistent layer-marching kernel
-//
-// The per-layer launches above stream every direction's top-exit plane through HBM twice per layer (read + write):
-// that plane traffic IS the sweep's HBM traffic (ncu: 925 MB per layer launch at 256^3).  Here a block keeps its
-// tile of the planes in shared memory and marches through all n layers itself: block = 8 rows x (31 cells + 1
-// recomputed halo cell), the same tile and the same per-cell arithmetic (direction_body) as sweep_cell_kernel.
-// What a tile needs from its upstream neighbours -- the previous layer's top-exit intensities of the cell column
-// left of it and of the cell row above it -- travels through an L2-resident ring of edge values in global memory,
-// guarded by one progress counter per block (release/acquire).  A block may run at most kRing-1 layers ahead of its
-// downstream neighbours (it checks their counters before it overwrites a ring slot), so all blocks of a task have to
-// be co-resident: the host sizes the batch from the occupancy query and launches cooperatively.
-// HBM traffic left: kappa (read once per zone task) and the J accumulator.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int kRing = 4;
-constexpr int kMaxMarchTasks = 16;
-
-struct MarchTask {
-  const LayerSeg* seg;  // [n][kMaxDirPerTask]
-  double* acc;          // slot accumulator [3][N]
-  double* ring;         // [kRing][ndir][3][(n+1)^2], filled with the boundary intensity (pads stay that way)
-  int32_t* prog;        // [gridDim.y][gridDim.x] layers completed
-  int32_t origin, si, sj, sk;
-  int32_t ndir, laneIsK, firstInSlot, pad;
-};
-struct MarchBatch {
-  MarchTask t[kMaxMarchTasks];
-};
-
-__device__ __forceinline__ int ld_acquire(const int32_t* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(int32_t* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-template <bool FAITHFUL_ALL, int EXPV, int MINB>
-__global__ void __launch_bounds__(256, MINB)
-sweep_march_kernel(const __grid_constant__ MarchBatch mb, const double* __restrict__ kappa, int N, int n, double u0,
-                   double u1, double u2, int32_t* __restrict__ err, int dbg) {
-  const MarchTask& T = mb.t[blockIdx.z];
-  extern __shared__ double smem[];
-  double* sT = smem;                // exp table (kExpTableSize entries)
-  double* sX = smem + kExpTableSize;           // plane tile [2][ndir][3][8][32]
-  if (threadIdx.y * 32 + threadIdx.x < kExpTableSize) sT[threadIdx.y * 32 + threadIdx.x] = kExpTable32[threadIdx.y * 32 + threadIdx.x];
-  const int ndir = T.ndir;
-  const int lane = threadIdx.x, row = threadIdx.y;
-  const int a = blockIdx.x * 31 - 1 + lane, b = blockIdx.y * 8 + row;
-  const bool rowActive = b < n;
-  const bool inRow = a < n;
-  const bool cell = rowActive && inRow && a >= 0;
-  const bool writer = cell && lane >= 1;
-  const bool halo = lane == 0;
-  const int laneIsK = T.laneIsK;
-  const int sA = laneIsK ? T.sk : T.sj, sB = laneIsK ? T.sj : T.sk;
-  const int np1 = n + 1, npl = np1 * np1;
-  const int pidx = (b + 1) * np1 + (inRow ? a + 1 : 0);
-  const int tileStride = 3 * 8 * 32;                    // doubles per direction in one tile buffer
-  const int bufStride = ndir * tileStride;
-  const int tpos = row * 32 + lane;
-  const double uvb[3] = {u0, u1, u2};
-  // edge duty: the last cell column / row of the tile is read by the block to the right / below
-  const bool pubCol = writer && lane == 31 && blockIdx.x + 1 < gridDim.x;
-  const bool pubRow = writer && row == 7 && blockIdx.y + 1 < gridDim.y;
-  // layer 0 reads "boundary intensity everywhere" (transportRoutinesModule.f90:594-597)
-  for (int q = 0; q < ndir; q++)
-#pragma unroll
-    for (int g = 0; g < 3; g++) sX[bufStride + q * tileStride + g * 256 + tpos] = uvb[g];   // buffer 1 = "layer -1"
-  int32_t* myProg = T.prog + blockIdx.y * gridDim.x + blockIdx.x;
-  // neighbour counters polled by lanes 0..5 of warp 0: 0..2 upstream, 3..5 downstream
-  const int32_t* pollPtr = nullptr;
-  if (row == 0 && lane < 6) {
-    const int dx = (lane == 0 || lane == 2) ? -1 : ((lane == 3 || lane == 5) ? 1 : 0);
-    const int dy = (lane == 1 || lane == 2) ? -1 : ((lane == 4 || lane == 5) ? 1 : 0);
-    const int bx = (int)blockIdx.x + dx, by = (int)blockIdx.y + dy;
-    if (bx >= 0 && bx < (int)gridDim.x && by >= 0 && by < (int)gridDim.y) pollPtr = T.prog + by * gridDim.x + bx;
-  }
-  int leaf = T.origin + a * sA + b * sB;
-  double kapN[3], kRN[3];
-#pragma unroll
-  for (int g = 0; g < 3; g++) {
-    const double* kg = kappa + (int64_t)g * N + leaf;
-    kapN[g] = cell ? __ldg(kg) : 0.;
-    kRN[g] = (cell && b > 0) ? __ldg(kg - sB) : 0.;
-  }
-  for (int i = 0; i < n; i++) {
-    if (pollPtr) {
-      // upstream: layer i-1 published (i layers done).  downstream: before ring slot i%kRing (layer i-kRing) is
-      // overwritten its readers must have completed layer i-kRing+1, i.e. i-kRing+2 layers
-      const int need = lane < 3 ? i : i - kRing + 2;
-      if (need > 0) {
-        unsigned spins = 0;
-        while (ld_acquire(pollPtr) < need) {
-          if (!(dbg & 2)) __nanosleep(64);
-          if (++spins > (1u << 24)) { atomicExch(err, RTB200_ERR_CUDA); break; }
-        }
-      }
-    }
-    __syncthreads();  // neighbours' edges of layer i-1 are visible; the tile buffer of layer i-1 is complete
-    const double* xin = sX + ((i + 1) & 1) * bufStride;   // tile of layer i-1
-    double* xout = sX + (i & 1) * bufStride;              // tile of layer i
-    const double* ringIn = T.ring + (int64_t)((i + kRing - 1) % kRing) * ndir * 3 * npl;
-    double* ringOut = T.ring + (int64_t)(i % kRing) * ndir * 3 * npl;
-    double kap[3], kapF[3], kR[3], old[3];
-#pragma unroll
-    for (int g = 0; g < 3; g++) {
-      kapF[g] = kapN[g]; kR[g] = kRN[g];
-      kap[g] = kapF[g] > 0. ? kapF[g] : kKappaFloor;
-    }
-    const double kmaxL = fmax(fmax(fmax(kap[0], kap[1]), fmax(kap[2], kR[0])), fmax(kR[1], kR[2]));
-    double* accp = T.acc + leaf;
-    if (i + 1 < n) {  // prefetch the next layer's opacities
-#pragma unroll
-      for (int g = 0; g < 3; g++) {
-        const double* kg = kappa + (int64_t)g * N + leaf + T.si;
-        kapN[g] = cell ? __ldg(kg) : 0.;
-        kRN[g] = (cell && b > 0) ? __ldg(kg - sB) : 0.;
-      }
-    }
-#pragma unroll
-    for (int g = 0; g < 3; g++) old[g] = (writer && !T.firstInSlot) ? accp[(int64_t)g * N] : 0.;
-    double acc[3] = {0., 0., 0.}, A[3] = {0., 0., 0.};
-    if (rowActive) {
-      for (int q = 0; q < ndir; q++) {
-        const LayerSeg* Pg = T.seg + (size_t)i * kMaxDirPerTask + q;
-        LayerSeg P;
-        P.d[0] = __ldg(&Pg->d[0]); P.d[1] = __ldg(&Pg->d[1]); P.d[2] = __ldg(&Pg->d[2]);
-        P.cs[0] = __ldg(&Pg->cs[0]); P.cs[1] = __ldg(&Pg->cs[1]); P.cs[2] = __ldg(&Pg->cs[2]);
-        P.dmax = __ldg(&Pg->dmax); P.w = __ldg(&Pg->w);
-        P.kind = __ldg(&Pg->kind); P.nseg = 0; P.thin = __ldg(&Pg->thin);
-        const int kind = P.kind;
-        const bool secL = (kind <= 2) == (laneIsK != 0);
-        const bool needUp = kind == 2 || kind == 4 || (kind != 0 && !secL);
-        double cur[3], upR[3] = {0., 0., 0.}, I[3];
-        // the halo lane owns no cell: its input is the left neighbour tile's edge value
-        if (halo && i > 0) {
-#pragma unroll
-          for (int g = 0; g < 3; g++) cur[g] = __ldcg(ringIn + ((int64_t)q * npl + pidx) * 3 + g);
-        } else {
-#pragma unroll
-          for (int g = 0; g < 3; g++) cur[g] = xin[q * tileStride + g * 256 + tpos];
-        }
-        if (needUp) {
-          if (i == 0) {
-#pragma unroll
-            for (int g = 0; g < 3; g++) upR[g] = uvb[g];
-          } else if (row == 0 || halo) {  // the cell above belongs to another tile (or is the pad row)
-#pragma unroll
-            for (int g = 0; g < 3; g++) upR[g] = __ldcg(ringIn + ((int64_t)q * npl + pidx - np1) * 3 + g);
-          } else {
-#pragma unroll
-            for (int g = 0; g < 3; g++) upR[g] = xin[q * tileStride + g * 256 + tpos - 32];
-          }
-        }
-        if (FAITHFUL_ALL || P.thin) direction_dispatch_faithful(P, secL, cur, upR, kapF, kR, I, acc);
-        else direction_dispatch_fast<EXPV>(P, secL, kmaxL, cur, upR, kap, kR, I, A, sT);
-#pragma unroll
-        for (int g = 0; g < 3; g++) xout[q * tileStride + g * 256 + tpos] = writer ? I[g] : cur[g];
-        if (pubCol || pubRow) {
-#pragma unroll
-          for (int g = 0; g < 3; g++) __stcg(ringOut + ((int64_t)q * npl + pidx) * 3 + g, I[g]);
-        }
-      }
-    }
-    if (writer) {
-#pragma unroll
-      for (int g = 0; g < 3; g++) {
-        if (!FAITHFUL_ALL) acc[g] = fma(A[g], kTwoM200 / kap[g], acc[g]);
-        accp[(int64_t)g * N] = T.firstInSlot ? acc[g] : __dadd_rn(old[g], acc[g]);
-      }
-    }
-    leaf += T.si;
-    __syncthreads();  // every edge value of layer i has been issued
-    if (row == 0 && lane == 0) {
-      __threadfence();
-      st_release(myProg, i + 1);
-    }
-  }
-}
-
 // z-major layout.  A zone whose sweep axis is the contiguous (z) axis of the leaf order has its lanes run along y:
 // every lane of a kappa load or accumulator store would touch its own 32-byte sector (measured: those 8 zones take 1.7x
 // the time of the others).  Such tasks read a z-major copy of kappa, index (z*n + x)*n + y, and write their accumulator
@@ -956,36 +774,6 @@ static LayerSeg make_layer_seg(const RayPattern& p, double cellSize, double weig
 }
 
 
-// ---- persistent march path: host side -------------------------------------------------------------------
-template <bool FA, int EXPV, int MINB>
-static int march_launch(Context& c, const MarchBatch& mb, dim3 grid, size_t smemBytes, int N, int n, const double* uvb,
-                        cudaStream_t st) {
-  auto kern = sweep_march_kernel<FA, EXPV, MINB>;
-  RTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(32, 8, 1);
-  cfg.dynamicSmemBytes = smemBytes;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeCooperative;  // all blocks co-resident, or the launch fails instead of hanging
-  at[0].val.cooperative = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  RTB_CUDA(cudaLaunchKernelEx(&cfg, kern, mb, (const double*)c.dKappa, N, n, uvb[0], uvb[1], uvb[2], c.dErr, c.tune.marchDebug));
-  return RTB200_OK;
-}
-
-template <bool FA, int EXPV, int MINB>
-static int march_capacity(Context& c, size_t smemBytes, int* blocks) {
-  auto kern = sweep_march_kernel<FA, EXPV, MINB>;
-  RTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-  int perSm = 0;
-  RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 256, smemBytes));
-  *blocks = perSm * c.smCount;
-  return RTB200_OK;
-}
-
 // `warps` = rows of the layer a block covers with one warp each (8, 4 or 2): small direction shards (multi-GPU ranks) put
 // only a few hundred 8-warp blocks on the device per layer, 1.5 "waves" of which cost as much as 2; smaller blocks
 // spread the same rows evenly over the SMs
@@ -1039,84 +827,6 @@ static cudaError_t launch_cells(int dense, int expv, bool faithful, bool pdl, di
 #undef RTB_LAUNCH
 }
 
-
-// Runs the whole sweep with the persistent kernel.  Returns -1 when the grid of one zone task does not fit
-// co-resident on the device (large n): the caller then uses the per-layer launches.
-static int run_march(Context& c, int n, const double* uvb, double* dJout, cudaStream_t s, bool faithful) {
-  const int64_t N = c.nleaf, npl = (int64_t)(n + 1) * (n + 1);
-  const int ntask = (int)c.uniTasks.size();
-  int maxNd = 1;
-  for (const auto& T : c.uniTasks) maxNd = std::max(maxNd, T.ndir);
-  const size_t smemBytes = (kExpTableSize + (size_t)2 * maxNd * 768) * sizeof(double);
-  const int expv = c.tune.expVariant;
-  int cap = 0;
-  // register budget: 2 blocks per SM (128 registers) unless the tile buffers allow 4 (64 registers)
-  const bool dense = !faithful && c.tune.minBlocks >= 2 && 4 * (smemBytes + 1024) <= 227 * 1024;
-  int st = faithful ? march_capacity<true, 0, 2>(c, smemBytes, &cap)
-                    : dense ? (expv == 1 ? march_capacity<false, 1, 4>(c, smemBytes, &cap) : march_capacity<false, 0, 4>(c, smemBytes, &cap))
-                            : (expv == 1 ? march_capacity<false, 1, 2>(c, smemBytes, &cap) : march_capacity<false, 0, 2>(c, smemBytes, &cap));
-  if (st) return st;
-  const int gx = (n + 30) / 31, gy = (n + 7) / 8;
-  const int perTask = gx * gy;
-  int B = std::min(std::min(cap / perTask, kMaxMarchTasks), ntask);
-  if (c.tune.slots > 0) B = std::min(B, c.tune.slots);
-  if (B < 1) return -1;
-  if (int e = ensure_buffer((void**)&c.dAcc, &c.accBytes, (size_t)B * 3 * N * sizeof(double))) return e;
-  const size_t ringPerTask = (size_t)kRing * maxNd * 3 * npl;
-  if (int e = ensure_buffer((void**)&c.dPlanes, &c.planeBytes, (size_t)B * ringPerTask * sizeof(double))) return e;
-  if (int e = ensure_buffer((void**)&c.dMarchProg, &c.marchProgBytes, (size_t)B * perTask * sizeof(int32_t))) return e;
-  const size_t segPerTask = (size_t)n * kMaxDirPerTask;
-  if (c.marchSegKey != c.uniPlanKey) {
-    if (int e = ensure_buffer((void**)&c.dMarchSeg, &c.marchSegBytes, (size_t)ntask * segPerTask * sizeof(LayerSeg))) return e;
-    for (int t = 0; t < ntask; t++)
-      RTB_CUDA(cudaMemcpyAsync((LayerSeg*)c.dMarchSeg + (size_t)t * segPerTask, c.uniTasks[t].seg.data(),
-                               segPerTask * sizeof(LayerSeg), cudaMemcpyHostToDevice, s));
-    RTB_CUDA(cudaStreamSynchronize(s));  // the host vectors may be rebuilt by the next plan
-    c.marchSegKey = c.uniPlanKey;
-  }
-  RTB_CUDA(cudaEventRecord(c.evSweep0, s));
-  {
-    const int64_t total = (int64_t)B * ringPerTask;
-    int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)c.smCount * 16);
-    fill_planes_kernel<<<blocks, 256, 0, s>>>(c.dPlanes, npl, total, uvb[0], uvb[1], uvb[2]);
-  }
-  int64_t launches = 1;
-  static thread_local MarchBatch mb;
-  for (int base = 0; base < ntask; base += B) {
-    const int nb = std::min(B, ntask - base);
-    RTB_CUDA(cudaMemsetAsync(c.dMarchProg, 0, (size_t)nb * perTask * sizeof(int32_t), s));
-    for (int z = 0; z < nb; z++) {
-      const UniTaskHost& T = c.uniTasks[base + z];
-      MarchTask& m = mb.t[z];
-      m.seg = (const LayerSeg*)c.dMarchSeg + (size_t)(base + z) * segPerTask;
-      m.acc = c.dAcc + (size_t)z * 3 * N;
-      m.ring = c.dPlanes + (size_t)z * ringPerTask;
-      m.prog = c.dMarchProg + (size_t)z * perTask;
-      m.origin = (int32_t)T.origin; m.si = (int32_t)T.si; m.sj = (int32_t)T.sj; m.sk = (int32_t)T.sk;
-      m.ndir = T.ndir; m.laneIsK = T.laneIsK; m.firstInSlot = base == 0; m.pad = 0;
-    }
-    dim3 grid(gx, gy, nb);
-    if (faithful) st = march_launch<true, 0, 2>(c, mb, grid, smemBytes, (int)N, n, uvb, s);
-    else if (dense) st = expv == 1 ? march_launch<false, 1, 4>(c, mb, grid, smemBytes, (int)N, n, uvb, s)
-                                   : march_launch<false, 0, 4>(c, mb, grid, smemBytes, (int)N, n, uvb, s);
-    else st = expv == 1 ? march_launch<false, 1, 2>(c, mb, grid, smemBytes, (int)N, n, uvb, s)
-                        : march_launch<false, 0, 2>(c, mb, grid, smemBytes, (int)N, n, uvb, s);
-    if (st) return st;
-    launches++;
-  }
-  RTB_CUDA(cudaEventRecord(c.evSweep1, s));
-  {
-    // tasks base+z with z >= ntask % B never ran in the last batch: every slot z < min(B, ntask) has been written
-    const int slotsUsed = std::min(B, ntask);
-    int blocks = std::min<int64_t>((3 * N + 255) / 256, (int64_t)c.smCount * 16);
-    merge_slots_kernel<<<blocks, 256, 0, s>>>(c.dAcc, slotsUsed, 3 * N, dJout);
-  }
-  RTB_CUDA(cudaGetLastError());
-  c.uniLaunches = launches;
-  c.lastSweepLaunches = launches;
-  c.lastLaunches = launches + 2 + (ntask + B - 1) / B;  // + compute_opacities + merge + the counter memsets
-  return RTB200_OK;
-}
 
 // Runs the sweep as one launch (see sweep_persistent_kernel).  Returns -1 when it does not apply.
 static int run_persistent(Context& c, int n, const double* uvb, double* dJout, cudaStream_t s, int ndir) {
@@ -1207,7 +917,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
   {
     char buf[128];
     snprintf(buf, sizeof(buf), "%d:%a:%d:%d:%d:%d:%d:%d:%d:", n, c.boxSize, nAngularLevel, c.tune.slots, c.tune.lockstep, c.tune.dirsPerTask,
-             c.tune.transposeZ, c.tune.march, c.tune.blockWarps);
+             c.tune.transposeZ, 0, c.tune.blockWarps);
     planKey = buf;
     for (const auto& d : dirs) { snprintf(buf, sizeof(buf), "%lld,", (long long)d.iray); planKey += buf; }
   }
@@ -1220,7 +930,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
     // count, so a shard with few zones (multi-GPU runs) fills the device better when its zones are cut into smaller
     // pieces: pick the piece size that minimises (waves of resident blocks) x (block time ~ directions + fixed part).
     int dpt = std::max(1, std::min(c.tune.dirsPerTask > 0 ? c.tune.dirsPerTask : kMaxDirPerTask, kMaxDirPerTask));
-    if (c.tune.dirsPerTask <= 0 && !c.tune.march) {
+    if (c.tune.dirsPerTask <= 0) {
       int perZone[25] = {0};
       for (int d = 0; d < ndir; d++) perZone[dirs[d].izone]++;
       const int64_t bpt = (int64_t)((n + 30) / 31) * ((n + 7) / 8);
@@ -1269,7 +979,6 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
           for (int i = 0; i < n; i++) {
             if (pat[i].status) return pat[i].status;
             LayerSeg L = make_layer_seg(pat[i], cellSize, weight);
-            if (c.tune.marchDebug & 4) L.thin = 0;  // timing experiments only
             T.seg[(size_t)i * kMaxDirPerTask + q] = L;
             nseg += (int64_t)L.nseg * nn;
           }
@@ -1300,7 +1009,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
       }
     }
     c.uniStdSlots = slots;
-    if (c.tune.transposeZ && c.tune.lockstep && !c.tune.march && ntask <= slots && n >= 32) {
+    if (c.tune.transposeZ && c.tune.lockstep && ntask <= slots && n >= 32) {
       // every task owns its slot: tasks sweeping along the contiguous axis switch to the z-major layout (see
       // transpose_kappa_kernel) and are moved behind the others so that their slots form one range
       std::stable_partition(c.uniTasks.begin(), c.uniTasks.end(), [](const UniTaskHost& T) { return T.si != 1 && T.si != -1; });
@@ -1340,11 +1049,6 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
     return RTB200_OK;
   }
 
-  if (c.tune.march) {
-    const int mst = run_march(c, n, uvb, dJout, s, c.mathMode == RTB200_MATH_FAITHFUL);
-    if (mst >= 0) return mst;
-  }
-  // the march path may have re-sized the shared scratch buffers for its own layout
   if (int st = ensure_buffer((void**)&c.dAcc, &c.accBytes, (size_t)c.uniSlots * 3 * N * sizeof(double))) return st;
   if (int st = ensure_buffer((void**)&c.dPlanes, &c.planeBytes, (size_t)2 * std::max(ndir, 1) * 3 * npl * sizeof(double))) return st;
   {
@@ -1352,7 +1056,7 @@ int diffuse_uniform(Context& c, int nAngularLevel, const double* uvb, const std:
     // 8-GPU run take 6.99-7.22 ms mean / 7.26-7.50 ms max against 7.03 / 7.31 ms with per-layer launches of one-cell
     // threads, and 4-, 2- and 1-GPU shards are 9-16% SLOWER (the layer tables come from shared memory instead of the
     // constant bank, 128 registers with spills, an L1 invalidation per tile), so per-layer launches stay the default
-    const bool fast = c.mathMode != RTB200_MATH_FAITHFUL && c.tune.expVariant == 1 && c.tune.lockstep && !c.tune.march;
+    const bool fast = c.mathMode != RTB200_MATH_FAITHFUL && c.tune.expVariant == 1 && c.tune.lockstep;
     const bool want = c.tune.persistent == 1 || (c.tune.persistent < 0 && ntask <= 6 && n >= 64);
     if (fast && want) {
       const int pst = run_persistent(c, n, uvb, dJout, s, ndir);

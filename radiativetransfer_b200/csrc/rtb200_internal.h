@@ -77,7 +77,6 @@ struct Tuning {
   int minBlocks = 2;     // 0: compiler's register choice (2 blocks per SM); 1: cap for 3 blocks; 2: cap for 4 blocks
   int expVariant = 1;    // exp(-tau) of the fast path: 0 = polynomial, 1 = 16-entry shared-memory table
   double l2BudgetMB = 96.0;
-  int march = 0;         // uniform sweep: 1 = persistent layer-marching kernel (experimental, slower: DESIGN.md)
   int pdl = 1;           // uniform sweep: programmatic dependent launch of layer l+1 on layer l (its prologue overlaps the tail)
   int persistent = 0;    // uniform sweep, FAST arithmetic: 1 = the whole sweep as one launch (sweep_persistent_kernel),
                          // -1 = for small direction shards only, 0 = per-layer launches (measured: not slower)
@@ -86,7 +85,6 @@ struct Tuning {
                          // sweep_cell2_kernel; 0 = 2 from n = 192 on, where it measured 1-2% faster, else 1: 6% faster at 128^3)
   int transposeZ = 1;    // uniform sweep: zones sweeping along the contiguous axis use a z-major copy of kappa / J
   int dirsPerTask = 0;   // directions of one zone swept together (0 = kMaxDirPerTask)
-  int marchDebug = 0;    // experiments only: 1 = skip the neighbour polling (wrong results), 2 = spin without nanosleep
   int portableMath = 1;  // point path, FAITHFUL mode: exp/log from portable_math.h (bit-identical on host and device)
   int pointDeposit = 2;  // point path: 0 = fp64 RED.ADD into the rate fields, 1 = atomic-free: (leaf, deposit) records,
                          // radix sort by (leaf, ray, segment), one thread per cell adds its run (deterministic order),
@@ -179,7 +177,7 @@ struct Context {
   void* dMarchSeg = nullptr;   // per-task layer tables of the persistent uniform sweep
   size_t marchSegBytes = 0;
   std::string marchSegKey;
-  int32_t* dMarchProg = nullptr;
+  int32_t* dMarchProg = nullptr;   // work counter + per-tile progress words of the persistent uniform sweep
   size_t marchProgBytes = 0;
   void* dAmrScratch = nullptr;
   size_t amrScratchBytes = 0;

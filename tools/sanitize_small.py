@@ -11,12 +11,10 @@ sp = W.synthetic_spectra()
 t = rt.Transport(device=0)
 g = W.uniform_grid(33, seed=1)
 t.set_grid(g["nx"], g["level"], g["HI"], g["HeI"], g["HeII"], g["rho"], g["abun2"], g["box_size"])
-for march in (0, 1):
-    for mode in (rt.MATH_FAST, rt.MATH_FAITHFUL):
-        t.set_math(mode); t.set_tuning(march=march)
-        J, nseg = t.diffuse(bg["uvb"], bg["beta"], rays=list(range(0, 192, 5)))
-        print("uniform", march, mode, nseg, float(J.sum()))
-t.set_tuning(march=0)
+for mode in (rt.MATH_FAST, rt.MATH_FAITHFUL):
+    t.set_math(mode)
+    J, nseg = t.diffuse(bg["uvb"], bg["beta"], rays=list(range(0, 192, 5)))
+    print("uniform", mode, nseg, float(J.sum()))
 t.set_math(rt.MATH_FAST)
 for kw in (dict(cells=1), dict(cells=2), dict(cells=2, block_warps=2), dict(persistent=1), dict(persistent=1, block_warps=8)):
     t.set_tuning(cells=0, block_warps=0, persistent=0); t.set_tuning(**kw)
