@@ -554,7 +554,9 @@ constexpr int kStreamDirs = 192;   // directions of a batch the streamed kernel 
 // SM, ncu profiles/r02k2_*: IPC 1.75, 1130 warp instructions per quarter, not by the latency of those loads.  Also
 // tried: register caps for 5 / 6 / 8 blocks per SM (8.15 / 8.15 / 8.65 ms at 64^3 + 3 levels), and completing the
 // partly written 32-byte sectors of the record rows of leaves with inactive lanes so that L2 evicts whole sectors
-// (8.56 against 8.37 ms: the extra stores cost more than the avoided fills).)
+// (8.56 against 8.37 ms: the extra stores cost more than the avoided fills); the pause between two polls of a missing
+// record, 40 ns to 3 us (8.13 ms +- 0.02 throughout, profiles/r02y_amr_stream_poll_interval_*: waiting warps are not what
+// limits the kernel); and issuing the first attempt at all three upstream records before examining any (8.22 ms).)
 template <bool FAITHFUL, int MINB>
 __global__ void __launch_bounds__(128, MINB) amr_stream_kernel(AmrParams P, StreamParams Q, int ndirs, int ngroups) {
   __shared__ double sT[kExpTableSize];
