@@ -68,7 +68,8 @@ int rtb200_destroy(rtb200_ctx* ctx);
  * Data path (csrc/multi.cu): slab H2D + NVLink all-gather of the species, direction / source shards on full grids,
  * reduce-scatter of the per-leaf sums (a peer-memory kernel of this library with the photo-rate epilogue fused, or
  * NCCL: set_tuning "multi_reduce" 1 / 0), slab D2H.  NCCL (libnccl.so.2) is loaded with dlopen when a group of more
- * than one device is created (RTB200_NCCL_LIB overrides the search path).  Results are bit-identical from run to run
+ * than one device is created (RTB200_NCCL_LIB overrides the search path).  RTB200_TIMING=1 in the environment makes rank 0
+ * print the host wall time of every phase of the host-buffer calls (slab copies, all-gather, sweep, reduce-scatter).  Results are bit-identical from run to run
  * and independent of multi_reduce only in mode 1 (fixed summation order rank 0, 1, ...). */
 int rtb200_comm_unique_id(char* id128);
 int rtb200_create_multi(int ngpus, const int* devices, rtb200_ctx** ctx);
