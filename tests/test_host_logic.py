@@ -121,3 +121,15 @@ def test_point_entry_points_reject_bad_arguments_without_a_device(build_product)
                                  None, None, None, C.byref(n)) == 12
     assert L.rtb200_point_tables(None, 0, None, None, None, 0.0, None, 1, 0.0, None) == 12
     assert b"idepth" in L.rtb200_status_string(11)
+
+
+def test_every_tuning_key_is_documented_in_the_header():
+    """rtb200_set_tuning keys accepted by the library (csrc/api.cu, csrc/multi.cu) = keys listed in include/rtb200.h"""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = "".join(open(os.path.join(root, "radiativetransfer_b200", "csrc", f)).read() for f in ("api.cu", "multi.cu"))
+    keys = sorted(set(re.findall(r'k == "([a-z0-9_]+)"', src)))
+    assert len(keys) > 20
+    hdr = open(os.path.join(root, "include", "rtb200.h")).read()
+    missing = [k for k in keys if f'"{k}"' not in hdr and not (k.startswith("zone_cost_") and f'"_{k[-1]}"' in hdr)]
+    assert not missing, missing
