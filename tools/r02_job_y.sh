@@ -1,13 +1,13 @@
 #!/bin/bash
-# why is the point workload slower as a `secondary` line than on its own?
+# 1-GPU job: bench lines of the nested-grid workloads with the final binary
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 mkdir -p gpurun_out
-timeout 600 python bench.py --workload "point-128^3-amr-100src" --no-secondary --no-cpu-baseline --steps 3 --warmup 5 > gpurun_out/r02y_pointA.json 2>/dev/null
-timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --secondary "point-128^3-amr-100src" > gpurun_out/r02y_pointB.json 2>/dev/null
-timeout 600 python bench.py --workload "diffuse-64^3-uniform-192dir" --steps 2 --warmup 3 --no-cpu-baseline --secondary "point-128^3-amr-100src" > gpurun_out/r02y_pointC.json 2>/dev/null
-python - <<'PY'
-import json
-d=json.loads(open("gpurun_out/r02y_pointA.json").read().strip().splitlines()[-1]); print("A standalone: resident %.2f e2e %.2f"%(d["ms_per_step"], d["e2e"]["ms_per_step"]))
-for f in ("B","C"):
-    d=json.loads(open("gpurun_out/r02y_point%s.json"%f).read().strip().splitlines()[-1]); s=d["secondary"]["point-128^3-amr-100src"]; print(f, "after", d["config"]["workload"], ": resident %.2f e2e %.2f"%(s["ms_per_step"], s["e2e_ms_per_step"]))
+for w in "diffuse-128^3-amr2-192dir" "iterate10-64^3-amr3-192dir"; do
+  f=gpurun_out/r02y_bench_n1_$(echo $w | tr '^' '_').json
+  timeout 600 python bench.py --workload "$w" --steps 5 --warmup 3 --no-secondary --cpu-seconds 6 > $f 2>/dev/null
+  python - "$f" <<'PY'
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); r=d["roofline"]
+print(d["config"]["workload"], "ms %.2f"%d["ms_per_step"], "value %.3g"%d["value"], "frac %.3f"%r["frac"], r["kernel"], "e2e %.2f"%d["e2e"]["ms_per_step"], d.get("parity",{}).get("ok"))
 PY
+done
